@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""Generate golden fixtures by executing the UNMODIFIED reference in place.
+
+Test infrastructure only.  Runs in the build container (needs /root/reference); the fixtures it
+writes (tests/golden/*.npz) are committed and are all the GPU box ever sees.
+
+How: `oracle/jax_shim` (a NumPy/SciPy stand-in for the jax==0.1.67 API surface) is put first on
+sys.path, then `/root/reference/kalmanjax` — so `from sde_gp import SDEGP` imports the reference's
+own sources, which then run on NumPy in fp64.  Each case replays exactly what
+`SDEGP.run()` does (`sde_gp.py:179-187`) minus the autodiff gradient: filter(store=True, sites)
+-> smoother(site update), for a few iterations, then `predict()` / `negative_log_predictive_density()`
+on held-out inputs.  Known-answer values printed in the reference's executed notebooks
+ are asserted here at their printed precision.
+
+usage:  python tests/golden/make_golden.py [case ...]
+"""
+import os
+import sys
+import time
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("KJX_REFERENCE", "/root/reference")
+sys.path.insert(0, os.path.join(REF, "kalmanjax"))
+sys.path.insert(0, os.path.join(ROOT, "oracle", "jax_shim"))
+
+import numpy as np  # noqa: E402
+import pandas as pd  # noqa: E402
+
+from sde_gp import SDEGP  # noqa: E402  (reference)
+import approximate_inference as approx_inf  # noqa: E402  (reference)
+import priors  # noqa: E402  (reference)
+import likelihoods  # noqa: E402  (reference)
+
+pi = 3.141592653589793
+DATA = os.path.join(REF, "data")
+
+
+# ----------------------------------------------------------------------------- data sets
+def data_regression(N=1000):
+    # notebooks/regression.py:16-29
+    def wiggly_time_series(x_):
+        noise_var = 0.15
+        return (np.cos(0.04 * x_ + 0.33 * pi) * np.sin(0.2 * x_) +
+                np.sqrt(noise_var) * np.random.normal(0, 1, x_.shape))
+    np.random.seed(12345)
+    x = np.random.permutation(np.linspace(-25.0, 150.0, num=N) + 0.5 * np.random.randn(N))
+    y = wiggly_time_series(x)
+    x_test = np.linspace(np.min(x) - 15.0, np.max(x) + 15.0, num=500)
+    y_test = wiggly_time_series(x_test)
+    return x, y, x_test[::10], y_test[::10]
+
+
+def data_classification(N=1000):
+    # notebooks/classification.py:17-27
+    np.random.seed(99)
+    x = 100 * np.random.rand(N)
+    f = lambda x_: 6 * np.sin(pi * x_ / 10.0) / (pi * x_ / 10.0 + 1)  # noqa: E731
+    y_ = f(x) + np.sqrt(0.05) * np.random.randn(x.shape[0])
+    y = np.sign(y_)
+    y[y == -1] = 0
+    x_test = np.linspace(np.min(x) - 5.0, np.max(x) + 5.0, num=500)
+    y_test = np.sign(f(x_test) + np.sqrt(0.05) * np.random.randn(x_test.shape[0]))
+    y_test[y_test == -1] = 0
+    return x, y, x_test[::10], y_test[::10]
+
+
+def data_coal_200():
+    # notebooks/log_gaussian_cox_process.py:17-23
+    disaster_timings = pd.read_csv(os.path.join(DATA, "coal.txt"), header=None).values[:, 0]
+    num_time_bins = 200
+    x = np.linspace(min(disaster_timings), max(disaster_timings), num_time_bins).T
+    y = np.histogram(disaster_timings, np.concatenate([[-1e10], x[:-1] + np.diff(x) / 2, [1e10]]))[0][:, None]
+    return x, y.astype(float)
+
+
+def data_coal_333():
+    # experiments/coal/binned.csv (t, count), used by experiments/coal/coal.py
+    D = np.loadtxt(os.path.join(REF, "kalmanjax", "experiments", "coal", "binned.csv"))
+    return D[:, 0], D[:, 1:2]
+
+
+def data_aircraft(n_keep=160):
+    # experiments/aircraft/aircraft.py:19-35 (daily bins), thinned to a small fixture
+    from datetime import date
+    acc = pd.read_csv(os.path.join(DATA, "aircraft_accidents.txt"), sep="-", header=None).values
+    xx = np.zeros([acc.shape[0], 1])
+    for j in range(acc.shape[0]):
+        xx[j] = date.toordinal(date(acc[j, 0], acc[j, 1], acc[j, 2])) + 366
+    x_min, x_max = np.floor(np.min(xx)), np.ceil(np.max(xx))
+    x = np.linspace(x_min, x_max, num=int((x_max - x_min) + 1))
+    x = np.concatenate([np.min(x) - np.linspace(61, 1, num=61), x])
+    y, _ = np.histogram(xx, np.concatenate([[-1e10], x[1:] - np.diff(x) / 2, [1e10]]))
+    rng = np.random.RandomState(123)
+    keep = np.sort(rng.permutation(2000)[:n_keep]) + 15000  # irregular gaps of a few days
+    return x[keep], y[keep].astype(float)[:, None]
+
+
+def data_banana():
+    # notebooks/2d_classification.py:18-21
+    inputs = np.loadtxt(os.path.join(DATA, "banana_X_train"), delimiter=",")
+    X = inputs[:, :1]
+    R = inputs[:, 1:]
+    Y = np.loadtxt(os.path.join(DATA, "banana_Y_train"))[:, None]
+    return X, Y, R
+
+
+# ----------------------------------------------------------------------------- the replay
+def replay(model, iters, keep_every=1, t_test=None, y_test=None, r_test=None):
+    """What SDEGP.run() does (sde_gp.py:163-188) minus the gradient, recorded step by step."""
+    out = {}
+    for it in range(iters):
+        params = [model.prior.hyp.copy() if not isinstance(model.prior.hyp, list) else list(model.prior.hyp),
+                  model.likelihood.hyp.copy()]
+        site_in = model.sites.site_params
+        nlml, (fm, fc, sites_f) = model.kalman_filter(model.y, model.dt, params, True, None, site_in, model.r)
+        model.sites.site_params = sites_f
+        sites_s, sm, sc = model.rauch_tung_striebel_smoother(params, fm, fc, model.dt, True, False, model.y,
+                                                            model.sites.site_params, model.r)
+        model.sites.site_params = sites_s
+        out["it%d_nlml" % it] = np.float64(nlml)
+        out["it%d_filter_mean" % it] = np.asarray(fm)[::keep_every]
+        out["it%d_filter_cov" % it] = np.asarray(fc)[::keep_every]
+        out["it%d_site_mean_filter" % it] = np.asarray(sites_f[0])
+        out["it%d_site_cov_filter" % it] = np.asarray(sites_f[1])
+        out["it%d_smoothed_mean" % it] = np.asarray(sm)
+        out["it%d_smoothed_cov" % it] = np.asarray(sc)
+        out["it%d_site_mean" % it] = np.asarray(sites_s[0])
+        out["it%d_site_cov" % it] = np.asarray(sites_s[1])
+    if t_test is not None:
+        pm, pv = model.predict(t=t_test, r=r_test)
+        out["predict_mean"], out["predict_var"] = np.asarray(pm), np.asarray(pv)
+        if y_test is not None:
+            out["nlpd"] = np.float64(model.negative_log_predictive_density(t=t_test, y=y_test, r=r_test))
+    out["keep_every"] = np.int64(keep_every)
+    return out
+
+
+def hyp_of(model):
+    from utils import softplus, softplus_list
+    ph = model.prior.hyp
+    if isinstance(ph, list):
+        theta = np.concatenate([np.atleast_1d(np.asarray(h, dtype=float)) for h in softplus_list(ph)])
+    else:
+        theta = np.atleast_1d(np.asarray(softplus(ph), dtype=float))
+    lh = np.atleast_1d(np.asarray(softplus(model.likelihood.hyp), dtype=float)) if np.size(model.likelihood.hyp) else np.zeros(0)
+    return theta, lh
+
+
+CASES = {}
+
+
+class poisson_slr_patch(object):
+    """Reference HEAD cannot run Poisson with the SLR family (SLEP/GHEP/UEP/GHKS/UKS/PL):
+    `Poisson.conditional_moments` (likelihoods.py:632) returns a [1,1,Q] covariance, so `S` in
+    `statistical_linear_regression_cubature` (likelihoods.py:229-231) becomes [1,1,1] and
+    `np.diag(np.diag(om_sig_om))` (approximate_inference.py:199) raises "diag input must be 1d or 2d".
+    For those cases only, this context manager swaps in the line the reference itself keeps commented
+    out one line above (likelihoods.py:631: `return self.link_fn(f), self.link_fn(f)`), which is the
+    evident scalar semantics.  Fixtures produced this way carry `reference_patched=1`."""
+    def __enter__(self):
+        self._orig = likelihoods.Poisson.conditional_moments
+        likelihoods.Poisson.conditional_moments = lambda self_, f, hyp=None: (self_.link_fn(f), self_.link_fn(f))
+        return self
+
+    def __exit__(self, *exc):
+        likelihoods.Poisson.conditional_moments = self._orig
+        return False
+
+
+class _nopatch(object):
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+def case(name):
+    def deco(fn):
+        CASES[name] = fn
+        return fn
+    return deco
+
+
+def finish(name, model, out, t, y, r=None, kat=None, extra=None):
+    theta, lh = hyp_of(model)
+    out.update(t=np.asarray(t, dtype=float), y=np.asarray(y, dtype=float), theta_prior=theta, theta_lik=lh)
+    if r is not None:
+        out["r"] = np.asarray(r, dtype=float)
+    if extra:
+        out.update(extra)
+    if kat is not None:
+        got = float(out["it0_nlml"])
+        assert abs(got - kat) < 0.0051, (name, got, kat)
+        out["kat_nlml_printed"] = np.float64(kat)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print("%-34s nlml it0 = %.10f%s" % (name, float(out["it0_nlml"]),
+                                         "" if kat is None else "   (notebook prints %.2f)" % kat))
+
+
+@case("k1_regression_m52_gauss_pep")
+def _():
+    x, y, xt, yt = data_regression()
+    m = SDEGP(prior=priors.Matern52(variance=1.0, lengthscale=5.0), likelihood=likelihoods.Gaussian(variance=0.5),
+              t=x, y=y, approx_inf=approx_inf.EP(power=0.5))
+    finish("k1_regression_m52_gauss_pep", m, replay(m, 2, t_test=xt, y_test=yt), x, y, kat=797.76,
+           extra=dict(t_test=xt, y_test=yt))
+
+
+@case("k2_coal200_m52_poisson_eks")
+def _():
+    x, y = data_coal_200()
+    m = SDEGP(prior=priors.Matern52(variance=1.0, lengthscale=1.0), likelihood=likelihoods.Poisson(),
+              t=x, y=y, approx_inf=approx_inf.EKS())
+    xt = np.linspace(x.min() - 2.0, x.max() + 2.0, 23)
+    finish("k2_coal200_m52_poisson_eks", m, replay(m, 3, t_test=xt), x, y, kat=295.62, extra=dict(t_test=xt))
+
+
+@case("k3_classif_m52_logit_pep_ut")
+def _():
+    x, y, xt, yt = data_classification()
+    m = SDEGP(prior=priors.Matern52(variance=1.0, lengthscale=5.0), likelihood=likelihoods.Bernoulli(link="logit"),
+              t=x, y=y, approx_inf=approx_inf.ExpectationPropagation(power=0.9, intmethod="UT"))
+    finish("k3_classif_m52_logit_pep_ut", m, replay(m, 2, t_test=xt, y_test=yt), x, y, kat=469.46,
+           extra=dict(t_test=xt, y_test=yt))
+
+
+def _is_slr(method):
+    return isinstance(method, approx_inf.StatisticallyLinearisedEP)
+
+
+def _coal333(name, prior_fn, method_fn, iters=3):
+    x, y = data_coal_333()
+    meth = method_fn()
+    m = SDEGP(prior=prior_fn(), likelihood=likelihoods.Poisson(), t=x, y=y, approx_inf=meth)
+    xt = x[::17] + 0.123
+    yt = y[::17]
+    with (poisson_slr_patch() if _is_slr(meth) else _nopatch()):
+        out = replay(m, iters, t_test=xt, y_test=yt)
+    finish(name, m, out, x, y, extra=dict(t_test=xt, y_test=yt, reference_patched=np.int64(_is_slr(meth))))
+
+
+M32 = lambda: priors.Matern32(variance=1.0, lengthscale=1.0)  # noqa: E731
+M52 = lambda: priors.Matern52(variance=1.0, lengthscale=1.0)  # noqa: E731
+
+for _name, _prior, _meth in [
+    ("c2_coal333_m32_poisson_pep_gh", M32, lambda: approx_inf.EP(power=0.5, intmethod="GH")),
+    ("coal333_m52_poisson_ep1_ut", M52, lambda: approx_inf.EP(power=1.0, intmethod="UT")),
+    ("coal333_m52_poisson_ep001_gh_damped", M52, lambda: approx_inf.EP(power=0.01, damping=0.5, intmethod="GH")),
+    ("coal333_m52_poisson_eep1", M52, lambda: approx_inf.EEP(power=1)),
+    ("coal333_m52_poisson_eep05_damped", M52, lambda: approx_inf.EEP(power=0.5, damping=0.7)),
+    ("coal333_m32_poisson_eks_damped", M32, lambda: approx_inf.EKS(damping=0.5)),
+    ("coal333_m52_poisson_ghep1", M52, lambda: approx_inf.GHEP(power=1)),
+    ("coal333_m52_poisson_ghep05_damped", M52, lambda: approx_inf.GHEP(power=0.5, damping=0.6)),
+    ("coal333_m52_poisson_ghks", M52, lambda: approx_inf.GHKS()),
+    ("coal333_m32_poisson_uep05", M32, lambda: approx_inf.UEP(power=0.5)),
+    ("coal333_m52_poisson_uks", M52, lambda: approx_inf.UKS()),
+    ("coal333_m52_poisson_vi_gh", M52, lambda: approx_inf.VI(intmethod="GH")),
+    ("coal333_m32_poisson_vi_ut_damped", M32, lambda: approx_inf.VI(intmethod="UT", damping=0.5)),
+]:
+    CASES[_name] = (lambda n=_name, p=_prior, mm=_meth: _coal333(n, p, mm))
+
+
+def _probit(name, method_fn, N=300, iters=3):
+    x, y, xt, yt = data_classification(N)
+    m = SDEGP(prior=priors.Matern52(variance=1.0, lengthscale=5.0), likelihood=likelihoods.Probit(),
+              t=x, y=y, approx_inf=method_fn())
+    finish(name, m, replay(m, iters, t_test=xt, y_test=yt), x, y, extra=dict(t_test=xt, y_test=yt))
+
+
+for _name, _meth in [
+    ("probit300_m52_ep1", lambda: approx_inf.EP(power=1.0)),
+    ("probit300_m52_pep05_gh", lambda: approx_inf.EP(power=0.5)),
+    ("probit300_m52_vi_gh", lambda: approx_inf.VI()),
+    ("probit300_m52_slep_ut", lambda: approx_inf.SLEP(intmethod="UT")),
+    ("probit300_m52_ghks_damped", lambda: approx_inf.GHKS(damping=0.5)),
+]:
+    CASES[_name] = (lambda n=_name, mm=_meth: _probit(n, mm))
+
+
+def _logit(name, method_fn, N=300, iters=3):
+    x, y, xt, yt = data_classification(N)
+    m = SDEGP(prior=priors.Matern32(variance=1.5, lengthscale=4.0), likelihood=likelihoods.Bernoulli(link="logit"),
+              t=x, y=y, approx_inf=method_fn())
+    finish(name, m, replay(m, iters, t_test=xt, y_test=yt), x, y, extra=dict(t_test=xt, y_test=yt))
+
+
+for _name, _meth in [
+    ("logit300_m32_eks", lambda: approx_inf.EKS()),
+    ("logit300_m32_eep1", lambda: approx_inf.EEP(power=1.0)),
+    ("logit300_m32_vi_gh", lambda: approx_inf.VI()),
+    ("logit300_m32_ghep1", lambda: approx_inf.GHEP(power=1)),
+]:
+    CASES[_name] = (lambda n=_name, mm=_meth: _logit(n, mm))
+
+
+def _aircraft(name, prior_fn, method_fn, iters=2, keep_every=8):
+    x, y = data_aircraft()
+    meth = method_fn()
+    m = SDEGP(prior=prior_fn(), likelihood=likelihoods.Poisson(), t=x, y=y, approx_inf=meth)
+    xt = x[5::20] + 0.5
+    yt = y[5::20]
+    with (poisson_slr_patch() if _is_slr(meth) else _nopatch()):
+        out = replay(m, iters, keep_every=keep_every, t_test=xt, y_test=yt)
+    finish(name, m, out, x, y, extra=dict(t_test=xt, y_test=yt, reference_patched=np.int64(_is_slr(meth))))
+
+
+def prior_aircraft_d59():
+    # experiments/aircraft/aircraft.py:62-66
+    return priors.Sum([priors.Matern52(variance=2., lengthscale=5.5e4),
+                       priors.QuasiPeriodicMatern32(variance=1., lengthscale_periodic=2., period=365.,
+                                                    lengthscale_matern=1.5e4),
+                       priors.QuasiPeriodicMatern32(variance=1., lengthscale_periodic=2., period=7.,
+                                                    lengthscale_matern=30 * 365.)])
+
+
+def prior_aircraft_d31():
+    return priors.Sum([priors.Matern52(variance=2., lengthscale=5.5e4),
+                       priors.QuasiPeriodicMatern32(variance=1., lengthscale_periodic=2., period=365.,
+                                                    lengthscale_matern=1.5e4)])
+
+
+for _name, _prior, _meth in [
+    ("c3_aircraft160_d59_poisson_ghep1", prior_aircraft_d59, lambda: approx_inf.GHEP(power=1)),
+    ("c3_aircraft160_d31_poisson_vi_gh", prior_aircraft_d31, lambda: approx_inf.VI(intmethod="GH")),
+    ("c3_aircraft160_d31_poisson_eks", prior_aircraft_d31, lambda: approx_inf.EKS()),
+]:
+    CASES[_name] = (lambda n=_name, p=_prior, mm=_meth: _aircraft(n, p, mm))
+
+
+def _banana(name, method_fn, kat=None, iters=2, n=None, keep_every=16):
+    X, Y, R = data_banana()
+    if n is not None:
+        X, Y, R = X[:n], Y[:n], R[:n]
+    prior = priors.SpatioTemporalMatern52(variance=0.3, lengthscale_time=0.3, lengthscale_space=0.3)
+    m = SDEGP(prior=prior, likelihood=likelihoods.Probit(), t=X, y=Y, r=R, approx_inf=method_fn())
+    out = replay(m, iters, keep_every=keep_every)
+    finish(name, m, out, X, Y, r=R, kat=kat, extra=dict(z=np.asarray(prior.z)))
+
+
+CASES["k5_banana400_st52_probit_pep05"] = lambda: _banana("k5_banana400_st52_probit_pep05",
+                                                          lambda: approx_inf.ExpectationPropagation(power=0.5),
+                                                          kat=178.81)
+CASES["c4_banana200_st52_probit_vi"] = lambda: _banana("c4_banana200_st52_probit_vi",
+                                                       lambda: approx_inf.VI(), n=200)
+
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or list(CASES)
+    for nm in names:
+        t0 = time.time()
+        CASES[nm]()
+        print("    (%.1f s)" % (time.time() - t0))
