@@ -1,0 +1,185 @@
+"""ORACLE (test infrastructure, not product): GP priors as LTI SDEs and their per-step discretisation.
+
+NumPy fp64 restatement of the parts of /root/reference/kalmanjax/priors.py (and kernels.py, utils.py)
+that the Kalman filter / RTS smoother touch: Pinf, H (measurement model) and the closed-form
+A(dt) = expm(F dt).  Hyperparameters are the already-transformed (positive) values.
+Only the priors named by BASELINE.json's configs are restated: Matern-3/2, Matern-5/2,
+QuasiPeriodicMatern32, Sum, SpatioTemporalMatern52.
+"""
+import numpy as np
+import scipy.linalg as sl
+
+
+class Matern32(object):
+    """priors.py:111-175."""
+    state_dim = 2
+
+    def __init__(self, variance=1.0, lengthscale=1.0):
+        self.hyp = np.array([variance, lengthscale], dtype=float)
+
+    def kernel_to_state_space(self):
+        var, ell = self.hyp
+        H = np.array([[1.0, 0.0]])
+        Pinf = np.array([[var, 0.0],
+                         [0.0, 3.0 * var / ell ** 2.0]])                     # :154-155
+        return H, Pinf
+
+    def measurement_model(self, r=None):
+        return np.array([[1.0, 0.0]])                                        # :160
+
+    def state_transition(self, dt):
+        lam = np.sqrt(3.0) / self.hyp[1]                                     # :172-174
+        return np.exp(-dt * lam) * (dt * np.array([[lam, 1.0], [-lam ** 2.0, -lam]]) + np.eye(2))
+
+
+class Matern52(object):
+    """priors.py:178-255."""
+    state_dim = 3
+
+    def __init__(self, variance=1.0, lengthscale=1.0):
+        self.hyp = np.array([variance, lengthscale], dtype=float)
+
+    def kernel_to_state_space(self):
+        var, ell = self.hyp
+        H = np.array([[1.0, 0.0, 0.0]])
+        kappa = 5.0 / 3.0 * var / ell ** 2.0                                 # :227
+        Pinf = np.array([[var, 0.0, -kappa],
+                         [0.0, kappa, 0.0],
+                         [-kappa, 0.0, 25.0 * var / ell ** 4.0]])            # :228-230
+        return H, Pinf
+
+    def measurement_model(self, r=None):
+        return np.array([[1.0, 0.0, 0.0]])                                   # :235
+
+    def state_transition(self, dt):
+        return matern52_transition(dt, self.hyp[1])
+
+
+def matern52_transition(dt, ell):
+    """priors.py:246-255 (also used by the spatio-temporal prior, priors.py:1171-1179)."""
+    lam = np.sqrt(5.0) / ell
+    dtlam = dt * lam
+    return np.exp(-dtlam) * (
+        dt * np.array([[lam * (0.5 * dtlam + 1.0), dtlam + 1.0, 0.5 * dt],
+                       [-0.5 * dtlam * lam ** 2, lam * (1.0 - dtlam), 1.0 - 0.5 * dtlam],
+                       [lam ** 3 * (0.5 * dtlam - 1.0), lam ** 2 * (dtlam - 3), lam * (0.5 * dtlam - 2.0)]])
+        + np.eye(3))
+
+
+def rotation_matrix(dt, omega):
+    """utils.py:253-265."""
+    return np.array([[np.cos(omega * dt), -np.sin(omega * dt)],
+                     [np.sin(omega * dt), np.cos(omega * dt)]])
+
+
+class QuasiPeriodicMatern32(object):
+    """priors.py:946-1084.  State is harmonic-major 4x4 blocks for A and Pinf, while H is
+    kron(H_m, H_p) = ones at indices 0,2,..,12 — reproduced exactly as written (SURVEY 8a trap ix)."""
+    order = 6
+    state_dim = 28
+
+    def __init__(self, variance=1.0, lengthscale_periodic=1.0, period=1.0, lengthscale_matern=1.0):
+        self.hyp = np.array([variance, lengthscale_periodic, period, lengthscale_matern], dtype=float)
+        K = np.meshgrid(np.arange(self.order + 1), np.arange(self.order + 1))[1]          # :962
+        factorial_mesh_K = np.array([[1.] * 7, [1.] * 7, [2.] * 7, [6.] * 7, [24.] * 7, [120.] * 7, [720.] * 7])
+        b = np.array([[1., 0., 0., 0., 0., 0., 0.],
+                      [0., 2., 0., 0., 0., 0., 0.],
+                      [2., 0., 2., 0., 0., 0., 0.],
+                      [0., 6., 0., 2., 0., 0., 0.],
+                      [6., 0., 8., 0., 2., 0., 0.],
+                      [0., 20., 0., 10., 0., 2., 0.],
+                      [20., 0., 30., 0., 12., 0., 2.]])                                   # :970-976
+        self.K = K
+        self.b_fmK_2K = b * (1. / factorial_mesh_K) * (2. ** -K)                          # :977
+
+    def q2(self):
+        ell_p = self.hyp[1]
+        a = self.b_fmK_2K * ell_p ** (-2. * self.K) * np.exp(-1. / ell_p ** 2.) * 1.      # :1001
+        return np.sum(a, axis=0)                                                          # :1002
+
+    def kernel_to_state_space(self):
+        var, ell_p, period, ell_m = self.hyp
+        q2 = self.q2()
+        Pinf_m = np.array([[var, 0.0],
+                           [0.0, 3.0 * var / ell_m ** 2.0]])                              # :1018-1019
+        Pinf = sl.block_diag(*[np.kron(Pinf_m, q2[j] * np.eye(2)) for j in range(self.order + 1)])  # :1026-1034
+        return self.measurement_model(), Pinf
+
+    def measurement_model(self, r=None):
+        H_p = np.kron(np.ones([1, self.order + 1]), np.array([1., 0.]))                   # :1039
+        H_m = np.array([[1.0, 0.0]])
+        return np.kron(H_m, H_p)                                                          # :1041
+
+    def state_transition(self, dt):
+        period, ell_m = self.hyp[2], self.hyp[3]
+        lam = np.sqrt(3.0) / ell_m                                                        # :1054
+        omega = 2 * np.pi / period
+        blocks = []
+        for j in range(self.order + 1):
+            R = rotation_matrix(dt, j * omega)                                            # :1078
+            blocks.append(np.block([[(1. + dt * lam) * R, dt * R],
+                                    [-dt * lam ** 2 * R, (1. - dt * lam) * R]]))          # :1079-1082
+        return np.exp(-dt * lam) * sl.block_diag(*blocks)                                 # :1066-1074
+
+
+class Sum(object):
+    """priors.py:1347-1414: block-diagonal stacking, H concatenated."""
+    def __init__(self, components):
+        self.components = components
+        self.state_dim = sum(c.state_dim for c in components)
+
+    def kernel_to_state_space(self):
+        parts = [c.kernel_to_state_space() for c in self.components]
+        return np.block([p[0] for p in parts]), sl.block_diag(*[p[1] for p in parts])
+
+    def measurement_model(self, r=None):
+        return np.block([c.measurement_model(r) for c in self.components])
+
+    def state_transition(self, dt):
+        return sl.block_diag(*[c.state_transition(dt) for c in self.components])
+
+
+def matern52_kernel(X, X2, lengthscale):
+    """kernels.py:29-36 + 90-93 with utils.py:626-654 (GPflow-style squared distance, clipped)."""
+    X, X2 = X / lengthscale, X2 / lengthscale
+    Xs, X2s = np.sum(np.square(X), axis=-1), np.sum(np.square(X2), axis=-1)
+    r2 = -2 * np.tensordot(X, X2, [[-1], [-1]]) + Xs.reshape(-1, 1) + X2s.reshape(1, -1)
+    r = np.sqrt(np.maximum(r2, 1e-36))
+    sqrt5 = np.sqrt(5.0)
+    return (1.0 + sqrt5 * r + 5.0 / 3.0 * np.square(r)) * np.exp(-sqrt5 * r)
+
+
+class SpatioTemporalMatern52(object):
+    """priors.py:1087-1181: M inducing points z, state = M copies of the Matern-5/2 temporal state."""
+    def __init__(self, variance=1.0, lengthscale_time=1.0, lengthscale_space=1.0, z=None, fixed_grid=False):
+        self.hyp = np.array([variance, lengthscale_time, lengthscale_space], dtype=float)
+        if z is None:
+            z = np.linspace(-3., 3., num=15)                                              # :1099
+        self.z = np.asarray(z, dtype=float).reshape(-1, 1)
+        self.M = self.z.shape[0]
+        self.state_dim = 3 * self.M
+        self.fixed_grid = fixed_grid
+
+    def kernel_to_state_space(self):
+        var, ell_time, ell_space = self.hyp
+        Kmm = matern52_kernel(self.z, self.z, ell_space)                                  # :1129
+        kappa = 5.0 / 3.0 * var / ell_time ** 2.0
+        Pinf_time = np.array([[var, 0.0, -kappa],
+                              [0.0, kappa, 0.0],
+                              [-kappa, 0.0, 25.0 * var / ell_time ** 4.0]])               # :1141-1144
+        return None, np.kron(Kmm, Pinf_time)                                              # :1145
+
+    def spatial_weights(self, r):
+        """Kx = Kxz Kzz^-1 (priors.py:1154-1159); r is one step's spatial location(s)."""
+        if self.fixed_grid:
+            return np.eye(self.M)
+        ell_space = self.hyp[2]
+        Kzz = matern52_kernel(self.z, self.z, ell_space)
+        Kxz = matern52_kernel(np.asarray(r, dtype=float).reshape(-1, 1), self.z, ell_space)
+        return sl.cho_solve(sl.cho_factor(Kzz), Kxz.T).T
+
+    def measurement_model(self, r):
+        return np.kron(self.spatial_weights(r), np.array([[1.0, 0.0, 0.0]]))              # :1160
+
+    def state_transition(self, dt):
+        return np.kron(np.eye(self.M), matern52_transition(dt, self.hyp[1]))              # :1180

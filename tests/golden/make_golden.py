@@ -147,7 +147,8 @@ def hyp_of(model):
     return theta, lh
 
 
-CASES = {}
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from golden_cases import CASES, KEEP_EVERY, build  # noqa: E402
 
 
 class poisson_slr_patch(object):
@@ -158,197 +159,81 @@ class poisson_slr_patch(object):
     For those cases only, this context manager swaps in the line the reference itself keeps commented
     out one line above (likelihoods.py:631: `return self.link_fn(f), self.link_fn(f)`), which is the
     evident scalar semantics.  Fixtures produced this way carry `reference_patched=1`."""
+    def __init__(self, active):
+        self.active = active
+
     def __enter__(self):
-        self._orig = likelihoods.Poisson.conditional_moments
-        likelihoods.Poisson.conditional_moments = lambda self_, f, hyp=None: (self_.link_fn(f), self_.link_fn(f))
+        if self.active:
+            self._orig = likelihoods.Poisson.conditional_moments
+            likelihoods.Poisson.conditional_moments = lambda self_, f, hyp=None: (self_.link_fn(f), self_.link_fn(f))
         return self
 
     def __exit__(self, *exc):
-        likelihoods.Poisson.conditional_moments = self._orig
+        if self.active:
+            likelihoods.Poisson.conditional_moments = self._orig
         return False
 
 
-class _nopatch(object):
-    def __enter__(self):
-        return self
+def load_data(name):
+    """-> t, y, r, t_test, y_test"""
+    if name == "regression":
+        x, y, xt, yt = data_regression()
+        return x, y, None, xt, yt
+    if name == "classification":
+        x, y, xt, yt = data_classification()
+        return x, y, None, xt, yt
+    if name == "classification300":
+        x, y, xt, yt = data_classification(300)
+        return x, y, None, xt, yt
+    if name == "coal200":
+        x, y = data_coal_200()
+        return x, y, None, np.linspace(x.min() - 2.0, x.max() + 2.0, 23), None
+    if name == "coal333":
+        x, y = data_coal_333()
+        return x, y, None, x[::17] + 0.123, y[::17]
+    if name == "aircraft160":
+        x, y = data_aircraft()
+        return x, y, None, x[5::20] + 0.5, y[5::20]
+    if name == "banana400":
+        X, Y, R = data_banana()
+        return X, Y, R, None, None
+    if name == "banana200":
+        X, Y, R = data_banana()
+        return X[:200], Y[:200], R[:200], None, None
+    raise KeyError(name)
 
-    def __exit__(self, *exc):
-        return False
 
-
-def case(name):
-    def deco(fn):
-        CASES[name] = fn
-        return fn
-    return deco
-
-
-def finish(name, model, out, t, y, r=None, kat=None, extra=None):
+def make(name):
+    data, prior_spec, lik_spec, (meth_name, meth_kw), iters, kat = CASES[name]
+    t, y, r, t_test, y_test = load_data(data)
+    prior = build(prior_spec, priors)
+    lik = build(lik_spec, likelihoods)
+    meth = getattr(approx_inf, meth_name)(**meth_kw)
+    patched = isinstance(lik, likelihoods.Poisson) and isinstance(meth, approx_inf.StatisticallyLinearisedEP)
+    model = SDEGP(prior=prior, likelihood=lik, t=t, y=y, r=r, approx_inf=meth)
+    with poisson_slr_patch(patched):
+        out = replay(model, iters, keep_every=KEEP_EVERY.get(data, 1), t_test=t_test, y_test=y_test)
     theta, lh = hyp_of(model)
-    out.update(t=np.asarray(t, dtype=float), y=np.asarray(y, dtype=float), theta_prior=theta, theta_lik=lh)
+    out.update(t=np.asarray(t, dtype=float), y=np.asarray(y, dtype=float), theta_prior=theta, theta_lik=lh,
+               reference_patched=np.int64(patched))
     if r is not None:
         out["r"] = np.asarray(r, dtype=float)
-    if extra:
-        out.update(extra)
+        out["z"] = np.asarray(prior.z)
+    if t_test is not None:
+        out["t_test"] = np.asarray(t_test, dtype=float)
+    if y_test is not None:
+        out["y_test"] = np.asarray(y_test, dtype=float)
     if kat is not None:
         got = float(out["it0_nlml"])
         assert abs(got - kat) < 0.0051, (name, got, kat)
         out["kat_nlml_printed"] = np.float64(kat)
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
-    print("%-34s nlml it0 = %.10f%s" % (name, float(out["it0_nlml"]),
+    print("%-38s nlml it0 = %.10f%s" % (name, float(out["it0_nlml"]),
                                          "" if kat is None else "   (notebook prints %.2f)" % kat))
 
 
-@case("k1_regression_m52_gauss_pep")
-def _():
-    x, y, xt, yt = data_regression()
-    m = SDEGP(prior=priors.Matern52(variance=1.0, lengthscale=5.0), likelihood=likelihoods.Gaussian(variance=0.5),
-              t=x, y=y, approx_inf=approx_inf.EP(power=0.5))
-    finish("k1_regression_m52_gauss_pep", m, replay(m, 2, t_test=xt, y_test=yt), x, y, kat=797.76,
-           extra=dict(t_test=xt, y_test=yt))
-
-
-@case("k2_coal200_m52_poisson_eks")
-def _():
-    x, y = data_coal_200()
-    m = SDEGP(prior=priors.Matern52(variance=1.0, lengthscale=1.0), likelihood=likelihoods.Poisson(),
-              t=x, y=y, approx_inf=approx_inf.EKS())
-    xt = np.linspace(x.min() - 2.0, x.max() + 2.0, 23)
-    finish("k2_coal200_m52_poisson_eks", m, replay(m, 3, t_test=xt), x, y, kat=295.62, extra=dict(t_test=xt))
-
-
-@case("k3_classif_m52_logit_pep_ut")
-def _():
-    x, y, xt, yt = data_classification()
-    m = SDEGP(prior=priors.Matern52(variance=1.0, lengthscale=5.0), likelihood=likelihoods.Bernoulli(link="logit"),
-              t=x, y=y, approx_inf=approx_inf.ExpectationPropagation(power=0.9, intmethod="UT"))
-    finish("k3_classif_m52_logit_pep_ut", m, replay(m, 2, t_test=xt, y_test=yt), x, y, kat=469.46,
-           extra=dict(t_test=xt, y_test=yt))
-
-
-def _is_slr(method):
-    return isinstance(method, approx_inf.StatisticallyLinearisedEP)
-
-
-def _coal333(name, prior_fn, method_fn, iters=3):
-    x, y = data_coal_333()
-    meth = method_fn()
-    m = SDEGP(prior=prior_fn(), likelihood=likelihoods.Poisson(), t=x, y=y, approx_inf=meth)
-    xt = x[::17] + 0.123
-    yt = y[::17]
-    with (poisson_slr_patch() if _is_slr(meth) else _nopatch()):
-        out = replay(m, iters, t_test=xt, y_test=yt)
-    finish(name, m, out, x, y, extra=dict(t_test=xt, y_test=yt, reference_patched=np.int64(_is_slr(meth))))
-
-
-M32 = lambda: priors.Matern32(variance=1.0, lengthscale=1.0)  # noqa: E731
-M52 = lambda: priors.Matern52(variance=1.0, lengthscale=1.0)  # noqa: E731
-
-for _name, _prior, _meth in [
-    ("c2_coal333_m32_poisson_pep_gh", M32, lambda: approx_inf.EP(power=0.5, intmethod="GH")),
-    ("coal333_m52_poisson_ep1_ut", M52, lambda: approx_inf.EP(power=1.0, intmethod="UT")),
-    ("coal333_m52_poisson_ep001_gh_damped", M52, lambda: approx_inf.EP(power=0.01, damping=0.5, intmethod="GH")),
-    ("coal333_m52_poisson_eep1", M52, lambda: approx_inf.EEP(power=1)),
-    ("coal333_m52_poisson_eep05_damped", M52, lambda: approx_inf.EEP(power=0.5, damping=0.7)),
-    ("coal333_m32_poisson_eks_damped", M32, lambda: approx_inf.EKS(damping=0.5)),
-    ("coal333_m52_poisson_ghep1", M52, lambda: approx_inf.GHEP(power=1)),
-    ("coal333_m52_poisson_ghep05_damped", M52, lambda: approx_inf.GHEP(power=0.5, damping=0.6)),
-    ("coal333_m52_poisson_ghks", M52, lambda: approx_inf.GHKS()),
-    ("coal333_m32_poisson_uep05", M32, lambda: approx_inf.UEP(power=0.5)),
-    ("coal333_m52_poisson_uks", M52, lambda: approx_inf.UKS()),
-    ("coal333_m52_poisson_vi_gh", M52, lambda: approx_inf.VI(intmethod="GH")),
-    ("coal333_m32_poisson_vi_ut_damped", M32, lambda: approx_inf.VI(intmethod="UT", damping=0.5)),
-]:
-    CASES[_name] = (lambda n=_name, p=_prior, mm=_meth: _coal333(n, p, mm))
-
-
-def _probit(name, method_fn, N=300, iters=3):
-    x, y, xt, yt = data_classification(N)
-    m = SDEGP(prior=priors.Matern52(variance=1.0, lengthscale=5.0), likelihood=likelihoods.Probit(),
-              t=x, y=y, approx_inf=method_fn())
-    finish(name, m, replay(m, iters, t_test=xt, y_test=yt), x, y, extra=dict(t_test=xt, y_test=yt))
-
-
-for _name, _meth in [
-    ("probit300_m52_ep1", lambda: approx_inf.EP(power=1.0)),
-    ("probit300_m52_pep05_gh", lambda: approx_inf.EP(power=0.5)),
-    ("probit300_m52_vi_gh", lambda: approx_inf.VI()),
-    ("probit300_m52_slep_ut", lambda: approx_inf.SLEP(intmethod="UT")),
-    ("probit300_m52_ghks_damped", lambda: approx_inf.GHKS(damping=0.5)),
-]:
-    CASES[_name] = (lambda n=_name, mm=_meth: _probit(n, mm))
-
-
-def _logit(name, method_fn, N=300, iters=3):
-    x, y, xt, yt = data_classification(N)
-    m = SDEGP(prior=priors.Matern32(variance=1.5, lengthscale=4.0), likelihood=likelihoods.Bernoulli(link="logit"),
-              t=x, y=y, approx_inf=method_fn())
-    finish(name, m, replay(m, iters, t_test=xt, y_test=yt), x, y, extra=dict(t_test=xt, y_test=yt))
-
-
-for _name, _meth in [
-    ("logit300_m32_eks", lambda: approx_inf.EKS()),
-    ("logit300_m32_eep1", lambda: approx_inf.EEP(power=1.0)),
-    ("logit300_m32_vi_gh", lambda: approx_inf.VI()),
-    ("logit300_m32_ghep1", lambda: approx_inf.GHEP(power=1)),
-]:
-    CASES[_name] = (lambda n=_name, mm=_meth: _logit(n, mm))
-
-
-def _aircraft(name, prior_fn, method_fn, iters=2, keep_every=8):
-    x, y = data_aircraft()
-    meth = method_fn()
-    m = SDEGP(prior=prior_fn(), likelihood=likelihoods.Poisson(), t=x, y=y, approx_inf=meth)
-    xt = x[5::20] + 0.5
-    yt = y[5::20]
-    with (poisson_slr_patch() if _is_slr(meth) else _nopatch()):
-        out = replay(m, iters, keep_every=keep_every, t_test=xt, y_test=yt)
-    finish(name, m, out, x, y, extra=dict(t_test=xt, y_test=yt, reference_patched=np.int64(_is_slr(meth))))
-
-
-def prior_aircraft_d59():
-    # experiments/aircraft/aircraft.py:62-66
-    return priors.Sum([priors.Matern52(variance=2., lengthscale=5.5e4),
-                       priors.QuasiPeriodicMatern32(variance=1., lengthscale_periodic=2., period=365.,
-                                                    lengthscale_matern=1.5e4),
-                       priors.QuasiPeriodicMatern32(variance=1., lengthscale_periodic=2., period=7.,
-                                                    lengthscale_matern=30 * 365.)])
-
-
-def prior_aircraft_d31():
-    return priors.Sum([priors.Matern52(variance=2., lengthscale=5.5e4),
-                       priors.QuasiPeriodicMatern32(variance=1., lengthscale_periodic=2., period=365.,
-                                                    lengthscale_matern=1.5e4)])
-
-
-for _name, _prior, _meth in [
-    ("c3_aircraft160_d59_poisson_ghep1", prior_aircraft_d59, lambda: approx_inf.GHEP(power=1)),
-    ("c3_aircraft160_d31_poisson_vi_gh", prior_aircraft_d31, lambda: approx_inf.VI(intmethod="GH")),
-    ("c3_aircraft160_d31_poisson_eks", prior_aircraft_d31, lambda: approx_inf.EKS()),
-]:
-    CASES[_name] = (lambda n=_name, p=_prior, mm=_meth: _aircraft(n, p, mm))
-
-
-def _banana(name, method_fn, kat=None, iters=2, n=None, keep_every=16):
-    X, Y, R = data_banana()
-    if n is not None:
-        X, Y, R = X[:n], Y[:n], R[:n]
-    prior = priors.SpatioTemporalMatern52(variance=0.3, lengthscale_time=0.3, lengthscale_space=0.3)
-    m = SDEGP(prior=prior, likelihood=likelihoods.Probit(), t=X, y=Y, r=R, approx_inf=method_fn())
-    out = replay(m, iters, keep_every=keep_every)
-    finish(name, m, out, X, Y, r=R, kat=kat, extra=dict(z=np.asarray(prior.z)))
-
-
-CASES["k5_banana400_st52_probit_pep05"] = lambda: _banana("k5_banana400_st52_probit_pep05",
-                                                          lambda: approx_inf.ExpectationPropagation(power=0.5),
-                                                          kat=178.81)
-CASES["c4_banana200_st52_probit_vi"] = lambda: _banana("c4_banana200_st52_probit_vi",
-                                                       lambda: approx_inf.VI(), n=200)
-
-
 if __name__ == "__main__":
-    names = sys.argv[1:] or list(CASES)
-    for nm in names:
+    for nm in (sys.argv[1:] or list(CASES)):
         t0 = time.time()
-        CASES[nm]()
+        make(nm)
         print("    (%.1f s)" % (time.time() - t0))

@@ -1,0 +1,63 @@
+"""Table of golden cases: name -> model specification in reference vocabulary.
+
+The same table drives (a) tests/golden/make_golden.py, which instantiates the *reference's* classes
+of these names under the jax shim, (b) the oracle builders and (c) the product (CUDA) builders in the
+tests — the class names and keyword arguments are identical in all three.
+A prior spec is (class name, kwargs) or ("Sum", [spec, ...]).
+"""
+
+AIR_M52 = ("Matern52", dict(variance=2., lengthscale=5.5e4))
+AIR_QP365 = ("QuasiPeriodicMatern32", dict(variance=1., lengthscale_periodic=2., period=365., lengthscale_matern=1.5e4))
+AIR_QP7 = ("QuasiPeriodicMatern32", dict(variance=1., lengthscale_periodic=2., period=7., lengthscale_matern=30 * 365.))
+M32_11 = ("Matern32", dict(variance=1.0, lengthscale=1.0))
+M52_11 = ("Matern52", dict(variance=1.0, lengthscale=1.0))
+M52_15 = ("Matern52", dict(variance=1.0, lengthscale=5.0))
+M32_154 = ("Matern32", dict(variance=1.5, lengthscale=4.0))
+ST52 = ("SpatioTemporalMatern52", dict(variance=0.3, lengthscale_time=0.3, lengthscale_space=0.3))
+POISSON = ("Poisson", dict())
+PROBIT = ("Probit", dict())
+LOGIT = ("Bernoulli", dict(link="logit"))
+
+# name: (data set, prior, likelihood, (method class, kwargs), iterations, kat)
+CASES = {
+    "k1_regression_m52_gauss_pep": ("regression", M52_15, ("Gaussian", dict(variance=0.5)), ("EP", dict(power=0.5)), 2, 797.76),
+    "k2_coal200_m52_poisson_eks": ("coal200", M52_11, POISSON, ("EKS", dict()), 3, 295.62),
+    "k3_classif_m52_logit_pep_ut": ("classification", M52_15, LOGIT, ("ExpectationPropagation", dict(power=0.9, intmethod="UT")), 2, 469.46),
+    "c2_coal333_m32_poisson_pep_gh": ("coal333", M32_11, POISSON, ("EP", dict(power=0.5, intmethod="GH")), 3, None),
+    "coal333_m52_poisson_ep1_ut": ("coal333", M52_11, POISSON, ("EP", dict(power=1.0, intmethod="UT")), 3, None),
+    "coal333_m52_poisson_ep001_gh_damped": ("coal333", M52_11, POISSON, ("EP", dict(power=0.01, damping=0.5, intmethod="GH")), 3, None),
+    "coal333_m52_poisson_eep1": ("coal333", M52_11, POISSON, ("EEP", dict(power=1)), 3, None),
+    "coal333_m52_poisson_eep05_damped": ("coal333", M52_11, POISSON, ("EEP", dict(power=0.5, damping=0.7)), 3, None),
+    "coal333_m32_poisson_eks_damped": ("coal333", M32_11, POISSON, ("EKS", dict(damping=0.5)), 3, None),
+    "coal333_m52_poisson_ghep1": ("coal333", M52_11, POISSON, ("GHEP", dict(power=1)), 3, None),
+    "coal333_m52_poisson_ghep05_damped": ("coal333", M52_11, POISSON, ("GHEP", dict(power=0.5, damping=0.6)), 3, None),
+    "coal333_m52_poisson_ghks": ("coal333", M52_11, POISSON, ("GHKS", dict()), 3, None),
+    "coal333_m32_poisson_uep05": ("coal333", M32_11, POISSON, ("UEP", dict(power=0.5)), 3, None),
+    "coal333_m52_poisson_uks": ("coal333", M52_11, POISSON, ("UKS", dict()), 3, None),
+    "coal333_m52_poisson_vi_gh": ("coal333", M52_11, POISSON, ("VI", dict(intmethod="GH")), 3, None),
+    "coal333_m32_poisson_vi_ut_damped": ("coal333", M32_11, POISSON, ("VI", dict(intmethod="UT", damping=0.5)), 3, None),
+    "probit300_m52_ep1": ("classification300", M52_15, PROBIT, ("EP", dict(power=1.0)), 3, None),
+    "probit300_m52_pep05_gh": ("classification300", M52_15, PROBIT, ("EP", dict(power=0.5)), 3, None),
+    "probit300_m52_vi_gh": ("classification300", M52_15, PROBIT, ("VI", dict()), 3, None),
+    "probit300_m52_slep_ut": ("classification300", M52_15, PROBIT, ("SLEP", dict(intmethod="UT")), 3, None),
+    "probit300_m52_ghks_damped": ("classification300", M52_15, PROBIT, ("GHKS", dict(damping=0.5)), 3, None),
+    "logit300_m32_eks": ("classification300", M32_154, LOGIT, ("EKS", dict()), 3, None),
+    "logit300_m32_eep1": ("classification300", M32_154, LOGIT, ("EEP", dict(power=1.0)), 3, None),
+    "logit300_m32_vi_gh": ("classification300", M32_154, LOGIT, ("VI", dict()), 3, None),
+    "logit300_m32_ghep1": ("classification300", M32_154, LOGIT, ("GHEP", dict(power=1)), 3, None),
+    "c3_aircraft160_d59_poisson_ghep1": ("aircraft160", ("Sum", [AIR_M52, AIR_QP365, AIR_QP7]), POISSON, ("GHEP", dict(power=1)), 2, None),
+    "c3_aircraft160_d31_poisson_vi_gh": ("aircraft160", ("Sum", [AIR_M52, AIR_QP365]), POISSON, ("VI", dict(intmethod="GH")), 2, None),
+    "c3_aircraft160_d31_poisson_eks": ("aircraft160", ("Sum", [AIR_M52, AIR_QP365]), POISSON, ("EKS", dict()), 2, None),
+    "k5_banana400_st52_probit_pep05": ("banana400", ST52, PROBIT, ("ExpectationPropagation", dict(power=0.5)), 2, 178.81),
+    "c4_banana200_st52_probit_vi": ("banana200", ST52, PROBIT, ("VI", dict()), 2, None),
+}
+
+KEEP_EVERY = {"aircraft160": 8, "banana400": 16, "banana200": 16}
+
+
+def build(spec, module):
+    """Instantiate `spec` from `module` (the reference's module, oracle.*, or the product's mirror)."""
+    name, arg = spec
+    if name == "Sum":
+        return module.Sum([build(s, module) for s in arg])
+    return getattr(module, name)(**arg)
