@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py — filter + smoother + site-update iteration throughput (time-steps/s) and % of HBM roofline.
+
+Workload (BASELINE.json configs[4] == SURVEY.md C5): synthetic Matern-5/2 GP regression, Gaussian
+likelihood, EP(power 0.5) sites, N = 2^24 time steps, state dimension d = 3, fp64; one "step" = one
+steady-state SDEGP.run() iteration without the gradient: filter with the stored sites -> RTS smoother ->
+per-step site update (sde_gp.py:179-187).  At --gpus G > 1 the SAME series is split into G contiguous
+time shards (strong scaling), one process per GPU, two 28/19-double all-gathers per iteration.
+
+  python bench.py [--gpus G] [--steps K] [--warmup W] [--n LOG2N] [--impl reference]
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "filter+smoother time-steps/s (N=2^24, d=3)"
+BYTES_PER_STEP = 288          # 2(1+2f+f^2) + 2(d+d^2) + 2(f+f^2) scalars at d=3, f=1, fp64
+BYTES_FILTER, BYTES_SMOOTHER = 128, 160
+
+
+def synth(N, seed=12345):
+    """SURVEY.md 8(d) synthetic series: spacing U(0.05, 0.15), the regression-notebook signal."""
+    rng = np.random.default_rng(seed)
+    dt = rng.uniform(0.05, 0.15, N)
+    dt[0] = 0.0
+    t = np.cumsum(dt)
+    y = np.cos(0.04 * t + 0.33 * np.pi) * np.sin(0.2 * t) + np.sqrt(0.15) * rng.standard_normal(N)
+    return dt, y
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_oracle_lib():
+    import __graft_entry__ as g
+    so = os.path.join(ROOT, "oracle", "libkjx_oracle.so")
+    if not os.path.exists(so):
+        g.build()
+    lib = C.CDLL(so)
+    lib.kjx_oracle_run.restype = C.c_double
+    return lib
+
+
+def cpu_chain(lib, dt, y, reps=1):
+    """The C restatement of the reference recursion (oracle/seq_filter.c): one sequential chain."""
+    n = len(dt)
+    fm, fP = np.empty([n, 3]), np.empty([n, 3, 3])
+    sm, sv, nsm, nsv = y.copy(), np.full(n, 0.5), np.empty(n), np.empty(n)
+    dp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    best = 1e30
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        lib.kjx_oracle_run(2, C.c_double(1.0), C.c_double(5.0), C.c_double(0.5), C.c_double(0.5), C.c_double(1.0), C.c_long(n),
+                           dp(dt), dp(y), dp(sm), dp(sv), dp(fm), dp(fP), dp(nsm), dp(nsv), None, None)
+        best = min(best, time.perf_counter() - t0)
+    return n / best
+
+
+def cpu_replicas(lib, dt, y, cores, reps=1):
+    """`cores` independent copies of the chain, one per host thread (the reference algorithm cannot use more
+    than one core on one series: step n needs step n-1, sde_gp.py:271)."""
+    res = [0.0] * cores
+
+    def work(i):
+        res[i] = cpu_chain(lib, dt, y, reps)   # ctypes releases the GIL during the call
+    t0 = time.perf_counter()
+    th = [threading.Thread(target=work, args=(i,)) for i in range(cores)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    wall = time.perf_counter() - t0
+    return cores * len(dt) * reps / wall
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path, restated in C (JAX cannot be installed)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    lib = cpu_oracle_lib()
+    cores = os.cpu_count() or 1
+    n = 1 << 21
+    dt, y = synth(n)
+    for _ in range(args.warmup):
+        cpu_chain(lib, dt[: 1 << 18], y[: 1 << 18])
+    t0 = time.perf_counter()
+    vals = [cpu_replicas(lib, dt, y, cores) for _ in range(args.steps)]
+    wall = time.perf_counter() - t0
+    single = cpu_chain(lib, dt, y)
+    v = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "time-steps/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "Matern-5/2 + Gaussian + EP(0.5), filter->smoother->site update, d=3 fp64 (C5 recipe)",
+                   "N_sample": n, "note": "one sequential chain per series; value aggregates independent replicas"},
+        "cpu_baseline": {"value": v, "unit": "time-steps/s", "cores": cores, "kind": "port",
+                         "sample": "%d independent replicas of a 2^21-step slice of the C5 series, one chain per host thread, "
+                                   "C restatement oracle/seq_filter.c (single chain: %.3g steps/s)" % (cores, single),
+                         "single_chain_value": single},
+        "e2e": {"value": v, "unit": "time-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--n", type=int, default=24, help="log2 of the number of time steps")
+    ap.add_argument("--impl", default="kjx")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import kalman_jax_b200 as kjx
+    from kalman_jax_b200 import _lib
+    from kalman_jax_b200.sharded import ShardedIteration, split_series
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, "launch with torchrun --nproc-per-node == --gpus"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    gather = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+        def gather(t):
+            out = torch.empty(world, t.numel(), dtype=t.dtype, device=t.device)
+            dist.all_gather_into_tensor(out, t)
+            return out
+
+    N = 1 << args.n
+    dt, y = synth(N)
+    sh_dt, sh_y, dt_next, lo, hi = split_series(dt, y, world)[rank]
+    n_local = hi - lo
+    prior, lik, rule = kjx.priors.Matern52(1.0, 5.0), kjx.likelihoods.Gaussian(0.5), kjx.approximate_inference.EP(power=0.5)
+    it = ShardedIteration(prior, lik, rule, sh_dt, sh_y, dt_next, rank, world, dev, gather,
+                          site_mean=sh_y.copy(), site_var=np.full(n_local, 0.5))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        it.iteration()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record()
+    for k in range(args.steps):
+        it.iteration(events=ev[k])
+    stop.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = start.elapsed_time(stop)
+    phases = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(3)] for e in ev]).mean(axis=0)   # ms
+    nlml = float(it.nlml)
+    tt = torch.tensor([ms_total, phases[0], phases[1], phases[2]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_total, ph = float(tt[0]), [float(x) for x in tt[1:]]
+    ms_step = ms_total / args.steps
+    value = N / (ms_step * 1e-3)
+
+    # ---- end to end: host (pinned) buffers in, sites + nlml back, through the C ABI ----
+    e2e = None
+    if not args.no_e2e:
+        pin = lambda a: torch.as_tensor(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
+        h_dt, h_y, h_sm, h_sv = pin(sh_dt), pin(sh_y), pin(sh_y.copy()), pin(np.full(n_local, 0.5))
+        o_sm, o_sv, o_nl = (torch.empty(n_local, dtype=torch.float64).pin_memory(),
+                            torch.empty(n_local, dtype=torch.float64).pin_memory(), torch.empty(1, dtype=torch.float64).pin_memory())
+        if world == 1:
+            nbytes = C.c_size_t(0)
+            _lib.check(_lib.lib().kjx_run_host_scratch_bytes(it.model.ref(), C.c_int64(N), 8, C.byref(nbytes)), "scratch")
+            del it.filt_mean, it.filt_cov
+            torch.cuda.empty_cache()
+            scratch = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+
+            def e2e_step():
+                _lib.check(_lib.lib().kjx_run_host_f64(it.model.ref(), C.c_int64(N), _lib.ptr(h_dt), _lib.ptr(h_y), _lib.ptr(h_sm),
+                                                       _lib.ptr(h_sv), _lib.ptr(o_sm), _lib.ptr(o_sv), None, None, _lib.ptr(o_nl),
+                                                       _lib.ptr(scratch), C.c_size_t(nbytes.value), 0,
+                                                       C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "kjx_run_host")
+        else:
+            def e2e_step():
+                it.dt.copy_(h_dt, non_blocking=True); it.y.copy_(h_y, non_blocking=True)
+                it.site_mean.copy_(h_sm, non_blocking=True); it.site_var.copy_(h_sv, non_blocking=True)
+                nl = it.iteration()
+                o_sm.copy_(it.site_mean, non_blocking=True); o_sv.copy_(it.site_var, non_blocking=True)
+                o_nl.copy_(nl.reshape(1), non_blocking=True)
+                torch.cuda.synchronize()
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        ke = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            e2e_step()
+        barrier()
+        dt_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt_e2e, op=dist.ReduceOp.MAX)
+        e2e = {"value": N * ke / float(dt_e2e[0]), "unit": "time-steps/s", "h2d_bytes_per_step": 4 * 8 * N,
+               "d2h_bytes_per_step": 2 * 8 * N + 8, "steps": ke,
+               "api": "kjx_run_host_f64 (pinned host arrays)" if world == 1 else "pinned copies + sharded C-ABI calls per rank",
+               "nlml": float(o_nl[0])}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    hbm, peak_src = peaks()
+    dom = int(np.argmax(ph[1:])) + 1                        # filter-apply or smoother-apply phase
+    dom_bytes = (BYTES_FILTER, BYTES_SMOOTHER)[dom - 1] * n_local
+    achieved = dom_bytes / (ph[dom] * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": "time-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C5: synthetic Matern-5/2 (var 1, len 5) + Gaussian(0.5) + EP(power 0.5); one iteration = "
+                               "filter(stored sites) -> RTS smoother -> site update; N=2^%d steps, d=3, f=1" % args.n,
+                   "N": N, "state_dim": 3, "sharding": "time axis, %d contiguous shard(s)" % world,
+                   "l2_policy": "inputs (%.1f GB per iteration per GPU) exceed the 126 MB L2; no flush needed" % (BYTES_PER_STEP * n_local / 1e9)},
+        "roofline": {"bound": "hbm", "kernel": ("filter_apply_kernel (F3, incl. smoother fold)", "smoother_apply_kernel (S3)")[dom - 1],
+                     "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_step": (BYTES_FILTER, BYTES_SMOOTHER)[dom - 1],
+                     "phase_ms": {"filter_summary(F1+F2)": ph[0], "filter_apply(F3+S2)": ph[1], "smoother_apply(S3)": ph[2]},
+                     "iteration": {"achieved": BYTES_PER_STEP * n_local / (ms_step * 1e-3) / 1e9,
+                                   "frac": BYTES_PER_STEP * n_local / (ms_step * 1e-3) / 1e9 / hbm, "bytes_per_step": BYTES_PER_STEP}},
+        "gpu_launches": it.launches_per_iteration * args.steps,
+        "clocks": clocks,
+        "nlml": nlml,
+    }
+    if e2e:
+        line["e2e"] = e2e
+    if not args.no_cpu:
+        lib = cpu_oracle_lib()
+        n_s = 1 << 22
+        v = cpu_chain(lib, dt[:n_s], y[:n_s], reps=3)
+        line["cpu_baseline"] = {"value": v, "unit": "time-steps/s", "cores": 1, "kind": "port",
+                                "sample": "first 2^22 steps of the same series, best of 3, C restatement of the reference's "
+                                          "sequential loops (oracle/seq_filter.c); the recursion is one dependent chain"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,254 @@
+/*
+ * kjx.h — C ABI of libkjx.so: the B200 (sm_100a) Kalman filter / RTS smoother / site-update path.
+ *
+ * This is the drop-in boundary for kalman-jax's shared inference core.  The reference has no
+ * FFI/plugin layer of its own (it is pure Python on JAX); the seam these entry points replace is the
+ * set of Python methods below (paths relative to /root/reference/kalmanjax):
+ *
+ *   kjx_filter_*        <- SDEGP.kalman_filter                      sde_gp.py:230-309
+ *   kjx_smoother_*      <- SDEGP.rauch_tung_striebel_smoother       sde_gp.py:311-384
+ *   kjx_run_*           <- SDEGP.run (filter -> smoother, no grad)  sde_gp.py:163-188
+ *   kjx_site_update_*   <- ApproxInf.update / Likelihood.moment_match,
+ *                          statistical_linear_regression, variational_expectation,
+ *                          analytical_linearisation                 approximate_inference.py:36-323,
+ *                                                                   likelihoods.py:122-321
+ *                          (and the vmapped NLPD of sde_gp.py:139-142)
+ *   kjx_discretise_*    <- Prior.state_transition closed forms      priors.py:163-175, 238-255,
+ *                          and Q = Pinf - A Pinf A^T                1044-1084, 1398-1414, 1163-1181;
+ *                                                                   sde_gp.py:409
+ *   kjx_*_summary/_apply<- (new) the time-sharded parallel-in-time scan; no reference counterpart
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / JAX types.
+ *   - Every array pointer is a DEVICE pointer unless its name ends in `_host` (the two small model
+ *     matrices kjx_model_t.Pinf / .H are HOST pointers too); arrays are dense,
+ *     row-major, in the reference's layouts (y[N,f], dt[N], site_mean[N,f,1], site_cov[N,f,f],
+ *     filt_mean[N,d,1], filt_cov[N,d,d]).  Outputs and workspace are caller-allocated.
+ *   - `?` in a comment marks a nullable pointer.
+ *   - Calls enqueue work on `stream` and return immediately; the library keeps no state between
+ *     calls.  The workspace passed to a call must stay alive until the stream has drained.
+ *   - Return value: 0 on success, negative kjx_status otherwise.  Numerical failure is NOT an
+ *     error: like the reference (utils.py:25-38 — a failed Cholesky yields NaN, no exception) NaNs
+ *     propagate into the outputs.
+ *   - Hyperparameters are the already-transformed positive values (after the reference's
+ *     softplus, utils.py:41-69); func_dim f = 1 (scalar sites) in this version.
+ *   - `_f64` entry points compute in IEEE double, `_f32` in float (same signatures with float data).
+ */
+#ifndef KJX_H_
+#define KJX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* kjx_stream_t; /* == cudaStream_t */
+
+enum kjx_status {
+  KJX_OK = 0,
+  KJX_ERR_INVALID_ARG = -1,   /* null pointer, N < 0, bad enum, misaligned pointer ...          */
+  KJX_ERR_UNSUPPORTED = -2,   /* valid request this build has no kernel for (e.g. f > 1)        */
+  KJX_ERR_WORKSPACE = -3,     /* ws_bytes smaller than kjx_workspace_bytes()                    */
+  KJX_ERR_CUDA = -4           /* a CUDA runtime call / kernel launch failed                     */
+};
+
+/* one diagonal block of the (always block-diagonal) transition matrix A(dt) = expm(F dt) */
+enum kjx_block_kind {
+  KJX_BLOCK_MATERN32 = 1,      /* 2x2, priors.py:163-175   : lam = sqrt(3)/ell                    */
+  KJX_BLOCK_MATERN52 = 2,      /* 3x3, priors.py:238-255   : lam = sqrt(5)/ell                    */
+  KJX_BLOCK_QP_MATERN32 = 3    /* 4x4 harmonic block of QuasiPeriodicMatern32, priors.py:1076-1084:
+                                  exp(-dt lam) [[(1+dt lam)R, dt R],[-dt lam^2 R,(1-dt lam)R]],
+                                  R = rotation(dt*omega), utils.py:253-265                        */
+};
+
+typedef struct kjx_block {
+  int32_t kind;    /* kjx_block_kind                                                              */
+  int32_t count;   /* this block repeated `count` times (spatio-temporal: M inducing points)      */
+  double lam;      /* decay rate                                                                  */
+  double omega;    /* angular frequency of the harmonic (KJX_BLOCK_QP_MATERN32 only)              */
+} kjx_block_t;
+
+enum kjx_likelihood {
+  KJX_LIK_GAUSSIAN = 1,          /* likelihoods.py:331-404; hyp = noise variance                  */
+  KJX_LIK_BERNOULLI_PROBIT = 2,  /* likelihoods.py:407-518, link 'probit' (with its 1e-10 jitter) */
+  KJX_LIK_BERNOULLI_LOGIT = 3,   /* likelihoods.py:407-518, link 'logit'                          */
+  KJX_LIK_POISSON_EXP = 4,       /* likelihoods.py:551-644, link 'exp'                            */
+  KJX_LIK_POISSON_LOGISTIC = 5   /* likelihoods.py:551-644, link 'logistic' (softplus)            */
+};
+
+enum kjx_method {
+  KJX_INF_EP = 1,    /* ExpectationPropagation.update      approximate_inference.py:50-73    */
+  KJX_INF_EEP = 2,   /* ExtendedEP.update (EKS: power 0)   approximate_inference.py:99-133   */
+  KJX_INF_SLEP = 3,  /* StatisticallyLinearisedEP.update   approximate_inference.py:180-210  */
+  KJX_INF_VI = 4     /* VariationalInference.update        approximate_inference.py:302-323  */
+};
+
+#define KJX_MAX_BLOCKS 16
+#define KJX_MAX_CUBATURE 32
+
+typedef struct kjx_model {
+  /* ---- prior (priors.py): block-diagonal A(dt), stationary covariance, measurement model ---- */
+  int32_t state_dim;               /* d = sum over blocks of count * block size                   */
+  int32_t func_dim;                /* f, rows of H; must be 1                                     */
+  int32_t n_blocks;
+  int32_t reserved0;
+  kjx_block_t blocks[KJX_MAX_BLOCKS];
+  const double* Pinf;              /* HOST [d,d] row-major stationary covariance (read at call time) */
+  const double* H;                 /* HOST [f,d] constant measurement model, or NULL with H_steps    */
+  const double* H_steps;           /* DEVICE [N,f,d] per-step measurement model (spatio-temporal prior
+                                      with scattered data, priors.py:1148-1161), else NULL           */
+  /* ---- likelihood + approximate-inference method ---- */
+  int32_t likelihood;              /* kjx_likelihood                                              */
+  int32_t method;                  /* kjx_method                                                  */
+  double lik_hyp;                  /* Gaussian noise variance (unused otherwise)                  */
+  double power;                    /* EP power / fraction                                         */
+  double damping;                  /* site damping                                                */
+  int32_t n_cub;                   /* number of cubature points, 1..KJX_MAX_CUBATURE              */
+  int32_t reserved;
+  double cub_x[KJX_MAX_CUBATURE];  /* unit sigma points  (utils.py:455-463 / 466-511)             */
+  double cub_w[KJX_MAX_CUBATURE];  /* weights                                                     */
+} kjx_model_t;
+
+/* flags */
+#define KJX_FLAG_SEQUENTIAL 1u   /* force the one-thread-chain sequential kernels (reference order) */
+#define KJX_FLAG_RETURN_FULL 2u  /* smoother: write the full state posterior [N,d],[N,d,d]          */
+#define KJX_FLAG_NO_SITE_UPDATE 4u /* kjx_run: smoother pass does not update the sites              */
+
+int kjx_version(void);
+const char* kjx_status_string(int status);
+
+/* Bytes of device workspace any call below needs for N steps of model `m` (dtype_bytes 8 or 4). */
+int kjx_workspace_bytes(const kjx_model_t* m, int64_t N, int dtype_bytes, size_t* bytes);
+
+/* Forward filter.  site_mean/site_cov null => sites are initialised from the predictive
+ * (sde_gp.py:287) and, when out_site_* are given, stored.  With a non-Gaussian likelihood that
+ * recursion is inherently sequential and runs as one dependent chain; otherwise the
+ * parallel-in-time scan is used.  filt_mean/filt_cov null => energy only (store=False). */
+int kjx_filter_f64(const kjx_model_t* m, int64_t N, const double* dt, const double* y,
+                   const uint8_t* mask /*?*/, const double* site_mean /*?*/, const double* site_cov /*?*/,
+                   double* filt_mean /*?*/, double* filt_cov /*?*/,
+                   double* out_site_mean /*?*/, double* out_site_cov /*?*/,
+                   double* nlml /* [1] */, void* ws, size_t ws_bytes, uint32_t flags, kjx_stream_t stream);
+
+/* Backward smoother.  When site_mean/site_cov (the previous sites) and y are given the sites are
+ * updated per step (sde_gp.py:371-379) into new_site_*.  smooth_* (nullable) receive H m, H P H^T
+ * ([N,f],[N,f,f]) or, with KJX_FLAG_RETURN_FULL, the full state ([N,d],[N,d,d]). */
+int kjx_smoother_f64(const kjx_model_t* m, int64_t N, const double* dt,
+                     const double* filt_mean, const double* filt_cov,
+                     const double* y /*?*/, const double* site_mean /*?*/, const double* site_cov /*?*/,
+                     double* smooth_mean /*?*/, double* smooth_cov /*?*/,
+                     double* new_site_mean /*?*/, double* new_site_cov /*?*/,
+                     void* ws, size_t ws_bytes, uint32_t flags, kjx_stream_t stream);
+
+/* One SDEGP.run() iteration (sde_gp.py:179-187 without the gradient): filter with the given (or
+ * initialised) sites, then smoother + site update.  Fuses the smoother's scan summaries into the
+ * filter pass.  site_* in; new_site_* out (may alias site_*); post_mean/post_var = smoothed
+ * marginals H m, H P H^T (nullable). */
+int kjx_run_f64(const kjx_model_t* m, int64_t N, const double* dt, const double* y,
+                const double* site_mean /*?*/, const double* site_cov /*?*/,
+                double* filt_mean, double* filt_cov,
+                double* new_site_mean, double* new_site_cov,
+                double* post_mean /*?*/, double* post_var /*?*/,
+                double* nlml, void* ws, size_t ws_bytes, uint32_t flags, kjx_stream_t stream);
+
+/* Per-step site update, embarrassingly parallel over N (f = 1):
+ * (log_lik, site_mean, site_var) = method.update(likelihood, y, post_mean, post_var, prev site?).
+ * With prev null this is the "initialise" branch; log_lik alone (site outputs null) with method EP
+ * is the vmapped NLPD term of sde_gp.py:139-142. */
+int kjx_site_update_f64(const kjx_model_t* m, int64_t N, const double* y,
+                        const double* post_mean, const double* post_var,
+                        const double* site_mean_prev /*?*/, const double* site_var_prev /*?*/,
+                        double* log_lik /*?*/, double* site_mean /*?*/, double* site_var /*?*/,
+                        kjx_stream_t stream);
+
+/* Batched discretisation of the prior SDE: A[n] = expm(F dt[n]) (closed forms) and, when Q is
+ * non-null, Q[n] = Pinf - A[n] Pinf A[n]^T. */
+int kjx_discretise_f64(const kjx_model_t* m, int64_t N, const double* dt,
+                       double* A /* [N,d,d] */, double* Q /*? [N,d,d] */, kjx_stream_t stream);
+
+/* ---- time-sharded form (one shard per GPU).  The caller exchanges the fixed-size summaries
+ * between the two halves (all-gather), folds the ones of the preceding (filter) / following
+ * (smoother) shards with kjx_fold_*_summaries_host, and passes the boundary state in. ---------- */
+/* packed sizes: (A[d,d], b[d], upper(C), eta[d], upper(J)) and (E[d,d], g[d], upper(L)) */
+size_t kjx_filter_summary_doubles(int32_t state_dim);    /* 2 d^2 + 3 d        (27 at d = 3)      */
+size_t kjx_smoother_summary_doubles(int32_t state_dim);  /* (3 d^2 + 3 d) / 2  (18 at d = 3)      */
+
+/* phase 1+2 of the filter scan over this shard; writes the shard's total element
+ * (A, b, C, eta, J) to summary_out (device, kjx_filter_summary_doubles). */
+int kjx_filter_summary_f64(const kjx_model_t* m, int64_t N, const double* dt, const double* y,
+                           const uint8_t* mask /*?*/, const double* site_mean /*?*/, const double* site_cov /*?*/,
+                           double* summary_out, void* ws, size_t ws_bytes, kjx_stream_t stream);
+/* phase 3: state_in = (mean[d], cov[d,d]) filtered state just before this shard (device, d+d^2
+ * doubles; for shard 0: (0, Pinf)).  dt_next = dt of the first step of the next shard (0 for the
+ * last shard); is_last_shard marks the shard holding step N-1.  Also produces this shard's
+ * smoother summary (E, g, L) and partial nlml. */
+int kjx_filter_apply_f64(const kjx_model_t* m, int64_t N, const double* dt, const double* y,
+                         const uint8_t* mask /*?*/, const double* site_mean /*?*/, const double* site_cov /*?*/,
+                         const double* state_in, double dt_next, int32_t is_last_shard,
+                         double* filt_mean, double* filt_cov,
+                         double* out_site_mean /*?*/, double* out_site_cov /*?*/,
+                         double* smoother_summary_out, double* nlml_partial,
+                         void* ws, size_t ws_bytes, kjx_stream_t stream);
+/* smoother phase 3: state_in = smoothed (mean[d], cov[d,d]) at the first step of the next shard
+ * (ignored for the last shard). */
+int kjx_smoother_apply_f64(const kjx_model_t* m, int64_t N, const double* dt, double dt_next,
+                           const double* filt_mean, const double* filt_cov,
+                           const double* y /*?*/, const double* site_mean /*?*/, const double* site_cov /*?*/,
+                           const double* state_in, int32_t is_last_shard,
+                           double* smooth_mean /*?*/, double* smooth_cov /*?*/,
+                           double* new_site_mean /*?*/, double* new_site_cov /*?*/,
+                           void* ws, size_t ws_bytes, uint32_t flags, kjx_stream_t stream);
+/* Host-side folds of gathered summaries (tiny, fp64): state before shard `rank` from the filter
+ * summaries of shards 0..rank-1 applied to the prior (0, Pinf); smoothed state entering shard
+ * `rank` from the smoother summaries of shards rank+1..world-1. */
+int kjx_fold_filter_summaries_host(int32_t state_dim, const double* Pinf_host, const double* summaries_host,
+                                   int32_t rank, double* state_out_host /* d + d^2 */);
+int kjx_fold_smoother_summaries_host(int32_t state_dim, const double* summaries_host, int32_t world,
+                                     int32_t rank, double* state_out_host /* d + d^2 */);
+
+/* Device-side versions of the two folds (one tiny kernel each, no host round trip): gathered
+ * summaries live in device memory as [world, kjx_*_summary_doubles(d)] (+ `stride` doubles between
+ * ranks, >= the packed size, so extra per-rank scalars can ride along in the same all-gather). */
+int kjx_fold_filter_summaries_f64(const kjx_model_t* m, const double* summaries, int64_t stride, int32_t rank,
+                                  double* state_out /* d + d^2 */, kjx_stream_t stream);
+int kjx_fold_smoother_summaries_f64(const kjx_model_t* m, const double* summaries, int64_t stride, int32_t world,
+                                    int32_t rank, double* state_out /* d + d^2 */, kjx_stream_t stream);
+
+/* ---- host-buffer entry point (end-to-end path): one run() iteration where every data array is a
+ * HOST pointer (pinned memory for full PCIe speed).  Inputs are copied to the device, the fused
+ * filter/smoother/site-update runs, new sites (+ optional posterior marginals) and nlml are copied back;
+ * the call returns after the stream has drained.  dev_scratch: caller-owned device memory of at least
+ * kjx_run_host_scratch_bytes() bytes (holds the staged arrays, the filter output and the workspace). -- */
+int kjx_run_host_scratch_bytes(const kjx_model_t* m, int64_t N, int dtype_bytes, size_t* bytes);
+int kjx_run_host_f64(const kjx_model_t* m, int64_t N, const double* dt_host, const double* y_host,
+                     const double* site_mean_host /*?*/, const double* site_cov_host /*?*/,
+                     double* new_site_mean_host, double* new_site_cov_host,
+                     double* post_mean_host /*?*/, double* post_var_host /*?*/, double* nlml_host,
+                     void* dev_scratch, size_t dev_scratch_bytes, uint32_t flags, kjx_stream_t stream);
+
+/* float variants: identical semantics, float data (Pinf/H in the model stay double). */
+int kjx_filter_f32(const kjx_model_t* m, int64_t N, const float* dt, const float* y,
+                   const uint8_t* mask, const float* site_mean, const float* site_cov,
+                   float* filt_mean, float* filt_cov, float* out_site_mean, float* out_site_cov,
+                   float* nlml, void* ws, size_t ws_bytes, uint32_t flags, kjx_stream_t stream);
+int kjx_smoother_f32(const kjx_model_t* m, int64_t N, const float* dt,
+                     const float* filt_mean, const float* filt_cov,
+                     const float* y, const float* site_mean, const float* site_cov,
+                     float* smooth_mean, float* smooth_cov, float* new_site_mean, float* new_site_cov,
+                     void* ws, size_t ws_bytes, uint32_t flags, kjx_stream_t stream);
+int kjx_run_f32(const kjx_model_t* m, int64_t N, const float* dt, const float* y,
+                const float* site_mean, const float* site_cov, float* filt_mean, float* filt_cov,
+                float* new_site_mean, float* new_site_cov, float* post_mean, float* post_var,
+                float* nlml, void* ws, size_t ws_bytes, uint32_t flags, kjx_stream_t stream);
+int kjx_site_update_f32(const kjx_model_t* m, int64_t N, const float* y, const float* post_mean,
+                        const float* post_var, const float* site_mean_prev, const float* site_var_prev,
+                        float* log_lik, float* site_mean, float* site_var, kjx_stream_t stream);
+int kjx_discretise_f32(const kjx_model_t* m, int64_t N, const float* dt, float* A, float* Q,
+                       kjx_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KJX_H_ */

@@ -1,0 +1,704 @@
+// kjx_api.cu — the C ABI of libkjx.so (see include/kjx.h) and the dispatch onto the sm_100a kernels.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+
+#include "../../include/kjx.h"
+#include "kjx_small_kernels.cuh"
+#include "kjx_elementwise_kernels.cuh"
+
+using namespace kjx;
+
+#define KJX_CUDA_CHECK(expr)                              \
+  do {                                                    \
+    cudaError_t e__ = (expr);                             \
+    if (e__ != cudaSuccess) return KJX_ERR_CUDA;          \
+  } while (0)
+
+namespace {
+
+inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
+
+// ------------------------------------------------------------------------------------------------
+// model inspection
+bool model_basic_ok(const kjx_model_t* m) {
+  if (!m) return false;
+  if (m->state_dim <= 0 || m->func_dim <= 0 || m->n_blocks <= 0 || m->n_blocks > KJX_MAX_BLOCKS) return false;
+  if (m->n_cub < 1 || m->n_cub > KJX_MAX_CUBATURE) return false;
+  if (m->likelihood < KJX_LIK_GAUSSIAN || m->likelihood > KJX_LIK_POISSON_LOGISTIC) return false;
+  if (m->method < KJX_INF_EP || m->method > KJX_INF_VI) return false;
+  if (!m->Pinf) return false;
+  int d = 0;
+  for (int b = 0; b < m->n_blocks; ++b) {
+    const kjx_block_t& k = m->blocks[b];
+    if (k.count <= 0) return false;
+    int bs = k.kind == KJX_BLOCK_MATERN32 ? 2 : k.kind == KJX_BLOCK_MATERN52 ? 3 : k.kind == KJX_BLOCK_QP_MATERN32 ? 4 : -1;
+    if (bs < 0) return false;
+    d += bs * k.count;
+  }
+  return d == m->state_dim;
+}
+
+// the register-resident path: one Matern-3/2 or Matern-5/2 block, scalar site, H = e0
+int small_kind(const kjx_model_t* m) {
+  if (m->func_dim != 1 || m->n_blocks != 1 || m->blocks[0].count != 1 || m->H_steps) return 0;
+  const int kind = m->blocks[0].kind;
+  if (kind != KJX_BLOCK_MATERN32 && kind != KJX_BLOCK_MATERN52) return 0;
+  if (!m->H) return 0;
+  const int d = m->state_dim;
+  if (m->H[0] != 1.0) return 0;
+  for (int i = 1; i < d; ++i) if (m->H[i] != 0.0) return 0;
+  return kind;
+}
+
+SiteModel make_site(const kjx_model_t* m) {
+  SiteModel s;
+  memset(&s, 0, sizeof(s));
+  s.lik = m->likelihood; s.method = m->method; s.n_cub = m->n_cub;
+  s.lik_hyp = m->lik_hyp; s.power = m->power; s.damping = m->damping;
+  for (int i = 0; i < KJX_MAX_CUBATURE; ++i) { s.cub_x[i] = m->cub_x[i]; s.cub_w[i] = m->cub_w[i]; }
+  return s;
+}
+
+// steps per thread chunk: long chunks amortise the O(d^3) scan combines, short ones keep every SM
+// busy on short series.  A multiple of 4 so a chunk starts on a 32-byte boundary of every array.
+int pick_chunk(int64_t N) {
+  const int64_t target_chunks = 148 * 2 * KJX_BLOCK;   // two resident blocks per SM
+  int64_t L = (N + target_chunks - 1) / target_chunks;
+  L = std::max<int64_t>(4, std::min<int64_t>(64, L));
+  return (int)round_up((size_t)L, 4);
+}
+
+template <typename T, int D> struct SmallLayout {
+  int L; int64_t nchunks, nblocks; size_t cstride, bstride;
+  size_t off_ftp, off_fbt, off_fbp, off_fst, off_sts, off_sbt, off_sbs, off_sst, off_nl, off_fin, off_sin, total;
+  explicit SmallLayout(int64_t N) {
+    constexpr size_t FNS = FSum<T, D>::NS, SNS = SSum<T, D>::NS;
+    L = pick_chunk(N);
+    nchunks = std::max<int64_t>(1, (N + L - 1) / L);
+    nblocks = (nchunks + KJX_BLOCK - 1) / KJX_BLOCK;
+    cstride = round_up((size_t)nchunks, 32);
+    bstride = round_up((size_t)nblocks, 32);
+    size_t o = 0;
+    auto take = [&](size_t n) { size_t r = o; o += round_up(n * sizeof(T), 256); return r; };
+    off_ftp = take(FNS * cstride); off_fbt = take(FNS * bstride); off_fbp = take(FNS * bstride); off_fst = take(FNS);
+    off_sts = take(SNS * cstride); off_sbt = take(SNS * bstride); off_sbs = take(SNS * bstride); off_sst = take(SNS);
+    off_nl = take(bstride); off_fin = take(D + D * D); off_sin = take(D + D * D);
+    total = o;
+  }
+};
+
+template <typename T, int D>
+void bind_workspace(SmallArgs<T, D>& a, const SmallLayout<T, D>& lay, void* ws) {
+  char* w = (char*)ws;
+  a.L = lay.L; a.nchunks = lay.nchunks; a.nblocks = lay.nblocks; a.cstride = lay.cstride; a.bstride = lay.bstride;
+  a.f_thread_prefix = (T*)(w + lay.off_ftp); a.f_block_total = (T*)(w + lay.off_fbt);
+  a.f_block_prefix = (T*)(w + lay.off_fbp); a.f_shard_total = (T*)(w + lay.off_fst);
+  a.s_thread_suffix = (T*)(w + lay.off_sts); a.s_block_total = (T*)(w + lay.off_sbt);
+  a.s_block_suffix = (T*)(w + lay.off_sbs); a.s_shard_total = (T*)(w + lay.off_sst);
+  a.block_nlml = (T*)(w + lay.off_nl);
+  a.f_state_in = (T*)(w + lay.off_fin); a.s_state_in = (T*)(w + lay.off_sin);
+}
+
+template <typename T, int D>
+void fill_prior(SmallArgs<T, D>& a, const kjx_model_t* m) {
+  a.prior.lam = (T)m->blocks[0].lam;
+  for (int i = 0; i < D; ++i)
+    for (int j = 0; j < D; ++j) a.prior.Pinf[i][j] = (T)m->Pinf[i * D + j];
+  a.site = make_site(m);
+}
+
+// writes a (mean, cov) boundary state into device memory from kernel arguments
+template <typename T, int D> struct StateArg { T v[D + D * D]; };
+template <typename T, int D> __global__ void set_state_kernel(T* dst, StateArg<T, D> s) {
+  if (threadIdx.x < D + D * D) dst[threadIdx.x] = s.v[threadIdx.x];
+}
+template <typename T, int D> __global__ void copy_state_kernel(T* dst, const T* src) {
+  if (threadIdx.x < D + D * D) dst[threadIdx.x] = src[threadIdx.x];
+}
+template <typename T> __global__ void copy_scalars_kernel(T* dst, const T* src, int n) {
+  if ((int)threadIdx.x < n) dst[threadIdx.x] = src[threadIdx.x];
+}
+
+template <typename T, int D>
+void launch_set_prior_state(T* dst, const kjx_model_t* m, cudaStream_t st) {
+  StateArg<T, D> s;
+  for (int i = 0; i < D; ++i) s.v[i] = T(0);                    // sde_gp.py:265  m0 = 0, P0 = Pinf
+  for (int i = 0; i < D * D; ++i) s.v[D + i] = (T)m->Pinf[i];
+  set_state_kernel<T, D><<<1, 32, 0, st>>>(dst, s);
+}
+
+bool gauss_ep(const kjx_model_t* m) { return m->likelihood == KJX_LIK_GAUSSIAN && m->method == KJX_INF_EP; }
+
+struct SmallCall {
+  // what the caller asked for (device pointers, type-erased)
+  const void *dt, *y; const uint8_t* mask; const void *site_mean, *site_var;
+  void *filt_mean, *filt_cov, *out_site_mean, *out_site_var;
+  const void *filt_mean_in, *filt_cov_in;
+  void *smooth_mean, *smooth_cov, *new_site_mean, *new_site_var;
+  void* nlml;
+};
+
+template <typename T, int KIND>
+int small_filter_scan(const kjx_model_t* m, int64_t N, SmallArgs<T, BlockDim<KIND>::D>& a, bool with_smoother,
+                      const T* f_state_in_dev /* null: prior */, cudaStream_t st) {
+  constexpr int D = BlockDim<KIND>::D;
+  filter_reduce_kernel<T, KIND><<<(unsigned)a.nblocks, KJX_BLOCK, 0, st>>>(a);
+  filter_blockscan_kernel<T, D><<<1, KJX_SCAN_BLOCK, 0, st>>>(a);
+  if (f_state_in_dev) copy_state_kernel<T, D><<<1, 32, 0, st>>>((T*)a.f_state_in, f_state_in_dev);
+  else launch_set_prior_state<T, D>((T*)a.f_state_in, m, st);
+  const bool fast = gauss_ep(m);
+  if (with_smoother) {
+    if (fast) filter_apply_kernel<T, KIND, true, true><<<(unsigned)a.nblocks, KJX_BLOCK, 0, st>>>(a);
+    else filter_apply_kernel<T, KIND, true, false><<<(unsigned)a.nblocks, KJX_BLOCK, 0, st>>>(a);
+  } else {
+    if (fast) filter_apply_kernel<T, KIND, false, true><<<(unsigned)a.nblocks, KJX_BLOCK, 0, st>>>(a);
+    else filter_apply_kernel<T, KIND, false, false><<<(unsigned)a.nblocks, KJX_BLOCK, 0, st>>>(a);
+  }
+  return KJX_OK;
+}
+
+template <typename T, int KIND>
+int small_smoother_apply(const kjx_model_t* m, SmallArgs<T, BlockDim<KIND>::D>& a, cudaStream_t st) {
+  if (gauss_ep(m)) smoother_apply_kernel<T, KIND, true><<<(unsigned)a.nblocks, KJX_BLOCK, 0, st>>>(a);
+  else smoother_apply_kernel<T, KIND, false><<<(unsigned)a.nblocks, KJX_BLOCK, 0, st>>>(a);
+  return KJX_OK;
+}
+
+// the filter must run as one chain when sites have to be initialised from the predictive and that
+// initialisation depends on the state (anything but Gaussian + EP, utils.py:241-244)
+bool needs_sequential_filter(const kjx_model_t* m, bool have_sites) { return !have_sites && !gauss_ep(m); }
+
+template <typename T, int KIND>
+int small_filter(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const uint8_t* mask,
+                 const T* site_mean, const T* site_var, T* filt_mean, T* filt_cov, T* out_site_mean,
+                 T* out_site_var, T* nlml, void* ws, size_t ws_bytes, uint32_t flags, cudaStream_t st) {
+  constexpr int D = BlockDim<KIND>::D;
+  SmallLayout<T, D> lay(N);
+  if (ws_bytes < lay.total || !ws) return KJX_ERR_WORKSPACE;
+  SmallArgs<T, D> a; memset(&a, 0, sizeof(a));
+  fill_prior<T, D>(a, m); bind_workspace<T, D>(a, lay, ws);
+  a.N = N; a.dt = dt; a.y = y; a.mask = mask; a.site_mean = site_mean; a.site_var = site_var;
+  a.filt_mean = filt_mean; a.filt_cov = filt_cov; a.out_site_mean = out_site_mean; a.out_site_var = out_site_var;
+  a.is_last_shard = 1; a.dt_next = T(0); a.nlml_out = nlml;
+  const bool have_sites = site_mean != nullptr;
+  a.gaussian_init = (!have_sites && gauss_ep(m)) ? 1 : 0;
+  if (N == 0) { cudaMemsetAsync(nlml, 0, sizeof(T), st); return KJX_OK; }
+  if ((flags & KJX_FLAG_SEQUENTIAL) || needs_sequential_filter(m, have_sites)) {
+    launch_set_prior_state<T, D>((T*)a.f_state_in, m, st);
+    const int init = (!have_sites && !a.gaussian_init) ? 1 : 0;
+    filter_sequential_kernel<T, KIND><<<1, 32, 0, st>>>(a, init);
+  } else {
+    small_filter_scan<T, KIND>(m, N, a, false, nullptr, st);
+    nlml_reduce_kernel<T><<<1, KJX_SCAN_BLOCK, 0, st>>>(a.block_nlml, a.nblocks, nlml);
+  }
+  KJX_CUDA_CHECK(cudaGetLastError());
+  return KJX_OK;
+}
+
+template <typename T, int KIND>
+int small_smoother(const kjx_model_t* m, int64_t N, const T* dt, const T* filt_mean, const T* filt_cov,
+                   const T* y, const T* site_mean, const T* site_var, T* smooth_mean, T* smooth_cov,
+                   T* new_site_mean, T* new_site_var, void* ws, size_t ws_bytes, uint32_t flags, cudaStream_t st) {
+  constexpr int D = BlockDim<KIND>::D;
+  SmallLayout<T, D> lay(N);
+  if (ws_bytes < lay.total || !ws) return KJX_ERR_WORKSPACE;
+  SmallArgs<T, D> a; memset(&a, 0, sizeof(a));
+  fill_prior<T, D>(a, m); bind_workspace<T, D>(a, lay, ws);
+  a.N = N; a.dt = dt; a.y = y; a.site_mean = site_mean; a.site_var = site_var;
+  a.filt_mean_in = filt_mean; a.filt_cov_in = filt_cov;
+  a.smooth_mean = smooth_mean; a.smooth_cov = smooth_cov; a.new_site_mean = new_site_mean; a.new_site_var = new_site_var;
+  a.return_full = (flags & KJX_FLAG_RETURN_FULL) ? 1 : 0;
+  a.update_sites = (new_site_mean != nullptr && site_mean != nullptr && y != nullptr) ? 1 : 0;
+  a.is_last_shard = 1; a.dt_next = T(0);
+  if (N == 0) return KJX_OK;
+  if (flags & KJX_FLAG_SEQUENTIAL) {
+    smoother_sequential_kernel<T, KIND><<<1, 32, 0, st>>>(a);
+  } else {
+    smoother_reduce_kernel<T, KIND><<<(unsigned)a.nblocks, KJX_BLOCK, 0, st>>>(a);
+    a.nlml_out = nullptr;
+    smoother_blockscan_kernel<T, D><<<1, KJX_SCAN_BLOCK, 0, st>>>(a);
+    cudaMemsetAsync((void*)a.s_state_in, 0, (D + D * D) * sizeof(T), st);
+    small_smoother_apply<T, KIND>(m, a, st);
+  }
+  KJX_CUDA_CHECK(cudaGetLastError());
+  return KJX_OK;
+}
+
+template <typename T, int KIND>
+int small_run(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const T* site_mean, const T* site_var,
+              T* filt_mean, T* filt_cov, T* new_site_mean, T* new_site_var, T* post_mean, T* post_var,
+              T* nlml, void* ws, size_t ws_bytes, uint32_t flags, cudaStream_t st) {
+  constexpr int D = BlockDim<KIND>::D;
+  SmallLayout<T, D> lay(N);
+  if (ws_bytes < lay.total || !ws) return KJX_ERR_WORKSPACE;
+  SmallArgs<T, D> a; memset(&a, 0, sizeof(a));
+  fill_prior<T, D>(a, m); bind_workspace<T, D>(a, lay, ws);
+  a.N = N; a.dt = dt; a.y = y; a.site_mean = site_mean; a.site_var = site_var;
+  a.filt_mean = filt_mean; a.filt_cov = filt_cov; a.filt_mean_in = filt_mean; a.filt_cov_in = filt_cov;
+  a.smooth_mean = post_mean; a.smooth_cov = post_var; a.new_site_mean = new_site_mean; a.new_site_var = new_site_var;
+  a.return_full = 0; a.update_sites = (flags & KJX_FLAG_NO_SITE_UPDATE) ? 0 : 1;
+  a.is_last_shard = 1; a.dt_next = T(0); a.nlml_out = nlml;
+  const bool have_sites = site_mean != nullptr;
+  a.gaussian_init = (!have_sites && gauss_ep(m)) ? 1 : 0;
+  if (N == 0) { cudaMemsetAsync(nlml, 0, sizeof(T), st); return KJX_OK; }
+  const bool seq = (flags & KJX_FLAG_SEQUENTIAL) != 0;
+  if (seq || needs_sequential_filter(m, have_sites)) {
+    // filter as one chain; freshly initialised sites land in new_site_* and are the smoother's "previous" sites
+    launch_set_prior_state<T, D>((T*)a.f_state_in, m, st);
+    const int init = (!have_sites && !a.gaussian_init) ? 1 : 0;
+    if (init) { a.out_site_mean = new_site_mean; a.out_site_var = new_site_var; }
+    filter_sequential_kernel<T, KIND><<<1, 32, 0, st>>>(a, init);
+    if (init) { a.site_mean = new_site_mean; a.site_var = new_site_var; a.out_site_mean = nullptr; a.out_site_var = nullptr; }
+    if (seq) {
+      smoother_sequential_kernel<T, KIND><<<1, 32, 0, st>>>(a);
+    } else {
+      smoother_reduce_kernel<T, KIND><<<(unsigned)a.nblocks, KJX_BLOCK, 0, st>>>(a);
+      a.nlml_out = nullptr;
+      smoother_blockscan_kernel<T, D><<<1, KJX_SCAN_BLOCK, 0, st>>>(a);
+      cudaMemsetAsync((void*)a.s_state_in, 0, (D + D * D) * sizeof(T), st);
+      small_smoother_apply<T, KIND>(m, a, st);
+    }
+  } else {
+    small_filter_scan<T, KIND>(m, N, a, true, nullptr, st);
+    smoother_blockscan_kernel<T, D><<<1, KJX_SCAN_BLOCK, 0, st>>>(a);   // also reduces nlml
+    cudaMemsetAsync((void*)a.s_state_in, 0, (D + D * D) * sizeof(T), st);
+    small_smoother_apply<T, KIND>(m, a, st);
+  }
+  KJX_CUDA_CHECK(cudaGetLastError());
+  return KJX_OK;
+}
+
+// ---- sharded halves ------------------------------------------------------------------------------
+template <typename T, int KIND>
+int small_filter_summary(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const uint8_t* mask,
+                         const T* site_mean, const T* site_var, T* summary_out, void* ws, size_t ws_bytes,
+                         cudaStream_t st) {
+  constexpr int D = BlockDim<KIND>::D;
+  SmallLayout<T, D> lay(N);
+  if (ws_bytes < lay.total || !ws) return KJX_ERR_WORKSPACE;
+  if (needs_sequential_filter(m, site_mean != nullptr)) return KJX_ERR_UNSUPPORTED;
+  SmallArgs<T, D> a; memset(&a, 0, sizeof(a));
+  fill_prior<T, D>(a, m); bind_workspace<T, D>(a, lay, ws);
+  a.N = N; a.dt = dt; a.y = y; a.mask = mask; a.site_mean = site_mean; a.site_var = site_var;
+  a.gaussian_init = (site_mean == nullptr) ? 1 : 0;
+  filter_reduce_kernel<T, KIND><<<(unsigned)a.nblocks, KJX_BLOCK, 0, st>>>(a);
+  filter_blockscan_kernel<T, D><<<1, KJX_SCAN_BLOCK, 0, st>>>(a);
+  copy_scalars_kernel<T><<<1, 64, 0, st>>>(summary_out, a.f_shard_total, (int)FSum<T, D>::NS);
+  KJX_CUDA_CHECK(cudaGetLastError());
+  return KJX_OK;
+}
+
+template <typename T, int KIND>
+int small_filter_apply(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const uint8_t* mask,
+                       const T* site_mean, const T* site_var, const T* state_in, T dt_next, int is_last,
+                       T* filt_mean, T* filt_cov, T* out_site_mean, T* out_site_var, T* ssum_out, T* nlml_partial,
+                       void* ws, size_t ws_bytes, cudaStream_t st) {
+  constexpr int D = BlockDim<KIND>::D;
+  SmallLayout<T, D> lay(N);
+  if (ws_bytes < lay.total || !ws) return KJX_ERR_WORKSPACE;
+  SmallArgs<T, D> a; memset(&a, 0, sizeof(a));
+  fill_prior<T, D>(a, m); bind_workspace<T, D>(a, lay, ws);
+  a.N = N; a.dt = dt; a.y = y; a.mask = mask; a.site_mean = site_mean; a.site_var = site_var;
+  a.gaussian_init = (site_mean == nullptr) ? 1 : 0;
+  a.filt_mean = filt_mean; a.filt_cov = filt_cov; a.out_site_mean = out_site_mean; a.out_site_var = out_site_var;
+  a.dt_next = dt_next; a.is_last_shard = is_last; a.nlml_out = nlml_partial;
+  copy_state_kernel<T, D><<<1, 32, 0, st>>>((T*)a.f_state_in, state_in);
+  if (gauss_ep(m)) filter_apply_kernel<T, KIND, true, true><<<(unsigned)a.nblocks, KJX_BLOCK, 0, st>>>(a);
+  else filter_apply_kernel<T, KIND, true, false><<<(unsigned)a.nblocks, KJX_BLOCK, 0, st>>>(a);
+  smoother_blockscan_kernel<T, D><<<1, KJX_SCAN_BLOCK, 0, st>>>(a);
+  copy_scalars_kernel<T><<<1, 64, 0, st>>>(ssum_out, a.s_shard_total, (int)SSum<T, D>::NS);
+  KJX_CUDA_CHECK(cudaGetLastError());
+  return KJX_OK;
+}
+
+template <typename T, int KIND>
+int small_smoother_apply_shard(const kjx_model_t* m, int64_t N, const T* dt, T dt_next, const T* filt_mean,
+                               const T* filt_cov, const T* y, const T* site_mean, const T* site_var,
+                               const T* state_in, int is_last, T* smooth_mean, T* smooth_cov, T* new_site_mean,
+                               T* new_site_var, void* ws, size_t ws_bytes, uint32_t flags, cudaStream_t st) {
+  constexpr int D = BlockDim<KIND>::D;
+  SmallLayout<T, D> lay(N);
+  if (ws_bytes < lay.total || !ws) return KJX_ERR_WORKSPACE;
+  SmallArgs<T, D> a; memset(&a, 0, sizeof(a));
+  fill_prior<T, D>(a, m); bind_workspace<T, D>(a, lay, ws);
+  a.N = N; a.dt = dt; a.y = y; a.site_mean = site_mean; a.site_var = site_var;
+  a.gaussian_init = (site_mean == nullptr) ? 1 : 0;
+  a.filt_mean_in = filt_mean; a.filt_cov_in = filt_cov;
+  a.smooth_mean = smooth_mean; a.smooth_cov = smooth_cov; a.new_site_mean = new_site_mean; a.new_site_var = new_site_var;
+  a.return_full = (flags & KJX_FLAG_RETURN_FULL) ? 1 : 0;
+  a.update_sites = (new_site_mean != nullptr && y != nullptr && !(flags & KJX_FLAG_NO_SITE_UPDATE)) ? 1 : 0;
+  a.dt_next = dt_next; a.is_last_shard = is_last;
+  if (state_in) copy_state_kernel<T, D><<<1, 32, 0, st>>>((T*)a.s_state_in, state_in);
+  else cudaMemsetAsync((void*)a.s_state_in, 0, (D + D * D) * sizeof(T), st);
+  small_smoother_apply<T, KIND>(m, a, st);
+  KJX_CUDA_CHECK(cudaGetLastError());
+  return KJX_OK;
+}
+
+// ---- host-side folds of gathered shard summaries (same math as the kernels, compiled for the host) ----
+template <int D>
+int fold_filter_host(const double* Pinf, const double* summaries, int rank, double* out) {
+  FiltState<double, D> x;
+  for (int i = 0; i < D; ++i) { x.m[i] = 0.0; for (int j = 0; j < D; ++j) x.P[i][j] = Pinf[i * D + j]; }
+  for (int r = 0; r < rank; ++r) {
+    FSum<double, D> s; fsum_unpack<double, D>(summaries + (size_t)r * FSum<double, D>::NS, s);
+    fsum_apply<double, D>(s, x);
+  }
+  for (int i = 0; i < D; ++i) out[i] = x.m[i];
+  for (int i = 0; i < D; ++i) for (int j = 0; j < D; ++j) out[D + i * D + j] = x.P[i][j];
+  return KJX_OK;
+}
+template <int D>
+int fold_smoother_host(const double* summaries, int world, int rank, double* out) {
+  FiltState<double, D> x;
+  for (int i = 0; i < D; ++i) { x.m[i] = 0.0; for (int j = 0; j < D; ++j) x.P[i][j] = 0.0; }
+  for (int r = world - 1; r > rank; --r) {
+    SSum<double, D> s; ssum_unpack<double, D>(summaries + (size_t)r * SSum<double, D>::NS, s);
+    ssum_apply<double, D>(s, x);
+  }
+  for (int i = 0; i < D; ++i) out[i] = x.m[i];
+  for (int i = 0; i < D; ++i) for (int j = 0; j < D; ++j) out[D + i * D + j] = x.P[i][j];
+  return KJX_OK;
+}
+
+template <int D>
+__global__ void fold_filter_kernel(StateArg<double, D> prior, const double* summaries, int64_t stride, int rank, double* out) {
+  if (threadIdx.x != 0) return;
+  FiltState<double, D> x;
+  for (int i = 0; i < D; ++i) { x.m[i] = prior.v[i]; for (int j = 0; j < D; ++j) x.P[i][j] = prior.v[D + i * D + j]; }
+  for (int r = 0; r < rank; ++r) {
+    FSum<double, D> s; fsum_unpack<double, D>(summaries + (size_t)r * stride, s);
+    fsum_apply<double, D>(s, x);
+  }
+  for (int i = 0; i < D; ++i) out[i] = x.m[i];
+  for (int i = 0; i < D; ++i) for (int j = 0; j < D; ++j) out[D + i * D + j] = x.P[i][j];
+}
+template <int D>
+__global__ void fold_smoother_kernel(const double* summaries, int64_t stride, int world, int rank, double* out) {
+  if (threadIdx.x != 0) return;
+  FiltState<double, D> x;
+  for (int i = 0; i < D; ++i) { x.m[i] = 0.0; for (int j = 0; j < D; ++j) x.P[i][j] = 0.0; }
+  for (int r = world - 1; r > rank; --r) {
+    SSum<double, D> s; ssum_unpack<double, D>(summaries + (size_t)r * stride, s);
+    ssum_apply<double, D>(s, x);
+  }
+  for (int i = 0; i < D; ++i) out[i] = x.m[i];
+  for (int i = 0; i < D; ++i) for (int j = 0; j < D; ++j) out[D + i * D + j] = x.P[i][j];
+}
+template <int D>
+int fold_filter_dev(const kjx_model_t* m, const double* summaries, int64_t stride, int rank, double* out, cudaStream_t st) {
+  StateArg<double, D> s;
+  for (int i = 0; i < D; ++i) s.v[i] = 0.0;
+  for (int i = 0; i < D * D; ++i) s.v[D + i] = m->Pinf[i];
+  fold_filter_kernel<D><<<1, 32, 0, st>>>(s, summaries, stride, rank, out);
+  return cudaGetLastError() == cudaSuccess ? KJX_OK : KJX_ERR_CUDA;
+}
+
+// ---- typed front ends shared by the _f64 / _f32 entry points ------------------------------------------
+template <typename T>
+int filter_T(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const uint8_t* mask, const T* site_mean,
+             const T* site_cov, T* filt_mean, T* filt_cov, T* out_site_mean, T* out_site_cov, T* nlml, void* ws,
+             size_t ws_bytes, uint32_t flags, kjx_stream_t stream) {
+  if (!model_basic_ok(m) || N < 0 || !dt || !y || !nlml) return KJX_ERR_INVALID_ARG;
+  if ((site_mean == nullptr) != (site_cov == nullptr)) return KJX_ERR_INVALID_ARG;
+  if ((filt_mean == nullptr) != (filt_cov == nullptr)) return KJX_ERR_INVALID_ARG;
+  if ((out_site_mean == nullptr) != (out_site_cov == nullptr)) return KJX_ERR_INVALID_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (small_kind(m)) {
+    case KJX_BLOCK_MATERN32: return small_filter<T, KJX_BLOCK_MATERN32>(m, N, dt, y, mask, site_mean, site_cov, filt_mean, filt_cov, out_site_mean, out_site_cov, nlml, ws, ws_bytes, flags, st);
+    case KJX_BLOCK_MATERN52: return small_filter<T, KJX_BLOCK_MATERN52>(m, N, dt, y, mask, site_mean, site_cov, filt_mean, filt_cov, out_site_mean, out_site_cov, nlml, ws, ws_bytes, flags, st);
+    default: return KJX_ERR_UNSUPPORTED;
+  }
+}
+
+template <typename T>
+int smoother_T(const kjx_model_t* m, int64_t N, const T* dt, const T* filt_mean, const T* filt_cov, const T* y,
+               const T* site_mean, const T* site_cov, T* smooth_mean, T* smooth_cov, T* new_site_mean,
+               T* new_site_cov, void* ws, size_t ws_bytes, uint32_t flags, kjx_stream_t stream) {
+  if (!model_basic_ok(m) || N < 0 || !dt || !filt_mean || !filt_cov) return KJX_ERR_INVALID_ARG;
+  if ((site_mean == nullptr) != (site_cov == nullptr)) return KJX_ERR_INVALID_ARG;
+  if ((smooth_mean == nullptr) != (smooth_cov == nullptr)) return KJX_ERR_INVALID_ARG;
+  if ((new_site_mean == nullptr) != (new_site_cov == nullptr)) return KJX_ERR_INVALID_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (small_kind(m)) {
+    case KJX_BLOCK_MATERN32: return small_smoother<T, KJX_BLOCK_MATERN32>(m, N, dt, filt_mean, filt_cov, y, site_mean, site_cov, smooth_mean, smooth_cov, new_site_mean, new_site_cov, ws, ws_bytes, flags, st);
+    case KJX_BLOCK_MATERN52: return small_smoother<T, KJX_BLOCK_MATERN52>(m, N, dt, filt_mean, filt_cov, y, site_mean, site_cov, smooth_mean, smooth_cov, new_site_mean, new_site_cov, ws, ws_bytes, flags, st);
+    default: return KJX_ERR_UNSUPPORTED;
+  }
+}
+
+template <typename T>
+int run_T(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const T* site_mean, const T* site_cov,
+          T* filt_mean, T* filt_cov, T* new_site_mean, T* new_site_cov, T* post_mean, T* post_var, T* nlml,
+          void* ws, size_t ws_bytes, uint32_t flags, kjx_stream_t stream) {
+  if (!model_basic_ok(m) || N < 0 || !dt || !y || !nlml || !filt_mean || !filt_cov) return KJX_ERR_INVALID_ARG;
+  if (!new_site_mean || !new_site_cov) return KJX_ERR_INVALID_ARG;
+  if ((site_mean == nullptr) != (site_cov == nullptr)) return KJX_ERR_INVALID_ARG;
+  if ((post_mean == nullptr) != (post_var == nullptr)) return KJX_ERR_INVALID_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (small_kind(m)) {
+    case KJX_BLOCK_MATERN32: return small_run<T, KJX_BLOCK_MATERN32>(m, N, dt, y, site_mean, site_cov, filt_mean, filt_cov, new_site_mean, new_site_cov, post_mean, post_var, nlml, ws, ws_bytes, flags, st);
+    case KJX_BLOCK_MATERN52: return small_run<T, KJX_BLOCK_MATERN52>(m, N, dt, y, site_mean, site_cov, filt_mean, filt_cov, new_site_mean, new_site_cov, post_mean, post_var, nlml, ws, ws_bytes, flags, st);
+    default: return KJX_ERR_UNSUPPORTED;
+  }
+}
+
+template <typename T>
+int site_update_T(const kjx_model_t* m, int64_t N, const T* y, const T* post_mean, const T* post_var,
+                  const T* sprev_mean, const T* sprev_var, T* log_lik, T* site_mean, T* site_var, kjx_stream_t stream) {
+  if (!model_basic_ok(m) || N < 0 || !y || !post_mean || !post_var) return KJX_ERR_INVALID_ARG;
+  if (m->func_dim != 1) return KJX_ERR_UNSUPPORTED;
+  if ((sprev_mean == nullptr) != (sprev_var == nullptr)) return KJX_ERR_INVALID_ARG;
+  if ((site_mean == nullptr) != (site_var == nullptr)) return KJX_ERR_INVALID_ARG;
+  if (N == 0) return KJX_OK;
+  const int threads = 128;
+  const int64_t blocks = (N + threads - 1) / threads;
+  site_update_kernel<T><<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(make_site(m), N, y, post_mean, post_var,
+                                                                                 sprev_mean, sprev_var, log_lik, site_mean, site_var);
+  KJX_CUDA_CHECK(cudaGetLastError());
+  return KJX_OK;
+}
+
+template <typename T>
+int discretise_T(const kjx_model_t* m, int64_t N, const T* dt, T* A, T* Q, void* /*unused*/, kjx_stream_t stream) {
+  if (!model_basic_ok(m) || N < 0 || !dt || !A) return KJX_ERR_INVALID_ARG;
+  if (N == 0) return KJX_OK;
+  DiscArgs da; memset(&da, 0, sizeof(da));
+  da.d = m->state_dim; da.n_blocks = m->n_blocks;
+  for (int b = 0; b < m->n_blocks; ++b) da.blocks[b] = m->blocks[b];
+  // Pinf is a host pointer: stage it into a small device buffer owned by this call's stream order
+  double* pinf_dev = nullptr;
+  if (Q) {
+    KJX_CUDA_CHECK(cudaMallocAsync((void**)&pinf_dev, sizeof(double) * m->state_dim * m->state_dim, (cudaStream_t)stream));
+    KJX_CUDA_CHECK(cudaMemcpyAsync(pinf_dev, m->Pinf, sizeof(double) * m->state_dim * m->state_dim, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  }
+  const int threads = 128, nw = threads / 32;
+  const int64_t blocks = (N + nw - 1) / nw;
+  const size_t smem = (size_t)nw * m->state_dim * (4 * sizeof(T) + sizeof(int));
+  if (smem > 48 * 1024) return KJX_ERR_UNSUPPORTED;
+  discretise_kernel<T><<<(unsigned)std::min<int64_t>(blocks, 148 * 16), threads, smem, (cudaStream_t)stream>>>(da, N, dt, A, Q, pinf_dev);
+  if (pinf_dev) KJX_CUDA_CHECK(cudaFreeAsync(pinf_dev, (cudaStream_t)stream));
+  KJX_CUDA_CHECK(cudaGetLastError());
+  return KJX_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int kjx_version(void) { return 100; }
+
+const char* kjx_status_string(int status) {
+  switch (status) {
+    case KJX_OK: return "ok";
+    case KJX_ERR_INVALID_ARG: return "invalid argument";
+    case KJX_ERR_UNSUPPORTED: return "unsupported model for this build";
+    case KJX_ERR_WORKSPACE: return "workspace too small";
+    case KJX_ERR_CUDA: return "CUDA error";
+    default: return "unknown status";
+  }
+}
+
+int kjx_workspace_bytes(const kjx_model_t* m, int64_t N, int dtype_bytes, size_t* bytes) {
+  if (!model_basic_ok(m) || N < 0 || !bytes || (dtype_bytes != 4 && dtype_bytes != 8)) return KJX_ERR_INVALID_ARG;
+  const int kind = small_kind(m);
+  size_t total = 0;
+  if (kind == KJX_BLOCK_MATERN32) total = dtype_bytes == 8 ? SmallLayout<double, 2>(N).total : SmallLayout<float, 2>(N).total;
+  else if (kind == KJX_BLOCK_MATERN52) total = dtype_bytes == 8 ? SmallLayout<double, 3>(N).total : SmallLayout<float, 3>(N).total;
+  else return KJX_ERR_UNSUPPORTED;
+  *bytes = total;
+  return KJX_OK;
+}
+
+int kjx_filter_f64(const kjx_model_t* m, int64_t N, const double* dt, const double* y, const uint8_t* mask,
+                   const double* site_mean, const double* site_cov, double* filt_mean, double* filt_cov,
+                   double* out_site_mean, double* out_site_cov, double* nlml, void* ws, size_t ws_bytes,
+                   uint32_t flags, kjx_stream_t stream) {
+  return filter_T<double>(m, N, dt, y, mask, site_mean, site_cov, filt_mean, filt_cov, out_site_mean, out_site_cov, nlml, ws, ws_bytes, flags, stream);
+}
+int kjx_filter_f32(const kjx_model_t* m, int64_t N, const float* dt, const float* y, const uint8_t* mask,
+                   const float* site_mean, const float* site_cov, float* filt_mean, float* filt_cov,
+                   float* out_site_mean, float* out_site_cov, float* nlml, void* ws, size_t ws_bytes,
+                   uint32_t flags, kjx_stream_t stream) {
+  return filter_T<float>(m, N, dt, y, mask, site_mean, site_cov, filt_mean, filt_cov, out_site_mean, out_site_cov, nlml, ws, ws_bytes, flags, stream);
+}
+
+int kjx_smoother_f64(const kjx_model_t* m, int64_t N, const double* dt, const double* filt_mean, const double* filt_cov,
+                     const double* y, const double* site_mean, const double* site_cov, double* smooth_mean,
+                     double* smooth_cov, double* new_site_mean, double* new_site_cov, void* ws, size_t ws_bytes,
+                     uint32_t flags, kjx_stream_t stream) {
+  return smoother_T<double>(m, N, dt, filt_mean, filt_cov, y, site_mean, site_cov, smooth_mean, smooth_cov, new_site_mean, new_site_cov, ws, ws_bytes, flags, stream);
+}
+int kjx_smoother_f32(const kjx_model_t* m, int64_t N, const float* dt, const float* filt_mean, const float* filt_cov,
+                     const float* y, const float* site_mean, const float* site_cov, float* smooth_mean,
+                     float* smooth_cov, float* new_site_mean, float* new_site_cov, void* ws, size_t ws_bytes,
+                     uint32_t flags, kjx_stream_t stream) {
+  return smoother_T<float>(m, N, dt, filt_mean, filt_cov, y, site_mean, site_cov, smooth_mean, smooth_cov, new_site_mean, new_site_cov, ws, ws_bytes, flags, stream);
+}
+
+int kjx_run_f64(const kjx_model_t* m, int64_t N, const double* dt, const double* y, const double* site_mean,
+                const double* site_cov, double* filt_mean, double* filt_cov, double* new_site_mean,
+                double* new_site_cov, double* post_mean, double* post_var, double* nlml, void* ws, size_t ws_bytes,
+                uint32_t flags, kjx_stream_t stream) {
+  return run_T<double>(m, N, dt, y, site_mean, site_cov, filt_mean, filt_cov, new_site_mean, new_site_cov, post_mean, post_var, nlml, ws, ws_bytes, flags, stream);
+}
+int kjx_run_f32(const kjx_model_t* m, int64_t N, const float* dt, const float* y, const float* site_mean,
+                const float* site_cov, float* filt_mean, float* filt_cov, float* new_site_mean, float* new_site_cov,
+                float* post_mean, float* post_var, float* nlml, void* ws, size_t ws_bytes, uint32_t flags,
+                kjx_stream_t stream) {
+  return run_T<float>(m, N, dt, y, site_mean, site_cov, filt_mean, filt_cov, new_site_mean, new_site_cov, post_mean, post_var, nlml, ws, ws_bytes, flags, stream);
+}
+
+int kjx_site_update_f64(const kjx_model_t* m, int64_t N, const double* y, const double* post_mean, const double* post_var,
+                        const double* site_mean_prev, const double* site_var_prev, double* log_lik, double* site_mean,
+                        double* site_var, kjx_stream_t stream) {
+  return site_update_T<double>(m, N, y, post_mean, post_var, site_mean_prev, site_var_prev, log_lik, site_mean, site_var, stream);
+}
+int kjx_site_update_f32(const kjx_model_t* m, int64_t N, const float* y, const float* post_mean, const float* post_var,
+                        const float* site_mean_prev, const float* site_var_prev, float* log_lik, float* site_mean,
+                        float* site_var, kjx_stream_t stream) {
+  return site_update_T<float>(m, N, y, post_mean, post_var, site_mean_prev, site_var_prev, log_lik, site_mean, site_var, stream);
+}
+
+int kjx_discretise_f64(const kjx_model_t* m, int64_t N, const double* dt, double* A, double* Q, kjx_stream_t stream) {
+  return discretise_T<double>(m, N, dt, A, Q, nullptr, stream);
+}
+int kjx_discretise_f32(const kjx_model_t* m, int64_t N, const float* dt, float* A, float* Q, kjx_stream_t stream) {
+  return discretise_T<float>(m, N, dt, A, Q, nullptr, stream);
+}
+
+size_t kjx_filter_summary_doubles(int32_t d) { return (size_t)(d * d + d + d * (d + 1) / 2 + d + d * (d + 1) / 2); }
+size_t kjx_smoother_summary_doubles(int32_t d) { return (size_t)(d * d + d + d * (d + 1) / 2); }
+
+int kjx_filter_summary_f64(const kjx_model_t* m, int64_t N, const double* dt, const double* y, const uint8_t* mask,
+                           const double* site_mean, const double* site_cov, double* summary_out, void* ws,
+                           size_t ws_bytes, kjx_stream_t stream) {
+  if (!model_basic_ok(m) || N <= 0 || !dt || !y || !summary_out) return KJX_ERR_INVALID_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (small_kind(m)) {
+    case KJX_BLOCK_MATERN32: return small_filter_summary<double, KJX_BLOCK_MATERN32>(m, N, dt, y, mask, site_mean, site_cov, summary_out, ws, ws_bytes, st);
+    case KJX_BLOCK_MATERN52: return small_filter_summary<double, KJX_BLOCK_MATERN52>(m, N, dt, y, mask, site_mean, site_cov, summary_out, ws, ws_bytes, st);
+    default: return KJX_ERR_UNSUPPORTED;
+  }
+}
+
+int kjx_filter_apply_f64(const kjx_model_t* m, int64_t N, const double* dt, const double* y, const uint8_t* mask,
+                         const double* site_mean, const double* site_cov, const double* state_in, double dt_next,
+                         int32_t is_last_shard, double* filt_mean, double* filt_cov, double* out_site_mean,
+                         double* out_site_cov, double* smoother_summary_out, double* nlml_partial, void* ws,
+                         size_t ws_bytes, kjx_stream_t stream) {
+  if (!model_basic_ok(m) || N <= 0 || !dt || !y || !state_in || !filt_mean || !filt_cov || !smoother_summary_out || !nlml_partial)
+    return KJX_ERR_INVALID_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (small_kind(m)) {
+    case KJX_BLOCK_MATERN32: return small_filter_apply<double, KJX_BLOCK_MATERN32>(m, N, dt, y, mask, site_mean, site_cov, state_in, dt_next, is_last_shard, filt_mean, filt_cov, out_site_mean, out_site_cov, smoother_summary_out, nlml_partial, ws, ws_bytes, st);
+    case KJX_BLOCK_MATERN52: return small_filter_apply<double, KJX_BLOCK_MATERN52>(m, N, dt, y, mask, site_mean, site_cov, state_in, dt_next, is_last_shard, filt_mean, filt_cov, out_site_mean, out_site_cov, smoother_summary_out, nlml_partial, ws, ws_bytes, st);
+    default: return KJX_ERR_UNSUPPORTED;
+  }
+}
+
+int kjx_smoother_apply_f64(const kjx_model_t* m, int64_t N, const double* dt, double dt_next, const double* filt_mean,
+                           const double* filt_cov, const double* y, const double* site_mean, const double* site_cov,
+                           const double* state_in, int32_t is_last_shard, double* smooth_mean, double* smooth_cov,
+                           double* new_site_mean, double* new_site_cov, void* ws, size_t ws_bytes, uint32_t flags,
+                           kjx_stream_t stream) {
+  if (!model_basic_ok(m) || N <= 0 || !dt || !filt_mean || !filt_cov) return KJX_ERR_INVALID_ARG;
+  if (!is_last_shard && !state_in) return KJX_ERR_INVALID_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (small_kind(m)) {
+    case KJX_BLOCK_MATERN32: return small_smoother_apply_shard<double, KJX_BLOCK_MATERN32>(m, N, dt, dt_next, filt_mean, filt_cov, y, site_mean, site_cov, state_in, is_last_shard, smooth_mean, smooth_cov, new_site_mean, new_site_cov, ws, ws_bytes, flags, st);
+    case KJX_BLOCK_MATERN52: return small_smoother_apply_shard<double, KJX_BLOCK_MATERN52>(m, N, dt, dt_next, filt_mean, filt_cov, y, site_mean, site_cov, state_in, is_last_shard, smooth_mean, smooth_cov, new_site_mean, new_site_cov, ws, ws_bytes, flags, st);
+    default: return KJX_ERR_UNSUPPORTED;
+  }
+}
+
+int kjx_fold_filter_summaries_host(int32_t d, const double* Pinf_host, const double* summaries_host, int32_t rank,
+                                   double* state_out_host) {
+  if (!Pinf_host || !summaries_host || !state_out_host || rank < 0) return KJX_ERR_INVALID_ARG;
+  if (d == 2) return fold_filter_host<2>(Pinf_host, summaries_host, rank, state_out_host);
+  if (d == 3) return fold_filter_host<3>(Pinf_host, summaries_host, rank, state_out_host);
+  return KJX_ERR_UNSUPPORTED;
+}
+int kjx_fold_smoother_summaries_host(int32_t d, const double* summaries_host, int32_t world, int32_t rank,
+                                     double* state_out_host) {
+  if (!summaries_host || !state_out_host || rank < 0 || world <= rank) return KJX_ERR_INVALID_ARG;
+  if (d == 2) return fold_smoother_host<2>(summaries_host, world, rank, state_out_host);
+  if (d == 3) return fold_smoother_host<3>(summaries_host, world, rank, state_out_host);
+  return KJX_ERR_UNSUPPORTED;
+}
+
+int kjx_fold_filter_summaries_f64(const kjx_model_t* m, const double* summaries, int64_t stride, int32_t rank,
+                                  double* state_out, kjx_stream_t stream) {
+  if (!model_basic_ok(m) || !summaries || !state_out || rank < 0) return KJX_ERR_INVALID_ARG;
+  if (stride < (int64_t)kjx_filter_summary_doubles(m->state_dim)) return KJX_ERR_INVALID_ARG;
+  if (m->state_dim == 2) return fold_filter_dev<2>(m, summaries, stride, rank, state_out, (cudaStream_t)stream);
+  if (m->state_dim == 3) return fold_filter_dev<3>(m, summaries, stride, rank, state_out, (cudaStream_t)stream);
+  return KJX_ERR_UNSUPPORTED;
+}
+int kjx_fold_smoother_summaries_f64(const kjx_model_t* m, const double* summaries, int64_t stride, int32_t world,
+                                    int32_t rank, double* state_out, kjx_stream_t stream) {
+  if (!model_basic_ok(m) || !summaries || !state_out || rank < 0 || world <= rank) return KJX_ERR_INVALID_ARG;
+  if (stride < (int64_t)kjx_smoother_summary_doubles(m->state_dim)) return KJX_ERR_INVALID_ARG;
+  if (m->state_dim == 2) fold_smoother_kernel<2><<<1, 32, 0, (cudaStream_t)stream>>>(summaries, stride, world, rank, state_out);
+  else if (m->state_dim == 3) fold_smoother_kernel<3><<<1, 32, 0, (cudaStream_t)stream>>>(summaries, stride, world, rank, state_out);
+  else return KJX_ERR_UNSUPPORTED;
+  return cudaGetLastError() == cudaSuccess ? KJX_OK : KJX_ERR_CUDA;
+}
+
+int kjx_run_host_scratch_bytes(const kjx_model_t* m, int64_t N, int dtype_bytes, size_t* bytes) {
+  size_t ws = 0;
+  int rc = kjx_workspace_bytes(m, N, dtype_bytes, &ws);
+  if (rc != KJX_OK) return rc;
+  const size_t d = (size_t)m->state_dim, n = (size_t)std::max<int64_t>(N, 1);
+  // dt, y, site_mean, site_var, new_site_mean, new_site_var, post_mean, post_var (8 N) + filter output + nlml
+  *bytes = round_up(ws, 256) + 10 * round_up(n * dtype_bytes, 256) + round_up(n * d * dtype_bytes, 256) +
+           round_up(n * d * d * dtype_bytes, 256) + 256;
+  return KJX_OK;
+}
+
+int kjx_run_host_f64(const kjx_model_t* m, int64_t N, const double* dt_host, const double* y_host,
+                     const double* site_mean_host, const double* site_cov_host, double* new_site_mean_host,
+                     double* new_site_cov_host, double* post_mean_host, double* post_var_host, double* nlml_host,
+                     void* dev_scratch, size_t dev_scratch_bytes, uint32_t flags, kjx_stream_t stream) {
+  if (!model_basic_ok(m) || N <= 0 || !dt_host || !y_host || !new_site_mean_host || !new_site_cov_host || !nlml_host || !dev_scratch)
+    return KJX_ERR_INVALID_ARG;
+  if ((site_mean_host == nullptr) != (site_cov_host == nullptr)) return KJX_ERR_INVALID_ARG;
+  if ((post_mean_host == nullptr) != (post_var_host == nullptr)) return KJX_ERR_INVALID_ARG;
+  size_t need = 0, ws_bytes = 0;
+  int rc = kjx_run_host_scratch_bytes(m, N, 8, &need);
+  if (rc != KJX_OK) return rc;
+  if (dev_scratch_bytes < need) return KJX_ERR_WORKSPACE;
+  kjx_workspace_bytes(m, N, 8, &ws_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t d = (size_t)m->state_dim, n = (size_t)N, nb = round_up(n * 8, 256);
+  char* p = (char*)dev_scratch;
+  auto take = [&](size_t b) { char* r = p; p += round_up(b, 256); return r; };
+  void* ws = take(ws_bytes);
+  double *dt = (double*)take(nb), *y = (double*)take(nb), *sm = (double*)take(nb), *sv = (double*)take(nb);
+  double *nsm = (double*)take(nb), *nsv = (double*)take(nb), *pm = (double*)take(nb), *pv = (double*)take(nb);
+  double *fm = (double*)take(n * d * 8), *fP = (double*)take(n * d * d * 8), *nlml = (double*)take(8);
+  KJX_CUDA_CHECK(cudaMemcpyAsync(dt, dt_host, n * 8, cudaMemcpyHostToDevice, st));
+  KJX_CUDA_CHECK(cudaMemcpyAsync(y, y_host, n * 8, cudaMemcpyHostToDevice, st));
+  if (site_mean_host) {
+    KJX_CUDA_CHECK(cudaMemcpyAsync(sm, site_mean_host, n * 8, cudaMemcpyHostToDevice, st));
+    KJX_CUDA_CHECK(cudaMemcpyAsync(sv, site_cov_host, n * 8, cudaMemcpyHostToDevice, st));
+  }
+  rc = kjx_run_f64(m, N, dt, y, site_mean_host ? sm : nullptr, site_mean_host ? sv : nullptr, fm, fP, nsm, nsv,
+                   post_mean_host ? pm : nullptr, post_mean_host ? pv : nullptr, nlml, ws, ws_bytes, flags, stream);
+  if (rc != KJX_OK) return rc;
+  KJX_CUDA_CHECK(cudaMemcpyAsync(new_site_mean_host, nsm, n * 8, cudaMemcpyDeviceToHost, st));
+  KJX_CUDA_CHECK(cudaMemcpyAsync(new_site_cov_host, nsv, n * 8, cudaMemcpyDeviceToHost, st));
+  if (post_mean_host) {
+    KJX_CUDA_CHECK(cudaMemcpyAsync(post_mean_host, pm, n * 8, cudaMemcpyDeviceToHost, st));
+    KJX_CUDA_CHECK(cudaMemcpyAsync(post_var_host, pv, n * 8, cudaMemcpyDeviceToHost, st));
+  }
+  KJX_CUDA_CHECK(cudaMemcpyAsync(nlml_host, nlml, 8, cudaMemcpyDeviceToHost, st));
+  KJX_CUDA_CHECK(cudaStreamSynchronize(st));
+  return KJX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,95 @@
+"""Likelihood models — host-side mirror of /root/reference/kalmanjax/likelihoods.py for the likelihoods
+named by BASELINE.json (Gaussian 331-404, Bernoulli probit/logit 407-548, Poisson 551-644).
+
+The classes only *describe* the likelihood (kind + link + hyperparameter, same constructor arguments and
+`hyp` convention as the reference); the moment primitives themselves (moment_match, statistical linear
+regression, variational expectation, analytical linearisation) are evaluated on the GPU inside the
+filter / smoother / site-update kernels (csrc/kjx_sites.cuh).
+"""
+import numpy as np
+
+from . import _lib
+from .utils import softplus, softplus_inv
+
+
+class Likelihood(object):
+    """likelihoods.py:20-47."""
+    kjx_code = None
+
+    def __init__(self, hyp=None):
+        hyp = [] if hyp is None else hyp
+        self.hyp = softplus_inv(np.array(hyp, dtype=np.float64))
+
+    def lik_hyp(self, hyp=None):
+        """already-transformed hyperparameter handed to the kernels (0 when the likelihood has none)."""
+        h = softplus(self.hyp) if hyp is None else np.asarray(hyp, dtype=np.float64)
+        return float(np.reshape(h, -1)[0]) if np.size(h) else 0.0
+
+    def moment_match(self, y, m, v, hyp=None, power=1.0, cubature_func=None):
+        """(log Z, site_mean, site_var) per entry of the batch, on the GPU (likelihoods.py:122-192).
+        cubature_func=None means 20-point Gauss-Hermite, like likelihoods.py:141-142."""
+        from .approximate_inference import ExpectationPropagation
+        from .sde_gp import site_update
+        rule = ExpectationPropagation(power=power)
+        if cubature_func is not None:
+            rule.cubature_func = cubature_func
+        return site_update(self, rule, y, m, v, hyp, None, force_power=power)
+
+
+class Gaussian(Likelihood):
+    """likelihoods.py:331-404."""
+    kjx_code = _lib.LIK_GAUSSIAN
+
+    def __init__(self, variance=0.1):
+        super().__init__(hyp=variance)
+        self.name = 'Gaussian'
+
+    @property
+    def variance(self):
+        return softplus(self.hyp)
+
+
+class Bernoulli(Likelihood):
+    """likelihoods.py:407-518."""
+    def __init__(self, link):
+        super().__init__(hyp=None)
+        if link == 'logit':
+            self.kjx_code = _lib.LIK_BERNOULLI_LOGIT
+        elif link == 'probit':
+            self.kjx_code = _lib.LIK_BERNOULLI_PROBIT
+        else:
+            raise NotImplementedError('link function not implemented')
+        self.link = link
+        self.name = 'Bernoulli'
+
+
+class Probit(Bernoulli):
+    def __init__(self):
+        super().__init__(link='probit')
+
+
+class Erf(Probit):
+    pass
+
+
+class Logit(Bernoulli):
+    def __init__(self):
+        super().__init__(link='logit')
+
+
+class Logistic(Logit):
+    pass
+
+
+class Poisson(Likelihood):
+    """likelihoods.py:551-644."""
+    def __init__(self, link='exp'):
+        super().__init__(hyp=None)
+        if link == 'exp':
+            self.kjx_code = _lib.LIK_POISSON_EXP
+        elif link == 'logistic':
+            self.kjx_code = _lib.LIK_POISSON_LOGISTIC
+        else:
+            raise NotImplementedError('link function not implemented')
+        self.link = link
+        self.name = 'Poisson'

@@ -1,0 +1,104 @@
+"""Time-sharded filter / smoother iteration: one contiguous block of time steps per GPU (one process per
+GPU), two fixed-size all-gathers per iteration:
+
+    local filter summary (A,b,C,eta,J)  --all-gather-->  fold ranks < me  -> filtered state entering my shard
+    local filter apply (+ smoother fold) -> local smoother summary (E,g,L) + partial nlml
+                                        --all-gather-->  fold ranks > me  -> smoothed state entering from the right
+    local smoother apply + site update
+
+No bulk data ever crosses NVLink: the payloads are 28 and 19 doubles per rank at d = 3.  With world == 1
+the same three library calls run without any collective.  The reference has no counterpart (it is a
+single sequential loop, sde_gp.py:271,349).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .sde_gp import _Model, _workspace
+
+
+class ShardedIteration(object):
+    """Holds one rank's shard of (dt, y, sites) resident in HBM and runs run()-style iterations on it.
+
+    gather(t) must return the all-gathered [world, t.numel()] tensor on the same device
+    (torch.distributed.all_gather_into_tensor); it is None for world == 1.
+    """
+    def __init__(self, prior, likelihood, sites, dt_shard, y_shard, dt_next, rank, world, device, gather=None,
+                 site_mean=None, site_var=None):
+        self.model = _Model(prior, likelihood, sites)
+        self.rank, self.world, self.device, self.gather = rank, world, torch.device(device), gather
+        self.dt = torch.as_tensor(dt_shard, dtype=torch.float64, device=self.device).contiguous()
+        self.y = torch.as_tensor(y_shard, dtype=torch.float64, device=self.device).contiguous().reshape(-1)
+        self.N = self.dt.numel()
+        self.dt_next = float(dt_next)
+        d = self.model.state_dim
+        self.d = d
+        z = lambda *s: torch.empty(*s, dtype=torch.float64, device=self.device)  # noqa: E731
+        self.site_mean = None if site_mean is None else torch.as_tensor(site_mean, dtype=torch.float64, device=self.device).contiguous()
+        self.site_var = None if site_var is None else torch.as_tensor(site_var, dtype=torch.float64, device=self.device).contiguous()
+        self.new_site_mean, self.new_site_var = z(self.N), z(self.N)
+        self.filt_mean, self.filt_cov = z(self.N, d), z(self.N, d, d)
+        self.post_mean, self.post_var = z(self.N), z(self.N)
+        L = _lib.lib()
+        self.fns, self.sns = int(L.kjx_filter_summary_doubles(d)), int(L.kjx_smoother_summary_doubles(d))
+        self.fmsg = torch.zeros(self.fns, dtype=torch.float64, device=self.device)
+        self.smsg = torch.zeros(self.sns + 1, dtype=torch.float64, device=self.device)   # + partial nlml
+        self.f_state, self.s_state = z(d + d * d), z(d + d * d)
+        self.ws, _ = _workspace(self.model, self.N, torch.float64, self.device)
+        self.nlml = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self.launches_per_iteration = 3 + 1 + 4 + 1 + 2   # see bench.py / DESIGN.md "kernel list"
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def iteration(self, update_sites=True, events=None):
+        """One filter -> smoother -> site-update pass over this shard.  `events`: optional list of 4
+        torch.cuda.Event recorded at the phase boundaries (summary | filter apply | smoother apply)."""
+        L, m, st = _lib.lib(), self.model.ref(), self._stream()
+        N, p = C.c_int64(self.N), _lib.ptr
+        last = 1 if self.rank == self.world - 1 else 0
+        if events:
+            events[0].record()
+        _lib.check(L.kjx_filter_summary_f64(m, N, p(self.dt), p(self.y), None, p(self.site_mean), p(self.site_var),
+                                            p(self.fmsg), p(self.ws), C.c_size_t(self.ws.numel()), st), "kjx_filter_summary")
+        allf = self.gather(self.fmsg) if self.gather else self.fmsg.reshape(1, -1)
+        _lib.check(L.kjx_fold_filter_summaries_f64(m, p(allf), C.c_int64(allf.shape[1]), self.rank, p(self.f_state), st),
+                   "kjx_fold_filter_summaries")
+        if events:
+            events[1].record()
+        _lib.check(L.kjx_filter_apply_f64(m, N, p(self.dt), p(self.y), None, p(self.site_mean), p(self.site_var),
+                                          p(self.f_state), C.c_double(self.dt_next), last, p(self.filt_mean),
+                                          p(self.filt_cov), None, None, p(self.smsg), p(self.smsg[self.sns:]),
+                                          p(self.ws), C.c_size_t(self.ws.numel()), st), "kjx_filter_apply")
+        alls = self.gather(self.smsg) if self.gather else self.smsg.reshape(1, -1)
+        _lib.check(L.kjx_fold_smoother_summaries_f64(m, p(alls), C.c_int64(alls.shape[1]), self.world, self.rank,
+                                                     p(self.s_state), st), "kjx_fold_smoother_summaries")
+        if events:
+            events[2].record()
+        flags = 0 if update_sites else _lib.FLAG_NO_SITE_UPDATE
+        _lib.check(L.kjx_smoother_apply_f64(m, N, p(self.dt), C.c_double(self.dt_next), p(self.filt_mean), p(self.filt_cov),
+                                            p(self.y), p(self.site_mean), p(self.site_var), p(self.s_state), last,
+                                            p(self.post_mean), p(self.post_var), p(self.new_site_mean), p(self.new_site_var),
+                                            p(self.ws), C.c_size_t(self.ws.numel()), C.c_uint32(flags), st), "kjx_smoother_apply")
+        if events:
+            events[3].record()
+        self.nlml = alls[:, self.sns].sum()       # partial nlml of every shard rode along in the second gather
+        if update_sites:
+            if self.site_mean is None:
+                self.site_mean, self.site_var = torch.empty_like(self.new_site_mean), torch.empty_like(self.new_site_var)
+            self.site_mean, self.new_site_mean = self.new_site_mean, self.site_mean
+            self.site_var, self.new_site_var = self.new_site_var, self.site_var
+        return self.nlml
+
+
+def split_series(dt, y, world):
+    """Contiguous time blocks: rank g owns steps [g N / G, (g+1) N / G); also dt of the next shard's first step."""
+    N = len(dt)
+    bounds = [(g * N) // world for g in range(world + 1)]
+    shards = []
+    for g in range(world):
+        lo, hi = bounds[g], bounds[g + 1]
+        shards.append((np.asarray(dt[lo:hi]), np.asarray(y[lo:hi]), float(dt[hi]) if hi < N else 0.0, lo, hi))
+    return shards

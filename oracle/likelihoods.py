@@ -142,11 +142,13 @@ class Gaussian(Likelihood):
         with np.errstate(all="ignore"):
             lZ = (- (y - m) ** 2 / (self.hyp + v) / 2
                   - np.log(np.maximum(2 * pi * (self.hyp + v), 1e-10)) / 2)
-        return lZ, y + 0.0 * m, self.hyp + 0.0 * m
+        # site = (y, sigma^2) whatever the cavity is, even a NaN one (utils.py:241-244)
+        return lZ, np.broadcast_to(y, lZ.shape).copy(), np.full(lZ.shape, self.hyp)
 
     def analytical_linearisation(self, m):
         # base class jacrev of f + chol(hyp) s (likelihoods.py:250-273): exact derivatives of a linear map
-        return 1.0 + 0.0 * np.asarray(m, dtype=float), np.sqrt(self.hyp) + 0.0 * np.asarray(m, dtype=float)
+        m = np.asarray(m, dtype=float)
+        return np.ones(m.shape), np.full(m.shape, np.sqrt(self.hyp))
 
 
 class Bernoulli(Likelihood):

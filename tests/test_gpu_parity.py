@@ -1,0 +1,312 @@
+"""Parity of the CUDA path (through the C ABI / SDEGP mirror) with the oracle and with fixtures recorded
+from the unmodified reference.  fp64 tolerance 1e-9 relative (BASELINE.json north_star), fp32 1e-4 on the
+benchmark's dt/lengthscale ~ 0.02 regime."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from golden_cases import CASES, KEEP_EVERY
+from golden_util import load, build_model, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL64 = 1e-9
+TOL32 = 1e-4
+
+
+def _kjx():
+    import kalman_jax_b200 as kjx
+    return kjx
+
+
+def _np(x):
+    return x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+
+
+def synth(N, seed=12345):
+    """the regression-notebook regime, mean spacing 0.1 and lengthscale 5."""
+    rng = np.random.default_rng(seed)
+    dt = rng.uniform(0.05, 0.15, N)
+    dt[0] = 0.0
+    t = np.cumsum(dt)
+    y = np.cos(0.04 * t + 0.33 * np.pi) * np.sin(0.2 * t) + np.sqrt(0.15) * rng.standard_normal(N)
+    return t, y
+
+
+SMALL_PRIORS = ("Matern32", "Matern52")
+
+
+def _supported(name):
+    return CASES[name][1][0] in SMALL_PRIORS
+
+
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", sorted(n for n in CASES if _supported(n)))
+def test_golden_cases_through_the_cuda_path(name):
+    """What SDEGP.run() does, replayed on the GPU, against the reference's own recorded outputs."""
+    kjx = _kjx()
+    g = load(name)
+    model, iters = build_model(name, g, kjx.priors, kjx.likelihoods, kjx.approximate_inference, kjx.SDEGP)
+    ke = KEEP_EVERY.get(CASES[name][0], 1)
+    params = model._params(None)
+    for it in range(iters):
+        nlml, (fm, fP, sites) = model.kalman_filter(model.y, model.dt, params, True, None, model.sites.site_params, model.r)
+        model.sites.site_params = sites
+        sites_s, sm, sc = model.rauch_tung_striebel_smoother(params, fm, fP, model.dt, True, False, model.y, sites, model.r)
+        model.sites.site_params = sites_s
+        pre = "it%d_" % it
+        assert abs(float(nlml) - g[pre + "nlml"]) <= TOL64 * abs(g[pre + "nlml"]), (it, float(nlml), g[pre + "nlml"])
+        assert rel_err(_np(fm)[::ke], g[pre + "filter_mean"]) < TOL64
+        assert rel_err(_np(fP)[::ke], g[pre + "filter_cov"]) < TOL64
+        assert rel_err(_np(sites[0]), g[pre + "site_mean_filter"]) < TOL64
+        assert rel_err(_np(sites[1]), g[pre + "site_cov_filter"]) < TOL64
+        assert rel_err(_np(sm), g[pre + "smoothed_mean"]) < TOL64
+        assert rel_err(_np(sc), g[pre + "smoothed_cov"]) < TOL64
+        assert rel_err(_np(sites_s[0]), g[pre + "site_mean"]) < TOL64
+        assert rel_err(_np(sites_s[1]), g[pre + "site_cov"]) < TOL64
+    if "predict_mean" in g:
+        pm, pv = model.predict(t=g["t_test"])
+        assert rel_err(_np(pm), g["predict_mean"]) < TOL64
+        assert rel_err(_np(pv), g["predict_var"]) < TOL64
+    if "nlpd" in g:
+        nlpd = model.negative_log_predictive_density(t=g["t_test"], y=g["y_test"])
+        assert abs(nlpd - g["nlpd"]) <= TOL64 * abs(g["nlpd"])
+
+
+@pytest.mark.parametrize("name", ["k1_regression_m52_gauss_pep", "k2_coal200_m52_poisson_eks", "c2_coal333_m32_poisson_pep_gh"])
+def test_fused_run_matches_golden(name):
+    """SDEGP.run() (one fused kjx_run call per iteration) against the recorded reference iterations."""
+    kjx = _kjx()
+    g = load(name)
+    model, iters = build_model(name, g, kjx.priors, kjx.likelihoods, kjx.approximate_inference, kjx.SDEGP)
+    for it in range(iters):
+        nlml, _ = model.run(compute_grad=False, store_posterior=True)
+        pre = "it%d_" % it
+        assert abs(nlml - g[pre + "nlml"]) <= TOL64 * abs(g[pre + "nlml"])
+        assert rel_err(_np(model.sites.site_params[0]), g[pre + "site_mean"]) < TOL64
+        assert rel_err(_np(model.sites.site_params[1]), g[pre + "site_cov"]) < TOL64
+        assert rel_err(_np(model.posterior[0]), g[pre + "smoothed_mean"]) < TOL64
+        assert rel_err(_np(model.posterior[1]), g[pre + "smoothed_cov"]) < TOL64
+
+
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prior_name", ["Matern52", "Matern32"])
+@pytest.mark.parametrize("N", [1, 2, 3, 5, 127, 128, 129, 4097, 10_000])
+def test_scan_filter_smoother_vs_oracle(prior_name, N):
+    """BASELINE config 1 (and ragged / tiny lengths): parallel-in-time scan vs the sequential oracle."""
+    kjx = _kjx()
+    t, y = synth(N)
+    mk = lambda mod, inf: mod.SDEGP(getattr(mod.priors, prior_name)(1.0, 5.0), mod.likelihoods.Gaussian(0.5), t, y,  # noqa: E731
+                                    approx_inf=inf.EP(power=0.5))
+    model, ref = mk(kjx, kjx.approximate_inference), mk(oracle, oracle.approx_inf)
+    params = model._params(None)
+    for it in range(2):
+        nlml, (fm, fP, sites) = model.kalman_filter(model.y, model.dt, params, True, None, model.sites.site_params, model.r)
+        s_new, sm, sc = model.rauch_tung_striebel_smoother(params, fm, fP, model.dt, True, True, model.y, sites, model.r)
+        want_nlml, (wfm, wfP, wsites) = ref.kalman_filter(ref.y, ref.dt, True, None, ref.sites.site_params, ref.r)
+        w_new, wsm, wsc = ref.rauch_tung_striebel_smoother(wfm, wfP, ref.dt, True, True, ref.y, wsites, ref.r)
+        assert abs(float(nlml) - want_nlml) <= TOL64 * abs(want_nlml)
+        assert rel_err(_np(fm), wfm) < TOL64 and rel_err(_np(fP), wfP) < TOL64
+        assert rel_err(_np(sm), wsm) < TOL64 and rel_err(_np(sc), wsc) < TOL64
+        assert rel_err(_np(s_new[0]), w_new[0]) < TOL64 and rel_err(_np(s_new[1]), w_new[1]) < TOL64
+        model.sites.site_params, ref.sites.site_params = s_new, w_new
+
+
+def test_scan_equals_sequential_kernel_at_2pow20():
+    """Size-independent property: the scan path and the one-chain reference-order kernel agree."""
+    kjx = _kjx()
+    N = 1 << 20
+    t, y = synth(N)
+    model = kjx.SDEGP(kjx.priors.Matern52(1.0, 5.0), kjx.likelihoods.Gaussian(0.5), t, y,
+                      approx_inf=kjx.approximate_inference.EP(power=0.5))
+    params = model._params(None)
+    rng = np.random.default_rng(5)
+    sites = (y[:, None, None] + 0.1 * rng.standard_normal([N, 1, 1]), rng.uniform(0.3, 0.8, [N, 1, 1]))
+    out = {}
+    for seq in (False, True):
+        nlml, (fm, fP, _) = model.kalman_filter(model.y, model.dt, params, True, None, sites, model.r, sequential=seq)
+        s_new, sm, sc = model.rauch_tung_striebel_smoother(params, fm, fP, model.dt, True, False, model.y, sites, model.r,
+                                                           sequential=seq)
+        out[seq] = (float(nlml), _np(fm), _np(fP), _np(sm), _np(sc), _np(s_new[0]), _np(s_new[1]))
+    assert abs(out[False][0] - out[True][0]) <= TOL64 * abs(out[True][0])
+    for a, b in zip(out[False][1:], out[True][1:]):
+        assert rel_err(a, b) < TOL64
+    assert np.isfinite(out[False][1]).all()
+
+
+def test_masked_prediction_path_vs_oracle():
+    """predict(): merged train/test grid, masked steps are predict-only (sde_gp.py:286, 297-300)."""
+    kjx = _kjx()
+    t, y = synth(3000)
+    t_test = np.linspace(t.min() - 3.0, t.max() + 3.0, 777)
+    for lik_args, inf_name, inf_kw in [(("Gaussian", dict(variance=0.5)), "EP", dict(power=0.5)),
+                                       (("Poisson", dict()), "EKS", dict())]:
+        yy = y if lik_args[0] == "Gaussian" else np.random.default_rng(0).poisson(np.exp(0.5 * y)).astype(float)
+        mk = lambda mod, inf: mod.SDEGP(mod.priors.Matern52(1.0, 5.0), getattr(mod.likelihoods, lik_args[0])(**lik_args[1]),  # noqa: E731
+                                        t, yy, approx_inf=getattr(inf, inf_name)(**inf_kw))
+        model, ref = mk(kjx, kjx.approximate_inference), mk(oracle, oracle.approx_inf)
+        model.run(compute_grad=False)
+        ref.run()
+        pm, pv = model.predict(t=t_test)
+        wm, wv = ref.predict(t=t_test)
+        assert rel_err(_np(pm), wm) < TOL64 and rel_err(_np(pv), wv) < TOL64
+        nlpd = model.negative_log_predictive_density(t=t_test, y=np.interp(t_test, t, yy).round())
+        want = ref.negative_log_predictive_density(t=t_test, y=np.interp(t_test, t, yy).round())
+        assert abs(nlpd - want) <= TOL64 * abs(want)
+
+
+def test_empty_series_is_a_no_op():
+    kjx = _kjx()
+    import ctypes as C
+    from kalman_jax_b200 import _lib
+    from kalman_jax_b200.sde_gp import _Model
+    model = _Model(kjx.priors.Matern52(1.0, 5.0), kjx.likelihoods.Gaussian(0.5), kjx.approximate_inference.EP())
+    nlml = torch.full((1,), 7.0, dtype=torch.float64, device="cuda")
+    ws = torch.empty(1 << 16, dtype=torch.uint8, device="cuda")
+    dummy = torch.zeros(4, dtype=torch.float64, device="cuda")
+    rc = _lib.lib().kjx_filter_f64(model.ref(), C.c_int64(0), _lib.ptr(dummy), _lib.ptr(dummy), None, None, None, None, None,
+                                   None, None, _lib.ptr(nlml), _lib.ptr(ws), C.c_size_t(ws.numel()), 0, None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert float(nlml[0]) == 0.0
+
+
+# ---------------------------------------------------------------------------------------------------
+LIKS = {
+    "gauss": ("Gaussian", dict(variance=0.37)),
+    "probit": ("Probit", dict()),
+    "logit": ("Logit", dict()),
+    "poisson": ("Poisson", dict()),
+    "poisson_logistic": ("Poisson", dict(link="logistic")),
+}
+METHODS = {
+    "ep1": ("EP", dict(power=1.0)),
+    "pep_gh_damped": ("EP", dict(power=0.5, damping=0.6)),
+    "pep_ut": ("EP", dict(power=0.9, intmethod="UT")),
+    "eep": ("EEP", dict(power=0.5, damping=0.7)),
+    "eks": ("EKS", dict()),
+    "ghep": ("GHEP", dict(power=1)),
+    "uks_damped": ("UKS", dict(damping=0.5)),
+    "vi": ("VI", dict()),
+    "vi_ut_damped": ("VI", dict(intmethod="UT", damping=0.5)),
+}
+
+
+@pytest.mark.parametrize("lik", sorted(LIKS))
+@pytest.mark.parametrize("meth", sorted(METHODS))
+@pytest.mark.parametrize("has_prev", [False, True])
+def test_site_update_kernel_vs_oracle(lik, meth, has_prev):
+    """kjx_site_update: every likelihood x rule, embarrassingly parallel over 100k steps."""
+    kjx = _kjx()
+    rng = np.random.default_rng(11)
+    N = 100_000
+    pm, pv = rng.normal(0.0, 1.0, N), rng.uniform(0.05, 1.5, N)
+    y = {"gauss": rng.normal(0, 1.5, N), "probit": (rng.uniform(size=N) < 0.5).astype(float),
+         "logit": (rng.uniform(size=N) < 0.5).astype(float)}.get(lik, rng.poisson(1.5, N).astype(float))
+    prev = (rng.normal(0, 1, N), rng.uniform(2.0, 6.0, N)) if has_prev else None
+    o_lik = getattr(oracle.likelihoods, LIKS[lik][0])(**LIKS[lik][1])
+    o_rule = getattr(oracle.approx_inf, METHODS[meth][0])(**METHODS[meth][1])
+    with np.errstate(all="ignore"):
+        want = o_rule.update(o_lik, y, pm, pv, prev)
+    k_lik = getattr(kjx.likelihoods, LIKS[lik][0])(**LIKS[lik][1])
+    k_rule = getattr(kjx.approximate_inference, METHODS[meth][0])(**METHODS[meth][1])
+    hyp = np.array(0.37) if lik == "gauss" else None
+    got = k_rule.update(k_lik, y, pm, pv, hyp, prev)
+    for a, b in zip(got, want):
+        a, b = _np(a), np.broadcast_to(np.asarray(b, dtype=float), (N,))
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        ok = ~np.isnan(b)
+        np.testing.assert_allclose(a[ok], b[ok], rtol=5e-9, atol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------------
+def _disc_case(name):
+    kjx = _kjx()
+    if name == "m32":
+        return kjx.priors.Matern32(1.3, 2.0), oracle.priors.Matern32(1.3, 2.0)
+    if name == "m52":
+        return kjx.priors.Matern52(0.7, 5.0), oracle.priors.Matern52(0.7, 5.0)
+    if name == "qp":
+        kw = dict(variance=1., lengthscale_periodic=2., period=7., lengthscale_matern=30.)
+        return kjx.priors.QuasiPeriodicMatern32(**kw), oracle.priors.QuasiPeriodicMatern32(**kw)
+    if name == "sum59":
+        mk = lambda P: P.Sum([P.Matern52(variance=2., lengthscale=5.5e4),  # noqa: E731
+                              P.QuasiPeriodicMatern32(variance=1., lengthscale_periodic=2., period=365., lengthscale_matern=1.5e4),
+                              P.QuasiPeriodicMatern32(variance=1., lengthscale_periodic=2., period=7., lengthscale_matern=30 * 365.)])
+        return mk(kjx.priors), mk(oracle.priors)
+    if name == "st":
+        z = np.linspace(-3, 3, 12)
+        return (kjx.priors.SpatioTemporalMatern52(0.3, 0.3, 0.3, z=z), oracle.priors.SpatioTemporalMatern52(0.3, 0.3, 0.3, z=z))
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("name", ["m32", "m52", "qp", "sum59", "st"])
+def test_discretise_kernel_vs_oracle(name):
+    """kjx_discretise: A(dt) = expm(F dt) closed forms and Q = Pinf - A Pinf A^T for varying dt."""
+    import ctypes as C
+    from kalman_jax_b200 import _lib
+    from kalman_jax_b200.sde_gp import _Model
+    kjx = _kjx()
+    k_prior, o_prior = _disc_case(name)
+    model = _Model(k_prior, kjx.likelihoods.Gaussian(0.5), kjx.approximate_inference.EP(), r0=np.array([0.1]))
+    d = model.state_dim
+    rng = np.random.default_rng(2)
+    N = 257
+    dt = np.concatenate([[0.0], rng.uniform(1e-3, 3.0, N - 1)])
+    dt_d = torch.as_tensor(dt, device="cuda")
+    A = torch.empty(N, d, d, dtype=torch.float64, device="cuda")
+    Q = torch.empty(N, d, d, dtype=torch.float64, device="cuda")
+    _lib.check(_lib.lib().kjx_discretise_f64(model.ref(), C.c_int64(N), _lib.ptr(dt_d), _lib.ptr(A), _lib.ptr(Q), None),
+               "kjx_discretise")
+    torch.cuda.synchronize()
+    _, Pinf = o_prior.kernel_to_state_space()
+    wantA = np.stack([o_prior.state_transition(h) for h in dt])
+    wantQ = np.stack([Pinf - a @ Pinf @ a.T for a in wantA])
+    assert rel_err(_np(A), wantA) < 1e-12
+    assert np.max(np.abs(_np(Q) - wantQ)) < 1e-12 * np.max(np.abs(Pinf))
+    assert np.array_equal(_np(A)[0], np.eye(d))          # dt = 0 -> A = I exactly (utils.py:112)
+
+
+# ---------------------------------------------------------------------------------------------------
+def test_fp32_variant_within_1e4_on_benchmark_regime():
+    """fp32 compute path vs the fp64 oracle, dt/lengthscale ~ 0.02."""
+    kjx = _kjx()
+    t, y = synth(20_000)
+    model = kjx.SDEGP(kjx.priors.Matern52(1.0, 5.0), kjx.likelihoods.Gaussian(0.5), t, y,
+                      approx_inf=kjx.approximate_inference.EP(power=0.5), dtype=torch.float32)
+    ref = oracle.SDEGP(oracle.priors.Matern52(1.0, 5.0), oracle.likelihoods.Gaussian(0.5), t, y,
+                       approx_inf=oracle.approx_inf.EP(power=0.5))
+    nlml, _ = model.run(compute_grad=False, store_posterior=True)
+    want_nlml, (wfm, wfP, wsites) = ref.kalman_filter(ref.y, ref.dt, True, None, None, ref.r)
+    _, wsm, wsc = ref.rauch_tung_striebel_smoother(wfm, wfP, ref.dt, True, False, ref.y, wsites, ref.r)
+    assert abs(nlml - want_nlml) <= TOL32 * abs(want_nlml)
+    assert rel_err(_np(model.posterior[0]), wsm) < TOL32
+    assert rel_err(_np(model.posterior[1]), wsc) < TOL32
+
+
+def test_host_buffer_entry_point_matches_device_path():
+    """kjx_run_host_f64 (pinned host arrays in, sites + nlml out) == kjx_run_f64 on resident arrays."""
+    import ctypes as C
+    from kalman_jax_b200 import _lib
+    from kalman_jax_b200.sde_gp import _Model
+    kjx = _kjx()
+    N = 50_000
+    t, y = synth(N)
+    model = kjx.SDEGP(kjx.priors.Matern52(1.0, 5.0), kjx.likelihoods.Gaussian(0.5), t, y,
+                      approx_inf=kjx.approximate_inference.EP(power=0.5))
+    nlml, _ = model.run(compute_grad=False)
+    cm = _Model(model.prior, model.likelihood, model.sites)
+    nbytes = C.c_size_t(0)
+    _lib.check(_lib.lib().kjx_run_host_scratch_bytes(cm.ref(), C.c_int64(N), 8, C.byref(nbytes)), "scratch")
+    scratch = torch.empty(nbytes.value, dtype=torch.uint8, device="cuda")
+    pin = lambda a: torch.as_tensor(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
+    dt_h, y_h = pin(model.dt), pin(model.y[:, 0])
+    nsm, nsv, nl = (torch.empty(N, dtype=torch.float64).pin_memory(), torch.empty(N, dtype=torch.float64).pin_memory(),
+                    torch.empty(1, dtype=torch.float64).pin_memory())
+    _lib.check(_lib.lib().kjx_run_host_f64(cm.ref(), C.c_int64(N), _lib.ptr(dt_h), _lib.ptr(y_h), None, None, _lib.ptr(nsm),
+                                           _lib.ptr(nsv), None, None, _lib.ptr(nl), _lib.ptr(scratch), C.c_size_t(nbytes.value), 0,
+                                           C.c_void_p(torch.cuda.current_stream().cuda_stream)), "kjx_run_host")
+    assert float(nl[0]) == nlml
+    assert np.array_equal(nsm.numpy(), _np(model.sites.site_params[0]).reshape(-1))
+    assert np.array_equal(nsv.numpy(), _np(model.sites.site_params[1]).reshape(-1))
