@@ -212,12 +212,18 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        it.iteration()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        it.iteration()
+    barrier()
+    # keep the device under the same load until nvidia-smi has delivered a few samples (not timed)
+    t_spin = time.perf_counter()
+    while rank == 0 and len(sampler.rows) < 3 and time.perf_counter() - t_spin < 3.0:
+        it.iteration(update_sites=False)
+        torch.cuda.synchronize()
+    sampler.rows = sampler.rows[-1:]
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -226,6 +232,11 @@ def main():
         it.iteration(events=ev[k])
     stop.record()
     barrier()
+    if rank == 0:                       # a few more samples under load right after the timed region
+        t_spin = time.perf_counter()
+        while len(sampler.rows) < 4 and time.perf_counter() - t_spin < 2.0:
+            it.iteration(update_sites=False)
+            torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     ms_total = start.elapsed_time(stop)
     phases = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(3)] for e in ev]).mean(axis=0)   # ms
