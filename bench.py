@@ -189,13 +189,21 @@ def main():
     assert world == args.gpus, "launch with torchrun --nproc-per-node == --gpus"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    gather = None
+    gather = reduce_nlml = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        gbuf = {}
 
         def gather(t):
-            out = torch.empty(world, t.numel(), dtype=t.dtype, device=t.device)
+            out = gbuf.get(t.numel())
+            if out is None:
+                out = gbuf[t.numel()] = torch.empty(world, t.numel(), dtype=t.dtype, device=t.device)
             dist.all_gather_into_tensor(out, t)
+            return out
+
+        def reduce_nlml(t):
+            out = t.clone()
+            dist.all_reduce(out)
             return out
 
     N = 1 << args.n
@@ -216,7 +224,7 @@ def main():
     if rank == 0:
         sampler.start()
     for _ in range(max(args.warmup, 3)):
-        it.iteration()
+        it.iteration(reduce_nlml=reduce_nlml)
     barrier()
     # keep the device under the same load until nvidia-smi has delivered a few samples (not timed)
     t_spin = time.perf_counter()
@@ -229,7 +237,7 @@ def main():
     barrier()
     start.record()
     for k in range(args.steps):
-        it.iteration(events=ev[k])
+        it.iteration(events=ev[k], reduce_nlml=reduce_nlml)
     stop.record()
     barrier()
     if rank == 0:                       # a few more samples under load right after the timed region
@@ -258,8 +266,6 @@ def main():
         if world == 1:
             nbytes = C.c_size_t(0)
             _lib.check(_lib.lib().kjx_run_host_scratch_bytes(it.model.ref(), C.c_int64(N), 8, C.byref(nbytes)), "scratch")
-            del it.filt_mean, it.filt_cov
-            torch.cuda.empty_cache()
             scratch = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
 
             def e2e_step():
@@ -271,7 +277,7 @@ def main():
             def e2e_step():
                 it.dt.copy_(h_dt, non_blocking=True); it.y.copy_(h_y, non_blocking=True)
                 it.site_mean.copy_(h_sm, non_blocking=True); it.site_var.copy_(h_sv, non_blocking=True)
-                nl = it.iteration()
+                nl = it.iteration(reduce_nlml=reduce_nlml)
                 o_sm.copy_(it.site_mean, non_blocking=True); o_sv.copy_(it.site_var, non_blocking=True)
                 o_nl.copy_(nl.reshape(1), non_blocking=True)
                 torch.cuda.synchronize()
@@ -307,10 +313,10 @@ def main():
                                "filter(stored sites) -> RTS smoother -> site update; N=2^%d steps, d=3, f=1" % args.n,
                    "N": N, "state_dim": 3, "sharding": "time axis, %d contiguous shard(s)" % world,
                    "l2_policy": "inputs (%.1f GB per iteration per GPU) exceed the 126 MB L2; no flush needed" % (BYTES_PER_STEP * n_local / 1e9)},
-        "roofline": {"bound": "hbm", "kernel": ("filter_apply_kernel (F3, incl. smoother fold)", "smoother_apply_kernel (S3)")[dom - 1],
+        "roofline": {"bound": "hbm", "kernel": ("fused_filter_kernel (R3)", "fused_smoother_kernel (R4)")[dom - 1],
                      "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
                      "peak_source": peak_src, "algorithmic_bytes_per_step": (BYTES_FILTER, BYTES_SMOOTHER)[dom - 1],
-                     "phase_ms": {"filter_summary(F1+F2)": ph[0], "filter_apply(F3+S2)": ph[1], "smoother_apply(S3)": ph[2]},
+                     "phase_ms": {"reduce+scan+fold(R1,R2)": ph[0], "filter(R3)": ph[1], "smoother+sites(R4)": ph[2]},
                      "iteration": {"achieved": BYTES_PER_STEP * n_local / (ms_step * 1e-3) / 1e9,
                                    "frac": BYTES_PER_STEP * n_local / (ms_step * 1e-3) / 1e9 / hbm, "bytes_per_step": BYTES_PER_STEP}},
         "gpu_launches": it.launches_per_iteration * args.steps,

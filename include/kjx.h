@@ -143,12 +143,14 @@ int kjx_smoother_f64(const kjx_model_t* m, int64_t N, const double* dt,
                      void* ws, size_t ws_bytes, uint32_t flags, kjx_stream_t stream);
 
 /* One SDEGP.run() iteration (sde_gp.py:179-187 without the gradient): filter with the given (or
- * initialised) sites, then smoother + site update.  Fuses the smoother's scan summaries into the
- * filter pass.  site_* in; new_site_* out (may alias site_*); post_mean/post_var = smoothed
- * marginals H m, H P H^T (nullable). */
+ * initialised) sites, then smoother + site update, as one fused parallel-in-time scan.  site_* in;
+ * new_site_* out; post_mean/post_var = smoothed marginals H m, H P H^T (nullable).  filt_mean/filt_cov
+ * are optional: run() only uses the filtered moments internally (sde_gp.py:183-187), so by default they
+ * stay in the workspace in a packed private layout; pass pointers to also get them in the reference's
+ * dense layout. */
 int kjx_run_f64(const kjx_model_t* m, int64_t N, const double* dt, const double* y,
                 const double* site_mean /*?*/, const double* site_cov /*?*/,
-                double* filt_mean, double* filt_cov,
+                double* filt_mean /*?*/, double* filt_cov /*?*/,
                 double* new_site_mean, double* new_site_cov,
                 double* post_mean /*?*/, double* post_var /*?*/,
                 double* nlml, void* ws, size_t ws_bytes, uint32_t flags, kjx_stream_t stream);
@@ -168,53 +170,38 @@ int kjx_site_update_f64(const kjx_model_t* m, int64_t N, const double* y,
 int kjx_discretise_f64(const kjx_model_t* m, int64_t N, const double* dt,
                        double* A /* [N,d,d] */, double* Q /*? [N,d,d] */, kjx_stream_t stream);
 
-/* ---- time-sharded form (one shard per GPU).  The caller exchanges the fixed-size summaries
- * between the two halves (all-gather), folds the ones of the preceding (filter) / following
- * (smoother) shards with kjx_fold_*_summaries_host, and passes the boundary state in. ---------- */
-/* packed sizes: (A[d,d], b[d], upper(C), eta[d], upper(J)) and (E[d,d], g[d], upper(L)) */
-size_t kjx_filter_summary_doubles(int32_t state_dim);    /* 2 d^2 + 3 d        (27 at d = 3)      */
-size_t kjx_smoother_summary_doubles(int32_t state_dim);  /* (3 d^2 + 3 d) / 2  (18 at d = 3)      */
-
-/* phase 1+2 of the filter scan over this shard; writes the shard's total element
- * (A, b, C, eta, J) to summary_out (device, kjx_filter_summary_doubles). */
+/* ---- time-sharded form (one contiguous shard of the time axis per GPU) ---------------------------
+ * The fused iteration split at its one exchange point.  Each shard reduces its steps to ONE filter scan
+ * element (A, b, C, eta, J); after an all-gather of those fixed-size summaries every rank folds the ones
+ * of the shards before it into the filtered state entering its shard, and the ones after it into the
+ * information (eta, J) about its last state — which is all the smoother needs (two-filter identity), so
+ * there is a single collective per iteration.  The three calls of a shard share `ws` (it carries the
+ * per-chunk prefixes and the filtered moments between them). */
+/* packed size of a summary: A[d,d], b[d], upper(C), eta[d], upper(J) -> 2 d^2 + 3 d (27 at d = 3) */
+size_t kjx_filter_summary_doubles(int32_t state_dim);
+/* phases 1+2: fold + scan this shard; summary_out (device) receives the shard's total element */
 int kjx_filter_summary_f64(const kjx_model_t* m, int64_t N, const double* dt, const double* y,
-                           const uint8_t* mask /*?*/, const double* site_mean /*?*/, const double* site_cov /*?*/,
+                           const double* site_mean /*?*/, const double* site_cov /*?*/,
                            double* summary_out, void* ws, size_t ws_bytes, kjx_stream_t stream);
-/* phase 3: state_in = (mean[d], cov[d,d]) filtered state just before this shard (device, d+d^2
- * doubles; for shard 0: (0, Pinf)).  dt_next = dt of the first step of the next shard (0 for the
- * last shard); is_last_shard marks the shard holding step N-1.  Also produces this shard's
- * smoother summary (E, g, L) and partial nlml. */
+/* the fold (one tiny kernel): summaries = gathered [world] rows of `stride` doubles (>= packed size, so
+ * extra per-rank scalars can ride in the same all-gather); state_out = (mean[d], cov[d,d]) entering
+ * shard `rank`; info_out = (eta[d], J[d,d]) of all later shards. */
+int kjx_fold_shard_summaries_f64(const kjx_model_t* m, const double* summaries, int64_t stride, int32_t world,
+                                 int32_t rank, double* state_out, double* info_out, kjx_stream_t stream);
+int kjx_fold_shard_summaries_host(const kjx_model_t* m, const double* summaries_host, int64_t stride, int32_t world,
+                                  int32_t rank, double* state_out_host, double* info_out_host);
+/* phase 3: the reference filter recursion over the shard from state_in; nlml_partial[1] = this shard's
+ * share of the negative log marginal likelihood (sum the shards' values) */
 int kjx_filter_apply_f64(const kjx_model_t* m, int64_t N, const double* dt, const double* y,
-                         const uint8_t* mask /*?*/, const double* site_mean /*?*/, const double* site_cov /*?*/,
-                         const double* state_in, double dt_next, int32_t is_last_shard,
-                         double* filt_mean, double* filt_cov,
-                         double* out_site_mean /*?*/, double* out_site_cov /*?*/,
-                         double* smoother_summary_out, double* nlml_partial,
+                         const double* site_mean /*?*/, const double* site_cov /*?*/,
+                         const double* state_in, double* nlml_partial,
                          void* ws, size_t ws_bytes, kjx_stream_t stream);
-/* smoother phase 3: state_in = smoothed (mean[d], cov[d,d]) at the first step of the next shard
- * (ignored for the last shard). */
-int kjx_smoother_apply_f64(const kjx_model_t* m, int64_t N, const double* dt, double dt_next,
-                           const double* filt_mean, const double* filt_cov,
-                           const double* y /*?*/, const double* site_mean /*?*/, const double* site_cov /*?*/,
-                           const double* state_in, int32_t is_last_shard,
-                           double* smooth_mean /*?*/, double* smooth_cov /*?*/,
+/* phase 4: RTS recursion backwards + site update; info_in from the fold (zeros for the last shard) */
+int kjx_smoother_apply_f64(const kjx_model_t* m, int64_t N, const double* dt, const double* y,
+                           const double* site_mean /*?*/, const double* site_cov /*?*/, const double* info_in,
+                           double* post_mean /*?*/, double* post_var /*?*/,
                            double* new_site_mean /*?*/, double* new_site_cov /*?*/,
                            void* ws, size_t ws_bytes, uint32_t flags, kjx_stream_t stream);
-/* Host-side folds of gathered summaries (tiny, fp64): state before shard `rank` from the filter
- * summaries of shards 0..rank-1 applied to the prior (0, Pinf); smoothed state entering shard
- * `rank` from the smoother summaries of shards rank+1..world-1. */
-int kjx_fold_filter_summaries_host(int32_t state_dim, const double* Pinf_host, const double* summaries_host,
-                                   int32_t rank, double* state_out_host /* d + d^2 */);
-int kjx_fold_smoother_summaries_host(int32_t state_dim, const double* summaries_host, int32_t world,
-                                     int32_t rank, double* state_out_host /* d + d^2 */);
-
-/* Device-side versions of the two folds (one tiny kernel each, no host round trip): gathered
- * summaries live in device memory as [world, kjx_*_summary_doubles(d)] (+ `stride` doubles between
- * ranks, >= the packed size, so extra per-rank scalars can ride along in the same all-gather). */
-int kjx_fold_filter_summaries_f64(const kjx_model_t* m, const double* summaries, int64_t stride, int32_t rank,
-                                  double* state_out /* d + d^2 */, kjx_stream_t stream);
-int kjx_fold_smoother_summaries_f64(const kjx_model_t* m, const double* summaries, int64_t stride, int32_t world,
-                                    int32_t rank, double* state_out /* d + d^2 */, kjx_stream_t stream);
 
 /* ---- host-buffer entry point (end-to-end path): one run() iteration where every data array is a
  * HOST pointer (pinned memory for full PCIe speed).  Inputs are copied to the device, the fused

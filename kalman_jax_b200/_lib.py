@@ -47,10 +47,9 @@ SYMBOLS = [
     "kjx_version", "kjx_status_string", "kjx_workspace_bytes",
     "kjx_filter_f64", "kjx_smoother_f64", "kjx_run_f64", "kjx_site_update_f64", "kjx_discretise_f64",
     "kjx_filter_f32", "kjx_smoother_f32", "kjx_run_f32", "kjx_site_update_f32", "kjx_discretise_f32",
-    "kjx_filter_summary_doubles", "kjx_smoother_summary_doubles",
+    "kjx_filter_summary_doubles",
     "kjx_filter_summary_f64", "kjx_filter_apply_f64", "kjx_smoother_apply_f64",
-    "kjx_fold_filter_summaries_host", "kjx_fold_smoother_summaries_host",
-    "kjx_fold_filter_summaries_f64", "kjx_fold_smoother_summaries_f64", "kjx_run_host_f64", "kjx_run_host_scratch_bytes",
+    "kjx_fold_shard_summaries_host", "kjx_fold_shard_summaries_f64", "kjx_run_host_f64", "kjx_run_host_scratch_bytes",
 ]
 
 
@@ -64,7 +63,6 @@ def lib():
         L = C.CDLL(LIB_PATH)
         L.kjx_status_string.restype = C.c_char_p
         L.kjx_filter_summary_doubles.restype = C.c_size_t
-        L.kjx_smoother_summary_doubles.restype = C.c_size_t
         for name in SYMBOLS:
             getattr(L, name)  # AttributeError if the symbol is missing
         _lib = L

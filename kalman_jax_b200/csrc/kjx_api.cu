@@ -7,6 +7,7 @@
 
 #include "../../include/kjx.h"
 #include "kjx_small_kernels.cuh"
+#include "kjx_fused_kernels.cuh"
 #include "kjx_elementwise_kernels.cuh"
 
 using namespace kjx;
@@ -73,7 +74,8 @@ int pick_chunk(int64_t N) {
 
 template <typename T, int D> struct SmallLayout {
   int L; int64_t nchunks, nblocks; size_t cstride, bstride;
-  size_t off_ftp, off_fbt, off_fbp, off_fst, off_sts, off_sbt, off_sbs, off_sst, off_nl, off_fin, off_sin, total;
+  size_t off_ftp, off_fbt, off_fbp, off_fst, off_sts, off_sbt, off_sbs, off_sst, off_nl, off_fin, off_sin;
+  size_t off_fts, off_fbs, off_info, off_xf, total;
   explicit SmallLayout(int64_t N) {
     constexpr size_t FNS = FSum<T, D>::NS, SNS = SSum<T, D>::NS;
     L = pick_chunk(N);
@@ -86,6 +88,9 @@ template <typename T, int D> struct SmallLayout {
     off_ftp = take(FNS * cstride); off_fbt = take(FNS * bstride); off_fbp = take(FNS * bstride); off_fst = take(FNS);
     off_sts = take(SNS * cstride); off_sbt = take(SNS * bstride); off_sbs = take(SNS * bstride); off_sst = take(SNS);
     off_nl = take(bstride); off_fin = take(D + D * D); off_sin = take(D + D * D);
+    off_fts = take(FNS * cstride); off_fbs = take(FNS * bstride); off_info = take(D + D * D);
+    // filtered moments between the fused filter and smoother passes: [warp][step][element][lane]
+    off_xf = take(cstride * (size_t)L * Packed<D>::NP);
     total = o;
   }
 };
@@ -101,6 +106,16 @@ void bind_workspace(SmallArgs<T, D>& a, const SmallLayout<T, D>& lay, void* ws) 
   a.block_nlml = (T*)(w + lay.off_nl);
   a.f_state_in = (T*)(w + lay.off_fin); a.s_state_in = (T*)(w + lay.off_sin);
 }
+
+template <typename T, int D>
+void bind_fused(FusedArgs<T, D>& fa, const SmallLayout<T, D>& lay, void* ws) {
+  char* w = (char*)ws;
+  bind_workspace<T, D>(fa.a, lay, ws);
+  fa.f_thread_suffix = (T*)(w + lay.off_fts); fa.f_block_suffix = (T*)(w + lay.off_fbs);
+  fa.s_info_in = (T*)(w + lay.off_info); fa.xf = (T*)(w + lay.off_xf);
+}
+
+inline bool aligned_to(const void* p, size_t a) { return p == nullptr || ((uintptr_t)p % a) == 0; }
 
 template <typename T, int D>
 void fill_prior(SmallArgs<T, D>& a, const kjx_model_t* m) {
@@ -227,6 +242,66 @@ int small_smoother(const kjx_model_t* m, int64_t N, const T* dt, const T* filt_m
   return KJX_OK;
 }
 
+// ---- the fused iteration (kjx_run and the sharded calls) ----------------------------------------------
+template <typename T, int KIND>
+struct Fused {
+  static constexpr int D = BlockDim<KIND>::D;
+  FusedArgs<T, D> fa;
+  SmallLayout<T, D> lay;
+  const kjx_model_t* m;
+  Fused(const kjx_model_t* m_, int64_t N, const T* dt, const T* y, const T* site_mean, const T* site_var, void* ws)
+      : lay(N), m(m_) {
+    memset(&fa, 0, sizeof(fa));
+    fill_prior<T, D>(fa.a, m);
+    bind_fused<T, D>(fa, lay, ws);
+    fa.a.N = N; fa.a.dt = dt; fa.a.y = y; fa.a.site_mean = site_mean; fa.a.site_var = site_var;
+    fa.a.gaussian_init = (site_mean == nullptr) ? 1 : 0;
+    fa.a.is_last_shard = 1;
+    const size_t al = sizeof(T) * 4;
+    fa.vec_ok = (lay.L % 4 == 0) && aligned_to(dt, al) && aligned_to(y, al) && aligned_to(site_mean, al) && aligned_to(site_var, al);
+  }
+  unsigned grid() const { return (unsigned)fa.a.nblocks; }
+  void reduce(cudaStream_t st) {
+    if (fa.vec_ok) fused_reduce_kernel<T, KIND, true><<<grid(), KJX_BLOCK, 0, st>>>(fa);
+    else fused_reduce_kernel<T, KIND, false><<<grid(), KJX_BLOCK, 0, st>>>(fa);
+    fused_blockscan_kernel<T, D><<<1, KJX_SCAN_BLOCK, 0, st>>>(fa);
+  }
+  void filter(cudaStream_t st) {
+    const bool fast = gauss_ep(m);
+    if (fast && fa.vec_ok) fused_filter_kernel<T, KIND, true, true><<<grid(), KJX_BLOCK, 0, st>>>(fa);
+    else if (fast) fused_filter_kernel<T, KIND, true, false><<<grid(), KJX_BLOCK, 0, st>>>(fa);
+    else if (fa.vec_ok) fused_filter_kernel<T, KIND, false, true><<<grid(), KJX_BLOCK, 0, st>>>(fa);
+    else fused_filter_kernel<T, KIND, false, false><<<grid(), KJX_BLOCK, 0, st>>>(fa);
+  }
+  void smoother(T* post_mean, T* post_var, T* new_site_mean, T* new_site_var, bool update, cudaStream_t st) {
+    fa.a.smooth_mean = post_mean; fa.a.smooth_cov = post_var; fa.a.new_site_mean = new_site_mean; fa.a.new_site_var = new_site_var;
+    fa.a.update_sites = (update && new_site_mean != nullptr) ? 1 : 0;
+    const size_t al = sizeof(T) * 4;
+    const bool vec = fa.vec_ok && aligned_to(post_mean, al) && aligned_to(post_var, al) && aligned_to(new_site_mean, al) && aligned_to(new_site_var, al);
+    const bool fast = gauss_ep(m);
+    if (fast && vec) fused_smoother_kernel<T, KIND, true, true><<<grid(), KJX_BLOCK, 0, st>>>(fa);
+    else if (fast) fused_smoother_kernel<T, KIND, true, false><<<grid(), KJX_BLOCK, 0, st>>>(fa);
+    else if (vec) fused_smoother_kernel<T, KIND, false, true><<<grid(), KJX_BLOCK, 0, st>>>(fa);
+    else fused_smoother_kernel<T, KIND, false, false><<<grid(), KJX_BLOCK, 0, st>>>(fa);
+  }
+};
+
+// private packed filtered moments -> the reference's dense [N,d,1] / [N,d,d] layout (optional output of kjx_run)
+template <typename T, int D>
+__global__ void unpack_filtered_kernel(const T* __restrict__ xf, int64_t N, int L, T* __restrict__ fm, T* __restrict__ fP) {
+  constexpr int NP = Packed<D>::NP;
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= N) return;
+  const int64_t c = k / L, i = k % L;
+  const T* base = xf + (((c >> 5) * (int64_t)L + i) * NP) * 32 + (c & 31);
+  T m[D], P[D][D];
+  int e = 0;
+  for (int a = 0; a < D; ++a) m[a] = base[32 * e++];
+  for (int a = 0; a < D; ++a) for (int b = a; b < D; ++b) { P[a][b] = base[32 * e]; P[b][a] = base[32 * e]; ++e; }
+  for (int a = 0; a < D; ++a) fm[k * D + a] = m[a];
+  for (int a = 0; a < D; ++a) for (int b = 0; b < D; ++b) fP[k * D * D + a * D + b] = P[a][b];
+}
+
 template <typename T, int KIND>
 int small_run(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const T* site_mean, const T* site_var,
               T* filt_mean, T* filt_cov, T* new_site_mean, T* new_site_var, T* post_mean, T* post_var,
@@ -234,21 +309,24 @@ int small_run(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const T*
   constexpr int D = BlockDim<KIND>::D;
   SmallLayout<T, D> lay(N);
   if (ws_bytes < lay.total || !ws) return KJX_ERR_WORKSPACE;
-  SmallArgs<T, D> a; memset(&a, 0, sizeof(a));
-  fill_prior<T, D>(a, m); bind_workspace<T, D>(a, lay, ws);
-  a.N = N; a.dt = dt; a.y = y; a.site_mean = site_mean; a.site_var = site_var;
-  a.filt_mean = filt_mean; a.filt_cov = filt_cov; a.filt_mean_in = filt_mean; a.filt_cov_in = filt_cov;
-  a.smooth_mean = post_mean; a.smooth_cov = post_var; a.new_site_mean = new_site_mean; a.new_site_var = new_site_var;
-  a.return_full = 0; a.update_sites = (flags & KJX_FLAG_NO_SITE_UPDATE) ? 0 : 1;
-  a.is_last_shard = 1; a.dt_next = T(0); a.nlml_out = nlml;
-  const bool have_sites = site_mean != nullptr;
-  a.gaussian_init = (!have_sites && gauss_ep(m)) ? 1 : 0;
   if (N == 0) { cudaMemsetAsync(nlml, 0, sizeof(T), st); return KJX_OK; }
+  const bool have_sites = site_mean != nullptr;
   const bool seq = (flags & KJX_FLAG_SEQUENTIAL) != 0;
+  const bool update = !(flags & KJX_FLAG_NO_SITE_UPDATE);
   if (seq || needs_sequential_filter(m, have_sites)) {
-    // filter as one chain; freshly initialised sites land in new_site_* and are the smoother's "previous" sites
+    // One dependent chain (reference order).  Needs dense filter output: use the caller's or scratch in ws is
+    // not provisioned for it, so the caller must pass filt_mean/filt_cov on this path.
+    if (!filt_mean || !filt_cov) return KJX_ERR_INVALID_ARG;
+    SmallArgs<T, D> a; memset(&a, 0, sizeof(a));
+    fill_prior<T, D>(a, m); bind_workspace<T, D>(a, lay, ws);
+    a.N = N; a.dt = dt; a.y = y; a.site_mean = site_mean; a.site_var = site_var;
+    a.filt_mean = filt_mean; a.filt_cov = filt_cov; a.filt_mean_in = filt_mean; a.filt_cov_in = filt_cov;
+    a.smooth_mean = post_mean; a.smooth_cov = post_var; a.new_site_mean = new_site_mean; a.new_site_var = new_site_var;
+    a.update_sites = update ? 1 : 0; a.is_last_shard = 1; a.nlml_out = nlml;
+    a.gaussian_init = (!have_sites && gauss_ep(m)) ? 1 : 0;
     launch_set_prior_state<T, D>((T*)a.f_state_in, m, st);
     const int init = (!have_sites && !a.gaussian_init) ? 1 : 0;
+    // freshly initialised sites land in new_site_* and are the smoother's "previous" sites (sde_gp.py:183-187)
     if (init) { a.out_site_mean = new_site_mean; a.out_site_var = new_site_var; }
     filter_sequential_kernel<T, KIND><<<1, 32, 0, st>>>(a, init);
     if (init) { a.site_mean = new_site_mean; a.site_var = new_site_var; a.out_site_mean = nullptr; a.out_site_var = nullptr; }
@@ -262,139 +340,81 @@ int small_run(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const T*
       small_smoother_apply<T, KIND>(m, a, st);
     }
   } else {
-    small_filter_scan<T, KIND>(m, N, a, true, nullptr, st);
-    smoother_blockscan_kernel<T, D><<<1, KJX_SCAN_BLOCK, 0, st>>>(a);   // also reduces nlml
-    cudaMemsetAsync((void*)a.s_state_in, 0, (D + D * D) * sizeof(T), st);
-    small_smoother_apply<T, KIND>(m, a, st);
+    Fused<T, KIND> f(m, N, dt, y, site_mean, site_var, ws);
+    f.reduce(st);
+    launch_set_prior_state<T, D>((T*)f.fa.a.f_state_in, m, st);
+    cudaMemsetAsync((void*)f.fa.s_info_in, 0, (D + D * D) * sizeof(T), st);
+    f.filter(st);
+    nlml_reduce_kernel<T><<<1, 256, 0, st>>>(f.fa.a.block_nlml, f.fa.a.nblocks, nlml);
+    f.smoother(post_mean, post_var, new_site_mean, new_site_var, update, st);
+    if (filt_mean && filt_cov)
+      unpack_filtered_kernel<T, D><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(f.fa.xf, N, f.lay.L, filt_mean, filt_cov);
   }
   KJX_CUDA_CHECK(cudaGetLastError());
   return KJX_OK;
 }
 
-// ---- sharded halves ------------------------------------------------------------------------------
+// ---- sharded calls -----------------------------------------------------------------------------------
 template <typename T, int KIND>
-int small_filter_summary(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const uint8_t* mask,
-                         const T* site_mean, const T* site_var, T* summary_out, void* ws, size_t ws_bytes,
-                         cudaStream_t st) {
+int shard_summary(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const T* site_mean, const T* site_var,
+                  T* summary_out, void* ws, size_t ws_bytes, cudaStream_t st) {
   constexpr int D = BlockDim<KIND>::D;
-  SmallLayout<T, D> lay(N);
-  if (ws_bytes < lay.total || !ws) return KJX_ERR_WORKSPACE;
+  if (ws_bytes < SmallLayout<T, D>(N).total || !ws) return KJX_ERR_WORKSPACE;
   if (needs_sequential_filter(m, site_mean != nullptr)) return KJX_ERR_UNSUPPORTED;
-  SmallArgs<T, D> a; memset(&a, 0, sizeof(a));
-  fill_prior<T, D>(a, m); bind_workspace<T, D>(a, lay, ws);
-  a.N = N; a.dt = dt; a.y = y; a.mask = mask; a.site_mean = site_mean; a.site_var = site_var;
-  a.gaussian_init = (site_mean == nullptr) ? 1 : 0;
-  filter_reduce_kernel<T, KIND><<<(unsigned)a.nblocks, KJX_BLOCK, 0, st>>>(a);
-  filter_blockscan_kernel<T, D><<<1, KJX_SCAN_BLOCK, 0, st>>>(a);
-  copy_scalars_kernel<T><<<1, 64, 0, st>>>(summary_out, a.f_shard_total, (int)FSum<T, D>::NS);
+  Fused<T, KIND> f(m, N, dt, y, site_mean, site_var, ws);
+  f.reduce(st);
+  copy_scalars_kernel<T><<<1, 64, 0, st>>>(summary_out, f.fa.a.f_shard_total, (int)FSum<T, D>::NS);
   KJX_CUDA_CHECK(cudaGetLastError());
   return KJX_OK;
 }
-
 template <typename T, int KIND>
-int small_filter_apply(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const uint8_t* mask,
-                       const T* site_mean, const T* site_var, const T* state_in, T dt_next, int is_last,
-                       T* filt_mean, T* filt_cov, T* out_site_mean, T* out_site_var, T* ssum_out, T* nlml_partial,
-                       void* ws, size_t ws_bytes, cudaStream_t st) {
+int shard_filter(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const T* site_mean, const T* site_var,
+                 const T* state_in, T* nlml_partial, void* ws, size_t ws_bytes, cudaStream_t st) {
   constexpr int D = BlockDim<KIND>::D;
-  SmallLayout<T, D> lay(N);
-  if (ws_bytes < lay.total || !ws) return KJX_ERR_WORKSPACE;
-  SmallArgs<T, D> a; memset(&a, 0, sizeof(a));
-  fill_prior<T, D>(a, m); bind_workspace<T, D>(a, lay, ws);
-  a.N = N; a.dt = dt; a.y = y; a.mask = mask; a.site_mean = site_mean; a.site_var = site_var;
-  a.gaussian_init = (site_mean == nullptr) ? 1 : 0;
-  a.filt_mean = filt_mean; a.filt_cov = filt_cov; a.out_site_mean = out_site_mean; a.out_site_var = out_site_var;
-  a.dt_next = dt_next; a.is_last_shard = is_last; a.nlml_out = nlml_partial;
-  copy_state_kernel<T, D><<<1, 32, 0, st>>>((T*)a.f_state_in, state_in);
-  if (gauss_ep(m)) filter_apply_kernel<T, KIND, true, true><<<(unsigned)a.nblocks, KJX_BLOCK, 0, st>>>(a);
-  else filter_apply_kernel<T, KIND, true, false><<<(unsigned)a.nblocks, KJX_BLOCK, 0, st>>>(a);
-  smoother_blockscan_kernel<T, D><<<1, KJX_SCAN_BLOCK, 0, st>>>(a);
-  copy_scalars_kernel<T><<<1, 64, 0, st>>>(ssum_out, a.s_shard_total, (int)SSum<T, D>::NS);
+  if (ws_bytes < SmallLayout<T, D>(N).total || !ws) return KJX_ERR_WORKSPACE;
+  Fused<T, KIND> f(m, N, dt, y, site_mean, site_var, ws);
+  copy_state_kernel<T, D><<<1, 32, 0, st>>>((T*)f.fa.a.f_state_in, state_in);
+  f.filter(st);
+  nlml_reduce_kernel<T><<<1, 256, 0, st>>>(f.fa.a.block_nlml, f.fa.a.nblocks, nlml_partial);
   KJX_CUDA_CHECK(cudaGetLastError());
   return KJX_OK;
 }
-
 template <typename T, int KIND>
-int small_smoother_apply_shard(const kjx_model_t* m, int64_t N, const T* dt, T dt_next, const T* filt_mean,
-                               const T* filt_cov, const T* y, const T* site_mean, const T* site_var,
-                               const T* state_in, int is_last, T* smooth_mean, T* smooth_cov, T* new_site_mean,
-                               T* new_site_var, void* ws, size_t ws_bytes, uint32_t flags, cudaStream_t st) {
+int shard_smoother(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const T* site_mean, const T* site_var,
+                   const T* info_in, T* post_mean, T* post_var, T* new_site_mean, T* new_site_var, void* ws,
+                   size_t ws_bytes, uint32_t flags, cudaStream_t st) {
   constexpr int D = BlockDim<KIND>::D;
-  SmallLayout<T, D> lay(N);
-  if (ws_bytes < lay.total || !ws) return KJX_ERR_WORKSPACE;
-  SmallArgs<T, D> a; memset(&a, 0, sizeof(a));
-  fill_prior<T, D>(a, m); bind_workspace<T, D>(a, lay, ws);
-  a.N = N; a.dt = dt; a.y = y; a.site_mean = site_mean; a.site_var = site_var;
-  a.gaussian_init = (site_mean == nullptr) ? 1 : 0;
-  a.filt_mean_in = filt_mean; a.filt_cov_in = filt_cov;
-  a.smooth_mean = smooth_mean; a.smooth_cov = smooth_cov; a.new_site_mean = new_site_mean; a.new_site_var = new_site_var;
-  a.return_full = (flags & KJX_FLAG_RETURN_FULL) ? 1 : 0;
-  a.update_sites = (new_site_mean != nullptr && y != nullptr && !(flags & KJX_FLAG_NO_SITE_UPDATE)) ? 1 : 0;
-  a.dt_next = dt_next; a.is_last_shard = is_last;
-  if (state_in) copy_state_kernel<T, D><<<1, 32, 0, st>>>((T*)a.s_state_in, state_in);
-  else cudaMemsetAsync((void*)a.s_state_in, 0, (D + D * D) * sizeof(T), st);
-  small_smoother_apply<T, KIND>(m, a, st);
+  if (ws_bytes < SmallLayout<T, D>(N).total || !ws) return KJX_ERR_WORKSPACE;
+  Fused<T, KIND> f(m, N, dt, y, site_mean, site_var, ws);
+  copy_state_kernel<T, D><<<1, 32, 0, st>>>((T*)f.fa.s_info_in, info_in);
+  f.smoother(post_mean, post_var, new_site_mean, new_site_var, !(flags & KJX_FLAG_NO_SITE_UPDATE), st);
   KJX_CUDA_CHECK(cudaGetLastError());
   return KJX_OK;
 }
 
-// ---- host-side folds of gathered shard summaries (same math as the kernels, compiled for the host) ----
+// the fold: filtered state entering shard `rank` and information of the shards after it (host and device)
 template <int D>
-int fold_filter_host(const double* Pinf, const double* summaries, int rank, double* out) {
+__host__ __device__ void fold_shards(const double* Pinf, const double* summaries, int64_t stride, int world, int rank,
+                                     double* state_out, double* info_out) {
   FiltState<double, D> x;
-  for (int i = 0; i < D; ++i) { x.m[i] = 0.0; for (int j = 0; j < D; ++j) x.P[i][j] = Pinf[i * D + j]; }
-  for (int r = 0; r < rank; ++r) {
-    FSum<double, D> s; fsum_unpack<double, D>(summaries + (size_t)r * FSum<double, D>::NS, s);
-    fsum_apply<double, D>(s, x);
-  }
-  for (int i = 0; i < D; ++i) out[i] = x.m[i];
-  for (int i = 0; i < D; ++i) for (int j = 0; j < D; ++j) out[D + i * D + j] = x.P[i][j];
-  return KJX_OK;
-}
-template <int D>
-int fold_smoother_host(const double* summaries, int world, int rank, double* out) {
-  FiltState<double, D> x;
-  for (int i = 0; i < D; ++i) { x.m[i] = 0.0; for (int j = 0; j < D; ++j) x.P[i][j] = 0.0; }
-  for (int r = world - 1; r > rank; --r) {
-    SSum<double, D> s; ssum_unpack<double, D>(summaries + (size_t)r * SSum<double, D>::NS, s);
-    ssum_apply<double, D>(s, x);
-  }
-  for (int i = 0; i < D; ++i) out[i] = x.m[i];
-  for (int i = 0; i < D; ++i) for (int j = 0; j < D; ++j) out[D + i * D + j] = x.P[i][j];
-  return KJX_OK;
-}
-
-template <int D>
-__global__ void fold_filter_kernel(StateArg<double, D> prior, const double* summaries, int64_t stride, int rank, double* out) {
-  if (threadIdx.x != 0) return;
-  FiltState<double, D> x;
-  for (int i = 0; i < D; ++i) { x.m[i] = prior.v[i]; for (int j = 0; j < D; ++j) x.P[i][j] = prior.v[D + i * D + j]; }
+  for (int i = 0; i < D; ++i) { x.m[i] = 0.0; for (int j = 0; j < D; ++j) x.P[i][j] = Pinf[i * D + j]; }   // sde_gp.py:265
   for (int r = 0; r < rank; ++r) {
     FSum<double, D> s; fsum_unpack<double, D>(summaries + (size_t)r * stride, s);
     fsum_apply<double, D>(s, x);
   }
-  for (int i = 0; i < D; ++i) out[i] = x.m[i];
-  for (int i = 0; i < D; ++i) for (int j = 0; j < D; ++j) out[D + i * D + j] = x.P[i][j];
-}
-template <int D>
-__global__ void fold_smoother_kernel(const double* summaries, int64_t stride, int world, int rank, double* out) {
-  if (threadIdx.x != 0) return;
-  FiltState<double, D> x;
-  for (int i = 0; i < D; ++i) { x.m[i] = 0.0; for (int j = 0; j < D; ++j) x.P[i][j] = 0.0; }
+  Info<double, D> f; info_zero<double, D>(f);
   for (int r = world - 1; r > rank; --r) {
-    SSum<double, D> s; ssum_unpack<double, D>(summaries + (size_t)r * stride, s);
-    ssum_apply<double, D>(s, x);
+    FSum<double, D> s; fsum_unpack<double, D>(summaries + (size_t)r * stride, s);
+    fsum_combine_info<double, D>(s, f, f);
   }
-  for (int i = 0; i < D; ++i) out[i] = x.m[i];
-  for (int i = 0; i < D; ++i) for (int j = 0; j < D; ++j) out[D + i * D + j] = x.P[i][j];
+  for (int i = 0; i < D; ++i) { state_out[i] = x.m[i]; info_out[i] = f.eta[i]; }
+  for (int i = 0; i < D; ++i) for (int j = 0; j < D; ++j) { state_out[D + i * D + j] = x.P[i][j]; info_out[D + i * D + j] = f.J[i][j]; }
 }
+template <int D> struct PinfArg { double v[D * D]; };
 template <int D>
-int fold_filter_dev(const kjx_model_t* m, const double* summaries, int64_t stride, int rank, double* out, cudaStream_t st) {
-  StateArg<double, D> s;
-  for (int i = 0; i < D; ++i) s.v[i] = 0.0;
-  for (int i = 0; i < D * D; ++i) s.v[D + i] = m->Pinf[i];
-  fold_filter_kernel<D><<<1, 32, 0, st>>>(s, summaries, stride, rank, out);
-  return cudaGetLastError() == cudaSuccess ? KJX_OK : KJX_ERR_CUDA;
+__global__ void fold_shards_kernel(PinfArg<D> pinf, const double* summaries, int64_t stride, int world, int rank,
+                                   double* state_out, double* info_out) {
+  if (threadIdx.x == 0) fold_shards<D>(pinf.v, summaries, stride, world, rank, state_out, info_out);
 }
 
 // ---- typed front ends shared by the _f64 / _f32 entry points ------------------------------------------
@@ -434,7 +454,8 @@ template <typename T>
 int run_T(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const T* site_mean, const T* site_cov,
           T* filt_mean, T* filt_cov, T* new_site_mean, T* new_site_cov, T* post_mean, T* post_var, T* nlml,
           void* ws, size_t ws_bytes, uint32_t flags, kjx_stream_t stream) {
-  if (!model_basic_ok(m) || N < 0 || !dt || !y || !nlml || !filt_mean || !filt_cov) return KJX_ERR_INVALID_ARG;
+  if (!model_basic_ok(m) || N < 0 || !dt || !y || !nlml) return KJX_ERR_INVALID_ARG;
+  if ((filt_mean == nullptr) != (filt_cov == nullptr)) return KJX_ERR_INVALID_ARG;
   if (!new_site_mean || !new_site_cov) return KJX_ERR_INVALID_ARG;
   if ((site_mean == nullptr) != (site_cov == nullptr)) return KJX_ERR_INVALID_ARG;
   if ((post_mean == nullptr) != (post_var == nullptr)) return KJX_ERR_INVALID_ARG;
@@ -572,80 +593,68 @@ int kjx_discretise_f32(const kjx_model_t* m, int64_t N, const float* dt, float* 
 }
 
 size_t kjx_filter_summary_doubles(int32_t d) { return (size_t)(d * d + d + d * (d + 1) / 2 + d + d * (d + 1) / 2); }
-size_t kjx_smoother_summary_doubles(int32_t d) { return (size_t)(d * d + d + d * (d + 1) / 2); }
 
-int kjx_filter_summary_f64(const kjx_model_t* m, int64_t N, const double* dt, const double* y, const uint8_t* mask,
-                           const double* site_mean, const double* site_cov, double* summary_out, void* ws,
-                           size_t ws_bytes, kjx_stream_t stream) {
+#define KJX_SMALL_DISPATCH(call32, call52)                     \
+  switch (small_kind(m)) {                                     \
+    case KJX_BLOCK_MATERN32: return call32;                    \
+    case KJX_BLOCK_MATERN52: return call52;                    \
+    default: return KJX_ERR_UNSUPPORTED;                       \
+  }
+
+int kjx_filter_summary_f64(const kjx_model_t* m, int64_t N, const double* dt, const double* y, const double* site_mean,
+                           const double* site_cov, double* summary_out, void* ws, size_t ws_bytes, kjx_stream_t stream) {
   if (!model_basic_ok(m) || N <= 0 || !dt || !y || !summary_out) return KJX_ERR_INVALID_ARG;
+  if ((site_mean == nullptr) != (site_cov == nullptr)) return KJX_ERR_INVALID_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  switch (small_kind(m)) {
-    case KJX_BLOCK_MATERN32: return small_filter_summary<double, KJX_BLOCK_MATERN32>(m, N, dt, y, mask, site_mean, site_cov, summary_out, ws, ws_bytes, st);
-    case KJX_BLOCK_MATERN52: return small_filter_summary<double, KJX_BLOCK_MATERN52>(m, N, dt, y, mask, site_mean, site_cov, summary_out, ws, ws_bytes, st);
-    default: return KJX_ERR_UNSUPPORTED;
-  }
+  KJX_SMALL_DISPATCH((shard_summary<double, KJX_BLOCK_MATERN32>(m, N, dt, y, site_mean, site_cov, summary_out, ws, ws_bytes, st)),
+                     (shard_summary<double, KJX_BLOCK_MATERN52>(m, N, dt, y, site_mean, site_cov, summary_out, ws, ws_bytes, st)))
 }
 
-int kjx_filter_apply_f64(const kjx_model_t* m, int64_t N, const double* dt, const double* y, const uint8_t* mask,
-                         const double* site_mean, const double* site_cov, const double* state_in, double dt_next,
-                         int32_t is_last_shard, double* filt_mean, double* filt_cov, double* out_site_mean,
-                         double* out_site_cov, double* smoother_summary_out, double* nlml_partial, void* ws,
-                         size_t ws_bytes, kjx_stream_t stream) {
-  if (!model_basic_ok(m) || N <= 0 || !dt || !y || !state_in || !filt_mean || !filt_cov || !smoother_summary_out || !nlml_partial)
-    return KJX_ERR_INVALID_ARG;
+int kjx_filter_apply_f64(const kjx_model_t* m, int64_t N, const double* dt, const double* y, const double* site_mean,
+                         const double* site_cov, const double* state_in, double* nlml_partial, void* ws, size_t ws_bytes,
+                         kjx_stream_t stream) {
+  if (!model_basic_ok(m) || N <= 0 || !dt || !y || !state_in || !nlml_partial) return KJX_ERR_INVALID_ARG;
+  if ((site_mean == nullptr) != (site_cov == nullptr)) return KJX_ERR_INVALID_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  switch (small_kind(m)) {
-    case KJX_BLOCK_MATERN32: return small_filter_apply<double, KJX_BLOCK_MATERN32>(m, N, dt, y, mask, site_mean, site_cov, state_in, dt_next, is_last_shard, filt_mean, filt_cov, out_site_mean, out_site_cov, smoother_summary_out, nlml_partial, ws, ws_bytes, st);
-    case KJX_BLOCK_MATERN52: return small_filter_apply<double, KJX_BLOCK_MATERN52>(m, N, dt, y, mask, site_mean, site_cov, state_in, dt_next, is_last_shard, filt_mean, filt_cov, out_site_mean, out_site_cov, smoother_summary_out, nlml_partial, ws, ws_bytes, st);
-    default: return KJX_ERR_UNSUPPORTED;
-  }
+  KJX_SMALL_DISPATCH((shard_filter<double, KJX_BLOCK_MATERN32>(m, N, dt, y, site_mean, site_cov, state_in, nlml_partial, ws, ws_bytes, st)),
+                     (shard_filter<double, KJX_BLOCK_MATERN52>(m, N, dt, y, site_mean, site_cov, state_in, nlml_partial, ws, ws_bytes, st)))
 }
 
-int kjx_smoother_apply_f64(const kjx_model_t* m, int64_t N, const double* dt, double dt_next, const double* filt_mean,
-                           const double* filt_cov, const double* y, const double* site_mean, const double* site_cov,
-                           const double* state_in, int32_t is_last_shard, double* smooth_mean, double* smooth_cov,
+int kjx_smoother_apply_f64(const kjx_model_t* m, int64_t N, const double* dt, const double* y, const double* site_mean,
+                           const double* site_cov, const double* info_in, double* post_mean, double* post_var,
                            double* new_site_mean, double* new_site_cov, void* ws, size_t ws_bytes, uint32_t flags,
                            kjx_stream_t stream) {
-  if (!model_basic_ok(m) || N <= 0 || !dt || !filt_mean || !filt_cov) return KJX_ERR_INVALID_ARG;
-  if (!is_last_shard && !state_in) return KJX_ERR_INVALID_ARG;
+  if (!model_basic_ok(m) || N <= 0 || !dt || !y || !info_in) return KJX_ERR_INVALID_ARG;
+  if ((site_mean == nullptr) != (site_cov == nullptr)) return KJX_ERR_INVALID_ARG;
+  if ((post_mean == nullptr) != (post_var == nullptr)) return KJX_ERR_INVALID_ARG;
+  if ((new_site_mean == nullptr) != (new_site_cov == nullptr)) return KJX_ERR_INVALID_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  switch (small_kind(m)) {
-    case KJX_BLOCK_MATERN32: return small_smoother_apply_shard<double, KJX_BLOCK_MATERN32>(m, N, dt, dt_next, filt_mean, filt_cov, y, site_mean, site_cov, state_in, is_last_shard, smooth_mean, smooth_cov, new_site_mean, new_site_cov, ws, ws_bytes, flags, st);
-    case KJX_BLOCK_MATERN52: return small_smoother_apply_shard<double, KJX_BLOCK_MATERN52>(m, N, dt, dt_next, filt_mean, filt_cov, y, site_mean, site_cov, state_in, is_last_shard, smooth_mean, smooth_cov, new_site_mean, new_site_cov, ws, ws_bytes, flags, st);
-    default: return KJX_ERR_UNSUPPORTED;
-  }
+  KJX_SMALL_DISPATCH((shard_smoother<double, KJX_BLOCK_MATERN32>(m, N, dt, y, site_mean, site_cov, info_in, post_mean, post_var, new_site_mean, new_site_cov, ws, ws_bytes, flags, st)),
+                     (shard_smoother<double, KJX_BLOCK_MATERN52>(m, N, dt, y, site_mean, site_cov, info_in, post_mean, post_var, new_site_mean, new_site_cov, ws, ws_bytes, flags, st)))
 }
 
-int kjx_fold_filter_summaries_host(int32_t d, const double* Pinf_host, const double* summaries_host, int32_t rank,
-                                   double* state_out_host) {
-  if (!Pinf_host || !summaries_host || !state_out_host || rank < 0) return KJX_ERR_INVALID_ARG;
-  if (d == 2) return fold_filter_host<2>(Pinf_host, summaries_host, rank, state_out_host);
-  if (d == 3) return fold_filter_host<3>(Pinf_host, summaries_host, rank, state_out_host);
-  return KJX_ERR_UNSUPPORTED;
-}
-int kjx_fold_smoother_summaries_host(int32_t d, const double* summaries_host, int32_t world, int32_t rank,
-                                     double* state_out_host) {
-  if (!summaries_host || !state_out_host || rank < 0 || world <= rank) return KJX_ERR_INVALID_ARG;
-  if (d == 2) return fold_smoother_host<2>(summaries_host, world, rank, state_out_host);
-  if (d == 3) return fold_smoother_host<3>(summaries_host, world, rank, state_out_host);
-  return KJX_ERR_UNSUPPORTED;
-}
-
-int kjx_fold_filter_summaries_f64(const kjx_model_t* m, const double* summaries, int64_t stride, int32_t rank,
-                                  double* state_out, kjx_stream_t stream) {
-  if (!model_basic_ok(m) || !summaries || !state_out || rank < 0) return KJX_ERR_INVALID_ARG;
+int kjx_fold_shard_summaries_host(const kjx_model_t* m, const double* summaries_host, int64_t stride, int32_t world,
+                                  int32_t rank, double* state_out_host, double* info_out_host) {
+  if (!model_basic_ok(m) || !summaries_host || !state_out_host || !info_out_host || rank < 0 || world <= rank) return KJX_ERR_INVALID_ARG;
   if (stride < (int64_t)kjx_filter_summary_doubles(m->state_dim)) return KJX_ERR_INVALID_ARG;
-  if (m->state_dim == 2) return fold_filter_dev<2>(m, summaries, stride, rank, state_out, (cudaStream_t)stream);
-  if (m->state_dim == 3) return fold_filter_dev<3>(m, summaries, stride, rank, state_out, (cudaStream_t)stream);
-  return KJX_ERR_UNSUPPORTED;
+  if (!small_kind(m)) return KJX_ERR_UNSUPPORTED;
+  if (m->state_dim == 2) fold_shards<2>(m->Pinf, summaries_host, stride, world, rank, state_out_host, info_out_host);
+  else fold_shards<3>(m->Pinf, summaries_host, stride, world, rank, state_out_host, info_out_host);
+  return KJX_OK;
 }
-int kjx_fold_smoother_summaries_f64(const kjx_model_t* m, const double* summaries, int64_t stride, int32_t world,
-                                    int32_t rank, double* state_out, kjx_stream_t stream) {
-  if (!model_basic_ok(m) || !summaries || !state_out || rank < 0 || world <= rank) return KJX_ERR_INVALID_ARG;
-  if (stride < (int64_t)kjx_smoother_summary_doubles(m->state_dim)) return KJX_ERR_INVALID_ARG;
-  if (m->state_dim == 2) fold_smoother_kernel<2><<<1, 32, 0, (cudaStream_t)stream>>>(summaries, stride, world, rank, state_out);
-  else if (m->state_dim == 3) fold_smoother_kernel<3><<<1, 32, 0, (cudaStream_t)stream>>>(summaries, stride, world, rank, state_out);
-  else return KJX_ERR_UNSUPPORTED;
+
+int kjx_fold_shard_summaries_f64(const kjx_model_t* m, const double* summaries, int64_t stride, int32_t world,
+                                 int32_t rank, double* state_out, double* info_out, kjx_stream_t stream) {
+  if (!model_basic_ok(m) || !summaries || !state_out || !info_out || rank < 0 || world <= rank) return KJX_ERR_INVALID_ARG;
+  if (stride < (int64_t)kjx_filter_summary_doubles(m->state_dim)) return KJX_ERR_INVALID_ARG;
+  if (!small_kind(m)) return KJX_ERR_UNSUPPORTED;
+  if (m->state_dim == 2) {
+    PinfArg<2> p; for (int i = 0; i < 4; ++i) p.v[i] = m->Pinf[i];
+    fold_shards_kernel<2><<<1, 32, 0, (cudaStream_t)stream>>>(p, summaries, stride, world, rank, state_out, info_out);
+  } else {
+    PinfArg<3> p; for (int i = 0; i < 9; ++i) p.v[i] = m->Pinf[i];
+    fold_shards_kernel<3><<<1, 32, 0, (cudaStream_t)stream>>>(p, summaries, stride, world, rank, state_out, info_out);
+  }
   return cudaGetLastError() == cudaSuccess ? KJX_OK : KJX_ERR_CUDA;
 }
 
@@ -654,9 +663,11 @@ int kjx_run_host_scratch_bytes(const kjx_model_t* m, int64_t N, int dtype_bytes,
   int rc = kjx_workspace_bytes(m, N, dtype_bytes, &ws);
   if (rc != KJX_OK) return rc;
   const size_t d = (size_t)m->state_dim, n = (size_t)std::max<int64_t>(N, 1);
-  // dt, y, site_mean, site_var, new_site_mean, new_site_var, post_mean, post_var (8 N) + filter output + nlml
-  *bytes = round_up(ws, 256) + 10 * round_up(n * dtype_bytes, 256) + round_up(n * d * dtype_bytes, 256) +
-           round_up(n * d * d * dtype_bytes, 256) + 256;
+  // dt, y, site_mean, site_var, new_site_mean, new_site_var, post_mean, post_var (8 N) + nlml; plus a dense
+  // filter output only when the model needs the one-chain filter (first iteration of non-Gaussian models)
+  const bool dense = !gauss_ep(m);
+  *bytes = round_up(ws, 256) + 10 * round_up(n * dtype_bytes, 256) +
+           (dense ? round_up(n * d * dtype_bytes, 256) + round_up(n * d * d * dtype_bytes, 256) : 0) + 256;
   return KJX_OK;
 }
 
@@ -680,7 +691,9 @@ int kjx_run_host_f64(const kjx_model_t* m, int64_t N, const double* dt_host, con
   void* ws = take(ws_bytes);
   double *dt = (double*)take(nb), *y = (double*)take(nb), *sm = (double*)take(nb), *sv = (double*)take(nb);
   double *nsm = (double*)take(nb), *nsv = (double*)take(nb), *pm = (double*)take(nb), *pv = (double*)take(nb);
-  double *fm = (double*)take(n * d * 8), *fP = (double*)take(n * d * d * 8), *nlml = (double*)take(8);
+  const bool dense = !gauss_ep(m);
+  double *fm = dense ? (double*)take(n * d * 8) : nullptr, *fP = dense ? (double*)take(n * d * d * 8) : nullptr;
+  double* nlml = (double*)take(8);
   KJX_CUDA_CHECK(cudaMemcpyAsync(dt, dt_host, n * 8, cudaMemcpyHostToDevice, st));
   KJX_CUDA_CHECK(cudaMemcpyAsync(y, y_host, n * 8, cudaMemcpyHostToDevice, st));
   if (site_mean_host) {

@@ -1,0 +1,309 @@
+// kjx_fused_kernels.cuh — the fused run() iteration for small state dimension (d = 2, 3) on sm_100a:
+// filter (stored sites) -> RTS smoother -> per-step site update, as ONE parallel-in-time scan.
+//
+//   R1 fused_reduce     every thread folds its L steps into a filter element (A,b,C,eta,J); a block-wide
+//                       PREFIX scan gives the element of everything before the thread's chunk and a SUFFIX
+//                       scan the element of everything after it (kjx_small_math.cuh, "two-filter identity")
+//   R2 fused_blockscan  one CTA: prefix + suffix scans of the block totals, shard total
+//   R3 fused_filter     rebuild the true incoming (m,P), run the reference filter recursion verbatim
+//                       (sde_gp.py:276-301) over the chunk, accumulate log Z, park the filtered moments in a
+//                       private warp-transposed, symmetric-packed scratch (9 instead of 12 scalars per step at
+//                       d=3, every access a fully coalesced 256-byte warp transaction)
+//   R4 fused_smoother   smoothed state of the chunk's last step from the suffix information, then the
+//                       reference RTS recursion (sde_gp.py:351-361) backwards + site update (sde_gp.py:373-379)
+//
+// HBM streaming: the per-step scalar arrays keep the reference layout (dt[N], y[N,1], site_mean[N,1,1],
+// site_cov[N,1,1], outputs alike); a thread owns L consecutive steps, so it moves them as 256-bit vectors
+// (4 steps per LDG.256/STG.256 — exactly one 32-byte sector per access, nothing fetched twice).
+#pragma once
+#include "kjx_small_kernels.cuh"
+
+namespace kjx {
+
+// ------------------------------------------------------------------------------------------------
+// 4 consecutive steps of a per-step scalar array
+template <typename T> struct Vec4 { T x[4]; };
+
+__device__ __forceinline__ Vec4<double> load4(const double* p) {
+  Vec4<double> v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(v.x[0]), "=d"(v.x[1]), "=d"(v.x[2]), "=d"(v.x[3]) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ Vec4<float> load4(const float* p) {
+  const float4 f = __ldg(reinterpret_cast<const float4*>(p));
+  Vec4<float> v; v.x[0] = f.x; v.x[1] = f.y; v.x[2] = f.z; v.x[3] = f.w;
+  return v;
+}
+__device__ __forceinline__ void store4(double* p, const Vec4<double>& v) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(v.x[0]), "d"(v.x[1]), "d"(v.x[2]), "d"(v.x[3]) : "memory");
+}
+__device__ __forceinline__ void store4(float* p, const Vec4<float>& v) {
+  *reinterpret_cast<float4*>(p) = make_float4(v.x[0], v.x[1], v.x[2], v.x[3]);
+}
+template <typename T, bool VEC> __device__ __forceinline__ Vec4<T> load4v(const T* p) {
+  if (VEC) return load4(p);
+  Vec4<T> v;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) v.x[j] = p[j];
+  return v;
+}
+template <typename T, bool VEC> __device__ __forceinline__ void store4v(T* p, const Vec4<T>& v) {
+  if (VEC) { store4(p, v); return; }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) p[j] = v.x[j];
+}
+
+// ------------------------------------------------------------------------------------------------
+// private scratch for the filtered moments: [warp][step][element][lane], element = m (D) then upper(P)
+template <int D> struct Packed { static constexpr int NP = D + D * (D + 1) / 2; };
+
+template <typename T, int D>
+__device__ __forceinline__ void xf_store(T* base, const FiltState<T, D>& x) {   // base already points at [warp][step][0][lane]
+  int e = 0;
+#pragma unroll
+  for (int i = 0; i < D; ++i) base[32 * e++] = x.m[i];
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = i; j < D; ++j) base[32 * e++] = x.P[i][j];
+}
+template <typename T, int D>
+__device__ __forceinline__ void xf_load(const T* base, T (&m)[D], T (&P)[D][D]) {
+  int e = 0;
+#pragma unroll
+  for (int i = 0; i < D; ++i) m[i] = __ldcs(base + 32 * e++);
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = i; j < D; ++j) { const T v = __ldcs(base + 32 * e++); P[i][j] = v; P[j][i] = v; }
+}
+
+template <typename T, int D> struct FusedArgs {
+  SmallArgs<T, D> a;        // prior, site model, data pointers, scan workspace (see kjx_small_kernels.cuh)
+  T* f_thread_suffix;       // [NS][cstride] exclusive suffix element of every chunk within its block
+  T* f_block_suffix;        // [NS][bstride] exclusive suffix element of every block within the shard
+  T* xf;                    // filtered moments, private layout
+  const T* s_info_in;       // [D + D*D] information (eta, J) of all later shards about this shard's last state
+  int vec_ok;               // every per-step array is 32-byte (fp64) / 16-byte (fp32) aligned
+};
+
+template <typename T, int D>
+__device__ __forceinline__ void load_info(const T* p, Info<T, D>& f) {
+#pragma unroll
+  for (int i = 0; i < D; ++i) f.eta[i] = p[i];
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) f.J[i][j] = p[D + i * D + j];
+}
+
+// ------------------------------------------------------------------------------------------------
+// R1
+template <typename T, int KIND, bool VEC>
+__global__ void __launch_bounds__(KJX_BLOCK) fused_reduce_kernel(const FusedArgs<T, BlockDim<KIND>::D> fa) {
+  constexpr int D = BlockDim<KIND>::D;
+  using S = FSum<T, D>;
+  const SmallArgs<T, D>& a = fa.a;
+  __shared__ T smem[S::NS * (KJX_BLOCK / 32 + 1)];
+  const int64_t c = (int64_t)blockIdx.x * KJX_BLOCK + threadIdx.x;
+  const int64_t s0 = c * a.L;
+  const int64_t s1 = (s0 + a.L < a.N) ? s0 + a.L : a.N;
+  T Pinf[D][D]; load_pinf<T, D>(a.prior, Pinf);
+  S mine; fsum_identity<T, D>(mine);
+  const T* ysrc = a.gaussian_init ? a.y : a.site_mean;
+  const T lik_hyp = T(a.site.lik_hyp);
+  int64_t k = s0;
+  for (; k + 4 <= s1; k += 4) {
+    const Vec4<T> vdt = load4v<T, VEC>(a.dt + k);
+    const Vec4<T> vy = load4v<T, VEC>(ysrc + k);
+    Vec4<T> vr;
+    if (!a.gaussian_init) vr = load4v<T, VEC>(a.site_var + k);
+    uint32_t mk = 0;
+    if (a.mask) mk = (uint32_t)a.mask[k] | ((uint32_t)a.mask[k + 1] << 8) | ((uint32_t)a.mask[k + 2] << 16) | ((uint32_t)a.mask[k + 3] << 24);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      T F[D][D];
+      Transition<T, KIND>::eval(vdt.x[j], a.prior.lam, F);
+      fsum_fold_step<T, D>(mine, F, Pinf, vy.x[j], a.gaussian_init ? lik_hyp : vr.x[j], ((mk >> (8 * j)) & 0xff) != 0);
+    }
+  }
+  for (; k < s1; ++k) {
+    T F[D][D];
+    Transition<T, KIND>::eval(a.dt[k], a.prior.lam, F);
+    T yt, R; step_site<T, D>(a, k, yt, R);
+    fsum_fold_step<T, D>(mine, F, Pinf, yt, R, a.mask ? (a.mask[k] != 0) : false);
+  }
+  {
+    S excl, total;
+    block_scan_exclusive<S, false, KJX_BLOCK>(mine, excl, total, smem);
+    if (c < a.nchunks) sum_store<S>(a.f_thread_prefix, a.cstride, c, excl);
+    if (threadIdx.x == 0) sum_store<S>(a.f_block_total, a.bstride, blockIdx.x, total);
+  }
+  {
+    S excl, total;
+    block_scan_exclusive<S, true, KJX_BLOCK>(mine, excl, total, smem);
+    if (c < a.nchunks) sum_store<S>(fa.f_thread_suffix, a.cstride, c, excl);
+  }
+}
+
+// R2
+template <typename T, int D>
+__global__ void __launch_bounds__(KJX_SCAN_BLOCK) fused_blockscan_kernel(const FusedArgs<T, D> fa) {
+  using S = FSum<T, D>;
+  __shared__ T smem[S::NS * (KJX_SCAN_BLOCK / 32 + 1)];
+  const SmallArgs<T, D>& a = fa.a;
+  blockscan_body<S, false>(a.f_block_total, a.f_block_prefix, a.f_shard_total, a.nblocks, a.bstride, smem);
+  __syncthreads();
+  blockscan_body<S, true>(a.f_block_total, fa.f_block_suffix, a.f_shard_total, a.nblocks, a.bstride, smem);
+}
+
+// ------------------------------------------------------------------------------------------------
+// R3
+template <typename T, int KIND, bool GAUSS_EP, bool VEC>
+__global__ void __launch_bounds__(KJX_BLOCK) fused_filter_kernel(const FusedArgs<T, BlockDim<KIND>::D> fa) {
+  constexpr int D = BlockDim<KIND>::D;
+  constexpr int NP = Packed<D>::NP;
+  using FS = FSum<T, D>;
+  const SmallArgs<T, D>& a = fa.a;
+  __shared__ T red[KJX_BLOCK / 32];
+  const int64_t c = (int64_t)blockIdx.x * KJX_BLOCK + threadIdx.x;
+  const int64_t s0 = c * a.L;
+  const int64_t s1 = (s0 + a.L < a.N) ? s0 + a.L : a.N;
+  T Pinf[D][D]; load_pinf<T, D>(a.prior, Pinf);
+  T nl = T(0);
+  if (s0 < s1) {
+    FiltState<T, D> x; load_state<T, D>(a.f_state_in, x);
+    { FS bp; sum_load<FS>(a.f_block_prefix, a.bstride, blockIdx.x, bp); fsum_apply<T, D>(bp, x); }
+    { FS tp; sum_load<FS>(a.f_thread_prefix, a.cstride, c, tp); fsum_apply<T, D>(tp, x); }
+    T* xf = fa.xf + ((c >> 5) * (int64_t)a.L * NP) * 32 + (c & 31);
+    const T* ysrc = a.gaussian_init ? a.y : a.site_mean;
+    const T lik_hyp = T(a.site.lik_hyp);
+    int64_t k = s0;
+    for (; k + 4 <= s1; k += 4) {
+      const Vec4<T> vdt = load4v<T, VEC>(a.dt + k);
+      const Vec4<T> vy = load4v<T, VEC>(a.y + k);
+      Vec4<T> vm, vr;
+      if (!a.gaussian_init) { vm = load4v<T, VEC>(a.site_mean + k); vr = load4v<T, VEC>(a.site_var + k); }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        T F[D][D];
+        Transition<T, KIND>::eval(vdt.x[j], a.prior.lam, F);
+        filter_predict<T, D>(F, Pinf, x);                                   // sde_gp.py:276-278
+        const T pm = x.m[0], pv = x.P[0][0];
+        const T smean = a.gaussian_init ? vy.x[j] : vm.x[j], svar = a.gaussian_init ? lik_hyp : vr.x[j];
+        nl += GAUSS_EP ? gaussian_moment_match<T>(vy.x[j], pm, pv, lik_hyp).lml     // sde_gp.py:287 (log Z only)
+                       : filter_loglik<T>(a.site, vy.x[j], pm, pv);
+        filter_update<T, D>(x, smean, svar);                                // sde_gp.py:292-296
+        xf_store<T, D>(xf + (k - s0 + j) * NP * 32, x);
+      }
+    }
+    (void)ysrc;
+    for (; k < s1; ++k) {
+      T F[D][D];
+      Transition<T, KIND>::eval(a.dt[k], a.prior.lam, F);
+      filter_predict<T, D>(F, Pinf, x);
+      T smean, svar;
+      nl += filter_step_body<T, D, GAUSS_EP>(a, k, x, false, smean, svar);
+      xf_store<T, D>(xf + (k - s0) * NP * 32, x);
+    }
+  }
+  T s = nl;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    T t = T(0);
+    for (int w = 0; w < KJX_BLOCK / 32; ++w) t += red[w];
+    a.block_nlml[blockIdx.x] = t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// R4: outputs of one smoothed step (sde_gp.py:368-379)
+template <typename T, int D, bool GAUSS_EP>
+__device__ __forceinline__ void smoothed_outputs(const SmallArgs<T, D>& a, const FiltState<T, D>& x, T y, T prev_mean,
+                                                 T prev_var, T& pm, T& pv, T& nsm, T& nsv) {
+  pm = x.m[0]; pv = x.P[0][0];
+  if (GAUSS_EP) {
+    nsm = y; nsv = T(a.site.lik_hyp);
+    const T damping = T(a.site.damping);
+    if (damping != T(1)) damp<T>(inv1(nsv), nsm, inv1(prev_var), prev_mean, damping, T(0), nsm, nsv);
+  } else {
+    const SiteOut<T> o = site_update<T>(a.site, y, pm, pv, true, prev_mean, prev_var);
+    nsm = o.mean; nsv = o.var;
+  }
+}
+
+template <typename T, int KIND, bool GAUSS_EP, bool VEC>
+__global__ void __launch_bounds__(KJX_BLOCK) fused_smoother_kernel(const FusedArgs<T, BlockDim<KIND>::D> fa) {
+  constexpr int D = BlockDim<KIND>::D;
+  constexpr int NP = Packed<D>::NP;
+  using FS = FSum<T, D>;
+  const SmallArgs<T, D>& a = fa.a;
+  const int64_t c = (int64_t)blockIdx.x * KJX_BLOCK + threadIdx.x;
+  const int64_t s0 = c * a.L;
+  const int64_t s1 = (s0 + a.L < a.N) ? s0 + a.L : a.N;
+  if (s0 >= s1) return;
+  T Pinf[D][D]; load_pinf<T, D>(a.prior, Pinf);
+  const T* xf = fa.xf + ((c >> 5) * (int64_t)a.L * NP) * 32 + (c & 31);
+  const T lik_hyp = T(a.site.lik_hyp);
+  const bool upd = a.update_sites != 0, post = a.smooth_mean != nullptr;
+
+  // smoothed state of the chunk's last step: filtered moments x information of everything after it
+  FiltState<T, D> x;
+  int64_t k = s1 - 1;
+  {
+    Info<T, D> info; load_info<T, D>(fa.s_info_in, info);
+    { FS bs; sum_load<FS>(fa.f_block_suffix, a.bstride, blockIdx.x, bs); fsum_combine_info<T, D>(bs, info, info); }
+    { FS ts; sum_load<FS>(fa.f_thread_suffix, a.cstride, c, ts); fsum_combine_info<T, D>(ts, info, info); }
+    xf_load<T, D>(xf + (k - s0) * NP * 32, x.m, x.P);
+    info_smooth<T, D>(info, x);
+    T pm, pv, nsm, nsv, pmean, pvar;
+    step_site<T, D>(a, k, pmean, pvar);
+    smoothed_outputs<T, D, GAUSS_EP>(a, x, a.y[k], pmean, pvar, pm, pv, nsm, nsv);
+    if (post) { a.smooth_mean[k] = pm; a.smooth_cov[k] = pv; }
+    if (upd) { a.new_site_mean[k] = nsm; a.new_site_var[k] = nsv; }
+  }
+  T dt_after = a.dt[k];           // dt of the step just done = transition INTO it = what step k-1 needs (sde_gp.py:337)
+  // the remaining len-1 steps: scalar I/O down to a multiple of 4, then 256-bit groups
+  const int64_t ngroups = (k - s0) / 4;
+  for (--k; k >= s0 + 4 * ngroups; --k) {
+    T F[D][D], mf[D], Pf[D][D];
+    Transition<T, KIND>::eval(dt_after, a.prior.lam, F);
+    xf_load<T, D>(xf + (k - s0) * NP * 32, mf, Pf);
+    SmoothGain<T, D> g;
+    smoother_gain<T, D>(F, Pinf, mf, Pf, g);
+    smoother_step<T, D>(g, mf, Pf, x);
+    T pm, pv, nsm, nsv, pmean, pvar;
+    step_site<T, D>(a, k, pmean, pvar);
+    smoothed_outputs<T, D, GAUSS_EP>(a, x, a.y[k], pmean, pvar, pm, pv, nsm, nsv);
+    if (post) { a.smooth_mean[k] = pm; a.smooth_cov[k] = pv; }
+    if (upd) { a.new_site_mean[k] = nsm; a.new_site_var[k] = nsv; }
+    dt_after = a.dt[k];
+  }
+  for (int64_t g4 = ngroups - 1; g4 >= 0; --g4) {
+    const int64_t k0 = s0 + 4 * g4;
+    const Vec4<T> vdt = load4v<T, VEC>(a.dt + k0);
+    const Vec4<T> vy = load4v<T, VEC>(a.y + k0);
+    Vec4<T> vm, vr, opm, opv, onm, onv;
+    if (!a.gaussian_init) { vm = load4v<T, VEC>(a.site_mean + k0); vr = load4v<T, VEC>(a.site_var + k0); }
+#pragma unroll
+    for (int j = 3; j >= 0; --j) {
+      T F[D][D], mf[D], Pf[D][D];
+      Transition<T, KIND>::eval(dt_after, a.prior.lam, F);
+      xf_load<T, D>(xf + (k0 + j - s0) * NP * 32, mf, Pf);
+      SmoothGain<T, D> g;
+      smoother_gain<T, D>(F, Pinf, mf, Pf, g);                              // sde_gp.py:351-359
+      smoother_step<T, D>(g, mf, Pf, x);                                    // sde_gp.py:360-361
+      smoothed_outputs<T, D, GAUSS_EP>(a, x, vy.x[j], a.gaussian_init ? vy.x[j] : vm.x[j],
+                                       a.gaussian_init ? lik_hyp : vr.x[j], opm.x[j], opv.x[j], onm.x[j], onv.x[j]);
+      dt_after = vdt.x[j];
+    }
+    if (post) { store4v<T, VEC>(a.smooth_mean + k0, opm); store4v<T, VEC>(a.smooth_cov + k0, opv); }
+    if (upd) { store4v<T, VEC>(a.new_site_mean + k0, onm); store4v<T, VEC>(a.new_site_var + k0, onv); }
+  }
+}
+
+}  // namespace kjx

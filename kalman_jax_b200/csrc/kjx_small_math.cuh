@@ -467,6 +467,117 @@ KJX_HDN void fsum_apply(const FSum<T, D>& s, FiltState<T, D>& x) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// "Backward information" form of the smoother boundary (two-filter identity).  The (eta, J) part of
+// the combination of all filter elements AFTER step k is the likelihood of every later observation as
+// a function of x_k:  p(y_{k+1:N} | x_k) ∝ exp(-x'Jx/2 + eta'x).  Multiplying it into the filtered
+// N(m_k, P_k) gives the smoothed marginal of step k — mathematically identical to what the RTS
+// recursion (sde_gp.py:360-361) delivers there — so the smoother needs no scan of its own when it
+// runs right after the filter scan: a SUFFIX scan over the same elements provides its boundary states.
+template <typename T, int D> struct Info { T eta[D]; T J[D][D]; };
+
+template <typename T, int D> KJX_HD void info_zero(Info<T, D>& f) {
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    f.eta[i] = T(0);
+#pragma unroll
+    for (int j = 0; j < D; ++j) f.J[i][j] = T(0);
+  }
+}
+template <typename T, int D> KJX_HD void info_of(const FSum<T, D>& s, Info<T, D>& f) {
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    f.eta[i] = s.eta[i];
+#pragma unroll
+    for (int j = 0; j < D; ++j) f.J[i][j] = s.J[i][j];
+  }
+}
+// information of (si ⊗ later) about the state entering si, given only the information part of `later`
+template <typename T, int D>
+KJX_HDN void fsum_combine_info(const FSum<T, D>& si, const Info<T, D>& fj, Info<T, D>& out) {
+  T M[D][D], Minv[D][D], T2[D][D], W[D][D], u[D], w[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      T v = (i == j) ? T(1) : T(0);
+#pragma unroll
+      for (int k = 0; k < D; ++k) v += si.C[i][k] * fj.J[k][j];
+      M[i][j] = v;
+    }
+  inv_gj<T, D>(M, Minv);
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      T v = si.A[0][i] * Minv[j][0];
+#pragma unroll
+      for (int k = 1; k < D; ++k) v += si.A[k][i] * Minv[j][k];
+      T2[i][j] = v;
+    }
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    T v = fj.eta[i];
+#pragma unroll
+    for (int k = 0; k < D; ++k) v -= fj.J[i][k] * si.b[k];
+    u[i] = v;
+  }
+  mat_vec<T, D>(T2, u, w);
+  mat_mul<T, D>(T2, fj.J, W);
+  Info<T, D> r;
+#pragma unroll
+  for (int i = 0; i < D; ++i) r.eta[i] = w[i] + si.eta[i];
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = i; j < D; ++j) {
+      T v = si.J[i][j];
+#pragma unroll
+      for (int k = 0; k < D; ++k) v += W[i][k] * si.A[k][j];
+      r.J[i][j] = v; r.J[j][i] = v;
+    }
+  out = r;
+}
+// smoothed (m, P) of a step from its filtered (m, P) and the information of everything after it:
+//   P_s = (I + P J)^-1 P ,  m_s = (I + P J)^-1 (m + P eta)
+template <typename T, int D>
+KJX_HDN void info_smooth(const Info<T, D>& f, FiltState<T, D>& x) {
+  T M[D][D], Minv[D][D], u[D], w[D], Pn[D][D];
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      T v = (i == j) ? T(1) : T(0);
+#pragma unroll
+      for (int k = 0; k < D; ++k) v += x.P[i][k] * f.J[k][j];
+      M[i][j] = v;
+    }
+  inv_gj<T, D>(M, Minv);
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    T v = x.m[i];
+#pragma unroll
+    for (int k = 0; k < D; ++k) v += x.P[i][k] * f.eta[k];
+    u[i] = v;
+  }
+  mat_vec<T, D>(Minv, u, w);
+#pragma unroll
+  for (int i = 0; i < D; ++i)
+#pragma unroll
+    for (int j = i; j < D; ++j) {
+      T v = Minv[i][0] * x.P[0][j];
+#pragma unroll
+      for (int k = 1; k < D; ++k) v += Minv[i][k] * x.P[k][j];
+      Pn[i][j] = v; Pn[j][i] = v;
+    }
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    x.m[i] = w[i];
+#pragma unroll
+    for (int j = 0; j < D; ++j) x.P[i][j] = Pn[i][j];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Smoother scan element / chunk summary: smoothed(start of chunk) = E smoothed(next chunk) + g, cov E P E^T + L
 template <typename T, int D> struct SSum {
   T E[D][D]; T g[D]; T L[D][D];

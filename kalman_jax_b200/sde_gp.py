@@ -295,12 +295,13 @@ class SDEGP(object):
         sm_in = sv_in = None
         if sites_in is not None:
             sm_in, sv_in = self._dev(sites_in[0]), self._dev(sites_in[1])
-        bufs = getattr(self, "_run_bufs", None)
-        if bufs is None or bufs[0].shape[0] != N or bufs[0].shape[1] != d:
-            bufs = (torch.empty(N, d, 1, dtype=self.dtype, device=self.device),
-                    torch.empty(N, d, d, dtype=self.dtype, device=self.device))
-            self._run_bufs = bufs
-        fm, fP = bufs
+        # run() only uses the filtered moments internally (sde_gp.py:183-187): the fused scan keeps them packed
+        # in its workspace.  Dense buffers are needed only by the one-chain filter that initialises the sites of
+        # a non-Gaussian model on the first iteration.
+        fm = fP = None
+        if sites_in is None and not (self.likelihood.kjx_code == _lib.LIK_GAUSSIAN and self.sites.kjx_code == _lib.INF_EP):
+            fm = torch.empty(N, d, 1, dtype=self.dtype, device=self.device)
+            fP = torch.empty(N, d, d, dtype=self.dtype, device=self.device)
         new_sm = torch.empty(N, f, 1, dtype=self.dtype, device=self.device)
         new_sv = torch.empty(N, f, f, dtype=self.dtype, device=self.device)
         pm = pv = None

@@ -1,14 +1,15 @@
 """Time-sharded filter / smoother iteration: one contiguous block of time steps per GPU (one process per
-GPU), two fixed-size all-gathers per iteration:
+GPU) and ONE fixed-size all-gather per iteration (tightened by the two-filter identity):
 
-    local filter summary (A,b,C,eta,J)  --all-gather-->  fold ranks < me  -> filtered state entering my shard
-    local filter apply (+ smoother fold) -> local smoother summary (E,g,L) + partial nlml
-                                        --all-gather-->  fold ranks > me  -> smoothed state entering from the right
-    local smoother apply + site update
+    local fold + scan -> the shard's filter element (A,b,C,eta,J), 27 doubles at d = 3
+            --all-gather-->  fold ranks < me -> filtered state entering my shard
+                             fold ranks > me -> information (eta, J) about my last state
+    local filter recursion (log Z, filtered moments parked in the workspace)
+    local RTS recursion backwards + site update
 
-No bulk data ever crosses NVLink: the payloads are 28 and 19 doubles per rank at d = 3.  With world == 1
-the same three library calls run without any collective.  The reference has no counterpart (it is a
-single sequential loop, sde_gp.py:271,349).
+No bulk data ever crosses NVLink.  The shards' partial nlml values are summed with one scalar all-reduce
+off the critical path.  With world == 1 the same calls run without any collective.  The reference has no
+counterpart (it is a single sequential loop, sde_gp.py:271,349).
 """
 import ctypes as C
 
@@ -39,52 +40,46 @@ class ShardedIteration(object):
         self.site_mean = None if site_mean is None else torch.as_tensor(site_mean, dtype=torch.float64, device=self.device).contiguous()
         self.site_var = None if site_var is None else torch.as_tensor(site_var, dtype=torch.float64, device=self.device).contiguous()
         self.new_site_mean, self.new_site_var = z(self.N), z(self.N)
-        self.filt_mean, self.filt_cov = z(self.N, d), z(self.N, d, d)
         self.post_mean, self.post_var = z(self.N), z(self.N)
         L = _lib.lib()
-        self.fns, self.sns = int(L.kjx_filter_summary_doubles(d)), int(L.kjx_smoother_summary_doubles(d))
+        self.fns = int(L.kjx_filter_summary_doubles(d))
         self.fmsg = torch.zeros(self.fns, dtype=torch.float64, device=self.device)
-        self.smsg = torch.zeros(self.sns + 1, dtype=torch.float64, device=self.device)   # + partial nlml
-        self.f_state, self.s_state = z(d + d * d), z(d + d * d)
+        self.f_state, self.s_info = z(d + d * d), z(d + d * d)
         self.ws, _ = _workspace(self.model, self.N, torch.float64, self.device)
-        self.nlml = torch.zeros(1, dtype=torch.float64, device=self.device)
-        self.launches_per_iteration = 3 + 1 + 4 + 1 + 2   # see bench.py / DESIGN.md "kernel list"
+        self.nlml_part = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self.nlml = self.nlml_part
+        # kernels per iteration: reduce, blockscan, copy | fold | copy, filter, nlml-reduce | copy, smoother
+        self.launches_per_iteration = 9
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def iteration(self, update_sites=True, events=None):
+    def iteration(self, update_sites=True, events=None, reduce_nlml=None):
         """One filter -> smoother -> site-update pass over this shard.  `events`: optional list of 4
-        torch.cuda.Event recorded at the phase boundaries (summary | filter apply | smoother apply)."""
+        torch.cuda.Event recorded at the phase boundaries (reduce+scan | filter | smoother).
+        reduce_nlml(t): sums the shards' partial nlml (all-reduce) — None for world == 1."""
         L, m, st = _lib.lib(), self.model.ref(), self._stream()
-        N, p = C.c_int64(self.N), _lib.ptr
-        last = 1 if self.rank == self.world - 1 else 0
+        N, p, wsb = C.c_int64(self.N), _lib.ptr, C.c_size_t(self.ws.numel())
         if events:
             events[0].record()
-        _lib.check(L.kjx_filter_summary_f64(m, N, p(self.dt), p(self.y), None, p(self.site_mean), p(self.site_var),
-                                            p(self.fmsg), p(self.ws), C.c_size_t(self.ws.numel()), st), "kjx_filter_summary")
+        _lib.check(L.kjx_filter_summary_f64(m, N, p(self.dt), p(self.y), p(self.site_mean), p(self.site_var),
+                                            p(self.fmsg), p(self.ws), wsb, st), "kjx_filter_summary")
         allf = self.gather(self.fmsg) if self.gather else self.fmsg.reshape(1, -1)
-        _lib.check(L.kjx_fold_filter_summaries_f64(m, p(allf), C.c_int64(allf.shape[1]), self.rank, p(self.f_state), st),
-                   "kjx_fold_filter_summaries")
+        _lib.check(L.kjx_fold_shard_summaries_f64(m, p(allf), C.c_int64(allf.shape[1]), self.world, self.rank,
+                                                  p(self.f_state), p(self.s_info), st), "kjx_fold_shard_summaries")
         if events:
             events[1].record()
-        _lib.check(L.kjx_filter_apply_f64(m, N, p(self.dt), p(self.y), None, p(self.site_mean), p(self.site_var),
-                                          p(self.f_state), C.c_double(self.dt_next), last, p(self.filt_mean),
-                                          p(self.filt_cov), None, None, p(self.smsg), p(self.smsg[self.sns:]),
-                                          p(self.ws), C.c_size_t(self.ws.numel()), st), "kjx_filter_apply")
-        alls = self.gather(self.smsg) if self.gather else self.smsg.reshape(1, -1)
-        _lib.check(L.kjx_fold_smoother_summaries_f64(m, p(alls), C.c_int64(alls.shape[1]), self.world, self.rank,
-                                                     p(self.s_state), st), "kjx_fold_smoother_summaries")
+        _lib.check(L.kjx_filter_apply_f64(m, N, p(self.dt), p(self.y), p(self.site_mean), p(self.site_var),
+                                          p(self.f_state), p(self.nlml_part), p(self.ws), wsb, st), "kjx_filter_apply")
         if events:
             events[2].record()
         flags = 0 if update_sites else _lib.FLAG_NO_SITE_UPDATE
-        _lib.check(L.kjx_smoother_apply_f64(m, N, p(self.dt), C.c_double(self.dt_next), p(self.filt_mean), p(self.filt_cov),
-                                            p(self.y), p(self.site_mean), p(self.site_var), p(self.s_state), last,
-                                            p(self.post_mean), p(self.post_var), p(self.new_site_mean), p(self.new_site_var),
-                                            p(self.ws), C.c_size_t(self.ws.numel()), C.c_uint32(flags), st), "kjx_smoother_apply")
+        _lib.check(L.kjx_smoother_apply_f64(m, N, p(self.dt), p(self.y), p(self.site_mean), p(self.site_var),
+                                            p(self.s_info), p(self.post_mean), p(self.post_var), p(self.new_site_mean),
+                                            p(self.new_site_var), p(self.ws), wsb, C.c_uint32(flags), st), "kjx_smoother_apply")
         if events:
             events[3].record()
-        self.nlml = alls[:, self.sns].sum()       # partial nlml of every shard rode along in the second gather
+        self.nlml = reduce_nlml(self.nlml_part) if reduce_nlml else self.nlml_part
         if update_sites:
             if self.site_mean is None:
                 self.site_mean, self.site_var = torch.empty_like(self.new_site_mean), torch.empty_like(self.new_site_var)

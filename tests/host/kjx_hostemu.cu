@@ -11,7 +11,7 @@ using namespace kjx;
 
 template <int KIND>
 static void emu_run(double lam, const double* Pinf_, int64_t N, int L, const double* dt, const double* ytilde,
-                    const double* R, const uint8_t* mask, double* fm, double* fP, double* sm, double* sP) {
+                    const double* R, const uint8_t* mask, double* fm, double* fP, double* sm, double* sP, int two_filter) {
   constexpr int D = BlockDim<KIND>::D;
   double Pinf[D][D];
   for (int i = 0; i < D; ++i) for (int j = 0; j < D; ++j) Pinf[i][j] = Pinf_[i * D + j];
@@ -71,10 +71,37 @@ static void emu_run(double lam, const double* Pinf_, int64_t N, int L, const dou
     }
     for (int64_t c = 0; c < nch; ++c) { if (c == nch - 1) ssum_identity<double, D>(suffix[c]); else suffix[c] = inc[c + 1]; }
   }
+  // two-filter variant: boundary states from a suffix scan over the FILTER elements
+  std::vector<Info<double, D>> finfo(nch);
+  {
+    std::vector<FSum<double, D>> inc = sums;
+    for (int64_t off = 1; off < nch; off <<= 1) {
+      std::vector<FSum<double, D>> nxt = inc;
+      for (int64_t c = 0; c + off < nch; ++c) fsum_combine<double, D>(inc[c], inc[c + off], nxt[c]);
+      inc.swap(nxt);
+    }
+    for (int64_t c = 0; c < nch; ++c) { if (c == nch - 1) info_zero<double, D>(finfo[c]); else info_of<double, D>(inc[c + 1], finfo[c]); }
+  }
   // S3: apply + reference RTS recursion
   for (int64_t c = nch - 1; c >= 0; --c) {
     const int64_t s0 = c * L, s1 = std::min<int64_t>(N, (c + 1) * L);
     FiltState<double, D> x;
+    if (two_filter) {
+      // smoothed state of the chunk's LAST step directly, then RTS for the remaining steps
+      const int64_t k = s1 - 1;
+      for (int i = 0; i < D; ++i) { x.m[i] = fm[k * D + i]; for (int j = 0; j < D; ++j) x.P[i][j] = fP[k * D * D + i * D + j]; }
+      info_smooth<double, D>(finfo[c], x);
+      for (int i = 0; i < D; ++i) { sm[k * D + i] = x.m[i]; for (int j = 0; j < D; ++j) sP[k * D * D + i * D + j] = x.P[i][j]; }
+      for (int64_t kk = s1 - 2; kk >= s0; --kk) {
+        double F[D][D]; Transition<double, KIND>::eval(dt[kk + 1], lam, F);
+        double mf[D], Pf[D][D];
+        for (int i = 0; i < D; ++i) { mf[i] = fm[kk * D + i]; for (int j = 0; j < D; ++j) Pf[i][j] = fP[kk * D * D + i * D + j]; }
+        SmoothGain<double, D> g; smoother_gain<double, D>(F, Pinf, mf, Pf, g);
+        smoother_step<double, D>(g, mf, Pf, x);
+        for (int i = 0; i < D; ++i) { sm[kk * D + i] = x.m[i]; for (int j = 0; j < D; ++j) sP[kk * D * D + i * D + j] = x.P[i][j]; }
+      }
+      continue;
+    }
     if (s1 == N) {
       for (int i = 0; i < D; ++i) { x.m[i] = fm[(N - 1) * D + i]; for (int j = 0; j < D; ++j) x.P[i][j] = fP[(N - 1) * D * D + i * D + j]; }
     } else {
@@ -97,9 +124,9 @@ extern "C" {
 // three-phase scan emulation of filter + smoother for given pseudo-observations (ytilde, R)
 int emu_filter_smoother(int kind, double lam, const double* Pinf, int64_t N, int L, const double* dt,
                         const double* ytilde, const double* R, const uint8_t* mask, double* fm, double* fP,
-                        double* sm, double* sP) {
-  if (kind == KJX_BLOCK_MATERN32) emu_run<KJX_BLOCK_MATERN32>(lam, Pinf, N, L, dt, ytilde, R, mask, fm, fP, sm, sP);
-  else if (kind == KJX_BLOCK_MATERN52) emu_run<KJX_BLOCK_MATERN52>(lam, Pinf, N, L, dt, ytilde, R, mask, fm, fP, sm, sP);
+                        double* sm, double* sP, int two_filter) {
+  if (kind == KJX_BLOCK_MATERN32) emu_run<KJX_BLOCK_MATERN32>(lam, Pinf, N, L, dt, ytilde, R, mask, fm, fP, sm, sP, two_filter);
+  else if (kind == KJX_BLOCK_MATERN52) emu_run<KJX_BLOCK_MATERN52>(lam, Pinf, N, L, dt, ytilde, R, mask, fm, fP, sm, sP, two_filter);
   else return -1;
   return 0;
 }

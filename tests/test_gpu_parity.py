@@ -314,3 +314,75 @@ def test_host_buffer_entry_point_matches_device_path():
     assert float(nl[0]) == nlml
     assert np.array_equal(nsm.numpy(), _np(model.sites.site_params[0]).reshape(-1))
     assert np.array_equal(nsv.numpy(), _np(model.sites.site_params[1]).reshape(-1))
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("prior_name", ["Matern52", "Matern32"])
+def test_time_sharded_iteration_matches_oracle(world, prior_name):
+    """The multi-GPU path without a cluster: the G shards' phases are run one after another on one GPU
+    (summary for every shard, 'all-gather' = stack, fold, filter, smoother) and must reproduce the
+    single-chain oracle, including a shard count that does not divide N."""
+    from kalman_jax_b200.sharded import ShardedIteration, split_series
+    kjx = _kjx()
+    N = 20_011
+    t, y = synth(N)
+    ref = oracle.SDEGP(getattr(oracle.priors, prior_name)(1.0, 5.0), oracle.likelihoods.Gaussian(0.5), t, y,
+                       approx_inf=oracle.approx_inf.EP(power=0.5, damping=0.8))
+    dt = ref.dt
+    parts = split_series(dt, y, world)
+    gathered = {}
+
+    def make_gather(rank):
+        def gather(tensor):
+            return gathered["all"]
+        return gather
+    shards = [ShardedIteration(getattr(kjx.priors, prior_name)(1.0, 5.0), kjx.likelihoods.Gaussian(0.5),
+                               kjx.approximate_inference.EP(power=0.5, damping=0.8), p[0], p[1], p[2], g, world, "cuda",
+                               gather=make_gather(g)) for g, p in enumerate(parts)]
+    import ctypes as C
+    from kalman_jax_b200 import _lib
+    for it in range(2):
+        want_nlml, (wfm, wfP, wsites) = ref.kalman_filter(ref.y, ref.dt, True, None, ref.sites.site_params, ref.r)
+        w_new, wsm, wsc = ref.rauch_tung_striebel_smoother(wfm, wfP, ref.dt, True, False, ref.y, wsites, ref.r)
+        ref.sites.site_params = w_new
+        # phase 1 on every shard, then the gather, then the rest (one GPU: strictly one shard at a time)
+        L = _lib.lib()
+        for sh in shards:
+            _lib.check(L.kjx_filter_summary_f64(sh.model.ref(), C.c_int64(sh.N), _lib.ptr(sh.dt), _lib.ptr(sh.y), _lib.ptr(sh.site_mean),
+                                                _lib.ptr(sh.site_var), _lib.ptr(sh.fmsg), _lib.ptr(sh.ws), C.c_size_t(sh.ws.numel()), None),
+                       "summary")
+        torch.cuda.synchronize()
+        gathered["all"] = torch.stack([sh.fmsg.clone() for sh in shards])
+        nl = 0.0
+        for sh in shards:
+            nl += float(sh.iteration())      # recomputes its own summary (same values), then fold / filter / smoother
+        assert abs(nl - want_nlml) <= TOL64 * abs(want_nlml)
+        pm = np.concatenate([_np(sh.post_mean) for sh in shards])
+        pv = np.concatenate([_np(sh.post_var) for sh in shards])
+        sm = np.concatenate([_np(sh.site_mean) for sh in shards])
+        sv = np.concatenate([_np(sh.site_var) for sh in shards])
+        assert rel_err(pm, wsm[:, 0, 0]) < TOL64 and rel_err(pv, wsc[:, 0, 0]) < TOL64
+        assert rel_err(sm, w_new[0][:, 0, 0]) < TOL64 and rel_err(sv, w_new[1][:, 0, 0]) < TOL64
+
+
+def test_fused_run_returns_dense_filter_output_on_request():
+    """kjx_run keeps the filtered moments packed in its workspace; the optional dense copy must equal kjx_filter's."""
+    import ctypes as C
+    from kalman_jax_b200 import _lib
+    from kalman_jax_b200.sde_gp import _Model, _workspace
+    kjx = _kjx()
+    N = 7001
+    t, y = synth(N)
+    model = kjx.SDEGP(kjx.priors.Matern52(1.0, 5.0), kjx.likelihoods.Gaussian(0.5), t, y, approx_inf=kjx.approximate_inference.EP(power=0.5))
+    params = model._params(None)
+    nlml, (fm, fP, sites) = model.kalman_filter(model.y, model.dt, params, True, None, None, model.r)
+    cm = _Model(model.prior, model.likelihood, model.sites)
+    ws, _ = _workspace(cm, N, torch.float64, model.device)
+    z = lambda *s: torch.empty(*s, dtype=torch.float64, device="cuda")  # noqa: E731
+    fm2, fP2, nsm, nsv, nl = z(N, 3), z(N, 3, 3), z(N), z(N), z(1)
+    _lib.check(_lib.lib().kjx_run_f64(cm.ref(), C.c_int64(N), _lib.ptr(model._dev(model.dt)), _lib.ptr(model._dev(model.y)), None, None,
+                                      _lib.ptr(fm2), _lib.ptr(fP2), _lib.ptr(nsm), _lib.ptr(nsv), None, None, _lib.ptr(nl), _lib.ptr(ws),
+                                      C.c_size_t(ws.numel()), 0, None), "kjx_run")
+    torch.cuda.synchronize()
+    assert rel_err(_np(fm2), _np(fm)[:, :, 0]) < 1e-12 and rel_err(_np(fP2), _np(fP)) < 1e-12
+    assert abs(float(nl[0]) - float(nlml)) <= 1e-12 * abs(float(nlml))

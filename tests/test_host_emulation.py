@@ -29,8 +29,9 @@ def _dp(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+@pytest.mark.parametrize("two_filter", [0, 1])
 @pytest.mark.parametrize("kind,L", [("Matern52", 7), ("Matern52", 64), ("Matern32", 16)])
-def test_scan_emulation_matches_sequential_oracle(kind, L):
+def test_scan_emulation_matches_sequential_oracle(kind, L, two_filter):
     from kalman_jax_b200 import _lib as K
     lib = _lib()
     rng = np.random.default_rng(1)
@@ -52,7 +53,7 @@ def test_scan_emulation_matches_sequential_oracle(kind, L):
     rc = lib.emu_filter_smoother(K.BLOCK_MATERN52 if kind == "Matern52" else K.BLOCK_MATERN32, C.c_double(lam),
                                  _dp(np.ascontiguousarray(Pinf)), C.c_int64(N), L, _dp(model.dt),
                                  _dp(np.ascontiguousarray(site[0].reshape(-1))), _dp(np.ascontiguousarray(site[1].reshape(-1))),
-                                 _dp(m8), *[_dp(a) for a in o])
+                                 _dp(m8), *[_dp(a) for a in o], two_filter)
     assert rc == 0
     assert rel_err(o[0], fm[:, :, 0]) < 1e-11
     assert rel_err(o[1], fP) < 1e-11
