@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <vector>
 
@@ -66,29 +67,41 @@ SiteModel make_site(const kjx_model_t* m) {
 // steps per thread chunk: long chunks amortise the O(d^3) scan combines, short ones keep every SM
 // busy on short series.  A multiple of 4 so a chunk starts on a 32-byte boundary of every array.
 int pick_chunk(int64_t N) {
+  if (const char* e = getenv("KJX_CHUNK")) { const int v = atoi(e); if (v >= 4 && v % 4 == 0) return v; }   // tuning knob
   const int64_t target_chunks = 148 * 2 * KJX_BLOCK;   // two resident blocks per SM
   int64_t L = (N + target_chunks - 1) / target_chunks;
   L = std::max<int64_t>(4, std::min<int64_t>(64, L));
+  // the fused scan hierarchy has three levels of 128: at most 128^3 chunks
+  const int64_t max_chunks = (int64_t)KJX_SEG * KJX_SEG * KJX_SEG;
+  if ((N + L - 1) / L > max_chunks) L = (N + max_chunks - 1) / max_chunks;
   return (int)round_up((size_t)L, 4);
 }
 
 template <typename T, int D> struct SmallLayout {
   int L; int64_t nchunks, nblocks; size_t cstride, bstride;
   size_t off_ftp, off_fbt, off_fbp, off_fst, off_sts, off_sbt, off_sbs, off_sst, off_nl, off_fin, off_sin;
-  size_t off_fts, off_fbs, off_info, off_xf, total;
+  size_t off_info, off_xf, off_lvl[3][3], lvl_stride[3], total;
+  int64_t lvl_n[3];
   explicit SmallLayout(int64_t N) {
     constexpr size_t FNS = FSum<T, D>::NS, SNS = SSum<T, D>::NS;
     L = pick_chunk(N);
     nchunks = std::max<int64_t>(1, (N + L - 1) / L);
     nblocks = (nchunks + KJX_BLOCK - 1) / KJX_BLOCK;
-    cstride = round_up((size_t)nchunks, 32);
+    cstride = round_up((size_t)nchunks, 128);
     bstride = round_up((size_t)nblocks, 32);
     size_t o = 0;
     auto take = [&](size_t n) { size_t r = o; o += round_up(n * sizeof(T), 256); return r; };
     off_ftp = take(FNS * cstride); off_fbt = take(FNS * bstride); off_fbp = take(FNS * bstride); off_fst = take(FNS);
     off_sts = take(SNS * cstride); off_sbt = take(SNS * bstride); off_sbs = take(SNS * bstride); off_sst = take(SNS);
     off_nl = take(bstride); off_fin = take(D + D * D); off_sin = take(D + D * D);
-    off_fts = take(FNS * cstride); off_fbs = take(FNS * bstride); off_info = take(D + D * D);
+    off_info = take(D + D * D);
+    // three scan levels of the fused path: elements, exclusive prefix, exclusive suffix (strides = whole segments)
+    int64_t n = nchunks;
+    for (int l = 0; l < 3; ++l) {
+      lvl_n[l] = n; lvl_stride[l] = round_up((size_t)n, KJX_SEG);
+      for (int q = 0; q < 3; ++q) off_lvl[l][q] = take(FNS * lvl_stride[l]);
+      n = (n + KJX_SEG - 1) / KJX_SEG;
+    }
     // filtered moments between the fused filter and smoother passes: [warp][step][element][lane]
     off_xf = take(cstride * (size_t)L * Packed<D>::NP);
     total = o;
@@ -111,8 +124,11 @@ template <typename T, int D>
 void bind_fused(FusedArgs<T, D>& fa, const SmallLayout<T, D>& lay, void* ws) {
   char* w = (char*)ws;
   bind_workspace<T, D>(fa.a, lay, ws);
-  fa.f_thread_suffix = (T*)(w + lay.off_fts); fa.f_block_suffix = (T*)(w + lay.off_fbs);
   fa.s_info_in = (T*)(w + lay.off_info); fa.xf = (T*)(w + lay.off_xf);
+  for (int l = 0; l < 3; ++l) {
+    fa.lvl[l].items = (T*)(w + lay.off_lvl[l][0]); fa.lvl[l].prefix = (T*)(w + lay.off_lvl[l][1]);
+    fa.lvl[l].suffix = (T*)(w + lay.off_lvl[l][2]); fa.lvl[l].stride = lay.lvl_stride[l]; fa.lvl[l].n = lay.lvl_n[l];
+  }
 }
 
 inline bool aligned_to(const void* p, size_t a) { return p == nullptr || ((uintptr_t)p % a) == 0; }
@@ -249,6 +265,7 @@ struct Fused {
   FusedArgs<T, D> fa;
   SmallLayout<T, D> lay;
   const kjx_model_t* m;
+  int64_t ngroups, nthread_blocks;
   Fused(const kjx_model_t* m_, int64_t N, const T* dt, const T* y, const T* site_mean, const T* site_var, void* ws)
       : lay(N), m(m_) {
     memset(&fa, 0, sizeof(fa));
@@ -257,14 +274,23 @@ struct Fused {
     fa.a.N = N; fa.a.dt = dt; fa.a.y = y; fa.a.site_mean = site_mean; fa.a.site_var = site_var;
     fa.a.gaussian_init = (site_mean == nullptr) ? 1 : 0;
     fa.a.is_last_shard = 1;
+    nthread_blocks = fa.a.nblocks;
+    ngroups = 0;
     const size_t al = sizeof(T) * 4;
     fa.vec_ok = (lay.L % 4 == 0) && aligned_to(dt, al) && aligned_to(y, al) && aligned_to(site_mean, al) && aligned_to(site_var, al);
   }
-  unsigned grid() const { return (unsigned)fa.a.nblocks; }
+  unsigned grid() const { return (unsigned)((fa.a.nchunks + KJX_BLOCK - 1) / KJX_BLOCK); }
   void reduce(cudaStream_t st) {
-    if (fa.vec_ok) fused_reduce_kernel<T, KIND, true><<<grid(), KJX_BLOCK, 0, st>>>(fa);
-    else fused_reduce_kernel<T, KIND, false><<<grid(), KJX_BLOCK, 0, st>>>(fa);
-    fused_blockscan_kernel<T, D><<<1, KJX_SCAN_BLOCK, 0, st>>>(fa);
+    if (fa.vec_ok) fused_fold_kernel<T, KIND, true><<<grid(), KJX_BLOCK, 0, st>>>(fa);
+    else fused_fold_kernel<T, KIND, false><<<grid(), KJX_BLOCK, 0, st>>>(fa);
+    // three levels of segment scans; the top level's single total is the shard's element
+    const size_t smem = sizeof(T) * FSum<T, D>::NS * KJX_SEG;
+    for (int l = 0; l < 3; ++l) {
+      const unsigned nseg = (unsigned)((fa.lvl[l].n + KJX_SEG - 1) / KJX_SEG);
+      T* tot = (l < 2) ? fa.lvl[l + 1].items : fa.a.f_shard_total;
+      const size_t tstride = (l < 2) ? fa.lvl[l + 1].stride : 1;
+      fused_segscan_kernel<T, D><<<nseg, 64, smem, st>>>(fa.lvl[l], tot, tstride);
+    }
   }
   void filter(cudaStream_t st) {
     const bool fast = gauss_ep(m);
@@ -345,7 +371,7 @@ int small_run(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const T*
     launch_set_prior_state<T, D>((T*)f.fa.a.f_state_in, m, st);
     cudaMemsetAsync((void*)f.fa.s_info_in, 0, (D + D * D) * sizeof(T), st);
     f.filter(st);
-    nlml_reduce_kernel<T><<<1, 256, 0, st>>>(f.fa.a.block_nlml, f.fa.a.nblocks, nlml);
+    nlml_reduce_kernel<T><<<1, 256, 0, st>>>(f.fa.a.block_nlml, f.nthread_blocks, nlml);
     f.smoother(post_mean, post_var, new_site_mean, new_site_var, update, st);
     if (filt_mean && filt_cov)
       unpack_filtered_kernel<T, D><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(f.fa.xf, N, f.lay.L, filt_mean, filt_cov);
@@ -375,7 +401,7 @@ int shard_filter(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const
   Fused<T, KIND> f(m, N, dt, y, site_mean, site_var, ws);
   copy_state_kernel<T, D><<<1, 32, 0, st>>>((T*)f.fa.a.f_state_in, state_in);
   f.filter(st);
-  nlml_reduce_kernel<T><<<1, 256, 0, st>>>(f.fa.a.block_nlml, f.fa.a.nblocks, nlml_partial);
+  nlml_reduce_kernel<T><<<1, 256, 0, st>>>(f.fa.a.block_nlml, f.nthread_blocks, nlml_partial);
   KJX_CUDA_CHECK(cudaGetLastError());
   return KJX_OK;
 }

@@ -79,10 +79,17 @@ __device__ __forceinline__ void xf_load(const T* base, T (&m)[D], T (&P)[D][D]) 
     for (int j = i; j < D; ++j) { const T v = __ldcs(base + 32 * e++); P[i][j] = v; P[j][i] = v; }
 }
 
+template <typename T, int D> struct ScanLevel {
+  T* items;      // [NS][stride] elements of this level (slots, see seg_slot)
+  T* prefix;     // [NS][stride] exclusive prefix of every element within its segment
+  T* suffix;     // [NS][stride] exclusive suffix of every element within its segment
+  size_t stride;
+  int64_t n;     // number of elements
+};
+
 template <typename T, int D> struct FusedArgs {
   SmallArgs<T, D> a;        // prior, site model, data pointers, scan workspace (see kjx_small_kernels.cuh)
-  T* f_thread_suffix;       // [NS][cstride] exclusive suffix element of every chunk within its block
-  T* f_block_suffix;        // [NS][bstride] exclusive suffix element of every block within the shard
+  ScanLevel<T, D> lvl[3];   // chunk elements / segment totals / super-segment totals with their scans
   T* xf;                    // filtered moments, private layout
   const T* s_info_in;       // [D + D*D] information (eta, J) of all later shards about this shard's last state
   int vec_ok;               // every per-step array is 32-byte (fp64) / 16-byte (fp32) aligned
@@ -98,15 +105,27 @@ __device__ __forceinline__ void load_info(const T* p, Info<T, D>& f) {
     for (int j = 0; j < D; ++j) f.J[i][j] = p[D + i * D + j];
 }
 
+constexpr int KJX_SEG = 128;             // elements per scan segment = one block of the segment-scan kernel
+constexpr int KJX_SEG_PER = KJX_SEG / 32;
+
+// Slot of element i in a per-level workspace array.  A scan warp owns KJX_SEG_PER consecutive elements per
+// lane; storing element q = PER*lane + j of a segment at j*32 + lane makes the segment a [PER][32] tile that
+// stages into shared memory with coalesced copies and is read bank-conflict-free.  (The fold / filter /
+// smoother threads touch these arrays once per chunk, scattered, which is negligible.)
+__host__ __device__ __forceinline__ int64_t seg_slot(int64_t i) {
+  const int64_t q = i % KJX_SEG;
+  return (i - q) + (q % KJX_SEG_PER) * 32 + q / KJX_SEG_PER;
+}
+
 // ------------------------------------------------------------------------------------------------
-// R1
+// R1a: fold.  One thread per chunk; the chunk's element goes to the workspace (struct-of-arrays, coalesced).
 template <typename T, int KIND, bool VEC>
-__global__ void __launch_bounds__(KJX_BLOCK) fused_reduce_kernel(const FusedArgs<T, BlockDim<KIND>::D> fa) {
+__global__ void __launch_bounds__(KJX_BLOCK) fused_fold_kernel(const FusedArgs<T, BlockDim<KIND>::D> fa) {
   constexpr int D = BlockDim<KIND>::D;
   using S = FSum<T, D>;
   const SmallArgs<T, D>& a = fa.a;
-  __shared__ T smem[S::NS * (KJX_BLOCK / 32 + 1)];
   const int64_t c = (int64_t)blockIdx.x * KJX_BLOCK + threadIdx.x;
+  if (c >= a.nchunks) return;
   const int64_t s0 = c * a.L;
   const int64_t s1 = (s0 + a.L < a.N) ? s0 + a.L : a.N;
   T Pinf[D][D]; load_pinf<T, D>(a.prior, Pinf);
@@ -134,28 +153,89 @@ __global__ void __launch_bounds__(KJX_BLOCK) fused_reduce_kernel(const FusedArgs
     T yt, R; step_site<T, D>(a, k, yt, R);
     fsum_fold_step<T, D>(mine, F, Pinf, yt, R, a.mask ? (a.mask[k] != 0) : false);
   }
-  {
-    S excl, total;
-    block_scan_exclusive<S, false, KJX_BLOCK>(mine, excl, total, smem);
-    if (c < a.nchunks) sum_store<S>(a.f_thread_prefix, a.cstride, c, excl);
-    if (threadIdx.x == 0) sum_store<S>(a.f_block_total, a.bstride, blockIdx.x, total);
+  sum_store<S>(fa.lvl[0].items, fa.lvl[0].stride, seg_slot(c), mine);
+}
+
+// ------------------------------------------------------------------------------------------------
+// R2: segment scan, used at every level of the hierarchy (chunks -> 128-chunk segments -> 128-segment
+// super-segments -> shard).  One block of two warps per segment: the 128 elements are staged into shared memory
+// with cp.async (27 KB at d=3), warp 0 produces the exclusive PREFIX of every element, warp 1 the exclusive SUFFIX,
+// concurrently.  Per warp: 3 sequential combines for the lane totals, a 5-level shuffle scan, 3 more to expand —
+// a dependent chain of 11 combines whose operands all live in shared memory or registers.
+template <typename S> __device__ __forceinline__ void smem_item(const typename SumOps<S>::Scalar* sm, int slot, S& it) {
+  typename SumOps<S>::Scalar v[SumOps<S>::NS];
+#pragma unroll
+  for (int k = 0; k < SumOps<S>::NS; ++k) v[k] = sm[k * KJX_SEG + slot];
+  SumOps<S>::unpack(v, it);
+}
+
+template <typename S, bool REVERSE> __device__ __forceinline__ S warp_scan_inclusive_rolled(const S& mine, int lane) {
+  S inc = mine;
+#pragma unroll 1
+  for (int off = 1; off < 32; off <<= 1) {
+    const int src = REVERSE ? lane + off : lane - off;
+    S other = sum_shfl<S>(inc, src & 31);
+    const bool ok = REVERSE ? (src < 32) : (src >= 0);
+    if (!ok) SumOps<S>::identity(other);       // combining with the identity is exact: no divergence needed
+    S r;
+    if (REVERSE) SumOps<S>::combine(inc, other, r); else SumOps<S>::combine(other, inc, r);
+    inc = r;
   }
-  {
-    S excl, total;
-    block_scan_exclusive<S, true, KJX_BLOCK>(mine, excl, total, smem);
-    if (c < a.nchunks) sum_store<S>(fa.f_thread_suffix, a.cstride, c, excl);
+  return inc;
+}
+
+template <typename T, int D, bool REVERSE>
+__device__ __forceinline__ void segscan_pass(const T* sm, const ScanLevel<T, D>& lv, int64_t first, int lane, T* total_out,
+                                             size_t total_stride, int64_t total_slot) {
+  using S = FSum<T, D>;
+  auto live = [&](int j) { return first + (int64_t)lane * KJX_SEG_PER + j < lv.n; };
+  auto item = [&](int j, S& it) { if (live(j)) smem_item<S>(sm, j * 32 + lane, it); else SumOps<S>::identity(it); };
+  S tot; item(0, tot);
+#pragma unroll 1
+  for (int j = 1; j < KJX_SEG_PER; ++j) { S it; item(j, it); S r; SumOps<S>::combine(tot, it, r); tot = r; }
+  S inc = warp_scan_inclusive_rolled<S, REVERSE>(tot, lane);
+  if (!REVERSE && total_out != nullptr) {
+    S whole = sum_shfl<S>(inc, 31);
+    if (lane == 0) sum_store<S>(total_out, total_stride, total_slot, whole);
+  }
+  S run = sum_shfl<S>(inc, (REVERSE ? lane + 1 : lane - 1) & 31);
+  if (REVERSE ? (lane == 31) : (lane == 0)) SumOps<S>::identity(run);
+  T* out = REVERSE ? lv.suffix : lv.prefix;
+  if (!REVERSE) {
+#pragma unroll 1
+    for (int j = 0; j < KJX_SEG_PER; ++j) {
+      if (live(j)) sum_store<S>(out, lv.stride, first + j * 32 + lane, run);
+      if (j + 1 < KJX_SEG_PER) { S it; item(j, it); S r; SumOps<S>::combine(run, it, r); run = r; }
+    }
+  } else {
+#pragma unroll 1
+    for (int j = KJX_SEG_PER - 1; j >= 0; --j) {
+      if (live(j)) sum_store<S>(out, lv.stride, first + j * 32 + lane, run);
+      if (j > 0) { S it; item(j, it); S r; SumOps<S>::combine(it, run, r); run = r; }
+    }
   }
 }
 
-// R2
 template <typename T, int D>
-__global__ void __launch_bounds__(KJX_SCAN_BLOCK) fused_blockscan_kernel(const FusedArgs<T, D> fa) {
+__global__ void __launch_bounds__(64) fused_segscan_kernel(const ScanLevel<T, D> lv, T* total_out, size_t total_stride) {
   using S = FSum<T, D>;
-  __shared__ T smem[S::NS * (KJX_SCAN_BLOCK / 32 + 1)];
-  const SmallArgs<T, D>& a = fa.a;
-  blockscan_body<S, false>(a.f_block_total, a.f_block_prefix, a.f_shard_total, a.nblocks, a.bstride, smem);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* sm = reinterpret_cast<T*>(smem_raw);                  // [NS][KJX_SEG]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t first = (int64_t)blockIdx.x * KJX_SEG;
+  // stage the segment: 16-byte asynchronous copies, coalesced (stride is a multiple of KJX_SEG)
+  constexpr int PER16 = 16 / sizeof(T);
+  for (int idx = threadIdx.x; idx < S::NS * KJX_SEG / PER16; idx += 64) {
+    const int k = (idx * PER16) / KJX_SEG, sl = (idx * PER16) % KJX_SEG;
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(sm + k * KJX_SEG + sl);
+    const T* src = lv.items + k * lv.stride + first + sl;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  blockscan_body<S, true>(a.f_block_total, fa.f_block_suffix, a.f_shard_total, a.nblocks, a.bstride, smem);
+  if (warp == 0) segscan_pass<T, D, false>(sm, lv, first, lane, total_out, total_stride, seg_slot(blockIdx.x));
+  else segscan_pass<T, D, true>(sm, lv, first, lane, nullptr, 0, 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -174,8 +254,11 @@ __global__ void __launch_bounds__(KJX_BLOCK) fused_filter_kernel(const FusedArgs
   T nl = T(0);
   if (s0 < s1) {
     FiltState<T, D> x; load_state<T, D>(a.f_state_in, x);
-    { FS bp; sum_load<FS>(a.f_block_prefix, a.bstride, blockIdx.x, bp); fsum_apply<T, D>(bp, x); }
-    { FS tp; sum_load<FS>(a.f_thread_prefix, a.cstride, c, tp); fsum_apply<T, D>(tp, x); }
+    {   // everything before this chunk: super-segments, segments, chunks (outermost first)
+      int64_t idx[3] = {c, c / KJX_SEG, c / (KJX_SEG * KJX_SEG)};
+#pragma unroll 1
+      for (int l = 2; l >= 0; --l) { FS p; sum_load<FS>(fa.lvl[l].prefix, fa.lvl[l].stride, seg_slot(idx[l]), p); fsum_apply<T, D>(p, x); }
+    }
     T* xf = fa.xf + ((c >> 5) * (int64_t)a.L * NP) * 32 + (c & 31);
     const T* ysrc = a.gaussian_init ? a.y : a.site_mean;
     const T lik_hyp = T(a.site.lik_hyp);
@@ -256,8 +339,11 @@ __global__ void __launch_bounds__(KJX_BLOCK) fused_smoother_kernel(const FusedAr
   int64_t k = s1 - 1;
   {
     Info<T, D> info; load_info<T, D>(fa.s_info_in, info);
-    { FS bs; sum_load<FS>(fa.f_block_suffix, a.bstride, blockIdx.x, bs); fsum_combine_info<T, D>(bs, info, info); }
-    { FS ts; sum_load<FS>(fa.f_thread_suffix, a.cstride, c, ts); fsum_combine_info<T, D>(ts, info, info); }
+    {   // everything after this chunk
+      int64_t idx[3] = {c, c / KJX_SEG, c / (KJX_SEG * KJX_SEG)};
+#pragma unroll 1
+      for (int l = 2; l >= 0; --l) { FS q; sum_load<FS>(fa.lvl[l].suffix, fa.lvl[l].stride, seg_slot(idx[l]), q); fsum_combine_info<T, D>(q, info, info); }
+    }
     xf_load<T, D>(xf + (k - s0) * NP * 32, x.m, x.P);
     info_smooth<T, D>(info, x);
     T pm, pv, nsm, nsv, pmean, pvar;

@@ -163,7 +163,9 @@ def test_empty_series_is_a_no_op():
     from kalman_jax_b200.sde_gp import _Model
     model = _Model(kjx.priors.Matern52(1.0, 5.0), kjx.likelihoods.Gaussian(0.5), kjx.approximate_inference.EP())
     nlml = torch.full((1,), 7.0, dtype=torch.float64, device="cuda")
-    ws = torch.empty(1 << 16, dtype=torch.uint8, device="cuda")
+    nbytes = C.c_size_t(0)
+    assert _lib.lib().kjx_workspace_bytes(model.ref(), C.c_int64(0), 8, C.byref(nbytes)) == 0
+    ws = torch.empty(max(nbytes.value, 256), dtype=torch.uint8, device="cuda")
     dummy = torch.zeros(4, dtype=torch.float64, device="cuda")
     rc = _lib.lib().kjx_filter_f64(model.ref(), C.c_int64(0), _lib.ptr(dummy), _lib.ptr(dummy), None, None, None, None, None,
                                    None, None, _lib.ptr(nlml), _lib.ptr(ws), C.c_size_t(ws.numel()), 0, None)
