@@ -18,6 +18,14 @@
 #pragma once
 #include "kjx_small_kernels.cuh"
 
+// minimum resident blocks per SM requested from ptxas (register caps 168 / 128): measured best on B200
+#ifndef KJX_R4_MINB
+#define KJX_R4_MINB 3
+#endif
+#ifndef KJX_R3_MINB
+#define KJX_R3_MINB 4
+#endif
+
 namespace kjx {
 
 // ------------------------------------------------------------------------------------------------
@@ -241,7 +249,7 @@ __global__ void __launch_bounds__(64) fused_segscan_kernel(const ScanLevel<T, D>
 // ------------------------------------------------------------------------------------------------
 // R3
 template <typename T, int KIND, bool GAUSS_EP, bool VEC>
-__global__ void __launch_bounds__(KJX_BLOCK) fused_filter_kernel(const FusedArgs<T, BlockDim<KIND>::D> fa) {
+__global__ void __launch_bounds__(KJX_BLOCK, KJX_R3_MINB) fused_filter_kernel(const FusedArgs<T, BlockDim<KIND>::D> fa) {
   constexpr int D = BlockDim<KIND>::D;
   constexpr int NP = Packed<D>::NP;
   using FS = FSum<T, D>;
@@ -320,7 +328,7 @@ __device__ __forceinline__ void smoothed_outputs(const SmallArgs<T, D>& a, const
 }
 
 template <typename T, int KIND, bool GAUSS_EP, bool VEC>
-__global__ void __launch_bounds__(KJX_BLOCK) fused_smoother_kernel(const FusedArgs<T, BlockDim<KIND>::D> fa) {
+__global__ void __launch_bounds__(KJX_BLOCK, KJX_R4_MINB) fused_smoother_kernel(const FusedArgs<T, BlockDim<KIND>::D> fa) {
   constexpr int D = BlockDim<KIND>::D;
   constexpr int NP = Packed<D>::NP;
   using FS = FSum<T, D>;
@@ -369,6 +377,9 @@ __global__ void __launch_bounds__(KJX_BLOCK) fused_smoother_kernel(const FusedAr
     if (upd) { a.new_site_mean[k] = nsm; a.new_site_var[k] = nsv; }
     dt_after = a.dt[k];
   }
+  // software pipeline: the packed filtered moments of the NEXT step to process are requested one step ahead
+  T nm[D], nP[D][D];
+  if (ngroups > 0) xf_load<T, D>(xf + (4 * ngroups - 1) * NP * 32, nm, nP);
   for (int64_t g4 = ngroups - 1; g4 >= 0; --g4) {
     const int64_t k0 = s0 + 4 * g4;
     const Vec4<T> vdt = load4v<T, VEC>(a.dt + k0);
@@ -378,8 +389,14 @@ __global__ void __launch_bounds__(KJX_BLOCK) fused_smoother_kernel(const FusedAr
 #pragma unroll
     for (int j = 3; j >= 0; --j) {
       T F[D][D], mf[D], Pf[D][D];
+#pragma unroll
+      for (int p = 0; p < D; ++p) {
+        mf[p] = nm[p];
+#pragma unroll
+        for (int q = 0; q < D; ++q) Pf[p][q] = nP[p][q];
+      }
+      if (j > 0 || g4 > 0) xf_load<T, D>(xf + (k0 + j - 1 - s0) * NP * 32, nm, nP);      // prefetch step k-1
       Transition<T, KIND>::eval(dt_after, a.prior.lam, F);
-      xf_load<T, D>(xf + (k0 + j - s0) * NP * 32, mf, Pf);
       SmoothGain<T, D> g;
       smoother_gain<T, D>(F, Pinf, mf, Pf, g);                              // sde_gp.py:351-359
       smoother_step<T, D>(g, mf, Pf, x);                                    // sde_gp.py:360-361
