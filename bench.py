@@ -168,9 +168,9 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--n", type=int, default=24, help="log2 of the number of time steps")
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--log2n", type=int, default=24, help="log2 of the number of time steps")
     ap.add_argument("--impl", default="kjx")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
@@ -206,7 +206,7 @@ def main():
             dist.all_reduce(out)
             return out
 
-    N = 1 << args.n
+    N = 1 << args.log2n
     dt, y = synth(N)
     sh_dt, sh_y, dt_next, lo, hi = split_series(dt, y, world)[rank]
     n_local = hi - lo
@@ -223,15 +223,20 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    t_w = time.perf_counter()
     for _ in range(max(args.warmup, 3)):
         it.iteration(reduce_nlml=reduce_nlml)
     barrier()
-    # keep the device under the same load until nvidia-smi has delivered a few samples (not timed)
-    t_spin = time.perf_counter()
-    while rank == 0 and len(sampler.rows) < 3 and time.perf_counter() - t_spin < 3.0:
-        it.iteration(update_sites=False)
-        torch.cuda.synchronize()
-    sampler.rows = sampler.rows[-1:]
+    # Keep every rank under the same load for ~0.8 s more so nvidia-smi (200 ms period) delivers samples taken under
+    # load before the timed region starts (not timed).  The count is agreed across ranks: the loop contains collectives.
+    est = torch.tensor([(time.perf_counter() - t_w) / max(args.warmup, 3)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(est, op=dist.ReduceOp.MAX)
+    n_extra = int(min(2000, max(1, 0.8 / max(float(est[0]), 1e-5))))
+    for _ in range(n_extra):
+        it.iteration(update_sites=False, reduce_nlml=reduce_nlml)
+    barrier()
+    sampler.rows = sampler.rows[-2:]
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -240,11 +245,9 @@ def main():
         it.iteration(events=ev[k], reduce_nlml=reduce_nlml)
     stop.record()
     barrier()
-    if rank == 0:                       # a few more samples under load right after the timed region
-        t_spin = time.perf_counter()
-        while len(sampler.rows) < 4 and time.perf_counter() - t_spin < 2.0:
-            it.iteration(update_sites=False)
-            torch.cuda.synchronize()
+    for _ in range(n_extra // 2):       # a few more samples under the same load right after the timed region
+        it.iteration(update_sites=False, reduce_nlml=reduce_nlml)
+    barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms_total = start.elapsed_time(stop)
     phases = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(3)] for e in ev]).mean(axis=0)   # ms
@@ -310,7 +313,7 @@ def main():
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "C5: synthetic Matern-5/2 (var 1, len 5) + Gaussian(0.5) + EP(power 0.5); one iteration = "
-                               "filter(stored sites) -> RTS smoother -> site update; N=2^%d steps, d=3, f=1" % args.n,
+                               "filter(stored sites) -> RTS smoother -> site update; N=2^%d steps, d=3, f=1" % args.log2n,
                    "N": N, "state_dim": 3, "sharding": "time axis, %d contiguous shard(s)" % world,
                    "l2_policy": "inputs (%.1f GB per iteration per GPU) exceed the 126 MB L2; no flush needed" % (BYTES_PER_STEP * n_local / 1e9)},
         "roofline": {"bound": "hbm", "kernel": ("fused_filter_kernel (R3)", "fused_smoother_kernel (R4)")[dom - 1],
