@@ -10,6 +10,7 @@
 #include "kjx_small_kernels.cuh"
 #include "kjx_fused_kernels.cuh"
 #include "kjx_elementwise_kernels.cuh"
+#include "kjx_generic_kernels.cuh"
 
 using namespace kjx;
 
@@ -443,6 +444,106 @@ __global__ void fold_shards_kernel(PinfArg<D> pinf, const double* summaries, int
   if (threadIdx.x == 0) fold_shards<D>(pinf.v, summaries, stride, world, rank, state_out, info_out);
 }
 
+// ---- generic block-diagonal prior, d <= 64: one CTA walks the series in reference order ------------------
+bool generic_ok(const kjx_model_t* m) {
+  return m->func_dim == 1 && m->state_dim <= KJX_GEN_DMAX && (m->H != nullptr || m->H_steps != nullptr);
+}
+template <typename T> size_t generic_ws_bytes(const kjx_model_t* m, int64_t N) {
+  const size_t d = (size_t)m->state_dim, n = (size_t)std::max<int64_t>(N, 1);
+  return round_up(d * d * 8, 256) + round_up(d * 8, 256) + round_up(n * d * sizeof(T), 256) + round_up(n * d * d * sizeof(T), 256);
+}
+template <typename T>
+int generic_setup(const kjx_model_t* m, int64_t N, void* ws, size_t ws_bytes, GenArgs<T>& g, T** scratch_mean, T** scratch_cov,
+                  cudaStream_t st) {
+  if (!ws || ws_bytes < generic_ws_bytes<T>(m, N)) return KJX_ERR_WORKSPACE;
+  const size_t d = (size_t)m->state_dim;
+  memset(&g, 0, sizeof(g));
+  g.disc.d = m->state_dim; g.disc.n_blocks = m->n_blocks;
+  for (int b = 0; b < m->n_blocks; ++b) g.disc.blocks[b] = m->blocks[b];
+  g.site = make_site(m); g.d = m->state_dim; g.N = N;
+  char* w = (char*)ws;
+  double* pinf_dev = (double*)w; w += round_up(d * d * 8, 256);
+  double* h_dev = (double*)w; w += round_up(d * 8, 256);
+  *scratch_mean = (T*)w; w += round_up((size_t)std::max<int64_t>(N, 1) * d * sizeof(T), 256);
+  *scratch_cov = (T*)w;
+  KJX_CUDA_CHECK(cudaMemcpyAsync(pinf_dev, m->Pinf, d * d * 8, cudaMemcpyHostToDevice, st));
+  g.Pinf = pinf_dev;
+  if (m->H_steps) { g.H_steps = m->H_steps; g.H = nullptr; }
+  else { KJX_CUDA_CHECK(cudaMemcpyAsync(h_dev, m->H, d * 8, cudaMemcpyHostToDevice, st)); g.H = h_dev; }
+  return KJX_OK;
+}
+template <typename T> int generic_launch_filter(const GenArgs<T>& g, cudaStream_t st) {
+  const size_t smem = generic_filter_smem<T>(g.d);
+  KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_filter_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  generic_filter_kernel<T><<<1, KJX_GEN_THREADS, smem, st>>>(g);
+  return KJX_OK;
+}
+template <typename T> int generic_launch_smoother(const GenArgs<T>& g, cudaStream_t st) {
+  const size_t smem = generic_smoother_smem<T>(g.d);
+  KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_smoother_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  generic_smoother_kernel<T><<<1, KJX_GEN_THREADS, smem, st>>>(g);
+  return KJX_OK;
+}
+
+template <typename T>
+int generic_filter(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const uint8_t* mask, const T* site_mean,
+                   const T* site_var, T* filt_mean, T* filt_cov, T* out_site_mean, T* out_site_var, T* nlml, void* ws,
+                   size_t ws_bytes, cudaStream_t st) {
+  GenArgs<T> g; T *sm, *sc;
+  int rc = generic_setup<T>(m, N, ws, ws_bytes, g, &sm, &sc, st);
+  if (rc != KJX_OK) return rc;
+  if (N == 0) { cudaMemsetAsync(nlml, 0, sizeof(T), st); return KJX_OK; }
+  g.dt = dt; g.y = y; g.mask = mask; g.site_mean = site_mean; g.site_var = site_var;
+  g.init_sites = (site_mean == nullptr && !gauss_ep(m)) ? 1 : 0;
+  g.filt_mean = filt_mean; g.filt_cov = filt_cov; g.out_site_mean = out_site_mean; g.out_site_var = out_site_var; g.nlml = nlml;
+  rc = generic_launch_filter<T>(g, st);
+  if (rc != KJX_OK) return rc;
+  KJX_CUDA_CHECK(cudaGetLastError());
+  return KJX_OK;
+}
+template <typename T>
+int generic_smoother(const kjx_model_t* m, int64_t N, const T* dt, const T* filt_mean, const T* filt_cov, const T* y,
+                     const T* site_mean, const T* site_var, T* smooth_mean, T* smooth_cov, T* new_site_mean, T* new_site_var,
+                     void* ws, size_t ws_bytes, uint32_t flags, cudaStream_t st) {
+  GenArgs<T> g; T *sm, *sc;
+  int rc = generic_setup<T>(m, N, ws, ws_bytes, g, &sm, &sc, st);
+  if (rc != KJX_OK) return rc;
+  if (N == 0) return KJX_OK;
+  g.dt = dt; g.y = y; g.site_mean = site_mean; g.site_var = site_var;
+  g.filt_mean_in = filt_mean; g.filt_cov_in = filt_cov;
+  g.smooth_mean = smooth_mean; g.smooth_cov = smooth_cov; g.new_site_mean = new_site_mean; g.new_site_var = new_site_var;
+  g.return_full = (flags & KJX_FLAG_RETURN_FULL) ? 1 : 0;
+  g.update_sites = (new_site_mean != nullptr && site_mean != nullptr && y != nullptr) ? 1 : 0;
+  rc = generic_launch_smoother<T>(g, st);
+  if (rc != KJX_OK) return rc;
+  KJX_CUDA_CHECK(cudaGetLastError());
+  return KJX_OK;
+}
+template <typename T>
+int generic_run(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const T* site_mean, const T* site_var,
+                T* filt_mean, T* filt_cov, T* new_site_mean, T* new_site_var, T* post_mean, T* post_var, T* nlml,
+                void* ws, size_t ws_bytes, uint32_t flags, cudaStream_t st) {
+  GenArgs<T> g; T *sm, *sc;
+  int rc = generic_setup<T>(m, N, ws, ws_bytes, g, &sm, &sc, st);
+  if (rc != KJX_OK) return rc;
+  if (N == 0) { cudaMemsetAsync(nlml, 0, sizeof(T), st); return KJX_OK; }
+  if (!filt_mean) { filt_mean = sm; filt_cov = sc; }       // run() uses the filtered moments only internally
+  g.dt = dt; g.y = y; g.site_mean = site_mean; g.site_var = site_var;
+  g.init_sites = (site_mean == nullptr && !gauss_ep(m)) ? 1 : 0;
+  g.filt_mean = filt_mean; g.filt_cov = filt_cov; g.nlml = nlml;
+  if (g.init_sites) { g.out_site_mean = new_site_mean; g.out_site_var = new_site_var; }   // sde_gp.py:183
+  rc = generic_launch_filter<T>(g, st);
+  if (rc != KJX_OK) return rc;
+  if (g.init_sites) { g.site_mean = new_site_mean; g.site_var = new_site_var; g.out_site_mean = nullptr; g.out_site_var = nullptr; }
+  g.filt_mean_in = filt_mean; g.filt_cov_in = filt_cov;
+  g.smooth_mean = post_mean; g.smooth_cov = post_var; g.new_site_mean = new_site_mean; g.new_site_var = new_site_var;
+  g.return_full = 0; g.update_sites = (flags & KJX_FLAG_NO_SITE_UPDATE) ? 0 : 1;
+  rc = generic_launch_smoother<T>(g, st);
+  if (rc != KJX_OK) return rc;
+  KJX_CUDA_CHECK(cudaGetLastError());
+  return KJX_OK;
+}
+
 // ---- typed front ends shared by the _f64 / _f32 entry points ------------------------------------------
 template <typename T>
 int filter_T(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const uint8_t* mask, const T* site_mean,
@@ -456,7 +557,9 @@ int filter_T(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const uin
   switch (small_kind(m)) {
     case KJX_BLOCK_MATERN32: return small_filter<T, KJX_BLOCK_MATERN32>(m, N, dt, y, mask, site_mean, site_cov, filt_mean, filt_cov, out_site_mean, out_site_cov, nlml, ws, ws_bytes, flags, st);
     case KJX_BLOCK_MATERN52: return small_filter<T, KJX_BLOCK_MATERN52>(m, N, dt, y, mask, site_mean, site_cov, filt_mean, filt_cov, out_site_mean, out_site_cov, nlml, ws, ws_bytes, flags, st);
-    default: return KJX_ERR_UNSUPPORTED;
+    default:
+      if (!generic_ok(m)) return KJX_ERR_UNSUPPORTED;
+      return generic_filter<T>(m, N, dt, y, mask, site_mean, site_cov, filt_mean, filt_cov, out_site_mean, out_site_cov, nlml, ws, ws_bytes, st);
   }
 }
 
@@ -472,7 +575,9 @@ int smoother_T(const kjx_model_t* m, int64_t N, const T* dt, const T* filt_mean,
   switch (small_kind(m)) {
     case KJX_BLOCK_MATERN32: return small_smoother<T, KJX_BLOCK_MATERN32>(m, N, dt, filt_mean, filt_cov, y, site_mean, site_cov, smooth_mean, smooth_cov, new_site_mean, new_site_cov, ws, ws_bytes, flags, st);
     case KJX_BLOCK_MATERN52: return small_smoother<T, KJX_BLOCK_MATERN52>(m, N, dt, filt_mean, filt_cov, y, site_mean, site_cov, smooth_mean, smooth_cov, new_site_mean, new_site_cov, ws, ws_bytes, flags, st);
-    default: return KJX_ERR_UNSUPPORTED;
+    default:
+      if (!generic_ok(m)) return KJX_ERR_UNSUPPORTED;
+      return generic_smoother<T>(m, N, dt, filt_mean, filt_cov, y, site_mean, site_cov, smooth_mean, smooth_cov, new_site_mean, new_site_cov, ws, ws_bytes, flags, st);
   }
 }
 
@@ -489,7 +594,9 @@ int run_T(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const T* sit
   switch (small_kind(m)) {
     case KJX_BLOCK_MATERN32: return small_run<T, KJX_BLOCK_MATERN32>(m, N, dt, y, site_mean, site_cov, filt_mean, filt_cov, new_site_mean, new_site_cov, post_mean, post_var, nlml, ws, ws_bytes, flags, st);
     case KJX_BLOCK_MATERN52: return small_run<T, KJX_BLOCK_MATERN52>(m, N, dt, y, site_mean, site_cov, filt_mean, filt_cov, new_site_mean, new_site_cov, post_mean, post_var, nlml, ws, ws_bytes, flags, st);
-    default: return KJX_ERR_UNSUPPORTED;
+    default:
+      if (!generic_ok(m)) return KJX_ERR_UNSUPPORTED;
+      return generic_run<T>(m, N, dt, y, site_mean, site_cov, filt_mean, filt_cov, new_site_mean, new_site_cov, post_mean, post_var, nlml, ws, ws_bytes, flags, st);
   }
 }
 
@@ -556,6 +663,7 @@ int kjx_workspace_bytes(const kjx_model_t* m, int64_t N, int dtype_bytes, size_t
   size_t total = 0;
   if (kind == KJX_BLOCK_MATERN32) total = dtype_bytes == 8 ? SmallLayout<double, 2>(N).total : SmallLayout<float, 2>(N).total;
   else if (kind == KJX_BLOCK_MATERN52) total = dtype_bytes == 8 ? SmallLayout<double, 3>(N).total : SmallLayout<float, 3>(N).total;
+  else if (generic_ok(m)) total = dtype_bytes == 8 ? generic_ws_bytes<double>(m, N) : generic_ws_bytes<float>(m, N);
   else return KJX_ERR_UNSUPPORTED;
   *bytes = total;
   return KJX_OK;
