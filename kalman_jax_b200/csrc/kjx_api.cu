@@ -281,14 +281,15 @@ struct Fused {
     fa.vec_ok = (lay.L % 4 == 0) && aligned_to(dt, al) && aligned_to(y, al) && aligned_to(site_mean, al) && aligned_to(site_var, al);
   }
   unsigned grid() const { return (unsigned)((fa.a.nchunks + KJX_BLOCK - 1) / KJX_BLOCK); }
-  void reduce(cudaStream_t st) {
+  // total_out: where the top-level scan writes the shard's element (default: the workspace slot)
+  void reduce(cudaStream_t st, T* total_out = nullptr) {
     if (fa.vec_ok) fused_fold_kernel<T, KIND, true><<<grid(), KJX_BLOCK, 0, st>>>(fa);
     else fused_fold_kernel<T, KIND, false><<<grid(), KJX_BLOCK, 0, st>>>(fa);
     // three levels of segment scans; the top level's single total is the shard's element
     const size_t smem = sizeof(T) * FSum<T, D>::NS * KJX_SEG;
     for (int l = 0; l < 3; ++l) {
       const unsigned nseg = (unsigned)((fa.lvl[l].n + KJX_SEG - 1) / KJX_SEG);
-      T* tot = (l < 2) ? fa.lvl[l + 1].items : fa.a.f_shard_total;
+      T* tot = (l < 2) ? fa.lvl[l + 1].items : (total_out ? total_out : fa.a.f_shard_total);
       const size_t tstride = (l < 2) ? fa.lvl[l + 1].stride : 1;
       fused_segscan_kernel<T, D><<<nseg, 64, smem, st>>>(fa.lvl[l], tot, tstride);
     }
@@ -389,8 +390,7 @@ int shard_summary(const kjx_model_t* m, int64_t N, const T* dt, const T* y, cons
   if (ws_bytes < SmallLayout<T, D>(N).total || !ws) return KJX_ERR_WORKSPACE;
   if (needs_sequential_filter(m, site_mean != nullptr)) return KJX_ERR_UNSUPPORTED;
   Fused<T, KIND> f(m, N, dt, y, site_mean, site_var, ws);
-  f.reduce(st);
-  copy_scalars_kernel<T><<<1, 64, 0, st>>>(summary_out, f.fa.a.f_shard_total, (int)FSum<T, D>::NS);
+  f.reduce(st, summary_out);              // the top-level scan writes the shard's element straight to the caller
   KJX_CUDA_CHECK(cudaGetLastError());
   return KJX_OK;
 }
@@ -400,7 +400,7 @@ int shard_filter(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const
   constexpr int D = BlockDim<KIND>::D;
   if (ws_bytes < SmallLayout<T, D>(N).total || !ws) return KJX_ERR_WORKSPACE;
   Fused<T, KIND> f(m, N, dt, y, site_mean, site_var, ws);
-  copy_state_kernel<T, D><<<1, 32, 0, st>>>((T*)f.fa.a.f_state_in, state_in);
+  f.fa.a.f_state_in = state_in;           // read in place
   f.filter(st);
   nlml_reduce_kernel<T><<<1, 256, 0, st>>>(f.fa.a.block_nlml, f.nthread_blocks, nlml_partial);
   KJX_CUDA_CHECK(cudaGetLastError());
@@ -413,7 +413,7 @@ int shard_smoother(const kjx_model_t* m, int64_t N, const T* dt, const T* y, con
   constexpr int D = BlockDim<KIND>::D;
   if (ws_bytes < SmallLayout<T, D>(N).total || !ws) return KJX_ERR_WORKSPACE;
   Fused<T, KIND> f(m, N, dt, y, site_mean, site_var, ws);
-  copy_state_kernel<T, D><<<1, 32, 0, st>>>((T*)f.fa.s_info_in, info_in);
+  f.fa.s_info_in = info_in;               // read in place
   f.smoother(post_mean, post_var, new_site_mean, new_site_var, !(flags & KJX_FLAG_NO_SITE_UPDATE), st);
   KJX_CUDA_CHECK(cudaGetLastError());
   return KJX_OK;

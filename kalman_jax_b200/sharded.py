@@ -48,8 +48,8 @@ class ShardedIteration(object):
         self.ws, _ = _workspace(self.model, self.N, torch.float64, self.device)
         self.nlml_part = torch.zeros(1, dtype=torch.float64, device=self.device)
         self.nlml = self.nlml_part
-        # kernels per iteration: reduce, blockscan, copy | fold | copy, filter, nlml-reduce | copy, smoother
-        self.launches_per_iteration = 9
+        # kernels per iteration: fold, 3 segment scans | fold-shards | filter, nlml-reduce | smoother
+        self.launches_per_iteration = 8
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)

@@ -119,7 +119,64 @@ static void emu_run(double lam, const double* Pinf_, int64_t N, int L, const dou
   }
 }
 
+template <int KIND>
+static void emu_shard_summary_t(double lam, const double* Pinf_, int64_t N, const double* dt, const double* yt, const double* R, double* out) {
+  constexpr int D = BlockDim<KIND>::D;
+  double Pinf[D][D];
+  for (int i = 0; i < D; ++i) for (int j = 0; j < D; ++j) Pinf[i][j] = Pinf_[i * D + j];
+  FSum<double, D> s; fsum_identity<double, D>(s);
+  for (int64_t k = 0; k < N; ++k) {
+    double F[D][D]; Transition<double, KIND>::eval(dt[k], lam, F);
+    fsum_fold_step<double, D>(s, F, Pinf, yt[k], R[k], false);
+  }
+  fsum_pack<double, D>(s, out);
+}
+
+template <int KIND>
+static void emu_shard_apply_t(double lam, const double* Pinf_, int64_t N, const double* dt, const double* yt, const double* R,
+                              const double* state_in, const double* info_in, double* fm, double* fP, double* sm, double* sP) {
+  constexpr int D = BlockDim<KIND>::D;
+  double Pinf[D][D];
+  for (int i = 0; i < D; ++i) for (int j = 0; j < D; ++j) Pinf[i][j] = Pinf_[i * D + j];
+  FiltState<double, D> x;
+  for (int i = 0; i < D; ++i) { x.m[i] = state_in[i]; for (int j = 0; j < D; ++j) x.P[i][j] = state_in[D + i * D + j]; }
+  for (int64_t k = 0; k < N; ++k) {
+    double F[D][D]; Transition<double, KIND>::eval(dt[k], lam, F);
+    filter_predict<double, D>(F, Pinf, x);
+    filter_update<double, D>(x, yt[k], R[k]);
+    for (int i = 0; i < D; ++i) { fm[k * D + i] = x.m[i]; for (int j = 0; j < D; ++j) fP[k * D * D + i * D + j] = x.P[i][j]; }
+  }
+  Info<double, D> f;
+  for (int i = 0; i < D; ++i) { f.eta[i] = info_in[i]; for (int j = 0; j < D; ++j) f.J[i][j] = info_in[D + i * D + j]; }
+  info_smooth<double, D>(f, x);                    // smoothed state of the shard's last step (two-filter identity)
+  for (int64_t k = N - 1; k >= 0; --k) {
+    if (k < N - 1) {
+      double F[D][D]; Transition<double, KIND>::eval(dt[k + 1], lam, F);
+      double mf[D], Pf[D][D];
+      for (int i = 0; i < D; ++i) { mf[i] = fm[k * D + i]; for (int j = 0; j < D; ++j) Pf[i][j] = fP[k * D * D + i * D + j]; }
+      SmoothGain<double, D> g; smoother_gain<double, D>(F, Pinf, mf, Pf, g);
+      smoother_step<double, D>(g, mf, Pf, x);
+    }
+    for (int i = 0; i < D; ++i) { sm[k * D + i] = x.m[i]; for (int j = 0; j < D; ++j) sP[k * D * D + i * D + j] = x.P[i][j]; }
+  }
+}
+
 extern "C" {
+
+// one shard of the time-sharded iteration, emulated on the host with the product's math
+int emu_shard_summary(int kind, double lam, const double* Pinf, int64_t N, const double* dt, const double* yt, const double* R, double* out) {
+  if (kind == KJX_BLOCK_MATERN32) emu_shard_summary_t<KJX_BLOCK_MATERN32>(lam, Pinf, N, dt, yt, R, out);
+  else if (kind == KJX_BLOCK_MATERN52) emu_shard_summary_t<KJX_BLOCK_MATERN52>(lam, Pinf, N, dt, yt, R, out);
+  else return -1;
+  return 0;
+}
+int emu_shard_apply(int kind, double lam, const double* Pinf, int64_t N, const double* dt, const double* yt, const double* R,
+                    const double* state_in, const double* info_in, double* fm, double* fP, double* sm, double* sP) {
+  if (kind == KJX_BLOCK_MATERN32) emu_shard_apply_t<KJX_BLOCK_MATERN32>(lam, Pinf, N, dt, yt, R, state_in, info_in, fm, fP, sm, sP);
+  else if (kind == KJX_BLOCK_MATERN52) emu_shard_apply_t<KJX_BLOCK_MATERN52>(lam, Pinf, N, dt, yt, R, state_in, info_in, fm, fP, sm, sP);
+  else return -1;
+  return 0;
+}
 
 // three-phase scan emulation of filter + smoother for given pseudo-observations (ytilde, R)
 int emu_filter_smoother(int kind, double lam, const double* Pinf, int64_t N, int L, const double* dt,
