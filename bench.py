@@ -306,6 +306,13 @@ def main():
         return
     hbm, peak_src = peaks()
     dom = int(np.argmax(ph[1:])) + 1                        # filter-apply or smoother-apply phase
+    traffic = None                                          # dram bytes per launch from the committed ncu --set full capture
+    try:
+        if world == 1 and args.log2n == 24:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")))["dram_bytes_per_launch"]
+            traffic = tr[("fused_filter_kernel", "fused_smoother_kernel")[dom - 1]]
+    except Exception:
+        pass
     dom_bytes = (BYTES_FILTER, BYTES_SMOOTHER)[dom - 1] * n_local
     achieved = dom_bytes / (ph[dom] * 1e-3) / 1e9
     line = {
@@ -317,7 +324,7 @@ def main():
                    "N": N, "state_dim": 3, "sharding": "time axis, %d contiguous shard(s)" % world,
                    "l2_policy": "inputs (%.1f GB per iteration per GPU) exceed the 126 MB L2; no flush needed" % (BYTES_PER_STEP * n_local / 1e9)},
         "roofline": {"bound": "hbm", "kernel": ("fused_filter_kernel (R3)", "fused_smoother_kernel (R4)")[dom - 1],
-                     "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                     "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
                      "peak_source": peak_src, "algorithmic_bytes_per_step": (BYTES_FILTER, BYTES_SMOOTHER)[dom - 1],
                      "phase_ms": {"reduce+scan+fold(R1,R2)": ph[0], "filter(R3)": ph[1], "smoother+sites(R4)": ph[2]},
                      "iteration": {"achieved": BYTES_PER_STEP * n_local / (ms_step * 1e-3) / 1e9,
