@@ -174,6 +174,7 @@ def main():
     ap.add_argument("--impl", default="kjx")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying CUDA graphs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -201,10 +202,12 @@ def main():
             dist.all_gather_into_tensor(out, t)
             return out
 
+        nl_buf = torch.zeros(1, dtype=torch.float64, device=dev)
+
         def reduce_nlml(t):
-            out = t.clone()
-            dist.all_reduce(out)
-            return out
+            nl_buf.copy_(t)
+            dist.all_reduce(nl_buf)
+            return nl_buf
 
     N = 1 << args.log2n
     dt, y = synth(N)
@@ -237,12 +240,28 @@ def main():
         it.iteration(update_sites=False, reduce_nlml=reduce_nlml)
     barrier()
     sampler.rows = sampler.rows[-2:]
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    # per-phase CUDA-event times (eager launches with events between the library calls; untimed for `value`)
+    n_ev = max(3, min(args.steps, 20))
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(n_ev)]
+    for k in range(n_ev):
+        it.iteration(events=ev[k], reduce_nlml=reduce_nlml)
+    barrier()
+    graphed = None
+    if not args.no_graph:
+        from kalman_jax_b200.sharded import GraphedIteration
+        try:
+            graphed = GraphedIteration(it, reduce_nlml)
+        except Exception as e:      # keep going eagerly, but say so
+            print("bench: CUDA-graph capture failed (%s); launching eagerly" % str(e).splitlines()[0], file=sys.stderr)
+            graphed = None
+    step_fn = graphed.replay if graphed else (lambda: it.iteration(reduce_nlml=reduce_nlml))
+    for _ in range(3):
+        step_fn()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     start.record()
     for k in range(args.steps):
-        it.iteration(events=ev[k], reduce_nlml=reduce_nlml)
+        nl_t = step_fn()
     stop.record()
     barrier()
     for _ in range(n_extra // 2):       # a few more samples under the same load right after the timed region
@@ -251,7 +270,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     ms_total = start.elapsed_time(stop)
     phases = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(3)] for e in ev]).mean(axis=0)   # ms
-    nlml = float(it.nlml)
+    nlml = float(nl_t)
     tt = torch.tensor([ms_total, phases[0], phases[1], phases[2]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -322,6 +341,7 @@ def main():
         "config": {"workload": "C5: synthetic Matern-5/2 (var 1, len 5) + Gaussian(0.5) + EP(power 0.5); one iteration = "
                                "filter(stored sites) -> RTS smoother -> site update; N=2^%d steps, d=3, f=1" % args.log2n,
                    "N": N, "state_dim": 3, "sharding": "time axis, %d contiguous shard(s)" % world,
+                   "launch": "CUDA graph replay (2 graphs: sites ping/pong)" if graphed else "eager (ctypes calls per iteration)",
                    "l2_policy": "inputs (%.1f GB per iteration per GPU) exceed the 126 MB L2; no flush needed" % (BYTES_PER_STEP * n_local / 1e9)},
         "roofline": {"bound": "hbm", "kernel": ("fused_filter_kernel (R3)", "fused_smoother_kernel (R4)")[dom - 1],
                      "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,

@@ -88,6 +88,34 @@ class ShardedIteration(object):
         return self.nlml
 
 
+class GraphedIteration(object):
+    """Two CUDA graphs (sites ping -> pong, pong -> ping) replaying ShardedIteration.iteration() without any host
+    work per step: at 8 GPUs a shard's iteration is ~200 us of device time, the same order as the Python / ctypes /
+    NCCL launch path, so the launch sequence is captured once (the all-gather included) and replayed."""
+    def __init__(self, it, reduce_nlml=None):
+        self.it, self.graphs, self.parity = it, [], 0
+        assert it.site_mean is not None
+        stream = torch.cuda.Stream(device=it.device)
+        stream.wait_stream(torch.cuda.current_stream(it.device))
+        with torch.cuda.stream(stream):
+            for _ in range(2):                                   # warm up on the side stream (NCCL, allocator)
+                it.iteration(reduce_nlml=reduce_nlml)
+        torch.cuda.current_stream(it.device).wait_stream(stream)
+        torch.cuda.synchronize(it.device)
+        self.nlml = []
+        for _ in range(2):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                self.nlml.append(it.iteration(reduce_nlml=reduce_nlml))
+            self.graphs.append(g)
+
+    def replay(self):
+        self.graphs[self.parity].replay()
+        out = self.nlml[self.parity]
+        self.parity ^= 1
+        return out
+
+
 def split_series(dt, y, world):
     """Contiguous time blocks: rank g owns steps [g N / G, (g+1) N / G); also dt of the next shard's first step."""
     N = len(dt)
