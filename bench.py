@@ -174,6 +174,8 @@ def main():
     ap.add_argument("--impl", default="kjx")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU summary exchange: fused peer-memory kernel (default) or NCCL all-gather")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying CUDA graphs")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -214,8 +216,22 @@ def main():
     sh_dt, sh_y, dt_next, lo, hi = split_series(dt, y, world)[rank]
     n_local = hi - lo
     prior, lik, rule = kjx.priors.Matern52(1.0, 5.0), kjx.likelihoods.Gaussian(0.5), kjx.approximate_inference.EP(power=0.5)
+    peer, exchange = None, "none (1 GPU)"
+    if world > 1:
+        exchange = "NCCL all_gather_into_tensor + fold kernel"
+        if args.exchange == "peer":
+            try:
+                from kalman_jax_b200.sharded import PeerExchange
+                peer = PeerExchange(world, rank, dev)
+                exchange = "fused peer-memory exchange+fold kernel (symmetric memory over NVLink)"
+            except Exception as e:
+                print("bench: symmetric memory unavailable (%s); using NCCL" % str(e).splitlines()[0], file=sys.stderr)
+        ok = torch.tensor([1 if (peer is not None or args.exchange == "nccl") else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)          # all ranks must agree on the path
+        if int(ok[0]) == 0:
+            peer, exchange = None, "NCCL all_gather_into_tensor + fold kernel"
     it = ShardedIteration(prior, lik, rule, sh_dt, sh_y, dt_next, rank, world, dev, gather,
-                          site_mean=sh_y.copy(), site_var=np.full(n_local, 0.5))
+                          site_mean=sh_y.copy(), site_var=np.full(n_local, 0.5), peer=peer)
 
     def barrier():
         torch.cuda.synchronize()
@@ -319,10 +335,18 @@ def main():
                "api": "kjx_run_host_f64 (pinned host arrays)" if world == 1 else "pinned copies + sharded C-ABI calls per rank",
                "nlml": float(o_nl[0])}
 
-    if rank != 0:
+    def finish():
+        # tear down without destroying the process group: the captured graphs hold NCCL work and
+        # destroy_process_group() can block on them; every rank is past its last collective here
+        sys.stdout.flush()
+        sys.stderr.flush()
         if world > 1:
-            dist.destroy_process_group()
-        return
+            torch.cuda.synchronize()
+            dist.barrier()
+            os._exit(0)
+
+    if rank != 0:
+        return finish()
     hbm, peak_src = peaks()
     dom = int(np.argmax(ph[1:])) + 1                        # filter-apply or smoother-apply phase
     traffic = None                                          # dram bytes per launch from the committed ncu --set full capture
@@ -341,6 +365,7 @@ def main():
         "config": {"workload": "C5: synthetic Matern-5/2 (var 1, len 5) + Gaussian(0.5) + EP(power 0.5); one iteration = "
                                "filter(stored sites) -> RTS smoother -> site update; N=2^%d steps, d=3, f=1" % args.log2n,
                    "N": N, "state_dim": 3, "sharding": "time axis, %d contiguous shard(s)" % world,
+                   "exchange": exchange,
                    "launch": "CUDA graph replay (2 graphs: sites ping/pong)" if graphed else "eager (ctypes calls per iteration)",
                    "l2_policy": "inputs (%.1f GB per iteration per GPU) exceed the 126 MB L2; no flush needed" % (BYTES_PER_STEP * n_local / 1e9)},
         "roofline": {"bound": "hbm", "kernel": ("fused_filter_kernel (R3)", "fused_smoother_kernel (R4)")[dom - 1],
@@ -363,8 +388,7 @@ def main():
                                 "sample": "first 2^22 steps of the same series, best of 3, C restatement of the reference's "
                                           "sequential loops (oracle/seq_filter.c); the recursion is one dependent chain"}
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == "__main__":

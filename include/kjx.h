@@ -190,6 +190,16 @@ int kjx_fold_shard_summaries_f64(const kjx_model_t* m, const double* summaries, 
                                  int32_t rank, double* state_out, double* info_out, kjx_stream_t stream);
 int kjx_fold_shard_summaries_host(const kjx_model_t* m, const double* summaries_host, int64_t stride, int32_t world,
                                   int32_t rank, double* state_out_host, double* info_out_host);
+/* The same exchange + fold fused into ONE kernel over NVLink / NVSwitch peer memory (no NCCL call): every
+ * rank's kernel stores its element straight into all peers' receive buffers, publishes a flag with system
+ * scope, waits for the world's flags in its own buffer and folds.  peer_bufs: DEVICE array [world] of pointers
+ * to each rank's receive buffer (symmetric memory mapped in every process, zero-initialised before first use):
+ *   doubles [2][world][stride] (two parities) followed by 64-bit flags [2][world].
+ * epoch: DEVICE counter owned by this rank (starts at 0); incremented by the kernel, so the call can be
+ * captured in a CUDA graph and replayed.  All `world` ranks must make the call the same number of times. */
+int kjx_exchange_fold_f64(const kjx_model_t* m, const double* my_summary, double* const* peer_bufs, int64_t stride,
+                          int32_t world, int32_t rank, uint64_t* epoch, double* state_out, double* info_out,
+                          kjx_stream_t stream);
 /* phase 3: the reference filter recursion over the shard from state_in; nlml_partial[1] = this shard's
  * share of the negative log marginal likelihood (sum the shards' values) */
 int kjx_filter_apply_f64(const kjx_model_t* m, int64_t N, const double* dt, const double* y,

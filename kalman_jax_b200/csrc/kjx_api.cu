@@ -69,8 +69,11 @@ SiteModel make_site(const kjx_model_t* m) {
 // busy on short series.  A multiple of 4 so a chunk starts on a 32-byte boundary of every array.
 int pick_chunk(int64_t N) {
   if (const char* e = getenv("KJX_CHUNK")) { const int v = atoi(e); if (v >= 4 && v % 4 == 0) return v; }   // tuning knob
-  const int64_t target_chunks = 148 * 2 * KJX_BLOCK;   // two resident blocks per SM
-  int64_t L = (N + target_chunks - 1) / target_chunks;
+  // Long series: 64 steps per thread amortise the O(d^3) scan combines (several waves of blocks anyway).
+  // Short series / small shards: the kernels are one wave of latency-bound threads, so the time is (steps per
+  // thread) x (latency of a step): spread the series over 95 % of the resident thread slots (3 blocks of 128 per SM).
+  const int64_t slots = (int64_t)(148 * 3 * KJX_BLOCK * 0.95);
+  int64_t L = (N + slots - 1) / slots;
   L = std::max<int64_t>(4, std::min<int64_t>(64, L));
   // the fused scan hierarchy has three levels of 128: at most 128^3 chunks
   const int64_t max_chunks = (int64_t)KJX_SEG * KJX_SEG * KJX_SEG;
@@ -438,6 +441,41 @@ __host__ __device__ void fold_shards(const double* Pinf, const double* summaries
   for (int i = 0; i < D; ++i) for (int j = 0; j < D; ++j) { state_out[D + i * D + j] = x.P[i][j]; info_out[D + i * D + j] = f.J[i][j]; }
 }
 template <int D> struct PinfArg { double v[D * D]; };
+
+// Exchange + fold over peer memory.  One block; thread r < world talks to peer r.
+template <int D>
+__global__ void exchange_fold_kernel(PinfArg<D> pinf, const double* __restrict__ mine, double* const* __restrict__ peer_bufs,
+                                     int64_t stride, int world, int rank, unsigned long long* epoch, double* state_out,
+                                     double* info_out) {
+  constexpr int NS = FSum<double, D>::NS;
+  __shared__ double gathered[8 * 64];       // world <= 8 here, stride <= 64
+  const unsigned long long e = *epoch + 1ull;
+  const int par = (int)(e & 1ull);
+  const int r = threadIdx.x;
+  if (r < world) {
+    // 1. my element -> peer r's receive slot [par][rank]   (remote stores over NVLink; local for r == rank)
+    double* dst = peer_bufs[r] + ((size_t)par * world + rank) * stride;
+    for (int k = 0; k < NS; ++k) dst[k] = mine[k];
+    __threadfence_system();
+    unsigned long long* flag = reinterpret_cast<unsigned long long*>(peer_bufs[r] + (size_t)2 * world * stride) + (size_t)par * world + rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(flag), "l"(e) : "memory");
+    // 2. wait for peer r's element in MY buffer
+    const unsigned long long* myflag = reinterpret_cast<const unsigned long long*>(peer_bufs[rank] + (size_t)2 * world * stride) + (size_t)par * world + r;
+    unsigned long long seen;
+    do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(myflag) : "memory"); } while (seen < e);
+    const double* src = peer_bufs[rank] + ((size_t)par * world + r) * stride;
+    for (int k = 0; k < NS; ++k) {
+      double v;
+      asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(src + k) : "memory");
+      gathered[r * 64 + k] = v;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    fold_shards<D>(pinf.v, gathered, 64, world, rank, state_out, info_out);
+    *epoch = e;
+  }
+}
 template <int D>
 __global__ void fold_shards_kernel(PinfArg<D> pinf, const double* summaries, int64_t stride, int world, int rank,
                                    double* state_out, double* info_out) {
@@ -788,6 +826,24 @@ int kjx_fold_shard_summaries_f64(const kjx_model_t* m, const double* summaries, 
   } else {
     PinfArg<3> p; for (int i = 0; i < 9; ++i) p.v[i] = m->Pinf[i];
     fold_shards_kernel<3><<<1, 32, 0, (cudaStream_t)stream>>>(p, summaries, stride, world, rank, state_out, info_out);
+  }
+  return cudaGetLastError() == cudaSuccess ? KJX_OK : KJX_ERR_CUDA;
+}
+
+int kjx_exchange_fold_f64(const kjx_model_t* m, const double* my_summary, double* const* peer_bufs, int64_t stride,
+                          int32_t world, int32_t rank, uint64_t* epoch, double* state_out, double* info_out,
+                          kjx_stream_t stream) {
+  if (!model_basic_ok(m) || !my_summary || !peer_bufs || !epoch || !state_out || !info_out) return KJX_ERR_INVALID_ARG;
+  if (world < 1 || world > 8 || rank < 0 || rank >= world) return KJX_ERR_INVALID_ARG;
+  if (stride < (int64_t)kjx_filter_summary_doubles(m->state_dim) || stride > 64) return KJX_ERR_INVALID_ARG;
+  if (!small_kind(m)) return KJX_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (m->state_dim == 2) {
+    PinfArg<2> p; for (int i = 0; i < 4; ++i) p.v[i] = m->Pinf[i];
+    exchange_fold_kernel<2><<<1, 32, 0, st>>>(p, my_summary, peer_bufs, stride, world, rank, (unsigned long long*)epoch, state_out, info_out);
+  } else {
+    PinfArg<3> p; for (int i = 0; i < 9; ++i) p.v[i] = m->Pinf[i];
+    exchange_fold_kernel<3><<<1, 32, 0, st>>>(p, my_summary, peer_bufs, stride, world, rank, (unsigned long long*)epoch, state_out, info_out);
   }
   return cudaGetLastError() == cudaSuccess ? KJX_OK : KJX_ERR_CUDA;
 }

@@ -20,6 +20,26 @@ from . import _lib
 from .sde_gp import _Model, _workspace
 
 
+class PeerExchange(object):
+    """Symmetric-memory receive buffers for kjx_exchange_fold (one fused exchange + fold kernel over NVLink peer
+    memory instead of an NCCL all-gather followed by a fold kernel)."""
+    STRIDE = 32
+
+    def __init__(self, world, rank, device, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group or dist.group.WORLD
+        n = 2 * world * self.STRIDE + 2 * world             # data [2][world][stride] + flags [2][world] (8 bytes each)
+        self.buf = symm_mem.empty(n, dtype=torch.float64, device=device)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, group)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)                                  # every buffer is zeroed before anyone writes
+        self.ptrs = torch.tensor(list(self.handle.buffer_ptrs), dtype=torch.int64, device=device)
+        self.epoch = torch.zeros(1, dtype=torch.int64, device=device)
+        self.world, self.rank = world, rank
+
+
 class ShardedIteration(object):
     """Holds one rank's shard of (dt, y, sites) resident in HBM and runs run()-style iterations on it.
 
@@ -27,8 +47,9 @@ class ShardedIteration(object):
     (torch.distributed.all_gather_into_tensor); it is None for world == 1.
     """
     def __init__(self, prior, likelihood, sites, dt_shard, y_shard, dt_next, rank, world, device, gather=None,
-                 site_mean=None, site_var=None):
+                 site_mean=None, site_var=None, peer=None):
         self.model = _Model(prior, likelihood, sites)
+        self.peer = peer
         self.rank, self.world, self.device, self.gather = rank, world, torch.device(device), gather
         self.dt = torch.as_tensor(dt_shard, dtype=torch.float64, device=self.device).contiguous()
         self.y = torch.as_tensor(y_shard, dtype=torch.float64, device=self.device).contiguous().reshape(-1)
@@ -64,9 +85,14 @@ class ShardedIteration(object):
             events[0].record()
         _lib.check(L.kjx_filter_summary_f64(m, N, p(self.dt), p(self.y), p(self.site_mean), p(self.site_var),
                                             p(self.fmsg), p(self.ws), wsb, st), "kjx_filter_summary")
-        allf = self.gather(self.fmsg) if self.gather else self.fmsg.reshape(1, -1)
-        _lib.check(L.kjx_fold_shard_summaries_f64(m, p(allf), C.c_int64(allf.shape[1]), self.world, self.rank,
-                                                  p(self.f_state), p(self.s_info), st), "kjx_fold_shard_summaries")
+        if self.peer is not None:
+            _lib.check(L.kjx_exchange_fold_f64(m, p(self.fmsg), p(self.peer.ptrs), C.c_int64(self.peer.STRIDE), self.world,
+                                               self.rank, p(self.peer.epoch), p(self.f_state), p(self.s_info), st),
+                       "kjx_exchange_fold")
+        else:
+            allf = self.gather(self.fmsg) if self.gather else self.fmsg.reshape(1, -1)
+            _lib.check(L.kjx_fold_shard_summaries_f64(m, p(allf), C.c_int64(allf.shape[1]), self.world, self.rank,
+                                                      p(self.f_state), p(self.s_info), st), "kjx_fold_shard_summaries")
         if events:
             events[1].record()
         _lib.check(L.kjx_filter_apply_f64(m, N, p(self.dt), p(self.y), p(self.site_mean), p(self.site_var),
