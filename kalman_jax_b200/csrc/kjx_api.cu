@@ -75,8 +75,8 @@ int pick_chunk(int64_t N) {
   const int64_t slots = (int64_t)(148 * 3 * KJX_BLOCK * 0.95);
   int64_t L = (N + slots - 1) / slots;
   L = std::max<int64_t>(4, std::min<int64_t>(64, L));
-  // the fused scan hierarchy has three levels of 128: at most 128^3 chunks
-  const int64_t max_chunks = (int64_t)KJX_SEG * KJX_SEG * KJX_SEG;
+  // the fused scan hierarchy has three levels of at most 128: at most 128^3 chunks
+  const int64_t max_chunks = (int64_t)KJX_SEG_MAX * KJX_SEG_MAX * KJX_SEG_MAX;
   if ((N + L - 1) / L > max_chunks) L = (N + max_chunks - 1) / max_chunks;
   return (int)round_up((size_t)L, 4);
 }
@@ -86,6 +86,7 @@ template <typename T, int D> struct SmallLayout {
   size_t off_ftp, off_fbt, off_fbp, off_fst, off_sts, off_sbt, off_sbs, off_sst, off_nl, off_fin, off_sin;
   size_t off_info, off_xf, off_lvl[3][3], lvl_stride[3], total;
   int64_t lvl_n[3];
+  int seg;
   explicit SmallLayout(int64_t N) {
     constexpr size_t FNS = FSum<T, D>::NS, SNS = SSum<T, D>::NS;
     L = pick_chunk(N);
@@ -100,11 +101,13 @@ template <typename T, int D> struct SmallLayout {
     off_nl = take(bstride); off_fin = take(D + D * D); off_sin = take(D + D * D);
     off_info = take(D + D * D);
     // three scan levels of the fused path: elements, exclusive prefix, exclusive suffix (strides = whole segments)
+    // segments of 64 while three levels of 64 hold every chunk (shorter dependent chains), else 128
+    seg = (nchunks <= 64 * 64 * 64 / 2) ? 64 : 128;
     int64_t n = nchunks;
     for (int l = 0; l < 3; ++l) {
-      lvl_n[l] = n; lvl_stride[l] = round_up((size_t)n, KJX_SEG);
+      lvl_n[l] = n; lvl_stride[l] = round_up((size_t)n, KJX_SEG_MAX);
       for (int q = 0; q < 3; ++q) off_lvl[l][q] = take(FNS * lvl_stride[l]);
-      n = (n + KJX_SEG - 1) / KJX_SEG;
+      n = (n + seg - 1) / seg;
     }
     // filtered moments between the fused filter and smoother passes: [warp][step][element][lane]
     off_xf = take(cstride * (size_t)L * Packed<D>::NP);
@@ -129,6 +132,7 @@ void bind_fused(FusedArgs<T, D>& fa, const SmallLayout<T, D>& lay, void* ws) {
   char* w = (char*)ws;
   bind_workspace<T, D>(fa.a, lay, ws);
   fa.s_info_in = (T*)(w + lay.off_info); fa.xf = (T*)(w + lay.off_xf);
+  fa.seg = lay.seg;
   for (int l = 0; l < 3; ++l) {
     fa.lvl[l].items = (T*)(w + lay.off_lvl[l][0]); fa.lvl[l].prefix = (T*)(w + lay.off_lvl[l][1]);
     fa.lvl[l].suffix = (T*)(w + lay.off_lvl[l][2]); fa.lvl[l].stride = lay.lvl_stride[l]; fa.lvl[l].n = lay.lvl_n[l];
@@ -289,12 +293,13 @@ struct Fused {
     if (fa.vec_ok) fused_fold_kernel<T, KIND, true><<<grid(), KJX_BLOCK, 0, st>>>(fa);
     else fused_fold_kernel<T, KIND, false><<<grid(), KJX_BLOCK, 0, st>>>(fa);
     // three levels of segment scans; the top level's single total is the shard's element
-    const size_t smem = sizeof(T) * FSum<T, D>::NS * KJX_SEG;
+    const size_t smem = sizeof(T) * FSum<T, D>::NS * fa.seg;
     for (int l = 0; l < 3; ++l) {
-      const unsigned nseg = (unsigned)((fa.lvl[l].n + KJX_SEG - 1) / KJX_SEG);
+      const unsigned nseg = (unsigned)((fa.lvl[l].n + fa.seg - 1) / fa.seg);
       T* tot = (l < 2) ? fa.lvl[l + 1].items : (total_out ? total_out : fa.a.f_shard_total);
       const size_t tstride = (l < 2) ? fa.lvl[l + 1].stride : 1;
-      fused_segscan_kernel<T, D><<<nseg, 64, smem, st>>>(fa.lvl[l], tot, tstride);
+      if (fa.seg == 64) fused_segscan_kernel<T, D, 64><<<nseg, 64, smem, st>>>(fa.lvl[l], tot, tstride);
+      else fused_segscan_kernel<T, D, 128><<<nseg, 64, smem, st>>>(fa.lvl[l], tot, tstride);
     }
   }
   void filter(cudaStream_t st) {

@@ -101,6 +101,7 @@ template <typename T, int D> struct FusedArgs {
   T* xf;                    // filtered moments, private layout
   const T* s_info_in;       // [D + D*D] information (eta, J) of all later shards about this shard's last state
   int vec_ok;               // every per-step array is 32-byte (fp64) / 16-byte (fp32) aligned
+  int seg;                  // elements per scan segment (64 or 128)
 };
 
 template <typename T, int D>
@@ -113,16 +114,17 @@ __device__ __forceinline__ void load_info(const T* p, Info<T, D>& f) {
     for (int j = 0; j < D; ++j) f.J[i][j] = p[D + i * D + j];
 }
 
-constexpr int KJX_SEG = 128;             // elements per scan segment = one block of the segment-scan kernel
-constexpr int KJX_SEG_PER = KJX_SEG / 32;
+constexpr int KJX_SEG_MAX = 128;         // elements per scan segment (= one block of the segment-scan kernel): 128
+                                         // for long series (fewer, fuller levels), 64 for short ones (shorter chains)
 
 // Slot of element i in a per-level workspace array.  A scan warp owns KJX_SEG_PER consecutive elements per
 // lane; storing element q = PER*lane + j of a segment at j*32 + lane makes the segment a [PER][32] tile that
 // stages into shared memory with coalesced copies and is read bank-conflict-free.  (The fold / filter /
 // smoother threads touch these arrays once per chunk, scattered, which is negligible.)
-__host__ __device__ __forceinline__ int64_t seg_slot(int64_t i) {
-  const int64_t q = i % KJX_SEG;
-  return (i - q) + (q % KJX_SEG_PER) * 32 + q / KJX_SEG_PER;
+__host__ __device__ __forceinline__ int64_t seg_slot(int64_t i, int seg) {
+  const int per = seg >> 5;
+  const int64_t q = i % seg;
+  return (i - q) + (q % per) * 32 + q / per;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(KJX_BLOCK) fused_fold_kernel(const FusedArgs<T
     T yt, R; step_site<T, D>(a, k, yt, R);
     fsum_fold_step<T, D>(mine, F, Pinf, yt, R, a.mask ? (a.mask[k] != 0) : false);
   }
-  sum_store<S>(fa.lvl[0].items, fa.lvl[0].stride, seg_slot(c), mine);
+  sum_store<S>(fa.lvl[0].items, fa.lvl[0].stride, seg_slot(c, fa.seg), mine);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -170,10 +172,10 @@ __global__ void __launch_bounds__(KJX_BLOCK) fused_fold_kernel(const FusedArgs<T
 // with cp.async (27 KB at d=3), warp 0 produces the exclusive PREFIX of every element, warp 1 the exclusive SUFFIX,
 // concurrently.  Per warp: 3 sequential combines for the lane totals, a 5-level shuffle scan, 3 more to expand —
 // a dependent chain of 11 combines whose operands all live in shared memory or registers.
-template <typename S> __device__ __forceinline__ void smem_item(const typename SumOps<S>::Scalar* sm, int slot, S& it) {
+template <typename S, int SEG> __device__ __forceinline__ void smem_item(const typename SumOps<S>::Scalar* sm, int slot, S& it) {
   typename SumOps<S>::Scalar v[SumOps<S>::NS];
 #pragma unroll
-  for (int k = 0; k < SumOps<S>::NS; ++k) v[k] = sm[k * KJX_SEG + slot];
+  for (int k = 0; k < SumOps<S>::NS; ++k) v[k] = sm[k * SEG + slot];
   SumOps<S>::unpack(v, it);
 }
 
@@ -192,12 +194,13 @@ template <typename S, bool REVERSE> __device__ __forceinline__ S warp_scan_inclu
   return inc;
 }
 
-template <typename T, int D, bool REVERSE>
+template <typename T, int D, bool REVERSE, int SEG>
 __device__ __forceinline__ void segscan_pass(const T* sm, const ScanLevel<T, D>& lv, int64_t first, int lane, T* total_out,
                                              size_t total_stride, int64_t total_slot) {
   using S = FSum<T, D>;
+  constexpr int KJX_SEG_PER = SEG / 32;
   auto live = [&](int j) { return first + (int64_t)lane * KJX_SEG_PER + j < lv.n; };
-  auto item = [&](int j, S& it) { if (live(j)) smem_item<S>(sm, j * 32 + lane, it); else SumOps<S>::identity(it); };
+  auto item = [&](int j, S& it) { if (live(j)) smem_item<S, SEG>(sm, j * 32 + lane, it); else SumOps<S>::identity(it); };
   S tot; item(0, tot);
 #pragma unroll 1
   for (int j = 1; j < KJX_SEG_PER; ++j) { S it; item(j, it); S r; SumOps<S>::combine(tot, it, r); tot = r; }
@@ -224,9 +227,10 @@ __device__ __forceinline__ void segscan_pass(const T* sm, const ScanLevel<T, D>&
   }
 }
 
-template <typename T, int D>
+template <typename T, int D, int SEG>
 __global__ void __launch_bounds__(64) fused_segscan_kernel(const ScanLevel<T, D> lv, T* total_out, size_t total_stride) {
   using S = FSum<T, D>;
+  constexpr int KJX_SEG = SEG;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* sm = reinterpret_cast<T*>(smem_raw);                  // [NS][KJX_SEG]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -242,8 +246,8 @@ __global__ void __launch_bounds__(64) fused_segscan_kernel(const ScanLevel<T, D>
   asm volatile("cp.async.commit_group;" ::: "memory");
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  if (warp == 0) segscan_pass<T, D, false>(sm, lv, first, lane, total_out, total_stride, seg_slot(blockIdx.x));
-  else segscan_pass<T, D, true>(sm, lv, first, lane, nullptr, 0, 0);
+  if (warp == 0) segscan_pass<T, D, false, SEG>(sm, lv, first, lane, total_out, total_stride, seg_slot(blockIdx.x, SEG));
+  else segscan_pass<T, D, true, SEG>(sm, lv, first, lane, nullptr, 0, 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -263,9 +267,9 @@ __global__ void __launch_bounds__(KJX_BLOCK, KJX_R3_MINB) fused_filter_kernel(co
   if (s0 < s1) {
     FiltState<T, D> x; load_state<T, D>(a.f_state_in, x);
     {   // everything before this chunk: super-segments, segments, chunks (outermost first)
-      int64_t idx[3] = {c, c / KJX_SEG, c / (KJX_SEG * KJX_SEG)};
+      int64_t idx[3] = {c, c / fa.seg, c / ((int64_t)fa.seg * fa.seg)};
 #pragma unroll 1
-      for (int l = 2; l >= 0; --l) { FS p; sum_load<FS>(fa.lvl[l].prefix, fa.lvl[l].stride, seg_slot(idx[l]), p); fsum_apply<T, D>(p, x); }
+      for (int l = 2; l >= 0; --l) { FS p; sum_load<FS>(fa.lvl[l].prefix, fa.lvl[l].stride, seg_slot(idx[l], fa.seg), p); fsum_apply<T, D>(p, x); }
     }
     T* xf = fa.xf + ((c >> 5) * (int64_t)a.L * NP) * 32 + (c & 31);
     const T* ysrc = a.gaussian_init ? a.y : a.site_mean;
@@ -348,9 +352,9 @@ __global__ void __launch_bounds__(KJX_BLOCK, KJX_R4_MINB) fused_smoother_kernel(
   {
     Info<T, D> info; load_info<T, D>(fa.s_info_in, info);
     {   // everything after this chunk
-      int64_t idx[3] = {c, c / KJX_SEG, c / (KJX_SEG * KJX_SEG)};
+      int64_t idx[3] = {c, c / fa.seg, c / ((int64_t)fa.seg * fa.seg)};
 #pragma unroll 1
-      for (int l = 2; l >= 0; --l) { FS q; sum_load<FS>(fa.lvl[l].suffix, fa.lvl[l].stride, seg_slot(idx[l]), q); fsum_combine_info<T, D>(q, info, info); }
+      for (int l = 2; l >= 0; --l) { FS q; sum_load<FS>(fa.lvl[l].suffix, fa.lvl[l].stride, seg_slot(idx[l], fa.seg), q); fsum_combine_info<T, D>(q, info, info); }
     }
     xf_load<T, D>(xf + (k - s0) * NP * 32, x.m, x.P);
     info_smooth<T, D>(info, x);
