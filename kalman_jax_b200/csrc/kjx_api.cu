@@ -493,11 +493,12 @@ bool generic_ok(const kjx_model_t* m) {
 }
 template <typename T> size_t generic_ws_bytes(const kjx_model_t* m, int64_t N) {
   const size_t d = (size_t)m->state_dim, n = (size_t)std::max<int64_t>(N, 1);
-  return round_up(d * d * 8, 256) + round_up(d * 8, 256) + round_up(n * d * sizeof(T), 256) + round_up(n * d * d * sizeof(T), 256);
+  // Pinf, H | dense filter output (kjx_run without caller buffers) | RTS gains [N,d,d]
+  return round_up(d * d * 8, 256) + round_up(d * 8, 256) + round_up(n * d * sizeof(T), 256) + 2 * round_up(n * d * d * sizeof(T), 256);
 }
 template <typename T>
 int generic_setup(const kjx_model_t* m, int64_t N, void* ws, size_t ws_bytes, GenArgs<T>& g, T** scratch_mean, T** scratch_cov,
-                  cudaStream_t st) {
+                  T** scratch_gain, cudaStream_t st) {
   if (!ws || ws_bytes < generic_ws_bytes<T>(m, N)) return KJX_ERR_WORKSPACE;
   const size_t d = (size_t)m->state_dim;
   memset(&g, 0, sizeof(g));
@@ -508,7 +509,8 @@ int generic_setup(const kjx_model_t* m, int64_t N, void* ws, size_t ws_bytes, Ge
   double* pinf_dev = (double*)w; w += round_up(d * d * 8, 256);
   double* h_dev = (double*)w; w += round_up(d * 8, 256);
   *scratch_mean = (T*)w; w += round_up((size_t)std::max<int64_t>(N, 1) * d * sizeof(T), 256);
-  *scratch_cov = (T*)w;
+  *scratch_cov = (T*)w; w += round_up((size_t)std::max<int64_t>(N, 1) * d * d * sizeof(T), 256);
+  *scratch_gain = (T*)w;
   KJX_CUDA_CHECK(cudaMemcpyAsync(pinf_dev, m->Pinf, d * d * 8, cudaMemcpyHostToDevice, st));
   g.Pinf = pinf_dev;
   if (m->H_steps) { g.H_steps = m->H_steps; g.H = nullptr; }
@@ -521,10 +523,15 @@ template <typename T> int generic_launch_filter(const GenArgs<T>& g, cudaStream_
   generic_filter_kernel<T><<<1, KJX_GEN_THREADS, smem, st>>>(g);
   return KJX_OK;
 }
-template <typename T> int generic_launch_smoother(const GenArgs<T>& g, cudaStream_t st) {
+template <typename T> int generic_launch_smoother(const GenArgs<T>& g, T* gains, cudaStream_t st) {
   const size_t smem = generic_smoother_smem<T>(g.d);
+  // 1. all RTS gains, parallel over time (they depend on the filtered moments only)
+  KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_gain_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const unsigned grid = (unsigned)std::min<int64_t>(g.N, 148 * 4);
+  generic_gain_kernel<T><<<grid, KJX_GEN_THREADS, smem, st>>>(g, gains);
+  // 2. the backward recursion itself (two d^3 products per step), one CTA in reference order
   KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_smoother_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  generic_smoother_kernel<T><<<1, KJX_GEN_THREADS, smem, st>>>(g);
+  generic_smoother_kernel<T><<<1, KJX_GEN_THREADS, smem, st>>>(g, gains);
   return KJX_OK;
 }
 
@@ -532,8 +539,8 @@ template <typename T>
 int generic_filter(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const uint8_t* mask, const T* site_mean,
                    const T* site_var, T* filt_mean, T* filt_cov, T* out_site_mean, T* out_site_var, T* nlml, void* ws,
                    size_t ws_bytes, cudaStream_t st) {
-  GenArgs<T> g; T *sm, *sc;
-  int rc = generic_setup<T>(m, N, ws, ws_bytes, g, &sm, &sc, st);
+  GenArgs<T> g; T *sm, *sc, *sg;
+  int rc = generic_setup<T>(m, N, ws, ws_bytes, g, &sm, &sc, &sg, st);
   if (rc != KJX_OK) return rc;
   if (N == 0) { cudaMemsetAsync(nlml, 0, sizeof(T), st); return KJX_OK; }
   g.dt = dt; g.y = y; g.mask = mask; g.site_mean = site_mean; g.site_var = site_var;
@@ -548,8 +555,8 @@ template <typename T>
 int generic_smoother(const kjx_model_t* m, int64_t N, const T* dt, const T* filt_mean, const T* filt_cov, const T* y,
                      const T* site_mean, const T* site_var, T* smooth_mean, T* smooth_cov, T* new_site_mean, T* new_site_var,
                      void* ws, size_t ws_bytes, uint32_t flags, cudaStream_t st) {
-  GenArgs<T> g; T *sm, *sc;
-  int rc = generic_setup<T>(m, N, ws, ws_bytes, g, &sm, &sc, st);
+  GenArgs<T> g; T *sm, *sc, *sg;
+  int rc = generic_setup<T>(m, N, ws, ws_bytes, g, &sm, &sc, &sg, st);
   if (rc != KJX_OK) return rc;
   if (N == 0) return KJX_OK;
   g.dt = dt; g.y = y; g.site_mean = site_mean; g.site_var = site_var;
@@ -557,7 +564,7 @@ int generic_smoother(const kjx_model_t* m, int64_t N, const T* dt, const T* filt
   g.smooth_mean = smooth_mean; g.smooth_cov = smooth_cov; g.new_site_mean = new_site_mean; g.new_site_var = new_site_var;
   g.return_full = (flags & KJX_FLAG_RETURN_FULL) ? 1 : 0;
   g.update_sites = (new_site_mean != nullptr && site_mean != nullptr && y != nullptr) ? 1 : 0;
-  rc = generic_launch_smoother<T>(g, st);
+  rc = generic_launch_smoother<T>(g, sg, st);
   if (rc != KJX_OK) return rc;
   KJX_CUDA_CHECK(cudaGetLastError());
   return KJX_OK;
@@ -566,8 +573,8 @@ template <typename T>
 int generic_run(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const T* site_mean, const T* site_var,
                 T* filt_mean, T* filt_cov, T* new_site_mean, T* new_site_var, T* post_mean, T* post_var, T* nlml,
                 void* ws, size_t ws_bytes, uint32_t flags, cudaStream_t st) {
-  GenArgs<T> g; T *sm, *sc;
-  int rc = generic_setup<T>(m, N, ws, ws_bytes, g, &sm, &sc, st);
+  GenArgs<T> g; T *sm, *sc, *sg;
+  int rc = generic_setup<T>(m, N, ws, ws_bytes, g, &sm, &sc, &sg, st);
   if (rc != KJX_OK) return rc;
   if (N == 0) { cudaMemsetAsync(nlml, 0, sizeof(T), st); return KJX_OK; }
   if (!filt_mean) { filt_mean = sm; filt_cov = sc; }       // run() uses the filtered moments only internally
@@ -581,7 +588,7 @@ int generic_run(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const 
   g.filt_mean_in = filt_mean; g.filt_cov_in = filt_cov;
   g.smooth_mean = post_mean; g.smooth_cov = post_var; g.new_site_mean = new_site_mean; g.new_site_var = new_site_var;
   g.return_full = 0; g.update_sites = (flags & KJX_FLAG_NO_SITE_UPDATE) ? 0 : 1;
-  rc = generic_launch_smoother<T>(g, st);
+  rc = generic_launch_smoother<T>(g, sg, st);
   if (rc != KJX_OK) return rc;
   KJX_CUDA_CHECK(cudaGetLastError());
   return KJX_OK;

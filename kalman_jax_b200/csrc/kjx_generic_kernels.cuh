@@ -127,23 +127,25 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_filter_kernel(const G
       HP[j] = s;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {            // warp 0: the step's scalar work; cubature points spread over its lanes
       T pm = T(0), pv = T(0);
       for (int i = 0; i < d; ++i) { pm += Hrow[i] * mp[i]; pv += HP[i] * Hrow[i]; }   // :283-284
       const bool masked = g.mask ? (g.mask[n] != 0) : false;
       T smean, svar, lml = T(0);
       if (g.init_sites) {
-        const SiteOut<T> o = site_update<T>(g.site, masked ? pm : g.y[n], pm, pv, false, T(0), T(0));   // :286-287
+        const SiteOut<T> o = site_update<T, WarpRed>(g.site, masked ? pm : g.y[n], pm, pv, false, T(0), T(0));   // :286-287
         smean = o.mean; svar = o.var; lml = o.lml;
       } else {
         if (g.site_mean) { smean = g.site_mean[n]; svar = g.site_var[n]; }           // :290
         else { smean = g.y[n]; svar = T(g.site.lik_hyp); }                           // Gaussian + EP initialisation
-        if (!masked) lml = filter_loglik<T>(g.site, g.y[n], pm, pv);                 // log Z is always the true likelihood's
+        if (!masked) lml = filter_loglik<T, WarpRed>(g.site, g.y[n], pm, pv);        // log Z is always the true likelihood's
       }
       if (masked) lml = T(0);                                                        // :300
-      sh[0] = pm; sh[2] = smean; sh[3] = svar; sh[4] = inv1(pv + svar); sh[5] = masked ? T(1) : T(0);   // :292-294
-      sh[6] += lml;                                                                  // :301
-      if (g.out_site_mean) { g.out_site_mean[n] = smean; g.out_site_var[n] = svar; }
+      if (threadIdx.x == 0) {
+        sh[0] = pm; sh[2] = smean; sh[3] = svar; sh[4] = inv1(pv + svar); sh[5] = masked ? T(1) : T(0);   // :292-294
+        sh[6] += lml;                                                                // :301
+        if (g.out_site_mean) { g.out_site_mean[n] = smean; g.out_site_var[n] = svar; }
+      }
     }
     __syncthreads();
     const bool masked = sh[5] != T(0);
@@ -166,9 +168,17 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_filter_kernel(const G
 }
 
 // ------------------------------------------------------------------------------------------------
-// in-place Cholesky (lower) of the d x d matrix A in shared memory; rinv[j] = 1 / L[j][j]
+// in-place Cholesky (lower, left-looking) of the d x d matrix A in shared memory; rinv[j] = 1 / L[j][j].
+// Column j: every row i >= j subtracts its dot product with row j of the already finished columns (one thread per
+// row), then the column is scaled: 2 barriers per column and no d^2 trailing update.
 template <typename T> __device__ void chol_inplace(int d, T* A, T* rinv) {
   for (int j = 0; j < d; ++j) {
+    for (int i = j + threadIdx.x; i < d; i += blockDim.x) {
+      T v = A[i * d + j];
+      for (int k = 0; k < j; ++k) v -= A[i * d + k] * A[j * d + k];
+      A[i * d + j] = v;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
       const T piv = A[j * d + j];
       const T r = rsqrt_(piv);           // NaN for a negative pivot, like a failed potrf propagated by jaxlib
@@ -178,19 +188,70 @@ template <typename T> __device__ void chol_inplace(int d, T* A, T* rinv) {
     __syncthreads();
     const T r = rinv[j];
     for (int i = j + 1 + threadIdx.x; i < d; i += blockDim.x) A[i * d + j] *= r;
-    __syncthreads();
-    const int rem = d - j - 1;
-    for (int e = threadIdx.x; e < rem * rem; e += blockDim.x) {
-      const int i = j + 1 + e / rem, k = j + 1 + e % rem;
-      if (k <= i) A[i * d + k] -= A[i * d + j] * A[k * d + j];
+    // (row j itself is only read by later columns after the next barrier)
+  }
+  __syncthreads();
+}
+
+// X <- solve(L L^T, X) for the d right-hand-side columns of X (utils.py:30).  The substitutions run over rows; within
+// a row every column is independent, so (column, k-slice) pairs are spread over the CTA: `TPC` threads share one
+// column's dot product and combine by shuffle.
+template <typename T, int TPC> __device__ void chol_substitute(int d, const T* L, const T* rinv, T* X) {
+  const int lane_in = threadIdx.x % TPC;
+  const int col0 = threadIdx.x / TPC, ncol = blockDim.x / TPC;
+  for (int i = 0; i < d; ++i) {                               // forward: L z = b
+    for (int c = col0; c < d + (ncol - d % ncol) % ncol; c += ncol) {
+      T v = T(0);
+      if (c < d) for (int k = lane_in; k < i; k += TPC) v -= L[i * d + k] * X[k * d + c];
+#pragma unroll
+      for (int o = TPC / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (c < d && lane_in == 0) X[i * d + c] = (X[i * d + c] + v) * rinv[i];
     }
+    __syncthreads();
+  }
+  for (int i = d - 1; i >= 0; --i) {                          // backward: L^T x = z
+    for (int c = col0; c < d + (ncol - d % ncol) % ncol; c += ncol) {
+      T v = T(0);
+      if (c < d) for (int k = i + 1 + lane_in; k < d; k += TPC) v -= L[k * d + i] * X[k * d + c];
+#pragma unroll
+      for (int o = TPC / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (c < d && lane_in == 0) X[i * d + c] = (X[i * d + c] + v) * rinv[i];
+    }
+    __syncthreads();
+  }
+}
+
+// RTS gains, embarrassingly parallel over time: Gt[n] = solve(P_pred[n], A[n+1] Pf[n]) depends only on the FILTERED
+// moments (sde_gp.py:351-359), so a grid of CTAs computes them all before the (sequential) backward recursion.
+template <typename T>
+__global__ void __launch_bounds__(KJX_GEN_THREADS) generic_gain_kernel(const GenArgs<T> g, T* __restrict__ Gt_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmemCarver<T> sc(smem_raw);
+  const int d = g.d, dd = d * d;
+  T* Pf = sc.take(dd); T* Pp = sc.take(dd); T* Gt = sc.take(dd); T* W = sc.take(dd); T* Pinf = sc.take(dd);
+  T* vals = sc.take(4 * d); T* rinv = sc.take(d);
+  int* c0n = sc.take_int(d);
+  for (int e = threadIdx.x; e < dd; e += blockDim.x) Pinf[e] = (T)g.Pinf[e];
+  __syncthreads();
+  for (int64_t n = blockIdx.x; n < g.N; n += gridDim.x) {
+    build_rows<T>(g.disc, d, (n + 1 < g.N) ? g.dt[n + 1] : T(0), vals, c0n);        // :337, :351
+    for (int e = threadIdx.x; e < dd; e += blockDim.x) { const T v = g.filt_cov_in[n * (int64_t)dd + e]; Pf[e] = v; W[e] = v - Pinf[e]; }
+    __syncthreads();
+    rows_left<T>(d, vals, c0n, Pf, Gt);                                             // Gt <- A Pf        (:353)
+    rows_left<T>(d, vals, c0n, W, Pp);                                              // Pp <- A (Pf - Pinf)
+    __syncthreads();
+    rows_right_add<T>(d, vals, c0n, Pp, Pinf, W);                                   // W  <- P_pred       (:354)
+    __syncthreads();
+    chol_inplace<T>(d, W, rinv);                                                    // utils.py:29
+    chol_substitute<T, 4>(d, W, rinv, Gt);                                          // :359, utils.py:30
+    for (int e = threadIdx.x; e < dd; e += blockDim.x) Gt_out[n * (int64_t)dd + e] = Gt[e];
     __syncthreads();
   }
 }
 
 // backward smoother, sde_gp.py:337-379
 template <typename T>
-__global__ void __launch_bounds__(KJX_GEN_THREADS) generic_smoother_kernel(const GenArgs<T> g) {
+__global__ void __launch_bounds__(KJX_GEN_THREADS) generic_smoother_kernel(const GenArgs<T> g, const T* __restrict__ Gt_in) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemCarver<T> sc(smem_raw);
   const int d = g.d, dd = d * d;
@@ -208,28 +269,14 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_smoother_kernel(const
     for (int i = threadIdx.x; i < d; i += blockDim.x) mf[i] = g.filt_mean_in[n * d + i];
     __syncthreads();
     rows_matvec<T>(d, vals, c0n, mf, mp);                                           // :352
-    rows_left<T>(d, vals, c0n, Pf, Gt);                                             // Gt <- A Pf        (:353)
     rows_left<T>(d, vals, c0n, W, Pp);                                              // Pp <- A (Pf - Pinf)
     __syncthreads();
     rows_right_add<T>(d, vals, c0n, Pp, Pinf, W);                                   // W  <- P_pred       (:354)
     __syncthreads();
-    for (int e = threadIdx.x; e < dd; e += blockDim.x) { Pp[e] = W[e]; W[e] = Ps[e] - W[e]; }   // keep P_pred; W <- Ps - P_pred
+    for (int e = threadIdx.x; e < dd; e += blockDim.x) W[e] = Ps[e] - W[e];         // W <- Ps - P_pred
     for (int i = threadIdx.x; i < d; i += blockDim.x) dm[i] = ms[i] - mp[i];
     __syncthreads();
-    chol_inplace<T>(d, Pp, rinv);                                                   // utils.py:29
-    // Gt <- solve(P_pred, A Pf): one right-hand-side column per thread               (:359, utils.py:30)
-    for (int c = threadIdx.x; c < d; c += blockDim.x) {
-      for (int i = 0; i < d; ++i) {
-        T v = Gt[i * d + c];
-        for (int k = 0; k < i; ++k) v -= Pp[i * d + k] * Gt[k * d + c];
-        Gt[i * d + c] = v * rinv[i];
-      }
-      for (int i = d - 1; i >= 0; --i) {
-        T v = Gt[i * d + c];
-        for (int k = i + 1; k < d; ++k) v -= Pp[k * d + i] * Gt[k * d + c];
-        Gt[i * d + c] = v * rinv[i];
-      }
-    }
+    for (int e = threadIdx.x; e < dd; e += blockDim.x) Gt[e] = Gt_in[n * (int64_t)dd + e];   // gain from generic_gain_kernel
     __syncthreads();
     // m = mf + G (m - m_pred);  P = Pf + G (P - P_pred) G^T  with G = Gt^T              (:360-361)
     for (int i = threadIdx.x; i < d; i += blockDim.x) {
@@ -260,15 +307,16 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_smoother_kernel(const
       dm[j] = s;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {            // warp 0, cubature points spread over its lanes
       T pm = T(0), pv = T(0);
       for (int i = 0; i < d; ++i) { pm += Hrow[i] * ms[i]; pv += dm[i] * Hrow[i]; }
-      if (g.smooth_mean && !g.return_full) { g.smooth_mean[n] = pm; g.smooth_cov[n] = pv; }
+      if (threadIdx.x == 0 && g.smooth_mean && !g.return_full) { g.smooth_mean[n] = pm; g.smooth_cov[n] = pv; }
       if (g.update_sites) {
         T pmean, pvar;
         if (g.site_mean) { pmean = g.site_mean[n]; pvar = g.site_var[n]; } else { pmean = g.y[n]; pvar = T(g.site.lik_hyp); }
-        const SiteOut<T> o = site_update<T>(g.site, g.y[n], pm, pv, true, pmean, pvar);   // :375
-        g.new_site_mean[n] = o.mean; g.new_site_var[n] = o.var;
+        __syncwarp();                    // every lane has read the previous site before lane 0 may overwrite it in place
+        const SiteOut<T> o = site_update<T, WarpRed>(g.site, g.y[n], pm, pv, true, pmean, pvar);   // :375
+        if (threadIdx.x == 0) { g.new_site_mean[n] = o.mean; g.new_site_var[n] = o.var; }
       }
     }
     __syncthreads();

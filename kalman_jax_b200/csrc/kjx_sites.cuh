@@ -55,6 +55,39 @@ template <typename T> KJX_HD T ensure_pos1(T k) { return (k < T(0)) ? T(1e-2) : 
 
 #define KJX_PI 3.141592653589793
 
+// How the cubature sums are evaluated: by one thread (SerialRed), or spread over the 32 lanes of a warp whose lanes
+// all hold the same arguments (WarpRed: lane i evaluates sigma points i, i+32, ...; butterfly reduction, so every
+// lane ends up with the same total).  The one-chain kernels use WarpRed: the chain is sequential in time, but the
+// 20 Gauss-Hermite evaluations of a step are not.
+struct SerialRed {
+  static KJX_HD int first() { return 0; }
+  static KJX_HD int stride() { return 1; }
+  template <typename T> static KJX_HD T sum(T v) { return v; }
+};
+struct WarpRed {
+  static KJX_HD int first() {
+#ifdef __CUDA_ARCH__
+    return threadIdx.x & 31;
+#else
+    return 0;
+#endif
+  }
+  static KJX_HD int stride() {
+#ifdef __CUDA_ARCH__
+    return 32;
+#else
+    return 1;
+#endif
+  }
+  template <typename T> static KJX_HD T sum(T v) {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+#endif
+    return v;
+  }
+};
+
 // ------------------------------------------------------------------------------------------------
 // link functions (likelihoods.py:421-433, 571-576; utils.py:67-73)
 template <typename T> KJX_HD T link_fn(int lik, T f) {
@@ -162,13 +195,13 @@ template <typename T> KJX_HD void logphi(T z, T& lp, T& dlp) {
 }
 
 // likelihoods.py:122-185 (the live moment_match_cubature)
-template <typename T>
+template <typename T, class Red = SerialRed>
 KJX_HDN SiteOut<T> moment_match_cubature(const SiteModel& sm, T y, T cm, T cv, T power) {
   const LikStep<T> ls = lik_step<T>(sm, y);
   const T cho = chol1(cv);
   const T invC = inv1(cv);
   T Z = T(0), dZ = T(0), d2Z = T(0);
-  for (int i = 0; i < sm.n_cub; ++i) {
+  for (int i = Red::first(); i < sm.n_cub; i += Red::stride()) {
     const T f = cho * T(sm.cub_x[i]) + cm;                       // :147
     T l = eval_lik<T>(sm, ls, f);
     if (power != T(1)) l = pow(l, power);
@@ -178,6 +211,7 @@ KJX_HDN SiteOut<T> moment_match_cubature(const SiteModel& sm, T y, T cm, T cv, T
     dZ += invC * d * wl;                                         // :163-166
     d2Z += (invC * d * d * invC - invC) * wl;                    // :173-176
   }
+  Z = Red::sum(Z); dZ = Red::sum(dZ); d2Z = Red::sum(d2Z);
   SiteOut<T> o;
   const T Zc = max_nan(Z, T(1e-8));
   o.lml = log(Zc);                                               // :157
@@ -192,7 +226,7 @@ KJX_HDN SiteOut<T> moment_match_cubature(const SiteModel& sm, T y, T cm, T cv, T
 
 // Likelihood.moment_match dispatch: Gaussian closed form (likelihoods.py:385-404), probit closed form
 // when power == 1 (likelihoods.py:487-502), cubature otherwise.
-template <typename T>
+template <typename T, class Red = SerialRed>
 KJX_HDN SiteOut<T> moment_match(const SiteModel& sm, T y, T m, T v, T power) {
   if (sm.lik == KJX_LIK_GAUSSIAN) return gaussian_moment_match<T>(y, m, v, T(sm.lik_hyp));
   if (sm.lik == KJX_LIK_BERNOULLI_PROBIT || sm.lik == KJX_LIK_BERNOULLI_LOGIT) {
@@ -209,7 +243,7 @@ KJX_HDN SiteOut<T> moment_match(const SiteModel& sm, T y, T m, T v, T power) {
       return o;
     }
   }
-  return moment_match_cubature<T>(sm, y, m, v, power);
+  return moment_match_cubature<T, Red>(sm, y, m, v, power);
 }
 
 // approximate_inference.py:8-15
@@ -221,37 +255,40 @@ KJX_HD void compute_cavity(T pm, T pv, T smean, T svar, T power, T& cm, T& cv) {
 }
 
 // likelihoods.py:203-242
-template <typename T>
+template <typename T, class Red = SerialRed>
 KJX_HDN void slr_cubature(const SiteModel& sm, T cm, T cv, T& mu, T& S, T& C, T& omega) {
   const T cho = chol1(cv), invC = inv1(cv);
   mu = T(0);
-  for (int i = 0; i < sm.n_cub; ++i) {
+  for (int i = Red::first(); i < sm.n_cub; i += Red::stride()) {
     T E, V; cond_moments<T>(sm, cho * T(sm.cub_x[i]) + cm, E, V);
     mu += T(sm.cub_w[i]) * E;                                    // :219-221
   }
+  mu = Red::sum(mu);
   S = T(0); C = T(0); omega = T(0);
-  for (int i = 0; i < sm.n_cub; ++i) {
+  for (int i = Red::first(); i < sm.n_cub; i += Red::stride()) {
     const T f = cho * T(sm.cub_x[i]) + cm, w = T(sm.cub_w[i]);
     T E, V; cond_moments<T>(sm, f, E, V);
     S += w * ((E - mu) * (E - mu) + V);                          // :226-228
     C += w * (f - cm) * (E - mu);                                // :232-234
     omega += w * E * (invC * (f - cm));                          // :238-240
   }
+  S = Red::sum(S); C = Red::sum(C); omega = Red::sum(omega);
 }
 
 // likelihoods.py:275-321
-template <typename T>
+template <typename T, class Red = SerialRed>
 KJX_HDN void var_exp_cubature(const SiteModel& sm, T y, T pm, T pv, T& dE_dm, T& dE_dv) {
   const LikStep<T> ls = lik_step<T>(sm, y);
   const T cho = chol1(pv), invv = T(1) / pv;                     // :307 plain reciprocal
   dE_dm = T(0); dE_dv = T(0);
-  for (int i = 0; i < sm.n_cub; ++i) {
+  for (int i = Red::first(); i < sm.n_cub; i += Red::stride()) {
     const T f = cho * T(sm.cub_x[i]) + pm;
     const T wll = T(sm.cub_w[i]) * eval_loglik<T>(sm, ls, f);    // :297
     const T d = f - pm;
     dE_dm += invv * d * wll;                                     // :308-311
     dE_dv += (T(0.5) * (invv * invv * d * d) - T(0.5) * invv) * wll;   // :315-318
   }
+  dE_dm = Red::sum(dE_dm); dE_dv = Red::sum(dE_dv);
 }
 
 // natural-parameter damping shared by the rules (each passes its own jitter)
@@ -265,16 +302,16 @@ KJX_HD void damp(T nat2, T smean, T nat2_prev, T smean_prev, T damping, T jitter
 
 // ------------------------------------------------------------------------------------------------
 // ApproxInf.update: has_prev == false is the `site_params is None` branch used by the filter.
-template <typename T>
+template <typename T, class Red = SerialRed>
 KJX_HDN SiteOut<T> site_update(const SiteModel& sm, T y, T pm, T pv, bool has_prev, T sprev_mean, T sprev_var) {
   const T damping = T(sm.damping);
   SiteOut<T> o;
   switch (sm.method) {
     case KJX_INF_EP: {                                           // approximate_inference.py:50-73
-      if (!has_prev) return moment_match<T>(sm, y, pm, pv, T(1));
+      if (!has_prev) return moment_match<T, Red>(sm, y, pm, pv, T(1));
       const T power = T(sm.power);
       T cm, cv; compute_cavity<T>(pm, pv, sprev_mean, sprev_var, power, cm, cv);
-      o = moment_match<T>(sm, y, cm, cv, power);
+      o = moment_match<T, Red>(sm, y, cm, cv, power);
       if (damping != T(1))
         damp<T>(inv1(o.var), o.mean, inv1(sprev_var), sprev_mean, damping, T(0), o.mean, o.var);   // :68-72
       return o;
@@ -299,10 +336,10 @@ KJX_HDN SiteOut<T> site_update(const SiteModel& sm, T y, T pm, T pv, bool has_pr
     }
     case KJX_INF_SLEP: {                                         // approximate_inference.py:180-210
       const T power = has_prev ? T(sm.power) : T(1);
-      o.lml = moment_match<T>(sm, y, pm, pv, T(1)).lml;          // :186
+      o.lml = moment_match<T, Red>(sm, y, pm, pv, T(1)).lml;     // :186
       T cm = pm, cv = pv;
       if (has_prev && power != T(0)) compute_cavity<T>(pm, pv, sprev_mean, sprev_var, power, cm, cv);
-      T mu, S, C, omega; slr_cubature<T>(sm, cm, cv, mu, S, C, omega);     // :194
+      T mu, S, C, omega; slr_cubature<T, Red>(sm, cm, cv, mu, S, C, omega);     // :194
       const T residual = y - mu;
       const T sigma = S + (power - T(1)) * C * inv1(cv + T(1e-10)) * C;    // :197
       const T isig = inv1(sigma);
@@ -315,7 +352,7 @@ KJX_HDN SiteOut<T> site_update(const SiteModel& sm, T y, T pm, T pv, bool has_pr
       return o;
     }
     default: {                                                   // VI: approximate_inference.py:302-323
-      T dE_dm, dE_dv; var_exp_cubature<T>(sm, y, pm, pv, dE_dm, dE_dv);
+      T dE_dm, dE_dv; var_exp_cubature<T, Red>(sm, y, pm, pv, dE_dm, dE_dv);
       if (!has_prev) {
         o.var = T(0.5) * inv1(ensure_pos1(-dE_dv) + T(1e-10));   // :309
         o.mean = pm + o.var * dE_dm;                             // :310
@@ -328,17 +365,17 @@ KJX_HDN SiteOut<T> site_update(const SiteModel& sm, T y, T pm, T pv, bool has_pr
         o.var = inv1(lam2 + T(1e-10));                           // :320
         o.mean = o.var * lam1;
       }
-      o.lml = moment_match<T>(sm, y, pm, pv, T(1)).lml;          // :322
+      o.lml = moment_match<T, Red>(sm, y, pm, pv, T(1)).lml;     // :322
       return o;
     }
   }
 }
 
 // log-likelihood term of the filter (sde_gp.py:287 with site_params=None): only `lml` of update()
-template <typename T>
+template <typename T, class Red = SerialRed>
 KJX_HD T filter_loglik(const SiteModel& sm, T y, T pm, T pv) {
-  if (sm.method == KJX_INF_EEP) return site_update<T>(sm, y, pm, pv, false, T(0), T(0)).lml;
-  return moment_match<T>(sm, y, pm, pv, T(1)).lml;   // EP :57, SLEP :186, VI :322
+  if (sm.method == KJX_INF_EEP) return site_update<T, Red>(sm, y, pm, pv, false, T(0), T(0)).lml;
+  return moment_match<T, Red>(sm, y, pm, pv, T(1)).lml;   // EP :57, SLEP :186, VI :322
 }
 
 }  // namespace kjx

@@ -314,7 +314,9 @@ __global__ void __launch_bounds__(KJX_SCAN_BLOCK) smoother_blockscan_kernel(cons
 // ------------------------------------------------------------------------------------------------
 // one step of the reference filter given the predicted state in x; returns log_lik_n
 // GAUSS_EP: compile-time fast path for Gaussian likelihood + EP (closed-form moments, utils.py:219-244)
-template <typename T, int D, bool GAUSS_EP>
+// Red: SerialRed (one thread owns the step) or WarpRed (the 32 lanes of a warp run the same chain and share the
+// cubature evaluations of every step)
+template <typename T, int D, bool GAUSS_EP, class Red = SerialRed>
 __device__ __forceinline__ T filter_step_body(const SmallArgs<T, D>& a, int64_t k, FiltState<T, D>& x,
                                               bool init_sites, T& smean, T& svar) {
   const bool masked = a.mask ? (a.mask[k] != 0) : false;
@@ -323,13 +325,13 @@ __device__ __forceinline__ T filter_step_body(const SmallArgs<T, D>& a, int64_t 
   if (init_sites) {
     // sde_gp.py:287 — site from the predictive (site_params=None); masked: y := predict_mean (:286)
     const T yk = masked ? pm : a.y[k];
-    SiteOut<T> o = site_update<T>(a.site, yk, pm, pv, false, T(0), T(0));
+    SiteOut<T> o = site_update<T, Red>(a.site, yk, pm, pv, false, T(0), T(0));
     smean = o.mean; svar = o.var; lml = o.lml;
   } else {
     step_site<T, D>(a, k, smean, svar);
     // log Z is always the true likelihood under the predictive, even when stored sites do the update
     if (!masked) lml = GAUSS_EP ? gaussian_moment_match<T>(a.y[k], pm, pv, T(a.site.lik_hyp)).lml
-                                : filter_loglik<T>(a.site, a.y[k], pm, pv);
+                                : filter_loglik<T, Red>(a.site, a.y[k], pm, pv);
   }
   if (!masked) filter_update<T, D>(x, smean, svar);  // :292-296 ; masked: keep the prediction (:297-299)
   else lml = T(0);                                   // :300
@@ -441,7 +443,7 @@ __global__ void __launch_bounds__(KJX_BLOCK) smoother_reduce_kernel(const SmallA
 }
 
 // one reference RTS step at k (sde_gp.py:351-379); x = smoothed state at k+1 on entry, at k on exit
-template <typename T, int KIND, bool GAUSS_EP>
+template <typename T, int KIND, bool GAUSS_EP, class Red = SerialRed>
 __device__ __forceinline__ void smoother_step_body(const SmallArgs<T, BlockDim<KIND>::D>& a, int64_t k,
                                                    const T (&Pinf)[BlockDim<KIND>::D][BlockDim<KIND>::D],
                                                    FiltState<T, BlockDim<KIND>::D>& x) {
@@ -469,7 +471,7 @@ __device__ __forceinline__ void smoother_step_body(const SmallArgs<T, BlockDim<K
       const T damping = T(a.site.damping);
       if (damping != T(1)) damp<T>(inv1(o.var), o.mean, inv1(pvar), pmean, damping, T(0), o.mean, o.var);
     } else {
-      o = site_update<T>(a.site, a.y[k], pm, pv, true, pmean, pvar);                               // :375
+      o = site_update<T, Red>(a.site, a.y[k], pm, pv, true, pmean, pvar);                          // :375
     }
     a.new_site_mean[k] = o.mean; a.new_site_var[k] = o.var;
   }
@@ -503,7 +505,9 @@ __global__ void __launch_bounds__(KJX_BLOCK) smoother_apply_kernel(const SmallAr
 template <typename T, int KIND>
 __global__ void filter_sequential_kernel(const SmallArgs<T, BlockDim<KIND>::D> a, int init_sites) {
   constexpr int D = BlockDim<KIND>::D;
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (threadIdx.x >= 32 || blockIdx.x != 0) return;
+  // the 32 lanes run the same chain on the same values; they split the cubature of every step, lane 0 stores
+  const bool lead = threadIdx.x == 0;
   T Pinf[D][D]; load_pinf<T, D>(a.prior, Pinf);
   FiltState<T, D> x; load_state<T, D>(a.f_state_in, x);
   T nl = T(0);
@@ -512,11 +516,11 @@ __global__ void filter_sequential_kernel(const SmallArgs<T, BlockDim<KIND>::D> a
     Transition<T, KIND>::eval(a.dt[k], a.prior.lam, F);
     filter_predict<T, D>(F, Pinf, x);
     T smean, svar;
-    nl += filter_step_body<T, D, false>(a, k, x, init_sites != 0, smean, svar);
-    if (a.filt_mean) store_state<T, D>(a.filt_mean, a.filt_cov, k, x);
-    if (a.out_site_mean) { a.out_site_mean[k] = smean; a.out_site_var[k] = svar; }
+    nl += filter_step_body<T, D, false, WarpRed>(a, k, x, init_sites != 0, smean, svar);
+    if (lead && a.filt_mean) store_state<T, D>(a.filt_mean, a.filt_cov, k, x);
+    if (lead && a.out_site_mean) { a.out_site_mean[k] = smean; a.out_site_var[k] = svar; }
   }
-  if (a.nlml_out) a.nlml_out[0] = -nl;
+  if (lead && a.nlml_out) a.nlml_out[0] = -nl;
 }
 
 template <typename T, int KIND>
