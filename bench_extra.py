@@ -88,7 +88,7 @@ def c3():
     t0 = time.perf_counter(); ref.run(); cpu = (time.perf_counter() - t0) / n_cpu
     print(json.dumps({"bench": "c3_aircraft_d59", "N": N, "d": 59, "first_iteration_s": first, "s_per_iteration": sec,
                       "steps_per_s": N / sec, "numpy_oracle_steps_per_s": 1 / cpu,
-                      "note": "one CTA walks the series in reference order (generic d <= 64 path, not yet time-parallel)"}))
+                      "note": "generic d <= 64 path: CTA-level chunked scan (fold -> boundary -> filter / gains / smoother per chunk); the first iteration initialises the Poisson sites with the one-chain filter"}))
 
 
 def first_iter():

@@ -3,6 +3,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <stdlib.h>
+#include <math.h>
 #include <algorithm>
 #include <vector>
 
@@ -487,40 +488,74 @@ __global__ void fold_shards_kernel(PinfArg<D> pinf, const double* summaries, int
   if (threadIdx.x == 0) fold_shards<D>(pinf.v, summaries, stride, world, rank, state_out, info_out);
 }
 
-// ---- generic block-diagonal prior, d <= 64: one CTA walks the series in reference order ------------------
+// ---- generic block-diagonal prior, d <= 64: CTA-level chunked scan (kjx_generic_kernels.cuh) ------------------
 bool generic_ok(const kjx_model_t* m) {
   return m->func_dim == 1 && m->state_dim <= KJX_GEN_DMAX && (m->H != nullptr || m->H_steps != nullptr);
 }
+// number of chunks: the boundary kernel walks them one after another (~0.15 ms each at d = 59) while every chunk is
+// walked concurrently (~70 us per step), so about sqrt(N / 2) chunks balance the two; at most two per SM
+int generic_chunks(int64_t N) {
+  if (const char* e = getenv("KJX_GEN_CHUNKS")) { const int v = atoi(e); if (v >= 1) return (int)std::min<int64_t>(v, std::max<int64_t>(N, 1)); }
+  const int64_t p = (int64_t)(sqrt((double)N / 2.0) + 0.5);
+  return (int)std::max<int64_t>(1, std::min<int64_t>(p, 148 * 2));
+}
+constexpr int KJX_GEN_MAXCHUNKS = 148 * 2;
 template <typename T> size_t generic_ws_bytes(const kjx_model_t* m, int64_t N) {
-  const size_t d = (size_t)m->state_dim, n = (size_t)std::max<int64_t>(N, 1);
-  // Pinf, H | dense filter output (kjx_run without caller buffers) | RTS gains [N,d,d]
-  return round_up(d * d * 8, 256) + round_up(d * 8, 256) + round_up(n * d * sizeof(T), 256) + 2 * round_up(n * d * d * sizeof(T), 256);
+  const size_t d = (size_t)m->state_dim, n = (size_t)std::max<int64_t>(N, 1), P = KJX_GEN_MAXCHUNKS;
+  // Pinf, H | dense filter output (kjx_run without caller buffers) | RTS gains [N,d,d] | chunk elements, states, infos, nlml
+  return round_up(d * d * 8, 256) + round_up(d * 8, 256) + round_up(n * d * sizeof(T), 256) + 2 * round_up(n * d * d * sizeof(T), 256) +
+         round_up(P * (3 * d * d + 2 * d) * sizeof(T), 256) + 2 * round_up(P * d * sizeof(T), 256) + 2 * round_up(P * d * d * sizeof(T), 256) +
+         round_up(P * sizeof(T), 256);
 }
 template <typename T>
 int generic_setup(const kjx_model_t* m, int64_t N, void* ws, size_t ws_bytes, GenArgs<T>& g, T** scratch_mean, T** scratch_cov,
                   T** scratch_gain, cudaStream_t st) {
   if (!ws || ws_bytes < generic_ws_bytes<T>(m, N)) return KJX_ERR_WORKSPACE;
-  const size_t d = (size_t)m->state_dim;
+  const size_t d = (size_t)m->state_dim, n = (size_t)std::max<int64_t>(N, 1), P = KJX_GEN_MAXCHUNKS;
   memset(&g, 0, sizeof(g));
   g.disc.d = m->state_dim; g.disc.n_blocks = m->n_blocks;
   for (int b = 0; b < m->n_blocks; ++b) g.disc.blocks[b] = m->blocks[b];
   g.site = make_site(m); g.d = m->state_dim; g.N = N;
   char* w = (char*)ws;
-  double* pinf_dev = (double*)w; w += round_up(d * d * 8, 256);
-  double* h_dev = (double*)w; w += round_up(d * 8, 256);
-  *scratch_mean = (T*)w; w += round_up((size_t)std::max<int64_t>(N, 1) * d * sizeof(T), 256);
-  *scratch_cov = (T*)w; w += round_up((size_t)std::max<int64_t>(N, 1) * d * d * sizeof(T), 256);
-  *scratch_gain = (T*)w;
+  auto take = [&](size_t bytes) { char* r = w; w += round_up(bytes, 256); return r; };
+  double* pinf_dev = (double*)take(d * d * 8);
+  double* h_dev = (double*)take(d * 8);
+  *scratch_mean = (T*)take(n * d * sizeof(T));
+  *scratch_cov = (T*)take(n * d * d * sizeof(T));
+  *scratch_gain = (T*)take(n * d * d * sizeof(T));
+  g.sum = (T*)take(P * (3 * d * d + 2 * d) * sizeof(T));
+  g.st_m = (T*)take(P * d * sizeof(T)); g.in_eta = (T*)take(P * d * sizeof(T));
+  g.st_P = (T*)take(P * d * d * sizeof(T)); g.in_J = (T*)take(P * d * d * sizeof(T));
+  g.chunk_nlml = (T*)take(P * sizeof(T));
+  g.nchunks = 1; g.chunk_len = std::max<int64_t>(N, 1);
   KJX_CUDA_CHECK(cudaMemcpyAsync(pinf_dev, m->Pinf, d * d * 8, cudaMemcpyHostToDevice, st));
   g.Pinf = pinf_dev;
   if (m->H_steps) { g.H_steps = m->H_steps; g.H = nullptr; }
   else { KJX_CUDA_CHECK(cudaMemcpyAsync(h_dev, m->H, d * 8, cudaMemcpyHostToDevice, st)); g.H = h_dev; }
   return KJX_OK;
 }
+template <typename T> void generic_set_chunks(GenArgs<T>& g, bool chunked) {
+  g.nchunks = chunked ? generic_chunks(g.N) : 1;
+  g.chunk_len = (g.N + g.nchunks - 1) / g.nchunks;
+  g.nchunks = (int)((g.N + g.chunk_len - 1) / g.chunk_len);
+}
+// elements of all chunks (when there are several), then the state / information at every chunk boundary
+template <typename T> int generic_launch_scan(const GenArgs<T>& g, cudaStream_t st) {
+  if (g.nchunks > 1) {
+    const size_t smem = generic_fold_smem<T>(g.d);
+    KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_fold_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    generic_fold_kernel<T><<<g.nchunks, KJX_GEN_THREADS, smem, st>>>(g);
+  }
+  const size_t smem = generic_boundary_smem<T>(g.d);
+  KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_boundary_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  generic_boundary_kernel<T><<<2, KJX_GEN_THREADS, smem, st>>>(g);
+  return KJX_OK;
+}
 template <typename T> int generic_launch_filter(const GenArgs<T>& g, cudaStream_t st) {
   const size_t smem = generic_filter_smem<T>(g.d);
   KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_filter_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  generic_filter_kernel<T><<<1, KJX_GEN_THREADS, smem, st>>>(g);
+  generic_filter_kernel<T><<<g.nchunks, KJX_GEN_THREADS, smem, st>>>(g);
+  if (g.nlml) nlml_reduce_kernel<T><<<1, 256, 0, st>>>(g.chunk_nlml, g.nchunks, g.nlml);
   return KJX_OK;
 }
 template <typename T> int generic_launch_smoother(const GenArgs<T>& g, T* gains, cudaStream_t st) {
@@ -529,16 +564,16 @@ template <typename T> int generic_launch_smoother(const GenArgs<T>& g, T* gains,
   KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_gain_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned grid = (unsigned)std::min<int64_t>(g.N, 148 * 4);
   generic_gain_kernel<T><<<grid, KJX_GEN_THREADS, smem, st>>>(g, gains);
-  // 2. the backward recursion itself (two d^3 products per step), one CTA in reference order
+  // 2. the backward recursion (two d^3 products per step), every chunk concurrently, reference order inside a chunk
   KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_smoother_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  generic_smoother_kernel<T><<<1, KJX_GEN_THREADS, smem, st>>>(g, gains);
+  generic_smoother_kernel<T><<<g.nchunks, KJX_GEN_THREADS, smem, st>>>(g, gains);
   return KJX_OK;
 }
 
 template <typename T>
 int generic_filter(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const uint8_t* mask, const T* site_mean,
                    const T* site_var, T* filt_mean, T* filt_cov, T* out_site_mean, T* out_site_var, T* nlml, void* ws,
-                   size_t ws_bytes, cudaStream_t st) {
+                   size_t ws_bytes, uint32_t flags, cudaStream_t st) {
   GenArgs<T> g; T *sm, *sc, *sg;
   int rc = generic_setup<T>(m, N, ws, ws_bytes, g, &sm, &sc, &sg, st);
   if (rc != KJX_OK) return rc;
@@ -546,8 +581,9 @@ int generic_filter(const kjx_model_t* m, int64_t N, const T* dt, const T* y, con
   g.dt = dt; g.y = y; g.mask = mask; g.site_mean = site_mean; g.site_var = site_var;
   g.init_sites = (site_mean == nullptr && !gauss_ep(m)) ? 1 : 0;
   g.filt_mean = filt_mean; g.filt_cov = filt_cov; g.out_site_mean = out_site_mean; g.out_site_var = out_site_var; g.nlml = nlml;
-  rc = generic_launch_filter<T>(g, st);
-  if (rc != KJX_OK) return rc;
+  generic_set_chunks<T>(g, !g.init_sites && !(flags & KJX_FLAG_SEQUENTIAL));
+  if ((rc = generic_launch_scan<T>(g, st)) != KJX_OK) return rc;
+  if ((rc = generic_launch_filter<T>(g, st)) != KJX_OK) return rc;
   KJX_CUDA_CHECK(cudaGetLastError());
   return KJX_OK;
 }
@@ -564,8 +600,11 @@ int generic_smoother(const kjx_model_t* m, int64_t N, const T* dt, const T* filt
   g.smooth_mean = smooth_mean; g.smooth_cov = smooth_cov; g.new_site_mean = new_site_mean; g.new_site_var = new_site_var;
   g.return_full = (flags & KJX_FLAG_RETURN_FULL) ? 1 : 0;
   g.update_sites = (new_site_mean != nullptr && site_mean != nullptr && y != nullptr) ? 1 : 0;
-  rc = generic_launch_smoother<T>(g, sg, st);
-  if (rc != KJX_OK) return rc;
+  // the stand-alone smoother only sees filtered moments (which mask / sites produced them is unknown here), so it
+  // cannot rebuild the filter elements: one chunk, gains still computed in parallel
+  generic_set_chunks<T>(g, false);
+  if ((rc = generic_launch_scan<T>(g, st)) != KJX_OK) return rc;
+  if ((rc = generic_launch_smoother<T>(g, sg, st)) != KJX_OK) return rc;
   KJX_CUDA_CHECK(cudaGetLastError());
   return KJX_OK;
 }
@@ -582,14 +621,20 @@ int generic_run(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const 
   g.init_sites = (site_mean == nullptr && !gauss_ep(m)) ? 1 : 0;
   g.filt_mean = filt_mean; g.filt_cov = filt_cov; g.nlml = nlml;
   if (g.init_sites) { g.out_site_mean = new_site_mean; g.out_site_var = new_site_var; }   // sde_gp.py:183
-  rc = generic_launch_filter<T>(g, st);
-  if (rc != KJX_OK) return rc;
-  if (g.init_sites) { g.site_mean = new_site_mean; g.site_var = new_site_var; g.out_site_mean = nullptr; g.out_site_var = nullptr; }
+  generic_set_chunks<T>(g, !g.init_sites && !(flags & KJX_FLAG_SEQUENTIAL));
+  if ((rc = generic_launch_scan<T>(g, st)) != KJX_OK) return rc;
+  if ((rc = generic_launch_filter<T>(g, st)) != KJX_OK) return rc;
+  if (g.init_sites) {
+    // sites were just initialised by the one-chain filter: rebuild the scan elements from them so the smoother can
+    // run chunk-parallel too (the filter elements only depend on dt and the sites)
+    g.site_mean = new_site_mean; g.site_var = new_site_var; g.out_site_mean = nullptr; g.out_site_var = nullptr; g.init_sites = 0;
+    generic_set_chunks<T>(g, !(flags & KJX_FLAG_SEQUENTIAL));
+    if ((rc = generic_launch_scan<T>(g, st)) != KJX_OK) return rc;
+  }
   g.filt_mean_in = filt_mean; g.filt_cov_in = filt_cov;
   g.smooth_mean = post_mean; g.smooth_cov = post_var; g.new_site_mean = new_site_mean; g.new_site_var = new_site_var;
   g.return_full = 0; g.update_sites = (flags & KJX_FLAG_NO_SITE_UPDATE) ? 0 : 1;
-  rc = generic_launch_smoother<T>(g, sg, st);
-  if (rc != KJX_OK) return rc;
+  if ((rc = generic_launch_smoother<T>(g, sg, st)) != KJX_OK) return rc;
   KJX_CUDA_CHECK(cudaGetLastError());
   return KJX_OK;
 }
@@ -609,7 +654,7 @@ int filter_T(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const uin
     case KJX_BLOCK_MATERN52: return small_filter<T, KJX_BLOCK_MATERN52>(m, N, dt, y, mask, site_mean, site_cov, filt_mean, filt_cov, out_site_mean, out_site_cov, nlml, ws, ws_bytes, flags, st);
     default:
       if (!generic_ok(m)) return KJX_ERR_UNSUPPORTED;
-      return generic_filter<T>(m, N, dt, y, mask, site_mean, site_cov, filt_mean, filt_cov, out_site_mean, out_site_cov, nlml, ws, ws_bytes, st);
+      return generic_filter<T>(m, N, dt, y, mask, site_mean, site_cov, filt_mean, filt_cov, out_site_mean, out_site_cov, nlml, ws, ws_bytes, flags, st);
   }
 }
 

@@ -9,8 +9,13 @@
 //   * the update is rank one (f = 1): K = P H^T / S, P -= K (H P);
 //   * the RTS gain is the reference's Cholesky solve (utils.py:25-30): right-looking factorisation in place,
 //     then forward/backward substitution with one thread per right-hand side.
-// This is the first correct CUDA path for d > 3 (the chunked parallel-in-time scan of the small-d path and a
-// multi-CTA tiled path for d > 64 are the next step).
+// Parallel in time like the d <= 3 path, at CTA granularity: the series is cut into chunks of consecutive steps, one
+// CTA per chunk.  generic_fold_kernel reduces every chunk to a filter scan element (A,b,C,eta,J) — O(d^2) per step
+// because A(dt) is block-sparse and the update is rank one —, generic_boundary_kernel turns the elements into the
+// filtered state entering every chunk and the information (eta, J) of everything after it (two CTAs: prefix, suffix),
+// and then the filter / smoother kernels below run all chunks concurrently, each in reference order inside its
+// chunk.  With one chunk (short series, or sites that must be initialised from the predictive) it is the plain
+// sequential walk.  A multi-CTA tiled path for d > 64 is the next step, see DESIGN.md.
 #pragma once
 #include <stdint.h>
 #include "kjx_elementwise_kernels.cuh"
@@ -35,6 +40,12 @@ template <typename T> struct GenArgs {
   const T* filt_mean_in; const T* filt_cov_in;
   T* smooth_mean; T* smooth_cov; T* new_site_mean; T* new_site_var;
   int return_full; int update_sites;
+  // chunked scan (one CTA per chunk)
+  int64_t chunk_len; int nchunks;
+  T* sum;                  // [nchunks][3 d^2 + 2 d]  chunk elements: A | C | J | b | eta
+  T* st_m; T* st_P;        // [nchunks][d], [nchunks][d^2]  filtered state entering every chunk
+  T* in_eta; T* in_J;      // [nchunks][d], [nchunks][d^2]  information of everything after every chunk
+  T* chunk_nlml;           // [nchunks]
 };
 
 // rows of A(dt) for all d rows: vals[d][4], c0n[d] = first column | nnz << 24
@@ -93,7 +104,243 @@ template <typename T> size_t generic_filter_smem(int d) {
   return (size_t)(3 * d * d + 4 * d + 5 * d + 16) * sizeof(T) + (size_t)d * sizeof(int) + 16 * 12;
 }
 template <typename T> size_t generic_smoother_smem(int d) {
-  return (size_t)(6 * d * d + 4 * d + 6 * d + 16) * sizeof(T) + (size_t)d * sizeof(int) + 16 * 14;
+  return (size_t)(6 * d * d + 4 * d + 7 * d + 16) * sizeof(T) + (size_t)(d + 4) * sizeof(int) + 16 * 16;
+}
+
+// ------------------------------------------------------------------------------------------------
+// dense d x d products shared by the scan kernels (operands in shared or global memory)
+template <typename T> __device__ __forceinline__ void mm_nn(int d, const T* A, const T* B, T* C) {        // C = A B
+  for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
+    const int i = e / d, j = e % d;
+    T s = T(0);
+    for (int k = 0; k < d; ++k) s += A[i * d + k] * B[k * d + j];
+    C[e] = s;
+  }
+}
+template <typename T> __device__ __forceinline__ void mm_nt_add(int d, const T* A, const T* B, const T* S, T* C) {   // C = A B^T + S
+  for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
+    const int i = e / d, j = e % d;
+    T s = S[e];
+    for (int k = 0; k < d; ++k) s += A[i * d + k] * B[j * d + k];
+    C[e] = s;
+  }
+}
+template <typename T> __device__ __forceinline__ void mm_tn_add(int d, const T* A, const T* B, const T* S, T* C) {   // C = A^T B + S
+  for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
+    const int i = e / d, j = e % d;
+    T s = S[e];
+    for (int k = 0; k < d; ++k) s += A[k * d + i] * B[k * d + j];
+    C[e] = s;
+  }
+}
+
+// Solve M X = R in place by Gaussian elimination with partial pivoting (M: d x d, destroyed; R: d x nr, leading
+// dimension ldr, overwritten by X).  Used on I + P J / I + J C, whose eigenvalues are real and >= 1 but which are not
+// symmetric, so no Cholesky.  `piv` is one int of shared memory.
+template <typename T> __device__ void lu_solve(int d, T* M, T* R, int nr, int ldr, int* piv) {
+  for (int k = 0; k < d; ++k) {
+    if (threadIdx.x < 32) {
+      T best = T(-1); int bi = k;
+      for (int i = k + (int)threadIdx.x; i < d; i += 32) { const T v = fabs(M[i * d + k]); if (v > best) { best = v; bi = i; } }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const T ob = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      if (threadIdx.x == 0) *piv = bi;
+    }
+    __syncthreads();
+    const int p = *piv;
+    if (p != k) {
+      for (int j = threadIdx.x; j < d + nr; j += blockDim.x) {
+        T* a = (j < d) ? &M[k * d + j] : &R[k * ldr + (j - d)];
+        T* b = (j < d) ? &M[p * d + j] : &R[p * ldr + (j - d)];
+        const T t = *a; *a = *b; *b = t;
+      }
+    }
+    __syncthreads();
+    const T pinv = T(1) / M[k * d + k];
+    for (int i = k + 1 + threadIdx.x; i < d; i += blockDim.x) M[i * d + k] *= pinv;
+    __syncthreads();
+    const int rem = d - k - 1, wid = rem + nr;
+    for (int e = threadIdx.x; e < rem * wid; e += blockDim.x) {
+      const int i = k + 1 + e / wid, jj = e % wid;
+      const T l = M[i * d + k];
+      if (jj < rem) M[i * d + k + 1 + jj] -= l * M[k * d + k + 1 + jj];
+      else R[i * ldr + (jj - rem)] -= l * R[k * ldr + (jj - rem)];
+    }
+    __syncthreads();
+  }
+  for (int i = d - 1; i >= 0; --i) {
+    const T dinv = T(1) / M[i * d + i];
+    for (int c = threadIdx.x; c < nr; c += blockDim.x) {
+      T v = R[i * ldr + c];
+      for (int k = i + 1; k < d; ++k) v -= M[i * d + k] * R[k * ldr + c];
+      R[i * ldr + c] = v * dinv;
+    }
+    __syncthreads();
+  }
+}
+
+// (m, P) <- smoothed / propagated through the information (eta, J):  X = (I + P J)^-1 [P | m + P eta]
+// on return R (d x (d+1), ld d+1) holds [(I+PJ)^-1 P | (I+PJ)^-1 (m + P eta)].   M, R: scratch (d^2, d^2 + d)
+template <typename T>
+__device__ void info_solve(int d, const T* P, const T* m, const T* J, const T* eta, T* M, T* R, int* piv) {
+  const int ld = d + 1;
+  for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
+    const int i = e / d, j = e % d;
+    T s = (i == j) ? T(1) : T(0);
+    for (int k = 0; k < d; ++k) s += P[i * d + k] * J[k * d + j];
+    M[e] = s;
+    R[i * ld + j] = P[e];
+  }
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    T s = m[i];
+    for (int k = 0; k < d; ++k) s += P[i * d + k] * eta[k];
+    R[i * ld + d] = s;
+  }
+  __syncthreads();
+  lu_solve<T>(d, M, R, d + 1, ld, piv);
+}
+
+template <typename T> size_t generic_fold_smem(int d) {
+  return (size_t)(5 * d * d + 4 * d + 8 * d + 16) * sizeof(T) + (size_t)d * sizeof(int) + 16 * 16;
+}
+template <typename T> size_t generic_boundary_smem(int d) {
+  return (size_t)(4 * d * d + 4 * d + 16) * sizeof(T) + 64 + 16 * 8;
+}
+
+// fold: one CTA per chunk reduces its steps to the scan element (A, b, C, eta, J) of SURVEY.md 7.3
+template <typename T>
+__global__ void __launch_bounds__(KJX_GEN_THREADS) generic_fold_kernel(const GenArgs<T> g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmemCarver<T> sc(smem_raw);
+  const int d = g.d, dd = d * d;
+  T* A = sc.take(dd); T* C = sc.take(dd); T* J = sc.take(dd); T* X = sc.take(dd); T* Pinf = sc.take(dd);
+  T* vals = sc.take(4 * d); T* b = sc.take(d); T* eta = sc.take(d); T* t1 = sc.take(d); T* Hrow = sc.take(d);
+  T* av = sc.take(d); T* cv = sc.take(d); T* Kv = sc.take(d); T* sh = sc.take(16);
+  int* c0n = sc.take_int(d);
+  const int64_t n0 = (int64_t)blockIdx.x * g.chunk_len, n1 = (n0 + g.chunk_len < g.N) ? n0 + g.chunk_len : g.N;
+  for (int e = threadIdx.x; e < dd; e += blockDim.x) { Pinf[e] = (T)g.Pinf[e]; A[e] = (e / d == e % d) ? T(1) : T(0); C[e] = T(0); J[e] = T(0); }
+  for (int i = threadIdx.x; i < d; i += blockDim.x) { b[i] = T(0); eta[i] = T(0); if (g.H) Hrow[i] = (T)g.H[i]; }
+  __syncthreads();
+  for (int64_t n = n0; n < n1; ++n) {
+    build_rows<T>(g.disc, d, g.dt[n], vals, c0n);
+    if (g.H_steps) for (int i = threadIdx.x; i < d; i += blockDim.x) Hrow[i] = (T)g.H_steps[n * d + i];
+    __syncthreads();
+    rows_left<T>(d, vals, c0n, A, X);                       // X <- F A
+    rows_matvec<T>(d, vals, c0n, b, t1);                    // t1 <- F b
+    __syncthreads();
+    for (int e = threadIdx.x; e < dd; e += blockDim.x) { A[e] = X[e]; X[e] = C[e] - Pinf[e]; }
+    for (int i = threadIdx.x; i < d; i += blockDim.x) b[i] = t1[i];
+    __syncthreads();
+    rows_left<T>(d, vals, c0n, X, C);                       // C <- F (C - Pinf)
+    __syncthreads();
+    rows_right_add<T>(d, vals, c0n, C, Pinf, X);            // X <- F (C - Pinf) F^T + Pinf
+    __syncthreads();
+    const bool masked = g.mask ? (g.mask[n] != 0) : false;
+    if (!masked) {
+      for (int j = threadIdx.x; j < d; j += blockDim.x) {   // a = A^T h, c = C' h
+        T sa = T(0), scv = T(0);
+        for (int i = 0; i < d; ++i) { sa += Hrow[i] * A[i * d + j]; scv += X[j * d + i] * Hrow[i]; }
+        av[j] = sa; cv[j] = scv;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        T beta = T(0), sv = T(0);
+        for (int i = 0; i < d; ++i) { beta += Hrow[i] * b[i]; sv += Hrow[i] * cv[i]; }
+        T yt, R;
+        if (g.site_mean) { yt = g.site_mean[n]; R = g.site_var[n]; } else { yt = g.y[n]; R = T(g.site.lik_hyp); }
+        sh[0] = inv1(sv + R); sh[1] = yt - beta;
+      }
+      __syncthreads();
+      const T sinv = sh[0], res = sh[1];
+      for (int i = threadIdx.x; i < d; i += blockDim.x) { Kv[i] = cv[i] * sinv; eta[i] += av[i] * (res * sinv); b[i] += cv[i] * sinv * res; }
+      __syncthreads();
+      for (int e = threadIdx.x; e < dd; e += blockDim.x) {
+        const int i = e / d, j = e % d;
+        J[e] += av[i] * av[j] * sinv;
+        A[e] -= Kv[i] * av[j];
+        C[e] = X[e] - Kv[i] * cv[j];
+      }
+    } else {
+      for (int e = threadIdx.x; e < dd; e += blockDim.x) C[e] = X[e];
+    }
+    __syncthreads();
+  }
+  T* out = g.sum + (size_t)blockIdx.x * (3 * dd + 2 * d);
+  for (int e = threadIdx.x; e < dd; e += blockDim.x) { out[e] = A[e]; out[dd + e] = C[e]; out[2 * dd + e] = J[e]; }
+  for (int i = threadIdx.x; i < d; i += blockDim.x) { out[3 * dd + i] = b[i]; out[3 * dd + d + i] = eta[i]; }
+}
+
+// boundary: block 0 walks the chunk elements forwards (filtered state entering every chunk), block 1 backwards
+// (information of everything after every chunk).  nchunks is a few hundred at most.
+template <typename T>
+__global__ void __launch_bounds__(KJX_GEN_THREADS) generic_boundary_kernel(const GenArgs<T> g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmemCarver<T> sc(smem_raw);
+  const int d = g.d, dd = d * d, ld = d + 1;
+  T* P = sc.take(dd); T* M = sc.take(dd); T* R = sc.take(dd + d); T* Tm = sc.take(dd);
+  T* m = sc.take(d); T* u = sc.take(d); T* w = sc.take(d);
+  int* piv = sc.take_int(4);
+  const size_t ssz = (size_t)3 * dd + 2 * d;
+  if (blockIdx.x == 0) {
+    for (int e = threadIdx.x; e < dd; e += blockDim.x) P[e] = (T)g.Pinf[e];          // sde_gp.py:265
+    for (int i = threadIdx.x; i < d; i += blockDim.x) m[i] = T(0);
+    __syncthreads();
+    for (int c = 0; c < g.nchunks; ++c) {
+      for (int e = threadIdx.x; e < dd; e += blockDim.x) g.st_P[(size_t)c * dd + e] = P[e];
+      for (int i = threadIdx.x; i < d; i += blockDim.x) g.st_m[(size_t)c * d + i] = m[i];
+      if (c + 1 == g.nchunks) break;
+      const T* A = g.sum + c * ssz; const T* C = A + dd; const T* J = A + 2 * dd; const T* b = A + 3 * dd; const T* eta = b + d;
+      info_solve<T>(d, P, m, J, eta, M, R, piv);            // R = [(I+PJ)^-1 P | (I+PJ)^-1 (m + P eta)]
+      for (int e = threadIdx.x; e < dd; e += blockDim.x) M[e] = R[(e / d) * ld + e % d];
+      for (int i = threadIdx.x; i < d; i += blockDim.x) u[i] = R[i * ld + d];
+      __syncthreads();
+      mm_nn<T>(d, A, M, Tm);                                // Tm = A X
+      for (int i = threadIdx.x; i < d; i += blockDim.x) { T s = b[i]; for (int k = 0; k < d; ++k) s += A[i * d + k] * u[k]; m[i] = s; }
+      __syncthreads();
+      mm_nt_add<T>(d, Tm, A, C, P);                         // P' = A X A^T + C
+      __syncthreads();
+    }
+  } else {
+    // information (eta, J): J in P, eta in m
+    for (int e = threadIdx.x; e < dd; e += blockDim.x) P[e] = T(0);
+    for (int i = threadIdx.x; i < d; i += blockDim.x) m[i] = T(0);
+    __syncthreads();
+    for (int c = g.nchunks - 1; c >= 0; --c) {
+      for (int e = threadIdx.x; e < dd; e += blockDim.x) g.in_J[(size_t)c * dd + e] = P[e];
+      for (int i = threadIdx.x; i < d; i += blockDim.x) g.in_eta[(size_t)c * d + i] = m[i];
+      if (c == 0) break;
+      const T* A = g.sum + c * ssz; const T* C = A + dd; const T* Ji = A + 2 * dd; const T* b = A + 3 * dd; const T* etai = b + d;
+      // (I + J_j C_i)^T = I + C_i J_j.  Solve (I + J_j C_i) Y = [J_j A_i | eta_j - J_j b_i]
+      for (int e = threadIdx.x; e < dd; e += blockDim.x) {
+        const int i = e / d, j = e % d;
+        T s = (i == j) ? T(1) : T(0), r = T(0);
+        for (int k = 0; k < d; ++k) { s += P[i * d + k] * C[k * d + j]; r += P[i * d + k] * A[k * d + j]; }
+        M[e] = s; R[i * ld + j] = r;
+      }
+      for (int i = threadIdx.x; i < d; i += blockDim.x) {
+        T s = m[i];
+        for (int k = 0; k < d; ++k) s -= P[i * d + k] * b[k];
+        R[i * ld + d] = s;
+      }
+      __syncthreads();
+      lu_solve<T>(d, M, R, d + 1, ld, piv);
+      for (int e = threadIdx.x; e < dd; e += blockDim.x) M[e] = R[(e / d) * ld + e % d];
+      for (int i = threadIdx.x; i < d; i += blockDim.x) u[i] = R[i * ld + d];
+      __syncthreads();
+      mm_tn_add<T>(d, A, M, Ji, P);                         // J' = A_i^T Y + J_i
+      for (int i = threadIdx.x; i < d; i += blockDim.x) { T s = etai[i]; for (int k = 0; k < d; ++k) s += A[k * d + i] * u[k]; w[i] = s; }
+      __syncthreads();
+      for (int i = threadIdx.x; i < d; i += blockDim.x) m[i] = w[i];
+      // keep J' exactly symmetric
+      for (int e = threadIdx.x; e < dd; e += blockDim.x) { const int i = e / d, j = e % d; if (i < j) { const T v = T(0.5) * (P[e] + P[j * d + i]); Tm[e] = v; Tm[j * d + i] = v; } else if (i == j) Tm[e] = P[e]; }
+      __syncthreads();
+      for (int e = threadIdx.x; e < dd; e += blockDim.x) P[e] = Tm[e];
+      __syncthreads();
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -107,11 +354,13 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_filter_kernel(const G
   T* vals = sc.take(4 * d); T* m = sc.take(d); T* mp = sc.take(d); T* Hrow = sc.take(d); T* HP = sc.take(d); T* K = sc.take(d);
   T* sh = sc.take(16);                 // scalars: 0 pm, 1 pv, 2 site_mean, 3 site_var, 4 Sinv, 5 masked, 6 nlml
   int* c0n = sc.take_int(d);
-  for (int e = threadIdx.x; e < dd; e += blockDim.x) { Pinf[e] = (T)g.Pinf[e]; P[e] = (T)g.Pinf[e]; }   // sde_gp.py:265
-  for (int i = threadIdx.x; i < d; i += blockDim.x) { m[i] = T(0); if (g.H) Hrow[i] = (T)g.H[i]; }
+  // this CTA's chunk and the filtered state entering it (chunk 0: the prior, sde_gp.py:265)
+  const int64_t n0 = (int64_t)blockIdx.x * g.chunk_len, n1 = (n0 + g.chunk_len < g.N) ? n0 + g.chunk_len : g.N;
+  for (int e = threadIdx.x; e < dd; e += blockDim.x) { Pinf[e] = (T)g.Pinf[e]; P[e] = g.st_P[(size_t)blockIdx.x * dd + e]; }
+  for (int i = threadIdx.x; i < d; i += blockDim.x) { m[i] = g.st_m[(size_t)blockIdx.x * d + i]; if (g.H) Hrow[i] = (T)g.H[i]; }
   if (threadIdx.x == 0) sh[6] = T(0);
   __syncthreads();
-  for (int64_t n = 0; n < g.N; ++n) {
+  for (int64_t n = n0; n < n1; ++n) {
     build_rows<T>(g.disc, d, g.dt[n], vals, c0n);                                   // :276
     if (g.H_steps) for (int i = threadIdx.x; i < d; i += blockDim.x) Hrow[i] = (T)g.H_steps[n * d + i];   // :282
     for (int e = threadIdx.x; e < dd; e += blockDim.x) X[e] = P[e] - Pinf[e];
@@ -164,7 +413,7 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_filter_kernel(const G
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0 && g.nlml) g.nlml[0] = -sh[6];
+  if (threadIdx.x == 0) g.chunk_nlml[blockIdx.x] = sh[6];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -255,14 +504,35 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_smoother_kernel(const
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemCarver<T> sc(smem_raw);
   const int d = g.d, dd = d * d;
-  T* Pf = sc.take(dd); T* Pp = sc.take(dd); T* Gt = sc.take(dd); T* Ps = sc.take(dd); T* W = sc.take(dd); T* Pinf = sc.take(dd);
+  T* Pf = sc.take(dd); T* Pp = sc.take(dd + d); T* Gt = sc.take(dd); T* Ps = sc.take(dd); T* W = sc.take(dd); T* Pinf = sc.take(dd);
   T* vals = sc.take(4 * d); T* mf = sc.take(d); T* mp = sc.take(d); T* ms = sc.take(d); T* dm = sc.take(d); T* Hrow = sc.take(d);
   T* rinv = sc.take(d); T* sh = sc.take(16);
   int* c0n = sc.take_int(d);
-  for (int e = threadIdx.x; e < dd; e += blockDim.x) { Pinf[e] = (T)g.Pinf[e]; Ps[e] = g.filt_cov_in[(g.N - 1) * (int64_t)dd + e]; }   // :339
-  for (int i = threadIdx.x; i < d; i += blockDim.x) { ms[i] = g.filt_mean_in[(g.N - 1) * d + i]; if (g.H) Hrow[i] = (T)g.H[i]; }
+  int* piv = sc.take_int(4);
+  const int64_t n0 = (int64_t)blockIdx.x * g.chunk_len, n1 = (n0 + g.chunk_len < g.N) ? n0 + g.chunk_len : g.N;
+  for (int e = threadIdx.x; e < dd; e += blockDim.x) Pinf[e] = (T)g.Pinf[e];
+  for (int i = threadIdx.x; i < d; i += blockDim.x) if (g.H) Hrow[i] = (T)g.H[i];
   __syncthreads();
-  for (int64_t n = g.N - 1; n >= 0; --n) {
+  for (int64_t n = n1 - 1; n >= n0; --n) {
+    if (n == n1 - 1) {
+      // Last step of the chunk: smoothed = filtered x information of everything after the chunk (two-filter identity;
+      // for the chunk that ends the series the information is zero and this is sde_gp.py:339).  Pp/W are scratch here.
+      if (g.H_steps) for (int i = threadIdx.x; i < d; i += blockDim.x) Hrow[i] = (T)g.H_steps[n * d + i];
+      for (int e = threadIdx.x; e < dd; e += blockDim.x) Pf[e] = g.filt_cov_in[n * (int64_t)dd + e];
+      for (int i = threadIdx.x; i < d; i += blockDim.x) mf[i] = g.filt_mean_in[n * d + i];
+      __syncthreads();
+      info_solve<T>(d, Pf, mf, g.in_J + (size_t)blockIdx.x * dd, g.in_eta + (size_t)blockIdx.x * d, W, Pp, piv);
+      for (int e = threadIdx.x; e < dd; e += blockDim.x) {
+        const int i = e / d, j = e % d;
+        Ps[e] = (i <= j) ? Pp[i * (d + 1) + j] : Pp[j * (d + 1) + i];          // symmetric by construction; take the upper part
+        if (g.smooth_mean && g.return_full) g.smooth_cov[n * (int64_t)dd + e] = Ps[e];
+      }
+      for (int i = threadIdx.x; i < d; i += blockDim.x) {
+        ms[i] = Pp[i * (d + 1) + d];
+        if (g.smooth_mean && g.return_full) g.smooth_mean[n * d + i] = ms[i];
+      }
+      __syncthreads();
+    } else {
     build_rows<T>(g.disc, d, (n + 1 < g.N) ? g.dt[n + 1] : T(0), vals, c0n);        // :337, :351
     if (g.H_steps) for (int i = threadIdx.x; i < d; i += blockDim.x) Hrow[i] = (T)g.H_steps[n * d + i];
     for (int e = threadIdx.x; e < dd; e += blockDim.x) { const T v = g.filt_cov_in[n * (int64_t)dd + e]; Pf[e] = v; W[e] = v - Pinf[e]; }
@@ -300,6 +570,7 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_smoother_kernel(const
     }
     if (g.smooth_mean && g.return_full) for (int i = threadIdx.x; i < d; i += blockDim.x) g.smooth_mean[n * d + i] = ms[i];
     __syncthreads();
+    }  // recursion step
     // marginal of the function value: H m, H P H^T                                      (:368-369, :373)
     for (int j = threadIdx.x; j < d; j += blockDim.x) {
       T s = T(0);
