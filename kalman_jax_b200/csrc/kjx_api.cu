@@ -490,7 +490,7 @@ __global__ void fold_shards_kernel(PinfArg<D> pinf, const double* summaries, int
 
 // ---- generic block-diagonal prior, d <= 64: CTA-level chunked scan (kjx_generic_kernels.cuh) ------------------
 bool generic_ok(const kjx_model_t* m) {
-  return m->func_dim == 1 && m->state_dim <= KJX_GEN_DMAX && (m->H != nullptr || m->H_steps != nullptr);
+  return m->func_dim == 1 && m->state_dim <= KJX_GEN_DMAX_GLOBAL && (m->H != nullptr || m->H_steps != nullptr);
 }
 // number of chunks: the boundary kernel walks them one after another (~0.15 ms each at d = 59) while every chunk is
 // walked concurrently (~70 us per step), so about sqrt(N / 2) chunks balance the two; at most two per SM
@@ -500,12 +500,20 @@ int generic_chunks(int64_t N) {
   return (int)std::max<int64_t>(1, std::min<int64_t>(p, 148 * 2));
 }
 constexpr int KJX_GEN_MAXCHUNKS = 148 * 2;
+constexpr int KJX_GEN_GAIN_GRID = 148 * 4;
+// per-CTA working set when it lives in global memory (d > KJX_GEN_DMAX): the largest of the kernels' carve-ups
+template <typename T> size_t generic_scratch_bytes(int d) {
+  if (d <= KJX_GEN_DMAX) return 0;
+  return round_up(std::max(std::max(generic_smoother_smem<T>(d), generic_fold_smem<T>(d)),
+                           std::max(generic_filter_smem<T>(d), generic_boundary_smem<T>(d))), 256);
+}
 template <typename T> size_t generic_ws_bytes(const kjx_model_t* m, int64_t N) {
   const size_t d = (size_t)m->state_dim, n = (size_t)std::max<int64_t>(N, 1), P = KJX_GEN_MAXCHUNKS;
+  const size_t scratch = generic_scratch_bytes<T>(m->state_dim) * KJX_GEN_GAIN_GRID;
   // Pinf, H | dense filter output (kjx_run without caller buffers) | RTS gains [N,d,d] | chunk elements, states, infos, nlml
   return round_up(d * d * 8, 256) + round_up(d * 8, 256) + round_up(n * d * sizeof(T), 256) + 2 * round_up(n * d * d * sizeof(T), 256) +
          round_up(P * (3 * d * d + 2 * d) * sizeof(T), 256) + 2 * round_up(P * d * sizeof(T), 256) + 2 * round_up(P * d * d * sizeof(T), 256) +
-         round_up(P * sizeof(T), 256);
+         round_up(P * sizeof(T), 256) + scratch;
 }
 template <typename T>
 int generic_setup(const kjx_model_t* m, int64_t N, void* ws, size_t ws_bytes, GenArgs<T>& g, T** scratch_mean, T** scratch_cov,
@@ -527,6 +535,8 @@ int generic_setup(const kjx_model_t* m, int64_t N, void* ws, size_t ws_bytes, Ge
   g.st_m = (T*)take(P * d * sizeof(T)); g.in_eta = (T*)take(P * d * sizeof(T));
   g.st_P = (T*)take(P * d * d * sizeof(T)); g.in_J = (T*)take(P * d * d * sizeof(T));
   g.chunk_nlml = (T*)take(P * sizeof(T));
+  g.gscratch_stride = generic_scratch_bytes<T>(m->state_dim);
+  g.gscratch = g.gscratch_stride ? (unsigned char*)take(g.gscratch_stride * KJX_GEN_GAIN_GRID) : nullptr;
   g.nchunks = 1; g.chunk_len = std::max<int64_t>(N, 1);
   KJX_CUDA_CHECK(cudaMemcpyAsync(pinf_dev, m->Pinf, d * d * 8, cudaMemcpyHostToDevice, st));
   g.Pinf = pinf_dev;
@@ -542,27 +552,27 @@ template <typename T> void generic_set_chunks(GenArgs<T>& g, bool chunked) {
 // elements of all chunks (when there are several), then the state / information at every chunk boundary
 template <typename T> int generic_launch_scan(const GenArgs<T>& g, cudaStream_t st) {
   if (g.nchunks > 1) {
-    const size_t smem = generic_fold_smem<T>(g.d);
+    const size_t smem = g.gscratch ? 0 : generic_fold_smem<T>(g.d);
     KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_fold_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     generic_fold_kernel<T><<<g.nchunks, KJX_GEN_THREADS, smem, st>>>(g);
   }
-  const size_t smem = generic_boundary_smem<T>(g.d);
+  const size_t smem = g.gscratch ? 0 : generic_boundary_smem<T>(g.d);
   KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_boundary_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   generic_boundary_kernel<T><<<2, KJX_GEN_THREADS, smem, st>>>(g);
   return KJX_OK;
 }
 template <typename T> int generic_launch_filter(const GenArgs<T>& g, cudaStream_t st) {
-  const size_t smem = generic_filter_smem<T>(g.d);
+  const size_t smem = g.gscratch ? 0 : generic_filter_smem<T>(g.d);
   KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_filter_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   generic_filter_kernel<T><<<g.nchunks, KJX_GEN_THREADS, smem, st>>>(g);
   if (g.nlml) nlml_reduce_kernel<T><<<1, 256, 0, st>>>(g.chunk_nlml, g.nchunks, g.nlml);
   return KJX_OK;
 }
 template <typename T> int generic_launch_smoother(const GenArgs<T>& g, T* gains, cudaStream_t st) {
-  const size_t smem = generic_smoother_smem<T>(g.d);
+  const size_t smem = g.gscratch ? 0 : generic_smoother_smem<T>(g.d);
   // 1. all RTS gains, parallel over time (they depend on the filtered moments only)
   KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_gain_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const unsigned grid = (unsigned)std::min<int64_t>(g.N, 148 * 4);
+  const unsigned grid = (unsigned)std::min<int64_t>(g.N, KJX_GEN_GAIN_GRID);
   generic_gain_kernel<T><<<grid, KJX_GEN_THREADS, smem, st>>>(g, gains);
   // 2. the backward recursion (two d^3 products per step), every chunk concurrently, reference order inside a chunk
   KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_smoother_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

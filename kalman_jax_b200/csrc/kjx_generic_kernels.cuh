@@ -23,7 +23,9 @@
 
 namespace kjx {
 
-constexpr int KJX_GEN_DMAX = 64;
+constexpr int KJX_GEN_DMAX = 64;          // d x d working set (6 d^2 scalars) fits one SM's shared memory up to here
+constexpr int KJX_GEN_DMAX_GLOBAL = 256;  // above it the same kernels keep their matrices in per-CTA global scratch
+                                          // (L2-resident; correct but untuned: the tiled multi-CTA path is future work)
 constexpr int KJX_GEN_THREADS = 256;
 
 template <typename T> struct GenArgs {
@@ -46,6 +48,8 @@ template <typename T> struct GenArgs {
   T* st_m; T* st_P;        // [nchunks][d], [nchunks][d^2]  filtered state entering every chunk
   T* in_eta; T* in_J;      // [nchunks][d], [nchunks][d^2]  information of everything after every chunk
   T* chunk_nlml;           // [nchunks]
+  unsigned char* gscratch; // d > KJX_GEN_DMAX: per-CTA working set in global memory instead of shared memory
+  size_t gscratch_stride;
 };
 
 // rows of A(dt) for all d rows: vals[d][4], c0n[d] = first column | nnz << 24
@@ -214,7 +218,7 @@ template <typename T> size_t generic_boundary_smem(int d) {
 template <typename T>
 __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_fold_kernel(const GenArgs<T> g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  SmemCarver<T> sc(smem_raw);
+  SmemCarver<T> sc(g.gscratch ? g.gscratch + (size_t)blockIdx.x * g.gscratch_stride : smem_raw);
   const int d = g.d, dd = d * d;
   T* A = sc.take(dd); T* C = sc.take(dd); T* J = sc.take(dd); T* X = sc.take(dd); T* Pinf = sc.take(dd);
   T* vals = sc.take(4 * d); T* b = sc.take(d); T* eta = sc.take(d); T* t1 = sc.take(d); T* Hrow = sc.take(d);
@@ -278,7 +282,7 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_fold_kernel(const Gen
 template <typename T>
 __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_boundary_kernel(const GenArgs<T> g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  SmemCarver<T> sc(smem_raw);
+  SmemCarver<T> sc(g.gscratch ? g.gscratch + (size_t)blockIdx.x * g.gscratch_stride : smem_raw);
   const int d = g.d, dd = d * d, ld = d + 1;
   T* P = sc.take(dd); T* M = sc.take(dd); T* R = sc.take(dd + d); T* Tm = sc.take(dd);
   T* m = sc.take(d); T* u = sc.take(d); T* w = sc.take(d);
@@ -348,7 +352,7 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_boundary_kernel(const
 template <typename T>
 __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_filter_kernel(const GenArgs<T> g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  SmemCarver<T> sc(smem_raw);
+  SmemCarver<T> sc(g.gscratch ? g.gscratch + (size_t)blockIdx.x * g.gscratch_stride : smem_raw);
   const int d = g.d, dd = d * d;
   T* P = sc.take(dd); T* X = sc.take(dd); T* Pinf = sc.take(dd);
   T* vals = sc.take(4 * d); T* m = sc.take(d); T* mp = sc.take(d); T* Hrow = sc.take(d); T* HP = sc.take(d); T* K = sc.take(d);
@@ -475,7 +479,7 @@ template <typename T, int TPC> __device__ void chol_substitute(int d, const T* L
 template <typename T>
 __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_gain_kernel(const GenArgs<T> g, T* __restrict__ Gt_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  SmemCarver<T> sc(smem_raw);
+  SmemCarver<T> sc(g.gscratch ? g.gscratch + (size_t)blockIdx.x * g.gscratch_stride : smem_raw);
   const int d = g.d, dd = d * d;
   T* Pf = sc.take(dd); T* Pp = sc.take(dd); T* Gt = sc.take(dd); T* W = sc.take(dd); T* Pinf = sc.take(dd);
   T* vals = sc.take(4 * d); T* rinv = sc.take(d);
@@ -502,7 +506,7 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_gain_kernel(const Gen
 template <typename T>
 __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_smoother_kernel(const GenArgs<T> g, const T* __restrict__ Gt_in) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  SmemCarver<T> sc(smem_raw);
+  SmemCarver<T> sc(g.gscratch ? g.gscratch + (size_t)blockIdx.x * g.gscratch_stride : smem_raw);
   const int d = g.d, dd = d * d;
   T* Pf = sc.take(dd); T* Pp = sc.take(dd + d); T* Gt = sc.take(dd); T* Ps = sc.take(dd); T* W = sc.take(dd); T* Pinf = sc.take(dd);
   T* vals = sc.take(4 * d); T* mf = sc.take(d); T* mp = sc.take(d); T* ms = sc.take(d); T* dm = sc.take(d); T* Hrow = sc.take(d);

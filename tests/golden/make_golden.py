@@ -200,6 +200,9 @@ def load_data(name):
     if name == "banana200":
         X, Y, R = data_banana()
         return X[:200], Y[:200], R[:200], None, None
+    if name == "banana120":
+        X, Y, R = data_banana()
+        return X[:120], Y[:120], R[:120], None, None
     raise KeyError(name)
 
 

@@ -14,6 +14,8 @@ M52_11 = ("Matern52", dict(variance=1.0, lengthscale=1.0))
 M52_15 = ("Matern52", dict(variance=1.0, lengthscale=5.0))
 M32_154 = ("Matern32", dict(variance=1.5, lengthscale=4.0))
 ST52 = ("SpatioTemporalMatern52", dict(variance=0.3, lengthscale_time=0.3, lengthscale_space=0.3))
+ST52_M25 = ("SpatioTemporalMatern52", dict(variance=0.3, lengthscale_time=0.3, lengthscale_space=0.3,
+                                            z=[-3.0 + 0.25 * i for i in range(25)]))
 POISSON = ("Poisson", dict())
 PROBIT = ("Probit", dict())
 LOGIT = ("Bernoulli", dict(link="logit"))
@@ -50,9 +52,11 @@ CASES = {
     "c3_aircraft160_d31_poisson_eks": ("aircraft160", ("Sum", [AIR_M52, AIR_QP365]), POISSON, ("EKS", dict()), 2, None),
     "k5_banana400_st52_probit_pep05": ("banana400", ST52, PROBIT, ("ExpectationPropagation", dict(power=0.5)), 2, 178.81),
     "c4_banana200_st52_probit_vi": ("banana200", ST52, PROBIT, ("VI", dict()), 2, None),
+    # 25 inducing points -> state dimension 75: above what one SM's shared memory holds (global-scratch path)
+    "c4_banana120_st52_m25_probit_ep": ("banana120", ST52_M25, PROBIT, ("EP", dict(power=0.8)), 2, None),
 }
 
-KEEP_EVERY = {"aircraft160": 8, "banana400": 16, "banana200": 16}
+KEEP_EVERY = {"aircraft160": 8, "banana400": 16, "banana200": 16, "banana120": 24}
 
 
 def build(spec, module):
@@ -60,4 +64,8 @@ def build(spec, module):
     name, arg = spec
     if name == "Sum":
         return module.Sum([build(s, module) for s in arg])
+    arg = dict(arg)
+    if "z" in arg:
+        import numpy as np
+        arg["z"] = np.asarray(arg["z"], dtype=float)
     return getattr(module, name)(**arg)

@@ -385,3 +385,35 @@ def test_fused_run_returns_dense_filter_output_on_request():
     torch.cuda.synchronize()
     assert rel_err(_np(fm2), _np(fm)[:, :, 0]) < 1e-12 and rel_err(_np(fP2), _np(fP)) < 1e-12
     assert abs(float(nl[0]) - float(nlml)) <= 1e-12 * abs(float(nlml))
+
+
+def test_spatio_temporal_ns64_d192_vs_oracle():
+    """BASELINE config 4 shape: Ns = 64 inducing points -> state dimension 192 (per-step dense H, Probit, VI).
+    The d x d working set no longer fits shared memory; the kernels run from per-CTA global scratch."""
+    kjx = _kjx()
+    rng = np.random.default_rng(99)
+    N = 72
+    t = np.sort(rng.uniform(0, 6, N))
+    r = rng.uniform(-3, 3, N)
+    y = (rng.uniform(size=N) < 0.5).astype(float)
+    z = np.linspace(-3, 3, 64)
+    # spatial lengthscale 0.3: cond(Kzz) ~ 4e3.  (With lengthscale 1 the 64 inducing points are 0.095 apart, Kzz and
+    # hence P_pred are numerically singular and whether a Cholesky pivot comes out as +1e-17 or -1e-17 — a factor
+    # or NaN — is rounding luck, in LAPACK as much as here.)
+    mk = lambda mod, inf: mod.SDEGP(mod.priors.SpatioTemporalMatern52(1.0, 1.0, 0.3, z=z), mod.likelihoods.Probit(), t, y, r=r,  # noqa: E731
+                                    approx_inf=inf.VI())
+    model, ref = mk(kjx, kjx.approximate_inference), mk(oracle, oracle.approx_inf)
+    assert model.state_dim == 192
+    for it in range(2):
+        nlml, _ = model.run(compute_grad=False, store_posterior=True)
+        want_nlml, (wfm, wfP, wsites) = ref.kalman_filter(ref.y, ref.dt, True, None, ref.sites.site_params, ref.r)
+        w_new, wsm, wsc = ref.rauch_tung_striebel_smoother(wfm, wfP, ref.dt, True, False, ref.y, wsites, ref.r)
+        ref.sites.site_params = w_new
+        # The filter (no factorisation of a d x d matrix) agrees to 1e-9; the RTS gain solves with P_pred, whose
+        # condition number here is ~1e9 (Kzz (x) Pinf_t), so two correct Cholesky solves (LAPACK's blocked potrf/potrs in
+        # the oracle, the left-looking CTA factorisation here) may differ by cond * eps ~ 1e-7 .. 1e-6 in the smoothed
+        # moments.  Tolerance 1e-5, stated as such.
+        assert abs(nlml - want_nlml) <= 1e-9 * abs(want_nlml)
+        assert rel_err(_np(model.posterior[0]), wsm) < 1e-5 and rel_err(_np(model.posterior[1]), wsc) < 1e-5
+        assert rel_err(_np(model.sites.site_params[0]), w_new[0]) < 1e-5
+        assert rel_err(_np(model.sites.site_params[1]), w_new[1]) < 1e-5
