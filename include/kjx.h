@@ -155,6 +155,14 @@ int kjx_run_f64(const kjx_model_t* m, int64_t N, const double* dt, const double*
                 double* post_mean /*?*/, double* post_var /*?*/,
                 double* nlml, void* ws, size_t ws_bytes, uint32_t flags, kjx_stream_t stream);
 
+/* Posterior marginals on a merged train/test grid — SDEGP.predict_everywhere (sde_gp.py:85-103) in one fused scan:
+ * filter with the given sites where masked steps (mask[n] != 0, the test inputs) are predict-only
+ * (sde_gp.py:286, 297-300), then the smoother without site update; post_mean/post_var = H m, H P H^T per step.
+ * nlml (nullable) receives the filter energy of the unmasked steps. */
+int kjx_posterior_f64(const kjx_model_t* m, int64_t N, const double* dt, const double* y, const uint8_t* mask /*?*/,
+                      const double* site_mean, const double* site_cov, double* post_mean, double* post_var,
+                      double* nlml /*?*/, void* ws, size_t ws_bytes, kjx_stream_t stream);
+
 /* Per-step site update, embarrassingly parallel over N (f = 1):
  * (log_lik, site_mean, site_var) = method.update(likelihood, y, post_mean, post_var, prev site?).
  * With prev null this is the "initialise" branch; log_lik alone (site outputs null) with method EP

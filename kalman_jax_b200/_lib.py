@@ -45,7 +45,7 @@ _lib = None
 # every symbol include/kjx.h declares (tests check the shared object exports each of them)
 SYMBOLS = [
     "kjx_version", "kjx_status_string", "kjx_workspace_bytes",
-    "kjx_filter_f64", "kjx_smoother_f64", "kjx_run_f64", "kjx_site_update_f64", "kjx_discretise_f64",
+    "kjx_filter_f64", "kjx_smoother_f64", "kjx_run_f64", "kjx_posterior_f64", "kjx_site_update_f64", "kjx_discretise_f64",
     "kjx_filter_f32", "kjx_smoother_f32", "kjx_run_f32", "kjx_site_update_f32", "kjx_discretise_f32",
     "kjx_filter_summary_doubles",
     "kjx_filter_summary_f64", "kjx_filter_apply_f64", "kjx_smoother_apply_f64",

@@ -181,92 +181,6 @@ struct SmallCall {
   void* nlml;
 };
 
-template <typename T, int KIND>
-int small_filter_scan(const kjx_model_t* m, int64_t N, SmallArgs<T, BlockDim<KIND>::D>& a, bool with_smoother,
-                      const T* f_state_in_dev /* null: prior */, cudaStream_t st) {
-  constexpr int D = BlockDim<KIND>::D;
-  filter_reduce_kernel<T, KIND><<<(unsigned)a.nblocks, KJX_BLOCK, 0, st>>>(a);
-  filter_blockscan_kernel<T, D><<<1, KJX_SCAN_BLOCK, 0, st>>>(a);
-  if (f_state_in_dev) copy_state_kernel<T, D><<<1, 32, 0, st>>>((T*)a.f_state_in, f_state_in_dev);
-  else launch_set_prior_state<T, D>((T*)a.f_state_in, m, st);
-  const bool fast = gauss_ep(m);
-  if (with_smoother) {
-    if (fast) filter_apply_kernel<T, KIND, true, true><<<(unsigned)a.nblocks, KJX_BLOCK, 0, st>>>(a);
-    else filter_apply_kernel<T, KIND, true, false><<<(unsigned)a.nblocks, KJX_BLOCK, 0, st>>>(a);
-  } else {
-    if (fast) filter_apply_kernel<T, KIND, false, true><<<(unsigned)a.nblocks, KJX_BLOCK, 0, st>>>(a);
-    else filter_apply_kernel<T, KIND, false, false><<<(unsigned)a.nblocks, KJX_BLOCK, 0, st>>>(a);
-  }
-  return KJX_OK;
-}
-
-template <typename T, int KIND>
-int small_smoother_apply(const kjx_model_t* m, SmallArgs<T, BlockDim<KIND>::D>& a, cudaStream_t st) {
-  if (gauss_ep(m)) smoother_apply_kernel<T, KIND, true><<<(unsigned)a.nblocks, KJX_BLOCK, 0, st>>>(a);
-  else smoother_apply_kernel<T, KIND, false><<<(unsigned)a.nblocks, KJX_BLOCK, 0, st>>>(a);
-  return KJX_OK;
-}
-
-// the filter must run as one chain when sites have to be initialised from the predictive and that
-// initialisation depends on the state (anything but Gaussian + EP, utils.py:241-244)
-bool needs_sequential_filter(const kjx_model_t* m, bool have_sites) { return !have_sites && !gauss_ep(m); }
-
-template <typename T, int KIND>
-int small_filter(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const uint8_t* mask,
-                 const T* site_mean, const T* site_var, T* filt_mean, T* filt_cov, T* out_site_mean,
-                 T* out_site_var, T* nlml, void* ws, size_t ws_bytes, uint32_t flags, cudaStream_t st) {
-  constexpr int D = BlockDim<KIND>::D;
-  SmallLayout<T, D> lay(N);
-  if (ws_bytes < lay.total || !ws) return KJX_ERR_WORKSPACE;
-  SmallArgs<T, D> a; memset(&a, 0, sizeof(a));
-  fill_prior<T, D>(a, m); bind_workspace<T, D>(a, lay, ws);
-  a.N = N; a.dt = dt; a.y = y; a.mask = mask; a.site_mean = site_mean; a.site_var = site_var;
-  a.filt_mean = filt_mean; a.filt_cov = filt_cov; a.out_site_mean = out_site_mean; a.out_site_var = out_site_var;
-  a.is_last_shard = 1; a.dt_next = T(0); a.nlml_out = nlml;
-  const bool have_sites = site_mean != nullptr;
-  a.gaussian_init = (!have_sites && gauss_ep(m)) ? 1 : 0;
-  if (N == 0) { cudaMemsetAsync(nlml, 0, sizeof(T), st); return KJX_OK; }
-  if ((flags & KJX_FLAG_SEQUENTIAL) || needs_sequential_filter(m, have_sites)) {
-    launch_set_prior_state<T, D>((T*)a.f_state_in, m, st);
-    const int init = (!have_sites && !a.gaussian_init) ? 1 : 0;
-    filter_sequential_kernel<T, KIND><<<1, 32, 0, st>>>(a, init);
-  } else {
-    small_filter_scan<T, KIND>(m, N, a, false, nullptr, st);
-    nlml_reduce_kernel<T><<<1, KJX_SCAN_BLOCK, 0, st>>>(a.block_nlml, a.nblocks, nlml);
-  }
-  KJX_CUDA_CHECK(cudaGetLastError());
-  return KJX_OK;
-}
-
-template <typename T, int KIND>
-int small_smoother(const kjx_model_t* m, int64_t N, const T* dt, const T* filt_mean, const T* filt_cov,
-                   const T* y, const T* site_mean, const T* site_var, T* smooth_mean, T* smooth_cov,
-                   T* new_site_mean, T* new_site_var, void* ws, size_t ws_bytes, uint32_t flags, cudaStream_t st) {
-  constexpr int D = BlockDim<KIND>::D;
-  SmallLayout<T, D> lay(N);
-  if (ws_bytes < lay.total || !ws) return KJX_ERR_WORKSPACE;
-  SmallArgs<T, D> a; memset(&a, 0, sizeof(a));
-  fill_prior<T, D>(a, m); bind_workspace<T, D>(a, lay, ws);
-  a.N = N; a.dt = dt; a.y = y; a.site_mean = site_mean; a.site_var = site_var;
-  a.filt_mean_in = filt_mean; a.filt_cov_in = filt_cov;
-  a.smooth_mean = smooth_mean; a.smooth_cov = smooth_cov; a.new_site_mean = new_site_mean; a.new_site_var = new_site_var;
-  a.return_full = (flags & KJX_FLAG_RETURN_FULL) ? 1 : 0;
-  a.update_sites = (new_site_mean != nullptr && site_mean != nullptr && y != nullptr) ? 1 : 0;
-  a.is_last_shard = 1; a.dt_next = T(0);
-  if (N == 0) return KJX_OK;
-  if (flags & KJX_FLAG_SEQUENTIAL) {
-    smoother_sequential_kernel<T, KIND><<<1, 32, 0, st>>>(a);
-  } else {
-    smoother_reduce_kernel<T, KIND><<<(unsigned)a.nblocks, KJX_BLOCK, 0, st>>>(a);
-    a.nlml_out = nullptr;
-    smoother_blockscan_kernel<T, D><<<1, KJX_SCAN_BLOCK, 0, st>>>(a);
-    cudaMemsetAsync((void*)a.s_state_in, 0, (D + D * D) * sizeof(T), st);
-    small_smoother_apply<T, KIND>(m, a, st);
-  }
-  KJX_CUDA_CHECK(cudaGetLastError());
-  return KJX_OK;
-}
-
 // ---- the fused iteration (kjx_run and the sharded calls) ----------------------------------------------
 template <typename T, int KIND>
 struct Fused {
@@ -303,12 +217,21 @@ struct Fused {
       else fused_segscan_kernel<T, D, 128><<<nseg, 64, smem, st>>>(fa.lvl[l], tot, tstride);
     }
   }
-  void filter(cudaStream_t st) {
+  // plain: the run() iteration; otherwise mask / energy-only / site write-back are honoured
+  void filter(cudaStream_t st, bool plain = true) {
     const bool fast = gauss_ep(m);
-    if (fast && fa.vec_ok) fused_filter_kernel<T, KIND, true, true><<<grid(), KJX_BLOCK, 0, st>>>(fa);
-    else if (fast) fused_filter_kernel<T, KIND, true, false><<<grid(), KJX_BLOCK, 0, st>>>(fa);
-    else if (fa.vec_ok) fused_filter_kernel<T, KIND, false, true><<<grid(), KJX_BLOCK, 0, st>>>(fa);
-    else fused_filter_kernel<T, KIND, false, false><<<grid(), KJX_BLOCK, 0, st>>>(fa);
+    if (plain) {
+      fa.store_xf = 1;
+      if (fast && fa.vec_ok) fused_filter_kernel<T, KIND, true, true, true><<<grid(), KJX_BLOCK, 0, st>>>(fa);
+      else if (fast) fused_filter_kernel<T, KIND, true, false, true><<<grid(), KJX_BLOCK, 0, st>>>(fa);
+      else if (fa.vec_ok) fused_filter_kernel<T, KIND, false, true, true><<<grid(), KJX_BLOCK, 0, st>>>(fa);
+      else fused_filter_kernel<T, KIND, false, false, true><<<grid(), KJX_BLOCK, 0, st>>>(fa);
+    } else {
+      if (fast && fa.vec_ok) fused_filter_kernel<T, KIND, true, true, false><<<grid(), KJX_BLOCK, 0, st>>>(fa);
+      else if (fast) fused_filter_kernel<T, KIND, true, false, false><<<grid(), KJX_BLOCK, 0, st>>>(fa);
+      else if (fa.vec_ok) fused_filter_kernel<T, KIND, false, true, false><<<grid(), KJX_BLOCK, 0, st>>>(fa);
+      else fused_filter_kernel<T, KIND, false, false, false><<<grid(), KJX_BLOCK, 0, st>>>(fa);
+    }
   }
   void smoother(T* post_mean, T* post_var, T* new_site_mean, T* new_site_var, bool update, cudaStream_t st) {
     fa.a.smooth_mean = post_mean; fa.a.smooth_cov = post_var; fa.a.new_site_mean = new_site_mean; fa.a.new_site_var = new_site_var;
@@ -340,13 +263,87 @@ __global__ void unpack_filtered_kernel(const T* __restrict__ xf, int64_t N, int 
 }
 
 template <typename T, int KIND>
-int small_run(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const T* site_mean, const T* site_var,
-              T* filt_mean, T* filt_cov, T* new_site_mean, T* new_site_var, T* post_mean, T* post_var,
-              T* nlml, void* ws, size_t ws_bytes, uint32_t flags, cudaStream_t st) {
+int small_smoother_apply(const kjx_model_t* m, SmallArgs<T, BlockDim<KIND>::D>& a, cudaStream_t st) {
+  if (gauss_ep(m)) smoother_apply_kernel<T, KIND, true><<<(unsigned)a.nblocks, KJX_BLOCK, 0, st>>>(a);
+  else smoother_apply_kernel<T, KIND, false><<<(unsigned)a.nblocks, KJX_BLOCK, 0, st>>>(a);
+  return KJX_OK;
+}
+
+// the filter must run as one chain when sites have to be initialised from the predictive and that
+// initialisation depends on the state (anything but Gaussian + EP, utils.py:241-244)
+bool needs_sequential_filter(const kjx_model_t* m, bool have_sites) { return !have_sites && !gauss_ep(m); }
+
+template <typename T, int KIND>
+int small_filter(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const uint8_t* mask,
+                 const T* site_mean, const T* site_var, T* filt_mean, T* filt_cov, T* out_site_mean,
+                 T* out_site_var, T* nlml, void* ws, size_t ws_bytes, uint32_t flags, cudaStream_t st) {
   constexpr int D = BlockDim<KIND>::D;
   SmallLayout<T, D> lay(N);
   if (ws_bytes < lay.total || !ws) return KJX_ERR_WORKSPACE;
+  SmallArgs<T, D> a; memset(&a, 0, sizeof(a));
+  fill_prior<T, D>(a, m); bind_workspace<T, D>(a, lay, ws);
+  a.N = N; a.dt = dt; a.y = y; a.mask = mask; a.site_mean = site_mean; a.site_var = site_var;
+  a.filt_mean = filt_mean; a.filt_cov = filt_cov; a.out_site_mean = out_site_mean; a.out_site_var = out_site_var;
+  a.is_last_shard = 1; a.dt_next = T(0); a.nlml_out = nlml;
+  const bool have_sites = site_mean != nullptr;
+  a.gaussian_init = (!have_sites && gauss_ep(m)) ? 1 : 0;
   if (N == 0) { cudaMemsetAsync(nlml, 0, sizeof(T), st); return KJX_OK; }
+  if ((flags & KJX_FLAG_SEQUENTIAL) || needs_sequential_filter(m, have_sites)) {
+    launch_set_prior_state<T, D>((T*)a.f_state_in, m, st);
+    const int init = (!have_sites && !a.gaussian_init) ? 1 : 0;
+    filter_sequential_kernel<T, KIND><<<1, 32, 0, st>>>(a, init);
+  } else {
+    // parallel-in-time: the fused scan's fold / segment scans / filter (energy-only when no output is asked for)
+    Fused<T, KIND> f(m, N, dt, y, site_mean, site_var, ws);
+    f.fa.a.mask = mask; f.fa.a.out_site_mean = out_site_mean; f.fa.a.out_site_var = out_site_var;
+    f.fa.store_xf = (filt_mean != nullptr) ? 1 : 0;
+    f.reduce(st);
+    launch_set_prior_state<T, D>((T*)f.fa.a.f_state_in, m, st);
+    f.filter(st, /*plain=*/false);
+    nlml_reduce_kernel<T><<<1, 256, 0, st>>>(f.fa.a.block_nlml, f.nthread_blocks, nlml);
+    if (filt_mean) unpack_filtered_kernel<T, D><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(f.fa.xf, N, f.lay.L, filt_mean, filt_cov);
+  }
+  KJX_CUDA_CHECK(cudaGetLastError());
+  return KJX_OK;
+}
+
+template <typename T, int KIND>
+int small_smoother(const kjx_model_t* m, int64_t N, const T* dt, const T* filt_mean, const T* filt_cov,
+                   const T* y, const T* site_mean, const T* site_var, T* smooth_mean, T* smooth_cov,
+                   T* new_site_mean, T* new_site_var, void* ws, size_t ws_bytes, uint32_t flags, cudaStream_t st) {
+  constexpr int D = BlockDim<KIND>::D;
+  SmallLayout<T, D> lay(N);
+  if (ws_bytes < lay.total || !ws) return KJX_ERR_WORKSPACE;
+  SmallArgs<T, D> a; memset(&a, 0, sizeof(a));
+  fill_prior<T, D>(a, m); bind_workspace<T, D>(a, lay, ws);
+  a.N = N; a.dt = dt; a.y = y; a.site_mean = site_mean; a.site_var = site_var;
+  a.filt_mean_in = filt_mean; a.filt_cov_in = filt_cov;
+  a.smooth_mean = smooth_mean; a.smooth_cov = smooth_cov; a.new_site_mean = new_site_mean; a.new_site_var = new_site_var;
+  a.return_full = (flags & KJX_FLAG_RETURN_FULL) ? 1 : 0;
+  a.update_sites = (new_site_mean != nullptr && site_mean != nullptr && y != nullptr) ? 1 : 0;
+  a.is_last_shard = 1; a.dt_next = T(0);
+  if (N == 0) return KJX_OK;
+  if (flags & KJX_FLAG_SEQUENTIAL) {
+    smoother_sequential_kernel<T, KIND><<<1, 32, 0, st>>>(a);
+  } else {
+    smoother_reduce_kernel<T, KIND><<<(unsigned)a.nblocks, KJX_BLOCK, 0, st>>>(a);
+    a.nlml_out = nullptr;
+    smoother_blockscan_kernel<T, D><<<1, KJX_SCAN_BLOCK, 0, st>>>(a);
+    cudaMemsetAsync((void*)a.s_state_in, 0, (D + D * D) * sizeof(T), st);
+    small_smoother_apply<T, KIND>(m, a, st);
+  }
+  KJX_CUDA_CHECK(cudaGetLastError());
+  return KJX_OK;
+}
+
+template <typename T, int KIND>
+int small_run(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const T* site_mean, const T* site_var,
+              T* filt_mean, T* filt_cov, T* new_site_mean, T* new_site_var, T* post_mean, T* post_var,
+              T* nlml, void* ws, size_t ws_bytes, uint32_t flags, cudaStream_t st, const uint8_t* mask = nullptr) {
+  constexpr int D = BlockDim<KIND>::D;
+  SmallLayout<T, D> lay(N);
+  if (ws_bytes < lay.total || !ws) return KJX_ERR_WORKSPACE;
+  if (N == 0) { if (nlml) cudaMemsetAsync(nlml, 0, sizeof(T), st); return KJX_OK; }
   const bool have_sites = site_mean != nullptr;
   const bool seq = (flags & KJX_FLAG_SEQUENTIAL) != 0;
   const bool update = !(flags & KJX_FLAG_NO_SITE_UPDATE);
@@ -356,7 +353,7 @@ int small_run(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const T*
     if (!filt_mean || !filt_cov) return KJX_ERR_INVALID_ARG;
     SmallArgs<T, D> a; memset(&a, 0, sizeof(a));
     fill_prior<T, D>(a, m); bind_workspace<T, D>(a, lay, ws);
-    a.N = N; a.dt = dt; a.y = y; a.site_mean = site_mean; a.site_var = site_var;
+    a.N = N; a.dt = dt; a.y = y; a.mask = mask; a.site_mean = site_mean; a.site_var = site_var;
     a.filt_mean = filt_mean; a.filt_cov = filt_cov; a.filt_mean_in = filt_mean; a.filt_cov_in = filt_cov;
     a.smooth_mean = post_mean; a.smooth_cov = post_var; a.new_site_mean = new_site_mean; a.new_site_var = new_site_var;
     a.update_sites = update ? 1 : 0; a.is_last_shard = 1; a.nlml_out = nlml;
@@ -378,11 +375,12 @@ int small_run(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const T*
     }
   } else {
     Fused<T, KIND> f(m, N, dt, y, site_mean, site_var, ws);
+    f.fa.a.mask = mask;
     f.reduce(st);
     launch_set_prior_state<T, D>((T*)f.fa.a.f_state_in, m, st);
     cudaMemsetAsync((void*)f.fa.s_info_in, 0, (D + D * D) * sizeof(T), st);
-    f.filter(st);
-    nlml_reduce_kernel<T><<<1, 256, 0, st>>>(f.fa.a.block_nlml, f.nthread_blocks, nlml);
+    if (mask) { f.fa.store_xf = 1; f.filter(st, /*plain=*/false); } else f.filter(st);
+    if (nlml) nlml_reduce_kernel<T><<<1, 256, 0, st>>>(f.fa.a.block_nlml, f.nthread_blocks, nlml);
     f.smoother(post_mean, post_var, new_site_mean, new_site_var, update, st);
     if (filt_mean && filt_cov)
       unpack_filtered_kernel<T, D><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(f.fa.xf, N, f.lay.L, filt_mean, filt_cov);
@@ -621,13 +619,13 @@ int generic_smoother(const kjx_model_t* m, int64_t N, const T* dt, const T* filt
 template <typename T>
 int generic_run(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const T* site_mean, const T* site_var,
                 T* filt_mean, T* filt_cov, T* new_site_mean, T* new_site_var, T* post_mean, T* post_var, T* nlml,
-                void* ws, size_t ws_bytes, uint32_t flags, cudaStream_t st) {
+                void* ws, size_t ws_bytes, uint32_t flags, cudaStream_t st, const uint8_t* mask = nullptr) {
   GenArgs<T> g; T *sm, *sc, *sg;
   int rc = generic_setup<T>(m, N, ws, ws_bytes, g, &sm, &sc, &sg, st);
   if (rc != KJX_OK) return rc;
-  if (N == 0) { cudaMemsetAsync(nlml, 0, sizeof(T), st); return KJX_OK; }
+  if (N == 0) { if (nlml) cudaMemsetAsync(nlml, 0, sizeof(T), st); return KJX_OK; }
   if (!filt_mean) { filt_mean = sm; filt_cov = sc; }       // run() uses the filtered moments only internally
-  g.dt = dt; g.y = y; g.site_mean = site_mean; g.site_var = site_var;
+  g.dt = dt; g.y = y; g.mask = mask; g.site_mean = site_mean; g.site_var = site_var;
   g.init_sites = (site_mean == nullptr && !gauss_ep(m)) ? 1 : 0;
   g.filt_mean = filt_mean; g.filt_cov = filt_cov; g.nlml = nlml;
   if (g.init_sites) { g.out_site_mean = new_site_mean; g.out_site_var = new_site_var; }   // sde_gp.py:183
@@ -702,6 +700,23 @@ int run_T(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const T* sit
     default:
       if (!generic_ok(m)) return KJX_ERR_UNSUPPORTED;
       return generic_run<T>(m, N, dt, y, site_mean, site_cov, filt_mean, filt_cov, new_site_mean, new_site_cov, post_mean, post_var, nlml, ws, ws_bytes, flags, st);
+  }
+}
+
+template <typename T>
+int posterior_T(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const uint8_t* mask, const T* site_mean,
+                const T* site_cov, T* post_mean, T* post_var, T* nlml, void* ws, size_t ws_bytes, kjx_stream_t stream) {
+  if (!model_basic_ok(m) || N < 0 || !dt || !y || !post_mean || !post_var) return KJX_ERR_INVALID_ARG;
+  if ((site_mean == nullptr) != (site_cov == nullptr)) return KJX_ERR_INVALID_ARG;
+  if (needs_sequential_filter(m, site_mean != nullptr)) return KJX_ERR_UNSUPPORTED;   // use kjx_filter + kjx_smoother
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint32_t flags = KJX_FLAG_NO_SITE_UPDATE;
+  switch (small_kind(m)) {
+    case KJX_BLOCK_MATERN32: return small_run<T, KJX_BLOCK_MATERN32>(m, N, dt, y, site_mean, site_cov, nullptr, nullptr, nullptr, nullptr, post_mean, post_var, nlml, ws, ws_bytes, flags, st, mask);
+    case KJX_BLOCK_MATERN52: return small_run<T, KJX_BLOCK_MATERN52>(m, N, dt, y, site_mean, site_cov, nullptr, nullptr, nullptr, nullptr, post_mean, post_var, nlml, ws, ws_bytes, flags, st, mask);
+    default:
+      if (!generic_ok(m)) return KJX_ERR_UNSUPPORTED;
+      return generic_run<T>(m, N, dt, y, site_mean, site_cov, nullptr, nullptr, nullptr, nullptr, post_mean, post_var, nlml, ws, ws_bytes, flags, st, mask);
   }
 }
 
@@ -811,6 +826,12 @@ int kjx_run_f32(const kjx_model_t* m, int64_t N, const float* dt, const float* y
                 float* post_mean, float* post_var, float* nlml, void* ws, size_t ws_bytes, uint32_t flags,
                 kjx_stream_t stream) {
   return run_T<float>(m, N, dt, y, site_mean, site_cov, filt_mean, filt_cov, new_site_mean, new_site_cov, post_mean, post_var, nlml, ws, ws_bytes, flags, stream);
+}
+
+int kjx_posterior_f64(const kjx_model_t* m, int64_t N, const double* dt, const double* y, const uint8_t* mask,
+                      const double* site_mean, const double* site_cov, double* post_mean, double* post_var, double* nlml,
+                      void* ws, size_t ws_bytes, kjx_stream_t stream) {
+  return posterior_T<double>(m, N, dt, y, mask, site_mean, site_cov, post_mean, post_var, nlml, ws, ws_bytes, stream);
 }
 
 int kjx_site_update_f64(const kjx_model_t* m, int64_t N, const double* y, const double* post_mean, const double* post_var,

@@ -102,6 +102,7 @@ template <typename T, int D> struct FusedArgs {
   const T* s_info_in;       // [D + D*D] information (eta, J) of all later shards about this shard's last state
   int vec_ok;               // every per-step array is 32-byte (fp64) / 16-byte (fp32) aligned
   int seg;                  // elements per scan segment (64 or 128)
+  int store_xf;             // keep the filtered moments (0: energy-only filter)
 };
 
 template <typename T, int D>
@@ -252,7 +253,10 @@ __global__ void __launch_bounds__(64) fused_segscan_kernel(const ScanLevel<T, D>
 
 // ------------------------------------------------------------------------------------------------
 // R3
-template <typename T, int KIND, bool GAUSS_EP, bool VEC>
+// PLAIN: the run() iteration (no mask, filtered moments parked in the private layout, sites not written back).
+// !PLAIN adds, with runtime checks: masked (predict-only) steps, energy-only runs (no filtered moments kept) and
+// writing the initialised sites — the stand-alone kjx_filter and the prediction path.
+template <typename T, int KIND, bool GAUSS_EP, bool VEC, bool PLAIN>
 __global__ void __launch_bounds__(KJX_BLOCK, KJX_R3_MINB) fused_filter_kernel(const FusedArgs<T, BlockDim<KIND>::D> fa) {
   constexpr int D = BlockDim<KIND>::D;
   constexpr int NP = Packed<D>::NP;
@@ -280,6 +284,8 @@ __global__ void __launch_bounds__(KJX_BLOCK, KJX_R3_MINB) fused_filter_kernel(co
       const Vec4<T> vy = load4v<T, VEC>(a.y + k);
       Vec4<T> vm, vr;
       if (!a.gaussian_init) { vm = load4v<T, VEC>(a.site_mean + k); vr = load4v<T, VEC>(a.site_var + k); }
+      uint32_t mk = 0;
+      if (!PLAIN && a.mask) mk = (uint32_t)a.mask[k] | ((uint32_t)a.mask[k + 1] << 8) | ((uint32_t)a.mask[k + 2] << 16) | ((uint32_t)a.mask[k + 3] << 24);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         T F[D][D];
@@ -287,10 +293,14 @@ __global__ void __launch_bounds__(KJX_BLOCK, KJX_R3_MINB) fused_filter_kernel(co
         filter_predict<T, D>(F, Pinf, x);                                   // sde_gp.py:276-278
         const T pm = x.m[0], pv = x.P[0][0];
         const T smean = a.gaussian_init ? vy.x[j] : vm.x[j], svar = a.gaussian_init ? lik_hyp : vr.x[j];
-        nl += GAUSS_EP ? gaussian_moment_match<T>(vy.x[j], pm, pv, lik_hyp).lml     // sde_gp.py:287 (log Z only)
-                       : filter_loglik<T>(a.site, vy.x[j], pm, pv);
-        filter_update<T, D>(x, smean, svar);                                // sde_gp.py:292-296
-        xf_store<T, D>(xf + (k - s0 + j) * NP * 32, x);
+        const bool masked = !PLAIN && ((mk >> (8 * j)) & 0xff) != 0;
+        if (!masked) {
+          nl += GAUSS_EP ? gaussian_moment_match<T>(vy.x[j], pm, pv, lik_hyp).lml   // sde_gp.py:287 (log Z only)
+                         : filter_loglik<T>(a.site, vy.x[j], pm, pv);
+          filter_update<T, D>(x, smean, svar);                              // sde_gp.py:292-296
+        }                                                                   // masked: predict-only, :297-300
+        if (PLAIN || fa.store_xf) xf_store<T, D>(xf + (k - s0 + j) * NP * 32, x);
+        if (!PLAIN && a.out_site_mean) { a.out_site_mean[k + j] = smean; a.out_site_var[k + j] = svar; }
       }
     }
     (void)ysrc;
@@ -299,8 +309,9 @@ __global__ void __launch_bounds__(KJX_BLOCK, KJX_R3_MINB) fused_filter_kernel(co
       Transition<T, KIND>::eval(a.dt[k], a.prior.lam, F);
       filter_predict<T, D>(F, Pinf, x);
       T smean, svar;
-      nl += filter_step_body<T, D, GAUSS_EP>(a, k, x, false, smean, svar);
-      xf_store<T, D>(xf + (k - s0) * NP * 32, x);
+      nl += filter_step_body<T, D, GAUSS_EP>(a, k, x, false, smean, svar);   // handles the mask itself
+      if (PLAIN || fa.store_xf) xf_store<T, D>(xf + (k - s0) * NP * 32, x);
+      if (!PLAIN && a.out_site_mean) { a.out_site_mean[k] = smean; a.out_site_var[k] = svar; }
     }
   }
   T s = nl;

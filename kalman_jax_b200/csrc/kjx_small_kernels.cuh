@@ -5,15 +5,8 @@
 //
 //   time axis -> thread chunks of L consecutive steps -> blocks of KJX_BLOCK chunks -> shard (one GPU)
 //
-//   filter_reduce   (F1) every thread folds its L steps into one scan element (A,b,C,eta,J) with the
-//                        O(d^2) rank-one update, block-level exclusive scan (warp shuffles), writes the
-//                        per-thread prefix and the block total
-//   filter_blockscan(F2) one CTA scans the block totals -> per-block prefix + shard total
-//   filter_apply    (F3) every thread rebuilds its true incoming (m,P) from the prefixes and then runs
-//                        the REFERENCE recursion verbatim over its L steps, streaming filtered means /
-//                        covariances out and accumulating log Z; in the same pass it folds the smoother
-//                        scan elements (E,g,L) of its steps (the RTS gain needs exactly the predicted
-//                        moments the filter computes next) and block-scans them in reverse
+//   (the filter scan itself lives in kjx_fused_kernels.cuh: fold, segment scans, filter — also used by the
+//    stand-alone kjx_filter)
 //   smoother_reduce (S1) stand-alone version of the smoother fold (reads the stored filter output)
 //   smoother_blockscan (S2) one CTA: reverse scan of block totals; deterministic nlml reduction
 //   smoother_apply  (S3) every thread rebuilds the smoothed state entering its chunk from the right and
@@ -227,30 +220,6 @@ __device__ __forceinline__ void step_site(const SmallArgs<T, D>& a, int64_t k, T
 }
 
 // ------------------------------------------------------------------------------------------------
-// F1
-template <typename T, int KIND>
-__global__ void __launch_bounds__(KJX_BLOCK) filter_reduce_kernel(const SmallArgs<T, BlockDim<KIND>::D> a) {
-  constexpr int D = BlockDim<KIND>::D;
-  using S = FSum<T, D>;
-  __shared__ T smem[S::NS * (KJX_BLOCK / 32 + 1)];
-  const int64_t c = (int64_t)blockIdx.x * KJX_BLOCK + threadIdx.x;
-  const int64_t s0 = c * a.L;
-  const int64_t s1 = (s0 + a.L < a.N) ? s0 + a.L : a.N;
-  T Pinf[D][D]; load_pinf<T, D>(a.prior, Pinf);
-  S mine; fsum_identity<T, D>(mine);
-  for (int64_t k = s0; k < s1; ++k) {
-    T F[D][D];
-    Transition<T, KIND>::eval(a.dt[k], a.prior.lam, F);
-    T yt, R; step_site<T, D>(a, k, yt, R);
-    const bool masked = a.mask ? (a.mask[k] != 0) : false;
-    fsum_fold_step<T, D>(mine, F, Pinf, yt, R, masked);
-  }
-  S excl, total;
-  block_scan_exclusive<S, false, KJX_BLOCK>(mine, excl, total, smem);
-  if (c < a.nchunks) sum_store<S>(a.f_thread_prefix, a.cstride, c, excl);
-  if (threadIdx.x == 0) sum_store<S>(a.f_block_total, a.bstride, blockIdx.x, total);
-}
-
 // F2 / S2: single CTA scan over the per-block totals.
 template <typename S, bool REVERSE>
 __device__ void blockscan_body(const typename SumOps<S>::Scalar* totals, typename SumOps<S>::Scalar* prefix,
@@ -280,13 +249,6 @@ __device__ void blockscan_body(const typename SumOps<S>::Scalar* totals, typenam
     }
   }
   if (threadIdx.x == 0) sum_store<S>(shard_total, 1, 0, total);
-}
-
-template <typename T, int D>
-__global__ void __launch_bounds__(KJX_SCAN_BLOCK) filter_blockscan_kernel(const SmallArgs<T, D> a) {
-  using S = FSum<T, D>;
-  __shared__ T smem[S::NS * (KJX_SCAN_BLOCK / 32 + 1)];
-  blockscan_body<S, false>(a.f_block_total, a.f_block_prefix, a.f_shard_total, a.nblocks, a.bstride, smem);
 }
 
 template <typename T, int D>
@@ -336,78 +298,6 @@ __device__ __forceinline__ T filter_step_body(const SmallArgs<T, D>& a, int64_t 
   if (!masked) filter_update<T, D>(x, smean, svar);  // :292-296 ; masked: keep the prediction (:297-299)
   else lml = T(0);                                   // :300
   return lml;
-}
-
-// F3.  WITH_SMOOTHER: also fold + block-scan the smoother elements of this chunk.
-template <typename T, int KIND, bool WITH_SMOOTHER, bool GAUSS_EP>
-__global__ void __launch_bounds__(KJX_BLOCK) filter_apply_kernel(const SmallArgs<T, BlockDim<KIND>::D> a) {
-  constexpr int D = BlockDim<KIND>::D;
-  using FS = FSum<T, D>;
-  using SS = SSum<T, D>;
-  __shared__ T smem[SS::NS * (KJX_BLOCK / 32 + 1)];
-  __shared__ T red[KJX_BLOCK / 32];
-  const int64_t c = (int64_t)blockIdx.x * KJX_BLOCK + threadIdx.x;
-  const int64_t s0 = c * a.L;
-  const int64_t s1 = (s0 + a.L < a.N) ? s0 + a.L : a.N;
-  T Pinf[D][D]; load_pinf<T, D>(a.prior, Pinf);
-  SS acc; ssum_identity<T, D>(acc);
-  T nl = T(0);
-  if (s0 < s1) {
-    FiltState<T, D> x; load_state<T, D>(a.f_state_in, x);
-    { FS bp; sum_load<FS>(a.f_block_prefix, a.bstride, blockIdx.x, bp); fsum_apply<T, D>(bp, x); }
-    { FS tp; sum_load<FS>(a.f_thread_prefix, a.cstride, c, tp); fsum_apply<T, D>(tp, x); }
-    T F[D][D];
-    Transition<T, KIND>::eval(a.dt[s0], a.prior.lam, F);
-    filter_predict<T, D>(F, Pinf, x);                // sde_gp.py:276-278
-    for (int64_t k = s0; k < s1; ++k) {
-      T smean, svar;
-      nl += filter_step_body<T, D, GAUSS_EP>(a, k, x, false, smean, svar);
-      if (a.filt_mean) store_state<T, D>(a.filt_mean, a.filt_cov, k, x);
-      if (a.out_site_mean) { a.out_site_mean[k] = smean; a.out_site_var[k] = svar; }
-      const bool has_next = (k + 1 < a.N) || !a.is_last_shard;
-      if (has_next) {
-        const T dtn = (k + 1 < a.N) ? a.dt[k + 1] : a.dt_next;
-        Transition<T, KIND>::eval(dtn, a.prior.lam, F);
-        if (WITH_SMOOTHER) {
-          SmoothGain<T, D> g;
-          smoother_gain<T, D>(F, Pinf, x.m, x.P, g);
-          SS e; ssum_element<T, D>(g, x.m, x.P, e);
-          SS r; ssum_combine<T, D>(acc, e, r); acc = r;
-          // the predicted moments of step k+1 are exactly (m_pred, P_pred) of the gain
-#pragma unroll
-          for (int i = 0; i < D; ++i) {
-            x.m[i] = g.mp[i];
-#pragma unroll
-            for (int j = 0; j < D; ++j) x.P[i][j] = g.Pp[i][j];
-          }
-        } else if (k + 1 < s1) {
-          filter_predict<T, D>(F, Pinf, x);
-        }
-      } else if (WITH_SMOOTHER) {
-        SS e; ssum_terminal<T, D>(x.m, x.P, e);
-        SS r; ssum_combine<T, D>(acc, e, r); acc = r;
-      }
-    }
-  }
-  // per-block log-likelihood sum (fixed order: lanes by shuffle tree, then warps in order)
-  if (a.block_nlml) {
-    T s = nl;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      T t = T(0);
-      for (int w = 0; w < KJX_BLOCK / 32; ++w) t += red[w];
-      a.block_nlml[blockIdx.x] = t;
-    }
-  }
-  if (WITH_SMOOTHER) {
-    SS excl, total;
-    block_scan_exclusive<SS, true, KJX_BLOCK>(acc, excl, total, smem);
-    if (c < a.nchunks) sum_store<SS>(a.s_thread_suffix, a.cstride, c, excl);
-    if (threadIdx.x == 0) sum_store<SS>(a.s_block_total, a.bstride, blockIdx.x, total);
-  }
 }
 
 // S1: smoother fold from the stored filter output (stand-alone kjx_smoother)

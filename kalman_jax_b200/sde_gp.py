@@ -349,6 +349,25 @@ class SDEGP(object):
             site_mean[idx] += self._dev(site_params[0]).reshape(-1, self.func_dim, 1)
             site_cov[idx] = self._dev(site_params[1]).reshape(-1, self.func_dim, self.func_dim)
             site_params = (site_mean, site_cov)
+        if site_params is not None and not return_full and self.dtype == torch.float64:
+            # filter (masked steps predict-only) + smoother marginals as ONE fused scan (kjx_posterior)
+            model = self._model(params, r)
+            y_d, dt_d = self._dev(y), self._dev(dt)
+            N = dt_d.shape[0]
+            mask_d = None
+            if mask is not None:
+                mask_d = torch.as_tensor(np.any(np.asarray(mask).reshape(N, -1), axis=1).astype(np.uint8), device=self.device)
+            sm_in, sv_in = self._dev(site_params[0]), self._dev(site_params[1])
+            pm = torch.empty(N, self.func_dim, 1, dtype=self.dtype, device=self.device)
+            pc = torch.empty(N, self.func_dim, self.func_dim, dtype=self.dtype, device=self.device)
+            ws, _ = _workspace(model, N, self.dtype, self.device)
+            rc = _lib.lib().kjx_posterior_f64(model.ref(), C.c_int64(N), _lib.ptr(dt_d), _lib.ptr(y_d), _lib.ptr(mask_d),
+                                              _lib.ptr(sm_in), _lib.ptr(sv_in), _lib.ptr(pm), _lib.ptr(pc), None, _lib.ptr(ws),
+                                              C.c_size_t(ws.numel()), _stream(self.device))
+            if rc == 0:
+                return pm, pc, (sm_in.reshape(N, self.func_dim, 1), sv_in.reshape(N, self.func_dim, self.func_dim))
+            if rc != -2:                       # anything but "unsupported": a real error
+                _lib.check(rc, "kjx_posterior")
         _, (fm, fP, site_params) = self.kalman_filter(y, dt, params, True, mask, site_params, r)
         _, pm, pc = self.rauch_tung_striebel_smoother(params, fm, fP, dt, True, return_full, None, None, r)
         return pm, pc, site_params
