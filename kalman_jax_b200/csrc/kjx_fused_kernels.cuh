@@ -286,6 +286,7 @@ __global__ void __launch_bounds__(KJX_BLOCK, KJX_R3_MINB) fused_filter_kernel(co
       if (!a.gaussian_init) { vm = load4v<T, VEC>(a.site_mean + k); vr = load4v<T, VEC>(a.site_var + k); }
       uint32_t mk = 0;
       if (!PLAIN && a.mask) mk = (uint32_t)a.mask[k] | ((uint32_t)a.mask[k + 1] << 8) | ((uint32_t)a.mask[k + 2] << 16) | ((uint32_t)a.mask[k + 3] << 24);
+      T logarg = T(1);                      // Gaussian log Z: the four log terms of the group as one log of a product
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         T F[D][D];
@@ -295,13 +296,34 @@ __global__ void __launch_bounds__(KJX_BLOCK, KJX_R3_MINB) fused_filter_kernel(co
         const T smean = a.gaussian_init ? vy.x[j] : vm.x[j], svar = a.gaussian_init ? lik_hyp : vr.x[j];
         const bool masked = !PLAIN && ((mk >> (8 * j)) & 0xff) != 0;
         if (!masked) {
-          nl += GAUSS_EP ? gaussian_moment_match<T>(vy.x[j], pm, pv, lik_hyp).lml   // sde_gp.py:287 (log Z only)
-                         : filter_loglik<T>(a.site, vy.x[j], pm, pv);
-          filter_update<T, D>(x, smean, svar);                              // sde_gp.py:292-296
+          if (GAUSS_EP) {
+            // utils.py:237-240: -(y-m)^2/(s)/2 - log(max(2 pi s, 1e-10))/2 with s = sigma^2 + v.  One reciprocal serves
+            // both this term and the gain when the stored site variance equals sigma^2 (always, after the first EP sweep).
+            const T sv = lik_hyp + pv, r = vy.x[j] - pm;
+            const T rs = T(1) / sv;
+            nl -= T(0.5) * (r * r) * rs;
+            logarg *= max_nan(T(2 * KJX_PI) * sv, T(1e-10));               // each factor >= 1e-10 (or NaN): no sign issue
+            const T S = pv + svar;
+            const T Sinv = (svar == lik_hyp) ? ((S < T(0)) ? qnan<T>() : rs) : inv1(S);          // sde_gp.py:292-294
+            const T innov = smean - pm;
+            T HP[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) HP[i] = x.P[0][i];
+#pragma unroll
+            for (int i = 0; i < D; ++i) x.m[i] += (HP[i] * Sinv) * innov;                     // :295
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+              for (int q = i; q < D; ++q) { const T v = x.P[i][q] - (HP[i] * Sinv) * HP[q]; x.P[i][q] = v; x.P[q][i] = v; }   // :296
+          } else {
+            nl += filter_loglik<T>(a.site, vy.x[j], pm, pv);                // sde_gp.py:287 (log Z only)
+            filter_update<T, D>(x, smean, svar);                            // sde_gp.py:292-296
+          }
         }                                                                   // masked: predict-only, :297-300
         if (PLAIN || fa.store_xf) xf_store<T, D>(xf + (k - s0 + j) * NP * 32, x);
         if (!PLAIN && a.out_site_mean) { a.out_site_mean[k + j] = smean; a.out_site_var[k + j] = svar; }
       }
+      if (GAUSS_EP) nl -= T(0.5) * log(logarg);
     }
     (void)ysrc;
     for (; k < s1; ++k) {
