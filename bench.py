@@ -294,45 +294,71 @@ def main():
     ms_step = ms_total / args.steps
     value = N / (ms_step * 1e-3)
 
-    # ---- end to end: host (pinned) buffers in, sites + nlml back, through the C ABI ----
-    e2e = None
+    # ---- end to end through the C ABI with HOST (pinned) buffers ----
+    # e2e:          one training iteration as SDEGP.run() is used (sde_gp.py:179, once per optimiser step): the
+    #               step's inputs dt, y go host -> device, the result nlml comes back; the site parameters are the
+    #               state the iteration updates (self.sites.site_params) and stay on the device between calls.
+    # e2e_all_host: the same call with the sites as host arrays too (4 arrays up, 2 arrays + nlml down per step).
+    e2e = e2e_all = None
     if not args.no_e2e:
         pin = lambda a: torch.as_tensor(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
         h_dt, h_y, h_sm, h_sv = pin(sh_dt), pin(sh_y), pin(sh_y.copy()), pin(np.full(n_local, 0.5))
         o_sm, o_sv, o_nl = (torch.empty(n_local, dtype=torch.float64).pin_memory(),
                             torch.empty(n_local, dtype=torch.float64).pin_memory(), torch.empty(1, dtype=torch.float64).pin_memory())
+        ke = max(3, min(args.steps, 10))
+
+        def time_e2e(step):
+            for _ in range(2):
+                step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(ke):
+                step()
+            barrier()
+            t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return N * ke / float(t[0])
+
         if world == 1:
             nbytes = C.c_size_t(0)
             _lib.check(_lib.lib().kjx_run_host_scratch_bytes(it.model.ref(), C.c_int64(N), 8, C.byref(nbytes)), "scratch")
             scratch = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
-            def e2e_step():
-                _lib.check(_lib.lib().kjx_run_host_f64(it.model.ref(), C.c_int64(N), _lib.ptr(h_dt), _lib.ptr(h_y), _lib.ptr(h_sm),
-                                                       _lib.ptr(h_sv), _lib.ptr(o_sm), _lib.ptr(o_sv), None, None, _lib.ptr(o_nl),
-                                                       _lib.ptr(scratch), C.c_size_t(nbytes.value), 0,
-                                                       C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "kjx_run_host")
+            def host_call(sm, sv, osm, osv, flags):
+                _lib.check(_lib.lib().kjx_run_host_f64(it.model.ref(), C.c_int64(N), _lib.ptr(h_dt), _lib.ptr(h_y), sm, sv, osm, osv,
+                                                       None, None, _lib.ptr(o_nl), _lib.ptr(scratch), C.c_size_t(nbytes.value),
+                                                       flags, stream), "kjx_run_host")
+
+            def all_host_step():
+                host_call(_lib.ptr(h_sm), _lib.ptr(h_sv), _lib.ptr(o_sm), _lib.ptr(o_sv), 0)
+
+            def resident_step():
+                host_call(None, None, None, None, _lib.FLAG_RESIDENT_SITES)
+            host_call(_lib.ptr(h_sm), _lib.ptr(h_sv), None, None, _lib.FLAG_RESIDENT_INIT)    # sites -> device, once
         else:
-            def e2e_step():
+            def all_host_step():
                 it.dt.copy_(h_dt, non_blocking=True); it.y.copy_(h_y, non_blocking=True)
                 it.site_mean.copy_(h_sm, non_blocking=True); it.site_var.copy_(h_sv, non_blocking=True)
                 nl = it.iteration(reduce_nlml=reduce_nlml)
                 o_sm.copy_(it.site_mean, non_blocking=True); o_sv.copy_(it.site_var, non_blocking=True)
                 o_nl.copy_(nl.reshape(1), non_blocking=True)
                 torch.cuda.synchronize()
-        for _ in range(2):
-            e2e_step()
-        barrier()
-        ke = max(3, min(args.steps, 10))
-        t0 = time.perf_counter()
-        for _ in range(ke):
-            e2e_step()
-        barrier()
-        dt_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(dt_e2e, op=dist.ReduceOp.MAX)
-        e2e = {"value": N * ke / float(dt_e2e[0]), "unit": "time-steps/s", "h2d_bytes_per_step": 4 * 8 * N,
-               "d2h_bytes_per_step": 2 * 8 * N + 8, "steps": ke,
-               "api": "kjx_run_host_f64 (pinned host arrays)" if world == 1 else "pinned copies + sharded C-ABI calls per rank",
+
+            def resident_step():
+                it.dt.copy_(h_dt, non_blocking=True); it.y.copy_(h_y, non_blocking=True)
+                nl = it.iteration(reduce_nlml=reduce_nlml)
+                o_nl.copy_(nl.reshape(1), non_blocking=True)
+                torch.cuda.synchronize()
+        v_all = time_e2e(all_host_step)
+        e2e_all = {"value": v_all, "unit": "time-steps/s", "h2d_bytes_per_step": 4 * 8 * N, "d2h_bytes_per_step": 2 * 8 * N + 8,
+                   "steps": ke, "nlml": float(o_nl[0]), "api": "as e2e, with the site parameters passed and returned as host arrays too"}
+        v_res = time_e2e(resident_step)
+        e2e = {"value": v_res, "unit": "time-steps/s", "h2d_bytes_per_step": 2 * 8 * N, "d2h_bytes_per_step": 8, "steps": ke,
+               "api": ("kjx_run_host_f64" if world == 1 else "pinned copies + sharded C-ABI calls per rank") +
+                      ": dt, y from pinned host memory every step, nlml read back; the site parameters (the state the "
+                      "iteration updates, self.sites.site_params) stay on the device between iterations",
                "nlml": float(o_nl[0])}
 
     def finish():
@@ -380,6 +406,7 @@ def main():
     }
     if e2e:
         line["e2e"] = e2e
+        line["e2e_all_host"] = e2e_all
     if not args.no_cpu:
         lib = cpu_oracle_lib()
         n_s = 1 << 22

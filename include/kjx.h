@@ -115,6 +115,12 @@ typedef struct kjx_model {
 #define KJX_FLAG_SEQUENTIAL 1u   /* force the one-thread-chain sequential kernels (reference order) */
 #define KJX_FLAG_RETURN_FULL 2u  /* smoother: write the full state posterior [N,d],[N,d,d]          */
 #define KJX_FLAG_NO_SITE_UPDATE 4u /* kjx_run: smoother pass does not update the sites              */
+#define KJX_FLAG_RESIDENT_SITES 8u /* kjx_run_host: the site parameters are iteration state that lives in
+                                    * dev_scratch: read the ones the previous call left there (site_*_host
+                                    * may be NULL; if given they are uploaded first) and keep the new ones
+                                    * there (new_site_*_host may be NULL = no copy back)                   */
+#define KJX_FLAG_RESIDENT_INIT 16u /* kjx_run_host: first call of such a sequence: sites come from the host
+                                    * pointers (NULL = no sites yet, sde_gp.py:287), new sites stay resident */
 
 int kjx_version(void);
 const char* kjx_status_string(int status);
@@ -225,7 +231,11 @@ int kjx_smoother_apply_f64(const kjx_model_t* m, int64_t N, const double* dt, co
  * HOST pointer (pinned memory for full PCIe speed).  Inputs are copied to the device, the fused
  * filter/smoother/site-update runs, new sites (+ optional posterior marginals) and nlml are copied back;
  * the call returns after the stream has drained.  dev_scratch: caller-owned device memory of at least
- * kjx_run_host_scratch_bytes() bytes (holds the staged arrays, the filter output and the workspace). -- */
+ * kjx_run_host_scratch_bytes() bytes (holds the staged arrays, the filter output and the workspace).
+ * A training loop (sde_gp.py:179 called once per optimiser step) only needs nlml back: with
+ * KJX_FLAG_RESIDENT_INIT on the first call and KJX_FLAG_RESIDENT_SITES afterwards the site parameters — the
+ * state the iteration updates, self.sites.site_params in the reference — stay in dev_scratch between calls and
+ * only dt, y go up and nlml comes down; pass new_site_*_host on the call whose sites you want to read. -- */
 int kjx_run_host_scratch_bytes(const kjx_model_t* m, int64_t N, int dtype_bytes, size_t* bytes);
 int kjx_run_host_f64(const kjx_model_t* m, int64_t N, const double* dt_host, const double* y_host,
                      const double* site_mean_host /*?*/, const double* site_cov_host /*?*/,

@@ -17,7 +17,8 @@ KJX_MAX_CUBATURE = 32
 BLOCK_MATERN32, BLOCK_MATERN52, BLOCK_QP_MATERN32 = 1, 2, 3
 LIK_GAUSSIAN, LIK_BERNOULLI_PROBIT, LIK_BERNOULLI_LOGIT, LIK_POISSON_EXP, LIK_POISSON_LOGISTIC = 1, 2, 3, 4, 5
 INF_EP, INF_EEP, INF_SLEP, INF_VI = 1, 2, 3, 4
-FLAG_SEQUENTIAL, FLAG_RETURN_FULL, FLAG_NO_SITE_UPDATE = 1, 2, 4
+FLAG_SEQUENTIAL, FLAG_RETURN_FULL, FLAG_NO_SITE_UPDATE, FLAG_RESIDENT_SITES, FLAG_RESIDENT_INIT = 1, 2, 4, 8, 16
+OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_CUDA = 0, -1, -2, -3, -4
 
 
 class KjxBlock(C.Structure):

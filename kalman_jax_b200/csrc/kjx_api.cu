@@ -569,9 +569,10 @@ template <typename T> int generic_launch_filter(const GenArgs<T>& g, cudaStream_
 template <typename T> int generic_launch_smoother(const GenArgs<T>& g, T* gains, cudaStream_t st) {
   const size_t smem = g.gscratch ? 0 : generic_smoother_smem<T>(g.d);
   // 1. all RTS gains, parallel over time (they depend on the filtered moments only)
-  KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_gain_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t gsmem = g.gscratch ? 0 : generic_gain_smem<T>(g.d);
+  KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_gain_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
   const unsigned grid = (unsigned)std::min<int64_t>(g.N, KJX_GEN_GAIN_GRID);
-  generic_gain_kernel<T><<<grid, KJX_GEN_THREADS, smem, st>>>(g, gains);
+  generic_gain_kernel<T><<<grid, KJX_GEN_THREADS, gsmem, st>>>(g, gains);
   // 2. the backward recursion (two d^3 products per step), every chunk concurrently, reference order inside a chunk
   KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_smoother_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   generic_smoother_kernel<T><<<g.nchunks, KJX_GEN_THREADS, smem, st>>>(g, gains);
@@ -953,10 +954,13 @@ int kjx_run_host_f64(const kjx_model_t* m, int64_t N, const double* dt_host, con
                      const double* site_mean_host, const double* site_cov_host, double* new_site_mean_host,
                      double* new_site_cov_host, double* post_mean_host, double* post_var_host, double* nlml_host,
                      void* dev_scratch, size_t dev_scratch_bytes, uint32_t flags, kjx_stream_t stream) {
-  if (!model_basic_ok(m) || N <= 0 || !dt_host || !y_host || !new_site_mean_host || !new_site_cov_host || !nlml_host || !dev_scratch)
-    return KJX_ERR_INVALID_ARG;
+  const bool resident = (flags & KJX_FLAG_RESIDENT_SITES) != 0;
+  if (!model_basic_ok(m) || N <= 0 || !dt_host || !y_host || !nlml_host || !dev_scratch) return KJX_ERR_INVALID_ARG;
   if ((site_mean_host == nullptr) != (site_cov_host == nullptr)) return KJX_ERR_INVALID_ARG;
+  if ((new_site_mean_host == nullptr) != (new_site_cov_host == nullptr)) return KJX_ERR_INVALID_ARG;
   if ((post_mean_host == nullptr) != (post_var_host == nullptr)) return KJX_ERR_INVALID_ARG;
+  const bool keep = (flags & (KJX_FLAG_RESIDENT_SITES | KJX_FLAG_RESIDENT_INIT)) != 0;
+  if (!new_site_mean_host && !keep) return KJX_ERR_INVALID_ARG;         // the new sites must go somewhere
   size_t need = 0, ws_bytes = 0;
   int rc = kjx_run_host_scratch_bytes(m, N, 8, &need);
   if (rc != KJX_OK) return rc;
@@ -978,16 +982,25 @@ int kjx_run_host_f64(const kjx_model_t* m, int64_t N, const double* dt_host, con
     KJX_CUDA_CHECK(cudaMemcpyAsync(sm, site_mean_host, n * 8, cudaMemcpyHostToDevice, st));
     KJX_CUDA_CHECK(cudaMemcpyAsync(sv, site_cov_host, n * 8, cudaMemcpyHostToDevice, st));
   }
-  rc = kjx_run_f64(m, N, dt, y, site_mean_host ? sm : nullptr, site_mean_host ? sv : nullptr, fm, fP, nsm, nsv,
-                   post_mean_host ? pm : nullptr, post_mean_host ? pv : nullptr, nlml, ws, ws_bytes, flags, stream);
+  // sites on the device: the ones just uploaded, or (resident) the ones the previous call left in the scratch
+  const bool have_sites = site_mean_host != nullptr || resident;
+  rc = kjx_run_f64(m, N, dt, y, have_sites ? sm : nullptr, have_sites ? sv : nullptr, fm, fP, nsm, nsv,
+                   post_mean_host ? pm : nullptr, post_mean_host ? pv : nullptr, nlml, ws, ws_bytes,
+                   flags & ~(uint32_t)(KJX_FLAG_RESIDENT_SITES | KJX_FLAG_RESIDENT_INIT), stream);
   if (rc != KJX_OK) return rc;
-  KJX_CUDA_CHECK(cudaMemcpyAsync(new_site_mean_host, nsm, n * 8, cudaMemcpyDeviceToHost, st));
-  KJX_CUDA_CHECK(cudaMemcpyAsync(new_site_cov_host, nsv, n * 8, cudaMemcpyDeviceToHost, st));
+  if (new_site_mean_host) {
+    KJX_CUDA_CHECK(cudaMemcpyAsync(new_site_mean_host, nsm, n * 8, cudaMemcpyDeviceToHost, st));
+    KJX_CUDA_CHECK(cudaMemcpyAsync(new_site_cov_host, nsv, n * 8, cudaMemcpyDeviceToHost, st));
+  }
   if (post_mean_host) {
     KJX_CUDA_CHECK(cudaMemcpyAsync(post_mean_host, pm, n * 8, cudaMemcpyDeviceToHost, st));
     KJX_CUDA_CHECK(cudaMemcpyAsync(post_var_host, pv, n * 8, cudaMemcpyDeviceToHost, st));
   }
   KJX_CUDA_CHECK(cudaMemcpyAsync(nlml_host, nlml, 8, cudaMemcpyDeviceToHost, st));
+  if (keep) {                                                           // the new sites are the next call's sites
+    KJX_CUDA_CHECK(cudaMemcpyAsync(sm, nsm, n * 8, cudaMemcpyDeviceToDevice, st));
+    KJX_CUDA_CHECK(cudaMemcpyAsync(sv, nsv, n * 8, cudaMemcpyDeviceToDevice, st));
+  }
   KJX_CUDA_CHECK(cudaStreamSynchronize(st));
   return KJX_OK;
 }

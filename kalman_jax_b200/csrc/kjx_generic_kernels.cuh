@@ -476,24 +476,47 @@ template <typename T, int TPC> __device__ void chol_substitute(int d, const T* L
 
 // RTS gains, embarrassingly parallel over time: Gt[n] = solve(P_pred[n], A[n+1] Pf[n]) depends only on the FILTERED
 // moments (sde_gp.py:351-359), so a grid of CTAs computes them all before the (sequential) backward recursion.
+template <typename T> size_t generic_gain_smem(int d) {
+  return (size_t)(2 * d * d + 4 * d + d + 16) * sizeof(T) + (size_t)d * sizeof(int) + 16 * 8;
+}
+
+// Working set: two d x d tiles in shared memory (56 KB at d = 59, so four CTAs share an SM — the factorisation and
+// substitutions are barrier-latency-bound); Pf and Pinf are read straight from global / L1.
 template <typename T>
 __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_gain_kernel(const GenArgs<T> g, T* __restrict__ Gt_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemCarver<T> sc(g.gscratch ? g.gscratch + (size_t)blockIdx.x * g.gscratch_stride : smem_raw);
   const int d = g.d, dd = d * d;
-  T* Pf = sc.take(dd); T* Pp = sc.take(dd); T* Gt = sc.take(dd); T* W = sc.take(dd); T* Pinf = sc.take(dd);
+  T* W = sc.take(dd); T* Gt = sc.take(dd);
   T* vals = sc.take(4 * d); T* rinv = sc.take(d);
   int* c0n = sc.take_int(d);
-  for (int e = threadIdx.x; e < dd; e += blockDim.x) Pinf[e] = (T)g.Pinf[e];
-  __syncthreads();
   for (int64_t n = blockIdx.x; n < g.N; n += gridDim.x) {
     build_rows<T>(g.disc, d, (n + 1 < g.N) ? g.dt[n + 1] : T(0), vals, c0n);        // :337, :351
-    for (int e = threadIdx.x; e < dd; e += blockDim.x) { const T v = g.filt_cov_in[n * (int64_t)dd + e]; Pf[e] = v; W[e] = v - Pinf[e]; }
+    const T* Pf = g.filt_cov_in + n * (int64_t)dd;
     __syncthreads();
-    rows_left<T>(d, vals, c0n, Pf, Gt);                                             // Gt <- A Pf        (:353)
-    rows_left<T>(d, vals, c0n, W, Pp);                                              // Pp <- A (Pf - Pinf)
+    for (int e = threadIdx.x; e < dd; e += blockDim.x) {                            // Gt <- A (Pf - Pinf)
+      const int i = e / d, j = e % d;
+      const int c0 = c0n[i] & 0xffffff, nn = c0n[i] >> 24;
+      T s = T(0);
+      for (int q = 0; q < nn; ++q) s += vals[i * 4 + q] * (Pf[(c0 + q) * d + j] - (T)g.Pinf[(c0 + q) * d + j]);
+      Gt[e] = s;
+    }
     __syncthreads();
-    rows_right_add<T>(d, vals, c0n, Pp, Pinf, W);                                   // W  <- P_pred       (:354)
+    for (int e = threadIdx.x; e < dd; e += blockDim.x) {                            // W <- P_pred = . A^T + Pinf   (:354)
+      const int i = e / d, j = e % d;
+      const int c0 = c0n[j] & 0xffffff, nn = c0n[j] >> 24;
+      T s = T(0);
+      for (int q = 0; q < nn; ++q) s += Gt[i * d + c0 + q] * vals[j * 4 + q];
+      W[e] = s + (T)g.Pinf[e];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < dd; e += blockDim.x) {                            // Gt <- A Pf                  (:353)
+      const int i = e / d, j = e % d;
+      const int c0 = c0n[i] & 0xffffff, nn = c0n[i] >> 24;
+      T s = T(0);
+      for (int q = 0; q < nn; ++q) s += vals[i * 4 + q] * Pf[(c0 + q) * d + j];
+      Gt[e] = s;
+    }
     __syncthreads();
     chol_inplace<T>(d, W, rinv);                                                    // utils.py:29
     chol_substitute<T, 4>(d, W, rinv, Gt);                                          // :359, utils.py:30

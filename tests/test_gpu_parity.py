@@ -315,6 +315,43 @@ def test_host_buffer_entry_point_matches_device_path():
     assert np.array_equal(nsv.numpy(), _np(model.sites.site_params[1]).reshape(-1))
 
 
+def test_host_buffer_entry_point_resident_sites():
+    """Three iterations with the sites kept in the device scratch between calls (only dt, y up and nlml down)
+    reproduce three SDEGP.run() iterations; the sites are read back on the last call only."""
+    import ctypes as C
+    from kalman_jax_b200 import _lib
+    from kalman_jax_b200.sde_gp import _Model
+    kjx = _kjx()
+    N = 30_001
+    t, y = synth(N)
+    model = kjx.SDEGP(kjx.priors.Matern32(1.0, 5.0), kjx.likelihoods.Gaussian(0.5), t, y,
+                      approx_inf=kjx.approximate_inference.EP(power=0.5, damping=0.7))
+    want = [model.run(compute_grad=False)[0] for _ in range(3)]
+    cm = _Model(model.prior, model.likelihood, model.sites)
+    nbytes = C.c_size_t(0)
+    _lib.check(_lib.lib().kjx_run_host_scratch_bytes(cm.ref(), C.c_int64(N), 8, C.byref(nbytes)), "scratch")
+    scratch = torch.empty(nbytes.value, dtype=torch.uint8, device="cuda")
+    pin = lambda a: torch.as_tensor(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
+    dt_h, y_h = pin(model.dt), pin(model.y[:, 0])
+    nsm, nsv, nl = (torch.empty(N, dtype=torch.float64).pin_memory(), torch.empty(N, dtype=torch.float64).pin_memory(),
+                    torch.empty(1, dtype=torch.float64).pin_memory())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    got = []
+    for it, (flags, out) in enumerate([(_lib.FLAG_RESIDENT_INIT, False), (_lib.FLAG_RESIDENT_SITES, False),
+                                       (_lib.FLAG_RESIDENT_SITES, True)]):
+        _lib.check(_lib.lib().kjx_run_host_f64(cm.ref(), C.c_int64(N), _lib.ptr(dt_h), _lib.ptr(y_h), None, None,
+                                               _lib.ptr(nsm) if out else None, _lib.ptr(nsv) if out else None, None, None,
+                                               _lib.ptr(nl), _lib.ptr(scratch), C.c_size_t(nbytes.value), flags, st), "kjx_run_host")
+        got.append(float(nl[0]))
+    assert got == want
+    assert np.array_equal(nsm.numpy(), _np(model.sites.site_params[0]).reshape(-1))
+    assert np.array_equal(nsv.numpy(), _np(model.sites.site_params[1]).reshape(-1))
+    # without a resident flag the new sites must have a destination
+    rc = _lib.lib().kjx_run_host_f64(cm.ref(), C.c_int64(N), _lib.ptr(dt_h), _lib.ptr(y_h), None, None, None, None, None, None,
+                                     _lib.ptr(nl), _lib.ptr(scratch), C.c_size_t(nbytes.value), 0, st)
+    assert rc == _lib.ERR_INVALID_ARG
+
+
 @pytest.mark.parametrize("world", [2, 3, 8])
 @pytest.mark.parametrize("prior_name", ["Matern52", "Matern32"])
 def test_time_sharded_iteration_matches_oracle(world, prior_name):
