@@ -572,7 +572,7 @@ template <typename T> int generic_launch_smoother(const GenArgs<T>& g, T* gains,
   const size_t gsmem = g.gscratch ? 0 : generic_gain_smem<T>(g.d);
   KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_gain_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
   const unsigned grid = (unsigned)std::min<int64_t>(g.N, KJX_GEN_GAIN_GRID);
-  generic_gain_kernel<T><<<grid, KJX_GEN_THREADS, gsmem, st>>>(g, gains);
+  generic_gain_kernel<T><<<grid, KJX_GEN_GAIN_THREADS, gsmem, st>>>(g, gains);
   // 2. the backward recursion (two d^3 products per step), every chunk concurrently, reference order inside a chunk
   KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_smoother_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   generic_smoother_kernel<T><<<g.nchunks, KJX_GEN_THREADS, smem, st>>>(g, gains);

@@ -1,32 +1,40 @@
-// kjx_generic_kernels.cuh — filter / smoother for a general block-diagonal prior of state dimension d <= 64
-// (Sum of Matern / quasi-periodic components, spatio-temporal Matern-5/2 with up to 21 inducing points).
+// kjx_generic_kernels.cuh — filter / smoother for a general block-diagonal prior (Sum of Matern / quasi-periodic
+// components, spatio-temporal Matern-5/2): state dimension d <= 64 in shared memory, d <= 256 in per-CTA global scratch.
 //
-// One CTA owns one time series and walks it in reference order (sde_gp.py:271-306 and :349-379); the d x d
-// matrices live in shared memory (6 d^2 scalars in the smoother: 167 KB at d = 59) and the threads of the CTA
-// share the O(d^2) / O(d^3) work of each step:
-//   * A(dt) is never formed densely: every row of the block-diagonal transition has at most 4 non-zeros
-//     (transition_row, kjx_elementwise_kernels.cuh), so A X A^T costs 8 d^2 flops instead of 4 d^3;
-//   * the update is rank one (f = 1): K = P H^T / S, P -= K (H P);
-//   * the RTS gain is the reference's Cholesky solve (utils.py:25-30): right-looking factorisation in place,
-//     then forward/backward substitution with one thread per right-hand side.
 // Parallel in time like the d <= 3 path, at CTA granularity: the series is cut into chunks of consecutive steps, one
 // CTA per chunk.  generic_fold_kernel reduces every chunk to a filter scan element (A,b,C,eta,J) — O(d^2) per step
 // because A(dt) is block-sparse and the update is rank one —, generic_boundary_kernel turns the elements into the
 // filtered state entering every chunk and the information (eta, J) of everything after it (two CTAs: prefix, suffix),
-// and then the filter / smoother kernels below run all chunks concurrently, each in reference order inside its
-// chunk.  With one chunk (short series, or sites that must be initialised from the predictive) it is the plain
-// sequential walk.  A multi-CTA tiled path for d > 64 is the next step, see DESIGN.md.
+// and then the filter / smoother kernels run all chunks concurrently, each in reference order inside its chunk
+// (sde_gp.py:271-306 and :349-379).  The RTS gains only depend on filtered moments, so generic_gain_kernel computes
+// all of them in parallel before the backward recursion.  With one chunk (short series, or sites that must be
+// initialised from the predictive) it is the plain sequential walk.
+//
+// How a CTA (8 warps) spends a step:
+//   * A(dt) is never formed densely: every row of the block-diagonal transition has at most 4 non-zeros
+//     (transition_row, kjx_elementwise_kernels.cuh), so A X A^T costs 8 d^2 flops instead of 4 d^3;
+//   * the update is rank one (f = 1): K = P H^T / S, P -= K (H P);
+//   * the dense d^3 work — the two products of the RTS update, the trailing updates of the blocked Cholesky /
+//     triangular solves of the gain (utils.py:25-30), the products of the boundary walk — goes through the FP64
+//     tensor pipe: mma.sync.m8n8k4.f64 on 16 x 16 blocks per warp (gemm_cta).  Measured on this B200 the DMMA path
+//     sustains 37 TFLOP/s against 34 TFLOP/s for plain DFMA (scripts/micro/dmma_rate.cu) with 1/8 of the issue slots;
+//   * matrices are stored row-major with a padded leading dimension ld = 4 (mod 8) so that both the row-wise and the
+//     column-wise 8 x 4 fragment loads hit every bank exactly twice (conflict-free), and with zero padding up to the
+//     next multiple of 4 so the k loop needs no tail;
+//   * element-wise passes use (row = warp, column = lane) loops: no integer division anywhere in a step.
 #pragma once
 #include <stdint.h>
+#include <type_traits>
 #include "kjx_elementwise_kernels.cuh"
 #include "kjx_small_math.cuh"
 
 namespace kjx {
 
-constexpr int KJX_GEN_DMAX = 64;          // d x d working set (6 d^2 scalars) fits one SM's shared memory up to here
+constexpr int KJX_GEN_DMAX = 64;          // the working set (6 padded d x d tiles) fits one SM's shared memory up to here
 constexpr int KJX_GEN_DMAX_GLOBAL = 256;  // above it the same kernels keep their matrices in per-CTA global scratch
-                                          // (L2-resident; correct but untuned: the tiled multi-CTA path is future work)
-constexpr int KJX_GEN_THREADS = 256;
+constexpr int KJX_GEN_THREADS = 512;      // fold / boundary / filter / smoother: one CTA per SM, 16 warps to hide the latencies
+constexpr int KJX_GEN_GAIN_THREADS = 256; // gain kernel: several smaller CTAs per SM
+constexpr int KJX_GEN_WARPS = KJX_GEN_THREADS / 32;   // most warps any generic kernel runs with
 
 template <typename T> struct GenArgs {
   DiscArgs disc;           // block structure of A(dt)
@@ -44,7 +52,7 @@ template <typename T> struct GenArgs {
   int return_full; int update_sites;
   // chunked scan (one CTA per chunk)
   int64_t chunk_len; int nchunks;
-  T* sum;                  // [nchunks][3 d^2 + 2 d]  chunk elements: A | C | J | b | eta
+  T* sum;                  // [nchunks][3 d^2 + 2 d]  chunk elements: A | C | J | b | eta   (dense, leading dimension d)
   T* st_m; T* st_P;        // [nchunks][d], [nchunks][d^2]  filtered state entering every chunk
   T* in_eta; T* in_J;      // [nchunks][d], [nchunks][d^2]  information of everything after every chunk
   T* chunk_nlml;           // [nchunks]
@@ -52,49 +60,26 @@ template <typename T> struct GenArgs {
   size_t gscratch_stride;
 };
 
-// rows of A(dt) for all d rows: vals[d][4], c0n[d] = first column | nnz << 24
-template <typename T>
-__device__ __forceinline__ void build_rows(const DiscArgs& da, int d, T dt, T* vals, int* c0n) {
-  for (int r = threadIdx.x; r < d; r += blockDim.x) {
-    int c0, nnz; T v[4] = {T(0), T(0), T(0), T(0)};
-    transition_row<T>(da, r, dt, c0, nnz, v);
-    c0n[r] = c0 | (nnz << 24);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) vals[r * 4 + q] = v[q];
-  }
+// padded tile layout of a d x d matrix inside a kernel's working set
+struct GenLayout {
+  int d;     // logical size
+  int ld;    // leading dimension: >= round_up(d, 4) and = 4 (mod 8)
+  int mp;    // rows that fragment loads may touch: round_up(d, 16)
+  int msz;   // scalars per tile (mp * ld + a tail for column over-reads of the last row)
+};
+__host__ __device__ inline GenLayout gen_layout(int d) {
+  GenLayout L;
+  L.d = d;
+  const int kp = (d + 3) & ~3;
+  L.ld = kp + ((kp & 7) ? 0 : 4);
+  L.mp = (d + 15) & ~15;
+  L.msz = L.mp * L.ld + 16;
+  return L;
 }
-// out = A x
-template <typename T>
-__device__ __forceinline__ void rows_matvec(int d, const T* vals, const int* c0n, const T* x, T* out) {
-  for (int i = threadIdx.x; i < d; i += blockDim.x) {
-    const int c0 = c0n[i] & 0xffffff, nn = c0n[i] >> 24;
-    T s = T(0);
-    for (int q = 0; q < nn; ++q) s += vals[i * 4 + q] * x[c0 + q];
-    out[i] = s;
-  }
-}
-// Y = A X   (X, Y: d x d row-major)
-template <typename T>
-__device__ __forceinline__ void rows_left(int d, const T* vals, const int* c0n, const T* X, T* Y) {
-  for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
-    const int i = e / d, j = e % d;
-    const int c0 = c0n[i] & 0xffffff, nn = c0n[i] >> 24;
-    T s = T(0);
-    for (int q = 0; q < nn; ++q) s += vals[i * 4 + q] * X[(c0 + q) * d + j];
-    Y[e] = s;
-  }
-}
-// Z = Y A^T + Pinf
-template <typename T>
-__device__ __forceinline__ void rows_right_add(int d, const T* vals, const int* c0n, const T* Y, const T* Pinf, T* Z) {
-  for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
-    const int i = e / d, j = e % d;
-    const int c0 = c0n[j] & 0xffffff, nn = c0n[j] >> 24;
-    T s = T(0);
-    for (int q = 0; q < nn; ++q) s += Y[i * d + c0 + q] * vals[j * 4 + q];
-    Z[e] = s + Pinf[e];
-  }
-}
+
+#define KJX_GEN_ROWS(i, n) for (int i = (int)(threadIdx.x >> 5); i < (n); i += (int)(blockDim.x >> 5))
+#define KJX_GEN_COLS(j, n) for (int j = (int)(threadIdx.x & 31); j < (n); j += 32)
+#define KJX_GEN_VEC(i, n) for (int i = (int)threadIdx.x; i < (n); i += (int)blockDim.x)
 
 // shared-memory carve-up helper
 template <typename T> struct SmemCarver {
@@ -104,244 +89,573 @@ template <typename T> struct SmemCarver {
   __device__ int* take_int(int n) { int* r = reinterpret_cast<int*>(p); p += ((size_t)n * sizeof(int) + 15) / 16 * 16; return r; }
 };
 
-template <typename T> size_t generic_filter_smem(int d) {
-  return (size_t)(3 * d * d + 4 * d + 5 * d + 16) * sizeof(T) + (size_t)d * sizeof(int) + 16 * 12;
+// rows of A(dt) for all d rows: vals[d][4], c0n[d] = first column | nnz << 24
+template <typename T>
+__device__ __forceinline__ void build_rows(const DiscArgs& da, int d, T dt, T* vals, int* c0n) {
+  KJX_GEN_VEC(r, d) {
+    int c0, nnz; T v[4] = {T(0), T(0), T(0), T(0)};
+    transition_row<T>(da, r, dt, c0, nnz, v);
+    c0n[r] = c0 | (nnz << 24);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) vals[r * 4 + q] = v[q];
+  }
 }
-template <typename T> size_t generic_smoother_smem(int d) {
-  return (size_t)(6 * d * d + 4 * d + 7 * d + 16) * sizeof(T) + (size_t)(d + 4) * sizeof(int) + 16 * 16;
+// Element-wise pass over a d x d tile with (row = warp, column = lane): every thread first issues the loads of up to 4
+// rows, then stores, so the loads are in flight together (a plain load/store loop serialises on possible aliasing).
+template <typename T, class LoadF, class StoreF>
+__device__ __forceinline__ void tile_map(int d, LoadF load, StoreF store) {
+  constexpr int U = 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int i0 = warp; i0 < d; i0 += U * nw)
+    for (int j = lane; j < d; j += 32) {
+      T v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) { const int i = i0 + u * nw; if (i < d) v[u] = load(i, j); }
+#pragma unroll
+      for (int u = 0; u < U; ++u) { const int i = i0 + u * nw; if (i < d) store(i, j, v[u]); }
+    }
+}
+// out = A x
+template <typename T>
+__device__ __forceinline__ void rows_matvec(int d, const T* vals, const int* c0n, const T* x, T* out) {
+  KJX_GEN_VEC(i, d) {
+    const int c0 = c0n[i] & 0xffffff, nn = c0n[i] >> 24;
+    T s = T(0);
+    for (int q = 0; q < nn; ++q) s += vals[i * 4 + q] * x[c0 + q];
+    out[i] = s;
+  }
+}
+// Y = A (X - S)     (S may be null; ldx / lds: leading dimensions of X and S, Y uses L.ld)
+template <typename T, typename TS>
+__device__ __forceinline__ void rows_left(const GenLayout& L, const T* vals, const int* c0n, const T* X, int ldx,
+                                          const TS* S, int lds, T* Y) {
+  constexpr int U = 4;
+  const int d = L.d, ld = L.ld, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int i0 = warp; i0 < d; i0 += U * nw) {
+    int c0[U], nn[U]; T v[U][4];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * nw;
+      nn[u] = -1; c0[u] = 0;
+      if (i < d) {
+        const int c = c0n[i]; c0[u] = c & 0xffffff; nn[u] = c >> 24;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[u][q] = vals[i * 4 + q];
+      }
+    }
+    for (int j = lane; j < d; j += 32) {
+      T s[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        s[u] = T(0);
+        if (nn[u] >= 0) {
+          const T* x = X + c0[u] * ldx + j;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (q < nn[u]) s[u] += v[u][q] * (S ? x[q * ldx] - (T)S[(c0[u] + q) * lds + j] : x[q * ldx]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) if (nn[u] >= 0) Y[(i0 + u * nw) * ld + j] = s[u];
+    }
+  }
+}
+// X <- A X in place: the rows of one diagonal block of A only depend on the same rows of X.  bstart: first rows of the
+// blocks, nblk of them.
+template <typename T>
+__device__ __forceinline__ void rows_left_inplace(const GenLayout& L, const T* vals, const int* c0n, const int* bstart, int nblk, T* X) {
+  const int d = L.d, ld = L.ld, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int b = warp; b < nblk; b += nw) {
+    const int i = bstart[b], nn = c0n[i] >> 24;
+    for (int j = lane; j < d; j += 32) {
+      T x[4], s[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) x[q] = (q < nn) ? X[(i + q) * ld + j] : T(0);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        s[r] = T(0);
+        if (r < nn) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) if (q < nn) s[r] += vals[(i + r) * 4 + q] * x[q];
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) if (r < nn) X[(i + r) * ld + j] = s[r];
+    }
+  }
+}
+// Z = sign * (Y A^T + Pinf) + (Base ? Base : 0)      (ldp: leading dimension of Pinf; Y, Z, Base use L.ld)
+template <typename T, typename TP>
+__device__ __forceinline__ void rows_right_add(const GenLayout& L, const T* vals, const int* c0n, const T* Y, const TP* Pinf, int ldp,
+                                               T* Z, const T* Base = nullptr, T sign = T(1)) {
+  constexpr int U = 4;
+  const int d = L.d, ld = L.ld, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int j = lane; j < d; j += 32) {
+    const int c0 = c0n[j] & 0xffffff, nn = c0n[j] >> 24;
+    T v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = vals[j * 4 + q];
+    for (int i0 = warp; i0 < d; i0 += U * nw) {
+      T s[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * nw;
+        s[u] = T(0);
+        if (i < d) {
+          const T* y = Y + i * ld + c0;
+          T t = T(0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) if (q < nn) t += y[q] * v[q];
+          t += (T)Pinf[i * ldp + j];
+          s[u] = Base ? Base[i * ld + j] + sign * t : sign * t;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) { const int i = i0 + u * nw; if (i < d) Z[i * ld + j] = s[u]; }
+    }
+  }
+}
+// dense [d][d] global <-> padded tile
+template <typename T, typename S>
+__device__ __forceinline__ void load_dense(const GenLayout& L, const S* __restrict__ src, T* dst) {
+  const int d = L.d, ld = L.ld;
+  tile_map<T>(d, [&](int i, int j) { return (T)src[(size_t)i * d + j]; }, [&](int i, int j, T v) { dst[i * ld + j] = v; });
+}
+template <typename T>
+__device__ __forceinline__ void store_dense(const GenLayout& L, const T* src, T* __restrict__ dst) {
+  const int d = L.d, ld = L.ld;
+  tile_map<T>(d, [&](int i, int j) { return src[i * ld + j]; }, [&](int i, int j, T v) { dst[(size_t)i * d + j] = v; });
+}
+template <typename T> __device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// sum_i a[i] b[i] over a warp (every lane gets the result)
+template <typename T> __device__ __forceinline__ T warp_dot(int d, const T* a, const T* b) {
+  T s = T(0);
+  KJX_GEN_COLS(i, d) s += a[i] * b[i];
+  return warp_sum(s);
+}
+// part[w][j] = sum over the rows i = w, w + nwg, ... of h[i] X[i][j], for the nwg warps starting at warp w0 (other warps
+// skip).  Zero entries of h are skipped: H is sparse for Sum priors.
+template <typename T>
+__device__ __forceinline__ void rowvec_partial(const GenLayout& L, const T* h, const T* X, T* part, int w0, int nwg) {
+  const int w = (int)(threadIdx.x >> 5) - w0;
+  if (w < 0 || w >= nwg) return;
+  KJX_GEN_COLS(j, L.d) {
+    T s = T(0);
+    for (int i = w; i < L.d; i += nwg) { const T hi = h[i]; if (hi != T(0)) s += hi * X[i * L.ld + j]; }
+    part[w * L.d + j] = s;
+  }
+}
+template <typename T> __device__ __forceinline__ T partial_total(int d, const T* part, int j, int nwg) {
+  T s = T(0);
+  for (int w = 0; w < nwg; ++w) s += part[w * d + j];
+  return s;
 }
 
 // ------------------------------------------------------------------------------------------------
-// dense d x d products shared by the scan kernels (operands in shared or global memory)
-template <typename T> __device__ __forceinline__ void mm_nn(int d, const T* A, const T* B, T* C) {        // C = A B
-  for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
-    const int i = e / d, j = e % d;
-    T s = T(0);
-    for (int k = 0; k < d; ++k) s += A[i * d + k] * B[k * d + j];
-    C[e] = s;
-  }
+// CTA-wide product on the FP64 tensor pipe.  C(i,j) = sum_k opA(i,k) opB(k,j) for i < m, j < n, k < kk, handed to
+// epi(i, j, value); opA(i,k) = TA ? A[k*ld + i] : A[i*ld + k], opB(k,j) = TB ? B[j*ld + k] : B[k*ld + j].
+// Every warp takes 16 x 16 blocks of C (2 x 2 m8n8k4 tiles: 4 fragment loads feed 4 DMMAs per k-step of 4).
+// Requirements: operands zero (and finite) in the k range [kk, round_up(kk,4)); rows / columns up to the next multiple
+// of 16 readable (their products are discarded).  All threads of the CTA must call; no barrier inside.
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
-template <typename T> __device__ __forceinline__ void mm_nt_add(int d, const T* A, const T* B, const T* S, T* C) {   // C = A B^T + S
-  for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
-    const int i = e / d, j = e % d;
-    T s = S[e];
-    for (int k = 0; k < d; ++k) s += A[i * d + k] * B[j * d + k];
-    C[e] = s;
-  }
-}
-template <typename T> __device__ __forceinline__ void mm_tn_add(int d, const T* A, const T* B, const T* S, T* C) {   // C = A^T B + S
-  for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
-    const int i = e / d, j = e % d;
-    T s = S[e];
-    for (int k = 0; k < d; ++k) s += A[k * d + i] * B[k * d + j];
-    C[e] = s;
+template <typename T, bool TA, bool TB, class Epi>
+__device__ __forceinline__ void gemm_cta(int m, int n, int kk, const T* A, const T* B, int ld, Epi epi) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  if constexpr (std::is_same<T, double>::value) {
+    const int nbn = (n + 15) >> 4, nblk = ((m + 15) >> 4) * nbn;
+    const int r = lane >> 2, q = lane & 3;
+    const int kp = (kk + 3) & ~3;
+    const int astep = TA ? 4 * ld : 4, a8 = TA ? 8 : 8 * ld;
+    const int bstep = TB ? 4 : 4 * ld, b8 = TB ? 8 * ld : 8;
+    for (int blk = warp; blk < nblk; blk += nwarp) {
+      const int bi = (blk / nbn) << 4, bj = (blk % nbn) << 4;
+      const double* ap = TA ? A + q * ld + bi + r : A + (bi + r) * ld + q;
+      const double* bp = TB ? B + (bj + r) * ld + q : B + q * ld + bj + r;
+      double c00a = 0, c00b = 0, c01a = 0, c01b = 0, c10a = 0, c10b = 0, c11a = 0, c11b = 0;
+#pragma unroll 2
+      for (int k = 0; k < kp; k += 4) {
+        const double a0 = ap[0], a1 = ap[a8], b0 = bp[0], b1 = bp[b8];
+        dmma884(c00a, c00b, a0, b0);
+        dmma884(c01a, c01b, a0, b1);
+        dmma884(c10a, c10b, a1, b0);
+        dmma884(c11a, c11b, a1, b1);
+        ap += astep; bp += bstep;
+      }
+      __syncwarp();        // in-place use (C overlapping this block's own operands): all fragment loads done before any store
+      // lane holds C[r][2q], C[r][2q+1] of each 8 x 8 tile
+      const int i0 = bi + r, i1 = bi + 8 + r, j0 = bj + 2 * q, j1 = bj + 8 + 2 * q;
+      if (i0 < m) {
+        if (j0 < n) epi(i0, j0, c00a);
+        if (j0 + 1 < n) epi(i0, j0 + 1, c00b);
+        if (j1 < n) epi(i0, j1, c01a);
+        if (j1 + 1 < n) epi(i0, j1 + 1, c01b);
+      }
+      if (i1 < m) {
+        if (j0 < n) epi(i1, j0, c10a);
+        if (j0 + 1 < n) epi(i1, j0 + 1, c10b);
+        if (j1 < n) epi(i1, j1, c11a);
+        if (j1 + 1 < n) epi(i1, j1 + 1, c11b);
+      }
+    }
+  } else {
+    for (int i = warp; i < m; i += nwarp)
+      for (int j = lane; j < n; j += 32) {
+        T s = T(0);
+        for (int k = 0; k < kk; ++k) s += (TA ? A[k * ld + i] : A[i * ld + k]) * (TB ? B[j * ld + k] : B[k * ld + j]);
+        epi(i, j, s);
+      }
   }
 }
 
-// Solve M X = R in place by Gaussian elimination with partial pivoting (M: d x d, destroyed; R: d x nr, leading
-// dimension ldr, overwritten by X).  Used on I + P J / I + J C, whose eigenvalues are real and >= 1 but which are not
-// symmetric, so no Cholesky.  `piv` is one int of shared memory.
-template <typename T> __device__ void lu_solve(int d, T* M, T* R, int nr, int ldr, int* piv) {
-  for (int k = 0; k < d; ++k) {
-    if (threadIdx.x < 32) {
-      T best = T(-1); int bi = k;
-      for (int i = k + (int)threadIdx.x; i < d; i += 32) { const T v = fabs(M[i * d + k]); if (v > best) { best = v; bi = i; } }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const T ob = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-      }
-      if (threadIdx.x == 0) *piv = bi;
-    }
-    __syncthreads();
-    const int p = *piv;
-    if (p != k) {
-      for (int j = threadIdx.x; j < d + nr; j += blockDim.x) {
-        T* a = (j < d) ? &M[k * d + j] : &R[k * ldr + (j - d)];
-        T* b = (j < d) ? &M[p * d + j] : &R[p * ldr + (j - d)];
-        const T t = *a; *a = *b; *b = t;
-      }
-    }
-    __syncthreads();
-    const T pinv = T(1) / M[k * d + k];
-    for (int i = k + 1 + threadIdx.x; i < d; i += blockDim.x) M[i * d + k] *= pinv;
-    __syncthreads();
-    const int rem = d - k - 1, wid = rem + nr;
-    for (int e = threadIdx.x; e < rem * wid; e += blockDim.x) {
-      const int i = k + 1 + e / wid, jj = e % wid;
-      const T l = M[i * d + k];
-      if (jj < rem) M[i * d + k + 1 + jj] -= l * M[k * d + k + 1 + jj];
-      else R[i * ldr + (jj - rem)] -= l * R[k * ldr + (jj - rem)];
-    }
-    __syncthreads();
-  }
-  for (int i = d - 1; i >= 0; --i) {
-    const T dinv = T(1) / M[i * d + i];
-    for (int c = threadIdx.x; c < nr; c += blockDim.x) {
-      T v = R[i * ldr + c];
-      for (int k = i + 1; k < d; ++k) v -= M[i * d + k] * R[k * ldr + c];
-      R[i * ldr + c] = v * dinv;
-    }
-    __syncthreads();
-  }
-}
-
-// (m, P) <- smoothed / propagated through the information (eta, J):  X = (I + P J)^-1 [P | m + P eta]
-// on return R (d x (d+1), ld d+1) holds [(I+PJ)^-1 P | (I+PJ)^-1 (m + P eta)].   M, R: scratch (d^2, d^2 + d)
+// ------------------------------------------------------------------------------------------------
+// Solve M X = [R | rv] by Gauss-Jordan elimination with partial pivoting (M: d x d, destroyed; R: d x d and rv: d,
+// destroyed; X, xu receive the solution).  Used on I + P J / I + J C, whose eigenvalues are real and >= 1 but which are
+// not symmetric, so no Cholesky.  Rows are never swapped: the pivot of column k is the largest entry among the rows
+// that have not been a pivot yet, and rowof[k] remembers it.  One barrier per column: a warp updates its rows
+// (row = warp + 8u, column = lane, pivot row and multipliers in registers, loads batched before stores) and then
+// proposes its best candidate for the next column, so the pivot search needs no pass of its own.
+// slotv / sloti: 2 * KJX_GEN_WARPS scalars / ints of scratch.  Needs blockDim.x == KJX_GEN_THREADS.
 template <typename T>
-__device__ void info_solve(int d, const T* P, const T* m, const T* J, const T* eta, T* M, T* R, int* piv) {
-  const int ld = d + 1;
-  for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
-    const int i = e / d, j = e % d;
-    T s = (i == j) ? T(1) : T(0);
-    for (int k = 0; k < d; ++k) s += P[i * d + k] * J[k * d + j];
-    M[e] = s;
-    R[i * ld + j] = P[e];
+__device__ __forceinline__ void gj_candidates(int d, int ld, const T* M, const int* mark, int k, int pex, T* slotv, int* sloti) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  T best = T(-1); int bi = -1;
+  for (int i = warp + KJX_GEN_WARPS * lane; i < d; i += KJX_GEN_WARPS * 32)
+    if (!mark[i] && i != pex) { const T v = fabs(M[i * ld + k]); if (v > best) { best = v; bi = i; } }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const T ob = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (oi >= 0 && (ob > best || (ob == best && (bi < 0 || oi < bi)))) { best = ob; bi = oi; }
   }
-  for (int i = threadIdx.x; i < d; i += blockDim.x) {
-    T s = m[i];
-    for (int k = 0; k < d; ++k) s += P[i * d + k] * eta[k];
-    R[i * ld + d] = s;
+  if (lane == 0) { slotv[(k & 1) * KJX_GEN_WARPS + warp] = best; sloti[(k & 1) * KJX_GEN_WARPS + warp] = bi; }
+}
+template <typename T>
+__device__ void gj_solve(const GenLayout& L, T* M, T* R, T* rv, T* X, T* xu, int* rowof, int* mark, T* slotv, int* sloti) {
+  constexpr int U = 4;
+  const int d = L.d, ld = L.ld, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  KJX_GEN_VEC(i, d) mark[i] = 0;
+  __syncthreads();
+  gj_candidates<T>(d, ld, M, mark, 0, -1, slotv, sloti);
+  __syncthreads();
+  for (int k = 0; k < d; ++k) {
+    int p = -1;
+    {
+      T best = T(-1);
+#pragma unroll
+      for (int w = 0; w < KJX_GEN_WARPS; ++w) {
+        const T v = slotv[(k & 1) * KJX_GEN_WARPS + w]; const int i = sloti[(k & 1) * KJX_GEN_WARPS + w];
+        if (i >= 0 && (v > best || (v == best && (p < 0 || i < p)))) { best = v; p = i; }
+      }
+      if (p < 0) { for (int i = 0; i < d; ++i) if (!mark[i]) { p = i; break; } }      // column of NaNs: keep going
+    }
+    if (threadIdx.x == 0) { mark[p] = 1; rowof[k] = p; }    // read by others only after the next barrier (they exclude p explicitly)
+    const T pinv = T(1) / M[p * ld + k];
+    const T rvp = rv[p];
+    const int nm = d - k - 1;                         // columns of M still alive: k+1 .. d-1
+    for (int t = 0; t * 32 < d; ++t) {
+      const int jr = lane + 32 * t, jm = k + 1 + jr;
+      const bool hasr = jr < d, hasm = jr < nm;
+      const T pr = hasr ? R[p * ld + jr] : T(0), pm = hasm ? M[p * ld + jm] : T(0);
+      for (int i0 = warp; i0 < d; i0 += U * KJX_GEN_WARPS) {
+        T f[U], mv[U], rr[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { const int i = i0 + u * KJX_GEN_WARPS; f[u] = (i < d && i != p) ? M[i * ld + k] * pinv : T(0); }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int i = i0 + u * KJX_GEN_WARPS;
+          mv[u] = (f[u] != T(0) && hasm) ? M[i * ld + jm] : T(0);
+          rr[u] = (f[u] != T(0) && hasr) ? R[i * ld + jr] : T(0);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int i = i0 + u * KJX_GEN_WARPS;
+          if (f[u] != T(0)) {
+            if (hasm) M[i * ld + jm] = mv[u] - f[u] * pm;
+            if (hasr) R[i * ld + jr] = rr[u] - f[u] * pr;
+            if (t == 0 && lane == 0) rv[i] -= f[u] * rvp;
+          }
+        }
+      }
+    }
+    if (k + 1 < d) {
+      __syncwarp();                                   // column k+1 of this warp's rows was written by its lane 0
+      gj_candidates<T>(d, ld, M, mark, k + 1, p, slotv, sloti);
+    }
+    __syncthreads();
+  }
+  KJX_GEN_ROWS(k, d) {
+    const int p = rowof[k];
+    const T dinv = T(1) / M[p * ld + k];
+    KJX_GEN_COLS(j, d) X[k * ld + j] = R[p * ld + j] * dinv;
+    if (lane == 0) xu[k] = rv[p] * dinv;
   }
   __syncthreads();
-  lu_solve<T>(d, M, R, d + 1, ld, piv);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Blocked in-place Cholesky (lower) of the d x d tile W (utils.py:29).  Panels of 16 columns: warp 0 factors the 16 x 16
+// diagonal block with one row per lane held in registers (right-looking, shuffles) and replaces it by its INVERSE
+// (strict upper part zeroed); the panel below (L21 = A21 L11^-T) and the trailing update then go through gemm_cta.
+// 3 barriers per panel.  On return the tile holds L below the diagonal blocks and L11^-1 in them, which is what
+// chol_solve_blocked wants.  A non-positive pivot gives NaN, like a failed potrf propagated by jaxlib.
+template <typename T> __device__ void chol_blocked(const GenLayout& L, T* W) {
+  const int d = L.d, ld = L.ld, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k0 = 0; k0 < d; k0 += 16) {
+    const int kb = (d - k0 < 16) ? d - k0 : 16;
+    T* D = W + k0 * ld + k0;
+    if (warp == 0) {
+      // lane i < kb owns row i of the block; lanes >= kb carry an identity row so the arithmetic stays finite
+      T a[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) a[c] = (lane < kb && c < kb && c <= lane) ? D[lane * ld + c] : ((c == lane) ? T(1) : T(0));
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const T pv = __shfl_sync(0xffffffffu, a[j], j);
+        const T r = rsqrt_(pv);
+        a[j] = (lane == j) ? r : a[j] * r;                           // column j of L (rows > j); lane j keeps 1 / L[j][j]
+#pragma unroll
+        for (int c = j + 1; c < 16; ++c) {
+          const T lcj = __shfl_sync(0xffffffffu, a[j], c);             // L[c][j]
+          if (lane >= c) a[c] -= a[j] * lcj;
+        }
+      }
+      // inverse: lane c < 16 computes column c of L^-1 by forward substitution; L[i][k] comes from lane i's registers
+      T x[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        T v = (i == lane) ? T(1) : T(0);
+#pragma unroll
+        for (int k = 0; k < i; ++k) {
+          const T lik = __shfl_sync(0xffffffffu, a[k], i);             // L[i][k]
+          v -= lik * x[k];
+        }
+        const T ri = __shfl_sync(0xffffffffu, a[i], i);                  // 1 / L[i][i]  (every lane takes part in the shuffle)
+        x[i] = (i >= lane) ? v * ri : T(0);
+      }
+      // lane c holds column c of the inverse: X[i][c] = x[i]; write the block (zero above the diagonal)
+      if (lane < 16) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) if (i < kb && lane < kb) D[i * ld + lane] = (i >= lane) ? x[i] : T(0);
+      }
+    }
+    __syncthreads();
+    const int rem = d - k0 - kb;
+    if (rem > 0) {               // kb == 16 here
+      T* P21 = W + (k0 + 16) * ld + k0;
+      // L21 = A21 L11^-T, in place (every 16 x 16 block of the product only reads its own rows of A21)
+      gemm_cta<T, false, true>(rem, 16, 16, P21, D, ld, [&](int i, int j, T v) { P21[i * ld + j] = v; });
+      __syncthreads();
+      T* C = W + (k0 + 16) * ld + (k0 + 16);
+      gemm_cta<T, false, true>(rem, rem, 16, P21, P21, ld, [&](int i, int j, T v) { C[i * ld + j] -= v; });
+      __syncthreads();
+    }
+  }
+}
+
+// X <- solve(L L^T, X) for the ncol right-hand-side columns of X (utils.py:30) with the tile chol_blocked left behind:
+// block forward / backward substitution where the diagonal solves are products with the inverted diagonal blocks (in
+// place: a 16 x 16 block of the product only reads its own block of X), so everything is gemm_cta.
+template <typename T> __device__ void chol_solve_blocked(const GenLayout& L, const T* Lw, T* X, int ncol) {
+  const int d = L.d, ld = L.ld;
+  for (int k0 = 0; k0 < d; k0 += 16) {                        // forward: L z = b
+    const int kb = (d - k0 < 16) ? d - k0 : 16;
+    T* X1 = X + k0 * ld;
+    gemm_cta<T, false, false>(kb, ncol, kb, Lw + k0 * ld + k0, X1, ld, [&](int i, int j, T v) { X1[i * ld + j] = v; });
+    __syncthreads();
+    const int rem = d - k0 - kb;
+    if (rem > 0) {
+      T* C = X + (k0 + 16) * ld;
+      gemm_cta<T, false, false>(rem, ncol, 16, Lw + (k0 + 16) * ld + k0, X1, ld, [&](int i, int j, T v) { C[i * ld + j] -= v; });
+      __syncthreads();
+    }
+  }
+  for (int k0 = ((d - 1) >> 4) << 4; k0 >= 0; k0 -= 16) {     // backward: L^T x = z
+    const int kb = (d - k0 < 16) ? d - k0 : 16;
+    T* X1 = X + k0 * ld;
+    gemm_cta<T, true, false>(kb, ncol, kb, Lw + k0 * ld + k0, X1, ld, [&](int i, int j, T v) { X1[i * ld + j] = v; });
+    __syncthreads();
+    if (k0 > 0) {
+      // rows [0, k0) -= L[k0.., 0..k0)^T X[k0..]   (k range kb; row d of both tiles is zero padding when kb % 4 != 0)
+      gemm_cta<T, true, false>(k0, ncol, kb, Lw + k0 * ld, X1, ld, [&](int i, int j, T v) { X[i * ld + j] -= v; });
+      __syncthreads();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// working-set sizes (bytes); the same carve-up lives in global scratch when d > KJX_GEN_DMAX
 template <typename T> size_t generic_fold_smem(int d) {
-  return (size_t)(5 * d * d + 4 * d + 8 * d + 16) * sizeof(T) + (size_t)d * sizeof(int) + 16 * 16;
+  const GenLayout L = gen_layout(d);
+  return (size_t)(6 * L.msz + 4 * d + 7 * d + KJX_GEN_WARPS * d + 16 + 32) * sizeof(T) + (size_t)(d + 4) * sizeof(int) + 256;
 }
 template <typename T> size_t generic_boundary_smem(int d) {
-  return (size_t)(4 * d * d + 4 * d + 16) * sizeof(T) + 64 + 16 * 8;
+  const GenLayout L = gen_layout(d);
+  return (size_t)(4 * L.msz + 5 * d + 16 + 32) * sizeof(T) + (size_t)(2 * d + 40) * sizeof(int) + 512;
+}
+template <typename T> size_t generic_filter_smem(int d) {
+  const GenLayout L = gen_layout(d);
+  return (size_t)(3 * L.msz + 4 * d + 5 * d + KJX_GEN_WARPS * d + 16 + 32) * sizeof(T) + (size_t)(d + 4) * sizeof(int) + 256;
+}
+template <typename T> size_t generic_gain_smem(int d) {
+  const GenLayout L = gen_layout(d);
+  return (size_t)(2 * L.msz + 4 * d + 16) * sizeof(T) + (size_t)(2 * d + 8) * sizeof(int) + 256;
+}
+template <typename T> size_t generic_smoother_smem(int d) {
+  const GenLayout L = gen_layout(d);
+  return (size_t)(6 * L.msz + 4 * d + 7 * d + KJX_GEN_WARPS * d + 16 + 32) * sizeof(T) + (size_t)(3 * d + 44) * sizeof(int) + 512;
 }
 
+// ------------------------------------------------------------------------------------------------
 // fold: one CTA per chunk reduces its steps to the scan element (A, b, C, eta, J) of SURVEY.md 7.3
 template <typename T>
 __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_fold_kernel(const GenArgs<T> g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemCarver<T> sc(g.gscratch ? g.gscratch + (size_t)blockIdx.x * g.gscratch_stride : smem_raw);
-  const int d = g.d, dd = d * d;
-  T* A = sc.take(dd); T* C = sc.take(dd); T* J = sc.take(dd); T* X = sc.take(dd); T* Pinf = sc.take(dd);
+  const GenLayout L = gen_layout(g.d);
+  const int d = L.d, ld = L.ld, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  T* A = sc.take(L.msz); T* A2 = sc.take(L.msz); T* C = sc.take(L.msz); T* Y = sc.take(L.msz); T* J = sc.take(L.msz);
+  T* Pinf = sc.take(L.msz);
   T* vals = sc.take(4 * d); T* b = sc.take(d); T* eta = sc.take(d); T* t1 = sc.take(d); T* Hrow = sc.take(d);
-  T* av = sc.take(d); T* cv = sc.take(d); T* Kv = sc.take(d); T* sh = sc.take(16);
+  T* av = sc.take(d); T* cv = sc.take(d); T* part = sc.take(KJX_GEN_WARPS * d); T* sh = sc.take(16);
   int* c0n = sc.take_int(d);
   const int64_t n0 = (int64_t)blockIdx.x * g.chunk_len, n1 = (n0 + g.chunk_len < g.N) ? n0 + g.chunk_len : g.N;
-  for (int e = threadIdx.x; e < dd; e += blockDim.x) { Pinf[e] = (T)g.Pinf[e]; A[e] = (e / d == e % d) ? T(1) : T(0); C[e] = T(0); J[e] = T(0); }
-  for (int i = threadIdx.x; i < d; i += blockDim.x) { b[i] = T(0); eta[i] = T(0); if (g.H) Hrow[i] = (T)g.H[i]; }
+  KJX_GEN_VEC(e, 6 * L.msz) A[e] = T(0);                   // the six tiles are contiguous
+  __syncthreads();
+  load_dense<T>(L, g.Pinf, Pinf);
+  KJX_GEN_VEC(i, d) { A[i * ld + i] = T(1); b[i] = T(0); eta[i] = T(0); if (g.H) Hrow[i] = (T)g.H[i]; }
   __syncthreads();
   for (int64_t n = n0; n < n1; ++n) {
     build_rows<T>(g.disc, d, g.dt[n], vals, c0n);
-    if (g.H_steps) for (int i = threadIdx.x; i < d; i += blockDim.x) Hrow[i] = (T)g.H_steps[n * d + i];
+    if (g.H_steps) KJX_GEN_VEC(i, d) Hrow[i] = (T)g.H_steps[n * d + i];
     __syncthreads();
-    rows_left<T>(d, vals, c0n, A, X);                       // X <- F A
+    rows_left<T, T>(L, vals, c0n, A, ld, nullptr, 0, A2);   // A2 <- F A
+    rows_left<T, T>(L, vals, c0n, C, ld, Pinf, ld, Y);      // Y  <- F (C - Pinf)
     rows_matvec<T>(d, vals, c0n, b, t1);                    // t1 <- F b
     __syncthreads();
-    for (int e = threadIdx.x; e < dd; e += blockDim.x) { A[e] = X[e]; X[e] = C[e] - Pinf[e]; }
-    for (int i = threadIdx.x; i < d; i += blockDim.x) b[i] = t1[i];
-    __syncthreads();
-    rows_left<T>(d, vals, c0n, X, C);                       // C <- F (C - Pinf)
-    __syncthreads();
-    rows_right_add<T>(d, vals, c0n, C, Pinf, X);            // X <- F (C - Pinf) F^T + Pinf
+    { T* t = A; A = A2; A2 = t; }
+    rows_right_add<T, T>(L, vals, c0n, Y, Pinf, ld, C);     // C <- F (C - Pinf) F^T + Pinf
+    KJX_GEN_VEC(i, d) b[i] = t1[i];
     __syncthreads();
     const bool masked = g.mask ? (g.mask[n] != 0) : false;
     if (!masked) {
-      for (int j = threadIdx.x; j < d; j += blockDim.x) {   // a = A^T h, c = C' h
-        T sa = T(0), scv = T(0);
-        for (int i = 0; i < d; ++i) { sa += Hrow[i] * A[i * d + j]; scv += X[j * d + i] * Hrow[i]; }
-        av[j] = sa; cv[j] = scv;
-      }
+      constexpr int HW = KJX_GEN_WARPS / 2;                 // half of the warps per product
+      rowvec_partial<T>(L, Hrow, A, part, 0, HW);           // a = A^T h
+      rowvec_partial<T>(L, Hrow, C, part + HW * d, HW, HW); // c = C' h (C' symmetric)
       __syncthreads();
-      if (threadIdx.x == 0) {
-        T beta = T(0), sv = T(0);
-        for (int i = 0; i < d; ++i) { beta += Hrow[i] * b[i]; sv += Hrow[i] * cv[i]; }
-        T yt, R;
-        if (g.site_mean) { yt = g.site_mean[n]; R = g.site_var[n]; } else { yt = g.y[n]; R = T(g.site.lik_hyp); }
-        sh[0] = inv1(sv + R); sh[1] = yt - beta;
+      KJX_GEN_VEC(j, d) { av[j] = partial_total<T>(d, part, j, HW); cv[j] = partial_total<T>(d, part + HW * d, j, HW); }
+      if (warp == 0) {
+        T sv = T(0), beta = T(0);
+        KJX_GEN_COLS(j, d) { sv += Hrow[j] * partial_total<T>(d, part + HW * d, j, HW); beta += Hrow[j] * b[j]; }
+        sv = warp_sum(sv); beta = warp_sum(beta);
+        if (lane == 0) {
+          T yt, R;
+          if (g.site_mean) { yt = g.site_mean[n]; R = g.site_var[n]; } else { yt = g.y[n]; R = T(g.site.lik_hyp); }
+          sh[0] = inv1(sv + R); sh[1] = yt - beta;
+        }
       }
       __syncthreads();
       const T sinv = sh[0], res = sh[1];
-      for (int i = threadIdx.x; i < d; i += blockDim.x) { Kv[i] = cv[i] * sinv; eta[i] += av[i] * (res * sinv); b[i] += cv[i] * sinv * res; }
-      __syncthreads();
-      for (int e = threadIdx.x; e < dd; e += blockDim.x) {
-        const int i = e / d, j = e % d;
-        J[e] += av[i] * av[j] * sinv;
-        A[e] -= Kv[i] * av[j];
-        C[e] = X[e] - Kv[i] * cv[j];
+      for (int j = lane; j < d; j += 32) {
+        const T aj = av[j], cj = cv[j];
+        for (int i0 = warp; i0 < d; i0 += 4 * KJX_GEN_WARPS) {
+          T vj[4], va[4], vc[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * KJX_GEN_WARPS;
+            if (i < d) {
+              const T ai = av[i] * sinv, ki = cv[i] * sinv;
+              vj[u] = J[i * ld + j] + ai * aj; va[u] = A[i * ld + j] - ki * aj; vc[u] = C[i * ld + j] - ki * cj;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * KJX_GEN_WARPS;
+            if (i < d) { J[i * ld + j] = vj[u]; A[i * ld + j] = va[u]; C[i * ld + j] = vc[u]; }
+          }
+        }
       }
-    } else {
-      for (int e = threadIdx.x; e < dd; e += blockDim.x) C[e] = X[e];
+      KJX_GEN_VEC(i, d) { eta[i] += av[i] * (res * sinv); b[i] += cv[i] * sinv * res; }
     }
     __syncthreads();
   }
-  T* out = g.sum + (size_t)blockIdx.x * (3 * dd + 2 * d);
-  for (int e = threadIdx.x; e < dd; e += blockDim.x) { out[e] = A[e]; out[dd + e] = C[e]; out[2 * dd + e] = J[e]; }
-  for (int i = threadIdx.x; i < d; i += blockDim.x) { out[3 * dd + i] = b[i]; out[3 * dd + d + i] = eta[i]; }
+  T* out = g.sum + (size_t)blockIdx.x * (3 * d * d + 2 * d);
+  store_dense<T>(L, A, out); store_dense<T>(L, C, out + d * d); store_dense<T>(L, J, out + 2 * d * d);
+  KJX_GEN_VEC(i, d) { out[3 * d * d + i] = b[i]; out[3 * d * d + d + i] = eta[i]; }
 }
 
+// ------------------------------------------------------------------------------------------------
 // boundary: block 0 walks the chunk elements forwards (filtered state entering every chunk), block 1 backwards
-// (information of everything after every chunk).  nchunks is a few hundred at most.
+// (information of everything after every chunk).  nchunks is a few hundred at most; per chunk one Gauss-Jordan solve and
+// three d^3 products, with the chunk's matrices staged into the tile that is free at that point.
 template <typename T>
 __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_boundary_kernel(const GenArgs<T> g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemCarver<T> sc(g.gscratch ? g.gscratch + (size_t)blockIdx.x * g.gscratch_stride : smem_raw);
-  const int d = g.d, dd = d * d, ld = d + 1;
-  T* P = sc.take(dd); T* M = sc.take(dd); T* R = sc.take(dd + d); T* Tm = sc.take(dd);
-  T* m = sc.take(d); T* u = sc.take(d); T* w = sc.take(d);
-  int* piv = sc.take_int(4);
+  const GenLayout L = gen_layout(g.d);
+  const int d = L.d, dd = d * d, ld = L.ld;
+  T* P = sc.take(L.msz); T* M = sc.take(L.msz); T* R = sc.take(L.msz); T* Tm = sc.take(L.msz);
+  T* m = sc.take(d); T* u = sc.take(d); T* w = sc.take(d); T* rv = sc.take(d);
+  T* slotv = sc.take(2 * KJX_GEN_WARPS);
+  int* rowof = sc.take_int(d); int* mark = sc.take_int(d); int* sloti = sc.take_int(2 * KJX_GEN_WARPS);
   const size_t ssz = (size_t)3 * dd + 2 * d;
+  KJX_GEN_VEC(e, 4 * L.msz) P[e] = T(0);
+  KJX_GEN_VEC(i, d) m[i] = T(0);
+  __syncthreads();
   if (blockIdx.x == 0) {
-    for (int e = threadIdx.x; e < dd; e += blockDim.x) P[e] = (T)g.Pinf[e];          // sde_gp.py:265
-    for (int i = threadIdx.x; i < d; i += blockDim.x) m[i] = T(0);
+    load_dense<T>(L, g.Pinf, P);                                                     // sde_gp.py:265
     __syncthreads();
     for (int c = 0; c < g.nchunks; ++c) {
-      for (int e = threadIdx.x; e < dd; e += blockDim.x) g.st_P[(size_t)c * dd + e] = P[e];
-      for (int i = threadIdx.x; i < d; i += blockDim.x) g.st_m[(size_t)c * d + i] = m[i];
+      store_dense<T>(L, P, g.st_P + (size_t)c * dd);
+      KJX_GEN_VEC(i, d) g.st_m[(size_t)c * d + i] = m[i];
       if (c + 1 == g.nchunks) break;
       const T* A = g.sum + c * ssz; const T* C = A + dd; const T* J = A + 2 * dd; const T* b = A + 3 * dd; const T* eta = b + d;
-      info_solve<T>(d, P, m, J, eta, M, R, piv);            // R = [(I+PJ)^-1 P | (I+PJ)^-1 (m + P eta)]
-      for (int e = threadIdx.x; e < dd; e += blockDim.x) M[e] = R[(e / d) * ld + e % d];
-      for (int i = threadIdx.x; i < d; i += blockDim.x) u[i] = R[i * ld + d];
+      load_dense<T>(L, J, Tm);
       __syncthreads();
-      mm_nn<T>(d, A, M, Tm);                                // Tm = A X
-      for (int i = threadIdx.x; i < d; i += blockDim.x) { T s = b[i]; for (int k = 0; k < d; ++k) s += A[i * d + k] * u[k]; m[i] = s; }
+      // (I + P J) X = [P | m + P eta]
+      gemm_cta<T, false, false>(d, d, d, P, Tm, ld, [&](int i, int j, T v) { M[i * ld + j] = v + ((i == j) ? T(1) : T(0)); });
+      tile_map<T>(d, [&](int i, int j) { return P[i * ld + j]; }, [&](int i, int j, T v) { R[i * ld + j] = v; });
+      KJX_GEN_VEC(i, d) { T s = m[i]; for (int k = 0; k < d; ++k) s += P[i * ld + k] * eta[k]; rv[i] = s; }
       __syncthreads();
-      mm_nt_add<T>(d, Tm, A, C, P);                         // P' = A X A^T + C
+      gj_solve<T>(L, M, R, rv, Tm, u, rowof, mark, slotv, sloti);    // Tm <- X = (I+PJ)^-1 P,  u <- (I+PJ)^-1 (m + P eta)
+      load_dense<T>(L, A, M);
+      __syncthreads();
+      gemm_cta<T, false, false>(d, d, d, M, Tm, ld, [&](int i, int j, T v) { R[i * ld + j] = v; });          // R = A X
+      KJX_GEN_VEC(i, d) { T s = b[i]; for (int k = 0; k < d; ++k) s += M[i * ld + k] * u[k]; w[i] = s; }
+      __syncthreads();
+      gemm_cta<T, false, true>(d, d, d, R, M, ld, [&](int i, int j, T v) { P[i * ld + j] = v + C[i * d + j]; });   // P' = A X A^T + C
+      KJX_GEN_VEC(i, d) m[i] = w[i];
       __syncthreads();
     }
   } else {
     // information (eta, J): J in P, eta in m
-    for (int e = threadIdx.x; e < dd; e += blockDim.x) P[e] = T(0);
-    for (int i = threadIdx.x; i < d; i += blockDim.x) m[i] = T(0);
-    __syncthreads();
     for (int c = g.nchunks - 1; c >= 0; --c) {
-      for (int e = threadIdx.x; e < dd; e += blockDim.x) g.in_J[(size_t)c * dd + e] = P[e];
-      for (int i = threadIdx.x; i < d; i += blockDim.x) g.in_eta[(size_t)c * d + i] = m[i];
+      store_dense<T>(L, P, g.in_J + (size_t)c * dd);
+      KJX_GEN_VEC(i, d) g.in_eta[(size_t)c * d + i] = m[i];
       if (c == 0) break;
       const T* A = g.sum + c * ssz; const T* C = A + dd; const T* Ji = A + 2 * dd; const T* b = A + 3 * dd; const T* etai = b + d;
-      // (I + J_j C_i)^T = I + C_i J_j.  Solve (I + J_j C_i) Y = [J_j A_i | eta_j - J_j b_i]
-      for (int e = threadIdx.x; e < dd; e += blockDim.x) {
-        const int i = e / d, j = e % d;
-        T s = (i == j) ? T(1) : T(0), r = T(0);
-        for (int k = 0; k < d; ++k) { s += P[i * d + k] * C[k * d + j]; r += P[i * d + k] * A[k * d + j]; }
-        M[e] = s; R[i * ld + j] = r;
-      }
-      for (int i = threadIdx.x; i < d; i += blockDim.x) {
-        T s = m[i];
-        for (int k = 0; k < d; ++k) s -= P[i * d + k] * b[k];
-        R[i * ld + d] = s;
-      }
+      // (I + J_j C_i) Y = [J_j A_i | eta_j - J_j b_i]
+      load_dense<T>(L, C, Tm);
+      KJX_GEN_VEC(i, d) { T s = m[i]; for (int k = 0; k < d; ++k) s -= P[i * ld + k] * b[k]; rv[i] = s; }
       __syncthreads();
-      lu_solve<T>(d, M, R, d + 1, ld, piv);
-      for (int e = threadIdx.x; e < dd; e += blockDim.x) M[e] = R[(e / d) * ld + e % d];
-      for (int i = threadIdx.x; i < d; i += blockDim.x) u[i] = R[i * ld + d];
+      gemm_cta<T, false, false>(d, d, d, P, Tm, ld, [&](int i, int j, T v) { M[i * ld + j] = v + ((i == j) ? T(1) : T(0)); });
       __syncthreads();
-      mm_tn_add<T>(d, A, M, Ji, P);                         // J' = A_i^T Y + J_i
-      for (int i = threadIdx.x; i < d; i += blockDim.x) { T s = etai[i]; for (int k = 0; k < d; ++k) s += A[k * d + i] * u[k]; w[i] = s; }
+      load_dense<T>(L, A, Tm);
       __syncthreads();
-      for (int i = threadIdx.x; i < d; i += blockDim.x) m[i] = w[i];
-      // keep J' exactly symmetric
-      for (int e = threadIdx.x; e < dd; e += blockDim.x) { const int i = e / d, j = e % d; if (i < j) { const T v = T(0.5) * (P[e] + P[j * d + i]); Tm[e] = v; Tm[j * d + i] = v; } else if (i == j) Tm[e] = P[e]; }
+      gemm_cta<T, false, false>(d, d, d, P, Tm, ld, [&](int i, int j, T v) { R[i * ld + j] = v; });
       __syncthreads();
-      for (int e = threadIdx.x; e < dd; e += blockDim.x) P[e] = Tm[e];
+      gj_solve<T>(L, M, R, rv, P, u, rowof, mark, slotv, sloti);     // P <- Y (J_j is no longer needed), u <- the vector part
+      gemm_cta<T, true, false>(d, d, d, Tm, P, ld, [&](int i, int j, T v) { M[i * ld + j] = v + Ji[i * d + j]; });   // J' = A_i^T Y + J_i
+      KJX_GEN_VEC(i, d) { T s = etai[i]; for (int k = 0; k < d; ++k) s += Tm[k * ld + i] * u[k]; w[i] = s; }
+      __syncthreads();
+      KJX_GEN_VEC(i, d) m[i] = w[i];
+      tile_map<T>(d, [&](int i, int j) { return (i == j) ? M[i * ld + j] : T(0.5) * (M[i * ld + j] + M[j * ld + i]); },   // keep J' exactly symmetric
+                  [&](int i, int j, T v) { P[i * ld + j] = v; });
       __syncthreads();
     }
   }
@@ -353,36 +667,38 @@ template <typename T>
 __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_filter_kernel(const GenArgs<T> g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemCarver<T> sc(g.gscratch ? g.gscratch + (size_t)blockIdx.x * g.gscratch_stride : smem_raw);
-  const int d = g.d, dd = d * d;
-  T* P = sc.take(dd); T* X = sc.take(dd); T* Pinf = sc.take(dd);
-  T* vals = sc.take(4 * d); T* m = sc.take(d); T* mp = sc.take(d); T* Hrow = sc.take(d); T* HP = sc.take(d); T* K = sc.take(d);
-  T* sh = sc.take(16);                 // scalars: 0 pm, 1 pv, 2 site_mean, 3 site_var, 4 Sinv, 5 masked, 6 nlml
+  const GenLayout L = gen_layout(g.d);
+  const int d = L.d, dd = d * d, ld = L.ld, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  T* P = sc.take(L.msz); T* Y = sc.take(L.msz); T* Pinf = sc.take(L.msz);
+  T* vals = sc.take(4 * d); T* m = sc.take(d); T* mp = sc.take(d); T* Hrow = sc.take(d); T* HP = sc.take(d);
+  T* part = sc.take(KJX_GEN_WARPS * d);
+  T* sh = sc.take(16);                 // scalars: 0 pm, 2 site_mean, 4 Sinv, 5 masked, 6 nlml
   int* c0n = sc.take_int(d);
   // this CTA's chunk and the filtered state entering it (chunk 0: the prior, sde_gp.py:265)
   const int64_t n0 = (int64_t)blockIdx.x * g.chunk_len, n1 = (n0 + g.chunk_len < g.N) ? n0 + g.chunk_len : g.N;
-  for (int e = threadIdx.x; e < dd; e += blockDim.x) { Pinf[e] = (T)g.Pinf[e]; P[e] = g.st_P[(size_t)blockIdx.x * dd + e]; }
-  for (int i = threadIdx.x; i < d; i += blockDim.x) { m[i] = g.st_m[(size_t)blockIdx.x * d + i]; if (g.H) Hrow[i] = (T)g.H[i]; }
+  KJX_GEN_VEC(e, 3 * L.msz) P[e] = T(0);
+  __syncthreads();
+  load_dense<T>(L, g.Pinf, Pinf);
+  load_dense<T>(L, g.st_P + (size_t)blockIdx.x * dd, P);
+  KJX_GEN_VEC(i, d) { m[i] = g.st_m[(size_t)blockIdx.x * d + i]; if (g.H) Hrow[i] = (T)g.H[i]; }
   if (threadIdx.x == 0) sh[6] = T(0);
   __syncthreads();
   for (int64_t n = n0; n < n1; ++n) {
     build_rows<T>(g.disc, d, g.dt[n], vals, c0n);                                   // :276
-    if (g.H_steps) for (int i = threadIdx.x; i < d; i += blockDim.x) Hrow[i] = (T)g.H_steps[n * d + i];   // :282
-    for (int e = threadIdx.x; e < dd; e += blockDim.x) X[e] = P[e] - Pinf[e];
+    if (g.H_steps) KJX_GEN_VEC(i, d) Hrow[i] = (T)g.H_steps[n * d + i];             // :282
     __syncthreads();
     rows_matvec<T>(d, vals, c0n, m, mp);                                            // :277
-    rows_left<T>(d, vals, c0n, X, P);                                               // P <- A (P - Pinf)
+    rows_left<T, T>(L, vals, c0n, P, ld, Pinf, ld, Y);                              // Y <- A (P - Pinf)
     __syncthreads();
-    rows_right_add<T>(d, vals, c0n, P, Pinf, X);                                    // X <- P_ = . A^T + Pinf   (:278)
+    rows_right_add<T, T>(L, vals, c0n, Y, Pinf, ld, P);                             // P <- P_ = . A^T + Pinf   (:278)
     __syncthreads();
-    for (int j = threadIdx.x; j < d; j += blockDim.x) {                             // HP = H P_
-      T s = T(0);
-      for (int i = 0; i < d; ++i) s += Hrow[i] * X[i * d + j];
-      HP[j] = s;
-    }
+    rowvec_partial<T>(L, Hrow, P, part, 0, KJX_GEN_WARPS);                                            // HP = H P_
     __syncthreads();
-    if (threadIdx.x < 32) {            // warp 0: the step's scalar work; cubature points spread over its lanes
+    KJX_GEN_VEC(j, d) HP[j] = partial_total<T>(d, part, j, KJX_GEN_WARPS);
+    if (warp == 0) {                   // warp 0: the step's scalar work; cubature points spread over its lanes
       T pm = T(0), pv = T(0);
-      for (int i = 0; i < d; ++i) { pm += Hrow[i] * mp[i]; pv += HP[i] * Hrow[i]; }   // :283-284
+      KJX_GEN_COLS(j, d) { pm += Hrow[j] * mp[j]; pv += partial_total<T>(d, part, j, KJX_GEN_WARPS) * Hrow[j]; }   // :283-284
+      pm = warp_sum(pm); pv = warp_sum(pv);
       const bool masked = g.mask ? (g.mask[n] != 0) : false;
       T smean, svar, lml = T(0);
       if (g.init_sites) {
@@ -394,8 +710,8 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_filter_kernel(const G
         if (!masked) lml = filter_loglik<T, WarpRed>(g.site, g.y[n], pm, pv);        // log Z is always the true likelihood's
       }
       if (masked) lml = T(0);                                                        // :300
-      if (threadIdx.x == 0) {
-        sh[0] = pm; sh[2] = smean; sh[3] = svar; sh[4] = inv1(pv + svar); sh[5] = masked ? T(1) : T(0);   // :292-294
+      if (lane == 0) {
+        sh[0] = pm; sh[2] = smean; sh[4] = inv1(pv + svar); sh[5] = masked ? T(1) : T(0);   // :292-294
         sh[6] += lml;                                                                // :301
         if (g.out_site_mean) { g.out_site_mean[n] = smean; g.out_site_var[n] = svar; }
       }
@@ -403,218 +719,140 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_filter_kernel(const G
     __syncthreads();
     const bool masked = sh[5] != T(0);
     const T Sinv = sh[4], innov = sh[2] - sh[0];
-    for (int i = threadIdx.x; i < d; i += blockDim.x) {
-      K[i] = HP[i] * Sinv;
-      m[i] = masked ? mp[i] : mp[i] + K[i] * innov;                                  // :295 / :298
-      if (g.filt_mean) g.filt_mean[n * d + i] = m[i];
+    KJX_GEN_VEC(i, d) {
+      const T mi = masked ? mp[i] : mp[i] + HP[i] * Sinv * innov;                    // :295 / :298
+      m[i] = mi;
+      if (g.filt_mean) g.filt_mean[n * d + i] = mi;
     }
-    __syncthreads();
-    for (int e = threadIdx.x; e < dd; e += blockDim.x) {
-      const int i = e / d, j = e % d;
-      const T v = masked ? X[e] : X[e] - K[i] * HP[j];                               // :296 / :299
-      P[e] = v;
-      if (g.filt_cov) g.filt_cov[n * (int64_t)dd + e] = v;
-    }
+    T* fc = g.filt_cov ? g.filt_cov + n * (int64_t)dd : nullptr;
+    if (!masked || fc)
+      tile_map<T>(d, [&](int i, int j) { return masked ? P[i * ld + j] : P[i * ld + j] - HP[i] * Sinv * HP[j]; },    // :296 / :299
+                  [&](int i, int j, T v) { P[i * ld + j] = v; if (fc) fc[i * d + j] = v; });
     __syncthreads();
   }
   if (threadIdx.x == 0) g.chunk_nlml[blockIdx.x] = sh[6];
 }
 
 // ------------------------------------------------------------------------------------------------
-// in-place Cholesky (lower, left-looking) of the d x d matrix A in shared memory; rinv[j] = 1 / L[j][j].
-// Column j: every row i >= j subtracts its dot product with row j of the already finished columns (one thread per
-// row), then the column is scaled: 2 barriers per column and no d^2 trailing update.
-template <typename T> __device__ void chol_inplace(int d, T* A, T* rinv) {
-  for (int j = 0; j < d; ++j) {
-    for (int i = j + threadIdx.x; i < d; i += blockDim.x) {
-      T v = A[i * d + j];
-      for (int k = 0; k < j; ++k) v -= A[i * d + k] * A[j * d + k];
-      A[i * d + j] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const T piv = A[j * d + j];
-      const T r = rsqrt_(piv);           // NaN for a negative pivot, like a failed potrf propagated by jaxlib
-      rinv[j] = r;
-      A[j * d + j] = piv * r;
-    }
-    __syncthreads();
-    const T r = rinv[j];
-    for (int i = j + 1 + threadIdx.x; i < d; i += blockDim.x) A[i * d + j] *= r;
-    // (row j itself is only read by later columns after the next barrier)
-  }
-  __syncthreads();
-}
-
-// X <- solve(L L^T, X) for the d right-hand-side columns of X (utils.py:30).  The substitutions run over rows; within
-// a row every column is independent, so (column, k-slice) pairs are spread over the CTA: `TPC` threads share one
-// column's dot product and combine by shuffle.
-template <typename T, int TPC> __device__ void chol_substitute(int d, const T* L, const T* rinv, T* X) {
-  const int lane_in = threadIdx.x % TPC;
-  const int col0 = threadIdx.x / TPC, ncol = blockDim.x / TPC;
-  for (int i = 0; i < d; ++i) {                               // forward: L z = b
-    for (int c = col0; c < d + (ncol - d % ncol) % ncol; c += ncol) {
-      T v = T(0);
-      if (c < d) for (int k = lane_in; k < i; k += TPC) v -= L[i * d + k] * X[k * d + c];
-#pragma unroll
-      for (int o = TPC / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (c < d && lane_in == 0) X[i * d + c] = (X[i * d + c] + v) * rinv[i];
-    }
-    __syncthreads();
-  }
-  for (int i = d - 1; i >= 0; --i) {                          // backward: L^T x = z
-    for (int c = col0; c < d + (ncol - d % ncol) % ncol; c += ncol) {
-      T v = T(0);
-      if (c < d) for (int k = i + 1 + lane_in; k < d; k += TPC) v -= L[k * d + i] * X[k * d + c];
-#pragma unroll
-      for (int o = TPC / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (c < d && lane_in == 0) X[i * d + c] = (X[i * d + c] + v) * rinv[i];
-    }
-    __syncthreads();
-  }
-}
-
 // RTS gains, embarrassingly parallel over time: Gt[n] = solve(P_pred[n], A[n+1] Pf[n]) depends only on the FILTERED
 // moments (sde_gp.py:351-359), so a grid of CTAs computes them all before the (sequential) backward recursion.
-template <typename T> size_t generic_gain_smem(int d) {
-  return (size_t)(2 * d * d + 4 * d + d + 16) * sizeof(T) + (size_t)d * sizeof(int) + 16 * 8;
-}
-
-// Working set: two d x d tiles in shared memory (56 KB at d = 59, so four CTAs share an SM — the factorisation and
-// substitutions are barrier-latency-bound); Pf and Pinf are read straight from global / L1.
+// Working set: two tiles in shared memory (61 KB at d = 59, three CTAs per SM); Pf and Pinf are read from global / L1.
 template <typename T>
-__global__ void __launch_bounds__(KJX_GEN_THREADS) generic_gain_kernel(const GenArgs<T> g, T* __restrict__ Gt_out) {
+__global__ void __launch_bounds__(KJX_GEN_GAIN_THREADS, 2) generic_gain_kernel(const GenArgs<T> g, T* __restrict__ Gt_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemCarver<T> sc(g.gscratch ? g.gscratch + (size_t)blockIdx.x * g.gscratch_stride : smem_raw);
-  const int d = g.d, dd = d * d;
-  T* W = sc.take(dd); T* Gt = sc.take(dd);
-  T* vals = sc.take(4 * d); T* rinv = sc.take(d);
-  int* c0n = sc.take_int(d);
+  const GenLayout L = gen_layout(g.d);
+  const int d = L.d, dd = d * d, ld = L.ld;
+  T* W = sc.take(L.msz); T* Gt = sc.take(L.msz);
+  T* vals = sc.take(4 * d);
+  int* c0n = sc.take_int(d); int* bstart = sc.take_int(d + 1);
+  KJX_GEN_VEC(e, 2 * L.msz) W[e] = T(0);
+  build_rows<T>(g.disc, d, T(0), vals, c0n);                 // block structure of A: first rows of the diagonal blocks
+  __syncthreads();
+  if (threadIdx.x == 0) { int nb = 0; for (int i = 0; i < d; ++i) if ((c0n[i] & 0xffffff) == i) bstart[nb++] = i; bstart[d] = nb; }
+  __syncthreads();
+  const int nblk = bstart[d];
+  const double* Pinf = g.Pinf;
   for (int64_t n = blockIdx.x; n < g.N; n += gridDim.x) {
     build_rows<T>(g.disc, d, (n + 1 < g.N) ? g.dt[n + 1] : T(0), vals, c0n);        // :337, :351
     const T* Pf = g.filt_cov_in + n * (int64_t)dd;
+    tile_map<T>(d, [&](int i, int j) { return Pf[i * d + j] - (T)Pinf[i * d + j]; }, [&](int i, int j, T v) { W[i * ld + j] = v; });
     __syncthreads();
-    for (int e = threadIdx.x; e < dd; e += blockDim.x) {                            // Gt <- A (Pf - Pinf)
-      const int i = e / d, j = e % d;
-      const int c0 = c0n[i] & 0xffffff, nn = c0n[i] >> 24;
-      T s = T(0);
-      for (int q = 0; q < nn; ++q) s += vals[i * 4 + q] * (Pf[(c0 + q) * d + j] - (T)g.Pinf[(c0 + q) * d + j]);
-      Gt[e] = s;
-    }
+    rows_left<T, T>(L, vals, c0n, W, ld, nullptr, 0, Gt);                           // Gt <- A (Pf - Pinf)
     __syncthreads();
-    for (int e = threadIdx.x; e < dd; e += blockDim.x) {                            // W <- P_pred = . A^T + Pinf   (:354)
-      const int i = e / d, j = e % d;
-      const int c0 = c0n[j] & 0xffffff, nn = c0n[j] >> 24;
-      T s = T(0);
-      for (int q = 0; q < nn; ++q) s += Gt[i * d + c0 + q] * vals[j * 4 + q];
-      W[e] = s + (T)g.Pinf[e];
-    }
+    rows_right_add<T, double>(L, vals, c0n, Gt, Pinf, d, W);                        // W <- P_pred = . A^T + Pinf   (:354)
     __syncthreads();
-    for (int e = threadIdx.x; e < dd; e += blockDim.x) {                            // Gt <- A Pf                  (:353)
-      const int i = e / d, j = e % d;
-      const int c0 = c0n[i] & 0xffffff, nn = c0n[i] >> 24;
-      T s = T(0);
-      for (int q = 0; q < nn; ++q) s += vals[i * 4 + q] * Pf[(c0 + q) * d + j];
-      Gt[e] = s;
-    }
+    load_dense<T>(L, Pf, Gt);
     __syncthreads();
-    chol_inplace<T>(d, W, rinv);                                                    // utils.py:29
-    chol_substitute<T, 4>(d, W, rinv, Gt);                                          // :359, utils.py:30
-    for (int e = threadIdx.x; e < dd; e += blockDim.x) Gt_out[n * (int64_t)dd + e] = Gt[e];
+    rows_left_inplace<T>(L, vals, c0n, bstart, nblk, Gt);                           // Gt <- A Pf                  (:353)
+    __syncthreads();
+    chol_blocked<T>(L, W);                                                          // utils.py:29
+    chol_solve_blocked<T>(L, W, Gt, d);                                             // :359, utils.py:30
+    store_dense<T>(L, Gt, Gt_out + n * (int64_t)dd);
     __syncthreads();
   }
 }
 
+// ------------------------------------------------------------------------------------------------
 // backward smoother, sde_gp.py:337-379
 template <typename T>
 __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_smoother_kernel(const GenArgs<T> g, const T* __restrict__ Gt_in) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemCarver<T> sc(g.gscratch ? g.gscratch + (size_t)blockIdx.x * g.gscratch_stride : smem_raw);
-  const int d = g.d, dd = d * d;
-  T* Pf = sc.take(dd); T* Pp = sc.take(dd + d); T* Gt = sc.take(dd); T* Ps = sc.take(dd); T* W = sc.take(dd); T* Pinf = sc.take(dd);
+  const GenLayout L = gen_layout(g.d);
+  const int d = L.d, dd = d * d, ld = L.ld, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  T* Pf = sc.take(L.msz); T* Pp = sc.take(L.msz); T* Gt = sc.take(L.msz); T* Ps = sc.take(L.msz); T* W = sc.take(L.msz);
+  T* Pinf = sc.take(L.msz);
   T* vals = sc.take(4 * d); T* mf = sc.take(d); T* mp = sc.take(d); T* ms = sc.take(d); T* dm = sc.take(d); T* Hrow = sc.take(d);
-  T* rinv = sc.take(d); T* sh = sc.take(16);
-  int* c0n = sc.take_int(d);
-  int* piv = sc.take_int(4);
+  T* rv = sc.take(d); T* mnew = sc.take(d); T* part = sc.take(KJX_GEN_WARPS * d); T* slotv = sc.take(2 * KJX_GEN_WARPS);
+  int* c0n = sc.take_int(d); int* rowof = sc.take_int(d); int* mark = sc.take_int(d); int* sloti = sc.take_int(2 * KJX_GEN_WARPS);
   const int64_t n0 = (int64_t)blockIdx.x * g.chunk_len, n1 = (n0 + g.chunk_len < g.N) ? n0 + g.chunk_len : g.N;
-  for (int e = threadIdx.x; e < dd; e += blockDim.x) Pinf[e] = (T)g.Pinf[e];
-  for (int i = threadIdx.x; i < d; i += blockDim.x) if (g.H) Hrow[i] = (T)g.H[i];
+  KJX_GEN_VEC(e, 6 * L.msz) Pf[e] = T(0);
+  __syncthreads();
+  load_dense<T>(L, g.Pinf, Pinf);
+  KJX_GEN_VEC(i, d) if (g.H) Hrow[i] = (T)g.H[i];
   __syncthreads();
   for (int64_t n = n1 - 1; n >= n0; --n) {
     if (n == n1 - 1) {
       // Last step of the chunk: smoothed = filtered x information of everything after the chunk (two-filter identity;
-      // for the chunk that ends the series the information is zero and this is sde_gp.py:339).  Pp/W are scratch here.
-      if (g.H_steps) for (int i = threadIdx.x; i < d; i += blockDim.x) Hrow[i] = (T)g.H_steps[n * d + i];
-      for (int e = threadIdx.x; e < dd; e += blockDim.x) Pf[e] = g.filt_cov_in[n * (int64_t)dd + e];
-      for (int i = threadIdx.x; i < d; i += blockDim.x) mf[i] = g.filt_mean_in[n * d + i];
+      // for the chunk that ends the series the information is zero and this is sde_gp.py:339).  Pp/Gt/W are scratch here.
+      if (g.H_steps) KJX_GEN_VEC(i, d) Hrow[i] = (T)g.H_steps[n * d + i];
+      load_dense<T>(L, g.filt_cov_in + n * (int64_t)dd, Pf);
+      load_dense<T>(L, g.in_J + (size_t)blockIdx.x * dd, W);
+      KJX_GEN_VEC(i, d) mf[i] = g.filt_mean_in[n * d + i];
       __syncthreads();
-      info_solve<T>(d, Pf, mf, g.in_J + (size_t)blockIdx.x * dd, g.in_eta + (size_t)blockIdx.x * d, W, Pp, piv);
-      for (int e = threadIdx.x; e < dd; e += blockDim.x) {
-        const int i = e / d, j = e % d;
-        Ps[e] = (i <= j) ? Pp[i * (d + 1) + j] : Pp[j * (d + 1) + i];          // symmetric by construction; take the upper part
-        if (g.smooth_mean && g.return_full) g.smooth_cov[n * (int64_t)dd + e] = Ps[e];
-      }
-      for (int i = threadIdx.x; i < d; i += blockDim.x) {
-        ms[i] = Pp[i * (d + 1) + d];
-        if (g.smooth_mean && g.return_full) g.smooth_mean[n * d + i] = ms[i];
-      }
+      const T* eta = g.in_eta + (size_t)blockIdx.x * d;
+      gemm_cta<T, false, false>(d, d, d, Pf, W, ld, [&](int i, int j, T v) { Pp[i * ld + j] = v + ((i == j) ? T(1) : T(0)); });
+      tile_map<T>(d, [&](int i, int j) { return Pf[i * ld + j]; }, [&](int i, int j, T v) { Gt[i * ld + j] = v; });
+      KJX_GEN_VEC(i, d) { T s = mf[i]; for (int k = 0; k < d; ++k) s += Pf[i * ld + k] * eta[k]; rv[i] = s; }
       __syncthreads();
+      gj_solve<T>(L, Pp, Gt, rv, Ps, ms, rowof, mark, slotv, sloti);  // Ps <- (I + Pf J)^-1 Pf,  ms <- (I + Pf J)^-1 (mf + Pf eta)
+      KJX_GEN_ROWS(i, d) KJX_GEN_COLS(j, d) if (i > j) Ps[i * ld + j] = Ps[j * ld + i];   // symmetric by construction; keep the upper part
+      __syncthreads();
+      if (g.smooth_mean && g.return_full) {
+        store_dense<T>(L, Ps, g.smooth_cov + n * (int64_t)dd);
+        KJX_GEN_VEC(i, d) g.smooth_mean[n * d + i] = ms[i];
+      }
     } else {
-    build_rows<T>(g.disc, d, (n + 1 < g.N) ? g.dt[n + 1] : T(0), vals, c0n);        // :337, :351
-    if (g.H_steps) for (int i = threadIdx.x; i < d; i += blockDim.x) Hrow[i] = (T)g.H_steps[n * d + i];
-    for (int e = threadIdx.x; e < dd; e += blockDim.x) { const T v = g.filt_cov_in[n * (int64_t)dd + e]; Pf[e] = v; W[e] = v - Pinf[e]; }
-    for (int i = threadIdx.x; i < d; i += blockDim.x) mf[i] = g.filt_mean_in[n * d + i];
-    __syncthreads();
-    rows_matvec<T>(d, vals, c0n, mf, mp);                                           // :352
-    rows_left<T>(d, vals, c0n, W, Pp);                                              // Pp <- A (Pf - Pinf)
-    __syncthreads();
-    rows_right_add<T>(d, vals, c0n, Pp, Pinf, W);                                   // W  <- P_pred       (:354)
-    __syncthreads();
-    for (int e = threadIdx.x; e < dd; e += blockDim.x) W[e] = Ps[e] - W[e];         // W <- Ps - P_pred
-    for (int i = threadIdx.x; i < d; i += blockDim.x) dm[i] = ms[i] - mp[i];
-    __syncthreads();
-    for (int e = threadIdx.x; e < dd; e += blockDim.x) Gt[e] = Gt_in[n * (int64_t)dd + e];   // gain from generic_gain_kernel
-    __syncthreads();
-    // m = mf + G (m - m_pred);  P = Pf + G (P - P_pred) G^T  with G = Gt^T              (:360-361)
-    for (int i = threadIdx.x; i < d; i += blockDim.x) {
-      T v = mf[i];
-      for (int k = 0; k < d; ++k) v += Gt[k * d + i] * dm[k];
-      ms[i] = v;
+      build_rows<T>(g.disc, d, (n + 1 < g.N) ? g.dt[n + 1] : T(0), vals, c0n);      // :337, :351
+      if (g.H_steps) KJX_GEN_VEC(i, d) Hrow[i] = (T)g.H_steps[n * d + i];
+      load_dense<T>(L, g.filt_cov_in + n * (int64_t)dd, Pf);
+      load_dense<T>(L, Gt_in + n * (int64_t)dd, Gt);                                // gain from generic_gain_kernel
+      KJX_GEN_VEC(i, d) mf[i] = g.filt_mean_in[n * d + i];
+      __syncthreads();
+      rows_matvec<T>(d, vals, c0n, mf, mp);                                         // :352
+      rows_left<T, T>(L, vals, c0n, Pf, ld, Pinf, ld, Pp);                          // Pp <- A (Pf - Pinf)
+      __syncthreads();
+      rows_right_add<T, T>(L, vals, c0n, Pp, Pinf, ld, W, Ps, T(-1));               // W <- Ps - P_pred          (:354)
+      KJX_GEN_VEC(i, d) dm[i] = ms[i] - mp[i];
+      __syncthreads();
+      // m = mf + G (m - m_pred);  P = Pf + G (P - P_pred) G^T  with G = Gt^T          (:360-361)
+      gemm_cta<T, true, false>(d, d, d, Gt, W, ld, [&](int i, int j, T v) { Pp[i * ld + j] = v; });   // Pp <- G (Ps - P_pred)
+      KJX_GEN_VEC(i, d) { T v = mf[i]; for (int k = 0; k < d; ++k) v += Gt[k * ld + i] * dm[k]; mnew[i] = v; }
+      __syncthreads();
+      T* sc_out = (g.smooth_mean && g.return_full) ? g.smooth_cov + n * (int64_t)dd : nullptr;
+      gemm_cta<T, false, false>(d, d, d, Pp, Gt, ld, [&](int i, int j, T v) {
+        const T r = Pf[i * ld + j] + v;
+        Ps[i * ld + j] = r;
+        if (sc_out) sc_out[i * d + j] = r;
+      });
+      KJX_GEN_VEC(i, d) { ms[i] = mnew[i]; if (sc_out) g.smooth_mean[n * d + i] = mnew[i]; }
+      __syncthreads();
     }
-    for (int e = threadIdx.x; e < dd; e += blockDim.x) {          // Pp (free now) <- G (Ps - P_pred)
-      const int i = e / d, j = e % d;
-      T v = T(0);
-      for (int k = 0; k < d; ++k) v += Gt[k * d + i] * W[k * d + j];
-      Pp[e] = v;
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < dd; e += blockDim.x) {
-      const int i = e / d, j = e % d;
-      T v = Pf[e];
-      for (int k = 0; k < d; ++k) v += Pp[i * d + k] * Gt[k * d + j];
-      Ps[e] = v;
-      if (g.smooth_mean && g.return_full) g.smooth_cov[n * (int64_t)dd + e] = v;
-    }
-    if (g.smooth_mean && g.return_full) for (int i = threadIdx.x; i < d; i += blockDim.x) g.smooth_mean[n * d + i] = ms[i];
-    __syncthreads();
-    }  // recursion step
     // marginal of the function value: H m, H P H^T                                      (:368-369, :373)
-    for (int j = threadIdx.x; j < d; j += blockDim.x) {
-      T s = T(0);
-      for (int i = 0; i < d; ++i) s += Hrow[i] * Ps[i * d + j];
-      dm[j] = s;
-    }
+    rowvec_partial<T>(L, Hrow, Ps, part, 0, KJX_GEN_WARPS);
     __syncthreads();
-    if (threadIdx.x < 32) {            // warp 0, cubature points spread over its lanes
+    if (warp == 0) {                   // warp 0, cubature points spread over its lanes
       T pm = T(0), pv = T(0);
-      for (int i = 0; i < d; ++i) { pm += Hrow[i] * ms[i]; pv += dm[i] * Hrow[i]; }
-      if (threadIdx.x == 0 && g.smooth_mean && !g.return_full) { g.smooth_mean[n] = pm; g.smooth_cov[n] = pv; }
+      KJX_GEN_COLS(j, d) { pm += Hrow[j] * ms[j]; pv += partial_total<T>(d, part, j, KJX_GEN_WARPS) * Hrow[j]; }
+      pm = warp_sum(pm); pv = warp_sum(pv);
+      if (lane == 0 && g.smooth_mean && !g.return_full) { g.smooth_mean[n] = pm; g.smooth_cov[n] = pv; }
       if (g.update_sites) {
         T pmean, pvar;
         if (g.site_mean) { pmean = g.site_mean[n]; pvar = g.site_var[n]; } else { pmean = g.y[n]; pvar = T(g.site.lik_hyp); }
         __syncwarp();                    // every lane has read the previous site before lane 0 may overwrite it in place
         const SiteOut<T> o = site_update<T, WarpRed>(g.site, g.y[n], pm, pv, true, pmean, pvar);   // :375
-        if (threadIdx.x == 0) { g.new_site_mean[n] = o.mean; g.new_site_var[n] = o.var; }
+        if (lane == 0) { g.new_site_mean[n] = o.mean; g.new_site_var[n] = o.var; }
       }
     }
     __syncthreads();
