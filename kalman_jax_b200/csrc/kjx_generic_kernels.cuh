@@ -52,9 +52,10 @@ template <typename T> struct GenArgs {
   int return_full; int update_sites;
   // chunked scan (one CTA per chunk)
   int64_t chunk_len; int nchunks;
-  T* sum;                  // [nchunks][3 d^2 + 2 d]  chunk elements: A | C | J | b | eta   (dense, leading dimension d)
+  T* sum;                  // [nchunks][3 d^2 + 2 d]  chunk elements: A | C | J | b | eta   (dense, leading dimension d;
+                           //                         equilibrated coordinates, see scale_vectors)
   T* st_m; T* st_P;        // [nchunks][d], [nchunks][d^2]  filtered state entering every chunk
-  T* in_eta; T* in_J;      // [nchunks][d], [nchunks][d^2]  information of everything after every chunk
+  T* in_eta; T* in_J;      // [nchunks][d], [nchunks][d^2]  information of everything after every chunk (equilibrated)
   T* chunk_nlml;           // [nchunks]
   unsigned char* gscratch; // d > KJX_GEN_DMAX: per-CTA working set in global memory instead of shared memory
   size_t gscratch_stride;
@@ -315,87 +316,115 @@ __device__ __forceinline__ void gemm_cta(int m, int n, int kk, const T* A, const
 }
 
 // ------------------------------------------------------------------------------------------------
-// Solve M X = [R | rv] by Gauss-Jordan elimination with partial pivoting (M: d x d, destroyed; R: d x d and rv: d,
-// destroyed; X, xu receive the solution).  Used on I + P J / I + J C, whose eigenvalues are real and >= 1 but which are
-// not symmetric, so no Cholesky.  Rows are never swapped: the pivot of column k is the largest entry among the rows
-// that have not been a pivot yet, and rowof[k] remembers it.  One barrier per column: a warp updates its rows
-// (row = warp + 8u, column = lane, pivot row and multipliers in registers, loads batched before stores) and then
-// proposes its best candidate for the next column, so the pivot search needs no pass of its own.
-// slotv / sloti: 2 * KJX_GEN_WARPS scalars / ints of scratch.  Needs blockDim.x == KJX_GEN_THREADS.
+// Solve M X = [R | rv] in place by blocked LU with partial pivoting (M: d x d, overwritten by its factors; R: d x d
+// and rv: d, overwritten by the solution).  Used on I + P J / I + J C, whose eigenvalues are real and >= 1 but which
+// are not symmetric (and whose leading minors may vanish), so no Cholesky and no unpivoted elimination.
+// Panels of 8 columns: warp 0 factors the panel (pivot search by shuffle, row swap, rank-one update inside the panel),
+// then one thread per remaining column applies the swaps and the unit-lower 8 x 8 solve, and the rank-8 trailing
+// update of [M | R] goes through gemm_cta — 8x less shared-memory traffic than rank-one elimination, which is what
+// bounds that one.  Back substitution is blocked the same way.  piv: d ints of scratch.
+// M and R must not be the last tiles of the working set (fragment loads of the trailing update may run past the
+// tile by up to 16 rows; those products are discarded).
 template <typename T>
-__device__ __forceinline__ void gj_candidates(int d, int ld, const T* M, const int* mark, int k, int pex, T* slotv, int* sloti) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  T best = T(-1); int bi = -1;
-  for (int i = warp + KJX_GEN_WARPS * lane; i < d; i += KJX_GEN_WARPS * 32)
-    if (!mark[i] && i != pex) { const T v = fabs(M[i * ld + k]); if (v > best) { best = v; bi = i; } }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const T ob = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (oi >= 0 && (ob > best || (ob == best && (bi < 0 || oi < bi)))) { best = ob; bi = oi; }
-  }
-  if (lane == 0) { slotv[(k & 1) * KJX_GEN_WARPS + warp] = best; sloti[(k & 1) * KJX_GEN_WARPS + warp] = bi; }
-}
-template <typename T>
-__device__ void gj_solve(const GenLayout& L, T* M, T* R, T* rv, T* X, T* xu, int* rowof, int* mark, T* slotv, int* sloti) {
-  constexpr int U = 4;
+__device__ void lu_solve_blocked(const GenLayout& L, T* M, T* R, T* rv, int* piv) {
+  constexpr int NB = 8;
   const int d = L.d, ld = L.ld, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  KJX_GEN_VEC(i, d) mark[i] = 0;
-  __syncthreads();
-  gj_candidates<T>(d, ld, M, mark, 0, -1, slotv, sloti);
-  __syncthreads();
-  for (int k = 0; k < d; ++k) {
-    int p = -1;
-    {
-      T best = T(-1);
+  for (int k0 = 0; k0 < d; k0 += NB) {
+    const int kb = (d - k0 < NB) ? d - k0 : NB;
+    if (warp == 0) {
+      for (int j = 0; j < kb; ++j) {
+        const int k = k0 + j;
+        T best = T(-1); int bi = -1;
+        for (int i = k + lane; i < d; i += 32) { const T v = fabs(M[i * ld + k]); if (v > best) { best = v; bi = i; } }
 #pragma unroll
-      for (int w = 0; w < KJX_GEN_WARPS; ++w) {
-        const T v = slotv[(k & 1) * KJX_GEN_WARPS + w]; const int i = sloti[(k & 1) * KJX_GEN_WARPS + w];
-        if (i >= 0 && (v > best || (v == best && (p < 0 || i < p)))) { best = v; p = i; }
-      }
-      if (p < 0) { for (int i = 0; i < d; ++i) if (!mark[i]) { p = i; break; } }      // column of NaNs: keep going
-    }
-    if (threadIdx.x == 0) { mark[p] = 1; rowof[k] = p; }    // read by others only after the next barrier (they exclude p explicitly)
-    const T pinv = T(1) / M[p * ld + k];
-    const T rvp = rv[p];
-    const int nm = d - k - 1;                         // columns of M still alive: k+1 .. d-1
-    for (int t = 0; t * 32 < d; ++t) {
-      const int jr = lane + 32 * t, jm = k + 1 + jr;
-      const bool hasr = jr < d, hasm = jr < nm;
-      const T pr = hasr ? R[p * ld + jr] : T(0), pm = hasm ? M[p * ld + jm] : T(0);
-      for (int i0 = warp; i0 < d; i0 += U * KJX_GEN_WARPS) {
-        T f[U], mv[U], rr[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) { const int i = i0 + u * KJX_GEN_WARPS; f[u] = (i < d && i != p) ? M[i * ld + k] * pinv : T(0); }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int i = i0 + u * KJX_GEN_WARPS;
-          mv[u] = (f[u] != T(0) && hasm) ? M[i * ld + jm] : T(0);
-          rr[u] = (f[u] != T(0) && hasr) ? R[i * ld + jr] : T(0);
+        for (int o = 16; o > 0; o >>= 1) {
+          const T ob = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (oi >= 0 && (ob > best || (ob == best && (bi < 0 || oi < bi)))) { best = ob; bi = oi; }
         }
+        const int p = (bi < 0) ? k : bi;                     // column of NaNs: keep going
+        if (lane == 0) piv[k] = p;
+        if (p != k && lane < kb) { const T t = M[k * ld + k0 + lane]; M[k * ld + k0 + lane] = M[p * ld + k0 + lane]; M[p * ld + k0 + lane] = t; }
+        __syncwarp();
+        const T pinv = T(1) / M[k * ld + k];
+        T prow[NB];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int i = i0 + u * KJX_GEN_WARPS;
-          if (f[u] != T(0)) {
-            if (hasm) M[i * ld + jm] = mv[u] - f[u] * pm;
-            if (hasr) R[i * ld + jr] = rr[u] - f[u] * pr;
-            if (t == 0 && lane == 0) rv[i] -= f[u] * rvp;
-          }
+        for (int c = 0; c < NB; ++c) prow[c] = (c > j && c < kb) ? M[k * ld + k0 + c] : T(0);
+        for (int i = k + 1 + lane; i < d; i += 32) {
+          T* row = M + i * ld + k0;
+          const T l = row[j] * pinv;
+          row[j] = l;
+#pragma unroll
+          for (int c = 0; c < NB; ++c) if (c > j && c < kb) row[c] -= l * prow[c];
         }
+        __syncwarp();
       }
-    }
-    if (k + 1 < d) {
-      __syncwarp();                                   // column k+1 of this warp's rows was written by its lane 0
-      gj_candidates<T>(d, ld, M, mark, k + 1, p, slotv, sloti);
     }
     __syncthreads();
+    // swaps + U12 = L11^-1 [M12 | R1 | rv1] for every column right of the panel (one thread per column)
+    const int nright = d - k0 - kb;
+    for (int c = threadIdx.x; c < nright + d + 1; c += blockDim.x) {
+      T* base; int st;
+      if (c < nright) { base = M + k0 + kb + c; st = ld; } else if (c < nright + d) { base = R + (c - nright); st = ld; } else { base = rv; st = 1; }
+      T x[NB];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        if (j < kb) {
+          const int k = k0 + j, p = piv[k];
+          T v = base[p * st];
+          if (p != k) base[p * st] = base[k * st];          // row k's old value moves down; row k is rewritten below
+          const T* lrow = M + k * ld + k0;
+#pragma unroll
+          for (int q = 0; q < j; ++q) v -= lrow[q] * x[q];
+          x[j] = v;
+          base[k * st] = v;
+        }
+      }
+    }
+    __syncthreads();
+    if (nright > 0) {            // kb == NB here
+      const T* L21 = M + (k0 + NB) * ld + k0;
+      T* M22 = M + (k0 + NB) * ld + k0 + NB; T* R2 = R + (k0 + NB) * ld;
+      gemm_cta<T, false, false>(nright, nright, NB, L21, M + k0 * ld + k0 + NB, ld, [&](int i, int j, T v) { M22[i * ld + j] -= v; });
+      gemm_cta<T, false, false>(nright, d, NB, L21, R + k0 * ld, ld, [&](int i, int j, T v) { R2[i * ld + j] -= v; });
+      for (int i = threadIdx.x; i < nright; i += blockDim.x) {
+        T v = rv[k0 + NB + i];
+#pragma unroll
+        for (int q = 0; q < NB; ++q) v -= L21[i * ld + q] * rv[k0 + q];
+        rv[k0 + NB + i] = v;
+      }
+      __syncthreads();
+    }
   }
-  KJX_GEN_ROWS(k, d) {
-    const int p = rowof[k];
-    const T dinv = T(1) / M[p * ld + k];
-    KJX_GEN_COLS(j, d) X[k * ld + j] = R[p * ld + j] * dinv;
-    if (lane == 0) xu[k] = rv[p] * dinv;
+  // U X = (forward-substituted right-hand sides), from the last panel up
+  for (int k0 = ((d - 1) / NB) * NB; k0 >= 0; k0 -= NB) {
+    const int kb = (d - k0 < NB) ? d - k0 : NB;
+    for (int c = threadIdx.x; c < d + 1; c += blockDim.x) {
+      T* base = (c < d) ? R + c : rv; const int st = (c < d) ? ld : 1;
+      T x[NB];
+#pragma unroll
+      for (int j = NB - 1; j >= 0; --j) {
+        if (j < kb) {
+          const T* urow = M + (k0 + j) * ld + k0;
+          T v = base[(k0 + j) * st];
+#pragma unroll
+          for (int q = NB - 1; q > j; --q) if (q < kb) v -= urow[q] * x[q];
+          x[j] = v / urow[j];
+          base[(k0 + j) * st] = x[j];
+        }
+      }
+    }
+    __syncthreads();
+    if (k0 > 0) {
+      const T* U01 = M + k0;                                 // rows 0..k0-1, columns k0..k0+kb-1
+      gemm_cta<T, false, false>(k0, d, kb, U01, R + k0 * ld, ld, [&](int i, int j, T v) { R[i * ld + j] -= v; });
+      for (int i = threadIdx.x; i < k0; i += blockDim.x) {
+        T v = rv[i];
+        for (int q = 0; q < kb; ++q) v -= U01[i * ld + q] * rv[k0 + q];
+        rv[i] = v;
+      }
+      __syncthreads();
+    }
   }
-  __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -492,11 +521,11 @@ template <typename T> __device__ void chol_solve_blocked(const GenLayout& L, con
 // working-set sizes (bytes); the same carve-up lives in global scratch when d > KJX_GEN_DMAX
 template <typename T> size_t generic_fold_smem(int d) {
   const GenLayout L = gen_layout(d);
-  return (size_t)(6 * L.msz + 4 * d + 7 * d + KJX_GEN_WARPS * d + 16 + 32) * sizeof(T) + (size_t)(d + 4) * sizeof(int) + 256;
+  return (size_t)(6 * L.msz + 4 * d + 9 * d + KJX_GEN_WARPS * d + 16 + 32) * sizeof(T) + (size_t)(d + 4) * sizeof(int) + 256;
 }
 template <typename T> size_t generic_boundary_smem(int d) {
   const GenLayout L = gen_layout(d);
-  return (size_t)(4 * L.msz + 5 * d + 16 + 32) * sizeof(T) + (size_t)(2 * d + 40) * sizeof(int) + 512;
+  return (size_t)(4 * L.msz + 7 * d + 16 + 32) * sizeof(T) + (size_t)(2 * d + 40) * sizeof(int) + 512;
 }
 template <typename T> size_t generic_filter_smem(int d) {
   const GenLayout L = gen_layout(d);
@@ -508,7 +537,20 @@ template <typename T> size_t generic_gain_smem(int d) {
 }
 template <typename T> size_t generic_smoother_smem(int d) {
   const GenLayout L = gen_layout(d);
-  return (size_t)(6 * L.msz + 4 * d + 7 * d + KJX_GEN_WARPS * d + 16 + 32) * sizeof(T) + (size_t)(3 * d + 44) * sizeof(int) + 512;
+  return (size_t)(6 * L.msz + 4 * d + 9 * d + KJX_GEN_WARPS * d + 16 + 32) * sizeof(T) + (size_t)(3 * d + 44) * sizeof(int) + 512;
+}
+
+// Scan quantities are kept in EQUILIBRATED coordinates x~ = D^-1 x with D = sqrt(diag(Pinf)): the components of a Sum
+// prior differ by many orders of magnitude in scale (high harmonics of a quasi-periodic component), and the solves of
+// the scan would otherwise only be accurate relative to the largest component — the small ones then enter the chunks
+// with errors that the smoother amplifies.  In these coordinates Pinf has a unit diagonal.  The recursions inside the
+// chunks (reference order) are NOT scaled.
+template <typename T> __device__ __forceinline__ void scale_vectors(int d, const double* Pinf, T* Dv, T* Dinv) {
+  KJX_GEN_VEC(i, d) {
+    const double v = Pinf[(size_t)i * d + i];
+    const double s = (v > 0.0) ? sqrt(v) : 1.0;
+    Dv[i] = (T)s; Dinv[i] = (T)(1.0 / s);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -523,16 +565,25 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_fold_kernel(const Gen
   T* Pinf = sc.take(L.msz);
   T* vals = sc.take(4 * d); T* b = sc.take(d); T* eta = sc.take(d); T* t1 = sc.take(d); T* Hrow = sc.take(d);
   T* av = sc.take(d); T* cv = sc.take(d); T* part = sc.take(KJX_GEN_WARPS * d); T* sh = sc.take(16);
+  T* Dv = sc.take(d); T* Dinv = sc.take(d);
   int* c0n = sc.take_int(d);
   const int64_t n0 = (int64_t)blockIdx.x * g.chunk_len, n1 = (n0 + g.chunk_len < g.N) ? n0 + g.chunk_len : g.N;
   KJX_GEN_VEC(e, 6 * L.msz) A[e] = T(0);                   // the six tiles are contiguous
+  scale_vectors<T>(d, g.Pinf, Dv, Dinv);
   __syncthreads();
-  load_dense<T>(L, g.Pinf, Pinf);
-  KJX_GEN_VEC(i, d) { A[i * ld + i] = T(1); b[i] = T(0); eta[i] = T(0); if (g.H) Hrow[i] = (T)g.H[i]; }
+  {
+    const double* Pg = g.Pinf;
+    tile_map<T>(d, [&](int i, int j) { return (T)Pg[(size_t)i * d + j] * Dinv[i] * Dinv[j]; }, [&](int i, int j, T v) { Pinf[i * ld + j] = v; });
+  }
+  KJX_GEN_VEC(i, d) { A[i * ld + i] = T(1); b[i] = T(0); eta[i] = T(0); if (g.H) Hrow[i] = (T)g.H[i] * Dv[i]; }
   __syncthreads();
   for (int64_t n = n0; n < n1; ++n) {
     build_rows<T>(g.disc, d, g.dt[n], vals, c0n);
-    if (g.H_steps) KJX_GEN_VEC(i, d) Hrow[i] = (T)g.H_steps[n * d + i];
+    KJX_GEN_VEC(r, d) {                                     // A~ = D^-1 A D  (each thread rescales the row it just built)
+      const int c0 = c0n[r] & 0xffffff, nn = c0n[r] >> 24;
+      for (int q = 0; q < nn; ++q) vals[r * 4 + q] *= Dv[c0 + q] * Dinv[r];
+    }
+    if (g.H_steps) KJX_GEN_VEC(i, d) Hrow[i] = (T)g.H_steps[n * d + i] * Dv[i];
     __syncthreads();
     rows_left<T, T>(L, vals, c0n, A, ld, nullptr, 0, A2);   // A2 <- F A
     rows_left<T, T>(L, vals, c0n, C, ld, Pinf, ld, Y);      // Y  <- F (C - Pinf)
@@ -600,19 +651,31 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_boundary_kernel(const
   const GenLayout L = gen_layout(g.d);
   const int d = L.d, dd = d * d, ld = L.ld;
   T* P = sc.take(L.msz); T* M = sc.take(L.msz); T* R = sc.take(L.msz); T* Tm = sc.take(L.msz);
-  T* m = sc.take(d); T* u = sc.take(d); T* w = sc.take(d); T* rv = sc.take(d);
-  T* slotv = sc.take(2 * KJX_GEN_WARPS);
-  int* rowof = sc.take_int(d); int* mark = sc.take_int(d); int* sloti = sc.take_int(2 * KJX_GEN_WARPS);
+  T* m = sc.take(d); T* w = sc.take(d); T* rv = sc.take(d); T* Dv = sc.take(d); T* Dinv = sc.take(d);
+  int* piv = sc.take_int(d);
   const size_t ssz = (size_t)3 * dd + 2 * d;
   KJX_GEN_VEC(e, 4 * L.msz) P[e] = T(0);
   KJX_GEN_VEC(i, d) m[i] = T(0);
+  scale_vectors<T>(d, g.Pinf, Dv, Dinv);
   __syncthreads();
+  // everything below is in the equilibrated coordinates of the fold (see scale_vectors); the states entering the
+  // chunks are stored unscaled (the filter recursion is unscaled), the informations stay scaled (only the smoother's
+  // chunk-end solve reads them, and it solves in scaled coordinates too)
   if (blockIdx.x == 0) {
-    load_dense<T>(L, g.Pinf, P);                                                     // sde_gp.py:265
+    {
+      const double* Pg = g.Pinf;                                                     // sde_gp.py:265
+      tile_map<T>(d, [&](int i, int j) { return (T)Pg[(size_t)i * d + j] * Dinv[i] * Dinv[j]; }, [&](int i, int j, T v) { P[i * ld + j] = v; });
+    }
     __syncthreads();
     for (int c = 0; c < g.nchunks; ++c) {
-      store_dense<T>(L, P, g.st_P + (size_t)c * dd);
-      KJX_GEN_VEC(i, d) g.st_m[(size_t)c * d + i] = m[i];
+      T* sP = g.st_P + (size_t)c * dd;
+      if (c == 0) {                                          // the prior itself, bit for bit
+        const double* Pg = g.Pinf;
+        tile_map<T>(d, [&](int i, int j) { return (T)Pg[(size_t)i * d + j]; }, [&](int i, int j, T v) { sP[(size_t)i * d + j] = v; });
+      } else {
+        tile_map<T>(d, [&](int i, int j) { return P[i * ld + j] * Dv[i] * Dv[j]; }, [&](int i, int j, T v) { sP[(size_t)i * d + j] = v; });
+      }
+      KJX_GEN_VEC(i, d) g.st_m[(size_t)c * d + i] = m[i] * Dv[i];
       if (c + 1 == g.nchunks) break;
       const T* A = g.sum + c * ssz; const T* C = A + dd; const T* J = A + 2 * dd; const T* b = A + 3 * dd; const T* eta = b + d;
       load_dense<T>(L, J, Tm);
@@ -622,13 +685,13 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_boundary_kernel(const
       tile_map<T>(d, [&](int i, int j) { return P[i * ld + j]; }, [&](int i, int j, T v) { R[i * ld + j] = v; });
       KJX_GEN_VEC(i, d) { T s = m[i]; for (int k = 0; k < d; ++k) s += P[i * ld + k] * eta[k]; rv[i] = s; }
       __syncthreads();
-      gj_solve<T>(L, M, R, rv, Tm, u, rowof, mark, slotv, sloti);    // Tm <- X = (I+PJ)^-1 P,  u <- (I+PJ)^-1 (m + P eta)
+      lu_solve_blocked<T>(L, M, R, rv, piv);               // R <- X = (I+PJ)^-1 P,  rv <- (I+PJ)^-1 (m + P eta)
       load_dense<T>(L, A, M);
       __syncthreads();
-      gemm_cta<T, false, false>(d, d, d, M, Tm, ld, [&](int i, int j, T v) { R[i * ld + j] = v; });          // R = A X
-      KJX_GEN_VEC(i, d) { T s = b[i]; for (int k = 0; k < d; ++k) s += M[i * ld + k] * u[k]; w[i] = s; }
+      gemm_cta<T, false, false>(d, d, d, M, R, ld, [&](int i, int j, T v) { Tm[i * ld + j] = v; });        // Tm = A X
+      KJX_GEN_VEC(i, d) { T s = b[i]; for (int k = 0; k < d; ++k) s += M[i * ld + k] * rv[k]; w[i] = s; }
       __syncthreads();
-      gemm_cta<T, false, true>(d, d, d, R, M, ld, [&](int i, int j, T v) { P[i * ld + j] = v + C[i * d + j]; });   // P' = A X A^T + C
+      gemm_cta<T, false, true>(d, d, d, Tm, M, ld, [&](int i, int j, T v) { P[i * ld + j] = v + C[i * d + j]; });   // P' = A X A^T + C
       KJX_GEN_VEC(i, d) m[i] = w[i];
       __syncthreads();
     }
@@ -649,9 +712,9 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_boundary_kernel(const
       __syncthreads();
       gemm_cta<T, false, false>(d, d, d, P, Tm, ld, [&](int i, int j, T v) { R[i * ld + j] = v; });
       __syncthreads();
-      gj_solve<T>(L, M, R, rv, P, u, rowof, mark, slotv, sloti);     // P <- Y (J_j is no longer needed), u <- the vector part
-      gemm_cta<T, true, false>(d, d, d, Tm, P, ld, [&](int i, int j, T v) { M[i * ld + j] = v + Ji[i * d + j]; });   // J' = A_i^T Y + J_i
-      KJX_GEN_VEC(i, d) { T s = etai[i]; for (int k = 0; k < d; ++k) s += Tm[k * ld + i] * u[k]; w[i] = s; }
+      lu_solve_blocked<T>(L, M, R, rv, piv);               // R <- Y, rv <- the vector part
+      gemm_cta<T, true, false>(d, d, d, Tm, R, ld, [&](int i, int j, T v) { M[i * ld + j] = v + Ji[i * d + j]; });   // J' = A_i^T Y + J_i
+      KJX_GEN_VEC(i, d) { T s = etai[i]; for (int k = 0; k < d; ++k) s += Tm[k * ld + i] * rv[k]; w[i] = s; }
       __syncthreads();
       KJX_GEN_VEC(i, d) m[i] = w[i];
       tile_map<T>(d, [&](int i, int j) { return (i == j) ? M[i * ld + j] : T(0.5) * (M[i * ld + j] + M[j * ld + i]); },   // keep J' exactly symmetric
@@ -784,10 +847,11 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_smoother_kernel(const
   T* Pf = sc.take(L.msz); T* Pp = sc.take(L.msz); T* Gt = sc.take(L.msz); T* Ps = sc.take(L.msz); T* W = sc.take(L.msz);
   T* Pinf = sc.take(L.msz);
   T* vals = sc.take(4 * d); T* mf = sc.take(d); T* mp = sc.take(d); T* ms = sc.take(d); T* dm = sc.take(d); T* Hrow = sc.take(d);
-  T* rv = sc.take(d); T* mnew = sc.take(d); T* part = sc.take(KJX_GEN_WARPS * d); T* slotv = sc.take(2 * KJX_GEN_WARPS);
-  int* c0n = sc.take_int(d); int* rowof = sc.take_int(d); int* mark = sc.take_int(d); int* sloti = sc.take_int(2 * KJX_GEN_WARPS);
+  T* rv = sc.take(d); T* mnew = sc.take(d); T* part = sc.take(KJX_GEN_WARPS * d); T* Dv = sc.take(d); T* Dinv = sc.take(d);
+  int* c0n = sc.take_int(d); int* piv = sc.take_int(d);
   const int64_t n0 = (int64_t)blockIdx.x * g.chunk_len, n1 = (n0 + g.chunk_len < g.N) ? n0 + g.chunk_len : g.N;
   KJX_GEN_VEC(e, 6 * L.msz) Pf[e] = T(0);
+  scale_vectors<T>(d, g.Pinf, Dv, Dinv);
   __syncthreads();
   load_dense<T>(L, g.Pinf, Pinf);
   KJX_GEN_VEC(i, d) if (g.H) Hrow[i] = (T)g.H[i];
@@ -797,18 +861,29 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_smoother_kernel(const
       // Last step of the chunk: smoothed = filtered x information of everything after the chunk (two-filter identity;
       // for the chunk that ends the series the information is zero and this is sde_gp.py:339).  Pp/Gt/W are scratch here.
       if (g.H_steps) KJX_GEN_VEC(i, d) Hrow[i] = (T)g.H_steps[n * d + i];
-      load_dense<T>(L, g.filt_cov_in + n * (int64_t)dd, Pf);
-      load_dense<T>(L, g.in_J + (size_t)blockIdx.x * dd, W);
-      KJX_GEN_VEC(i, d) mf[i] = g.filt_mean_in[n * d + i];
-      __syncthreads();
-      const T* eta = g.in_eta + (size_t)blockIdx.x * d;
-      gemm_cta<T, false, false>(d, d, d, Pf, W, ld, [&](int i, int j, T v) { Pp[i * ld + j] = v + ((i == j) ? T(1) : T(0)); });
-      tile_map<T>(d, [&](int i, int j) { return Pf[i * ld + j]; }, [&](int i, int j, T v) { Gt[i * ld + j] = v; });
-      KJX_GEN_VEC(i, d) { T s = mf[i]; for (int k = 0; k < d; ++k) s += Pf[i * ld + k] * eta[k]; rv[i] = s; }
-      __syncthreads();
-      gj_solve<T>(L, Pp, Gt, rv, Ps, ms, rowof, mark, slotv, sloti);  // Ps <- (I + Pf J)^-1 Pf,  ms <- (I + Pf J)^-1 (mf + Pf eta)
-      KJX_GEN_ROWS(i, d) KJX_GEN_COLS(j, d) if (i > j) Ps[i * ld + j] = Ps[j * ld + i];   // symmetric by construction; keep the upper part
-      __syncthreads();
+      const T* Pg = g.filt_cov_in + n * (int64_t)dd;
+      if (n1 == g.N) {
+        // the chunk that ends the series: nothing comes after it, smoothed = filtered (sde_gp.py:339)
+        load_dense<T>(L, Pg, Ps);
+        KJX_GEN_VEC(i, d) ms[i] = g.filt_mean_in[n * d + i];
+        __syncthreads();
+      } else {
+        // (I + P~ J~) X~ = [P~ | m~ + P~ eta~] in the equilibrated coordinates of the scan (see scale_vectors)
+        tile_map<T>(d, [&](int i, int j) { return Pg[(size_t)i * d + j] * Dinv[i] * Dinv[j]; }, [&](int i, int j, T v) { Pf[i * ld + j] = v; });
+        load_dense<T>(L, g.in_J + (size_t)blockIdx.x * dd, W);
+        KJX_GEN_VEC(i, d) mf[i] = g.filt_mean_in[n * d + i] * Dinv[i];
+        __syncthreads();
+        const T* eta = g.in_eta + (size_t)blockIdx.x * d;
+        gemm_cta<T, false, false>(d, d, d, Pf, W, ld, [&](int i, int j, T v) { Pp[i * ld + j] = v + ((i == j) ? T(1) : T(0)); });
+        tile_map<T>(d, [&](int i, int j) { return Pf[i * ld + j]; }, [&](int i, int j, T v) { Gt[i * ld + j] = v; });
+        KJX_GEN_VEC(i, d) { T s = mf[i]; for (int k = 0; k < d; ++k) s += Pf[i * ld + k] * eta[k]; rv[i] = s; }
+        __syncthreads();
+        lu_solve_blocked<T>(L, Pp, Gt, rv, piv);           // Gt <- (I + P J)^-1 P,  rv <- (I + P J)^-1 (m + P eta)
+        tile_map<T>(d, [&](int i, int j) { return ((i <= j) ? Gt[i * ld + j] : Gt[j * ld + i]) * Dv[i] * Dv[j]; },   // symmetric by construction; keep the upper part
+                    [&](int i, int j, T v) { Ps[i * ld + j] = v; });
+        KJX_GEN_VEC(i, d) ms[i] = rv[i] * Dv[i];
+        __syncthreads();
+      }
       if (g.smooth_mean && g.return_full) {
         store_dense<T>(L, Ps, g.smooth_cov + n * (int64_t)dd);
         KJX_GEN_VEC(i, d) g.smooth_mean[n * d + i] = ms[i];
