@@ -32,7 +32,7 @@ namespace kjx {
 
 constexpr int KJX_GEN_DMAX = 64;          // the working set (6 padded d x d tiles) fits one SM's shared memory up to here
 constexpr int KJX_GEN_DMAX_GLOBAL = 256;  // above it the same kernels keep their matrices in per-CTA global scratch
-constexpr int KJX_GEN_THREADS = 512;      // fold / boundary / filter / smoother: one CTA per SM, 16 warps to hide the latencies
+constexpr int KJX_GEN_THREADS = 256;      // fold / boundary / filter / smoother: one CTA per SM (512 threads cap registers at 128 and spill)
 constexpr int KJX_GEN_GAIN_THREADS = 256; // gain kernel: several smaller CTAs per SM
 constexpr int KJX_GEN_WARPS = KJX_GEN_THREADS / 32;   // most warps any generic kernel runs with
 
@@ -322,16 +322,69 @@ __device__ __forceinline__ void gemm_cta(int m, int n, int kk, const T* A, const
 // Panels of 8 columns: warp 0 factors the panel (pivot search by shuffle, row swap, rank-one update inside the panel),
 // then one thread per remaining column applies the swaps and the unit-lower 8 x 8 solve, and the rank-8 trailing
 // update of [M | R] goes through gemm_cta — 8x less shared-memory traffic than rank-one elimination, which is what
-// bounds that one.  Back substitution is blocked the same way.  piv: d ints of scratch.
+// bounds that one.  Back substitution is blocked the same way.  piv: d ints, dscr: 8 scalars of scratch.
 // M and R must not be the last tiles of the working set (fragment loads of the trailing update may run past the
 // tile by up to 16 rows; those products are discarded).
 template <typename T>
-__device__ void lu_solve_blocked(const GenLayout& L, T* M, T* R, T* rv, int* piv) {
+__device__ void lu_solve_blocked(const GenLayout& L, T* M, T* R, T* rv, int* piv, T* dscr) {
   constexpr int NB = 8;
   const int d = L.d, ld = L.ld, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int k0 = 0; k0 < d; k0 += NB) {
     const int kb = (d - k0 < NB) ? d - k0 : NB;
-    if (warp == 0) {
+    if (warp == 0 && d - k0 <= 64) {
+      // the whole panel in registers: lane l owns rows k0 + l and k0 + 32 + l; row k0 + j is slot 0 of lane j
+      const int i0 = k0 + lane, i1 = k0 + 32 + lane;
+      const bool ok0 = i0 < d, ok1 = i1 < d;
+      T a0[NB], a1[NB];
+#pragma unroll
+      for (int c = 0; c < NB; ++c) {
+        a0[c] = (ok0 && c < kb) ? M[i0 * ld + k0 + c] : T(0);
+        a1[c] = (ok1 && c < kb) ? M[i1 * ld + k0 + c] : T(0);
+      }
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        if (j < kb) {
+          const int k = k0 + j;
+          const T v0 = (ok0 && lane >= j) ? fabs(a0[j]) : T(-1), v1 = ok1 ? fabs(a1[j]) : T(-1);
+          T best = (v1 > v0) ? v1 : v0; int bi = (v1 > v0) ? i1 : i0;
+          if (!(best >= T(0))) { best = T(-1); bi = -1; }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const T ob = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (oi >= 0 && (ob > best || (ob == best && (bi < 0 || oi < bi)))) { best = ob; bi = oi; }
+          }
+          const int p = (bi < 0) ? k : bi;                   // column of NaNs: keep going
+          if (lane == 0) piv[k] = p;
+          const int lp = (p - k0) & 31; const bool sp = (p - k0) >= 32;
+          T pr[NB], kr[NB];
+#pragma unroll
+          for (int c = 0; c < NB; ++c) { pr[c] = __shfl_sync(0xffffffffu, sp ? a1[c] : a0[c], lp); kr[c] = __shfl_sync(0xffffffffu, a0[c], j); }
+          if (p != k) {
+#pragma unroll
+            for (int c = 0; c < NB; ++c) {
+              if (lane == lp) { if (sp) a1[c] = kr[c]; else a0[c] = kr[c]; }
+              if (lane == j) a0[c] = pr[c];
+            }
+          }
+          const T pinv = T(1) / pr[j];
+          if (ok0 && lane > j) {
+            const T l = a0[j] * pinv; a0[j] = l;
+#pragma unroll
+            for (int c = 0; c < NB; ++c) if (c > j) a0[c] -= l * pr[c];
+          }
+          if (ok1) {
+            const T l = a1[j] * pinv; a1[j] = l;
+#pragma unroll
+            for (int c = 0; c < NB; ++c) if (c > j) a1[c] -= l * pr[c];
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < NB; ++c) {
+        if (ok0 && c < kb) M[i0 * ld + k0 + c] = a0[c];
+        if (ok1 && c < kb) M[i1 * ld + k0 + c] = a1[c];
+      }
+    } else if (warp == 0) {
       for (int j = 0; j < kb; ++j) {
         const int k = k0 + j;
         T best = T(-1); int bi = -1;
@@ -351,10 +404,13 @@ __device__ void lu_solve_blocked(const GenLayout& L, T* M, T* R, T* rv, int* piv
         for (int c = 0; c < NB; ++c) prow[c] = (c > j && c < kb) ? M[k * ld + k0 + c] : T(0);
         for (int i = k + 1 + lane; i < d; i += 32) {
           T* row = M + i * ld + k0;
-          const T l = row[j] * pinv;
+          T rowv[NB];
+#pragma unroll
+          for (int c = 0; c < NB; ++c) rowv[c] = (c >= j && c < kb) ? row[c] : T(0);
+          const T l = rowv[j] * pinv;
           row[j] = l;
 #pragma unroll
-          for (int c = 0; c < NB; ++c) if (c > j && c < kb) row[c] -= l * prow[c];
+          for (int c = 0; c < NB; ++c) if (c > j && c < kb) row[c] = rowv[c] - l * prow[c];
         }
         __syncwarp();
       }
@@ -398,20 +454,25 @@ __device__ void lu_solve_blocked(const GenLayout& L, T* M, T* R, T* rv, int* piv
   // U X = (forward-substituted right-hand sides), from the last panel up
   for (int k0 = ((d - 1) / NB) * NB; k0 >= 0; k0 -= NB) {
     const int kb = (d - k0 < NB) ? d - k0 : NB;
+    if (threadIdx.x < kb) dscr[threadIdx.x] = T(1) / M[(k0 + threadIdx.x) * ld + k0 + threadIdx.x];
+    __syncthreads();
     for (int c = threadIdx.x; c < d + 1; c += blockDim.x) {
       T* base = (c < d) ? R + c : rv; const int st = (c < d) ? ld : 1;
       T x[NB];
 #pragma unroll
+      for (int j = 0; j < NB; ++j) x[j] = (j < kb) ? base[(k0 + j) * st] : T(0);
+#pragma unroll
       for (int j = NB - 1; j >= 0; --j) {
         if (j < kb) {
           const T* urow = M + (k0 + j) * ld + k0;
-          T v = base[(k0 + j) * st];
+          T v = x[j];
 #pragma unroll
           for (int q = NB - 1; q > j; --q) if (q < kb) v -= urow[q] * x[q];
-          x[j] = v / urow[j];
-          base[(k0 + j) * st] = x[j];
+          x[j] = v * dscr[j];
         }
       }
+#pragma unroll
+      for (int j = 0; j < NB; ++j) if (j < kb) base[(k0 + j) * st] = x[j];
     }
     __syncthreads();
     if (k0 > 0) {
@@ -651,7 +712,7 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_boundary_kernel(const
   const GenLayout L = gen_layout(g.d);
   const int d = L.d, dd = d * d, ld = L.ld;
   T* P = sc.take(L.msz); T* M = sc.take(L.msz); T* R = sc.take(L.msz); T* Tm = sc.take(L.msz);
-  T* m = sc.take(d); T* w = sc.take(d); T* rv = sc.take(d); T* Dv = sc.take(d); T* Dinv = sc.take(d);
+  T* m = sc.take(d); T* w = sc.take(d); T* rv = sc.take(d); T* Dv = sc.take(d); T* Dinv = sc.take(d); T* dscr = sc.take(16);
   int* piv = sc.take_int(d);
   const size_t ssz = (size_t)3 * dd + 2 * d;
   KJX_GEN_VEC(e, 4 * L.msz) P[e] = T(0);
@@ -685,7 +746,7 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_boundary_kernel(const
       tile_map<T>(d, [&](int i, int j) { return P[i * ld + j]; }, [&](int i, int j, T v) { R[i * ld + j] = v; });
       KJX_GEN_VEC(i, d) { T s = m[i]; for (int k = 0; k < d; ++k) s += P[i * ld + k] * eta[k]; rv[i] = s; }
       __syncthreads();
-      lu_solve_blocked<T>(L, M, R, rv, piv);               // R <- X = (I+PJ)^-1 P,  rv <- (I+PJ)^-1 (m + P eta)
+      lu_solve_blocked<T>(L, M, R, rv, piv, dscr);               // R <- X = (I+PJ)^-1 P,  rv <- (I+PJ)^-1 (m + P eta)
       load_dense<T>(L, A, M);
       __syncthreads();
       gemm_cta<T, false, false>(d, d, d, M, R, ld, [&](int i, int j, T v) { Tm[i * ld + j] = v; });        // Tm = A X
@@ -712,7 +773,7 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_boundary_kernel(const
       __syncthreads();
       gemm_cta<T, false, false>(d, d, d, P, Tm, ld, [&](int i, int j, T v) { R[i * ld + j] = v; });
       __syncthreads();
-      lu_solve_blocked<T>(L, M, R, rv, piv);               // R <- Y, rv <- the vector part
+      lu_solve_blocked<T>(L, M, R, rv, piv, dscr);               // R <- Y, rv <- the vector part
       gemm_cta<T, true, false>(d, d, d, Tm, R, ld, [&](int i, int j, T v) { M[i * ld + j] = v + Ji[i * d + j]; });   // J' = A_i^T Y + J_i
       KJX_GEN_VEC(i, d) { T s = etai[i]; for (int k = 0; k < d; ++k) s += Tm[k * ld + i] * rv[k]; w[i] = s; }
       __syncthreads();
@@ -847,7 +908,7 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_smoother_kernel(const
   T* Pf = sc.take(L.msz); T* Pp = sc.take(L.msz); T* Gt = sc.take(L.msz); T* Ps = sc.take(L.msz); T* W = sc.take(L.msz);
   T* Pinf = sc.take(L.msz);
   T* vals = sc.take(4 * d); T* mf = sc.take(d); T* mp = sc.take(d); T* ms = sc.take(d); T* dm = sc.take(d); T* Hrow = sc.take(d);
-  T* rv = sc.take(d); T* mnew = sc.take(d); T* part = sc.take(KJX_GEN_WARPS * d); T* Dv = sc.take(d); T* Dinv = sc.take(d);
+  T* rv = sc.take(d); T* mnew = sc.take(d); T* part = sc.take(KJX_GEN_WARPS * d); T* Dv = sc.take(d); T* Dinv = sc.take(d); T* dscr = sc.take(16);
   int* c0n = sc.take_int(d); int* piv = sc.take_int(d);
   const int64_t n0 = (int64_t)blockIdx.x * g.chunk_len, n1 = (n0 + g.chunk_len < g.N) ? n0 + g.chunk_len : g.N;
   KJX_GEN_VEC(e, 6 * L.msz) Pf[e] = T(0);
@@ -878,7 +939,7 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_smoother_kernel(const
         tile_map<T>(d, [&](int i, int j) { return Pf[i * ld + j]; }, [&](int i, int j, T v) { Gt[i * ld + j] = v; });
         KJX_GEN_VEC(i, d) { T s = mf[i]; for (int k = 0; k < d; ++k) s += Pf[i * ld + k] * eta[k]; rv[i] = s; }
         __syncthreads();
-        lu_solve_blocked<T>(L, Pp, Gt, rv, piv);           // Gt <- (I + P J)^-1 P,  rv <- (I + P J)^-1 (m + P eta)
+        lu_solve_blocked<T>(L, Pp, Gt, rv, piv, dscr);           // Gt <- (I + P J)^-1 P,  rv <- (I + P J)^-1 (m + P eta)
         tile_map<T>(d, [&](int i, int j) { return ((i <= j) ? Gt[i * ld + j] : Gt[j * ld + i]) * Dv[i] * Dv[j]; },   // symmetric by construction; keep the upper part
                     [&](int i, int j, T v) { Ps[i * ld + j] = v; });
         KJX_GEN_VEC(i, d) ms[i] = rv[i] * Dv[i];
