@@ -498,7 +498,7 @@ int generic_chunks(int64_t N) {
   return (int)std::max<int64_t>(1, std::min<int64_t>(p, 148 * 2));
 }
 constexpr int KJX_GEN_MAXCHUNKS = 148 * 2;
-constexpr int KJX_GEN_GAIN_GRID = 148 * 4;
+constexpr int KJX_GEN_GAIN_GRID = 148 * 3;
 // per-CTA working set when it lives in global memory (d > KJX_GEN_DMAX): the largest of the kernels' carve-ups
 template <typename T> size_t generic_scratch_bytes(int d) {
   if (d <= KJX_GEN_DMAX) return 0;

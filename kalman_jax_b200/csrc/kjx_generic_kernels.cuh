@@ -33,7 +33,7 @@ namespace kjx {
 constexpr int KJX_GEN_DMAX = 64;          // the working set (6 padded d x d tiles) fits one SM's shared memory up to here
 constexpr int KJX_GEN_DMAX_GLOBAL = 256;  // above it the same kernels keep their matrices in per-CTA global scratch
 constexpr int KJX_GEN_THREADS = 256;      // fold / boundary / filter / smoother: one CTA per SM (512 threads cap registers at 128 and spill)
-constexpr int KJX_GEN_GAIN_THREADS = 256; // gain kernel: several smaller CTAs per SM
+constexpr int KJX_GEN_GAIN_THREADS = 128; // gain kernel: three small CTAs per SM (its serial diagonal-block phases overlap across CTAs)
 constexpr int KJX_GEN_WARPS = KJX_GEN_THREADS / 32;   // most warps any generic kernel runs with
 
 template <typename T> struct GenArgs {
@@ -862,7 +862,7 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_filter_kernel(const G
 // moments (sde_gp.py:351-359), so a grid of CTAs computes them all before the (sequential) backward recursion.
 // Working set: two tiles in shared memory (61 KB at d = 59, three CTAs per SM); Pf and Pinf are read from global / L1.
 template <typename T>
-__global__ void __launch_bounds__(KJX_GEN_GAIN_THREADS, 2) generic_gain_kernel(const GenArgs<T> g, T* __restrict__ Gt_out) {
+__global__ void __launch_bounds__(KJX_GEN_GAIN_THREADS, 3) generic_gain_kernel(const GenArgs<T> g, T* __restrict__ Gt_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemCarver<T> sc(g.gscratch ? g.gscratch + (size_t)blockIdx.x * g.gscratch_stride : smem_raw);
   const GenLayout L = gen_layout(g.d);
