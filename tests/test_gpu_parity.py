@@ -352,6 +352,49 @@ def test_host_buffer_entry_point_resident_sites():
     assert rc == _lib.ERR_INVALID_ARG
 
 
+@pytest.mark.parametrize("lik_name", ["Gaussian", "Poisson"])
+def test_hyperparameter_gradient_vs_oracle_energy(lik_name):
+    """dlZ of run() / neg_log_marg_lik() (sde_gp.py:158,179: value_and_grad of the filter energy w.r.t. the raw,
+    softplus-inverse hyperparameters, stored sites held constant).  The GPU path differentiates its fast energy kernel
+    by central differences; the check is a Richardson-extrapolated difference of the ORACLE's energy,
+    i.e. a different implementation of the function and a different difference scheme.  Tolerance 1e-6 relative."""
+    from kalman_jax_b200.utils import softplus
+    kjx = _kjx()
+    N = 400
+    t, y = synth(N)
+    if lik_name == "Poisson":
+        y = np.random.default_rng(3).poisson(np.exp(0.5 * y)).astype(float)
+    var, ell, noise = 1.3, 4.0, 0.4
+    mk_lik = lambda mod: mod.likelihoods.Gaussian(noise) if lik_name == "Gaussian" else mod.likelihoods.Poisson()  # noqa: E731
+    model = kjx.SDEGP(kjx.priors.Matern52(var, ell), mk_lik(kjx), t, y, approx_inf=kjx.approximate_inference.EP(power=0.5))
+    model.run(compute_grad=False)
+    model.run(compute_grad=False)
+    sites = model.sites.site_params
+    nlml, dlZ = model.neg_log_marg_lik(compute_grad=True)
+    raw_prior, raw_lik = np.asarray(model.prior.hyp, dtype=float).copy(), np.asarray(model.likelihood.hyp, dtype=float).copy()
+    sites_np = (_np(sites[0]), _np(sites[1]))
+
+    def energy(rp, rl):
+        v, l = softplus(rp)
+        lik = oracle.likelihoods.Gaussian(float(softplus(rl).reshape(-1)[0])) if lik_name == "Gaussian" else oracle.likelihoods.Poisson()
+        ref = oracle.SDEGP(oracle.priors.Matern52(float(v), float(l)), lik, t, y, approx_inf=oracle.approx_inf.EP(power=0.5))
+        return float(ref.kalman_filter(ref.y, ref.dt, False, None, sites_np, ref.r))
+
+    assert abs(energy(raw_prior, raw_lik) - nlml) <= TOL64 * abs(nlml)
+
+    def richardson(f, h=2e-3):
+        d1, d2 = (f(h) - f(-h)) / (2 * h), (f(h / 2) - f(-h / 2)) / h
+        return (4 * d2 - d1) / 3                                     # O(h^4)
+
+    want = [richardson(lambda e, j=j: energy(raw_prior + e * np.eye(2)[j], raw_lik)) for j in range(2)]
+    got = np.asarray(dlZ[0], dtype=float).reshape(-1)
+    scale = max(abs(w) for w in want)
+    assert np.all(np.abs(got - np.asarray(want)) <= 1e-6 * scale), (got, want)
+    if lik_name == "Gaussian":
+        want_l = richardson(lambda e: energy(raw_prior, raw_lik + e))
+        assert abs(float(np.asarray(dlZ[1]).reshape(-1)[0]) - want_l) <= 1e-6 * max(scale, abs(want_l)), (dlZ[1], want_l)
+
+
 @pytest.mark.parametrize("world", [2, 3, 8])
 @pytest.mark.parametrize("prior_name", ["Matern52", "Matern32"])
 def test_time_sharded_iteration_matches_oracle(world, prior_name):
