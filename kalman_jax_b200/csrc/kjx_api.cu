@@ -490,20 +490,22 @@ __global__ void fold_shards_kernel(PinfArg<D> pinf, const double* summaries, int
 bool generic_ok(const kjx_model_t* m) {
   return m->func_dim == 1 && m->state_dim <= KJX_GEN_DMAX_GLOBAL && (m->H != nullptr || m->H_steps != nullptr);
 }
-// number of chunks: the boundary kernel walks them one after another (~0.15 ms each at d = 59) while every chunk is
-// walked concurrently (~70 us per step), so about sqrt(N / 2) chunks balance the two; at most two per SM
+// number of chunks: every chunk is walked concurrently by its own CTA (~55 us per step at d = 59 over fold, filter and
+// smoother) while the two-level boundary walk costs ~22 us per chunk, so about sqrt(2.5 N) chunks balance the two; one
+// wave of CTAs (the fold's and the smoother's working sets fill an SM's shared memory), so at most one chunk per SM
 int generic_chunks(int64_t N) {
   if (const char* e = getenv("KJX_GEN_CHUNKS")) { const int v = atoi(e); if (v >= 1) return (int)std::min<int64_t>(v, std::max<int64_t>(N, 1)); }
-  const int64_t p = (int64_t)(sqrt((double)N / 2.0) + 0.5);
-  return (int)std::max<int64_t>(1, std::min<int64_t>(p, 148 * 2));
+  const int64_t p = (int64_t)(sqrt(2.5 * (double)N) + 0.5);
+  return (int)std::max<int64_t>(1, std::min<int64_t>(p, 148));
 }
 constexpr int KJX_GEN_MAXCHUNKS = 148 * 2;
+constexpr int KJX_GEN_MAXGROUPS = 64;      // two-level boundary walk: groups of ~sqrt(0.46 nchunks) chunks
 constexpr int KJX_GEN_GAIN_GRID = 148 * 3;
 // per-CTA working set when it lives in global memory (d > KJX_GEN_DMAX): the largest of the kernels' carve-ups
 template <typename T> size_t generic_scratch_bytes(int d) {
   if (d <= KJX_GEN_DMAX) return 0;
-  return round_up(std::max(std::max(generic_smoother_smem<T>(d), generic_fold_smem<T>(d)),
-                           std::max(generic_filter_smem<T>(d), generic_boundary_smem<T>(d))), 256);
+  return round_up(std::max(std::max(std::max(generic_smoother_smem<T>(d), generic_fold_smem<T>(d)),
+                                    std::max(generic_filter_smem<T>(d), generic_boundary_smem<T>(d))), generic_group_smem<T>(d)), 256);
 }
 template <typename T> size_t generic_ws_bytes(const kjx_model_t* m, int64_t N) {
   const size_t d = (size_t)m->state_dim, n = (size_t)std::max<int64_t>(N, 1), P = KJX_GEN_MAXCHUNKS;
@@ -511,7 +513,7 @@ template <typename T> size_t generic_ws_bytes(const kjx_model_t* m, int64_t N) {
   // Pinf, H | dense filter output (kjx_run without caller buffers) | RTS gains [N,d,d] | chunk elements, states, infos, nlml
   return round_up(d * d * 8, 256) + round_up(d * 8, 256) + round_up(n * d * sizeof(T), 256) + 2 * round_up(n * d * d * sizeof(T), 256) +
          round_up(P * (3 * d * d + 2 * d) * sizeof(T), 256) + 2 * round_up(P * d * sizeof(T), 256) + 2 * round_up(P * d * d * sizeof(T), 256) +
-         round_up(P * sizeof(T), 256) + scratch;
+         round_up(P * sizeof(T), 256) + round_up(KJX_GEN_MAXGROUPS * (3 * d * d + 2 * d) * sizeof(T), 256) + scratch;
 }
 template <typename T>
 int generic_setup(const kjx_model_t* m, int64_t N, void* ws, size_t ws_bytes, GenArgs<T>& g, T** scratch_mean, T** scratch_cov,
@@ -533,6 +535,7 @@ int generic_setup(const kjx_model_t* m, int64_t N, void* ws, size_t ws_bytes, Ge
   g.st_m = (T*)take(P * d * sizeof(T)); g.in_eta = (T*)take(P * d * sizeof(T));
   g.st_P = (T*)take(P * d * d * sizeof(T)); g.in_J = (T*)take(P * d * d * sizeof(T));
   g.chunk_nlml = (T*)take(P * sizeof(T));
+  g.gsum = (T*)take(KJX_GEN_MAXGROUPS * (3 * d * d + 2 * d) * sizeof(T));
   g.gscratch_stride = generic_scratch_bytes<T>(m->state_dim);
   g.gscratch = g.gscratch_stride ? (unsigned char*)take(g.gscratch_stride * KJX_GEN_GAIN_GRID) : nullptr;
   g.nchunks = 1; g.chunk_len = std::max<int64_t>(N, 1);
@@ -556,7 +559,20 @@ template <typename T> int generic_launch_scan(const GenArgs<T>& g, cudaStream_t 
   }
   const size_t smem = g.gscratch ? 0 : generic_boundary_smem<T>(g.d);
   KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_boundary_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  generic_boundary_kernel<T><<<2, KJX_GEN_THREADS, smem, st>>>(g);
+  // a walk over the chunk elements is a dependent chain (~90 us per element at d = 59, ~105 us per combine): beyond a
+  // few dozen chunks do it in two levels — group elements, a walk over the groups, walks inside all groups at once
+  int gsz = (int)(sqrt(0.46 * (double)g.nchunks) + 0.5);
+  if (const char* e = getenv("KJX_GEN_GROUP")) gsz = atoi(e);
+  if (g.nchunks >= 24 && gsz >= 2 && (g.nchunks + gsz - 1) / gsz <= KJX_GEN_MAXGROUPS) {
+    const int ngroups = (g.nchunks + gsz - 1) / gsz;
+    const size_t gs = g.gscratch ? 0 : generic_group_smem<T>(g.d);
+    KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_group_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gs));
+    generic_group_kernel<T><<<ngroups, KJX_GEN_THREADS, gs, st>>>(g, gsz);
+    generic_boundary_kernel<T><<<2, KJX_GEN_THREADS, smem, st>>>(g, KJX_WALK_TOP, gsz);
+    generic_boundary_kernel<T><<<2 * ngroups, KJX_GEN_THREADS, smem, st>>>(g, KJX_WALK_INNER, gsz);
+  } else {
+    generic_boundary_kernel<T><<<2, KJX_GEN_THREADS, smem, st>>>(g, KJX_WALK_FLAT, 1);
+  }
   return KJX_OK;
 }
 template <typename T> int generic_launch_filter(const GenArgs<T>& g, cudaStream_t st) {

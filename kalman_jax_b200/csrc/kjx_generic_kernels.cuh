@@ -56,6 +56,7 @@ template <typename T> struct GenArgs {
                            //                         equilibrated coordinates, see scale_vectors)
   T* st_m; T* st_P;        // [nchunks][d], [nchunks][d^2]  filtered state entering every chunk
   T* in_eta; T* in_J;      // [nchunks][d], [nchunks][d^2]  information of everything after every chunk (equilibrated)
+  T* gsum;                 // [ngroups][3 d^2 + 2 d]   group elements of the two-level boundary walk
   T* chunk_nlml;           // [nchunks]
   unsigned char* gscratch; // d > KJX_GEN_DMAX: per-CTA working set in global memory instead of shared memory
   size_t gscratch_stride;
@@ -218,7 +219,7 @@ __device__ __forceinline__ void rows_right_add(const GenLayout& L, const T* vals
 }
 // dense [d][d] global <-> padded tile
 template <typename T, typename S>
-__device__ __forceinline__ void load_dense(const GenLayout& L, const S* __restrict__ src, T* dst) {
+__device__ __forceinline__ void load_dense(const GenLayout& L, const S* src, T* dst) {   // src may have been written by this kernel: no __restrict__ / read-only path
   const int d = L.d, ld = L.ld;
   tile_map<T>(d, [&](int i, int j) { return (T)src[(size_t)i * d + j]; }, [&](int i, int j, T v) { dst[i * ld + j] = v; });
 }
@@ -316,8 +317,8 @@ __device__ __forceinline__ void gemm_cta(int m, int n, int kk, const T* A, const
 }
 
 // ------------------------------------------------------------------------------------------------
-// Solve M X = [R | rv] in place by blocked LU with partial pivoting (M: d x d, overwritten by its factors; R: d x d
-// and rv: d, overwritten by the solution).  Used on I + P J / I + J C, whose eigenvalues are real and >= 1 but which
+// Solve M X = [R | Rb | rv] in place by blocked LU with partial pivoting (M: d x d, overwritten by its factors; R, Rb
+// (optional): d x d and rv: d, overwritten by the solution).  Used on I + P J / I + J C, whose eigenvalues are real and >= 1 but which
 // are not symmetric (and whose leading minors may vanish), so no Cholesky and no unpivoted elimination.
 // Panels of 8 columns: warp 0 factors the panel (pivot search by shuffle, row swap, rank-one update inside the panel),
 // then one thread per remaining column applies the swaps and the unit-lower 8 x 8 solve, and the rank-8 trailing
@@ -326,7 +327,8 @@ __device__ __forceinline__ void gemm_cta(int m, int n, int kk, const T* A, const
 // M and R must not be the last tiles of the working set (fragment loads of the trailing update may run past the
 // tile by up to 16 rows; those products are discarded).
 template <typename T>
-__device__ void lu_solve_blocked(const GenLayout& L, T* M, T* R, T* rv, int* piv, T* dscr) {
+__device__ void lu_solve_blocked(const GenLayout& L, T* M, T* R, T* Rb, T* rv, int* piv, T* dscr) {
+  const int nrb = Rb ? L.d : 0;                             // optional second block of d right-hand sides
   constexpr int NB = 8;
   const int d = L.d, ld = L.ld, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int k0 = 0; k0 < d; k0 += NB) {
@@ -418,9 +420,10 @@ __device__ void lu_solve_blocked(const GenLayout& L, T* M, T* R, T* rv, int* piv
     __syncthreads();
     // swaps + U12 = L11^-1 [M12 | R1 | rv1] for every column right of the panel (one thread per column)
     const int nright = d - k0 - kb;
-    for (int c = threadIdx.x; c < nright + d + 1; c += blockDim.x) {
+    for (int c = threadIdx.x; c < nright + d + nrb + 1; c += blockDim.x) {
       T* base; int st;
-      if (c < nright) { base = M + k0 + kb + c; st = ld; } else if (c < nright + d) { base = R + (c - nright); st = ld; } else { base = rv; st = 1; }
+      if (c < nright) { base = M + k0 + kb + c; st = ld; } else if (c < nright + d) { base = R + (c - nright); st = ld; }
+      else if (c < nright + d + nrb) { base = Rb + (c - nright - d); st = ld; } else { base = rv; st = 1; }
       T x[NB];
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
@@ -442,6 +445,7 @@ __device__ void lu_solve_blocked(const GenLayout& L, T* M, T* R, T* rv, int* piv
       T* M22 = M + (k0 + NB) * ld + k0 + NB; T* R2 = R + (k0 + NB) * ld;
       gemm_cta<T, false, false>(nright, nright, NB, L21, M + k0 * ld + k0 + NB, ld, [&](int i, int j, T v) { M22[i * ld + j] -= v; });
       gemm_cta<T, false, false>(nright, d, NB, L21, R + k0 * ld, ld, [&](int i, int j, T v) { R2[i * ld + j] -= v; });
+      if (Rb) { T* Rb2 = Rb + (k0 + NB) * ld; gemm_cta<T, false, false>(nright, d, NB, L21, Rb + k0 * ld, ld, [&](int i, int j, T v) { Rb2[i * ld + j] -= v; }); }
       for (int i = threadIdx.x; i < nright; i += blockDim.x) {
         T v = rv[k0 + NB + i];
 #pragma unroll
@@ -456,8 +460,8 @@ __device__ void lu_solve_blocked(const GenLayout& L, T* M, T* R, T* rv, int* piv
     const int kb = (d - k0 < NB) ? d - k0 : NB;
     if (threadIdx.x < kb) dscr[threadIdx.x] = T(1) / M[(k0 + threadIdx.x) * ld + k0 + threadIdx.x];
     __syncthreads();
-    for (int c = threadIdx.x; c < d + 1; c += blockDim.x) {
-      T* base = (c < d) ? R + c : rv; const int st = (c < d) ? ld : 1;
+    for (int c = threadIdx.x; c < d + nrb + 1; c += blockDim.x) {
+      T* base = (c < d) ? R + c : ((c < d + nrb) ? Rb + (c - d) : rv); const int st = (c < d + nrb) ? ld : 1;
       T x[NB];
 #pragma unroll
       for (int j = 0; j < NB; ++j) x[j] = (j < kb) ? base[(k0 + j) * st] : T(0);
@@ -478,6 +482,7 @@ __device__ void lu_solve_blocked(const GenLayout& L, T* M, T* R, T* rv, int* piv
     if (k0 > 0) {
       const T* U01 = M + k0;                                 // rows 0..k0-1, columns k0..k0+kb-1
       gemm_cta<T, false, false>(k0, d, kb, U01, R + k0 * ld, ld, [&](int i, int j, T v) { R[i * ld + j] -= v; });
+      if (Rb) gemm_cta<T, false, false>(k0, d, kb, U01, Rb + k0 * ld, ld, [&](int i, int j, T v) { Rb[i * ld + j] -= v; });
       for (int i = threadIdx.x; i < k0; i += blockDim.x) {
         T v = rv[i];
         for (int q = 0; q < kb; ++q) v -= U01[i * ld + q] * rv[k0 + q];
@@ -702,11 +707,20 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_fold_kernel(const Gen
 }
 
 // ------------------------------------------------------------------------------------------------
-// boundary: block 0 walks the chunk elements forwards (filtered state entering every chunk), block 1 backwards
-// (information of everything after every chunk).  nchunks is a few hundred at most; per chunk one Gauss-Jordan solve and
-// three d^3 products, with the chunk's matrices staged into the tile that is free at that point.
+// boundary: from the chunk elements to the filtered state entering every chunk (walk forwards) and the information
+// (eta, J) of everything after every chunk (walk backwards).  Per element one blocked-LU solve and three d^3 products,
+// with the element's matrices staged into the tile that is free at that point.  A walk is a dependent chain, so for
+// many chunks it is done in two levels (mode): groups of `gsz` consecutive chunks are first combined into one element
+// each (generic_group_kernel, one CTA per group), a TOP walk over the group elements gives the state / information at
+// the group boundaries (2 CTAs), and INNER walks fill in the chunks of every group concurrently (2 CTAs per group):
+// depth ~ 3 sqrt(nchunks) instead of nchunks.  FLAT is the single-level walk (2 CTAs) for short series.
+// Everything is in the equilibrated coordinates of the fold (see scale_vectors); the states entering the chunks are
+// stored unscaled (the filter recursion is unscaled), the informations stay scaled (only the smoother's chunk-end
+// solve reads them, and it solves in scaled coordinates too).
+enum { KJX_WALK_FLAT = 0, KJX_WALK_TOP = 1, KJX_WALK_INNER = 2 };
+
 template <typename T>
-__global__ void __launch_bounds__(KJX_GEN_THREADS) generic_boundary_kernel(const GenArgs<T> g) {
+__global__ void __launch_bounds__(KJX_GEN_THREADS) generic_boundary_kernel(const GenArgs<T> g, int mode, int gsz) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemCarver<T> sc(g.gscratch ? g.gscratch + (size_t)blockIdx.x * g.gscratch_stride : smem_raw);
   const GenLayout L = gen_layout(g.d);
@@ -715,42 +729,58 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_boundary_kernel(const
   T* m = sc.take(d); T* w = sc.take(d); T* rv = sc.take(d); T* Dv = sc.take(d); T* Dinv = sc.take(d); T* dscr = sc.take(16);
   int* piv = sc.take_int(d);
   const size_t ssz = (size_t)3 * dd + 2 * d;
+  const bool forward = (blockIdx.x & 1) == 0;
+  const int grp = blockIdx.x >> 1;
+  // the walk: `count` elements E[0..count), element k sits between output slots out(k) (before it) ... see below
+  const T* E; int count, first;
+  if (mode == KJX_WALK_TOP) { E = g.gsum; count = (g.nchunks + gsz - 1) / gsz; first = 0; }
+  else if (mode == KJX_WALK_INNER) { first = grp * gsz; count = (g.nchunks - first < gsz) ? g.nchunks - first : gsz; E = g.sum + (size_t)first * ssz; }
+  else { E = g.sum; count = g.nchunks; first = 0; }
+  // chunk whose entering state (forward) / following information (backward) belongs to position k of the walk
+  auto slot = [&](int k) -> int {
+    if (mode == KJX_WALK_TOP) return forward ? k * gsz : (((k + 1) * gsz < g.nchunks) ? (k + 1) * gsz : g.nchunks) - 1;
+    return first + k;
+  };
   KJX_GEN_VEC(e, 4 * L.msz) P[e] = T(0);
   KJX_GEN_VEC(i, d) m[i] = T(0);
   scale_vectors<T>(d, g.Pinf, Dv, Dinv);
   __syncthreads();
-  // everything below is in the equilibrated coordinates of the fold (see scale_vectors); the states entering the
-  // chunks are stored unscaled (the filter recursion is unscaled), the informations stay scaled (only the smoother's
-  // chunk-end solve reads them, and it solves in scaled coordinates too)
-  if (blockIdx.x == 0) {
-    {
+  if (forward) {
+    if (mode == KJX_WALK_INNER) {                          // start from the state the top walk left at the group's first chunk
+      const T* sP = g.st_P + (size_t)first * dd; const T* sm = g.st_m + (size_t)first * d;
+      tile_map<T>(d, [&](int i, int j) { return sP[(size_t)i * d + j] * Dinv[i] * Dinv[j]; }, [&](int i, int j, T v) { P[i * ld + j] = v; });
+      KJX_GEN_VEC(i, d) m[i] = sm[i] * Dinv[i];
+    } else {
       const double* Pg = g.Pinf;                                                     // sde_gp.py:265
       tile_map<T>(d, [&](int i, int j) { return (T)Pg[(size_t)i * d + j] * Dinv[i] * Dinv[j]; }, [&](int i, int j, T v) { P[i * ld + j] = v; });
     }
     __syncthreads();
-    for (int c = 0; c < g.nchunks; ++c) {
-      T* sP = g.st_P + (size_t)c * dd;
-      if (c == 0) {                                          // the prior itself, bit for bit
-        const double* Pg = g.Pinf;
-        tile_map<T>(d, [&](int i, int j) { return (T)Pg[(size_t)i * d + j]; }, [&](int i, int j, T v) { sP[(size_t)i * d + j] = v; });
-      } else {
-        tile_map<T>(d, [&](int i, int j) { return P[i * ld + j] * Dv[i] * Dv[j]; }, [&](int i, int j, T v) { sP[(size_t)i * d + j] = v; });
+    for (int k = 0; k < count; ++k) {
+      if (!(mode == KJX_WALK_INNER && k == 0)) {
+        const int c = slot(k);
+        T* sP = g.st_P + (size_t)c * dd;
+        if (c == 0) {                                        // the prior itself, bit for bit
+          const double* Pg = g.Pinf;
+          tile_map<T>(d, [&](int i, int j) { return (T)Pg[(size_t)i * d + j]; }, [&](int i, int j, T v) { sP[(size_t)i * d + j] = v; });
+        } else {
+          tile_map<T>(d, [&](int i, int j) { return P[i * ld + j] * Dv[i] * Dv[j]; }, [&](int i, int j, T v) { sP[(size_t)i * d + j] = v; });
+        }
+        KJX_GEN_VEC(i, d) g.st_m[(size_t)c * d + i] = m[i] * Dv[i];
       }
-      KJX_GEN_VEC(i, d) g.st_m[(size_t)c * d + i] = m[i] * Dv[i];
-      if (c + 1 == g.nchunks) break;
-      const T* A = g.sum + c * ssz; const T* C = A + dd; const T* J = A + 2 * dd; const T* b = A + 3 * dd; const T* eta = b + d;
+      if (k + 1 == count) break;
+      const T* A = E + (size_t)k * ssz; const T* C = A + dd; const T* J = A + 2 * dd; const T* b = A + 3 * dd; const T* eta = b + d;
       load_dense<T>(L, J, Tm);
       __syncthreads();
       // (I + P J) X = [P | m + P eta]
       gemm_cta<T, false, false>(d, d, d, P, Tm, ld, [&](int i, int j, T v) { M[i * ld + j] = v + ((i == j) ? T(1) : T(0)); });
       tile_map<T>(d, [&](int i, int j) { return P[i * ld + j]; }, [&](int i, int j, T v) { R[i * ld + j] = v; });
-      KJX_GEN_VEC(i, d) { T s = m[i]; for (int k = 0; k < d; ++k) s += P[i * ld + k] * eta[k]; rv[i] = s; }
+      KJX_GEN_VEC(i, d) { T s = m[i]; for (int q = 0; q < d; ++q) s += P[i * ld + q] * eta[q]; rv[i] = s; }
       __syncthreads();
-      lu_solve_blocked<T>(L, M, R, rv, piv, dscr);               // R <- X = (I+PJ)^-1 P,  rv <- (I+PJ)^-1 (m + P eta)
+      lu_solve_blocked<T>(L, M, R, (T*)nullptr, rv, piv, dscr);               // R <- X = (I+PJ)^-1 P,  rv <- (I+PJ)^-1 (m + P eta)
       load_dense<T>(L, A, M);
       __syncthreads();
       gemm_cta<T, false, false>(d, d, d, M, R, ld, [&](int i, int j, T v) { Tm[i * ld + j] = v; });        // Tm = A X
-      KJX_GEN_VEC(i, d) { T s = b[i]; for (int k = 0; k < d; ++k) s += M[i * ld + k] * rv[k]; w[i] = s; }
+      KJX_GEN_VEC(i, d) { T s = b[i]; for (int q = 0; q < d; ++q) s += M[i * ld + q] * rv[q]; w[i] = s; }
       __syncthreads();
       gemm_cta<T, false, true>(d, d, d, Tm, M, ld, [&](int i, int j, T v) { P[i * ld + j] = v + C[i * d + j]; });   // P' = A X A^T + C
       KJX_GEN_VEC(i, d) m[i] = w[i];
@@ -758,14 +788,23 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_boundary_kernel(const
     }
   } else {
     // information (eta, J): J in P, eta in m
-    for (int c = g.nchunks - 1; c >= 0; --c) {
-      store_dense<T>(L, P, g.in_J + (size_t)c * dd);
-      KJX_GEN_VEC(i, d) g.in_eta[(size_t)c * d + i] = m[i];
-      if (c == 0) break;
-      const T* A = g.sum + c * ssz; const T* C = A + dd; const T* Ji = A + 2 * dd; const T* b = A + 3 * dd; const T* etai = b + d;
+    if (mode == KJX_WALK_INNER) {                          // start from the information the top walk left after the group
+      const int c = first + count - 1;
+      load_dense<T>(L, g.in_J + (size_t)c * dd, P);
+      KJX_GEN_VEC(i, d) m[i] = g.in_eta[(size_t)c * d + i];
+      __syncthreads();
+    }
+    for (int k = count - 1; k >= 0; --k) {
+      if (!(mode == KJX_WALK_INNER && k == count - 1)) {
+        const int c = slot(k);
+        store_dense<T>(L, P, g.in_J + (size_t)c * dd);
+        KJX_GEN_VEC(i, d) g.in_eta[(size_t)c * d + i] = m[i];
+      }
+      if (k == 0) break;
+      const T* A = E + (size_t)k * ssz; const T* C = A + dd; const T* Ji = A + 2 * dd; const T* b = A + 3 * dd; const T* etai = b + d;
       // (I + J_j C_i) Y = [J_j A_i | eta_j - J_j b_i]
       load_dense<T>(L, C, Tm);
-      KJX_GEN_VEC(i, d) { T s = m[i]; for (int k = 0; k < d; ++k) s -= P[i * ld + k] * b[k]; rv[i] = s; }
+      KJX_GEN_VEC(i, d) { T s = m[i]; for (int q = 0; q < d; ++q) s -= P[i * ld + q] * b[q]; rv[i] = s; }
       __syncthreads();
       gemm_cta<T, false, false>(d, d, d, P, Tm, ld, [&](int i, int j, T v) { M[i * ld + j] = v + ((i == j) ? T(1) : T(0)); });
       __syncthreads();
@@ -773,15 +812,76 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_boundary_kernel(const
       __syncthreads();
       gemm_cta<T, false, false>(d, d, d, P, Tm, ld, [&](int i, int j, T v) { R[i * ld + j] = v; });
       __syncthreads();
-      lu_solve_blocked<T>(L, M, R, rv, piv, dscr);               // R <- Y, rv <- the vector part
+      lu_solve_blocked<T>(L, M, R, (T*)nullptr, rv, piv, dscr);               // R <- Y, rv <- the vector part
       gemm_cta<T, true, false>(d, d, d, Tm, R, ld, [&](int i, int j, T v) { M[i * ld + j] = v + Ji[i * d + j]; });   // J' = A_i^T Y + J_i
-      KJX_GEN_VEC(i, d) { T s = etai[i]; for (int k = 0; k < d; ++k) s += Tm[k * ld + i] * rv[k]; w[i] = s; }
+      KJX_GEN_VEC(i, d) { T s = etai[i]; for (int q = 0; q < d; ++q) s += Tm[q * ld + i] * rv[q]; w[i] = s; }
       __syncthreads();
       KJX_GEN_VEC(i, d) m[i] = w[i];
       tile_map<T>(d, [&](int i, int j) { return (i == j) ? M[i * ld + j] : T(0.5) * (M[i * ld + j] + M[j * ld + i]); },   // keep J' exactly symmetric
                   [&](int i, int j, T v) { P[i * ld + j] = v; });
       __syncthreads();
     }
+  }
+}
+
+// group elements: CTA `grp` combines the elements of its gsz consecutive chunks, earliest first, into gsum[grp]
+// (the accumulator lives there).  acc (x) e  (Sarkka & Garcia-Fernandez 2021, Lemma 8) with
+// M = I + C_a J_e and ONE solve M [X_A | X_C | x_b] = [A_a | C_a | b_a + C_a eta_e]:
+//   A = A_e X_A,  b = A_e x_b + b_e,  C = A_e X_C A_e^T + C_e,
+//   J = A_a^T J_e X_A + J_a                      (push-through: M^-T J_e = J_e M^-1),
+//   eta = A_a^T (v - J_e X_C v) + eta_a,  v = eta_e - J_e b_a      (M^-T = I - J_e M^-1 C_a).
+template <typename T> size_t generic_group_smem(int d) {
+  const GenLayout L = gen_layout(d);
+  return (size_t)(5 * L.msz + 8 * d + 16 + 32) * sizeof(T) + (size_t)(d + 8) * sizeof(int) + 512;
+}
+template <typename T>
+__global__ void __launch_bounds__(KJX_GEN_THREADS) generic_group_kernel(const GenArgs<T> g, int gsz) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmemCarver<T> sc(g.gscratch ? g.gscratch + (size_t)blockIdx.x * g.gscratch_stride : smem_raw);
+  const GenLayout L = gen_layout(g.d);
+  const int d = L.d, dd = d * d, ld = L.ld;
+  T* T0 = sc.take(L.msz); T* T1 = sc.take(L.msz); T* T2 = sc.take(L.msz); T* T3 = sc.take(L.msz); T* T4 = sc.take(L.msz);
+  T* rv = sc.take(d); T* v = sc.take(d); T* w1 = sc.take(d); T* w2 = sc.take(d); T* bn = sc.take(d); T* en = sc.take(d); T* dscr = sc.take(16);
+  int* piv = sc.take_int(d);
+  const size_t ssz = (size_t)3 * dd + 2 * d;
+  const int first = blockIdx.x * gsz, count = (g.nchunks - first < gsz) ? g.nchunks - first : gsz;
+  T* acc = g.gsum + (size_t)blockIdx.x * ssz;
+  KJX_GEN_VEC(e, 5 * L.msz) T0[e] = T(0);
+  for (size_t e = threadIdx.x; e < ssz; e += blockDim.x) acc[e] = g.sum[(size_t)first * ssz + e];
+  __syncthreads();
+  T* Aa = acc; T* Ca = acc + dd; T* Ja = acc + 2 * dd; T* ba = acc + 3 * dd; T* ea = ba + d;
+  for (int k = 1; k < count; ++k) {
+    const T* Ae = g.sum + (size_t)(first + k) * ssz; const T* Ce = Ae + dd; const T* Je = Ae + 2 * dd; const T* be = Ae + 3 * dd; const T* ee = be + d;
+    load_dense<T>(L, Aa, T1); load_dense<T>(L, Ca, T2); load_dense<T>(L, Je, T3);
+    __syncthreads();
+    gemm_cta<T, false, false>(d, d, d, T2, T3, ld, [&](int i, int j, T x) { T0[i * ld + j] = x + ((i == j) ? T(1) : T(0)); });   // M = I + C_a J_e
+    KJX_GEN_VEC(i, d) {
+      T s = ba[i], t = ee[i];
+      for (int q = 0; q < d; ++q) { s += T2[i * ld + q] * ee[q]; t -= T3[i * ld + q] * ba[q]; }
+      rv[i] = s; v[i] = t;                                   // b_a + C_a eta_e ;  v = eta_e - J_e b_a
+    }
+    __syncthreads();
+    lu_solve_blocked<T>(L, T0, T1, T2, rv, piv, dscr);       // T1 <- X_A, T2 <- X_C, rv <- x_b
+    gemm_cta<T, false, false>(d, d, d, T3, T1, ld, [&](int i, int j, T x) { T4[i * ld + j] = x; });          // T4 = J_e X_A
+    KJX_GEN_VEC(i, d) { T s = T(0); for (int q = 0; q < d; ++q) s += T2[i * ld + q] * v[q]; w1[i] = s; }     // X_C v
+    load_dense<T>(L, Aa, T0);
+    __syncthreads();
+    KJX_GEN_VEC(i, d) { T s = v[i]; for (int q = 0; q < d; ++q) s -= T3[i * ld + q] * w1[q]; w2[i] = s; }    // M^-T v
+    __syncthreads();
+    gemm_cta<T, true, false>(d, d, d, T0, T4, ld, [&](int i, int j, T x) { T3[i * ld + j] = x + Ja[i * d + j]; });   // J = A_a^T J_e X_A + J_a
+    KJX_GEN_VEC(i, d) { T s = ea[i]; for (int q = 0; q < d; ++q) s += T0[q * ld + i] * w2[q]; en[i] = s; }
+    __syncthreads();
+    tile_map<T>(d, [&](int i, int j) { return (i == j) ? T3[i * ld + j] : T(0.5) * (T3[i * ld + j] + T3[j * ld + i]); },
+                [&](int i, int j, T x) { Ja[(size_t)i * d + j] = x; });
+    load_dense<T>(L, Ae, T0);
+    __syncthreads();
+    gemm_cta<T, false, false>(d, d, d, T0, T1, ld, [&](int i, int j, T x) { Aa[(size_t)i * d + j] = x; });   // A = A_e X_A
+    gemm_cta<T, false, false>(d, d, d, T0, T2, ld, [&](int i, int j, T x) { T4[i * ld + j] = x; });          // T4 = A_e X_C
+    KJX_GEN_VEC(i, d) { T s = be[i]; for (int q = 0; q < d; ++q) s += T0[i * ld + q] * rv[q]; bn[i] = s; }
+    __syncthreads();
+    gemm_cta<T, false, true>(d, d, d, T4, T0, ld, [&](int i, int j, T x) { Ca[(size_t)i * d + j] = x + Ce[i * d + j]; });   // C = A_e X_C A_e^T + C_e
+    KJX_GEN_VEC(i, d) { ba[i] = bn[i]; ea[i] = en[i]; }
+    __syncthreads();
   }
 }
 
@@ -939,7 +1039,7 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_smoother_kernel(const
         tile_map<T>(d, [&](int i, int j) { return Pf[i * ld + j]; }, [&](int i, int j, T v) { Gt[i * ld + j] = v; });
         KJX_GEN_VEC(i, d) { T s = mf[i]; for (int k = 0; k < d; ++k) s += Pf[i * ld + k] * eta[k]; rv[i] = s; }
         __syncthreads();
-        lu_solve_blocked<T>(L, Pp, Gt, rv, piv, dscr);           // Gt <- (I + P J)^-1 P,  rv <- (I + P J)^-1 (m + P eta)
+        lu_solve_blocked<T>(L, Pp, Gt, (T*)nullptr, rv, piv, dscr);           // Gt <- (I + P J)^-1 P,  rv <- (I + P J)^-1 (m + P eta)
         tile_map<T>(d, [&](int i, int j) { return ((i <= j) ? Gt[i * ld + j] : Gt[j * ld + i]) * Dv[i] * Dv[j]; },   // symmetric by construction; keep the upper part
                     [&](int i, int j, T v) { Ps[i * ld + j] = v; });
         KJX_GEN_VEC(i, d) ms[i] = rv[i] * Dv[i];

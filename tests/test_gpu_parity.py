@@ -352,6 +352,32 @@ def test_host_buffer_entry_point_resident_sites():
     assert rc == _lib.ERR_INVALID_ARG
 
 
+def test_generic_path_two_level_boundary_walk_vs_oracle():
+    """Sum prior (d = 31) on a series long enough (N = 1500 -> 27 chunks) for the generic path's two-level boundary
+    walk (group elements, walk over groups, walks inside groups): three iterations against the sequential oracle."""
+    kjx = _kjx()
+    N = 1500
+    rng = np.random.default_rng(7)
+    t = np.cumsum(rng.uniform(0.5, 1.5, N))
+    y = rng.poisson(np.exp(0.3 * np.sin(2 * np.pi * t / 365.0) - 0.5)).astype(float)
+    mk = lambda mod, inf: mod.SDEGP(  # noqa: E731
+        mod.priors.Sum([mod.priors.Matern52(variance=2., lengthscale=400.),
+                        mod.priors.QuasiPeriodicMatern32(variance=1., lengthscale_periodic=2., period=365., lengthscale_matern=3000.)]),
+        mod.likelihoods.Poisson(), t, y, approx_inf=inf.EKS(damping=0.7))
+    model, ref = mk(kjx, kjx.approximate_inference), mk(oracle, oracle.approx_inf)
+    for it in range(3):
+        nlml, _ = model.run(compute_grad=False, store_posterior=True)
+        want_nlml, (wfm, wfP, wsites) = ref.kalman_filter(ref.y, ref.dt, True, None, ref.sites.site_params, ref.r)
+        if ref.sites.site_params is None:
+            ref.sites.site_params = wsites
+        w_new, wsm, wsc = ref.rauch_tung_striebel_smoother(wfm, wfP, ref.dt, True, False, ref.y, ref.sites.site_params, ref.r)
+        ref.sites.site_params = w_new
+        assert abs(nlml - want_nlml) <= TOL64 * abs(want_nlml), (it, nlml, want_nlml)
+        assert rel_err(_np(model.posterior[0]), wsm) < TOL64 and rel_err(_np(model.posterior[1]), wsc) < TOL64
+        assert rel_err(_np(model.sites.site_params[0]), w_new[0]) < TOL64
+        assert rel_err(_np(model.sites.site_params[1]), w_new[1]) < TOL64
+
+
 @pytest.mark.parametrize("lik_name", ["Gaussian", "Poisson"])
 def test_hyperparameter_gradient_vs_oracle_energy(lik_name):
     """dlZ of run() / neg_log_marg_lik() (sde_gp.py:158,179: value_and_grad of the filter energy w.r.t. the raw,
