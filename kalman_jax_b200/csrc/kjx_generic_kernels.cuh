@@ -498,8 +498,8 @@ __device__ void lu_solve_blocked(const GenLayout& L, T* M, T* R, T* Rb, T* rv, i
 // diagonal block with one row per lane held in registers (right-looking, shuffles) and replaces it by its INVERSE
 // (strict upper part zeroed); the panel below (L21 = A21 L11^-T) and the trailing update then go through gemm_cta.
 // 3 barriers per panel.  On return the tile holds L below the diagonal blocks and L11^-1 in them, which is what
-// chol_solve_blocked wants.  A non-positive pivot gives NaN, like a failed potrf propagated by jaxlib.
-template <typename T> __device__ void chol_blocked(const GenLayout& L, T* W) {
+// chol_solve_blocked wants.  A non-positive pivot gives NaN, like a failed potrf propagated by jaxlib.  scr16: 16 scalars.
+template <typename T> __device__ void chol_blocked(const GenLayout& L, T* W, T* scr16) {
   const int d = L.d, ld = L.ld, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int k0 = 0; k0 < d; k0 += 16) {
     const int kb = (d - k0 < 16) ? d - k0 : 16;
@@ -520,19 +520,27 @@ template <typename T> __device__ void chol_blocked(const GenLayout& L, T* W) {
           if (lane >= c) a[c] -= a[j] * lcj;
         }
       }
-      // inverse: lane c < 16 computes column c of L^-1 by forward substitution; L[i][k] comes from lane i's registers
+      // L goes back to the tile (1 / L[j][j] to scr16), then lane c < 16 computes column c of L^-1 by forward
+      // substitution with broadcast reads of L — the factor's registers are dead by then
+      if (lane < 16) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          if (c < lane && lane < kb) D[lane * ld + c] = a[c];
+          if (c == lane) scr16[lane] = a[c];
+        }
+      }
+      __syncwarp();
       T x[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         T v = (i == lane) ? T(1) : T(0);
+        if (i < kb) {
 #pragma unroll
-        for (int k = 0; k < i; ++k) {
-          const T lik = __shfl_sync(0xffffffffu, a[k], i);             // L[i][k]
-          v -= lik * x[k];
+          for (int k = 0; k < i; ++k) v -= D[i * ld + k] * x[k];
         }
-        const T ri = __shfl_sync(0xffffffffu, a[i], i);                  // 1 / L[i][i]  (every lane takes part in the shuffle)
-        x[i] = (i >= lane) ? v * ri : T(0);
+        x[i] = (i >= lane) ? v * scr16[i] : T(0);
       }
+      __syncwarp();
       // lane c holds column c of the inverse: X[i][c] = x[i]; write the block (zero above the diagonal)
       if (lane < 16) {
 #pragma unroll
@@ -968,7 +976,7 @@ __global__ void __launch_bounds__(KJX_GEN_GAIN_THREADS, 3) generic_gain_kernel(c
   const GenLayout L = gen_layout(g.d);
   const int d = L.d, dd = d * d, ld = L.ld;
   T* W = sc.take(L.msz); T* Gt = sc.take(L.msz);
-  T* vals = sc.take(4 * d);
+  T* vals = sc.take(4 * d); T* scr16 = sc.take(16);
   int* c0n = sc.take_int(d); int* bstart = sc.take_int(d + 1);
   KJX_GEN_VEC(e, 2 * L.msz) W[e] = T(0);
   build_rows<T>(g.disc, d, T(0), vals, c0n);                 // block structure of A: first rows of the diagonal blocks
@@ -990,7 +998,7 @@ __global__ void __launch_bounds__(KJX_GEN_GAIN_THREADS, 3) generic_gain_kernel(c
     __syncthreads();
     rows_left_inplace<T>(L, vals, c0n, bstart, nblk, Gt);                           // Gt <- A Pf                  (:353)
     __syncthreads();
-    chol_blocked<T>(L, W);                                                          // utils.py:29
+    chol_blocked<T>(L, W, scr16);                                                   // utils.py:29
     chol_solve_blocked<T>(L, W, Gt, d);                                             // :359, utils.py:30
     store_dense<T>(L, Gt, Gt_out + n * (int64_t)dd);
     __syncthreads();
