@@ -227,6 +227,15 @@ int kjx_smoother_apply_f64(const kjx_model_t* m, int64_t N, const double* dt, co
                            double* new_site_mean /*?*/, double* new_site_cov /*?*/,
                            void* ws, size_t ws_bytes, uint32_t flags, kjx_stream_t stream);
 
+/* ---- prior samples (SDEGP.prior_sample, sde_gp.py:386-417): num_samps independent draws of f = H x along the
+ * series, x_0 = chol(Pinf) eps, x_k = A(dt_k) x_{k-1} + chol(Q(dt_k) + 1e-6 I) eps.  f_sample: DEVICE [N, num_samps]
+ * (the reference's [N, func_dim = 1, num_samps]).  Counter-based Philox keyed by `seed`: the same seed gives the
+ * same draws; parity with the reference's PRNGKey(i * k + k) stream is in distribution only.  Block-diagonal priors
+ * with a constant measurement row and state_dim <= 64 (the reference has no spatio-temporal sampling either). -- */
+int kjx_prior_sample_workspace_bytes(const kjx_model_t* m, int64_t N, int32_t num_samps, size_t* bytes);
+int kjx_prior_sample_f64(const kjx_model_t* m, int64_t N, const double* dt, int32_t num_samps, uint64_t seed,
+                         double* f_sample, void* ws, size_t ws_bytes, kjx_stream_t stream);
+
 /* ---- host-buffer entry point (end-to-end path): one run() iteration where every data array is a
  * HOST pointer (pinned memory for full PCIe speed).  Inputs are copied to the device, the fused
  * filter/smoother/site-update runs, new sites (+ optional posterior marginals) and nlml are copied back;

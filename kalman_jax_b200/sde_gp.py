@@ -385,6 +385,53 @@ class SDEGP(object):
         idx = torch.as_tensor(test_id, device=self.device)
         return torch.squeeze(pm[idx]), torch.squeeze(pc[idx])
 
+    # ------------------------------------------------------------------ sde_gp.py:386-417
+    def prior_sample(self, num_samps, t=None, seed=0):
+        """num_samps draws of f ~ N(0, K) at the (sorted) inputs t, [N, func_dim, num_samps] like the reference.
+        kjx_prior_sample: the per-step noise factorisations run in parallel over time, one warp walks each sample."""
+        params = self._params(None)
+        if t is None:
+            t = self.t
+        else:
+            t = np.asarray(t, dtype=np.float64)
+            t = t[np.argsort(t[:, 0])]                                              # :398-399
+        dt = np.concatenate([np.array([0.0]), np.diff(t[:, 0])])                    # :400
+        N = dt.shape[0]
+        model = self._model(params, None)
+        dt_d = self._dev(dt)
+        out = torch.empty(N, self.func_dim, int(num_samps), dtype=torch.float64, device=self.device)
+        nbytes = C.c_size_t(0)
+        _lib.check(_lib.lib().kjx_prior_sample_workspace_bytes(model.ref(), C.c_int64(N), C.c_int32(int(num_samps)), C.byref(nbytes)),
+                   "kjx_prior_sample_workspace_bytes")
+        ws = torch.empty(max(nbytes.value, 256), dtype=torch.uint8, device=self.device)
+        _lib.check(_lib.lib().kjx_prior_sample_f64(model.ref(), C.c_int64(N), _lib.ptr(dt_d), C.c_int32(int(num_samps)),
+                                                   C.c_uint64(int(seed)), _lib.ptr(out), _lib.ptr(ws), C.c_size_t(ws.numel()),
+                                                   _stream(self.device)), "kjx_prior_sample")
+        return out
+
+    # ------------------------------------------------------------------ sde_gp.py:419-450
+    def posterior_sample(self, num_samps, t=None, r=None, seed=0):
+        """Posterior draws at the test inputs by smoothing prior draws through the Gaussian sites (Doucet's conditional
+        simulation, as the reference does it): prior_samp - smooth(prior_samp + site noise) + post_mean."""
+        if t is None:
+            t, r = self.t, self.r
+        (t_all, y_all, r_all, r_test, dt_all, train_id, test_id, mask) = test_input_admin(self.t, self.y, self.r, t, None, r)
+        y_all = np.where(np.isnan(y_all), 0.0, y_all)
+        post_mean, _, (site_mean, site_cov) = self.predict_everywhere(y_all, r_all, dt_all, train_id, mask)      # :438
+        prior_samp = self.prior_sample(num_samps, t=t_all, seed=seed)                                            # :439
+        gen = torch.Generator(device=self.device)
+        gen.manual_seed(int(seed) + 123)
+        noise = torch.randn(prior_samp.shape, generator=gen, dtype=torch.float64, device=self.device)
+        prior_samp_y = prior_samp + torch.sqrt(site_cov.reshape(-1, 1, 1)) * noise                               # utils.py:247-250
+        smoothed = torch.empty_like(prior_samp_y)
+        zeros = np.zeros_like(y_all)
+        for i in range(int(num_samps)):                                                                         # :443-449
+            sm_i, _, _ = self.predict_everywhere(zeros, r_all, dt_all, train_id, mask,
+                                                 (prior_samp_y[..., i].reshape(-1, 1, 1).contiguous(), site_cov), sampling=True)
+            smoothed[..., i] = sm_i[..., 0]
+        idx = torch.as_tensor(test_id, device=self.device)
+        return torch.squeeze(prior_samp - smoothed + post_mean)[idx]                                             # :450
+
     # ------------------------------------------------------------------ sde_gp.py:110-143
     def negative_log_predictive_density(self, t=None, y=None, r=None):
         if t is None:

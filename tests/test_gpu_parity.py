@@ -378,6 +378,67 @@ def test_generic_path_two_level_boundary_walk_vs_oracle():
         assert rel_err(_np(model.sites.site_params[1]), w_new[1]) < TOL64
 
 
+def _state_space_cov(prior, t):
+    """cov(f(t_i), f(t_j)) = H A(|t_j - t_i|) Pinf H^T of a stationary state-space prior, from the ORACLE's matrices."""
+    H, Pinf = prior.kernel_to_state_space()
+    H = np.asarray(H).reshape(1, -1)
+    n = len(t)
+    K = np.zeros((n, n))
+    for i in range(n):
+        for j in range(i, n):
+            A = prior.state_transition(t[j] - t[i])
+            K[i, j] = K[j, i] = float((H @ A @ Pinf @ H.T)[0, 0])
+    return K
+
+
+@pytest.mark.parametrize("prior_name", ["Matern32", "Sum"])
+def test_prior_sample_matches_the_prior_covariance(prior_name):
+    """SDEGP.prior_sample (sde_gp.py:386-417) on the GPU: the draws' sample covariance against the prior covariance
+    computed from the oracle's state-space matrices (parity for sampling is in distribution); same seed -> same draws."""
+    kjx = _kjx()
+    rng = np.random.default_rng(5)
+    t = np.cumsum(rng.uniform(0.2, 1.5, 10))
+    y = np.zeros_like(t)
+    if prior_name == "Matern32":
+        mk = lambda mod: mod.priors.Matern32(1.5, 2.0)  # noqa: E731
+    else:
+        mk = lambda mod: mod.priors.Sum([mod.priors.Matern52(variance=2., lengthscale=3.),  # noqa: E731
+                                         mod.priors.QuasiPeriodicMatern32(variance=1., lengthscale_periodic=2., period=4.,
+                                                                          lengthscale_matern=20.)])
+    model = kjx.SDEGP(mk(kjx), kjx.likelihoods.Gaussian(0.1), t, y)
+    S = 20000
+    f = _np(model.prior_sample(S, seed=11))
+    assert f.shape == (len(t), 1, S) and np.all(np.isfinite(f))
+    f = f[:, 0, :]
+    K = _state_space_cov(mk(oracle), t)
+    Khat = f @ f.T / S
+    # standard error of a covariance entry: sqrt((K_ii K_jj + K_ij^2) / S) <= sqrt(2) max(K) / sqrt(S); 5 sigma
+    tol = 5.0 * np.sqrt(2.0) * np.max(np.diag(K)) / np.sqrt(S)
+    assert np.max(np.abs(Khat - K)) < tol, (np.max(np.abs(Khat - K)), tol)
+    assert np.max(np.abs(f.mean(axis=1))) < 5.0 * np.sqrt(np.max(np.diag(K)) / S)
+    assert np.array_equal(f, _np(model.prior_sample(S, seed=11))[:, 0, :])
+    assert not np.array_equal(f[:, :64], _np(model.prior_sample(64, seed=12))[:, 0, :])
+
+
+def test_posterior_sample_moments_match_predict():
+    """SDEGP.posterior_sample (sde_gp.py:419-450): smoothing prior draws through the sites must reproduce the posterior
+    mean and variance that predict() reports at the test inputs."""
+    kjx = _kjx()
+    t, y = synth(60)
+    model = kjx.SDEGP(kjx.priors.Matern52(1.0, 1.0), kjx.likelihoods.Gaussian(0.3), t, y,
+                      approx_inf=kjx.approximate_inference.EP(power=1.0))
+    model.run(compute_grad=False)
+    model.run(compute_grad=False)
+    t_test = np.linspace(t[0] - 0.5, t[-1] + 0.7, 23)
+    pm, pv = model.predict(t=t_test)
+    S = 3000
+    samp = _np(model.posterior_sample(S, t=t_test, seed=3))
+    assert samp.shape == (len(t_test), S)
+    pm, pv = _np(pm), _np(pv)
+    assert np.max(np.abs(samp.mean(axis=1) - pm) / np.sqrt(pv / S)) < 5.0
+    assert np.max(np.abs(samp.var(axis=1) / pv - 1.0)) < 5.0 * np.sqrt(2.0 / S)
+
+
 @pytest.mark.parametrize("lik_name", ["Gaussian", "Poisson"])
 def test_hyperparameter_gradient_vs_oracle_energy(lik_name):
     """dlZ of run() / neg_log_marg_lik() (sde_gp.py:158,179: value_and_grad of the filter energy w.r.t. the raw,
