@@ -58,16 +58,20 @@ enum kjx_status {
 enum kjx_block_kind {
   KJX_BLOCK_MATERN32 = 1,      /* 2x2, priors.py:163-175   : lam = sqrt(3)/ell                    */
   KJX_BLOCK_MATERN52 = 2,      /* 3x3, priors.py:238-255   : lam = sqrt(5)/ell                    */
-  KJX_BLOCK_QP_MATERN32 = 3    /* 4x4 harmonic block of QuasiPeriodicMatern32, priors.py:1076-1084:
+  KJX_BLOCK_QP_MATERN32 = 3,   /* 4x4 harmonic block of QuasiPeriodicMatern32, priors.py:1076-1084:
                                   exp(-dt lam) [[(1+dt lam)R, dt R],[-dt lam^2 R,(1-dt lam)R]],
                                   R = rotation(dt*omega), utils.py:253-265                        */
+  KJX_BLOCK_MATERN12 = 4,      /* 1x1, priors.py:94-104 (Exponential / Matern12): exp(-dt lam), lam = 1/ell */
+  KJX_BLOCK_ROTATION = 5,      /* 2x2, exp(-dt lam) R(dt omega): Cosine (priors.py:397-408, lam = 0), a harmonic
+                                  of Periodic (:791-820, lam = 0) or of QuasiPeriodicMatern12 (:910-939, lam = 1/ell) */
+  KJX_BLOCK_MATERN72 = 6       /* 4x4, priors.py:326-350   : lam = sqrt(7)/ell                    */
 };
 
 typedef struct kjx_block {
   int32_t kind;    /* kjx_block_kind                                                              */
   int32_t count;   /* this block repeated `count` times (spatio-temporal: M inducing points)      */
   double lam;      /* decay rate                                                                  */
-  double omega;    /* angular frequency of the harmonic (KJX_BLOCK_QP_MATERN32 only)              */
+  double omega;    /* angular frequency of the harmonic (KJX_BLOCK_QP_MATERN32, KJX_BLOCK_ROTATION) */
 } kjx_block_t;
 
 enum kjx_likelihood {

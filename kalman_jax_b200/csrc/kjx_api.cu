@@ -39,7 +39,7 @@ bool model_basic_ok(const kjx_model_t* m) {
   for (int b = 0; b < m->n_blocks; ++b) {
     const kjx_block_t& k = m->blocks[b];
     if (k.count <= 0) return false;
-    int bs = k.kind == KJX_BLOCK_MATERN32 ? 2 : k.kind == KJX_BLOCK_MATERN52 ? 3 : k.kind == KJX_BLOCK_QP_MATERN32 ? 4 : -1;
+    int bs = block_size(k.kind);
     if (bs < 0) return false;
     d += bs * k.count;
   }

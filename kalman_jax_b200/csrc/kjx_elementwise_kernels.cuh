@@ -36,13 +36,18 @@ struct DiscArgs {
   kjx_block_t blocks[KJX_MAX_BLOCKS];
 };
 
+// rows (= columns) of one diagonal block of each kind
+__host__ __device__ __forceinline__ int block_size(int kind) {
+  return kind == KJX_BLOCK_MATERN12 ? 1 : (kind == KJX_BLOCK_MATERN32 || kind == KJX_BLOCK_ROTATION) ? 2 : kind == KJX_BLOCK_MATERN52 ? 3
+         : (kind == KJX_BLOCK_QP_MATERN32 || kind == KJX_BLOCK_MATERN72) ? 4 : -1;
+}
 // Row r of A(dt): at most 4 non-zeros starting at column c0.  Expressions follow the reference's order.
 template <typename T>
 __device__ __forceinline__ void transition_row(const DiscArgs& da, int r, T dt, int& c0, int& nnz, T (&v)[4]) {
   int base = 0;
   for (int b = 0; b < da.n_blocks; ++b) {
     const kjx_block_t& blk = da.blocks[b];
-    const int bs = blk.kind == KJX_BLOCK_MATERN32 ? 2 : (blk.kind == KJX_BLOCK_MATERN52 ? 3 : 4);
+    const int bs = block_size(blk.kind);
     const int span = bs * blk.count;
     if (r < base + span) {
       const int rr = (r - base) % bs;
@@ -57,6 +62,27 @@ __device__ __forceinline__ void transition_row(const DiscArgs& da, int r, T dt, 
         if (rr == 0) { v[0] = e * (dt * (lam * (T(0.5) * dtlam + T(1))) + T(1)); v[1] = e * (dt * (dtlam + T(1))); v[2] = e * (dt * (T(0.5) * dt)); }
         else if (rr == 1) { v[0] = e * (dt * (T(-0.5) * dtlam * lam2)); v[1] = e * (dt * (lam * (T(1) - dtlam)) + T(1)); v[2] = e * (dt * (T(1) - T(0.5) * dtlam)); }
         else { v[0] = e * (dt * (lam2 * lam * (T(0.5) * dtlam - T(1)))); v[1] = e * (dt * (lam2 * (dtlam - T(3)))); v[2] = e * (dt * (lam * (T(0.5) * dtlam - T(2))) + T(1)); }
+      } else if (blk.kind == KJX_BLOCK_MATERN12) {          // priors.py:94-104
+        v[0] = exp(-dt * lam);
+      } else if (blk.kind == KJX_BLOCK_ROTATION) {          // priors.py:397-408, :791-820, :910-939; utils.py:253-265
+        const T cs = cos((T)blk.omega * dt), sn = sin((T)blk.omega * dt);
+        const T e = (blk.lam != 0.0) ? exp(-dt * lam) : T(1);
+        if (rr == 0) { v[0] = e * cs; v[1] = e * (-sn); } else { v[0] = e * sn; v[1] = e * cs; }
+      } else if (blk.kind == KJX_BLOCK_MATERN72) {          // priors.py:326-350
+        const T lam2 = lam * lam, lam3 = lam2 * lam, dtlam = dt * lam, dtlam2 = dtlam * dtlam, e = exp(-dtlam);
+        if (rr == 0) {
+          v[0] = e * (dt * (lam * (T(1) + T(0.5) * dtlam + dtlam2 / T(6))) + T(1)); v[1] = e * (dt * (T(1) + dtlam + T(0.5) * dtlam2));
+          v[2] = e * (dt * (T(0.5) * dt * (T(1) + dtlam))); v[3] = e * (dt * (dt * dt / T(6)));
+        } else if (rr == 1) {
+          v[0] = e * (dt * (-dtlam2 * lam2 / T(6))); v[1] = e * (dt * (lam * (T(1) + T(0.5) * dtlam - T(0.5) * dtlam2)) + T(1));
+          v[2] = e * (dt * (T(1) + dtlam - T(0.5) * dtlam2)); v[3] = e * (dt * (dt * (T(0.5) - dtlam / T(6))));
+        } else if (rr == 2) {
+          v[0] = e * (dt * (lam3 * dtlam * (dtlam / T(6) - T(0.5)))); v[1] = e * (dt * (dtlam * lam2 * (T(0.5) * dtlam - T(2))));
+          v[2] = e * (dt * (lam * (T(1) - T(2.5) * dtlam + T(0.5) * dtlam2)) + T(1)); v[3] = e * (dt * (T(1) - dtlam + dtlam2 / T(6)));
+        } else {
+          v[0] = e * (dt * (lam2 * lam2 * (dtlam - T(1) - dtlam2 / T(6)))); v[1] = e * (dt * (lam3 * (T(3.5) * dtlam - T(4) - T(0.5) * dtlam2)));
+          v[2] = e * (dt * (lam2 * (T(4) * dtlam - T(6) - T(0.5) * dtlam2))); v[3] = e * (dt * (lam * (T(1.5) * dtlam - T(3) - dtlam2 / T(6))) + T(1));
+        }
       } else {                                              // priors.py:1066-1084, utils.py:253-265
         const T e = exp(-dt * lam);
         const T cs = cos((T)blk.omega * dt), sn = sin((T)blk.omega * dt);

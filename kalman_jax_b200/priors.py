@@ -1,5 +1,6 @@
 """GP priors as LTI SDEs — host-side mirror of /root/reference/kalmanjax/priors.py for the priors named
-by BASELINE.json (Matern-3/2, Matern-5/2, QuasiPeriodicMatern32, Sum, SpatioTemporalMatern52).
+by BASELINE.json (Matern-3/2, Matern-5/2, QuasiPeriodicMatern32, Sum, SpatioTemporalMatern52) and, from the model
+zoo of SURVEY 8(f)-4, Matern-1/2 (Exponential), Matern-7/2, Cosine, Periodic and QuasiPeriodicMatern12.
 
 Same class names, constructor arguments and `hyp` convention (softplus-inverse of the positive
 hyperparameters) as the reference.  What is computed here on the host is only what the reference
@@ -171,6 +172,186 @@ class QuasiPeriodicMatern32(Prior):
         omega = 2 * np.pi / theta[2]
         harmonics = np.arange(self.order + 1) * omega        # priors.py:1057
         return [(_lib.BLOCK_QP_MATERN32, 1, lam, float(harmonics[j])) for j in range(self.order + 1)]
+
+
+class Exponential(Prior):
+    """priors.py:50-104."""
+    state_dim = 1
+
+    def __init__(self, variance=1.0, lengthscale=1.0):
+        super().__init__(hyp=[variance, lengthscale])
+        self.name = 'Exponential'
+
+    @property
+    def variance(self):
+        return softplus(self.hyp[0])
+
+    @property
+    def lengthscale(self):
+        return softplus(self.hyp[1])
+
+    def kernel_to_state_space(self, hyperparams=None):
+        var, ell = self._theta(hyperparams)
+        return np.array([[-1.0 / ell]]), np.array([[1.0]]), np.array([[2.0 * var / ell]]), np.array([[1.0]]), np.array([[var]])
+
+    def measurement_model(self, r=None, hyperparams=None):
+        return np.array([[1.0]])
+
+    def state_transition(self, dt, hyperparams=None):
+        return np.broadcast_to(np.exp(-dt / self._theta(hyperparams)[1]), [1, 1])
+
+    def blocks(self, hyperparams=None):
+        return [(_lib.BLOCK_MATERN12, 1, float(1.0 / self._theta(hyperparams)[1]), 0.0)]
+
+
+class Matern12(Exponential):
+    """priors.py:107-108."""
+    pass
+
+
+class Matern72(Prior):
+    """priors.py:258-350."""
+    state_dim = 4
+
+    def __init__(self, variance=1.0, lengthscale=1.0):
+        super().__init__(hyp=[variance, lengthscale])
+        self.name = 'Matern-7/2'
+
+    @property
+    def variance(self):
+        return softplus(self.hyp[0])
+
+    @property
+    def lengthscale(self):
+        return softplus(self.hyp[1])
+
+    def kernel_to_state_space(self, hyperparams=None):
+        var, ell = self._theta(hyperparams)
+        lam = 7.0 ** 0.5 / ell
+        F = np.array([[0.0, 1.0, 0.0, 0.0], [0.0, 0.0, 1.0, 0.0], [0.0, 0.0, 0.0, 1.0],
+                      [-lam ** 4.0, -4.0 * lam ** 3.0, -6.0 * lam ** 2.0, -4.0 * lam]])
+        L = np.array([[0.0], [0.0], [0.0], [1.0]])
+        Qc = np.array([[var * 10976.0 * 7.0 ** 0.5 / 5.0 / ell ** 7.0]])
+        H = np.array([[1.0, 0.0, 0.0, 0.0]])
+        kappa = 7.0 / 5.0 * var / ell ** 2.0
+        kappa2 = 9.8 * var / ell ** 4.0
+        Pinf = np.array([[var, 0.0, -kappa, 0.0], [0.0, kappa, 0.0, -kappa2], [-kappa, 0.0, kappa2, 0.0],
+                         [0.0, -kappa2, 0.0, 343.0 * var / ell ** 6.0]])
+        return F, L, Qc, H, Pinf
+
+    def measurement_model(self, r=None, hyperparams=None):
+        return np.array([[1.0, 0.0, 0.0, 0.0]])
+
+    def state_transition(self, dt, hyperparams=None):
+        lam = np.sqrt(7.0) / self._theta(hyperparams)[1]
+        lam2, dtlam = lam * lam, dt * lam
+        lam3, dtlam2 = lam2 * lam, dtlam ** 2
+        return np.exp(-dtlam) * (
+            dt * np.array([[lam * (1.0 + 0.5 * dtlam + dtlam2 / 6.0), 1.0 + dtlam + 0.5 * dtlam2, 0.5 * dt * (1.0 + dtlam), dt ** 2 / 6],
+                           [-dtlam2 * lam ** 2.0 / 6.0, lam * (1.0 + 0.5 * dtlam - 0.5 * dtlam2), 1.0 + dtlam - 0.5 * dtlam2,
+                            dt * (0.5 - dtlam / 6.0)],
+                           [lam3 * dtlam * (dtlam / 6.0 - 0.5), dtlam * lam2 * (0.5 * dtlam - 2.0),
+                            lam * (1.0 - 2.5 * dtlam + 0.5 * dtlam2), 1.0 - dtlam + dtlam2 / 6.0],
+                           [lam2 ** 2 * (dtlam - 1.0 - dtlam2 / 6.0), lam3 * (3.5 * dtlam - 4.0 - 0.5 * dtlam2),
+                            lam2 * (4.0 * dtlam - 6.0 - 0.5 * dtlam2), lam * (1.5 * dtlam - 3.0 - dtlam2 / 6.0)]])
+            + np.eye(4))
+
+    def blocks(self, hyperparams=None):
+        return [(_lib.BLOCK_MATERN72, 1, float(np.sqrt(7.0) / self._theta(hyperparams)[1]), 0.0)]
+
+
+def _rotation(dt, omega):
+    """utils.py:253-265."""
+    return np.array([[np.cos(omega * dt), -np.sin(omega * dt)], [np.sin(omega * dt), np.cos(omega * dt)]])
+
+
+class Cosine(Prior):
+    """priors.py:353-408 (hyp is the scalar frequency)."""
+    state_dim = 2
+
+    def __init__(self, frequency=1.0):
+        super().__init__(hyp=frequency)
+        self.name = 'Cosine'
+
+    @property
+    def frequency(self):
+        return softplus(self.hyp)
+
+    def kernel_to_state_space(self, hyperparams=None):
+        omega = float(np.reshape(self._theta(hyperparams), -1)[0])
+        return np.array([[0.0, -omega], [omega, 0.0]]), [], [], np.array([[1.0, 0.0]]), np.eye(2)
+
+    def measurement_model(self, r=None, hyperparams=None):
+        return np.array([[1.0, 0.0]])
+
+    def state_transition(self, dt, hyperparams=None):
+        return _rotation(dt, float(np.reshape(self._theta(hyperparams), -1)[0]))
+
+    def blocks(self, hyperparams=None):
+        return [(_lib.BLOCK_ROTATION, 1, 0.0, float(np.reshape(self._theta(hyperparams), -1)[0]))]
+
+
+class Periodic(QuasiPeriodicMatern32):
+    """priors.py:724-820 (the series tables b_fmK_2K are the ones QuasiPeriodicMatern32 builds, :741-757)."""
+    state_dim = 14
+
+    def __init__(self, variance=1.0, lengthscale=1.0, period=1.0, order=6):
+        QuasiPeriodicMatern32.__init__(self, order=order)
+        Prior.__init__(self, hyp=[variance, lengthscale, period])
+        self.name = 'Periodic'
+
+    def _q2(self, var, ell):
+        return np.sum(self.b_fmK_2K * ell ** (-2. * self.K) * np.exp(-1. / ell ** 2.) * var, axis=0)
+
+    def kernel_to_state_space(self, hyperparams=None):
+        var, ell, period = self._theta(hyperparams)
+        omega = 2 * np.pi / period
+        F = np.kron(np.diag(np.arange(self.order + 1)), np.array([[0., -omega], [omega, 0.]]))
+        n = 2 * (self.order + 1)
+        return F, np.eye(n), np.zeros(n), self.measurement_model(), np.kron(np.diag(self._q2(var, ell)), np.eye(2))
+
+    def measurement_model(self, r=None, hyperparams=None):
+        return np.kron(np.ones([1, self.order + 1]), np.array([1., 0.]))
+
+    def state_transition(self, dt, hyperparams=None):
+        omega = 2 * np.pi / self._theta(hyperparams)[2]
+        return sl.block_diag(*[_rotation(dt, j * omega) for j in range(self.order + 1)])
+
+    def blocks(self, hyperparams=None):
+        omega = 2 * np.pi / self._theta(hyperparams)[2]
+        return [(_lib.BLOCK_ROTATION, 1, 0.0, float(j * omega)) for j in range(self.order + 1)]
+
+
+class QuasiPeriodicMatern12(QuasiPeriodicMatern32):
+    """priors.py:823-939."""
+    state_dim = 14
+
+    def __init__(self, variance=1.0, lengthscale_periodic=1.0, period=1.0, lengthscale_matern=1.0, order=6):
+        super().__init__(variance, lengthscale_periodic, period, lengthscale_matern, order)
+        self.name = 'Quasi-periodic Matern-1/2'
+
+    def kernel_to_state_space(self, hyperparams=None):
+        var, ell_p, period, ell_m = self._theta(hyperparams)
+        q2 = np.sum(self.b_fmK_2K * ell_p ** (-2. * self.K) * np.exp(-1. / ell_p ** 2.) * 1., axis=0)
+        omega = 2 * np.pi / period
+        n = 2 * (self.order + 1)
+        F_p = np.kron(np.diag(np.arange(self.order + 1)), np.array([[0., -omega], [omega, 0.]]))
+        Pinf_p = np.kron(np.diag(q2), np.eye(2))
+        F = np.kron(np.array([[-1.0 / ell_m]]), np.eye(n)) + F_p
+        return F, np.eye(n), np.kron(Pinf_p, np.array([[2.0 * var / ell_m]])), self.measurement_model(), np.kron(np.array([[var]]), Pinf_p)
+
+    def measurement_model(self, r=None, hyperparams=None):
+        return np.kron(np.array([[1.0]]), np.kron(np.ones([1, self.order + 1]), np.array([1., 0.])))
+
+    def state_transition(self, dt, hyperparams=None):
+        theta = self._theta(hyperparams)
+        omega = 2 * np.pi / theta[2]
+        return np.exp(-dt / theta[3]) * sl.block_diag(*[_rotation(dt, j * omega) for j in range(self.order + 1)])
+
+    def blocks(self, hyperparams=None):
+        theta = self._theta(hyperparams)
+        omega = 2 * np.pi / theta[2]
+        return [(_lib.BLOCK_ROTATION, 1, float(1.0 / theta[3]), float(j * omega)) for j in range(self.order + 1)]
 
 
 class Sum(object):

@@ -3,8 +3,9 @@
 NumPy fp64 restatement of the parts of /root/reference/kalmanjax/priors.py (and kernels.py, utils.py)
 that the Kalman filter / RTS smoother touch: Pinf, H (measurement model) and the closed-form
 A(dt) = expm(F dt).  Hyperparameters are the already-transformed (positive) values.
-Only the priors named by BASELINE.json's configs are restated: Matern-3/2, Matern-5/2,
-QuasiPeriodicMatern32, Sum, SpatioTemporalMatern52.
+Restated: the priors named by BASELINE.json's configs (Matern-3/2, Matern-5/2, QuasiPeriodicMatern32, Sum,
+SpatioTemporalMatern52) and, from SURVEY 8(f)-4's model zoo, Matern-1/2 (Exponential), Matern-7/2, Cosine, Periodic,
+QuasiPeriodicMatern12.
 """
 import numpy as np
 import scipy.linalg as sl
@@ -120,6 +121,123 @@ class QuasiPeriodicMatern32(object):
             blocks.append(np.block([[(1. + dt * lam) * R, dt * R],
                                     [-dt * lam ** 2 * R, (1. - dt * lam) * R]]))          # :1079-1082
         return np.exp(-dt * lam) * sl.block_diag(*blocks)                                 # :1066-1074
+
+
+class Matern12(object):
+    """priors.py:50-108 (Exponential / Matern-1/2)."""
+    state_dim = 1
+
+    def __init__(self, variance=1.0, lengthscale=1.0):
+        self.hyp = np.array([variance, lengthscale], dtype=float)
+
+    def kernel_to_state_space(self):
+        return np.array([[1.0]]), np.array([[self.hyp[0]]])                               # :85-86
+
+    def measurement_model(self, r=None):
+        return np.array([[1.0]])                                                          # :90
+
+    def state_transition(self, dt):
+        return np.broadcast_to(np.exp(-dt / self.hyp[1]), [1, 1])                         # :103
+
+
+Exponential = Matern12
+
+
+class Matern72(object):
+    """priors.py:258-350."""
+    state_dim = 4
+
+    def __init__(self, variance=1.0, lengthscale=1.0):
+        self.hyp = np.array([variance, lengthscale], dtype=float)
+
+    def kernel_to_state_space(self):
+        var, ell = self.hyp
+        kappa = 7.0 / 5.0 * var / ell ** 2.0                                              # :312
+        kappa2 = 9.8 * var / ell ** 4.0                                                   # :313
+        Pinf = np.array([[var, 0.0, -kappa, 0.0],
+                         [0.0, kappa, 0.0, -kappa2],
+                         [-kappa, 0.0, kappa2, 0.0],
+                         [0.0, -kappa2, 0.0, 343.0 * var / ell ** 6.0]])                  # :314-317
+        return np.array([[1.0, 0.0, 0.0, 0.0]]), Pinf
+
+    def measurement_model(self, r=None):
+        return np.array([[1.0, 0.0, 0.0, 0.0]])                                           # :322
+
+    def state_transition(self, dt):
+        lam = np.sqrt(7.0) / self.hyp[1]                                                  # :335-350
+        lam2 = lam * lam
+        lam3 = lam2 * lam
+        dtlam = dt * lam
+        dtlam2 = dtlam ** 2
+        return np.exp(-dtlam) * (
+            dt * np.array([[lam * (1.0 + 0.5 * dtlam + dtlam2 / 6.0), 1.0 + dtlam + 0.5 * dtlam2,
+                            0.5 * dt * (1.0 + dtlam), dt ** 2 / 6],
+                           [-dtlam2 * lam ** 2.0 / 6.0, lam * (1.0 + 0.5 * dtlam - 0.5 * dtlam2),
+                            1.0 + dtlam - 0.5 * dtlam2, dt * (0.5 - dtlam / 6.0)],
+                           [lam3 * dtlam * (dtlam / 6.0 - 0.5), dtlam * lam2 * (0.5 * dtlam - 2.0),
+                            lam * (1.0 - 2.5 * dtlam + 0.5 * dtlam2), 1.0 - dtlam + dtlam2 / 6.0],
+                           [lam2 ** 2 * (dtlam - 1.0 - dtlam2 / 6.0), lam3 * (3.5 * dtlam - 4.0 - 0.5 * dtlam2),
+                            lam2 * (4.0 * dtlam - 6.0 - 0.5 * dtlam2), lam * (1.5 * dtlam - 3.0 - dtlam2 / 6.0)]])
+            + np.eye(4))
+
+
+class Cosine(object):
+    """priors.py:353-408: a pure rotation, Pinf = I, no process noise."""
+    state_dim = 2
+
+    def __init__(self, frequency=1.0):
+        self.hyp = np.array(frequency, dtype=float)
+
+    def kernel_to_state_space(self):
+        return np.array([[1.0, 0.0]]), np.eye(2)                                          # :386-389
+
+    def measurement_model(self, r=None):
+        return np.array([[1.0, 0.0]])                                                     # :393
+
+    def state_transition(self, dt):
+        return rotation_matrix(dt, float(np.reshape(self.hyp, -1)[0]))                    # :406
+
+
+class Periodic(QuasiPeriodicMatern32):
+    """priors.py:724-820: sum of order + 1 = 7 cosines (2 x 2 rotations), Pinf = kron(diag(q2), I2), no process noise.
+    Inherits the series coefficients b_fmK_2K (identical tables, :741-757)."""
+    state_dim = 14
+
+    def __init__(self, variance=1.0, lengthscale=1.0, period=1.0):
+        QuasiPeriodicMatern32.__init__(self)
+        self.hyp = np.array([variance, lengthscale, period], dtype=float)
+
+    def q2(self):
+        var, ell = self.hyp[0], self.hyp[1]
+        a = self.b_fmK_2K * ell ** (-2. * self.K) * np.exp(-1. / ell ** 2.) * var         # :773
+        return np.sum(a, axis=0)                                                          # :774
+
+    def kernel_to_state_space(self):
+        return self.measurement_model(), np.kron(np.diag(self.q2()), np.eye(2))           # :781
+
+    def measurement_model(self, r=None):
+        return np.kron(np.ones([1, self.order + 1]), np.array([1., 0.]))                  # :787
+
+    def state_transition(self, dt):
+        omega = 2 * np.pi / self.hyp[2]                                                   # :802
+        return sl.block_diag(*[rotation_matrix(dt, j * omega) for j in range(self.order + 1)])   # :803-819
+
+
+class QuasiPeriodicMatern12(QuasiPeriodicMatern32):
+    """priors.py:823-939: kron(Matern-1/2, Periodic): blocks exp(-dt / ell_m) R(j omega dt), Pinf = var kron(diag(q2), I2)."""
+    state_dim = 14
+
+    def kernel_to_state_space(self):
+        var = self.hyp[0]
+        return self.measurement_model(), np.kron(np.array([[var]]), np.kron(np.diag(self.q2()), np.eye(2)))   # :899
+
+    def measurement_model(self, r=None):
+        return np.kron(np.array([[1.0]]), np.kron(np.ones([1, self.order + 1]), np.array([1., 0.])))           # :904-907
+
+    def state_transition(self, dt):
+        period, ell_m = self.hyp[2], self.hyp[3]
+        omega = 2 * np.pi / period                                                        # :921
+        return np.exp(-dt / ell_m) * sl.block_diag(*[rotation_matrix(dt, j * omega) for j in range(self.order + 1)])   # :930-938
 
 
 class Sum(object):

@@ -16,6 +16,11 @@ M32_154 = ("Matern32", dict(variance=1.5, lengthscale=4.0))
 ST52 = ("SpatioTemporalMatern52", dict(variance=0.3, lengthscale_time=0.3, lengthscale_space=0.3))
 ST52_M25 = ("SpatioTemporalMatern52", dict(variance=0.3, lengthscale_time=0.3, lengthscale_space=0.3,
                                             z=[-3.0 + 0.25 * i for i in range(25)]))
+M12_12 = ("Matern12", dict(variance=1.0, lengthscale=2.0))
+M72_15 = ("Matern72", dict(variance=1.0, lengthscale=5.0))
+COS_05 = ("Cosine", dict(frequency=[0.5]))   # the reference indexes hyp[0] (priors.py:382): frequency must be array-like
+PER_3 = ("Periodic", dict(variance=0.8, lengthscale=1.5, period=3.0))
+QPM12 = ("QuasiPeriodicMatern12", dict(variance=1.0, lengthscale_periodic=1.5, period=20., lengthscale_matern=40.))
 POISSON = ("Poisson", dict())
 PROBIT = ("Probit", dict())
 LOGIT = ("Bernoulli", dict(link="logit"))
@@ -54,6 +59,14 @@ CASES = {
     "c4_banana200_st52_probit_vi": ("banana200", ST52, PROBIT, ("VI", dict()), 2, None),
     # 25 inducing points -> state dimension 75: above what one SM's shared memory holds (global-scratch path)
     "c4_banana120_st52_m25_probit_ep": ("banana120", ST52_M25, PROBIT, ("EP", dict(power=0.8)), 2, None),
+    # model zoo: the other closed-form priors, through the generic block-diagonal path
+    "zoo_coal333_m12_poisson_ep05": ("coal333", M12_12, POISSON, ("EP", dict(power=0.5)), 3, None),
+    "zoo_regression_m72_gauss_pep": ("regression", M72_15, ("Gaussian", dict(variance=0.5)), ("EP", dict(power=0.5)), 2, None),
+    # (the reference's Cosine returns lists for L and Qc, so it cannot be a component of its Sum: used on its own)
+    "zoo_regression_cosine_gauss_pep": ("regression", COS_05, ("Gaussian", dict(variance=0.5)), ("EP", dict(power=0.5)), 2, None),
+    # (likewise Periodic: its 1-D Qc breaks the reference's Sum, priors.py:1376)
+    "zoo_probit300_periodic_ep1": ("classification300", PER_3, PROBIT, ("EP", dict(power=1.0)), 3, None),
+    "zoo_coal333_qpm12_poisson_vi_gh": ("coal333", QPM12, POISSON, ("VI", dict(intmethod="GH")), 3, None),
 }
 
 KEEP_EVERY = {"aircraft160": 8, "banana400": 16, "banana200": 16, "banana120": 24}
