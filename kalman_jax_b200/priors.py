@@ -1,6 +1,7 @@
 """GP priors as LTI SDEs — host-side mirror of /root/reference/kalmanjax/priors.py for the priors named
 by BASELINE.json (Matern-3/2, Matern-5/2, QuasiPeriodicMatern32, Sum, SpatioTemporalMatern52) and, from the model
-zoo of SURVEY 8(f)-4, Matern-1/2 (Exponential), Matern-7/2, Cosine, Periodic and QuasiPeriodicMatern12.
+zoo of SURVEY 8(f)-4, Matern-1/2 (Exponential), Matern-7/2, Cosine, Periodic, QuasiPeriodicMatern12,
+SubbandMatern12 and SubbandMatern32.
 
 Same class names, constructor arguments and `hyp` convention (softplus-inverse of the positive
 hyperparameters) as the reference.  What is computed here on the host is only what the reference
@@ -352,6 +353,68 @@ class QuasiPeriodicMatern12(QuasiPeriodicMatern32):
         theta = self._theta(hyperparams)
         omega = 2 * np.pi / theta[2]
         return [(_lib.BLOCK_ROTATION, 1, float(1.0 / theta[3]), float(j * omega)) for j in range(self.order + 1)]
+
+
+class SubbandMatern12(Prior):
+    """priors.py:411-494."""
+    state_dim = 2
+
+    def __init__(self, variance=1.0, lengthscale=1.0, radial_frequency=1.0):
+        super().__init__(hyp=[variance, lengthscale, radial_frequency])
+        self.name = 'Subband Matern-1/2'
+
+    def kernel_to_state_space(self, hyperparams=None):
+        var, ell, omega = self._theta(hyperparams)
+        F = np.kron(np.array([[-1.0 / ell]]), np.eye(2)) + np.array([[0.0, -omega], [omega, 0.0]])
+        return F, np.eye(2), np.kron(np.eye(2), np.array([[2.0 * var / ell]])), np.array([[1.0, 0.0]]), var * np.eye(2)
+
+    def measurement_model(self, r=None, hyperparams=None):
+        return np.array([[1.0, 0.0]])
+
+    def state_transition(self, dt, hyperparams=None):
+        theta = self._theta(hyperparams)
+        return np.exp(-dt / theta[1]) * _rotation(dt, theta[2])
+
+    def blocks(self, hyperparams=None):
+        theta = self._theta(hyperparams)
+        return [(_lib.BLOCK_ROTATION, 1, float(1.0 / theta[1]), float(theta[2]))]
+
+
+class SubbandExponential(SubbandMatern12):
+    """priors.py:497-498."""
+    pass
+
+
+class SubbandMatern32(Prior):
+    """priors.py:501-602: its transition is the 4 x 4 block kind of QuasiPeriodicMatern32's harmonics."""
+    state_dim = 4
+
+    def __init__(self, variance=1.0, lengthscale=1.0, radial_frequency=1.0):
+        super().__init__(hyp=[variance, lengthscale, radial_frequency])
+        self.name = 'Subband Matern-3/2'
+
+    def kernel_to_state_space(self, hyperparams=None):
+        var, ell, omega = self._theta(hyperparams)
+        lam = 3.0 ** 0.5 / ell
+        F_mat = np.array([[0.0, 1.0], [-lam ** 2, -2 * lam]])
+        F = np.kron(F_mat, np.eye(2)) + np.kron(np.eye(2), np.array([[0.0, -omega], [omega, 0.0]]))
+        L = np.kron(np.array([[0], [1]]), np.eye(2))
+        Qc = np.kron(np.eye(2), np.array([[12.0 * 3.0 ** 0.5 / ell ** 3.0 * var]]))
+        Pinf = np.kron(np.array([[var, 0.0], [0.0, 3.0 * var / ell ** 2.0]]), np.eye(2))
+        return F, L, Qc, self.measurement_model(), Pinf
+
+    def measurement_model(self, r=None, hyperparams=None):
+        return np.kron(np.array([[1.0, 0.0]]), np.array([[1.0, 0.0]]))
+
+    def state_transition(self, dt, hyperparams=None):
+        theta = self._theta(hyperparams)
+        lam = np.sqrt(3.0) / theta[1]
+        R = _rotation(dt, theta[2])
+        return np.exp(-dt * lam) * np.block([[(1. + dt * lam) * R, dt * R], [-dt * lam ** 2 * R, (1. - dt * lam) * R]])
+
+    def blocks(self, hyperparams=None):
+        theta = self._theta(hyperparams)
+        return [(_lib.BLOCK_QP_MATERN32, 1, float(np.sqrt(3.0) / theta[1]), float(theta[2]))]
 
 
 class Sum(object):

@@ -5,7 +5,7 @@ that the Kalman filter / RTS smoother touch: Pinf, H (measurement model) and the
 A(dt) = expm(F dt).  Hyperparameters are the already-transformed (positive) values.
 Restated: the priors named by BASELINE.json's configs (Matern-3/2, Matern-5/2, QuasiPeriodicMatern32, Sum,
 SpatioTemporalMatern52) and, from SURVEY 8(f)-4's model zoo, Matern-1/2 (Exponential), Matern-7/2, Cosine, Periodic,
-QuasiPeriodicMatern12.
+QuasiPeriodicMatern12, SubbandMatern12 / SubbandMatern32.
 """
 import numpy as np
 import scipy.linalg as sl
@@ -238,6 +238,48 @@ class QuasiPeriodicMatern12(QuasiPeriodicMatern32):
         period, ell_m = self.hyp[2], self.hyp[3]
         omega = 2 * np.pi / period                                                        # :921
         return np.exp(-dt / ell_m) * sl.block_diag(*[rotation_matrix(dt, j * omega) for j in range(self.order + 1)])   # :930-938
+
+
+class SubbandMatern12(object):
+    """priors.py:411-494: kron(Matern-1/2, Cosine)."""
+    state_dim = 2
+
+    def __init__(self, variance=1.0, lengthscale=1.0, radial_frequency=1.0):
+        self.hyp = np.array([variance, lengthscale, radial_frequency], dtype=float)
+
+    def kernel_to_state_space(self):
+        return np.array([[1.0, 0.0]]), np.kron(np.array([[self.hyp[0]]]), np.eye(2))      # :469-470
+
+    def measurement_model(self, r=None):
+        return np.array([[1.0, 0.0]])                                                     # :477
+
+    def state_transition(self, dt):
+        return np.exp(-dt / self.hyp[1]) * rotation_matrix(dt, self.hyp[2])               # :492-493
+
+
+SubbandExponential = SubbandMatern12
+
+
+class SubbandMatern32(object):
+    """priors.py:501-602: kron(Matern-3/2, Cosine)."""
+    state_dim = 4
+
+    def __init__(self, variance=1.0, lengthscale=1.0, radial_frequency=1.0):
+        self.hyp = np.array([variance, lengthscale, radial_frequency], dtype=float)
+
+    def kernel_to_state_space(self):
+        var, ell = self.hyp[0], self.hyp[1]
+        Pinf_mat = np.array([[var, 0.0], [0.0, 3.0 * var / ell ** 2.0]])                  # :561-562
+        return self.measurement_model(), np.kron(Pinf_mat, np.eye(2))                     # :575
+
+    def measurement_model(self, r=None):
+        return np.kron(np.array([[1.0, 0.0]]), np.array([[1.0, 0.0]]))                    # :583
+
+    def state_transition(self, dt):
+        lam = np.sqrt(3.0) / self.hyp[1]                                                  # :596
+        R = rotation_matrix(dt, self.hyp[2])
+        return np.exp(-dt * lam) * np.block([[(1. + dt * lam) * R, dt * R],
+                                             [-dt * lam ** 2 * R, (1. - dt * lam) * R]])  # :598-601
 
 
 class Sum(object):

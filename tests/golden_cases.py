@@ -21,6 +21,8 @@ M72_15 = ("Matern72", dict(variance=1.0, lengthscale=5.0))
 COS_05 = ("Cosine", dict(frequency=[0.5]))   # the reference indexes hyp[0] (priors.py:382): frequency must be array-like
 PER_3 = ("Periodic", dict(variance=0.8, lengthscale=1.5, period=3.0))
 QPM12 = ("QuasiPeriodicMatern12", dict(variance=1.0, lengthscale_periodic=1.5, period=20., lengthscale_matern=40.))
+SUB12 = ("SubbandMatern12", dict(variance=0.7, lengthscale=3.0, radial_frequency=1.3))
+SUB32 = ("SubbandMatern32", dict(variance=1.1, lengthscale=4.0, radial_frequency=0.4))
 POISSON = ("Poisson", dict())
 PROBIT = ("Probit", dict())
 LOGIT = ("Bernoulli", dict(link="logit"))
@@ -67,6 +69,9 @@ CASES = {
     # (likewise Periodic: its 1-D Qc breaks the reference's Sum, priors.py:1376)
     "zoo_probit300_periodic_ep1": ("classification300", PER_3, PROBIT, ("EP", dict(power=1.0)), 3, None),
     "zoo_coal333_qpm12_poisson_vi_gh": ("coal333", QPM12, POISSON, ("VI", dict(intmethod="GH")), 3, None),
+    "zoo_regression_sum_subbands_m12_gauss_ep1": ("regression", ("Sum", [SUB12, SUB32, M12_12]), ("Gaussian", dict(variance=0.5)),
+                                                  ("EP", dict(power=1.0)), 2, None),
+    "zoo_coal333_subband32_poisson_eks": ("coal333", SUB32, POISSON, ("EKS", dict(damping=0.8)), 3, None),
 }
 
 KEEP_EVERY = {"aircraft160": 8, "banana400": 16, "banana200": 16, "banana120": 24}
