@@ -7,7 +7,7 @@ own SDEGP / approximate_inference API.
 The hot path is hand-written CUDA in csrc/ behind the C ABI of include/kjx.h (libkjx.so, loaded with
 ctypes).  There is no CPU fallback: without the built library every compute call raises.
 """
-from . import _lib, utils, priors, likelihoods, approximate_inference  # noqa: F401
+from . import _lib, utils, priors, likelihoods, approximate_inference, optimizers  # noqa: F401
 from .sde_gp import SDEGP, site_update  # noqa: F401
 
-__all__ = ["SDEGP", "site_update", "priors", "likelihoods", "approximate_inference", "utils"]
+__all__ = ["SDEGP", "site_update", "priors", "likelihoods", "approximate_inference", "utils", "optimizers"]

@@ -378,6 +378,25 @@ def test_generic_path_two_level_boundary_walk_vs_oracle():
         assert rel_err(_np(model.sites.site_params[1]), w_new[1]) < TOL64
 
 
+def test_reference_regression_driver_runs_with_changed_imports():
+    """examples/regression.py = the reference's notebooks/regression.py:23-83 with the imports changed: Adam on the
+    (finite-difference) gradient of the filter energy must lower the energy, and NLPD / predict must work after it."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("kjx_example_regression", os.path.join(os.path.dirname(__file__), "..", "examples", "regression.py"))
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    state, energies = ex.opt_state, []
+    for j in range(8):
+        state, e = ex.gradient_step(j, state, ex.model)
+        energies.append(e)
+    assert np.all(np.isfinite(energies)) and energies[-1] < energies[0] - 1.0, energies
+    nlpd = ex.model.negative_log_predictive_density(t=ex.x_test, y=ex.y_test)
+    pm, pv = ex.model.predict(t=np.linspace(-40.0, 170.0, 50))
+    assert np.isfinite(nlpd) and 0.0 < nlpd < 2.0
+    assert np.all(np.isfinite(_np(pm))) and np.all(_np(pv) > 0)
+
+
 def _state_space_cov(prior, t):
     """cov(f(t_i), f(t_j)) = H A(|t_j - t_i|) Pinf H^T of a stationary state-space prior, from the ORACLE's matrices."""
     H, Pinf = prior.kernel_to_state_space()
