@@ -603,3 +603,45 @@ def test_spatio_temporal_ns64_d192_vs_oracle():
         assert rel_err(_np(model.posterior[0]), wsm) < 1e-5 and rel_err(_np(model.posterior[1]), wsc) < 1e-5
         assert rel_err(_np(model.sites.site_params[0]), w_new[0]) < 1e-5
         assert rel_err(_np(model.sites.site_params[1]), w_new[1]) < 1e-5
+
+
+def test_global_scratch_path_with_two_level_walk_d75():
+    """State dimension 75 (25 inducing points: working set in per-CTA global scratch) on a series long enough
+    (N = 300 -> 27 chunks) for the two-level boundary walk, three iterations against the oracle."""
+    kjx = _kjx()
+    rng = np.random.default_rng(17)
+    N = 300
+    t = np.sort(rng.uniform(0, 25, N))
+    r = rng.uniform(-3, 3, N)
+    y = (rng.uniform(size=N) < 0.5).astype(float)
+    z = np.linspace(-3, 3, 25)
+    mk = lambda mod, inf: mod.SDEGP(mod.priors.SpatioTemporalMatern52(0.5, 0.8, 0.5, z=z), mod.likelihoods.Probit(), t, y, r=r,  # noqa: E731
+                                    approx_inf=inf.EP(power=0.8))
+    model, ref = mk(kjx, kjx.approximate_inference), mk(oracle, oracle.approx_inf)
+    assert model.state_dim == 75
+    for it in range(3):
+        nlml, _ = model.run(compute_grad=False, store_posterior=True)
+        want_nlml, (wfm, wfP, wsites) = ref.kalman_filter(ref.y, ref.dt, True, None, ref.sites.site_params, ref.r)
+        w_new, wsm, wsc = ref.rauch_tung_striebel_smoother(wfm, wfP, ref.dt, True, False, ref.y, wsites, ref.r)
+        ref.sites.site_params = w_new
+        assert abs(nlml - want_nlml) <= TOL64 * abs(want_nlml), (it, nlml, want_nlml)
+        # cond(Kzz (x) Pinf_t) ~ 1e6 here: smoothed moments to 1e-7 (see the d = 192 test)
+        assert rel_err(_np(model.posterior[0]), wsm) < 1e-7 and rel_err(_np(model.posterior[1]), wsc) < 1e-7
+        assert rel_err(_np(model.sites.site_params[0]), w_new[0]) < 1e-7
+        assert rel_err(_np(model.sites.site_params[1]), w_new[1]) < 1e-7
+
+
+def test_generic_path_fp32_runs_within_1e3():
+    """The float instantiation of the generic path (no FP64 tensor pipe: gemm_cta's plain-FMA branch) on the Matern-7/2
+    golden (d = 4): first iteration against the fp64 fixture at 1e-3 relative.  (fp32 is only usable while
+    cond(P_pred) * 6e-8 << 1: on the Sum-prior goldens, whose components differ by 1e6 in scale, the RTS gain's Cholesky
+    breaks down in single precision — there as in the reference — so those are fp64-only.)"""
+    kjx = _kjx()
+    name = "zoo_regression_m72_gauss_pep"
+    g = load(name)
+    model, _ = build_model(name, g, kjx.priors, kjx.likelihoods, kjx.approximate_inference,
+                           lambda *a, **k: kjx.SDEGP(*a, dtype=torch.float32, **k))
+    nlml, _ = model.run(compute_grad=False, store_posterior=True)
+    assert abs(nlml - g["it0_nlml"]) <= 1e-3 * abs(g["it0_nlml"])
+    assert rel_err(_np(model.posterior[0]), g["it0_smoothed_mean"]) < 1e-3
+    assert rel_err(_np(model.posterior[1]), g["it0_smoothed_cov"]) < 1e-3
