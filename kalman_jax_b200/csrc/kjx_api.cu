@@ -1,50 +1,19 @@
 // kjx_api.cu — the C ABI of libkjx.so (see include/kjx.h) and the dispatch onto the sm_100a kernels.
-#include <cuda_runtime.h>
-#include <stdio.h>
-#include <string.h>
-#include <stdlib.h>
-#include <math.h>
-#include <algorithm>
+// KJX_PART: 64 = everything but the _f32 entry points, 32 = only the _f32 entry points (the two halves compile side by
+// side and instantiate disjoint sets of kernels); undefined = the whole interface in one object.
+#ifndef KJX_PART
+#define KJX_PART 0
+#endif
 #include <vector>
 
-#include "../../include/kjx.h"
+#include "kjx_internal.cuh"
 #include "kjx_small_kernels.cuh"
 #include "kjx_fused_kernels.cuh"
-#include "kjx_elementwise_kernels.cuh"
-#include "kjx_generic_kernels.cuh"
-#include "kjx_sampling_kernels.cuh"
 
 using namespace kjx;
-
-#define KJX_CUDA_CHECK(expr)                              \
-  do {                                                    \
-    cudaError_t e__ = (expr);                             \
-    if (e__ != cudaSuccess) return KJX_ERR_CUDA;          \
-  } while (0)
+using namespace kjx_impl;
 
 namespace {
-
-inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
-
-// ------------------------------------------------------------------------------------------------
-// model inspection
-bool model_basic_ok(const kjx_model_t* m) {
-  if (!m) return false;
-  if (m->state_dim <= 0 || m->func_dim <= 0 || m->n_blocks <= 0 || m->n_blocks > KJX_MAX_BLOCKS) return false;
-  if (m->n_cub < 1 || m->n_cub > KJX_MAX_CUBATURE) return false;
-  if (m->likelihood < KJX_LIK_GAUSSIAN || m->likelihood > KJX_LIK_POISSON_LOGISTIC) return false;
-  if (m->method < KJX_INF_EP || m->method > KJX_INF_VI) return false;
-  if (!m->Pinf) return false;
-  int d = 0;
-  for (int b = 0; b < m->n_blocks; ++b) {
-    const kjx_block_t& k = m->blocks[b];
-    if (k.count <= 0) return false;
-    int bs = block_size(k.kind);
-    if (bs < 0) return false;
-    d += bs * k.count;
-  }
-  return d == m->state_dim;
-}
 
 // the register-resident path: one Matern-3/2 or Matern-5/2 block, scalar site, H = e0
 int small_kind(const kjx_model_t* m) {
@@ -56,15 +25,6 @@ int small_kind(const kjx_model_t* m) {
   if (m->H[0] != 1.0) return 0;
   for (int i = 1; i < d; ++i) if (m->H[i] != 0.0) return 0;
   return kind;
-}
-
-SiteModel make_site(const kjx_model_t* m) {
-  SiteModel s;
-  memset(&s, 0, sizeof(s));
-  s.lik = m->likelihood; s.method = m->method; s.n_cub = m->n_cub;
-  s.lik_hyp = m->lik_hyp; s.power = m->power; s.damping = m->damping;
-  for (int i = 0; i < KJX_MAX_CUBATURE; ++i) { s.cub_x[i] = m->cub_x[i]; s.cub_w[i] = m->cub_w[i]; }
-  return s;
 }
 
 // steps per thread chunk: long chunks amortise the O(d^3) scan combines, short ones keep every SM
@@ -171,7 +131,6 @@ void launch_set_prior_state(T* dst, const kjx_model_t* m, cudaStream_t st) {
   set_state_kernel<T, D><<<1, 32, 0, st>>>(dst, s);
 }
 
-bool gauss_ep(const kjx_model_t* m) { return m->likelihood == KJX_LIK_GAUSSIAN && m->method == KJX_INF_EP; }
 
 struct SmallCall {
   // what the caller asked for (device pointers, type-erased)
@@ -487,184 +446,6 @@ __global__ void fold_shards_kernel(PinfArg<D> pinf, const double* summaries, int
   if (threadIdx.x == 0) fold_shards<D>(pinf.v, summaries, stride, world, rank, state_out, info_out);
 }
 
-// ---- generic block-diagonal prior, d <= 64: CTA-level chunked scan (kjx_generic_kernels.cuh) ------------------
-bool generic_ok(const kjx_model_t* m) {
-  return m->func_dim == 1 && m->state_dim <= KJX_GEN_DMAX_GLOBAL && (m->H != nullptr || m->H_steps != nullptr);
-}
-// number of chunks: every chunk is walked concurrently by its own CTA (~55 us per step at d = 59 over fold, filter and
-// smoother) while the two-level boundary walk costs ~22 us per chunk, so about sqrt(2.5 N) chunks balance the two; one
-// wave of CTAs (the fold's and the smoother's working sets fill an SM's shared memory), so at most one chunk per SM
-int generic_chunks(int64_t N) {
-  if (const char* e = getenv("KJX_GEN_CHUNKS")) { const int v = atoi(e); if (v >= 1) return (int)std::min<int64_t>(v, std::max<int64_t>(N, 1)); }
-  const int64_t p = (int64_t)(sqrt(2.5 * (double)N) + 0.5);
-  return (int)std::max<int64_t>(1, std::min<int64_t>(p, 148));
-}
-constexpr int KJX_GEN_MAXCHUNKS = 148 * 2;
-constexpr int KJX_GEN_MAXGROUPS = 64;      // two-level boundary walk: groups of ~sqrt(0.46 nchunks) chunks
-constexpr int KJX_GEN_GAIN_GRID = 148 * 3;
-// per-CTA working set when it lives in global memory (d > KJX_GEN_DMAX): the largest of the kernels' carve-ups
-template <typename T> size_t generic_scratch_bytes(int d) {
-  if (d <= KJX_GEN_DMAX) return 0;
-  return round_up(std::max(std::max(std::max(generic_smoother_smem<T>(d), generic_fold_smem<T>(d)),
-                                    std::max(generic_filter_smem<T>(d), generic_boundary_smem<T>(d))), generic_group_smem<T>(d)), 256);
-}
-template <typename T> size_t generic_ws_bytes(const kjx_model_t* m, int64_t N) {
-  const size_t d = (size_t)m->state_dim, n = (size_t)std::max<int64_t>(N, 1), P = KJX_GEN_MAXCHUNKS;
-  const size_t scratch = generic_scratch_bytes<T>(m->state_dim) * KJX_GEN_GAIN_GRID;
-  // Pinf, H | dense filter output (kjx_run without caller buffers) | RTS gains [N,d,d] | chunk elements, states, infos, nlml
-  return round_up(d * d * 8, 256) + round_up(d * 8, 256) + round_up(n * d * sizeof(T), 256) + 2 * round_up(n * d * d * sizeof(T), 256) +
-         round_up(P * (3 * d * d + 2 * d) * sizeof(T), 256) + 2 * round_up(P * d * sizeof(T), 256) + 2 * round_up(P * d * d * sizeof(T), 256) +
-         round_up(P * sizeof(T), 256) + round_up(KJX_GEN_MAXGROUPS * (3 * d * d + 2 * d) * sizeof(T), 256) + scratch;
-}
-template <typename T>
-int generic_setup(const kjx_model_t* m, int64_t N, void* ws, size_t ws_bytes, GenArgs<T>& g, T** scratch_mean, T** scratch_cov,
-                  T** scratch_gain, cudaStream_t st) {
-  if (!ws || ws_bytes < generic_ws_bytes<T>(m, N)) return KJX_ERR_WORKSPACE;
-  const size_t d = (size_t)m->state_dim, n = (size_t)std::max<int64_t>(N, 1), P = KJX_GEN_MAXCHUNKS;
-  memset(&g, 0, sizeof(g));
-  g.disc.d = m->state_dim; g.disc.n_blocks = m->n_blocks;
-  for (int b = 0; b < m->n_blocks; ++b) g.disc.blocks[b] = m->blocks[b];
-  g.site = make_site(m); g.d = m->state_dim; g.N = N;
-  char* w = (char*)ws;
-  auto take = [&](size_t bytes) { char* r = w; w += round_up(bytes, 256); return r; };
-  double* pinf_dev = (double*)take(d * d * 8);
-  double* h_dev = (double*)take(d * 8);
-  *scratch_mean = (T*)take(n * d * sizeof(T));
-  *scratch_cov = (T*)take(n * d * d * sizeof(T));
-  *scratch_gain = (T*)take(n * d * d * sizeof(T));
-  g.sum = (T*)take(P * (3 * d * d + 2 * d) * sizeof(T));
-  g.st_m = (T*)take(P * d * sizeof(T)); g.in_eta = (T*)take(P * d * sizeof(T));
-  g.st_P = (T*)take(P * d * d * sizeof(T)); g.in_J = (T*)take(P * d * d * sizeof(T));
-  g.chunk_nlml = (T*)take(P * sizeof(T));
-  g.gsum = (T*)take(KJX_GEN_MAXGROUPS * (3 * d * d + 2 * d) * sizeof(T));
-  g.gscratch_stride = generic_scratch_bytes<T>(m->state_dim);
-  g.gscratch = g.gscratch_stride ? (unsigned char*)take(g.gscratch_stride * KJX_GEN_GAIN_GRID) : nullptr;
-  g.nchunks = 1; g.chunk_len = std::max<int64_t>(N, 1);
-  KJX_CUDA_CHECK(cudaMemcpyAsync(pinf_dev, m->Pinf, d * d * 8, cudaMemcpyHostToDevice, st));
-  g.Pinf = pinf_dev;
-  if (m->H_steps) { g.H_steps = m->H_steps; g.H = nullptr; }
-  else { KJX_CUDA_CHECK(cudaMemcpyAsync(h_dev, m->H, d * 8, cudaMemcpyHostToDevice, st)); g.H = h_dev; }
-  return KJX_OK;
-}
-template <typename T> void generic_set_chunks(GenArgs<T>& g, bool chunked) {
-  g.nchunks = chunked ? generic_chunks(g.N) : 1;
-  g.chunk_len = (g.N + g.nchunks - 1) / g.nchunks;
-  g.nchunks = (int)((g.N + g.chunk_len - 1) / g.chunk_len);
-}
-// elements of all chunks (when there are several), then the state / information at every chunk boundary
-template <typename T> int generic_launch_scan(const GenArgs<T>& g, cudaStream_t st) {
-  if (g.nchunks > 1) {
-    const size_t smem = g.gscratch ? 0 : generic_fold_smem<T>(g.d);
-    KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_fold_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    generic_fold_kernel<T><<<g.nchunks, KJX_GEN_THREADS, smem, st>>>(g);
-  }
-  const size_t smem = g.gscratch ? 0 : generic_boundary_smem<T>(g.d);
-  KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_boundary_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  // a walk over the chunk elements is a dependent chain (~90 us per element at d = 59, ~105 us per combine): beyond a
-  // few dozen chunks do it in two levels — group elements, a walk over the groups, walks inside all groups at once
-  int gsz = (int)(sqrt(0.46 * (double)g.nchunks) + 0.5);
-  if (const char* e = getenv("KJX_GEN_GROUP")) gsz = atoi(e);
-  if (g.nchunks >= 24 && gsz >= 2 && (g.nchunks + gsz - 1) / gsz <= KJX_GEN_MAXGROUPS) {
-    const int ngroups = (g.nchunks + gsz - 1) / gsz;
-    const size_t gs = g.gscratch ? 0 : generic_group_smem<T>(g.d);
-    KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_group_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gs));
-    generic_group_kernel<T><<<ngroups, KJX_GEN_THREADS, gs, st>>>(g, gsz);
-    generic_boundary_kernel<T><<<2, KJX_GEN_THREADS, smem, st>>>(g, KJX_WALK_TOP, gsz);
-    generic_boundary_kernel<T><<<2 * ngroups, KJX_GEN_THREADS, smem, st>>>(g, KJX_WALK_INNER, gsz);
-  } else {
-    generic_boundary_kernel<T><<<2, KJX_GEN_THREADS, smem, st>>>(g, KJX_WALK_FLAT, 1);
-  }
-  return KJX_OK;
-}
-template <typename T> int generic_launch_filter(const GenArgs<T>& g, cudaStream_t st) {
-  const size_t smem = g.gscratch ? 0 : generic_filter_smem<T>(g.d);
-  KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_filter_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  generic_filter_kernel<T><<<g.nchunks, KJX_GEN_THREADS, smem, st>>>(g);
-  if (g.nlml) nlml_reduce_kernel<T><<<1, 256, 0, st>>>(g.chunk_nlml, g.nchunks, g.nlml);
-  return KJX_OK;
-}
-template <typename T> int generic_launch_smoother(const GenArgs<T>& g, T* gains, cudaStream_t st) {
-  const size_t smem = g.gscratch ? 0 : generic_smoother_smem<T>(g.d);
-  // 1. all RTS gains, parallel over time (they depend on the filtered moments only)
-  const size_t gsmem = g.gscratch ? 0 : generic_gain_smem<T>(g.d);
-  KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_gain_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-  const unsigned grid = (unsigned)std::min<int64_t>(g.N, KJX_GEN_GAIN_GRID);
-  generic_gain_kernel<T><<<grid, KJX_GEN_GAIN_THREADS, gsmem, st>>>(g, gains);
-  // 2. the backward recursion (two d^3 products per step), every chunk concurrently, reference order inside a chunk
-  KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_smoother_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  generic_smoother_kernel<T><<<g.nchunks, KJX_GEN_THREADS, smem, st>>>(g, gains);
-  return KJX_OK;
-}
-
-template <typename T>
-int generic_filter(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const uint8_t* mask, const T* site_mean,
-                   const T* site_var, T* filt_mean, T* filt_cov, T* out_site_mean, T* out_site_var, T* nlml, void* ws,
-                   size_t ws_bytes, uint32_t flags, cudaStream_t st) {
-  GenArgs<T> g; T *sm, *sc, *sg;
-  int rc = generic_setup<T>(m, N, ws, ws_bytes, g, &sm, &sc, &sg, st);
-  if (rc != KJX_OK) return rc;
-  if (N == 0) { cudaMemsetAsync(nlml, 0, sizeof(T), st); return KJX_OK; }
-  g.dt = dt; g.y = y; g.mask = mask; g.site_mean = site_mean; g.site_var = site_var;
-  g.init_sites = (site_mean == nullptr && !gauss_ep(m)) ? 1 : 0;
-  g.filt_mean = filt_mean; g.filt_cov = filt_cov; g.out_site_mean = out_site_mean; g.out_site_var = out_site_var; g.nlml = nlml;
-  generic_set_chunks<T>(g, !g.init_sites && !(flags & KJX_FLAG_SEQUENTIAL));
-  if ((rc = generic_launch_scan<T>(g, st)) != KJX_OK) return rc;
-  if ((rc = generic_launch_filter<T>(g, st)) != KJX_OK) return rc;
-  KJX_CUDA_CHECK(cudaGetLastError());
-  return KJX_OK;
-}
-template <typename T>
-int generic_smoother(const kjx_model_t* m, int64_t N, const T* dt, const T* filt_mean, const T* filt_cov, const T* y,
-                     const T* site_mean, const T* site_var, T* smooth_mean, T* smooth_cov, T* new_site_mean, T* new_site_var,
-                     void* ws, size_t ws_bytes, uint32_t flags, cudaStream_t st) {
-  GenArgs<T> g; T *sm, *sc, *sg;
-  int rc = generic_setup<T>(m, N, ws, ws_bytes, g, &sm, &sc, &sg, st);
-  if (rc != KJX_OK) return rc;
-  if (N == 0) return KJX_OK;
-  g.dt = dt; g.y = y; g.site_mean = site_mean; g.site_var = site_var;
-  g.filt_mean_in = filt_mean; g.filt_cov_in = filt_cov;
-  g.smooth_mean = smooth_mean; g.smooth_cov = smooth_cov; g.new_site_mean = new_site_mean; g.new_site_var = new_site_var;
-  g.return_full = (flags & KJX_FLAG_RETURN_FULL) ? 1 : 0;
-  g.update_sites = (new_site_mean != nullptr && site_mean != nullptr && y != nullptr) ? 1 : 0;
-  // the stand-alone smoother only sees filtered moments (which mask / sites produced them is unknown here), so it
-  // cannot rebuild the filter elements: one chunk, gains still computed in parallel
-  generic_set_chunks<T>(g, false);
-  if ((rc = generic_launch_scan<T>(g, st)) != KJX_OK) return rc;
-  if ((rc = generic_launch_smoother<T>(g, sg, st)) != KJX_OK) return rc;
-  KJX_CUDA_CHECK(cudaGetLastError());
-  return KJX_OK;
-}
-template <typename T>
-int generic_run(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const T* site_mean, const T* site_var,
-                T* filt_mean, T* filt_cov, T* new_site_mean, T* new_site_var, T* post_mean, T* post_var, T* nlml,
-                void* ws, size_t ws_bytes, uint32_t flags, cudaStream_t st, const uint8_t* mask = nullptr) {
-  GenArgs<T> g; T *sm, *sc, *sg;
-  int rc = generic_setup<T>(m, N, ws, ws_bytes, g, &sm, &sc, &sg, st);
-  if (rc != KJX_OK) return rc;
-  if (N == 0) { if (nlml) cudaMemsetAsync(nlml, 0, sizeof(T), st); return KJX_OK; }
-  if (!filt_mean) { filt_mean = sm; filt_cov = sc; }       // run() uses the filtered moments only internally
-  g.dt = dt; g.y = y; g.mask = mask; g.site_mean = site_mean; g.site_var = site_var;
-  g.init_sites = (site_mean == nullptr && !gauss_ep(m)) ? 1 : 0;
-  g.filt_mean = filt_mean; g.filt_cov = filt_cov; g.nlml = nlml;
-  if (g.init_sites) { g.out_site_mean = new_site_mean; g.out_site_var = new_site_var; }   // sde_gp.py:183
-  generic_set_chunks<T>(g, !g.init_sites && !(flags & KJX_FLAG_SEQUENTIAL));
-  if ((rc = generic_launch_scan<T>(g, st)) != KJX_OK) return rc;
-  if ((rc = generic_launch_filter<T>(g, st)) != KJX_OK) return rc;
-  if (g.init_sites) {
-    // sites were just initialised by the one-chain filter: rebuild the scan elements from them so the smoother can
-    // run chunk-parallel too (the filter elements only depend on dt and the sites)
-    g.site_mean = new_site_mean; g.site_var = new_site_var; g.out_site_mean = nullptr; g.out_site_var = nullptr; g.init_sites = 0;
-    generic_set_chunks<T>(g, !(flags & KJX_FLAG_SEQUENTIAL));
-    if ((rc = generic_launch_scan<T>(g, st)) != KJX_OK) return rc;
-  }
-  g.filt_mean_in = filt_mean; g.filt_cov_in = filt_cov;
-  g.smooth_mean = post_mean; g.smooth_cov = post_var; g.new_site_mean = new_site_mean; g.new_site_var = new_site_var;
-  g.return_full = 0; g.update_sites = (flags & KJX_FLAG_NO_SITE_UPDATE) ? 0 : 1;
-  if ((rc = generic_launch_smoother<T>(g, sg, st)) != KJX_OK) return rc;
-  KJX_CUDA_CHECK(cudaGetLastError());
-  return KJX_OK;
-}
-
 // ---- typed front ends shared by the _f64 / _f32 entry points ------------------------------------------
 template <typename T>
 int filter_T(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const uint8_t* mask, const T* site_mean,
@@ -782,8 +563,11 @@ int discretise_T(const kjx_model_t* m, int64_t N, const T* dt, T* A, T* Q, void*
 // ================================================================================================
 extern "C" {
 
+#if KJX_PART != 32
 int kjx_version(void) { return 100; }
+#endif
 
+#if KJX_PART != 32
 const char* kjx_status_string(int status) {
   switch (status) {
     case KJX_OK: return "ok";
@@ -794,7 +578,9 @@ const char* kjx_status_string(int status) {
     default: return "unknown status";
   }
 }
+#endif
 
+#if KJX_PART != 32
 int kjx_workspace_bytes(const kjx_model_t* m, int64_t N, int dtype_bytes, size_t* bytes) {
   if (!model_basic_ok(m) || N < 0 || !bytes || (dtype_bytes != 4 && dtype_bytes != 8)) return KJX_ERR_INVALID_ARG;
   const int kind = small_kind(m);
@@ -806,71 +592,96 @@ int kjx_workspace_bytes(const kjx_model_t* m, int64_t N, int dtype_bytes, size_t
   *bytes = total;
   return KJX_OK;
 }
+#endif
 
+#if KJX_PART != 32
 int kjx_filter_f64(const kjx_model_t* m, int64_t N, const double* dt, const double* y, const uint8_t* mask,
                    const double* site_mean, const double* site_cov, double* filt_mean, double* filt_cov,
                    double* out_site_mean, double* out_site_cov, double* nlml, void* ws, size_t ws_bytes,
                    uint32_t flags, kjx_stream_t stream) {
   return filter_T<double>(m, N, dt, y, mask, site_mean, site_cov, filt_mean, filt_cov, out_site_mean, out_site_cov, nlml, ws, ws_bytes, flags, stream);
 }
+#endif
+#if KJX_PART != 64
 int kjx_filter_f32(const kjx_model_t* m, int64_t N, const float* dt, const float* y, const uint8_t* mask,
                    const float* site_mean, const float* site_cov, float* filt_mean, float* filt_cov,
                    float* out_site_mean, float* out_site_cov, float* nlml, void* ws, size_t ws_bytes,
                    uint32_t flags, kjx_stream_t stream) {
   return filter_T<float>(m, N, dt, y, mask, site_mean, site_cov, filt_mean, filt_cov, out_site_mean, out_site_cov, nlml, ws, ws_bytes, flags, stream);
 }
+#endif
 
+#if KJX_PART != 32
 int kjx_smoother_f64(const kjx_model_t* m, int64_t N, const double* dt, const double* filt_mean, const double* filt_cov,
                      const double* y, const double* site_mean, const double* site_cov, double* smooth_mean,
                      double* smooth_cov, double* new_site_mean, double* new_site_cov, void* ws, size_t ws_bytes,
                      uint32_t flags, kjx_stream_t stream) {
   return smoother_T<double>(m, N, dt, filt_mean, filt_cov, y, site_mean, site_cov, smooth_mean, smooth_cov, new_site_mean, new_site_cov, ws, ws_bytes, flags, stream);
 }
+#endif
+#if KJX_PART != 64
 int kjx_smoother_f32(const kjx_model_t* m, int64_t N, const float* dt, const float* filt_mean, const float* filt_cov,
                      const float* y, const float* site_mean, const float* site_cov, float* smooth_mean,
                      float* smooth_cov, float* new_site_mean, float* new_site_cov, void* ws, size_t ws_bytes,
                      uint32_t flags, kjx_stream_t stream) {
   return smoother_T<float>(m, N, dt, filt_mean, filt_cov, y, site_mean, site_cov, smooth_mean, smooth_cov, new_site_mean, new_site_cov, ws, ws_bytes, flags, stream);
 }
+#endif
 
+#if KJX_PART != 32
 int kjx_run_f64(const kjx_model_t* m, int64_t N, const double* dt, const double* y, const double* site_mean,
                 const double* site_cov, double* filt_mean, double* filt_cov, double* new_site_mean,
                 double* new_site_cov, double* post_mean, double* post_var, double* nlml, void* ws, size_t ws_bytes,
                 uint32_t flags, kjx_stream_t stream) {
   return run_T<double>(m, N, dt, y, site_mean, site_cov, filt_mean, filt_cov, new_site_mean, new_site_cov, post_mean, post_var, nlml, ws, ws_bytes, flags, stream);
 }
+#endif
+#if KJX_PART != 64
 int kjx_run_f32(const kjx_model_t* m, int64_t N, const float* dt, const float* y, const float* site_mean,
                 const float* site_cov, float* filt_mean, float* filt_cov, float* new_site_mean, float* new_site_cov,
                 float* post_mean, float* post_var, float* nlml, void* ws, size_t ws_bytes, uint32_t flags,
                 kjx_stream_t stream) {
   return run_T<float>(m, N, dt, y, site_mean, site_cov, filt_mean, filt_cov, new_site_mean, new_site_cov, post_mean, post_var, nlml, ws, ws_bytes, flags, stream);
 }
+#endif
 
+#if KJX_PART != 32
 int kjx_posterior_f64(const kjx_model_t* m, int64_t N, const double* dt, const double* y, const uint8_t* mask,
                       const double* site_mean, const double* site_cov, double* post_mean, double* post_var, double* nlml,
                       void* ws, size_t ws_bytes, kjx_stream_t stream) {
   return posterior_T<double>(m, N, dt, y, mask, site_mean, site_cov, post_mean, post_var, nlml, ws, ws_bytes, stream);
 }
+#endif
 
+#if KJX_PART != 32
 int kjx_site_update_f64(const kjx_model_t* m, int64_t N, const double* y, const double* post_mean, const double* post_var,
                         const double* site_mean_prev, const double* site_var_prev, double* log_lik, double* site_mean,
                         double* site_var, kjx_stream_t stream) {
   return site_update_T<double>(m, N, y, post_mean, post_var, site_mean_prev, site_var_prev, log_lik, site_mean, site_var, stream);
 }
+#endif
+#if KJX_PART != 64
 int kjx_site_update_f32(const kjx_model_t* m, int64_t N, const float* y, const float* post_mean, const float* post_var,
                         const float* site_mean_prev, const float* site_var_prev, float* log_lik, float* site_mean,
                         float* site_var, kjx_stream_t stream) {
   return site_update_T<float>(m, N, y, post_mean, post_var, site_mean_prev, site_var_prev, log_lik, site_mean, site_var, stream);
 }
+#endif
 
+#if KJX_PART != 32
 int kjx_discretise_f64(const kjx_model_t* m, int64_t N, const double* dt, double* A, double* Q, kjx_stream_t stream) {
   return discretise_T<double>(m, N, dt, A, Q, nullptr, stream);
 }
+#endif
+#if KJX_PART != 64
 int kjx_discretise_f32(const kjx_model_t* m, int64_t N, const float* dt, float* A, float* Q, kjx_stream_t stream) {
   return discretise_T<float>(m, N, dt, A, Q, nullptr, stream);
 }
+#endif
 
+#if KJX_PART != 32
 size_t kjx_filter_summary_doubles(int32_t d) { return (size_t)(d * d + d + d * (d + 1) / 2 + d + d * (d + 1) / 2); }
+#endif
 
 #define KJX_SMALL_DISPATCH(call32, call52)                     \
   switch (small_kind(m)) {                                     \
@@ -879,6 +690,7 @@ size_t kjx_filter_summary_doubles(int32_t d) { return (size_t)(d * d + d + d * (
     default: return KJX_ERR_UNSUPPORTED;                       \
   }
 
+#if KJX_PART != 32
 int kjx_filter_summary_f64(const kjx_model_t* m, int64_t N, const double* dt, const double* y, const double* site_mean,
                            const double* site_cov, double* summary_out, void* ws, size_t ws_bytes, kjx_stream_t stream) {
   if (!model_basic_ok(m) || N <= 0 || !dt || !y || !summary_out) return KJX_ERR_INVALID_ARG;
@@ -887,7 +699,9 @@ int kjx_filter_summary_f64(const kjx_model_t* m, int64_t N, const double* dt, co
   KJX_SMALL_DISPATCH((shard_summary<double, KJX_BLOCK_MATERN32>(m, N, dt, y, site_mean, site_cov, summary_out, ws, ws_bytes, st)),
                      (shard_summary<double, KJX_BLOCK_MATERN52>(m, N, dt, y, site_mean, site_cov, summary_out, ws, ws_bytes, st)))
 }
+#endif
 
+#if KJX_PART != 32
 int kjx_filter_apply_f64(const kjx_model_t* m, int64_t N, const double* dt, const double* y, const double* site_mean,
                          const double* site_cov, const double* state_in, double* nlml_partial, void* ws, size_t ws_bytes,
                          kjx_stream_t stream) {
@@ -897,7 +711,9 @@ int kjx_filter_apply_f64(const kjx_model_t* m, int64_t N, const double* dt, cons
   KJX_SMALL_DISPATCH((shard_filter<double, KJX_BLOCK_MATERN32>(m, N, dt, y, site_mean, site_cov, state_in, nlml_partial, ws, ws_bytes, st)),
                      (shard_filter<double, KJX_BLOCK_MATERN52>(m, N, dt, y, site_mean, site_cov, state_in, nlml_partial, ws, ws_bytes, st)))
 }
+#endif
 
+#if KJX_PART != 32
 int kjx_smoother_apply_f64(const kjx_model_t* m, int64_t N, const double* dt, const double* y, const double* site_mean,
                            const double* site_cov, const double* info_in, double* post_mean, double* post_var,
                            double* new_site_mean, double* new_site_cov, void* ws, size_t ws_bytes, uint32_t flags,
@@ -910,7 +726,9 @@ int kjx_smoother_apply_f64(const kjx_model_t* m, int64_t N, const double* dt, co
   KJX_SMALL_DISPATCH((shard_smoother<double, KJX_BLOCK_MATERN32>(m, N, dt, y, site_mean, site_cov, info_in, post_mean, post_var, new_site_mean, new_site_cov, ws, ws_bytes, flags, st)),
                      (shard_smoother<double, KJX_BLOCK_MATERN52>(m, N, dt, y, site_mean, site_cov, info_in, post_mean, post_var, new_site_mean, new_site_cov, ws, ws_bytes, flags, st)))
 }
+#endif
 
+#if KJX_PART != 32
 int kjx_fold_shard_summaries_host(const kjx_model_t* m, const double* summaries_host, int64_t stride, int32_t world,
                                   int32_t rank, double* state_out_host, double* info_out_host) {
   if (!model_basic_ok(m) || !summaries_host || !state_out_host || !info_out_host || rank < 0 || world <= rank) return KJX_ERR_INVALID_ARG;
@@ -920,7 +738,9 @@ int kjx_fold_shard_summaries_host(const kjx_model_t* m, const double* summaries_
   else fold_shards<3>(m->Pinf, summaries_host, stride, world, rank, state_out_host, info_out_host);
   return KJX_OK;
 }
+#endif
 
+#if KJX_PART != 32
 int kjx_fold_shard_summaries_f64(const kjx_model_t* m, const double* summaries, int64_t stride, int32_t world,
                                  int32_t rank, double* state_out, double* info_out, kjx_stream_t stream) {
   if (!model_basic_ok(m) || !summaries || !state_out || !info_out || rank < 0 || world <= rank) return KJX_ERR_INVALID_ARG;
@@ -935,7 +755,9 @@ int kjx_fold_shard_summaries_f64(const kjx_model_t* m, const double* summaries, 
   }
   return cudaGetLastError() == cudaSuccess ? KJX_OK : KJX_ERR_CUDA;
 }
+#endif
 
+#if KJX_PART != 32
 int kjx_exchange_fold_f64(const kjx_model_t* m, const double* my_summary, double* const* peer_bufs, int64_t stride,
                           int32_t world, int32_t rank, uint64_t* epoch, double* state_out, double* info_out,
                           kjx_stream_t stream) {
@@ -953,7 +775,9 @@ int kjx_exchange_fold_f64(const kjx_model_t* m, const double* my_summary, double
   }
   return cudaGetLastError() == cudaSuccess ? KJX_OK : KJX_ERR_CUDA;
 }
+#endif
 
+#if KJX_PART != 32
 int kjx_run_host_scratch_bytes(const kjx_model_t* m, int64_t N, int dtype_bytes, size_t* bytes) {
   size_t ws = 0;
   int rc = kjx_workspace_bytes(m, N, dtype_bytes, &ws);
@@ -966,7 +790,9 @@ int kjx_run_host_scratch_bytes(const kjx_model_t* m, int64_t N, int dtype_bytes,
            (dense ? round_up(n * d * dtype_bytes, 256) + round_up(n * d * d * dtype_bytes, 256) : 0) + 256;
   return KJX_OK;
 }
+#endif
 
+#if KJX_PART != 32
 int kjx_run_host_f64(const kjx_model_t* m, int64_t N, const double* dt_host, const double* y_host,
                      const double* site_mean_host, const double* site_cov_host, double* new_site_mean_host,
                      double* new_site_cov_host, double* post_mean_host, double* post_var_host, double* nlml_host,
@@ -1021,45 +847,6 @@ int kjx_run_host_f64(const kjx_model_t* m, int64_t N, const double* dt_host, con
   KJX_CUDA_CHECK(cudaStreamSynchronize(st));
   return KJX_OK;
 }
-
-/* ---- prior samples (sde_gp.py:386-417), d <= 64, constant measurement row ---- */
-int kjx_prior_sample_workspace_bytes(const kjx_model_t* m, int64_t N, int32_t num_samps, size_t* bytes) {
-  if (!model_basic_ok(m) || N < 0 || num_samps < 0 || !bytes) return KJX_ERR_INVALID_ARG;
-  const size_t d = (size_t)m->state_dim, S = (size_t)std::min<int32_t>(std::max<int32_t>(num_samps, 1), KJX_SAMPLE_MAXS);
-  *bytes = round_up(d * d * 8, 256) + round_up(d * 8, 256) + round_up((size_t)(N + 1) * d * S * 8, 256);
-  return KJX_OK;
-}
-
-int kjx_prior_sample_f64(const kjx_model_t* m, int64_t N, const double* dt, int32_t num_samps, uint64_t seed,
-                         double* f_sample, void* ws, size_t ws_bytes, kjx_stream_t stream) {
-  if (!model_basic_ok(m) || N < 0 || num_samps < 0 || (N > 0 && num_samps > 0 && (!dt || !f_sample))) return KJX_ERR_INVALID_ARG;
-  if (m->func_dim != 1 || !m->H || m->state_dim > 64) return KJX_ERR_UNSUPPORTED;   // the reference has no spatio-temporal sampling either (:432)
-  if (N == 0 || num_samps == 0) return KJX_OK;
-  size_t need = 0;
-  kjx_prior_sample_workspace_bytes(m, N, num_samps, &need);
-  if (!ws || ws_bytes < need) return KJX_ERR_WORKSPACE;
-  cudaStream_t st = (cudaStream_t)stream;
-  const int d = m->state_dim;
-  DiscArgs da; memset(&da, 0, sizeof(da));
-  da.d = d; da.n_blocks = m->n_blocks;
-  for (int b = 0; b < m->n_blocks; ++b) da.blocks[b] = m->blocks[b];
-  char* p = (char*)ws;
-  double* pinf_dev = (double*)p; p += round_up((size_t)d * d * 8, 256);
-  double* h_dev = (double*)p; p += round_up((size_t)d * 8, 256);
-  double* W = (double*)p;
-  KJX_CUDA_CHECK(cudaMemcpyAsync(pinf_dev, m->Pinf, (size_t)d * d * 8, cudaMemcpyHostToDevice, st));
-  KJX_CUDA_CHECK(cudaMemcpyAsync(h_dev, m->H, (size_t)d * 8, cudaMemcpyHostToDevice, st));
-  for (int s0 = 0; s0 < num_samps; s0 += KJX_SAMPLE_MAXS) {
-    const int S = std::min<int>(KJX_SAMPLE_MAXS, num_samps - s0);
-    const size_t smem = sample_noise_smem(d, S);
-    KJX_CUDA_CHECK(cudaFuncSetAttribute(sample_noise_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sample_noise_kernel<<<(unsigned)std::min<int64_t>(N + 1, 148 * 8), KJX_SAMPLE_THREADS, smem, st>>>(da, N, dt, pinf_dev, S, s0, seed, W);
-    const int nw = KJX_SAMPLE_THREADS / 32;
-    sample_path_kernel<<<(unsigned)((S + nw - 1) / nw), KJX_SAMPLE_THREADS, (size_t)nw * 2 * d * sizeof(double), st>>>(
-        da, N, dt, h_dev, W, S, s0, num_samps, f_sample);
-  }
-  KJX_CUDA_CHECK(cudaGetLastError());
-  return KJX_OK;
-}
+#endif
 
 }  // extern "C"
