@@ -65,7 +65,8 @@ __device__ __forceinline__ void transition_row(const DiscArgs& da, int r, T dt, 
       } else if (blk.kind == KJX_BLOCK_MATERN12) {          // priors.py:94-104
         v[0] = exp(-dt * lam);
       } else if (blk.kind == KJX_BLOCK_ROTATION) {          // priors.py:397-408, :791-820, :910-939; utils.py:253-265
-        const T cs = cos((T)blk.omega * dt), sn = sin((T)blk.omega * dt);
+        T sn, cs;
+        sincos((T)blk.omega * dt, &sn, &cs);          // one argument reduction for both
         const T e = (blk.lam != 0.0) ? exp(-dt * lam) : T(1);
         if (rr == 0) { v[0] = e * cs; v[1] = e * (-sn); } else { v[0] = e * sn; v[1] = e * cs; }
       } else if (blk.kind == KJX_BLOCK_MATERN72) {          // priors.py:326-350
@@ -85,7 +86,8 @@ __device__ __forceinline__ void transition_row(const DiscArgs& da, int r, T dt, 
         }
       } else {                                              // priors.py:1066-1084, utils.py:253-265
         const T e = exp(-dt * lam);
-        const T cs = cos((T)blk.omega * dt), sn = sin((T)blk.omega * dt);
+        T sn, cs;
+        sincos((T)blk.omega * dt, &sn, &cs);          // one argument reduction for both
         // R = [[cs, -sn],[sn, cs]];  block = e * [[(1+dt lam) R, dt R], [-dt lam^2 R, (1-dt lam) R]]
         const T r0 = (rr & 1) ? sn : cs, r1 = (rr & 1) ? cs : -sn;   // row (rr&1) of R
         const T f0 = (rr < 2) ? (T(1) + dt * lam) : (-dt * lam * lam);

@@ -95,9 +95,18 @@ template <typename T> int generic_launch_scan(const GenArgs<T>& g, cudaStream_t 
   return KJX_OK;
 }
 template <typename T> int generic_launch_filter(const GenArgs<T>& g, cudaStream_t st) {
-  const size_t smem = g.gscratch ? 0 : generic_filter_smem<T>(g.d);
-  KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_filter_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  generic_filter_kernel<T><<<g.nchunks, KJX_GEN_THREADS, smem, st>>>(g);
+  int nblk = 0;
+  for (int b = 0; b < g.disc.n_blocks; ++b) nblk += g.disc.blocks[b].count;
+  if (nblk <= 16 && !getenv("KJX_GEN_TILE_FILTER")) {
+    // at most 16 diagonal blocks: P in registers, one thread per pair of blocks
+    const size_t smem = generic_filter_blocks_smem<T>(g.d);
+    KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_filter_blocks_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    generic_filter_blocks_kernel<T><<<g.nchunks, KJX_GEN_THREADS, smem, st>>>(g);
+  } else {
+    const size_t smem = g.gscratch ? 0 : generic_filter_smem<T>(g.d);
+    KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_filter_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    generic_filter_kernel<T><<<g.nchunks, KJX_GEN_THREADS, smem, st>>>(g);
+  }
   if (g.nlml) nlml_reduce_kernel<T><<<1, 256, 0, st>>>(g.chunk_nlml, g.nchunks, g.nlml);
   return KJX_OK;
 }

@@ -966,6 +966,138 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_filter_kernel(const G
 }
 
 // ------------------------------------------------------------------------------------------------
+// The same filter for priors with at most 16 diagonal blocks (every Sum of Matern / quasi-periodic components up to
+// d = 64): P lives in REGISTERS, thread (bi, bj) owning the (block bi, block bj) tile of at most 4 x 4 entries.  A is
+// block diagonal, so the prediction A (P - Pinf) A^T + Pinf is local to a thread — no pass over shared memory and no
+// barrier — and only the row vector H P needs a reduction over block rows.  Three barriers per step instead of six and
+// none of the tile traffic that bounds the kernel above; bit-compatible with it up to the order of that one reduction.
+template <typename T> size_t generic_filter_blocks_smem(int d) {
+  return (size_t)(4 * d + 4 * d + 16 * d + 16) * sizeof(T) + (size_t)(d + 40) * sizeof(int) + 256;
+}
+template <typename T>
+__global__ void __launch_bounds__(KJX_GEN_THREADS, 1) generic_filter_blocks_kernel(const GenArgs<T> g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmemCarver<T> sc(smem_raw);
+  const int d = g.d, dd = d * d, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  T* vals = sc.take(4 * d); T* m = sc.take(d); T* mp = sc.take(d); T* Hrow = sc.take(d); T* HP = sc.take(d);
+  T* part = sc.take(16 * d);
+  T* sh = sc.take(16);                 // scalars: 0 pm, 2 site_mean, 4 Sinv, 5 masked, 6 nlml
+  int* c0n = sc.take_int(d); int* bstart = sc.take_int(17); int* bsize = sc.take_int(17);
+  const int64_t n0 = (int64_t)blockIdx.x * g.chunk_len, n1 = (n0 + g.chunk_len < g.N) ? n0 + g.chunk_len : g.N;
+  build_rows<T>(g.disc, d, T(0), vals, c0n);                 // block structure of A
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int nb = 0;
+    for (int i = 0; i < d; ++i) if ((c0n[i] & 0xffffff) == i) { bstart[nb] = i; bsize[nb] = c0n[i] >> 24; ++nb; }
+    bstart[16] = nb; sh[6] = T(0);
+  }
+  KJX_GEN_VEC(i, d) { m[i] = g.st_m[(size_t)blockIdx.x * d + i]; if (g.H) Hrow[i] = (T)g.H[i]; }
+  __syncthreads();
+  const int nblk = bstart[16];
+  const bool owner = (int)threadIdx.x < nblk * nblk;
+  const int bi = owner ? (int)threadIdx.x / nblk : 0, bj = owner ? (int)threadIdx.x % nblk : 0;
+  const int r0 = bstart[bi], ni = owner ? bsize[bi] : 0, c0 = bstart[bj], nj = owner ? bsize[bj] : 0;
+  T Pb[4][4], Qb[4][4];
+  {
+    const T* sP = g.st_P + (size_t)blockIdx.x * dd;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const bool in = a < ni && b < nj;
+        Pb[a][b] = in ? sP[(size_t)(r0 + a) * d + c0 + b] : T(0);
+        Qb[a][b] = in ? (T)g.Pinf[(size_t)(r0 + a) * d + c0 + b] : T(0);
+      }
+  }
+  for (int64_t n = n0; n < n1; ++n) {
+    build_rows<T>(g.disc, d, g.dt[n], vals, c0n);                                   // :276
+    if (g.H_steps) KJX_GEN_VEC(i, d) Hrow[i] = (T)g.H_steps[n * d + i];             // :282
+    __syncthreads();
+    rows_matvec<T>(d, vals, c0n, m, mp);                                            // :277
+    if (owner) {
+      T Fi[4][4], Fj[4][4], Y[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { Fi[a][q] = (a < ni) ? vals[(r0 + a) * 4 + q] : T(0); Fj[a][q] = (a < nj) ? vals[(c0 + a) * 4 + q] : T(0); }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {                                               // Y = A (P - Pinf)
+          T s = T(0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) if (q < ni) s += Fi[a][q] * (Pb[q][b] - Qb[q][b]);
+          Y[a][b] = s;
+        }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {                                               // P_ = Y A^T + Pinf        (:278)
+          T t = T(0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) if (q < nj) t += Y[a][q] * Fj[b][q];
+          Pb[a][b] = (a < ni && b < nj) ? t + Qb[a][b] : T(0);
+        }
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {                                                 // this block row's share of H P_
+        if (b < nj) {
+          T s = T(0);
+#pragma unroll
+          for (int a = 0; a < 4; ++a) if (a < ni) s += Hrow[r0 + a] * Pb[a][b];
+          part[bi * d + c0 + b] = s;
+        }
+      }
+    }
+    __syncthreads();
+    KJX_GEN_VEC(j, d) HP[j] = partial_total<T>(d, part, j, nblk);
+    if (warp == 0) {                   // warp 0: the step's scalar work; cubature points spread over its lanes
+      T pm = T(0), pv = T(0);
+      KJX_GEN_COLS(j, d) { pm += Hrow[j] * mp[j]; pv += partial_total<T>(d, part, j, nblk) * Hrow[j]; }   // :283-284
+      pm = warp_sum(pm); pv = warp_sum(pv);
+      const bool masked = g.mask ? (g.mask[n] != 0) : false;
+      T smean, svar, lml = T(0);
+      if (g.init_sites) {
+        const SiteOut<T> o = site_update<T, WarpRed>(g.site, masked ? pm : g.y[n], pm, pv, false, T(0), T(0));   // :286-287
+        smean = o.mean; svar = o.var; lml = o.lml;
+      } else {
+        if (g.site_mean) { smean = g.site_mean[n]; svar = g.site_var[n]; }           // :290
+        else { smean = g.y[n]; svar = T(g.site.lik_hyp); }                           // Gaussian + EP initialisation
+        if (!masked) lml = filter_loglik<T, WarpRed>(g.site, g.y[n], pm, pv);        // log Z is always the true likelihood's
+      }
+      if (masked) lml = T(0);                                                        // :300
+      if (lane == 0) {
+        sh[0] = pm; sh[2] = smean; sh[4] = inv1(pv + svar); sh[5] = masked ? T(1) : T(0);   // :292-294
+        sh[6] += lml;                                                                // :301
+        if (g.out_site_mean) { g.out_site_mean[n] = smean; g.out_site_var[n] = svar; }
+      }
+    }
+    __syncthreads();
+    const bool masked = sh[5] != T(0);
+    const T Sinv = sh[4], innov = sh[2] - sh[0];
+    KJX_GEN_VEC(i, d) {
+      const T mi = masked ? mp[i] : mp[i] + HP[i] * Sinv * innov;                    // :295 / :298
+      m[i] = mi;
+      if (g.filt_mean) g.filt_mean[n * d + i] = mi;
+    }
+    if (owner) {
+      T* fc = g.filt_cov ? g.filt_cov + n * (int64_t)dd : nullptr;
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          if (a < ni && b < nj) {
+            if (!masked) Pb[a][b] = Pb[a][b] - HP[r0 + a] * Sinv * HP[c0 + b];       // :296 / :299
+            if (fc) fc[(size_t)(r0 + a) * d + c0 + b] = Pb[a][b];
+          }
+        }
+    }
+    // (the next step's first barrier separates these reads of HP / sh / mp from their next writes)
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) g.chunk_nlml[blockIdx.x] = sh[6];
+}
+
+// ------------------------------------------------------------------------------------------------
 // RTS gains, embarrassingly parallel over time: Gt[n] = solve(P_pred[n], A[n+1] Pf[n]) depends only on the FILTERED
 // moments (sde_gp.py:351-359), so a grid of CTAs computes them all before the (sequential) backward recursion.
 // Working set: two tiles in shared memory (61 KB at d = 59, three CTAs per SM); Pf and Pinf are read from global / L1.
