@@ -1,7 +1,7 @@
 """GP priors as LTI SDEs — host-side mirror of /root/reference/kalmanjax/priors.py for the priors named
 by BASELINE.json (Matern-3/2, Matern-5/2, QuasiPeriodicMatern32, Sum, SpatioTemporalMatern52) and, from the model
 zoo of SURVEY 8(f)-4, Matern-1/2 (Exponential), Matern-7/2, Cosine, Periodic, QuasiPeriodicMatern12,
-SubbandMatern12 and SubbandMatern32.
+SubbandMatern12, SubbandMatern32, SpatialMatern52 and SpatialMatern32.
 
 Same class names, constructor arguments and `hyp` convention (softplus-inverse of the positive
 hyperparameters) as the reference.  What is computed here on the host is only what the reference
@@ -511,3 +511,65 @@ class SpatioTemporalMatern52(Prior):
 
     def blocks(self, hyperparams=None):
         return [(_lib.BLOCK_MATERN52, int(self.M), float(np.sqrt(5.0) / self._theta(hyperparams)[1]), 0.0)]
+
+
+def _matern32_spatial_kernel(X, X2, lengthscale):
+    """kernels.py:29-36, 72-75 with utils.py:626-654."""
+    X, X2 = X / lengthscale, X2 / lengthscale
+    Xs, X2s = np.sum(np.square(X), axis=-1), np.sum(np.square(X2), axis=-1)
+    r2 = -2 * np.tensordot(X, X2, [[-1], [-1]]) + Xs.reshape(-1, 1) + X2s.reshape(1, -1)
+    r = np.sqrt(np.maximum(r2, 1e-36))
+    sqrt3 = np.sqrt(3.0)
+    return (1.0 + sqrt3 * r) * np.exp(-sqrt3 * r)
+
+
+class SpatialMatern52(SpatioTemporalMatern52):
+    """priors.py:1184-1267: one lengthscale shared by time and space; hyp = [variance, lengthscale]."""
+    def __init__(self, variance=1.0, lengthscale=1.0, z=None, fixed_grid=False):
+        SpatioTemporalMatern52.__init__(self, variance, lengthscale, lengthscale, z=z, fixed_grid=fixed_grid)
+        Prior.__init__(self, hyp=[variance, lengthscale])
+        self.name = 'Spatial Matern-5/2'
+
+    def _theta(self, hyperparams):
+        th = Prior._theta(self, hyperparams)
+        return np.array([th[0], th[1], th[1]]) if np.size(th) == 2 else th      # (variance, time = space lengthscale)
+
+
+class SpatialMatern32(Prior):
+    """priors.py:1270-1344."""
+    def __init__(self, variance=1.0, lengthscale=1.0, z=None, fixed_grid=False):
+        super().__init__(hyp=[variance, lengthscale])
+        if z is None:
+            z = np.linspace(-3., 3., num=15)
+        self.z = np.asarray(z, dtype=np.float64).reshape(-1, 1)
+        self.M = self.z.shape[0]
+        self.state_dim = 2 * self.M
+        self.fixed_grid = fixed_grid
+        self.name = 'Spatial Matern-3/2'
+
+    def kernel_to_state_space(self, hyperparams=None):
+        var, ell = self._theta(hyperparams)
+        Kmm = _matern32_spatial_kernel(self.z, self.z, ell)
+        lam = 3.0 ** 0.5 / ell
+        F = np.kron(np.eye(self.M), np.array([[0.0, 1.0], [-lam ** 2, -2 * lam]]))
+        Pinf_time = np.array([[var, 0.0], [0.0, 3.0 * var / ell ** 2.0]])
+        return F, np.array([[0], [1]]), np.array([[12.0 * 3.0 ** 0.5 / ell ** 3.0 * var]]), None, np.kron(Kmm, Pinf_time)
+
+    def spatial_weights(self, r, hyperparams=None):
+        ell = self._theta(hyperparams)[1]
+        r = np.asarray(r, dtype=np.float64).reshape(-1, 1)
+        if self.fixed_grid:
+            return np.tile(np.eye(self.M)[None], (r.shape[0], 1, 1))
+        Kzz = _matern32_spatial_kernel(self.z, self.z, ell)
+        Kxz = _matern32_spatial_kernel(r, self.z, ell)
+        return sl.cho_solve(sl.cho_factor(Kzz), Kxz.T).T
+
+    def measurement_model(self, r, hyperparams=None):
+        return np.kron(self.spatial_weights(r, hyperparams), np.array([[1.0, 0.0]]))
+
+    def state_transition(self, dt, hyperparams=None):
+        lam = np.sqrt(3.0) / self._theta(hyperparams)[1]
+        return np.kron(np.eye(self.M), np.exp(-dt * lam) * (dt * np.array([[lam, 1.0], [-lam ** 2.0, -lam]]) + np.eye(2)))
+
+    def blocks(self, hyperparams=None):
+        return [(_lib.BLOCK_MATERN32, int(self.M), float(np.sqrt(3.0) / self._theta(hyperparams)[1]), 0.0)]

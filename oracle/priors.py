@@ -5,7 +5,7 @@ that the Kalman filter / RTS smoother touch: Pinf, H (measurement model) and the
 A(dt) = expm(F dt).  Hyperparameters are the already-transformed (positive) values.
 Restated: the priors named by BASELINE.json's configs (Matern-3/2, Matern-5/2, QuasiPeriodicMatern32, Sum,
 SpatioTemporalMatern52) and, from SURVEY 8(f)-4's model zoo, Matern-1/2 (Exponential), Matern-7/2, Cosine, Periodic,
-QuasiPeriodicMatern12, SubbandMatern12 / SubbandMatern32.
+QuasiPeriodicMatern12, SubbandMatern12 / SubbandMatern32, SpatialMatern52 / SpatialMatern32.
 """
 import numpy as np
 import scipy.linalg as sl
@@ -343,3 +343,53 @@ class SpatioTemporalMatern52(object):
 
     def state_transition(self, dt):
         return np.kron(np.eye(self.M), matern52_transition(dt, self.hyp[1]))              # :1180
+
+
+def matern32_kernel(X, X2, lengthscale):
+    """kernels.py:29-36 + 72-75 with utils.py:626-654."""
+    X, X2 = X / lengthscale, X2 / lengthscale
+    Xs, X2s = np.sum(np.square(X), axis=-1), np.sum(np.square(X2), axis=-1)
+    r2 = -2 * np.tensordot(X, X2, [[-1], [-1]]) + Xs.reshape(-1, 1) + X2s.reshape(1, -1)
+    r = np.sqrt(np.maximum(r2, 1e-36))
+    sqrt3 = np.sqrt(3.0)
+    return (1.0 + sqrt3 * r) * np.exp(-sqrt3 * r)
+
+
+class SpatialMatern52(SpatioTemporalMatern52):
+    """priors.py:1184-1267: the spatio-temporal prior with ONE lengthscale shared by time and space."""
+    def __init__(self, variance=1.0, lengthscale=1.0, z=None, fixed_grid=False):
+        SpatioTemporalMatern52.__init__(self, variance, lengthscale, lengthscale, z=z, fixed_grid=fixed_grid)
+
+
+class SpatialMatern32(object):
+    """priors.py:1270-1344: M copies of the Matern-3/2 temporal state, Matern-3/2 spatial kernel, shared lengthscale."""
+    def __init__(self, variance=1.0, lengthscale=1.0, z=None, fixed_grid=False):
+        self.hyp = np.array([variance, lengthscale], dtype=float)
+        if z is None:
+            z = np.linspace(-3., 3., num=15)                                              # :1282
+        self.z = np.asarray(z, dtype=float).reshape(-1, 1)
+        self.M = self.z.shape[0]
+        self.state_dim = 2 * self.M
+        self.fixed_grid = fixed_grid
+
+    def kernel_to_state_space(self):
+        var, ell = self.hyp
+        Kmm = matern32_kernel(self.z, self.z, ell)                                        # :1302
+        Pinf_time = np.array([[var, 0.0], [0.0, 3.0 * var / ell ** 2.0]])                 # :1311-1312
+        return None, np.kron(Kmm, Pinf_time)                                              # :1313
+
+    def spatial_weights(self, r):
+        if self.fixed_grid:
+            return np.eye(self.M)
+        ell = self.hyp[1]
+        Kzz = matern32_kernel(self.z, self.z, ell)
+        Kxz = matern32_kernel(np.asarray(r, dtype=float).reshape(-1, 1), self.z, ell)
+        return sl.cho_solve(sl.cho_factor(Kzz), Kxz.T).T                                  # :1325-1327
+
+    def measurement_model(self, r):
+        return np.kron(self.spatial_weights(r), np.array([[1.0, 0.0]]))                   # :1328
+
+    def state_transition(self, dt):
+        lam = np.sqrt(3.0) / self.hyp[1]                                                  # :1341-1343
+        A_time = np.exp(-dt * lam) * (dt * np.array([[lam, 1.0], [-lam ** 2.0, -lam]]) + np.eye(2))
+        return np.kron(np.eye(self.M), A_time)
