@@ -6,6 +6,7 @@ One JSON object per line:
   * fp32:        the fused iteration in float (C5 recipe), steps/s and fraction of the 144 B/step fp32 roofline
   * c1:          BASELINE config 1 (N = 10k) iteration latency
   * c3:          aircraft-sized series (N = 36 020 daily bins, Sum[Matern52, QPM32, QPM32], d = 59, Poisson, GHEP)
+  * c4:          spatio-temporal Probit, Ns = 64 -> d = 192, N = 4096 (only when asked for: `bench_extra.py c4`)
   * first_iter:  first iteration of a non-Gaussian model (one-chain filter that initialises the sites), N = 2^17
 """
 import json
@@ -91,6 +92,25 @@ def c3():
                       "note": "generic d <= 64 path: CTA-level chunked scan (fold -> boundary -> filter / gains / smoother per chunk); the first iteration initialises the Poisson sites with the one-chain filter"}))
 
 
+def c4():
+    """BASELINE config 4 shape: Ns = 64 inducing points -> d = 192 (per-step dense H), N = 4096 scattered points,
+    Probit, VI.  The generic kernels run from per-CTA global scratch here (untuned: DESIGN.md)."""
+    rng = np.random.default_rng(99)
+    N = int(os.environ.get("C4_N", 4096))
+    t = np.sort(rng.uniform(0, 400, N))
+    r = rng.uniform(-3, 3, N)
+    y = (rng.uniform(size=N) < 0.5).astype(float)
+    z = np.linspace(-3, 3, 64)
+    model = kjx.SDEGP(kjx.priors.SpatioTemporalMatern52(1.0, 1.0, 0.3, z=z), kjx.likelihoods.Probit(), t, y, r=r,
+                      approx_inf=kjx.approximate_inference.VI())
+    t0 = time.perf_counter(); model.run(compute_grad=False); torch.cuda.synchronize(); first = time.perf_counter() - t0
+    sec = timed(lambda: model.run(compute_grad=False), reps=2, warm=0)
+    d = 192
+    print(json.dumps({"bench": "c4_st52_ns64_d192", "N": N, "d": d, "first_iteration_s": first, "s_per_iteration": sec,
+                      "steps_per_s": N / sec, "algorithmic_tflops": 12.0 * d ** 3 * N / sec / 1e12,
+                      "note": "generic path from per-CTA global scratch (d > 64), FP64 tensor-pipe products; untuned"}))
+
+
 def first_iter():
     N = 1 << 17
     dt, y = synth(N)
@@ -105,6 +125,8 @@ def first_iter():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["site_update", "fp32", "c1", "c3", "first_iter"]
+    if "c4" in which:
+        c4()
     if "site_update" in which:
         site_update()
     if "fp32" in which:
