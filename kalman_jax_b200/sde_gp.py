@@ -193,8 +193,13 @@ class SDEGP(object):
         theta_lik = softplus(params[1]) if np.size(params[1]) else None
         H_steps = None
         if hasattr(self.prior, "spatial_weights") and not self.prior.fixed_grid:
-            # spatio-temporal prior with scattered data: H depends on r_n (priors.py:1148-1161)
-            Hs = np.stack([self.prior.measurement_model(rn, theta_prior) for rn in np.asarray(r)])
+            # spatio-temporal prior with scattered data: H depends on r_n (priors.py:1148-1161).  All steps at once:
+            # one factorisation of Kzz and one solve with N right-hand sides instead of N of each
+            r_all = np.asarray(r, dtype=np.float64).reshape(len(r), -1)
+            Kx = self.prior.spatial_weights(r_all[:, 0], theta_prior)                 # [N, M]
+            bs = self.prior.state_dim // self.prior.M                                 # temporal states per inducing point
+            Hs = np.zeros((Kx.shape[0], 1, self.prior.state_dim))
+            Hs[:, 0, ::bs] = Kx                                                       # kron(Kx[n], [1, 0, ..])
             H_steps = torch.as_tensor(Hs, dtype=torch.float64, device=self.device).contiguous()
         return _Model(self.prior, self.likelihood, self.sites, theta_prior, theta_lik, H_steps=H_steps,
                       r0=None if r is None else np.asarray(r)[0])
