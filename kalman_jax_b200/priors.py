@@ -573,3 +573,36 @@ class SpatialMatern32(Prior):
 
     def blocks(self, hyperparams=None):
         return [(_lib.BLOCK_MATERN32, int(self.M), float(np.sqrt(3.0) / self._theta(hyperparams)[1]), 0.0)]
+
+
+class Matern52FixedVar(Matern52):
+    """priors.py:1552-1600: the variance is a constant of the object, hyp is the (scalar) lengthscale."""
+    def __init__(self, variance=1.0, lengthscale=1.0):
+        Prior.__init__(self, hyp=lengthscale)
+        self.variance_fixed = variance
+        self.name = 'Matern-5/2'
+
+    @property
+    def variance(self):
+        return self.variance_fixed
+
+    @property
+    def lengthscale(self):
+        return softplus(self.hyp)
+
+    def _theta(self, hyperparams):
+        ell = float(np.reshape(softplus(self.hyp) if hyperparams is None else np.asarray(hyperparams, dtype=np.float64), -1)[-1])
+        return np.array([self.variance_fixed, ell])
+
+
+class SubbandExponentialFixedVar(SubbandMatern12):
+    """priors.py:1498-1549: constant variance, hyp = [lengthscale, radial_frequency]."""
+    def __init__(self, variance=1.0, lengthscale=1.0, radial_frequency=1.0):
+        Prior.__init__(self, hyp=[lengthscale, radial_frequency])
+        self.variance_fixed = variance
+        self.name = 'Subband Matern-1/2'
+
+    def _theta(self, hyperparams):
+        th = softplus(self.hyp) if hyperparams is None else np.asarray(hyperparams, dtype=np.float64)
+        th = np.reshape(th, -1)
+        return np.array([self.variance_fixed, th[-2], th[-1]])

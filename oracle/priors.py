@@ -393,3 +393,15 @@ class SpatialMatern32(object):
         lam = np.sqrt(3.0) / self.hyp[1]                                                  # :1341-1343
         A_time = np.exp(-dt * lam) * (dt * np.array([[lam, 1.0], [-lam ** 2.0, -lam]]) + np.eye(2))
         return np.kron(np.eye(self.M), A_time)
+
+
+class Matern52FixedVar(Matern52):
+    """priors.py:1552-1600: Matern-5/2 whose variance is a constant, not a hyperparameter (hyp = lengthscale)."""
+    def __init__(self, variance=1.0, lengthscale=1.0):
+        Matern52.__init__(self, variance, lengthscale)
+
+
+class SubbandExponentialFixedVar(SubbandMatern12):
+    """priors.py:1498-1549: SubbandMatern12 with a constant variance (hyp = [lengthscale, radial_frequency])."""
+    def __init__(self, variance=1.0, lengthscale=1.0, radial_frequency=1.0):
+        SubbandMatern12.__init__(self, variance, lengthscale, radial_frequency)
