@@ -399,6 +399,7 @@ class SDEGP(object):
             t = self.t
         else:
             t = np.asarray(t, dtype=np.float64)
+            t = t.reshape(t.shape[0], -1)
             t = t[np.argsort(t[:, 0])]                                              # :398-399
         dt = np.concatenate([np.array([0.0]), np.diff(t[:, 0])])                    # :400
         N = dt.shape[0]
