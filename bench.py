@@ -118,6 +118,22 @@ def cpu_chain(lib, dt, y, reps=1):
     return n / best
 
 
+def cpu_oracle_full(lib, dt, y, site_mean, site_var, power=0.5, damping=1.0, lik_var=0.5):
+    """One whole run() iteration of the C oracle over the full series; returns nlml and every per-step output."""
+    n = len(dt)
+    out = dict(fm=np.empty([n, 3]), fP=np.empty([n, 3, 3]), nsm=np.empty(n), nsv=np.empty(n), pm=np.empty(n), pv=np.empty(n))
+    dp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    out["nlml"] = lib.kjx_oracle_run(2, C.c_double(1.0), C.c_double(5.0), C.c_double(lik_var), C.c_double(power), C.c_double(damping),
+                                     C.c_long(n), dp(dt), dp(y), dp(site_mean), dp(site_var), dp(out["fm"]), dp(out["fP"]),
+                                     dp(out["nsm"]), dp(out["nsv"]), dp(out["pm"]), dp(out["pv"]))
+    return out
+
+
+def rel_err(a, b):
+    """max |a - b| / max |b| — the definition the parity tests use (tests/golden_util.py)."""
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(float(np.max(np.abs(b))), 1e-300))
+
+
 def cpu_replicas(lib, dt, y, cores, reps=1):
     """`cores` independent copies of the chain, one per host thread (the reference algorithm cannot use more
     than one core on one series: step n needs step n-1, sde_gp.py:271)."""
@@ -164,6 +180,42 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def make_collectives(world, rank, dev, exchange="peer"):
+    """(gather, reduce_nlml, peer) for a world of `world` ranks: the NCCL all-gather of the shard summaries, the scalar
+    all-reduce of the partial nlml values, and the symmetric-memory peer exchange (None when unavailable or not asked
+    for; every rank agrees on the path)."""
+    import torch
+    import torch.distributed as dist
+    gbuf = {}
+
+    def gather(t):
+        out = gbuf.get(t.numel())
+        if out is None:
+            out = gbuf[t.numel()] = torch.empty(world, t.numel(), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t)
+        return out
+
+    nl_buf = torch.zeros(1, dtype=torch.float64, device=dev)
+
+    def reduce_nlml(t):
+        nl_buf.copy_(t)
+        dist.all_reduce(nl_buf)
+        return nl_buf
+
+    peer = None
+    if exchange == "peer":
+        try:
+            from kalman_jax_b200.sharded import PeerExchange
+            peer = PeerExchange(world, rank, dev)
+        except Exception as e:
+            print("bench: symmetric memory unavailable (%s); using NCCL" % str(e).splitlines()[0], file=sys.stderr)
+    ok = torch.tensor([1 if (peer is not None or exchange == "nccl") else 0], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)          # all ranks must agree on the path
+    if int(ok[0]) == 0:
+        peer = None
+    return gather, reduce_nlml, peer
+
+
 # ---------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -174,6 +226,7 @@ def main():
     ap.add_argument("--impl", default="kjx")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the full-size comparison with the C oracle")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU summary exchange: fused peer-memory kernel (default) or NCCL all-gather")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying CUDA graphs")
@@ -192,44 +245,19 @@ def main():
     assert world == args.gpus, "launch with torchrun --nproc-per-node == --gpus"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    gather = reduce_nlml = None
+    gather = reduce_nlml = peer = None
+    exchange = "none (1 GPU)"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-        gbuf = {}
-
-        def gather(t):
-            out = gbuf.get(t.numel())
-            if out is None:
-                out = gbuf[t.numel()] = torch.empty(world, t.numel(), dtype=t.dtype, device=t.device)
-            dist.all_gather_into_tensor(out, t)
-            return out
-
-        nl_buf = torch.zeros(1, dtype=torch.float64, device=dev)
-
-        def reduce_nlml(t):
-            nl_buf.copy_(t)
-            dist.all_reduce(nl_buf)
-            return nl_buf
+        gather, reduce_nlml, peer = make_collectives(world, rank, dev, args.exchange)
+        exchange = ("fused peer-memory exchange+fold kernel (symmetric memory over NVLink)" if peer is not None
+                    else "NCCL all_gather_into_tensor + fold kernel")
 
     N = 1 << args.log2n
     dt, y = synth(N)
     sh_dt, sh_y, dt_next, lo, hi = split_series(dt, y, world)[rank]
     n_local = hi - lo
     prior, lik, rule = kjx.priors.Matern52(1.0, 5.0), kjx.likelihoods.Gaussian(0.5), kjx.approximate_inference.EP(power=0.5)
-    peer, exchange = None, "none (1 GPU)"
-    if world > 1:
-        exchange = "NCCL all_gather_into_tensor + fold kernel"
-        if args.exchange == "peer":
-            try:
-                from kalman_jax_b200.sharded import PeerExchange
-                peer = PeerExchange(world, rank, dev)
-                exchange = "fused peer-memory exchange+fold kernel (symmetric memory over NVLink)"
-            except Exception as e:
-                print("bench: symmetric memory unavailable (%s); using NCCL" % str(e).splitlines()[0], file=sys.stderr)
-        ok = torch.tensor([1 if (peer is not None or args.exchange == "nccl") else 0], device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)          # all ranks must agree on the path
-        if int(ok[0]) == 0:
-            peer, exchange = None, "NCCL all_gather_into_tensor + fold kernel"
     it = ShardedIteration(prior, lik, rule, sh_dt, sh_y, dt_next, rank, world, dev, gather,
                           site_mean=sh_y.copy(), site_var=np.full(n_local, 0.5), peer=peer)
 
@@ -287,6 +315,23 @@ def main():
     ms_total = start.elapsed_time(stop)
     phases = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(3)] for e in ev]).mean(axis=0)   # ms
     nlml = float(nl_t)
+
+    # ---- parity at the benchmark size (untimed): one more iteration, its outputs gathered on rank 0 and compared
+    # below with the plain-C sequential oracle run over the FULL series
+    par_out = None
+    if not args.no_parity:
+        nl_par = it.iteration(reduce_nlml=reduce_nlml)
+        outs = [it.post_mean, it.post_var, it.site_mean, it.site_var]      # site_* = the sites this iteration produced
+        if world > 1:
+            full = []
+            for o in outs:
+                g = torch.empty(world, o.numel(), dtype=o.dtype, device=dev)
+                dist.all_gather_into_tensor(g, o.reshape(-1).contiguous())
+                full.append(g.reshape(-1).cpu().numpy() if rank == 0 else None)
+                del g
+        else:
+            full = [o.reshape(-1).cpu().numpy() for o in outs]
+        par_out = (float(nl_par), full)
     tt = torch.tensor([ms_total, phases[0], phases[1], phases[2]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -407,6 +452,20 @@ def main():
     if e2e:
         line["e2e"] = e2e
         line["e2e_all_host"] = e2e_all
+    if par_out is not None:
+        lib = cpu_oracle_lib()
+        t0 = time.perf_counter()
+        want = cpu_oracle_full(lib, dt, y, y.copy(), np.full(N, 0.5))
+        t_or = time.perf_counter() - t0
+        got_nl, (g_pm, g_pv, g_sm, g_sv) = par_out
+        par = {"oracle": "oracle/seq_filter.c, one sequential chain over all N = 2^%d steps (%.1f s on 1 host core)" % (args.log2n, t_or),
+               "nlml_rel": abs(got_nl - want["nlml"]) / abs(want["nlml"]),
+               "post_mean_rel": rel_err(g_pm, want["pm"]), "post_var_rel": rel_err(g_pv, want["pv"]),
+               "site_rel": max(rel_err(g_sm, want["nsm"]), rel_err(g_sv, want["nsv"])),
+               "tol": 1e-9, "norm": "max|a-b| / max|b| per array"}
+        par["ok"] = bool(max(par["nlml_rel"], par["post_mean_rel"], par["post_var_rel"], par["site_rel"]) <= par["tol"])
+        line["parity"] = par
+        del want
     if not args.no_cpu:
         lib = cpu_oracle_lib()
         n_s = 1 << 22

@@ -86,7 +86,9 @@ enum kjx_method {
   KJX_INF_EP = 1,    /* ExpectationPropagation.update      approximate_inference.py:50-73    */
   KJX_INF_EEP = 2,   /* ExtendedEP.update (EKS: power 0)   approximate_inference.py:99-133   */
   KJX_INF_SLEP = 3,  /* StatisticallyLinearisedEP.update   approximate_inference.py:180-210  */
-  KJX_INF_VI = 4     /* VariationalInference.update        approximate_inference.py:302-323  */
+  KJX_INF_VI = 4,    /* VariationalInference.update        approximate_inference.py:302-323  */
+  KJX_INF_MOMENT_MATCH = 5 /* no update rule: Likelihood.moment_match(y, m, v, hyp, power) itself, likelihoods.py:122-185
+                        (kjx_site_update only; `power` raises the likelihood and scales the site variance) */
 };
 
 #define KJX_MAX_BLOCKS 16

@@ -451,7 +451,7 @@ template <typename T>
 int filter_T(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const uint8_t* mask, const T* site_mean,
              const T* site_cov, T* filt_mean, T* filt_cov, T* out_site_mean, T* out_site_cov, T* nlml, void* ws,
              size_t ws_bytes, uint32_t flags, kjx_stream_t stream) {
-  if (!model_basic_ok(m) || N < 0 || !dt || !y || !nlml) return KJX_ERR_INVALID_ARG;
+  if (!model_run_ok(m) || N < 0 || !dt || !y || !nlml) return KJX_ERR_INVALID_ARG;
   if ((site_mean == nullptr) != (site_cov == nullptr)) return KJX_ERR_INVALID_ARG;
   if ((filt_mean == nullptr) != (filt_cov == nullptr)) return KJX_ERR_INVALID_ARG;
   if ((out_site_mean == nullptr) != (out_site_cov == nullptr)) return KJX_ERR_INVALID_ARG;
@@ -469,7 +469,7 @@ template <typename T>
 int smoother_T(const kjx_model_t* m, int64_t N, const T* dt, const T* filt_mean, const T* filt_cov, const T* y,
                const T* site_mean, const T* site_cov, T* smooth_mean, T* smooth_cov, T* new_site_mean,
                T* new_site_cov, void* ws, size_t ws_bytes, uint32_t flags, kjx_stream_t stream) {
-  if (!model_basic_ok(m) || N < 0 || !dt || !filt_mean || !filt_cov) return KJX_ERR_INVALID_ARG;
+  if (!model_run_ok(m) || N < 0 || !dt || !filt_mean || !filt_cov) return KJX_ERR_INVALID_ARG;
   if ((site_mean == nullptr) != (site_cov == nullptr)) return KJX_ERR_INVALID_ARG;
   if ((smooth_mean == nullptr) != (smooth_cov == nullptr)) return KJX_ERR_INVALID_ARG;
   if ((new_site_mean == nullptr) != (new_site_cov == nullptr)) return KJX_ERR_INVALID_ARG;
@@ -487,7 +487,7 @@ template <typename T>
 int run_T(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const T* site_mean, const T* site_cov,
           T* filt_mean, T* filt_cov, T* new_site_mean, T* new_site_cov, T* post_mean, T* post_var, T* nlml,
           void* ws, size_t ws_bytes, uint32_t flags, kjx_stream_t stream) {
-  if (!model_basic_ok(m) || N < 0 || !dt || !y || !nlml) return KJX_ERR_INVALID_ARG;
+  if (!model_run_ok(m) || N < 0 || !dt || !y || !nlml) return KJX_ERR_INVALID_ARG;
   if ((filt_mean == nullptr) != (filt_cov == nullptr)) return KJX_ERR_INVALID_ARG;
   if (!new_site_mean || !new_site_cov) return KJX_ERR_INVALID_ARG;
   if ((site_mean == nullptr) != (site_cov == nullptr)) return KJX_ERR_INVALID_ARG;
@@ -505,7 +505,7 @@ int run_T(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const T* sit
 template <typename T>
 int posterior_T(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const uint8_t* mask, const T* site_mean,
                 const T* site_cov, T* post_mean, T* post_var, T* nlml, void* ws, size_t ws_bytes, kjx_stream_t stream) {
-  if (!model_basic_ok(m) || N < 0 || !dt || !y || !post_mean || !post_var) return KJX_ERR_INVALID_ARG;
+  if (!model_run_ok(m) || N < 0 || !dt || !y || !post_mean || !post_var) return KJX_ERR_INVALID_ARG;
   if ((site_mean == nullptr) != (site_cov == nullptr)) return KJX_ERR_INVALID_ARG;
   if (needs_sequential_filter(m, site_mean != nullptr)) return KJX_ERR_UNSUPPORTED;   // use kjx_filter + kjx_smoother
   cudaStream_t st = (cudaStream_t)stream;
@@ -693,7 +693,7 @@ size_t kjx_filter_summary_doubles(int32_t d) { return (size_t)(d * d + d + d * (
 #if KJX_PART != 32
 int kjx_filter_summary_f64(const kjx_model_t* m, int64_t N, const double* dt, const double* y, const double* site_mean,
                            const double* site_cov, double* summary_out, void* ws, size_t ws_bytes, kjx_stream_t stream) {
-  if (!model_basic_ok(m) || N <= 0 || !dt || !y || !summary_out) return KJX_ERR_INVALID_ARG;
+  if (!model_run_ok(m) || N <= 0 || !dt || !y || !summary_out) return KJX_ERR_INVALID_ARG;
   if ((site_mean == nullptr) != (site_cov == nullptr)) return KJX_ERR_INVALID_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   KJX_SMALL_DISPATCH((shard_summary<double, KJX_BLOCK_MATERN32>(m, N, dt, y, site_mean, site_cov, summary_out, ws, ws_bytes, st)),
@@ -705,7 +705,7 @@ int kjx_filter_summary_f64(const kjx_model_t* m, int64_t N, const double* dt, co
 int kjx_filter_apply_f64(const kjx_model_t* m, int64_t N, const double* dt, const double* y, const double* site_mean,
                          const double* site_cov, const double* state_in, double* nlml_partial, void* ws, size_t ws_bytes,
                          kjx_stream_t stream) {
-  if (!model_basic_ok(m) || N <= 0 || !dt || !y || !state_in || !nlml_partial) return KJX_ERR_INVALID_ARG;
+  if (!model_run_ok(m) || N <= 0 || !dt || !y || !state_in || !nlml_partial) return KJX_ERR_INVALID_ARG;
   if ((site_mean == nullptr) != (site_cov == nullptr)) return KJX_ERR_INVALID_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   KJX_SMALL_DISPATCH((shard_filter<double, KJX_BLOCK_MATERN32>(m, N, dt, y, site_mean, site_cov, state_in, nlml_partial, ws, ws_bytes, st)),
@@ -718,7 +718,7 @@ int kjx_smoother_apply_f64(const kjx_model_t* m, int64_t N, const double* dt, co
                            const double* site_cov, const double* info_in, double* post_mean, double* post_var,
                            double* new_site_mean, double* new_site_cov, void* ws, size_t ws_bytes, uint32_t flags,
                            kjx_stream_t stream) {
-  if (!model_basic_ok(m) || N <= 0 || !dt || !y || !info_in) return KJX_ERR_INVALID_ARG;
+  if (!model_run_ok(m) || N <= 0 || !dt || !y || !info_in) return KJX_ERR_INVALID_ARG;
   if ((site_mean == nullptr) != (site_cov == nullptr)) return KJX_ERR_INVALID_ARG;
   if ((post_mean == nullptr) != (post_var == nullptr)) return KJX_ERR_INVALID_ARG;
   if ((new_site_mean == nullptr) != (new_site_cov == nullptr)) return KJX_ERR_INVALID_ARG;
@@ -731,7 +731,7 @@ int kjx_smoother_apply_f64(const kjx_model_t* m, int64_t N, const double* dt, co
 #if KJX_PART != 32
 int kjx_fold_shard_summaries_host(const kjx_model_t* m, const double* summaries_host, int64_t stride, int32_t world,
                                   int32_t rank, double* state_out_host, double* info_out_host) {
-  if (!model_basic_ok(m) || !summaries_host || !state_out_host || !info_out_host || rank < 0 || world <= rank) return KJX_ERR_INVALID_ARG;
+  if (!model_run_ok(m) || !summaries_host || !state_out_host || !info_out_host || rank < 0 || world <= rank) return KJX_ERR_INVALID_ARG;
   if (stride < (int64_t)kjx_filter_summary_doubles(m->state_dim)) return KJX_ERR_INVALID_ARG;
   if (!small_kind(m)) return KJX_ERR_UNSUPPORTED;
   if (m->state_dim == 2) fold_shards<2>(m->Pinf, summaries_host, stride, world, rank, state_out_host, info_out_host);
@@ -743,7 +743,7 @@ int kjx_fold_shard_summaries_host(const kjx_model_t* m, const double* summaries_
 #if KJX_PART != 32
 int kjx_fold_shard_summaries_f64(const kjx_model_t* m, const double* summaries, int64_t stride, int32_t world,
                                  int32_t rank, double* state_out, double* info_out, kjx_stream_t stream) {
-  if (!model_basic_ok(m) || !summaries || !state_out || !info_out || rank < 0 || world <= rank) return KJX_ERR_INVALID_ARG;
+  if (!model_run_ok(m) || !summaries || !state_out || !info_out || rank < 0 || world <= rank) return KJX_ERR_INVALID_ARG;
   if (stride < (int64_t)kjx_filter_summary_doubles(m->state_dim)) return KJX_ERR_INVALID_ARG;
   if (!small_kind(m)) return KJX_ERR_UNSUPPORTED;
   if (m->state_dim == 2) {
@@ -761,7 +761,7 @@ int kjx_fold_shard_summaries_f64(const kjx_model_t* m, const double* summaries, 
 int kjx_exchange_fold_f64(const kjx_model_t* m, const double* my_summary, double* const* peer_bufs, int64_t stride,
                           int32_t world, int32_t rank, uint64_t* epoch, double* state_out, double* info_out,
                           kjx_stream_t stream) {
-  if (!model_basic_ok(m) || !my_summary || !peer_bufs || !epoch || !state_out || !info_out) return KJX_ERR_INVALID_ARG;
+  if (!model_run_ok(m) || !my_summary || !peer_bufs || !epoch || !state_out || !info_out) return KJX_ERR_INVALID_ARG;
   if (world < 1 || world > 8 || rank < 0 || rank >= world) return KJX_ERR_INVALID_ARG;
   if (stride < (int64_t)kjx_filter_summary_doubles(m->state_dim) || stride > 64) return KJX_ERR_INVALID_ARG;
   if (!small_kind(m)) return KJX_ERR_UNSUPPORTED;
@@ -798,7 +798,7 @@ int kjx_run_host_f64(const kjx_model_t* m, int64_t N, const double* dt_host, con
                      double* new_site_cov_host, double* post_mean_host, double* post_var_host, double* nlml_host,
                      void* dev_scratch, size_t dev_scratch_bytes, uint32_t flags, kjx_stream_t stream) {
   const bool resident = (flags & KJX_FLAG_RESIDENT_SITES) != 0;
-  if (!model_basic_ok(m) || N <= 0 || !dt_host || !y_host || !nlml_host || !dev_scratch) return KJX_ERR_INVALID_ARG;
+  if (!model_run_ok(m) || N <= 0 || !dt_host || !y_host || !nlml_host || !dev_scratch) return KJX_ERR_INVALID_ARG;
   if ((site_mean_host == nullptr) != (site_cov_host == nullptr)) return KJX_ERR_INVALID_ARG;
   if ((new_site_mean_host == nullptr) != (new_site_cov_host == nullptr)) return KJX_ERR_INVALID_ARG;
   if ((post_mean_host == nullptr) != (post_var_host == nullptr)) return KJX_ERR_INVALID_ARG;

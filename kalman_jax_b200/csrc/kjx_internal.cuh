@@ -29,7 +29,7 @@ inline bool model_basic_ok(const kjx_model_t* m) {
   if (m->state_dim <= 0 || m->func_dim <= 0 || m->n_blocks <= 0 || m->n_blocks > KJX_MAX_BLOCKS) return false;
   if (m->n_cub < 1 || m->n_cub > KJX_MAX_CUBATURE) return false;
   if (m->likelihood < KJX_LIK_GAUSSIAN || m->likelihood > KJX_LIK_POISSON_LOGISTIC) return false;
-  if (m->method < KJX_INF_EP || m->method > KJX_INF_VI) return false;
+  if (m->method < KJX_INF_EP || m->method > KJX_INF_MOMENT_MATCH) return false;
   if (!m->Pinf) return false;
   int d = 0;
   for (int b = 0; b < m->n_blocks; ++b) {
@@ -41,6 +41,9 @@ inline bool model_basic_ok(const kjx_model_t* m) {
   }
   return d == m->state_dim;
 }
+
+// filter / smoother entry points: KJX_INF_MOMENT_MATCH is no update rule (kjx_site_update only)
+inline bool model_run_ok(const kjx_model_t* m) { return model_basic_ok(m) && m->method != KJX_INF_MOMENT_MATCH; }
 
 inline SiteModel make_site(const kjx_model_t* m) {
   SiteModel s;

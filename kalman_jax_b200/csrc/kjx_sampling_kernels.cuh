@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(KJX_SAMPLE_THREADS) sample_noise_kernel(const 
       __syncthreads();
       const double r = rinv[j];
       for (int i = j + 1 + threadIdx.x; i < d; i += blockDim.x) Q[i * d + j] *= r;
+      __syncthreads();               // column j is final before any row of the next column reads it (d > 32: several warps)
     }
     __syncthreads();
     double* Wk = W + (size_t)slot * d * S;

@@ -351,6 +351,8 @@ KJX_HDN SiteOut<T> site_update(const SiteModel& sm, T y, T pm, T pv, bool has_pr
                 o.mean, o.var);                                  // :203-209
       return o;
     }
+    case KJX_INF_MOMENT_MATCH:                                   // likelihoods.py:122-185 as called by sde_gp.py:139-142
+      return moment_match<T, Red>(sm, y, pm, pv, T(sm.power));
     default: {                                                   // VI: approximate_inference.py:302-323
       T dE_dm, dE_dv; var_exp_cubature<T, Red>(sm, y, pm, pv, dE_dm, dE_dv);
       if (!has_prev) {

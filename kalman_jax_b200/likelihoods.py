@@ -26,14 +26,19 @@ class Likelihood(object):
         return float(np.reshape(h, -1)[0]) if np.size(h) else 0.0
 
     def moment_match(self, y, m, v, hyp=None, power=1.0, cubature_func=None):
-        """(log Z, site_mean, site_var) per entry of the batch, on the GPU (likelihoods.py:122-192).
+        """(log Z, site_mean, site_var) per entry of the batch, on the GPU (likelihoods.py:122-192): the likelihood is
+        raised to `power` and the site variance scaled by it, exactly as the reference's moment_match does.
         cubature_func=None means 20-point Gauss-Hermite, like likelihoods.py:141-142."""
-        from .approximate_inference import ExpectationPropagation
         from .sde_gp import site_update
-        rule = ExpectationPropagation(power=power)
-        if cubature_func is not None:
-            rule.cubature_func = cubature_func
-        return site_update(self, rule, y, m, v, hyp, None, force_power=power)
+        from .utils import gauss_hermite
+
+        class _MomentMatch(object):          # no update rule: kjx_site_update evaluates moment_match itself
+            kjx_code = _lib.INF_MOMENT_MATCH
+            damping = 1.0
+        rule = _MomentMatch()
+        rule.power = float(power)
+        rule.cubature_func = gauss_hermite if cubature_func is None else cubature_func
+        return site_update(self, rule, y, m, v, hyp, None)
 
 
 class Gaussian(Likelihood):

@@ -1,6 +1,7 @@
 """Host-side helpers mirroring /root/reference/kalmanjax/utils.py (NumPy; nothing here is on the GPU path).
 
-softplus / softplus_inv / softplus_list (utils.py:41-84), input_admin (87-114), test_input_admin (117-197),
+softplus / softplus_inv / softplus_list (utils.py:41-84), input_admin / test_input_admin (own implementation of the
+contract of utils.py:87-197: one stable merge of the training and test time columns),
 gauss_hermite (455-463), symmetric_cubature_third_order / _fifth_order (466-511, one-dimensional rules).
 """
 import numpy as np
@@ -45,80 +46,79 @@ def symmetric_cubature_fifth_order(dim=1):
     return np.array([0., 1.7321, -1.7321]), np.array([0.6667, 0.1667, 0.1667])
 
 
+def _as_columns(x, like=None):
+    """float64 array with the sample axis first and at least one trailing axis ([N] -> [N,1]); None -> NaNs like `like`."""
+    if x is None:
+        return np.full_like(like, np.nan)
+    x = np.asarray(x, dtype=np.float64)
+    return x[:, None] if x.ndim < 2 else x
+
+
+def _time_ordered(t, *others):
+    """Rows of t (and of the arrays that travel with it) by increasing first column."""
+    order = np.argsort(t[:, 0], axis=0)
+    return (t[order],) + tuple(o[order] for o in others)
+
+
+def _steps(t_sorted):
+    """dt[0] = 0, dt[k] = t[k] - t[k-1] (the filter's first step starts AT the first input)."""
+    dt = np.zeros(t_sorted.shape[0])
+    dt[1:] = t_sorted[1:, 0] - t_sorted[:-1, 0]
+    return dt
+
+
 def input_admin(t, y, r):
-    """Order the inputs (utils.py:87-114)."""
-    t, y = np.asarray(t, dtype=np.float64), np.asarray(y, dtype=np.float64)
+    """Training inputs as the filter wants them (the contract of the reference's utils.py:87-114): 2-D float64 arrays
+    ordered by time, missing spatial inputs as NaN columns, and the step sizes."""
+    t, y = _as_columns(t), _as_columns(y)
     assert t.shape[0] == y.shape[0]
-    if t.ndim < 2:
-        t = np.expand_dims(t, 1)
-    if y.ndim < 2:
-        y = np.expand_dims(y, 1)
-    if r is None:
-        r = np.nan * t
-    r = np.asarray(r, dtype=np.float64)
-    if r.ndim < 2:
-        r = np.expand_dims(r, 1)
-    ind = np.argsort(t[:, 0], axis=0)
-    t_train, y_train, r_train = t[ind, ...], y[ind, ...], r[ind, ...]
-    dt_train = np.concatenate([np.array([0.0]), np.diff(t_train[:, 0])])
-    return t_train, y_train, r_train, dt_train
+    t, y, r = _time_ordered(t, y, _as_columns(r, like=t))
+    return t, y, r, _steps(t)
 
 
 def test_input_admin(t, y, r, t_test, y_test, r_test):
-    """Merge + sort train and test inputs, index them, build the mask (utils.py:117-197)."""
-    t, y = np.asarray(t, dtype=np.float64), np.asarray(y, dtype=np.float64)
-    assert t.shape[0] == y.shape[0]
-    if t.ndim < 2:
-        t = np.expand_dims(t, 1)
-    if y.ndim < 2:
-        y = np.expand_dims(y, 1)
-    if r is None:
-        r = np.nan * t
-    r = np.asarray(r, dtype=np.float64)
-    if r.ndim < 2:
-        r = np.expand_dims(r, 1)
-    ind = np.argsort(t[:, 0], axis=0)
-    t_train, y_train, r_train = t[ind, ...], y[ind, ...], r[ind, ...]
-    if t_test is None:
-        t_test = np.empty((1,) + t_train.shape[1:]) * np.nan
-        r_test = np.empty((1,) + t_train.shape[1:]) * np.nan
+    """Training and test inputs on ONE time grid (the contract of the reference's utils.py:117-197).
+
+    Returns (t_all, y_all, r_all, r_test, dt_all, train_id, test_id, mask): the merged grid ordered by time, the rows the
+    (time-ordered) training / test points occupy on it, y_all holding the training targets (and the test targets when
+    given, for the NLPD) with NaN elsewhere, and mask = True on the rows that are NOT training data (predict-only steps).
+    """
+    t_tr, y_tr, r_tr, _ = input_admin(t, y, r)
+    n_tr, n_tcol, n_rcol = t_tr.shape[0], t_tr.shape[1], r_tr.shape[1]
+    if t_test is None:                                          # nothing to predict: the grid is the training grid
+        t_te = np.empty((0, n_tcol))
+        r_test = np.full((1, n_tcol), np.nan)
+        r_te = np.empty((0, n_rcol))
+        y_te = None
     else:
-        t_test = np.asarray(t_test, dtype=np.float64)
-        if t_test.ndim < 2:
-            t_test = np.expand_dims(t_test, 1)
-        test_sort_ind = np.argsort(t_test[:, 0], axis=0)
-        t_test = t_test[test_sort_ind, ...]
-        if y_test is not None:
-            y_test = np.asarray(y_test, dtype=np.float64)[test_sort_ind, ...].reshape((-1,) + y.shape[1:])
-        if r_test is not None:
-            r_test = np.asarray(r_test, dtype=np.float64)
-            if r_test.ndim < 2:
-                r_test = np.expand_dims(r_test, 1)
-            r_test = r_test[test_sort_ind, ...]
+        t_te = _as_columns(t_test)
+        r_te = _as_columns(r_test, like=t_te)
+        if y_test is None:
+            t_te, r_te = _time_ordered(t_te, r_te)
+            y_te = None
         else:
-            r_test = np.nan * t_test
-    if not (t_test.shape[1] == t_train.shape[1]):
-        t_test = np.concatenate([t_test[:, 0][:, None],
-                                 np.nan * np.empty([t_test.shape[0], t_train.shape[1] - 1])], axis=1)
-    t_train_test = np.concatenate([t_train, t_test])
-    keep_ind = ~np.isnan(t_train_test[:, 0])
-    t_train_test = t_train_test[keep_ind, ...]
-    if r_test.shape[1] != r_train.shape[1]:
-        r_test_nan = np.nan * np.zeros([r_test.shape[0], r_train.shape[1]])
-    else:
-        r_test_nan = r_test
-    r_train_test = np.concatenate([r_train, r_test_nan])[keep_ind, ...]
-    t_ind = np.argsort(t_train_test[:, 0])
-    t_all, r_all = t_train_test[t_ind], r_train_test[t_ind]
-    reverse_ind = np.argsort(t_ind)
-    n_train = t_train.shape[0]
-    train_id, test_id = reverse_ind[:n_train], reverse_ind[n_train:]
-    y_all = np.nan * np.zeros([t_all.shape[0], y_train.shape[1]])
-    y_all[train_id] = y_train
-    if y_test is not None:
-        y_all[test_id] = y_test
-    mask = np.ones_like(y_all, dtype=bool)
+            t_te, r_te, y_te = _time_ordered(t_te, r_te, np.asarray(y_test, dtype=np.float64))
+            y_te = y_te.reshape((-1,) + y_tr.shape[1:])
+        r_test = r_te
+        if t_te.shape[1] != n_tcol:                             # only the time column of the test inputs is used
+            t_te = np.concatenate([t_te[:, :1], np.full((t_te.shape[0], n_tcol - 1), np.nan)], axis=1)
+        if r_te.shape[1] != n_rcol:                             # different spatial dimensionality: handled by the caller
+            r_te = np.full((r_te.shape[0], n_rcol), np.nan)
+        known = ~np.isnan(t_te[:, 0])                           # test rows without a time are dropped
+        t_te, r_te = t_te[known], r_te[known]
+        if y_te is not None:
+            y_te = y_te[known]
+    # one stable ordering of the stacked time columns; rank[i] = row of stacked point i on the merged grid
+    t_stack, r_stack = np.concatenate([t_tr, t_te]), np.concatenate([r_tr, r_te])
+    order = np.argsort(t_stack[:, 0], kind="stable")
+    rank = np.empty(order.size, dtype=np.int64)
+    rank[order] = np.arange(order.size)
+    train_id, test_id = rank[:n_tr], rank[n_tr:]
+    t_all, r_all = t_stack[order], r_stack[order]
+    y_all = np.full((order.size, y_tr.shape[1]), np.nan)
+    y_all[train_id] = y_tr
+    if y_te is not None:
+        y_all[test_id] = y_te
+    mask = np.ones(y_all.shape, dtype=bool)
     mask[train_id] = False
-    dt_all = np.concatenate([np.array([0.0]), np.diff(t_all[:, 0])])
-    return (t_all, y_all, r_all, r_test, dt_all, np.array(train_id, dtype=np.int64),
-            np.array(test_id, dtype=np.int64), mask)
+    return t_all, y_all, r_all, r_test, _steps(t_all), train_id, test_id, mask

@@ -132,6 +132,78 @@ def test_scan_equals_sequential_kernel_at_2pow20():
     assert np.isfinite(out[False][1]).all()
 
 
+def _c_oracle():
+    """oracle/seq_filter.c (plain-C restatement of the reference loops; pinned by tests/test_oracle_c.py)."""
+    import ctypes as C
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so, src = os.path.join(root, "oracle", "libkjx_oracle.so"), os.path.join(root, "oracle", "seq_filter.c")
+    if not os.path.exists(so) or os.path.getmtime(src) > os.path.getmtime(so):
+        subprocess.check_call(["gcc", "-O3", "-shared", "-fPIC", "-o", so, src, "-lm"])
+    lib = C.CDLL(so)
+    lib.kjx_oracle_run.restype = C.c_double
+
+    def run(kind, N, dt, y, sm, sv, power, damping, lik_var=0.5):
+        d = 2 if kind == 1 else 3
+        out = dict(fm=np.empty([N, d]), fP=np.empty([N, d, d]), nsm=np.empty(N), nsv=np.empty(N), pm=np.empty(N), pv=np.empty(N))
+        dp = lambda a: None if a is None else np.ascontiguousarray(a).ctypes.data_as(C.c_void_p)  # noqa: E731
+        out["nlml"] = lib.kjx_oracle_run(kind, C.c_double(1.0), C.c_double(5.0), C.c_double(lik_var), C.c_double(power),
+                                         C.c_double(damping), C.c_long(N), dp(dt), dp(y), dp(sm), dp(sv), dp(out["fm"]),
+                                         dp(out["fP"]), dp(out["nsm"]), dp(out["nsv"]), dp(out["pm"]), dp(out["pv"]))
+        return out
+    return run
+
+
+@pytest.mark.parametrize("prior_name,log2n", [("Matern52", 22), ("Matern32", 21)])
+def test_multi_level_scan_vs_c_oracle_at_2pow22(prior_name, log2n):
+    """A series long enough for all three scan levels (65 536 thread chunks -> 1024 segments -> 16 -> 1) against the
+    plain-C SEQUENTIAL oracle: nlml, dense filtered moments, smoothed marginals and the damped new sites at 1e-9.
+    Arbitrary (not fixed-point) sites and damping 0.6 so every output is non-trivial."""
+    kjx = _kjx()
+    N = 1 << log2n
+    t, y = synth(N)
+    rng = np.random.default_rng(7)
+    sm = y + 0.1 * rng.standard_normal(N)
+    sv = rng.uniform(0.3, 0.8, N)
+    model = kjx.SDEGP(getattr(kjx.priors, prior_name)(1.0, 5.0), kjx.likelihoods.Gaussian(0.5), t, y,
+                      approx_inf=kjx.approximate_inference.EP(power=0.5, damping=0.6))
+    want = _c_oracle()(1 if prior_name == "Matern32" else 2, N, model.dt, y, sm, sv, 0.5, 0.6)
+    params = model._params(None)
+    sites = (sm.reshape(N, 1, 1), sv.reshape(N, 1, 1))
+    # (i) the two stand-alone calls with dense filtered moments in between
+    nlml, (fm, fP, _) = model.kalman_filter(model.y, model.dt, params, True, None, sites, model.r)
+    assert abs(float(nlml) - want["nlml"]) <= TOL64 * abs(want["nlml"])
+    assert rel_err(_np(fm)[:, :, 0], want["fm"]) < TOL64 and rel_err(_np(fP), want["fP"]) < TOL64
+    s_new, pm, pv = model.rauch_tung_striebel_smoother(params, fm, fP, model.dt, True, False, model.y, sites, model.r)
+    assert rel_err(_np(pm).reshape(-1), want["pm"]) < TOL64 and rel_err(_np(pv).reshape(-1), want["pv"]) < TOL64
+    assert rel_err(_np(s_new[0]).reshape(-1), want["nsm"]) < TOL64 and rel_err(_np(s_new[1]).reshape(-1), want["nsv"]) < TOL64
+    del fm, fP, s_new, pm, pv
+    # (ii) the fused iteration the benchmark times (kjx_run)
+    model.sites.site_params = sites
+    got, _ = model.run(compute_grad=False, store_posterior=True)
+    assert abs(got - want["nlml"]) <= TOL64 * abs(want["nlml"])
+    assert rel_err(_np(model.posterior[0]).reshape(-1), want["pm"]) < TOL64
+    assert rel_err(_np(model.posterior[1]).reshape(-1), want["pv"]) < TOL64
+    assert rel_err(_np(model.sites.site_params[0]).reshape(-1), want["nsm"]) < TOL64
+    assert rel_err(_np(model.sites.site_params[1]).reshape(-1), want["nsv"]) < TOL64
+
+
+def test_fp32_fused_iteration_vs_fp64_c_oracle_at_2pow22():
+    """fp32 compute path at a multi-level-scan size against the fp64 sequential oracle: 1e-4 (north_star)."""
+    kjx = _kjx()
+    N = 1 << 22
+    t, y = synth(N)
+    model = kjx.SDEGP(kjx.priors.Matern52(1.0, 5.0), kjx.likelihoods.Gaussian(0.5), t, y,
+                      approx_inf=kjx.approximate_inference.EP(power=0.5), dtype=torch.float32)
+    want = _c_oracle()(2, N, model.dt, y, y.copy(), np.full(N, 0.5), 0.5, 1.0)
+    model.sites.site_params = (y.reshape(N, 1, 1).copy(), np.full([N, 1, 1], 0.5))
+    got, _ = model.run(compute_grad=False, store_posterior=True)
+    assert abs(got - want["nlml"]) <= TOL32 * abs(want["nlml"])
+    assert rel_err(_np(model.posterior[0]).reshape(-1), want["pm"]) < TOL32
+    assert rel_err(_np(model.posterior[1]).reshape(-1), want["pv"]) < TOL32
+
+
 def test_masked_prediction_path_vs_oracle():
     """predict(): merged train/test grid, masked steps are predict-only (sde_gp.py:286, 297-300)."""
     kjx = _kjx()
@@ -221,6 +293,27 @@ def test_site_update_kernel_vs_oracle(lik, meth, has_prev):
         err = np.abs(a[ok] - b[ok]) / np.maximum(np.abs(b[ok]), 1e-3)
         assert np.mean(err > 5e-9) < 2e-3, float(np.mean(err > 5e-9))
         assert err.max() < 1e-5, float(err.max())
+
+
+@pytest.mark.parametrize("lik_name,power", [("Poisson", 0.5), ("Probit", 0.3), ("Logit", 1.0), ("Gaussian", 0.7)])
+def test_likelihood_moment_match_honours_power(lik_name, power):
+    """Likelihood.moment_match(y, m, v, hyp, power) (likelihoods.py:122-185): the likelihood raised to `power`."""
+    from oracle.cubature import gauss_hermite
+    kjx = _kjx()
+    rng = np.random.default_rng(11)
+    n = 500
+    m, v = rng.normal(0, 1, n), rng.uniform(0.05, 1.5, n)
+    kw = dict(variance=0.5) if lik_name == "Gaussian" else {}
+    y = {"Poisson": rng.poisson(1.5, n).astype(float), "Gaussian": rng.normal(0, 1, n)}.get(lik_name, np.sign(rng.normal(0, 1, n)))
+    lik, ref = getattr(kjx.likelihoods, lik_name)(**kw), getattr(oracle.likelihoods, lik_name)(**kw)
+    lZ, sm, sv = lik.moment_match(y, m, v, np.array(0.5) if lik_name == "Gaussian" else None, power)
+    cub = gauss_hermite(20)
+    want = np.stack([np.asarray(a, dtype=float).reshape(-1) for a in ref.moment_match(y, m, v, power, cub)], axis=1)
+    assert rel_err(_np(lZ), want[:, 0]) < TOL64
+    ok = np.isfinite(want[:, 1]) & np.isfinite(want[:, 2])
+    assert ok.mean() > 0.9
+    assert np.max(np.abs(_np(sm)[ok] - want[ok, 1]) / np.maximum(np.abs(want[ok, 1]), 1.0)) < 1e-7
+    assert np.max(np.abs(_np(sv)[ok] - want[ok, 2]) / np.maximum(np.abs(want[ok, 2]), 1.0)) < 1e-7
 
 
 # ---------------------------------------------------------------------------------------------------
