@@ -203,7 +203,7 @@ def make_collectives(world, rank, dev, exchange="peer"):
         return nl_buf
 
     peer = None
-    if exchange == "peer":
+    if exchange != "nccl":
         try:
             from kalman_jax_b200.sharded import PeerExchange
             peer = PeerExchange(world, rank, dev)
@@ -227,8 +227,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the full-size comparison with the C oracle")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
-                    help="multi-GPU summary exchange: fused peer-memory kernel (default) or NCCL all-gather")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "peer-separate", "nccl"],
+                    help="summary exchange: inside the kernels over peer memory (default), the separate exchange+fold "
+                         "kernel over peer memory, or an NCCL all-gather")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying CUDA graphs")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -246,12 +247,21 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     gather = reduce_nlml = peer = None
-    exchange = "none (1 GPU)"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         gather, reduce_nlml, peer = make_collectives(world, rank, dev, args.exchange)
-        exchange = ("fused peer-memory exchange+fold kernel (symmetric memory over NVLink)" if peer is not None
-                    else "NCCL all_gather_into_tensor + fold kernel")
+    elif args.exchange != "nccl":
+        from kalman_jax_b200.sharded import PeerExchange
+        peer = PeerExchange(1, 0, dev)                       # one shard: an ordinary device buffer, same kernels
+    linked = peer is not None and args.exchange == "peer"
+    if linked:
+        exchange = ("inside the scan/filter/smoother kernels over symmetric memory (NVLink peer stores + epoch flags), "
+                    "nlml partials included; no collective call" if world > 1 else "none (1 shard; same kernels, local buffer)")
+        reduce_nlml = None
+    elif peer is not None:
+        exchange = "separate fused exchange+fold kernel over symmetric memory; nlml by NCCL all-reduce"
+    else:
+        exchange = "NCCL all_gather_into_tensor + fold kernel; nlml by NCCL all-reduce"
 
     N = 1 << args.log2n
     dt, y = synth(N)
@@ -259,7 +269,7 @@ def main():
     n_local = hi - lo
     prior, lik, rule = kjx.priors.Matern52(1.0, 5.0), kjx.likelihoods.Gaussian(0.5), kjx.approximate_inference.EP(power=0.5)
     it = ShardedIteration(prior, lik, rule, sh_dt, sh_y, dt_next, rank, world, dev, gather,
-                          site_mean=sh_y.copy(), site_var=np.full(n_local, 0.5), peer=peer)
+                          site_mean=sh_y.copy(), site_var=np.full(n_local, 0.5), peer=peer, linked=linked)
 
     def barrier():
         torch.cuda.synchronize()
@@ -284,12 +294,23 @@ def main():
         it.iteration(update_sites=False, reduce_nlml=reduce_nlml)
     barrier()
     sampler.rows = sampler.rows[-2:]
-    # per-phase CUDA-event times (eager launches with events between the library calls; untimed for `value`)
+    # per-phase CUDA-event times (untimed for `value`): eager launches with events between the SEPARATE library calls
+    # (fold + scans | exchange + fold of the shard elements | filter | smoother) — the same fold / filter / smoother
+    # kernels the linked iteration launches, so the split explains the timed number
     n_ev = max(3, min(args.steps, 20))
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(n_ev)]
-    for k in range(n_ev):
-        it.iteration(events=ev[k], reduce_nlml=reduce_nlml)
+    if linked:
+        gather_ph, reduce_ph, _ = make_collectives(world, rank, dev, "nccl") if world > 1 else (None, None, None)
+        it_ph = ShardedIteration(prior, lik, rule, sh_dt, sh_y, dt_next, rank, world, dev, gather_ph,
+                                 site_mean=sh_y.copy(), site_var=np.full(n_local, 0.5), peer=None, linked=False)
+    else:
+        it_ph, reduce_ph = it, reduce_nlml
+    for k in range(3 + n_ev):
+        it_ph.iteration(events=ev[max(k - 3, 0)], reduce_nlml=reduce_ph)
     barrier()
+    if linked:
+        del it_ph
+        torch.cuda.empty_cache()
     graphed = None
     if not args.no_graph:
         from kalman_jax_b200.sharded import GraphedIteration

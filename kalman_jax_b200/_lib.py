@@ -52,6 +52,7 @@ SYMBOLS = [
     "kjx_filter_summary_f64", "kjx_filter_apply_f64", "kjx_smoother_apply_f64",
     "kjx_fold_shard_summaries_host", "kjx_fold_shard_summaries_f64", "kjx_exchange_fold_f64", "kjx_run_host_f64", "kjx_run_host_scratch_bytes",
     "kjx_prior_sample_workspace_bytes", "kjx_prior_sample_f64",
+    "kjx_shard_link_doubles", "kjx_sharded_iteration_f64",
 ]
 
 
@@ -65,6 +66,7 @@ def lib():
         L = C.CDLL(LIB_PATH)
         L.kjx_status_string.restype = C.c_char_p
         L.kjx_filter_summary_doubles.restype = C.c_size_t
+        L.kjx_shard_link_doubles.restype = C.c_size_t
         for name in SYMBOLS:
             getattr(L, name)  # AttributeError if the symbol is missing
         _lib = L

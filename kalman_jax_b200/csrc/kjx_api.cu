@@ -27,24 +27,55 @@ int small_kind(const kjx_model_t* m) {
   return kind;
 }
 
+// number of SMs of the current device (queried once per device; 148 on a B200)
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    cached[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
+  }
+  return cached[dev];
+}
+// tuning knobs, read from the environment ONCE per process (0 = not set): KJX_CHUNK steps per thread chunk,
+// KJX_THREADS threads per block of the fold / filter / smoother kernels
+int env_knob(const char* name) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : 0;
+}
+int knob_chunk() { static const int v = env_knob("KJX_CHUNK"); return v; }
+int knob_threads() { static const int v = env_knob("KJX_THREADS"); return v; }
+
 // steps per thread chunk: long chunks amortise the O(d^3) scan combines, short ones keep every SM
 // busy on short series.  A multiple of 4 so a chunk starts on a 32-byte boundary of every array.
 int pick_chunk(int64_t N) {
-  if (const char* e = getenv("KJX_CHUNK")) { const int v = atoi(e); if (v >= 4 && v % 4 == 0) return v; }   // tuning knob
+  // the fused scan hierarchy has three levels of at most 128: at most 128^3 chunks
+  const int64_t max_chunks = (int64_t)KJX_SEG_MAX * KJX_SEG_MAX * KJX_SEG_MAX;
   // Long series: 64 steps per thread amortise the O(d^3) scan combines (several waves of blocks anyway).
   // Short series / small shards: the kernels are one wave of latency-bound threads, so the time is (steps per
   // thread) x (latency of a step): spread the series over 95 % of the resident thread slots (3 blocks of 128 per SM).
-  const int64_t slots = (int64_t)(148 * 3 * KJX_BLOCK * 0.95);
+  const int64_t slots = (int64_t)(sm_count() * 3 * KJX_BLOCK * 0.95);
   int64_t L = (N + slots - 1) / slots;
   L = std::max<int64_t>(4, std::min<int64_t>(64, L));
-  // the fused scan hierarchy has three levels of at most 128: at most 128^3 chunks
-  const int64_t max_chunks = (int64_t)KJX_SEG_MAX * KJX_SEG_MAX * KJX_SEG_MAX;
-  if ((N + L - 1) / L > max_chunks) L = (N + max_chunks - 1) / max_chunks;
+  const int v = knob_chunk();
+  if (v >= 4 && v % 4 == 0) L = v;
+  if ((N + L - 1) / L > max_chunks) L = (N + max_chunks - 1) / max_chunks;      // also bounds the knob
   return (int)round_up((size_t)L, 4);
+}
+// threads per block of the fold / filter / smoother kernels: 128 when there are several waves of blocks; for a single
+// wave smaller blocks spread the chunks more evenly over the SMs (the kernel ends with its fullest SM)
+int pick_threads(int64_t nchunks) {
+  const int v = knob_threads();
+  if (v == 32 || v == 64 || v == 128) return v;
+  const int64_t one_wave = (int64_t)sm_count() * 3 * KJX_BLOCK;
+  (void)one_wave;
+  return KJX_BLOCK;
 }
 
 template <typename T, int D> struct SmallLayout {
   int L; int64_t nchunks, nblocks; size_t cstride, bstride;
+  int threads; int64_t fblocks;     // fused kernels: threads per block (32 / 64 / 128) and blocks
   size_t off_ftp, off_fbt, off_fbp, off_fst, off_sts, off_sbt, off_sbs, off_sst, off_nl, off_fin, off_sin;
   size_t off_info, off_xf, off_lvl[3][3], lvl_stride[3], total;
   int64_t lvl_n[3];
@@ -54,13 +85,15 @@ template <typename T, int D> struct SmallLayout {
     L = pick_chunk(N);
     nchunks = std::max<int64_t>(1, (N + L - 1) / L);
     nblocks = (nchunks + KJX_BLOCK - 1) / KJX_BLOCK;
+    threads = pick_threads(nchunks);
+    fblocks = (nchunks + threads - 1) / threads;
     cstride = round_up((size_t)nchunks, 128);
     bstride = round_up((size_t)nblocks, 32);
     size_t o = 0;
     auto take = [&](size_t n) { size_t r = o; o += round_up(n * sizeof(T), 256); return r; };
     off_ftp = take(FNS * cstride); off_fbt = take(FNS * bstride); off_fbp = take(FNS * bstride); off_fst = take(FNS);
     off_sts = take(SNS * cstride); off_sbt = take(SNS * bstride); off_sbs = take(SNS * bstride); off_sst = take(SNS);
-    off_nl = take(bstride); off_fin = take(D + D * D); off_sin = take(D + D * D);
+    off_nl = take(round_up((size_t)((nchunks + 31) / 32), 32)); off_fin = take(D + D * D); off_sin = take(D + D * D);
     off_info = take(D + D * D);
     // three scan levels of the fused path: elements, exclusive prefix, exclusive suffix (strides = whole segments)
     // segments of 64 while three levels of 64 hold every chunk (shorter dependent chains), else 128
@@ -157,16 +190,17 @@ struct Fused {
     fa.a.N = N; fa.a.dt = dt; fa.a.y = y; fa.a.site_mean = site_mean; fa.a.site_var = site_var;
     fa.a.gaussian_init = (site_mean == nullptr) ? 1 : 0;
     fa.a.is_last_shard = 1;
-    nthread_blocks = fa.a.nblocks;
+    nthread_blocks = lay.fblocks;
     ngroups = 0;
     const size_t al = sizeof(T) * 4;
     fa.vec_ok = (lay.L % 4 == 0) && aligned_to(dt, al) && aligned_to(y, al) && aligned_to(site_mean, al) && aligned_to(site_var, al);
   }
-  unsigned grid() const { return (unsigned)((fa.a.nchunks + KJX_BLOCK - 1) / KJX_BLOCK); }
+  unsigned grid() const { return (unsigned)lay.fblocks; }
+  unsigned threads() const { return (unsigned)lay.threads; }
   // total_out: where the top-level scan writes the shard's element (default: the workspace slot)
   void reduce(cudaStream_t st, T* total_out = nullptr) {
-    if (fa.vec_ok) fused_fold_kernel<T, KIND, true><<<grid(), KJX_BLOCK, 0, st>>>(fa);
-    else fused_fold_kernel<T, KIND, false><<<grid(), KJX_BLOCK, 0, st>>>(fa);
+    if (fa.vec_ok) fused_fold_kernel<T, KIND, true><<<grid(), threads(), 0, st>>>(fa);
+    else fused_fold_kernel<T, KIND, false><<<grid(), threads(), 0, st>>>(fa);
     // three levels of segment scans; the top level's single total is the shard's element
     const size_t smem = sizeof(T) * FSum<T, D>::NS * fa.seg;
     for (int l = 0; l < 3; ++l) {
@@ -177,20 +211,53 @@ struct Fused {
       else fused_segscan_kernel<T, D, 128><<<nseg, 64, smem, st>>>(fa.lvl[l], tot, tstride);
     }
   }
+  // sharded iteration: fold, level-0 scan, then levels 1 + 2 and the publication of the shard's element in one launch
+  void reduce_linked(cudaStream_t st) {
+    if (fa.vec_ok) fused_fold_kernel<T, KIND, true><<<grid(), threads(), 0, st>>>(fa);
+    else fused_fold_kernel<T, KIND, false><<<grid(), threads(), 0, st>>>(fa);
+    const size_t smem = sizeof(T) * FSum<T, D>::NS * fa.seg;
+    const unsigned nseg0 = (unsigned)((fa.lvl[0].n + fa.seg - 1) / fa.seg), nseg1 = (unsigned)((fa.lvl[1].n + fa.seg - 1) / fa.seg);
+    if (fa.seg == 64) {
+      fused_segscan_kernel<T, D, 64><<<nseg0, 64, smem, st>>>(fa.lvl[0], fa.lvl[1].items, fa.lvl[1].stride);
+      fused_segscan_top_kernel<T, D, 64, true><<<nseg1, 64, smem, st>>>(fa.lvl[1], fa.lvl[2], fa.a.f_shard_total, fa.link.ctrl + 1, fa.link);
+    } else {
+      fused_segscan_kernel<T, D, 128><<<nseg0, 64, smem, st>>>(fa.lvl[0], fa.lvl[1].items, fa.lvl[1].stride);
+      fused_segscan_top_kernel<T, D, 128, true><<<nseg1, 64, smem, st>>>(fa.lvl[1], fa.lvl[2], fa.a.f_shard_total, fa.link.ctrl + 1, fa.link);
+    }
+  }
+  void filter_linked(cudaStream_t st) {
+    const bool fast = gauss_ep(m);
+    fa.store_xf = 1;
+    if (fast && fa.vec_ok) fused_filter_kernel<T, KIND, true, true, true, true><<<grid(), threads(), 0, st>>>(fa);
+    else if (fast) fused_filter_kernel<T, KIND, true, false, true, true><<<grid(), threads(), 0, st>>>(fa);
+    else if (fa.vec_ok) fused_filter_kernel<T, KIND, false, true, true, true><<<grid(), threads(), 0, st>>>(fa);
+    else fused_filter_kernel<T, KIND, false, false, true, true><<<grid(), threads(), 0, st>>>(fa);
+  }
+  void smoother_linked(T* post_mean, T* post_var, T* new_site_mean, T* new_site_var, bool update, cudaStream_t st) {
+    fa.a.smooth_mean = post_mean; fa.a.smooth_cov = post_var; fa.a.new_site_mean = new_site_mean; fa.a.new_site_var = new_site_var;
+    fa.a.update_sites = (update && new_site_mean != nullptr) ? 1 : 0;
+    const size_t al = sizeof(T) * 4;
+    const bool vec = fa.vec_ok && aligned_to(post_mean, al) && aligned_to(post_var, al) && aligned_to(new_site_mean, al) && aligned_to(new_site_var, al);
+    const bool fast = gauss_ep(m);
+    if (fast && vec) fused_smoother_kernel<T, KIND, true, true, true><<<grid(), threads(), 0, st>>>(fa);
+    else if (fast) fused_smoother_kernel<T, KIND, true, false, true><<<grid(), threads(), 0, st>>>(fa);
+    else if (vec) fused_smoother_kernel<T, KIND, false, true, true><<<grid(), threads(), 0, st>>>(fa);
+    else fused_smoother_kernel<T, KIND, false, false, true><<<grid(), threads(), 0, st>>>(fa);
+  }
   // plain: the run() iteration; otherwise mask / energy-only / site write-back are honoured
   void filter(cudaStream_t st, bool plain = true) {
     const bool fast = gauss_ep(m);
     if (plain) {
       fa.store_xf = 1;
-      if (fast && fa.vec_ok) fused_filter_kernel<T, KIND, true, true, true><<<grid(), KJX_BLOCK, 0, st>>>(fa);
-      else if (fast) fused_filter_kernel<T, KIND, true, false, true><<<grid(), KJX_BLOCK, 0, st>>>(fa);
-      else if (fa.vec_ok) fused_filter_kernel<T, KIND, false, true, true><<<grid(), KJX_BLOCK, 0, st>>>(fa);
-      else fused_filter_kernel<T, KIND, false, false, true><<<grid(), KJX_BLOCK, 0, st>>>(fa);
+      if (fast && fa.vec_ok) fused_filter_kernel<T, KIND, true, true, true><<<grid(), threads(), 0, st>>>(fa);
+      else if (fast) fused_filter_kernel<T, KIND, true, false, true><<<grid(), threads(), 0, st>>>(fa);
+      else if (fa.vec_ok) fused_filter_kernel<T, KIND, false, true, true><<<grid(), threads(), 0, st>>>(fa);
+      else fused_filter_kernel<T, KIND, false, false, true><<<grid(), threads(), 0, st>>>(fa);
     } else {
-      if (fast && fa.vec_ok) fused_filter_kernel<T, KIND, true, true, false><<<grid(), KJX_BLOCK, 0, st>>>(fa);
-      else if (fast) fused_filter_kernel<T, KIND, true, false, false><<<grid(), KJX_BLOCK, 0, st>>>(fa);
-      else if (fa.vec_ok) fused_filter_kernel<T, KIND, false, true, false><<<grid(), KJX_BLOCK, 0, st>>>(fa);
-      else fused_filter_kernel<T, KIND, false, false, false><<<grid(), KJX_BLOCK, 0, st>>>(fa);
+      if (fast && fa.vec_ok) fused_filter_kernel<T, KIND, true, true, false><<<grid(), threads(), 0, st>>>(fa);
+      else if (fast) fused_filter_kernel<T, KIND, true, false, false><<<grid(), threads(), 0, st>>>(fa);
+      else if (fa.vec_ok) fused_filter_kernel<T, KIND, false, true, false><<<grid(), threads(), 0, st>>>(fa);
+      else fused_filter_kernel<T, KIND, false, false, false><<<grid(), threads(), 0, st>>>(fa);
     }
   }
   void smoother(T* post_mean, T* post_var, T* new_site_mean, T* new_site_var, bool update, cudaStream_t st) {
@@ -199,10 +266,10 @@ struct Fused {
     const size_t al = sizeof(T) * 4;
     const bool vec = fa.vec_ok && aligned_to(post_mean, al) && aligned_to(post_var, al) && aligned_to(new_site_mean, al) && aligned_to(new_site_var, al);
     const bool fast = gauss_ep(m);
-    if (fast && vec) fused_smoother_kernel<T, KIND, true, true><<<grid(), KJX_BLOCK, 0, st>>>(fa);
-    else if (fast) fused_smoother_kernel<T, KIND, true, false><<<grid(), KJX_BLOCK, 0, st>>>(fa);
-    else if (vec) fused_smoother_kernel<T, KIND, false, true><<<grid(), KJX_BLOCK, 0, st>>>(fa);
-    else fused_smoother_kernel<T, KIND, false, false><<<grid(), KJX_BLOCK, 0, st>>>(fa);
+    if (fast && vec) fused_smoother_kernel<T, KIND, true, true><<<grid(), threads(), 0, st>>>(fa);
+    else if (fast) fused_smoother_kernel<T, KIND, true, false><<<grid(), threads(), 0, st>>>(fa);
+    else if (vec) fused_smoother_kernel<T, KIND, false, true><<<grid(), threads(), 0, st>>>(fa);
+    else fused_smoother_kernel<T, KIND, false, false><<<grid(), threads(), 0, st>>>(fa);
   }
 };
 
@@ -382,6 +449,23 @@ int shard_smoother(const kjx_model_t* m, int64_t N, const T* dt, const T* y, con
   Fused<T, KIND> f(m, N, dt, y, site_mean, site_var, ws);
   f.fa.s_info_in = info_in;               // read in place
   f.smoother(post_mean, post_var, new_site_mean, new_site_var, !(flags & KJX_FLAG_NO_SITE_UPDATE), st);
+  KJX_CUDA_CHECK(cudaGetLastError());
+  return KJX_OK;
+}
+
+// one whole iteration of a shard with the exchange inside the kernels (kjx_sharded_iteration_f64)
+template <int KIND>
+int shard_iteration(const kjx_model_t* m, int64_t N, const double* dt, const double* y, const double* site_mean, const double* site_var,
+                    const ShardLink& link, double* post_mean, double* post_var, double* new_site_mean, double* new_site_var,
+                    void* ws, size_t ws_bytes, uint32_t flags, cudaStream_t st) {
+  constexpr int D = BlockDim<KIND>::D;
+  if (ws_bytes < SmallLayout<double, D>(N).total || !ws) return KJX_ERR_WORKSPACE;
+  if (needs_sequential_filter(m, site_mean != nullptr)) return KJX_ERR_UNSUPPORTED;
+  Fused<double, KIND> f(m, N, dt, y, site_mean, site_var, ws);
+  f.fa.link = link;
+  f.reduce_linked(st);
+  f.filter_linked(st);
+  f.smoother_linked(post_mean, post_var, new_site_mean, new_site_var, !(flags & KJX_FLAG_NO_SITE_UPDATE), st);
   KJX_CUDA_CHECK(cudaGetLastError());
   return KJX_OK;
 }
@@ -774,6 +858,29 @@ int kjx_exchange_fold_f64(const kjx_model_t* m, const double* my_summary, double
     exchange_fold_kernel<3><<<1, 32, 0, st>>>(p, my_summary, peer_bufs, stride, world, rank, (unsigned long long*)epoch, state_out, info_out);
   }
   return cudaGetLastError() == cudaSuccess ? KJX_OK : KJX_ERR_CUDA;
+}
+#endif
+
+#if KJX_PART != 32
+size_t kjx_shard_link_doubles(int32_t world, int64_t stride) {
+  return (world < 1 || stride < 1) ? 0 : (size_t)2 * world * (size_t)stride + (size_t)6 * world;
+}
+int kjx_sharded_iteration_f64(const kjx_model_t* m, int64_t N, const double* dt, const double* y, const double* site_mean,
+                              const double* site_cov, double* const* peer_bufs, int64_t stride, int32_t world, int32_t rank,
+                              uint64_t* ctrl, double* post_mean, double* post_var, double* new_site_mean, double* new_site_cov,
+                              double* nlml, void* ws, size_t ws_bytes, uint32_t flags, kjx_stream_t stream) {
+  if (!model_run_ok(m) || N <= 0 || !dt || !y || !peer_bufs || !ctrl || !nlml) return KJX_ERR_INVALID_ARG;
+  if ((site_mean == nullptr) != (site_cov == nullptr)) return KJX_ERR_INVALID_ARG;
+  if ((post_mean == nullptr) != (post_var == nullptr)) return KJX_ERR_INVALID_ARG;
+  if ((new_site_mean == nullptr) != (new_site_cov == nullptr)) return KJX_ERR_INVALID_ARG;
+  if (world < 1 || world > 64 || rank < 0 || rank >= world) return KJX_ERR_INVALID_ARG;
+  if (stride < (int64_t)kjx_filter_summary_doubles(m->state_dim)) return KJX_ERR_INVALID_ARG;
+  ShardLink link;
+  link.peer_bufs = peer_bufs; link.ctrl = (unsigned long long*)ctrl; link.nlml_out = nlml; link.stride = stride;
+  link.world = world; link.rank = rank;
+  cudaStream_t st = (cudaStream_t)stream;
+  KJX_SMALL_DISPATCH((shard_iteration<KJX_BLOCK_MATERN32>(m, N, dt, y, site_mean, site_cov, link, post_mean, post_var, new_site_mean, new_site_cov, ws, ws_bytes, flags, st)),
+                     (shard_iteration<KJX_BLOCK_MATERN52>(m, N, dt, y, site_mean, site_cov, link, post_mean, post_var, new_site_mean, new_site_cov, ws, ws_bytes, flags, st)))
 }
 #endif
 

@@ -16,6 +16,7 @@
 // site_cov[N,1,1], outputs alike); a thread owns L consecutive steps, so it moves them as 256-bit vectors
 // (4 steps per LDG.256/STG.256 — exactly one 32-byte sector per access, nothing fetched twice).
 #pragma once
+#include <type_traits>
 #include "kjx_small_kernels.cuh"
 
 // minimum resident blocks per SM requested from ptxas (register caps 168 / 128): measured best on B200
@@ -95,8 +96,58 @@ template <typename T, int D> struct ScanLevel {
   int64_t n;     // number of elements
 };
 
+// ------------------------------------------------------------------------------------------------
+// Time-sharded iteration (one shard per GPU): the exchange of the shards' scan elements and of their partial nlml
+// values lives INSIDE the scan / filter / smoother kernels, over NVLink / NVSwitch peer memory — no collective call and
+// no extra launch.  Every rank owns a receive buffer that all ranks can write (symmetric memory):
+//   doubles: summaries [2][world][stride] | flags [2][world] (u64) | nlml [2][world] | nlml flags [2][world] (u64)
+// (two parities; a slot of parity p is rewritten two iterations later, and the nlml exchange — every rank waits for
+// every rank's partial at the end of its smoother — keeps the ranks within one iteration of each other).
+struct ShardLink {
+  double* const* peer_bufs;      // DEVICE array [world]: receive buffer of every rank (own one included)
+  unsigned long long* ctrl;      // DEVICE [4], zero before first use: epoch | top-scan ticket | filter ticket | smoother ticket
+  double* nlml_out;              // [1] negative log marginal likelihood of the WHOLE series (every rank gets it)
+  long long stride;              // doubles per summary slot (>= packed element size)
+  int world, rank;
+};
+__device__ __forceinline__ double* link_summary(double* buf, const ShardLink& l, int par, int r) {
+  return buf + ((size_t)par * l.world + r) * l.stride;
+}
+__device__ __forceinline__ unsigned long long* link_flag(double* buf, const ShardLink& l, int par, int r) {
+  return reinterpret_cast<unsigned long long*>(buf + (size_t)2 * l.world * l.stride) + (size_t)par * l.world + r;
+}
+__device__ __forceinline__ double* link_nlml(double* buf, const ShardLink& l, int par, int r) {
+  return buf + (size_t)2 * l.world * l.stride + (size_t)2 * l.world + (size_t)par * l.world + r;
+}
+__device__ __forceinline__ unsigned long long* link_nlml_flag(double* buf, const ShardLink& l, int par, int r) {
+  return reinterpret_cast<unsigned long long*>(buf + (size_t)2 * l.world * l.stride + (size_t)4 * l.world) + (size_t)par * l.world + r;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void wait_flag_sys(const unsigned long long* p, unsigned long long e) {
+  unsigned long long seen;
+  do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(p) : "memory"); } while (seen < e);
+}
+__device__ __forceinline__ double ld_relaxed_sys(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+// element of shard r of this epoch, out of the own receive buffer (waits for it to arrive)
+template <int D>
+__device__ __forceinline__ void link_wait_element(const ShardLink& l, double* mybuf, int par, unsigned long long e, int r, FSum<double, D>& s) {
+  wait_flag_sys(link_flag(mybuf, l, par, r), e);
+  const double* src = link_summary(mybuf, l, par, r);
+  double v[FSum<double, D>::NS];
+#pragma unroll
+  for (int k = 0; k < FSum<double, D>::NS; ++k) v[k] = ld_relaxed_sys(src + k);
+  fsum_unpack<double, D>(v, s);
+}
+
 template <typename T, int D> struct FusedArgs {
   SmallArgs<T, D> a;        // prior, site model, data pointers, scan workspace (see kjx_small_kernels.cuh)
+  ShardLink link;           // time-sharded iteration only (kernels instantiated with SHARDED)
   ScanLevel<T, D> lvl[3];   // chunk elements / segment totals / super-segment totals with their scans
   T* xf;                    // filtered moments, private layout
   const T* s_info_in;       // [D + D*D] information (eta, J) of all later shards about this shard's last state
@@ -135,7 +186,7 @@ __global__ void __launch_bounds__(KJX_BLOCK) fused_fold_kernel(const FusedArgs<T
   constexpr int D = BlockDim<KIND>::D;
   using S = FSum<T, D>;
   const SmallArgs<T, D>& a = fa.a;
-  const int64_t c = (int64_t)blockIdx.x * KJX_BLOCK + threadIdx.x;
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= a.nchunks) return;
   const int64_t s0 = c * a.L;
   const int64_t s1 = (s0 + a.L < a.N) ? s0 + a.L : a.N;
@@ -228,6 +279,20 @@ __device__ __forceinline__ void segscan_pass(const T* sm, const ScanLevel<T, D>&
   }
 }
 
+template <typename T, int D, int SEG> __device__ __forceinline__ void segscan_stage(T* sm, const ScanLevel<T, D>& lv, int64_t first) {
+  using S = FSum<T, D>;
+  constexpr int PER16 = 16 / sizeof(T);
+  for (int idx = threadIdx.x; idx < S::NS * SEG / PER16; idx += 64) {
+    const int k = (idx * PER16) / SEG, sl = (idx * PER16) % SEG;
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(sm + k * SEG + sl);
+    const T* src = lv.items + k * lv.stride + first + sl;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+}
+
 template <typename T, int D, int SEG>
 __global__ void __launch_bounds__(64) fused_segscan_kernel(const ScanLevel<T, D> lv, T* total_out, size_t total_stride) {
   using S = FSum<T, D>;
@@ -236,19 +301,54 @@ __global__ void __launch_bounds__(64) fused_segscan_kernel(const ScanLevel<T, D>
   T* sm = reinterpret_cast<T*>(smem_raw);                  // [NS][KJX_SEG]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t first = (int64_t)blockIdx.x * KJX_SEG;
-  // stage the segment: 16-byte asynchronous copies, coalesced (stride is a multiple of KJX_SEG)
-  constexpr int PER16 = 16 / sizeof(T);
-  for (int idx = threadIdx.x; idx < S::NS * KJX_SEG / PER16; idx += 64) {
-    const int k = (idx * PER16) / KJX_SEG, sl = (idx * PER16) % KJX_SEG;
-    const unsigned dst = (unsigned)__cvta_generic_to_shared(sm + k * KJX_SEG + sl);
-    const T* src = lv.items + k * lv.stride + first + sl;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
+  segscan_stage<T, D, SEG>(sm, lv, first);   // 16-byte asynchronous copies, coalesced (stride is a multiple of the segment)
   if (warp == 0) segscan_pass<T, D, false, SEG>(sm, lv, first, lane, total_out, total_stride, seg_slot(blockIdx.x, SEG));
   else segscan_pass<T, D, true, SEG>(sm, lv, first, lane, nullptr, 0, 0);
+}
+
+// The two upper levels in ONE launch: every block scans one level-1 segment exactly like fused_segscan_kernel; the block
+// that finishes last (ticket) then scans the single level-2 segment, whose total is the shard's element.  SHARDED: that
+// block also PUBLISHES the element — thread r stores it into rank r's receive buffer over NVLink and releases the epoch
+// flag —, so the exchange costs no launch of its own and starts the instant the element exists.
+template <typename T, int D, int SEG, bool SHARDED>
+__global__ void __launch_bounds__(64) fused_segscan_top_kernel(const ScanLevel<T, D> lv1, const ScanLevel<T, D> lv2, T* total_out,
+                                                               unsigned long long* ticket, const ShardLink link) {
+  using S = FSum<T, D>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* sm = reinterpret_cast<T*>(smem_raw);                  // [NS][SEG]
+  __shared__ int s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t first = (int64_t)blockIdx.x * SEG;
+  segscan_stage<T, D, SEG>(sm, lv1, first);
+  if (warp == 0) segscan_pass<T, D, false, SEG>(sm, lv1, first, lane, lv2.items, lv2.stride, seg_slot(blockIdx.x, SEG));
+  else segscan_pass<T, D, true, SEG>(sm, lv1, first, lane, nullptr, 0, 0);
+  // last block done?
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long t = atomicAdd(ticket, 1ull);
+    s_last = (t == (unsigned long long)gridDim.x - 1ull) ? 1 : 0;
+    if (s_last) *ticket = 0ull;                            // self-resetting: the next launch starts from zero again
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  segscan_stage<T, D, SEG>(sm, lv2, 0);                    // cp.async.cg reads through L2: sees every block's total
+  if (warp == 0) segscan_pass<T, D, false, SEG>(sm, lv2, 0, lane, total_out, 1, 0);
+  else segscan_pass<T, D, true, SEG>(sm, lv2, 0, lane, nullptr, 0, 0);
+  if constexpr (SHARDED && std::is_same<T, double>::value) {
+    __syncthreads();                                       // total_out (written by lane 0 of warp 0) is visible to the block
+    const int r = threadIdx.x;
+    if (r < link.world) {
+      const unsigned long long e = link.ctrl[0] + 1ull;
+      const int par = (int)(e & 1ull);
+      double* dst = link_summary(link.peer_bufs[r], link, par, link.rank);
+#pragma unroll
+      for (int k = 0; k < S::NS; ++k) dst[k] = total_out[k];
+      __threadfence_system();
+      st_release_sys(link_flag(link.peer_bufs[r], link, par, link.rank), e);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -256,20 +356,41 @@ __global__ void __launch_bounds__(64) fused_segscan_kernel(const ScanLevel<T, D>
 // PLAIN: the run() iteration (no mask, filtered moments parked in the private layout, sites not written back).
 // !PLAIN adds, with runtime checks: masked (predict-only) steps, energy-only runs (no filtered moments kept) and
 // writing the initialised sites — the stand-alone kjx_filter and the prediction path.
-template <typename T, int KIND, bool GAUSS_EP, bool VEC, bool PLAIN>
+// SHARDED (fp64): the filtered state entering the shard is not read from f_state_in but folded, by thread 0 of every
+// block, from the elements the earlier shards published into this rank's receive buffer (waiting for them if need be);
+// the block that finishes last sums the per-block log-likelihoods and publishes the shard's partial nlml to every rank.
+template <typename T, int KIND, bool GAUSS_EP, bool VEC, bool PLAIN, bool SHARDED = false>
 __global__ void __launch_bounds__(KJX_BLOCK, KJX_R3_MINB) fused_filter_kernel(const FusedArgs<T, BlockDim<KIND>::D> fa) {
   constexpr int D = BlockDim<KIND>::D;
   constexpr int NP = Packed<D>::NP;
   using FS = FSum<T, D>;
   const SmallArgs<T, D>& a = fa.a;
   __shared__ T red[KJX_BLOCK / 32];
-  const int64_t c = (int64_t)blockIdx.x * KJX_BLOCK + threadIdx.x;
+  __shared__ T st_in[D + D * D];
+  __shared__ int s_last;
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t s0 = c * a.L;
   const int64_t s1 = (s0 + a.L < a.N) ? s0 + a.L : a.N;
   T Pinf[D][D]; load_pinf<T, D>(a.prior, Pinf);
   T nl = T(0);
+  if constexpr (SHARDED && std::is_same<T, double>::value) {
+    if (threadIdx.x == 0) {
+      const ShardLink& l = fa.link;
+      const unsigned long long e = l.ctrl[0] + 1ull;
+      const int par = (int)(e & 1ull);
+      double* mybuf = l.peer_bufs[l.rank];
+      FiltState<double, D> x0;
+#pragma unroll
+      for (int i = 0; i < D; ++i) { x0.m[i] = 0.0; for (int j = 0; j < D; ++j) x0.P[i][j] = Pinf[i][j]; }    // sde_gp.py:265
+#pragma unroll 1
+      for (int r = 0; r < l.rank; ++r) { FSum<double, D> sr; link_wait_element<D>(l, mybuf, par, e, r, sr); fsum_apply<double, D>(sr, x0); }
+#pragma unroll
+      for (int i = 0; i < D; ++i) { st_in[i] = x0.m[i]; for (int j = 0; j < D; ++j) st_in[D + i * D + j] = x0.P[i][j]; }
+    }
+    __syncthreads();
+  }
   if (s0 < s1) {
-    FiltState<T, D> x; load_state<T, D>(a.f_state_in, x);
+    FiltState<T, D> x; load_state<T, D>(SHARDED ? st_in : a.f_state_in, x);
     {   // everything before this chunk: super-segments, segments, chunks (outermost first)
       int64_t idx[3] = {c, c / fa.seg, c / ((int64_t)fa.seg * fa.seg)};
 #pragma unroll 1
@@ -343,8 +464,37 @@ __global__ void __launch_bounds__(KJX_BLOCK, KJX_R3_MINB) fused_filter_kernel(co
   __syncthreads();
   if (threadIdx.x == 0) {
     T t = T(0);
-    for (int w = 0; w < KJX_BLOCK / 32; ++w) t += red[w];
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
     a.block_nlml[blockIdx.x] = t;
+  }
+  if constexpr (SHARDED && std::is_same<T, double>::value) {
+    const ShardLink& l = fa.link;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned long long t = atomicAdd(l.ctrl + 2, 1ull);
+      s_last = (t == (unsigned long long)gridDim.x - 1ull) ? 1 : 0;
+      if (s_last) l.ctrl[2] = 0ull;
+    }
+    __syncthreads();
+    if (s_last) {                                            // fixed-order sum of the per-block values (deterministic)
+      __threadfence();
+      double p = 0.0;
+      for (int64_t b = threadIdx.x; b < (int64_t)gridDim.x; b += blockDim.x) p += __ldcg(a.block_nlml + b);
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) p += __shfl_down_sync(0xffffffffu, p, off);
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = p;
+      __syncthreads();
+      if ((int)threadIdx.x < l.world) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+        const unsigned long long e = l.ctrl[0] + 1ull;
+        const int par = (int)(e & 1ull), r = threadIdx.x;
+        *link_nlml(l.peer_bufs[r], l, par, l.rank) = -t;      // sde_gp.py:301  nlml -= sum(log_lik_n)
+        __threadfence_system();
+        st_release_sys(link_nlml_flag(l.peer_bufs[r], l, par, l.rank), e);
+      }
+    }
   }
 }
 
@@ -364,16 +514,35 @@ __device__ __forceinline__ void smoothed_outputs(const SmallArgs<T, D>& a, const
   }
 }
 
-template <typename T, int KIND, bool GAUSS_EP, bool VEC>
+// SHARDED (fp64): the information of the later shards about this shard's last state is folded, by thread 0 of every
+// block, from the elements in the receive buffer; the block that finishes last collects the shards' partial nlml values
+// (rank order: every rank gets the same bits), writes the total and closes the epoch.
+template <typename T, int KIND, bool GAUSS_EP, bool VEC, bool SHARDED = false>
 __global__ void __launch_bounds__(KJX_BLOCK, KJX_R4_MINB) fused_smoother_kernel(const FusedArgs<T, BlockDim<KIND>::D> fa) {
   constexpr int D = BlockDim<KIND>::D;
   constexpr int NP = Packed<D>::NP;
   using FS = FSum<T, D>;
   const SmallArgs<T, D>& a = fa.a;
-  const int64_t c = (int64_t)blockIdx.x * KJX_BLOCK + threadIdx.x;
+  __shared__ T info_in[D + D * D];
+  __shared__ int s_last;
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t s0 = c * a.L;
   const int64_t s1 = (s0 + a.L < a.N) ? s0 + a.L : a.N;
-  if (s0 >= s1) return;
+  if constexpr (SHARDED && std::is_same<T, double>::value) {
+    if (threadIdx.x == 0) {
+      const ShardLink& l = fa.link;
+      const unsigned long long e = l.ctrl[0] + 1ull;
+      const int par = (int)(e & 1ull);
+      double* mybuf = l.peer_bufs[l.rank];
+      Info<double, D> f; info_zero<double, D>(f);
+#pragma unroll 1
+      for (int r = l.world - 1; r > l.rank; --r) { FSum<double, D> sr; link_wait_element<D>(l, mybuf, par, e, r, sr); fsum_combine_info<double, D>(sr, f, f); }
+#pragma unroll
+      for (int i = 0; i < D; ++i) { info_in[i] = f.eta[i]; for (int j = 0; j < D; ++j) info_in[D + i * D + j] = f.J[i][j]; }
+    }
+    __syncthreads();
+  }
+  if (s0 < s1) {
   T Pinf[D][D]; load_pinf<T, D>(a.prior, Pinf);
   const T* xf = fa.xf + ((c >> 5) * (int64_t)a.L * NP) * 32 + (c & 31);
   const T lik_hyp = T(a.site.lik_hyp);
@@ -383,7 +552,7 @@ __global__ void __launch_bounds__(KJX_BLOCK, KJX_R4_MINB) fused_smoother_kernel(
   FiltState<T, D> x;
   int64_t k = s1 - 1;
   {
-    Info<T, D> info; load_info<T, D>(fa.s_info_in, info);
+    Info<T, D> info; load_info<T, D>(SHARDED ? info_in : fa.s_info_in, info);
     {   // everything after this chunk
       int64_t idx[3] = {c, c / fa.seg, c / ((int64_t)fa.seg * fa.seg)};
 #pragma unroll 1
@@ -443,6 +612,30 @@ __global__ void __launch_bounds__(KJX_BLOCK, KJX_R4_MINB) fused_smoother_kernel(
     }
     if (post) { store4v<T, VEC>(a.smooth_mean + k0, opm); store4v<T, VEC>(a.smooth_cov + k0, opv); }
     if (upd) { store4v<T, VEC>(a.new_site_mean + k0, onm); store4v<T, VEC>(a.new_site_var + k0, onv); }
+  }
+  }   // s0 < s1
+  if constexpr (SHARDED && std::is_same<T, double>::value) {
+    const ShardLink& l = fa.link;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned long long t = atomicAdd(l.ctrl + 3, 1ull);
+      s_last = (t == (unsigned long long)gridDim.x - 1ull) ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+      const unsigned long long e = l.ctrl[0] + 1ull;
+      const int par = (int)(e & 1ull);
+      double* mybuf = l.peer_bufs[l.rank];
+      double total = 0.0;
+      for (int r = 0; r < l.world; ++r) {
+        wait_flag_sys(link_nlml_flag(mybuf, l, par, r), e);
+        total += ld_relaxed_sys(link_nlml(mybuf, l, par, r));
+      }
+      l.nlml_out[0] = total;
+      l.ctrl[3] = 0ull;
+      __threadfence();
+      l.ctrl[0] = e;                                         // epoch closed: every block of this iteration has read it
+    }
   }
 }
 

@@ -17,26 +17,32 @@ import numpy as np
 import torch
 
 from . import _lib
-from .sde_gp import _Model, _workspace
+from .sde_gp import _Model
 
 
 class PeerExchange(object):
-    """Symmetric-memory receive buffers for kjx_exchange_fold (one fused exchange + fold kernel over NVLink peer
-    memory instead of an NCCL all-gather followed by a fold kernel)."""
+    """Receive buffers of the in-kernel exchange (kjx_sharded_iteration / kjx_exchange_fold): symmetric memory that
+    every rank's kernels can write over NVLink.  world == 1 needs no peer: an ordinary device buffer."""
     STRIDE = 32
 
     def __init__(self, world, rank, device, group=None):
-        import torch.distributed as dist
-        import torch.distributed._symmetric_memory as symm_mem
-        group = group or dist.group.WORLD
-        n = 2 * world * self.STRIDE + 2 * world             # data [2][world][stride] + flags [2][world] (8 bytes each)
-        self.buf = symm_mem.empty(n, dtype=torch.float64, device=device)
-        self.buf.zero_()
-        self.handle = symm_mem.rendezvous(self.buf, group)
-        torch.cuda.synchronize(device)
-        dist.barrier(group)                                  # every buffer is zeroed before anyone writes
-        self.ptrs = torch.tensor(list(self.handle.buffer_ptrs), dtype=torch.int64, device=device)
-        self.epoch = torch.zeros(1, dtype=torch.int64, device=device)
+        n = int(_lib.lib().kjx_shard_link_doubles(C.c_int32(world), C.c_int64(self.STRIDE)))
+        if world > 1:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
+            group = group or dist.group.WORLD
+            self.buf = symm_mem.empty(n, dtype=torch.float64, device=device)
+            self.buf.zero_()
+            self.handle = symm_mem.rendezvous(self.buf, group)
+            torch.cuda.synchronize(device)
+            dist.barrier(group)                              # every buffer is zeroed before anyone writes
+            ptrs = list(self.handle.buffer_ptrs)
+        else:
+            self.buf = torch.zeros(n, dtype=torch.float64, device=device)
+            ptrs = [self.buf.data_ptr()]
+        self.ptrs = torch.tensor(ptrs, dtype=torch.int64, device=device)
+        self.epoch = torch.zeros(1, dtype=torch.int64, device=device)     # kjx_exchange_fold (separate-kernel form)
+        self.ctrl = torch.zeros(4, dtype=torch.int64, device=device)      # kjx_sharded_iteration: epoch + three tickets
         self.world, self.rank = world, rank
 
 
@@ -47,9 +53,14 @@ class ShardedIteration(object):
     (torch.distributed.all_gather_into_tensor); it is None for world == 1.
     """
     def __init__(self, prior, likelihood, sites, dt_shard, y_shard, dt_next, rank, world, device, gather=None,
-                 site_mean=None, site_var=None, peer=None):
+                 site_mean=None, site_var=None, peer=None, linked=None):
+        """peer: PeerExchange or None (NCCL all-gather through `gather`).  linked (default: whenever there is a peer):
+        the whole iteration is ONE library call, kjx_sharded_iteration — exchange, fold and nlml sum inside the scan /
+        filter / smoother kernels; otherwise the four separate calls with kjx_exchange_fold or gather + fold between."""
         self.model = _Model(prior, likelihood, sites)
         self.peer = peer
+        self.linked = (peer is not None) if linked is None else bool(linked)
+        assert not self.linked or peer is not None
         self.rank, self.world, self.device, self.gather = rank, world, torch.device(device), gather
         self.dt = torch.as_tensor(dt_shard, dtype=torch.float64, device=self.device).contiguous()
         self.y = torch.as_tensor(y_shard, dtype=torch.float64, device=self.device).contiguous().reshape(-1)
@@ -66,11 +77,16 @@ class ShardedIteration(object):
         self.fns = int(L.kjx_filter_summary_doubles(d))
         self.fmsg = torch.zeros(self.fns, dtype=torch.float64, device=self.device)
         self.f_state, self.s_info = z(d + d * d), z(d + d * d)
-        self.ws, _ = _workspace(self.model, self.N, torch.float64, self.device)
+        nbytes = C.c_size_t(0)
+        _lib.check(L.kjx_workspace_bytes(self.model.ref(), C.c_int64(self.N), 8, C.byref(nbytes)), "kjx_workspace_bytes")
+        self.ws = torch.empty(max(nbytes.value, 256), dtype=torch.uint8, device=self.device)   # owned: carries the
+        # per-chunk prefixes and the packed filtered moments between the phases of an iteration
         self.nlml_part = torch.zeros(1, dtype=torch.float64, device=self.device)
         self.nlml = self.nlml_part
-        # kernels per iteration: fold, 3 segment scans | fold-shards | filter, nlml-reduce | smoother
-        self.launches_per_iteration = 8
+        self.nlml_all = torch.zeros(1, dtype=torch.float64, device=self.device)
+        # kernels per iteration.  linked: fold, level-0 scan, top scan (+ publish) | filter | smoother = 5;
+        # separate calls: fold, 3 segment scans | exchange-fold | filter, nlml-reduce | smoother = 8
+        self.launches_per_iteration = 5 if self.linked else 8
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -81,6 +97,17 @@ class ShardedIteration(object):
         reduce_nlml(t): sums the shards' partial nlml (all-reduce) — None for world == 1."""
         L, m, st = _lib.lib(), self.model.ref(), self._stream()
         N, p, wsb = C.c_int64(self.N), _lib.ptr, C.c_size_t(self.ws.numel())
+        if self.linked:
+            flags = 0 if update_sites else _lib.FLAG_NO_SITE_UPDATE
+            _lib.check(L.kjx_sharded_iteration_f64(m, N, p(self.dt), p(self.y), p(self.site_mean), p(self.site_var),
+                                                   p(self.peer.ptrs), C.c_int64(self.peer.STRIDE), self.world, self.rank,
+                                                   p(self.peer.ctrl), p(self.post_mean), p(self.post_var),
+                                                   p(self.new_site_mean), p(self.new_site_var), p(self.nlml_all), p(self.ws),
+                                                   wsb, C.c_uint32(flags), st), "kjx_sharded_iteration")
+            self.nlml = self.nlml_all
+            if update_sites:
+                self._swap_sites()
+            return self.nlml
         if events:
             events[0].record()
         _lib.check(L.kjx_filter_summary_f64(m, N, p(self.dt), p(self.y), p(self.site_mean), p(self.site_var),
@@ -107,11 +134,14 @@ class ShardedIteration(object):
             events[3].record()
         self.nlml = reduce_nlml(self.nlml_part) if reduce_nlml else self.nlml_part
         if update_sites:
-            if self.site_mean is None:
-                self.site_mean, self.site_var = torch.empty_like(self.new_site_mean), torch.empty_like(self.new_site_var)
-            self.site_mean, self.new_site_mean = self.new_site_mean, self.site_mean
-            self.site_var, self.new_site_var = self.new_site_var, self.site_var
+            self._swap_sites()
         return self.nlml
+
+    def _swap_sites(self):
+        if self.site_mean is None:
+            self.site_mean, self.site_var = torch.empty_like(self.new_site_mean), torch.empty_like(self.new_site_var)
+        self.site_mean, self.new_site_mean = self.new_site_mean, self.site_mean
+        self.site_var, self.new_site_var = self.new_site_var, self.site_var
 
 
 class GraphedIteration(object):

@@ -36,12 +36,18 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
         from bench import make_collectives
         gather, reduce_nlml, peer = make_collectives(world, rank, dev, args.exchange)
+    elif args.exchange != "nccl":
+        from kalman_jax_b200.sharded import PeerExchange
+        peer = PeerExchange(1, 0, dev)
+    linked = peer is not None and args.exchange == "peer"
+    if linked:
+        reduce_nlml = None
     N = 1 << args.log2n
     dt, y = synth(N)
     sh_dt, sh_y, dt_next, lo, hi = split_series(dt, y, world)[rank]
     it = ShardedIteration(kjx.priors.Matern52(1.0, 5.0), kjx.likelihoods.Gaussian(0.5), kjx.approximate_inference.EP(power=0.5),
                           sh_dt, sh_y, dt_next, rank, world, dev, gather, site_mean=sh_y.copy(),
-                          site_var=np.full(hi - lo, 0.5), peer=peer)
+                          site_var=np.full(hi - lo, 0.5), peer=peer, linked=linked)
     g = GraphedIteration(it, reduce_nlml)
     for _ in range(10):
         g.replay()
