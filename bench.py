@@ -25,7 +25,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "filter+smoother time-steps/s (N=2^24, d=3)"
+METRIC = "filter+smoother time-steps/s (N=2^24, d=3/30) & % HBM roofline at 1/2/4/8 GPU"
 BYTES_PER_STEP = 288          # 2(1+2f+f^2) + 2(d+d^2) + 2(f+f^2) scalars at d=3, f=1, fp64
 BYTES_FILTER, BYTES_SMOOTHER = 128, 160
 
@@ -134,6 +134,85 @@ def rel_err(a, b):
     return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(float(np.max(np.abs(b))), 1e-300))
 
 
+def fp64_peak():
+    """Measured FP64 peak of this GPU (TFLOP/s): scripts/micro/dmma_rate (mma.sync.m8n8k4.f64 and plain DFMA streams,
+    built in-tree by __graft_entry__.build()), run live; falls back to the committed measurement, then to 37.0."""
+    exe = os.path.join(ROOT, "scripts", "micro", "dmma_rate")
+    try:
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=60).stdout
+        best = {"dmma": 0.0, "dfma": 0.0}
+        for ln in out.splitlines():
+            p = ln.split()
+            if len(p) > 2 and p[0] in best and p[-1] == "TFLOP/s":
+                best[p[0]] = max(best[p[0]], float(p[-2]))
+        if best["dmma"] > 0:
+            return {"tflops": max(best.values()), "dmma_tflops": best["dmma"], "dfma_tflops": best["dfma"],
+                    "source": "measured live: scripts/micro/dmma_rate.cu (best over 4..32 warps per CTA, 2 CTAs per SM)"}
+    except Exception:
+        pass
+    try:
+        p = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak_r02.json")))
+        p["source"] = "profiles/fp64_peak_r02.json (committed measurement of the same microbenchmark)"
+        return p
+    except Exception:
+        return {"tflops": 37.0, "source": "fallback: round-1 measurement of scripts/micro/dmma_rate.cu"}
+
+
+def extra_workloads(peak):
+    """The d ~ 30 / spatio-temporal legs of BASELINE's metric (C3 and C4), FP64-compute-bound: steady-state
+    run() iterations per second on synthetic data of the named shapes, with the algorithmic 12 d^3 flops per step
+    against the measured FP64 peak.  One GPU; a few iterations each (seconds)."""
+    import torch
+    import kalman_jax_b200 as kjx
+    P = kjx.priors
+    out = {}
+
+    def timed(model, reps):
+        t0 = time.perf_counter(); model.run(compute_grad=False); torch.cuda.synchronize(); first = time.perf_counter() - t0
+        model.run(compute_grad=False)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            model.run(compute_grad=False)
+        b.record()
+        torch.cuda.synchronize()
+        return first, a.elapsed_time(b) / reps * 1e-3
+
+    def entry(name, workload, N, d, first, sec):
+        tf = 12.0 * d ** 3 * N / sec / 1e12
+        out[name] = {"workload": workload, "N": N, "state_dim": d, "s_per_iteration": sec, "first_iteration_s": first,
+                     "value": N / sec, "unit": "time-steps/s",
+                     "roofline": {"bound": "fp64", "achieved": tf, "peak": peak["tflops"], "unit": "TFLOP/s",
+                                  "frac": tf / peak["tflops"], "algorithmic_flops_per_step": 12.0 * d ** 3}}
+
+    rng = np.random.default_rng(1)
+    N = 36020                                                   # aircraft.py:27-35: daily bins incl. padding
+    t, y = np.arange(N, dtype=float), rng.poisson(0.035, N).astype(float)
+    m52 = dict(variance=2., lengthscale=5.5e4)
+    qp_year = dict(variance=1., lengthscale_periodic=2., period=365., lengthscale_matern=1.5e4)
+    qp_week = dict(variance=1., lengthscale_periodic=2., period=7., lengthscale_matern=30 * 365.)
+    for name, parts, rule, d in [
+            ("c3_d59", [P.Matern52(**m52), P.QuasiPeriodicMatern32(**qp_year), P.QuasiPeriodicMatern32(**qp_week)],
+             kjx.approximate_inference.GHEP(power=1), 59),
+            ("c3_d31", [P.Matern52(**m52), P.QuasiPeriodicMatern32(**qp_year)], kjx.approximate_inference.VI(), 31)]:
+        model = kjx.SDEGP(P.Sum(parts), kjx.likelihoods.Poisson(), t, y, approx_inf=rule)
+        first, sec = timed(model, 5)
+        entry(name, "C3: aircraft-shaped daily counts, Poisson, Sum[Matern52, QuasiPeriodicMatern32 x%d], %s; steady-state "
+              "run() iteration" % (len(parts) - 1, rule.name), N, d, first, sec)
+        del model
+    rng = np.random.default_rng(99)
+    N = 4096
+    t, r = np.sort(rng.uniform(0, 400, N)), rng.uniform(-3, 3, N)
+    y = (rng.uniform(size=N) < 0.5).astype(float)
+    model = kjx.SDEGP(P.SpatioTemporalMatern52(1.0, 1.0, 0.3, z=np.linspace(-3, 3, 64)), kjx.likelihoods.Probit(), t, y, r=r,
+                      approx_inf=kjx.approximate_inference.VI())
+    first, sec = timed(model, 2)
+    entry("c4_d192", "C4: spatio-temporal Matern-5/2, Ns=64 inducing points (d=192), Probit, VI, N=4096 scattered points; "
+          "steady-state run() iteration (includes the host-side per-step measurement rows)", N, 192, first, sec)
+    return out
+
+
 def cpu_replicas(lib, dt, y, cores, reps=1):
     """`cores` independent copies of the chain, one per host thread (the reference algorithm cannot use more
     than one core on one series: step n needs step n-1, sde_gp.py:271)."""
@@ -227,6 +306,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the full-size comparison with the C oracle")
+    ap.add_argument("--no-extra", action="store_true", help="skip the d~30 / spatio-temporal legs (extra_workloads)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "peer-separate", "nccl"],
                     help="summary exchange: inside the kernels over peer memory (default), the separate exchange+fold "
                          "kernel over peer memory, or an NCCL all-gather")
@@ -312,21 +392,30 @@ def main():
         del it_ph
         torch.cuda.empty_cache()
     graphed = None
+    # iterations per graph launch: the sites ping-pong between two buffers, so iterations are captured in pairs; the
+    # largest of 5, 2, 1 pairs whose length divides --steps (an odd --steps falls back to one iteration per launch)
+    pairs = next((p for p in (5, 2, 1) if args.steps % (2 * p) == 0), 0)
     if not args.no_graph:
         from kalman_jax_b200.sharded import GraphedIteration
         try:
-            graphed = GraphedIteration(it, reduce_nlml)
+            graphed = GraphedIteration(it, reduce_nlml, pairs=pairs)
         except Exception as e:      # keep going eagerly, but say so
             print("bench: CUDA-graph capture failed (%s); launching eagerly" % str(e).splitlines()[0], file=sys.stderr)
             graphed = None
     step_fn = graphed.replay if graphed else (lambda: it.iteration(reduce_nlml=reduce_nlml))
-    for _ in range(3):
+    for _ in range(4):
         step_fn()
+    if graphed and pairs:
+        graphed.replay_many()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     start.record()
-    for k in range(args.steps):
-        nl_t = step_fn()
+    if graphed and pairs:                                   # K steps = K / (2 pairs) launches of the multi-iteration graph
+        for k in range(args.steps // (2 * pairs)):
+            nl_t = graphed.replay_many()
+    else:
+        for k in range(args.steps):
+            nl_t = step_fn()
     stop.record()
     barrier()
     for _ in range(n_extra // 2):       # a few more samples under the same load right after the timed region
@@ -458,7 +547,8 @@ def main():
                                "filter(stored sites) -> RTS smoother -> site update; N=2^%d steps, d=3, f=1" % args.log2n,
                    "N": N, "state_dim": 3, "sharding": "time axis, %d contiguous shard(s)" % world,
                    "exchange": exchange,
-                   "launch": "CUDA graph replay (2 graphs: sites ping/pong)" if graphed else "eager (ctypes calls per iteration)",
+                   "launch": ("CUDA graph replay, %d iterations per graph launch (sites ping/pong between two buffers)" % max(2 * pairs, 1))
+                             if graphed else "eager (ctypes calls per iteration)",
                    "l2_policy": "inputs (%.1f GB per iteration per GPU) exceed the 126 MB L2; no flush needed" % (BYTES_PER_STEP * n_local / 1e9)},
         "roofline": {"bound": "hbm", "kernel": ("fused_filter_kernel (R3)", "fused_smoother_kernel (R4)")[dom - 1],
                      "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
@@ -487,6 +577,16 @@ def main():
         par["ok"] = bool(max(par["nlml_rel"], par["post_mean_rel"], par["post_var_rel"], par["site_rel"]) <= par["tol"])
         line["parity"] = par
         del want
+    if world == 1 and not args.no_extra:
+        # free the headline workload's buffers first
+        del it, graphed
+        torch.cuda.empty_cache()
+        pk = fp64_peak()
+        line["fp64_peak"] = pk
+        try:
+            line["extra_workloads"] = extra_workloads(pk)
+        except Exception as e:
+            line["extra_workloads"] = {"error": str(e).splitlines()[0]}
     if not args.no_cpu:
         lib = cpu_oracle_lib()
         n_s = 1 << 22

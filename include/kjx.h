@@ -224,17 +224,18 @@ int kjx_exchange_fold_f64(const kjx_model_t* m, const double* my_summary, double
  * separate exchange launch; 5 kernels): the block that completes the shard's scan stores the shard's element into every
  * rank's receive buffer over NVLink / NVSwitch and releases an epoch flag; the filter kernel's blocks wait for the
  * elements of the earlier shards and fold them into the state entering the shard, the smoother kernel's blocks fold the
- * later shards' elements into the information about the shard's last state; the filter's last block publishes the
- * shard's partial nlml and the smoother's last block sums all partials in rank order into nlml[0] (every rank gets the
- * same bits) and closes the epoch.  peer_bufs: DEVICE array [world] of receive-buffer pointers (symmetric memory;
+ * later shards' elements into the information about the shard's last state; one extra block of the smoother kernel
+ * publishes the shard's partial nlml and sums all shards' partials in rank order into nlml[0] (every rank gets the same
+ * bits) while the other blocks work; the block that finishes last closes the epoch.  peer_bufs: DEVICE array [world] of receive-buffer pointers (symmetric memory;
  * kjx_shard_link_doubles(world, stride) doubles each, ZERO before first use): summaries [2][world][stride] | flags
- * [2][world] | nlml [2][world] | nlml flags [2][world].  ctrl: DEVICE uint64[4] owned by this rank, zero before first
- * use (epoch and three tickets).  Graph-capturable; all ranks must make the call the same number of times.  world == 1
+ * [2][world] | nlml [2][world] | nlml flags [2][world]; my_buf: this rank's own buffer, by value.  ctrl: DEVICE uint64[4]
+ * owned by this rank, zero before first use (epoch and tickets).  Graph-capturable; all ranks must make the call the same number of times.  world == 1
  * works with an ordinary device buffer.  Same outputs as kjx_filter_summary / exchange / filter_apply / smoother_apply. */
 size_t kjx_shard_link_doubles(int32_t world, int64_t stride);
 int kjx_sharded_iteration_f64(const kjx_model_t* m, int64_t N, const double* dt, const double* y,
                               const double* site_mean /*?*/, const double* site_cov /*?*/,
-                              double* const* peer_bufs, int64_t stride, int32_t world, int32_t rank, uint64_t* ctrl,
+                              double* const* peer_bufs, double* my_buf /* == peer_bufs[rank] */, int64_t stride,
+                              int32_t world, int32_t rank, uint64_t* ctrl,
                               double* post_mean /*?*/, double* post_var /*?*/,
                               double* new_site_mean /*?*/, double* new_site_cov /*?*/, double* nlml /* [1] */,
                               void* ws, size_t ws_bytes, uint32_t flags, kjx_stream_t stream);

@@ -46,6 +46,8 @@ int env_knob(const char* name) {
 }
 int knob_chunk() { static const int v = env_knob("KJX_CHUNK"); return v; }
 int knob_threads() { static const int v = env_knob("KJX_THREADS"); return v; }
+int knob_seg() { static const int v = env_knob("KJX_SEG"); return v; }
+int knob_seg1() { static const int v = env_knob("KJX_SEG1"); return v; }
 
 // steps per thread chunk: long chunks amortise the O(d^3) scan combines, short ones keep every SM
 // busy on short series.  A multiple of 4 so a chunk starts on a 32-byte boundary of every array.
@@ -79,7 +81,7 @@ template <typename T, int D> struct SmallLayout {
   size_t off_ftp, off_fbt, off_fbp, off_fst, off_sts, off_sbt, off_sbs, off_sst, off_nl, off_fin, off_sin;
   size_t off_info, off_xf, off_lvl[3][3], lvl_stride[3], total;
   int64_t lvl_n[3];
-  int seg;
+  int seg0, seg1;
   explicit SmallLayout(int64_t N) {
     constexpr size_t FNS = FSum<T, D>::NS, SNS = SSum<T, D>::NS;
     L = pick_chunk(N);
@@ -97,12 +99,20 @@ template <typename T, int D> struct SmallLayout {
     off_info = take(D + D * D);
     // three scan levels of the fused path: elements, exclusive prefix, exclusive suffix (strides = whole segments)
     // segments of 64 while three levels of 64 hold every chunk (shorter dependent chains), else 128
-    seg = (nchunks <= 64 * 64 * 64 / 2) ? 64 : 128;
+    // level 0: long segments (3 + 5 + 3 combines per 128 elements instead of 1 + 5 + 1 per 64: less FP64 work per
+    // element; measured 16.5 vs 20.5 us at 52 429 chunks) unless the series is short; levels 1 and 2 are one or a few
+    // blocks each, i.e. pure latency: the shortest segments that still reach the top in three levels
+    seg0 = (nchunks >= 8192) ? 128 : 64;
+    if (knob_seg() == 64 || knob_seg() == 128) seg0 = knob_seg();
+    seg1 = 128;
+    for (int c : {64, 32}) if ((int64_t)seg0 * c * c >= nchunks) seg1 = c;
+    if (knob_seg1() == 32 || knob_seg1() == 64 || knob_seg1() == 128) seg1 = std::max(seg1, knob_seg1());
+    if ((int64_t)seg0 * seg1 * seg1 < nchunks) { seg0 = 128; seg1 = 128; }
     int64_t n = nchunks;
     for (int l = 0; l < 3; ++l) {
       lvl_n[l] = n; lvl_stride[l] = round_up((size_t)n, KJX_SEG_MAX);
       for (int q = 0; q < 3; ++q) off_lvl[l][q] = take(FNS * lvl_stride[l]);
-      n = (n + seg - 1) / seg;
+      n = (n + (l ? seg1 : seg0) - 1) / (l ? seg1 : seg0);
     }
     // filtered moments between the fused filter and smoother passes: [warp][step][element][lane]
     off_xf = take(cstride * (size_t)L * Packed<D>::NP);
@@ -127,7 +137,7 @@ void bind_fused(FusedArgs<T, D>& fa, const SmallLayout<T, D>& lay, void* ws) {
   char* w = (char*)ws;
   bind_workspace<T, D>(fa.a, lay, ws);
   fa.s_info_in = (T*)(w + lay.off_info); fa.xf = (T*)(w + lay.off_xf);
-  fa.seg = lay.seg;
+  fa.seg0 = lay.seg0; fa.seg1 = lay.seg1;
   for (int l = 0; l < 3; ++l) {
     fa.lvl[l].items = (T*)(w + lay.off_lvl[l][0]); fa.lvl[l].prefix = (T*)(w + lay.off_lvl[l][1]);
     fa.lvl[l].suffix = (T*)(w + lay.off_lvl[l][2]); fa.lvl[l].stride = lay.lvl_stride[l]; fa.lvl[l].n = lay.lvl_n[l];
@@ -202,28 +212,30 @@ struct Fused {
     if (fa.vec_ok) fused_fold_kernel<T, KIND, true><<<grid(), threads(), 0, st>>>(fa);
     else fused_fold_kernel<T, KIND, false><<<grid(), threads(), 0, st>>>(fa);
     // three levels of segment scans; the top level's single total is the shard's element
-    const size_t smem = sizeof(T) * FSum<T, D>::NS * fa.seg;
     for (int l = 0; l < 3; ++l) {
-      const unsigned nseg = (unsigned)((fa.lvl[l].n + fa.seg - 1) / fa.seg);
+      const int seg = l ? fa.seg1 : fa.seg0;
+      const unsigned nseg = (unsigned)((fa.lvl[l].n + seg - 1) / seg);
       T* tot = (l < 2) ? fa.lvl[l + 1].items : (total_out ? total_out : fa.a.f_shard_total);
       const size_t tstride = (l < 2) ? fa.lvl[l + 1].stride : 1;
-      if (fa.seg == 64) fused_segscan_kernel<T, D, 64><<<nseg, 64, smem, st>>>(fa.lvl[l], tot, tstride);
-      else fused_segscan_kernel<T, D, 128><<<nseg, 64, smem, st>>>(fa.lvl[l], tot, tstride);
+      launch_segscan(seg, nseg, fa.lvl[l], tot, tstride, st);
     }
+  }
+  void launch_segscan(int seg, unsigned nseg, const ScanLevel<T, D>& lv, T* tot, size_t tstride, cudaStream_t st) {
+    const size_t smem = sizeof(T) * FSum<T, D>::NS * seg;
+    if (seg == 32) fused_segscan_kernel<T, D, 32><<<nseg, 64, smem, st>>>(lv, tot, tstride, fa.seg1);
+    else if (seg == 64) fused_segscan_kernel<T, D, 64><<<nseg, 64, smem, st>>>(lv, tot, tstride, fa.seg1);
+    else fused_segscan_kernel<T, D, 128><<<nseg, 64, smem, st>>>(lv, tot, tstride, fa.seg1);
   }
   // sharded iteration: fold, level-0 scan, then levels 1 + 2 and the publication of the shard's element in one launch
   void reduce_linked(cudaStream_t st) {
     if (fa.vec_ok) fused_fold_kernel<T, KIND, true><<<grid(), threads(), 0, st>>>(fa);
     else fused_fold_kernel<T, KIND, false><<<grid(), threads(), 0, st>>>(fa);
-    const size_t smem = sizeof(T) * FSum<T, D>::NS * fa.seg;
-    const unsigned nseg0 = (unsigned)((fa.lvl[0].n + fa.seg - 1) / fa.seg), nseg1 = (unsigned)((fa.lvl[1].n + fa.seg - 1) / fa.seg);
-    if (fa.seg == 64) {
-      fused_segscan_kernel<T, D, 64><<<nseg0, 64, smem, st>>>(fa.lvl[0], fa.lvl[1].items, fa.lvl[1].stride);
-      fused_segscan_top_kernel<T, D, 64, true><<<nseg1, 64, smem, st>>>(fa.lvl[1], fa.lvl[2], fa.a.f_shard_total, fa.link.ctrl + 1, fa.link);
-    } else {
-      fused_segscan_kernel<T, D, 128><<<nseg0, 64, smem, st>>>(fa.lvl[0], fa.lvl[1].items, fa.lvl[1].stride);
-      fused_segscan_top_kernel<T, D, 128, true><<<nseg1, 64, smem, st>>>(fa.lvl[1], fa.lvl[2], fa.a.f_shard_total, fa.link.ctrl + 1, fa.link);
-    }
+    const unsigned nseg0 = (unsigned)((fa.lvl[0].n + fa.seg0 - 1) / fa.seg0), nseg1 = (unsigned)((fa.lvl[1].n + fa.seg1 - 1) / fa.seg1);
+    launch_segscan(fa.seg0, nseg0, fa.lvl[0], fa.lvl[1].items, fa.lvl[1].stride, st);
+    const size_t smem = sizeof(T) * FSum<T, D>::NS * fa.seg1;
+    if (fa.seg1 == 32) fused_segscan_top_kernel<T, D, 32, true><<<nseg1, 64, smem, st>>>(fa.lvl[1], fa.lvl[2], fa.a.f_shard_total, fa.link.ctrl + 1, fa.link);
+    else if (fa.seg1 == 64) fused_segscan_top_kernel<T, D, 64, true><<<nseg1, 64, smem, st>>>(fa.lvl[1], fa.lvl[2], fa.a.f_shard_total, fa.link.ctrl + 1, fa.link);
+    else fused_segscan_top_kernel<T, D, 128, true><<<nseg1, 64, smem, st>>>(fa.lvl[1], fa.lvl[2], fa.a.f_shard_total, fa.link.ctrl + 1, fa.link);
   }
   void filter_linked(cudaStream_t st) {
     const bool fast = gauss_ep(m);
@@ -239,10 +251,11 @@ struct Fused {
     const size_t al = sizeof(T) * 4;
     const bool vec = fa.vec_ok && aligned_to(post_mean, al) && aligned_to(post_var, al) && aligned_to(new_site_mean, al) && aligned_to(new_site_var, al);
     const bool fast = gauss_ep(m);
-    if (fast && vec) fused_smoother_kernel<T, KIND, true, true, true><<<grid(), threads(), 0, st>>>(fa);
-    else if (fast) fused_smoother_kernel<T, KIND, true, false, true><<<grid(), threads(), 0, st>>>(fa);
-    else if (vec) fused_smoother_kernel<T, KIND, false, true, true><<<grid(), threads(), 0, st>>>(fa);
-    else fused_smoother_kernel<T, KIND, false, false, true><<<grid(), threads(), 0, st>>>(fa);
+    const unsigned g1 = grid() + 1;                         // one extra block: the nlml exchange
+    if (fast && vec) fused_smoother_kernel<T, KIND, true, true, true><<<g1, threads(), 0, st>>>(fa);
+    else if (fast) fused_smoother_kernel<T, KIND, true, false, true><<<g1, threads(), 0, st>>>(fa);
+    else if (vec) fused_smoother_kernel<T, KIND, false, true, true><<<g1, threads(), 0, st>>>(fa);
+    else fused_smoother_kernel<T, KIND, false, false, true><<<g1, threads(), 0, st>>>(fa);
   }
   // plain: the run() iteration; otherwise mask / energy-only / site write-back are honoured
   void filter(cudaStream_t st, bool plain = true) {
@@ -866,17 +879,17 @@ size_t kjx_shard_link_doubles(int32_t world, int64_t stride) {
   return (world < 1 || stride < 1) ? 0 : (size_t)2 * world * (size_t)stride + (size_t)6 * world;
 }
 int kjx_sharded_iteration_f64(const kjx_model_t* m, int64_t N, const double* dt, const double* y, const double* site_mean,
-                              const double* site_cov, double* const* peer_bufs, int64_t stride, int32_t world, int32_t rank,
-                              uint64_t* ctrl, double* post_mean, double* post_var, double* new_site_mean, double* new_site_cov,
+                              const double* site_cov, double* const* peer_bufs, double* my_buf, int64_t stride, int32_t world,
+                              int32_t rank, uint64_t* ctrl, double* post_mean, double* post_var, double* new_site_mean, double* new_site_cov,
                               double* nlml, void* ws, size_t ws_bytes, uint32_t flags, kjx_stream_t stream) {
-  if (!model_run_ok(m) || N <= 0 || !dt || !y || !peer_bufs || !ctrl || !nlml) return KJX_ERR_INVALID_ARG;
+  if (!model_run_ok(m) || N <= 0 || !dt || !y || !peer_bufs || !my_buf || !ctrl || !nlml) return KJX_ERR_INVALID_ARG;
   if ((site_mean == nullptr) != (site_cov == nullptr)) return KJX_ERR_INVALID_ARG;
   if ((post_mean == nullptr) != (post_var == nullptr)) return KJX_ERR_INVALID_ARG;
   if ((new_site_mean == nullptr) != (new_site_cov == nullptr)) return KJX_ERR_INVALID_ARG;
   if (world < 1 || world > 64 || rank < 0 || rank >= world) return KJX_ERR_INVALID_ARG;
   if (stride < (int64_t)kjx_filter_summary_doubles(m->state_dim)) return KJX_ERR_INVALID_ARG;
   ShardLink link;
-  link.peer_bufs = peer_bufs; link.ctrl = (unsigned long long*)ctrl; link.nlml_out = nlml; link.stride = stride;
+  link.peer_bufs = peer_bufs; link.my_buf = my_buf; link.ctrl = (unsigned long long*)ctrl; link.nlml_out = nlml; link.stride = stride;
   link.world = world; link.rank = rank;
   cudaStream_t st = (cudaStream_t)stream;
   KJX_SMALL_DISPATCH((shard_iteration<KJX_BLOCK_MATERN32>(m, N, dt, y, site_mean, site_cov, link, post_mean, post_var, new_site_mean, new_site_cov, ws, ws_bytes, flags, st)),

@@ -105,6 +105,7 @@ template <typename T, int D> struct ScanLevel {
 // every rank's partial at the end of its smoother — keeps the ranks within one iteration of each other).
 struct ShardLink {
   double* const* peer_bufs;      // DEVICE array [world]: receive buffer of every rank (own one included)
+  double* my_buf;                // == peer_bufs[rank], by value (no pointer chase on the kernels' critical path)
   unsigned long long* ctrl;      // DEVICE [4], zero before first use: epoch | top-scan ticket | filter ticket | smoother ticket
   double* nlml_out;              // [1] negative log marginal likelihood of the WHOLE series (every rank gets it)
   long long stride;              // doubles per summary slot (>= packed element size)
@@ -152,7 +153,7 @@ template <typename T, int D> struct FusedArgs {
   T* xf;                    // filtered moments, private layout
   const T* s_info_in;       // [D + D*D] information (eta, J) of all later shards about this shard's last state
   int vec_ok;               // every per-step array is 32-byte (fp64) / 16-byte (fp32) aligned
-  int seg;                  // elements per scan segment (64 or 128)
+  int seg0, seg1;           // elements per scan segment: level 0 (64 / 128: throughput) and levels 1, 2 (32 / 64 / 128: latency)
   int store_xf;             // keep the filtered moments (0: energy-only filter)
 };
 
@@ -166,8 +167,9 @@ __device__ __forceinline__ void load_info(const T* p, Info<T, D>& f) {
     for (int j = 0; j < D; ++j) f.J[i][j] = p[D + i * D + j];
 }
 
-constexpr int KJX_SEG_MAX = 128;         // elements per scan segment (= one block of the segment-scan kernel): 128
-                                         // for long series (fewer, fuller levels), 64 for short ones (shorter chains)
+constexpr int KJX_SEG_MAX = 128;         // most elements per scan segment (= one block of the segment-scan kernel).  Level 0
+                                         // wants long segments (fewer combines per element), the two upper levels short ones
+                                         // (they are pure latency: 32 = one element per lane, no sequential part)
 
 // Slot of element i in a per-level workspace array.  A scan warp owns KJX_SEG_PER consecutive elements per
 // lane; storing element q = PER*lane + j of a segment at j*32 + lane makes the segment a [PER][32] tile that
@@ -215,7 +217,7 @@ __global__ void __launch_bounds__(KJX_BLOCK) fused_fold_kernel(const FusedArgs<T
     T yt, R; step_site<T, D>(a, k, yt, R);
     fsum_fold_step<T, D>(mine, F, Pinf, yt, R, a.mask ? (a.mask[k] != 0) : false);
   }
-  sum_store<S>(fa.lvl[0].items, fa.lvl[0].stride, seg_slot(c, fa.seg), mine);
+  sum_store<S>(fa.lvl[0].items, fa.lvl[0].stride, seg_slot(c, fa.seg0), mine);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -231,10 +233,12 @@ template <typename S, int SEG> __device__ __forceinline__ void smem_item(const t
   SumOps<S>::unpack(v, it);
 }
 
-template <typename S, bool REVERSE> __device__ __forceinline__ S warp_scan_inclusive_rolled(const S& mine, int lane) {
+// nlanes: lanes that hold real items (the others hold the identity): offsets >= nlanes would only combine with
+// identities, so a short top level (a handful of segment totals) takes 3 steps instead of 5
+template <typename S, bool REVERSE> __device__ __forceinline__ S warp_scan_inclusive_rolled(const S& mine, int lane, int nlanes = 32) {
   S inc = mine;
 #pragma unroll 1
-  for (int off = 1; off < 32; off <<= 1) {
+  for (int off = 1; off < nlanes; off <<= 1) {
     const int src = REVERSE ? lane + off : lane - off;
     S other = sum_shfl<S>(inc, src & 31);
     const bool ok = REVERSE ? (src < 32) : (src >= 0);
@@ -256,9 +260,11 @@ __device__ __forceinline__ void segscan_pass(const T* sm, const ScanLevel<T, D>&
   S tot; item(0, tot);
 #pragma unroll 1
   for (int j = 1; j < KJX_SEG_PER; ++j) { S it; item(j, it); S r; SumOps<S>::combine(tot, it, r); tot = r; }
-  S inc = warp_scan_inclusive_rolled<S, REVERSE>(tot, lane);
+  const int64_t left = lv.n - first;
+  const int nlanes = (left >= (int64_t)SEG) ? 32 : (int)((left + KJX_SEG_PER - 1) / KJX_SEG_PER);
+  S inc = warp_scan_inclusive_rolled<S, REVERSE>(tot, lane, nlanes);
   if (!REVERSE && total_out != nullptr) {
-    S whole = sum_shfl<S>(inc, 31);
+    S whole = sum_shfl<S>(inc, nlanes - 1);     // last lane that holds real items (the scan stops at nlanes)
     if (lane == 0) sum_store<S>(total_out, total_stride, total_slot, whole);
   }
   S run = sum_shfl<S>(inc, (REVERSE ? lane + 1 : lane - 1) & 31);
@@ -294,7 +300,7 @@ template <typename T, int D, int SEG> __device__ __forceinline__ void segscan_st
 }
 
 template <typename T, int D, int SEG>
-__global__ void __launch_bounds__(64) fused_segscan_kernel(const ScanLevel<T, D> lv, T* total_out, size_t total_stride) {
+__global__ void __launch_bounds__(64) fused_segscan_kernel(const ScanLevel<T, D> lv, T* total_out, size_t total_stride, int next_seg) {
   using S = FSum<T, D>;
   constexpr int KJX_SEG = SEG;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -302,7 +308,8 @@ __global__ void __launch_bounds__(64) fused_segscan_kernel(const ScanLevel<T, D>
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t first = (int64_t)blockIdx.x * KJX_SEG;
   segscan_stage<T, D, SEG>(sm, lv, first);   // 16-byte asynchronous copies, coalesced (stride is a multiple of the segment)
-  if (warp == 0) segscan_pass<T, D, false, SEG>(sm, lv, first, lane, total_out, total_stride, seg_slot(blockIdx.x, SEG));
+  // the total goes where the NEXT level (segments of next_seg) will stage it from
+  if (warp == 0) segscan_pass<T, D, false, SEG>(sm, lv, first, lane, total_out, total_stride, seg_slot(blockIdx.x, next_seg));
   else segscan_pass<T, D, true, SEG>(sm, lv, first, lane, nullptr, 0, 0);
 }
 
@@ -318,24 +325,31 @@ __global__ void __launch_bounds__(64) fused_segscan_top_kernel(const ScanLevel<T
   T* sm = reinterpret_cast<T*>(smem_raw);                  // [NS][SEG]
   __shared__ int s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t first = (int64_t)blockIdx.x * SEG;
-  segscan_stage<T, D, SEG>(sm, lv1, first);
-  if (warp == 0) segscan_pass<T, D, false, SEG>(sm, lv1, first, lane, lv2.items, lv2.stride, seg_slot(blockIdx.x, SEG));
-  else segscan_pass<T, D, true, SEG>(sm, lv1, first, lane, nullptr, 0, 0);
-  // last block done?
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned long long t = atomicAdd(ticket, 1ull);
-    s_last = (t == (unsigned long long)gridDim.x - 1ull) ? 1 : 0;
-    if (s_last) *ticket = 0ull;                            // self-resetting: the next launch starts from zero again
+  // ONE copy of the scan code serves both levels (rolled loop): the level-2 pass is executed once, by one block, and
+  // would otherwise run from cold instruction memory (measured: 32 us instead of 14 for the two levels)
+#pragma unroll 1
+  for (int stage = 0; stage < 2; ++stage) {
+    const ScanLevel<T, D>& lv = stage ? lv2 : lv1;
+    const int64_t first = stage ? 0 : (int64_t)blockIdx.x * SEG;
+    T* tot = stage ? total_out : lv2.items;
+    const size_t tstride = stage ? 1 : lv2.stride;
+    const int64_t tslot = stage ? 0 : seg_slot(blockIdx.x, SEG);
+    segscan_stage<T, D, SEG>(sm, lv, first);               // cp.async.cg reads through L2: sees every block's total
+    if (warp == 0) segscan_pass<T, D, false, SEG>(sm, lv, first, lane, tot, tstride, tslot);
+    else segscan_pass<T, D, true, SEG>(sm, lv, first, lane, nullptr, 0, 0);
+    if (stage == 0) {                                      // last block done?
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const unsigned long long t = atomicAdd(ticket, 1ull);
+        s_last = (t == (unsigned long long)gridDim.x - 1ull) ? 1 : 0;
+        if (s_last) *ticket = 0ull;                        // self-resetting: the next launch starts from zero again
+      }
+      __syncthreads();
+      if (!s_last) return;
+      __threadfence();
+    }
   }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  segscan_stage<T, D, SEG>(sm, lv2, 0);                    // cp.async.cg reads through L2: sees every block's total
-  if (warp == 0) segscan_pass<T, D, false, SEG>(sm, lv2, 0, lane, total_out, 1, 0);
-  else segscan_pass<T, D, true, SEG>(sm, lv2, 0, lane, nullptr, 0, 0);
   if constexpr (SHARDED && std::is_same<T, double>::value) {
     __syncthreads();                                       // total_out (written by lane 0 of warp 0) is visible to the block
     const int r = threadIdx.x;
@@ -357,8 +371,8 @@ __global__ void __launch_bounds__(64) fused_segscan_top_kernel(const ScanLevel<T
 // !PLAIN adds, with runtime checks: masked (predict-only) steps, energy-only runs (no filtered moments kept) and
 // writing the initialised sites — the stand-alone kjx_filter and the prediction path.
 // SHARDED (fp64): the filtered state entering the shard is not read from f_state_in but folded, by thread 0 of every
-// block, from the elements the earlier shards published into this rank's receive buffer (waiting for them if need be);
-// the block that finishes last sums the per-block log-likelihoods and publishes the shard's partial nlml to every rank.
+// block, from the elements the earlier shards published into this rank's receive buffer (waiting for them if need be).
+// The per-block log-likelihood sums are picked up by the smoother kernel's extra block.
 template <typename T, int KIND, bool GAUSS_EP, bool VEC, bool PLAIN, bool SHARDED = false>
 __global__ void __launch_bounds__(KJX_BLOCK, KJX_R3_MINB) fused_filter_kernel(const FusedArgs<T, BlockDim<KIND>::D> fa) {
   constexpr int D = BlockDim<KIND>::D;
@@ -367,7 +381,6 @@ __global__ void __launch_bounds__(KJX_BLOCK, KJX_R3_MINB) fused_filter_kernel(co
   const SmallArgs<T, D>& a = fa.a;
   __shared__ T red[KJX_BLOCK / 32];
   __shared__ T st_in[D + D * D];
-  __shared__ int s_last;
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t s0 = c * a.L;
   const int64_t s1 = (s0 + a.L < a.N) ? s0 + a.L : a.N;
@@ -376,14 +389,15 @@ __global__ void __launch_bounds__(KJX_BLOCK, KJX_R3_MINB) fused_filter_kernel(co
   if constexpr (SHARDED && std::is_same<T, double>::value) {
     if (threadIdx.x == 0) {
       const ShardLink& l = fa.link;
-      const unsigned long long e = l.ctrl[0] + 1ull;
-      const int par = (int)(e & 1ull);
-      double* mybuf = l.peer_bufs[l.rank];
       FiltState<double, D> x0;
 #pragma unroll
       for (int i = 0; i < D; ++i) { x0.m[i] = 0.0; for (int j = 0; j < D; ++j) x0.P[i][j] = Pinf[i][j]; }    // sde_gp.py:265
+      if (l.rank > 0) {                                      // shard 0 starts from the prior: nothing to wait for
+        const unsigned long long e = l.ctrl[0] + 1ull;
+        const int par = (int)(e & 1ull);
 #pragma unroll 1
-      for (int r = 0; r < l.rank; ++r) { FSum<double, D> sr; link_wait_element<D>(l, mybuf, par, e, r, sr); fsum_apply<double, D>(sr, x0); }
+        for (int r = 0; r < l.rank; ++r) { FSum<double, D> sr; link_wait_element<D>(l, l.my_buf, par, e, r, sr); fsum_apply<double, D>(sr, x0); }
+      }
 #pragma unroll
       for (int i = 0; i < D; ++i) { st_in[i] = x0.m[i]; for (int j = 0; j < D; ++j) st_in[D + i * D + j] = x0.P[i][j]; }
     }
@@ -392,9 +406,9 @@ __global__ void __launch_bounds__(KJX_BLOCK, KJX_R3_MINB) fused_filter_kernel(co
   if (s0 < s1) {
     FiltState<T, D> x; load_state<T, D>(SHARDED ? st_in : a.f_state_in, x);
     {   // everything before this chunk: super-segments, segments, chunks (outermost first)
-      int64_t idx[3] = {c, c / fa.seg, c / ((int64_t)fa.seg * fa.seg)};
+      int64_t idx[3] = {c, c / fa.seg0, c / ((int64_t)fa.seg0 * fa.seg1)};
 #pragma unroll 1
-      for (int l = 2; l >= 0; --l) { FS p; sum_load<FS>(fa.lvl[l].prefix, fa.lvl[l].stride, seg_slot(idx[l], fa.seg), p); fsum_apply<T, D>(p, x); }
+      for (int l = 2; l >= 0; --l) { FS p; sum_load<FS>(fa.lvl[l].prefix, fa.lvl[l].stride, seg_slot(idx[l], l ? fa.seg1 : fa.seg0), p); fsum_apply<T, D>(p, x); }
     }
     T* xf = fa.xf + ((c >> 5) * (int64_t)a.L * NP) * 32 + (c & 31);
     const T* ysrc = a.gaussian_init ? a.y : a.site_mean;
@@ -467,35 +481,6 @@ __global__ void __launch_bounds__(KJX_BLOCK, KJX_R3_MINB) fused_filter_kernel(co
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
     a.block_nlml[blockIdx.x] = t;
   }
-  if constexpr (SHARDED && std::is_same<T, double>::value) {
-    const ShardLink& l = fa.link;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const unsigned long long t = atomicAdd(l.ctrl + 2, 1ull);
-      s_last = (t == (unsigned long long)gridDim.x - 1ull) ? 1 : 0;
-      if (s_last) l.ctrl[2] = 0ull;
-    }
-    __syncthreads();
-    if (s_last) {                                            // fixed-order sum of the per-block values (deterministic)
-      __threadfence();
-      double p = 0.0;
-      for (int64_t b = threadIdx.x; b < (int64_t)gridDim.x; b += blockDim.x) p += __ldcg(a.block_nlml + b);
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) p += __shfl_down_sync(0xffffffffu, p, off);
-      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = p;
-      __syncthreads();
-      if ((int)threadIdx.x < l.world) {
-        double t = 0.0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
-        const unsigned long long e = l.ctrl[0] + 1ull;
-        const int par = (int)(e & 1ull), r = threadIdx.x;
-        *link_nlml(l.peer_bufs[r], l, par, l.rank) = -t;      // sde_gp.py:301  nlml -= sum(log_lik_n)
-        __threadfence_system();
-        st_release_sys(link_nlml_flag(l.peer_bufs[r], l, par, l.rank), e);
-      }
-    }
-  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -515,8 +500,8 @@ __device__ __forceinline__ void smoothed_outputs(const SmallArgs<T, D>& a, const
 }
 
 // SHARDED (fp64): the information of the later shards about this shard's last state is folded, by thread 0 of every
-// block, from the elements in the receive buffer; the block that finishes last collects the shards' partial nlml values
-// (rank order: every rank gets the same bits), writes the total and closes the epoch.
+// block, from the elements in the receive buffer.  The grid has ONE EXTRA block that exchanges the shards' partial nlml
+// values while the others work; the block that finishes last closes the epoch.
 template <typename T, int KIND, bool GAUSS_EP, bool VEC, bool SHARDED = false>
 __global__ void __launch_bounds__(KJX_BLOCK, KJX_R4_MINB) fused_smoother_kernel(const FusedArgs<T, BlockDim<KIND>::D> fa) {
   constexpr int D = BlockDim<KIND>::D;
@@ -529,14 +514,45 @@ __global__ void __launch_bounds__(KJX_BLOCK, KJX_R4_MINB) fused_smoother_kernel(
   const int64_t s0 = c * a.L;
   const int64_t s1 = (s0 + a.L < a.N) ? s0 + a.L : a.N;
   if constexpr (SHARDED && std::is_same<T, double>::value) {
-    if (threadIdx.x == 0) {
-      const ShardLink& l = fa.link;
+    const ShardLink& l = fa.link;
+    if (blockIdx.x == gridDim.x - 1) {
+      // The EXTRA block (no chunks): the nlml exchange, off everybody's critical path.  Fixed-order sum of the filter
+      // kernel's per-block values -> this shard's partial, stored into every rank's buffer; then the partials of all
+      // shards are summed in rank order (every rank gets the same bits).
+      __shared__ double red[KJX_BLOCK / 32];
+      const int64_t nb = (int64_t)gridDim.x - 1;             // blocks of the filter kernel
+      double p = 0.0;
+      for (int64_t b = threadIdx.x; b < nb; b += blockDim.x) p += a.block_nlml[b];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) p += __shfl_down_sync(0xffffffffu, p, off);
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = p;
+      __syncthreads();
       const unsigned long long e = l.ctrl[0] + 1ull;
       const int par = (int)(e & 1ull);
-      double* mybuf = l.peer_bufs[l.rank];
+      if ((int)threadIdx.x < l.world) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+        const int r = threadIdx.x;
+        *link_nlml(l.peer_bufs[r], l, par, l.rank) = -t;      // sde_gp.py:301  nlml -= sum(log_lik_n)
+        __threadfence_system();
+        st_release_sys(link_nlml_flag(l.peer_bufs[r], l, par, l.rank), e);
+      }
+      if (threadIdx.x == 0) {
+        double total = 0.0;
+        for (int r = 0; r < l.world; ++r) {
+          wait_flag_sys(link_nlml_flag(l.my_buf, l, par, r), e);
+          total += ld_relaxed_sys(link_nlml(l.my_buf, l, par, r));
+        }
+        l.nlml_out[0] = total;
+      }
+    } else if (threadIdx.x == 0) {
       Info<double, D> f; info_zero<double, D>(f);
+      if (l.rank + 1 < l.world) {                            // the last shard ends the series: no later information
+        const unsigned long long e = l.ctrl[0] + 1ull;
+        const int par = (int)(e & 1ull);
 #pragma unroll 1
-      for (int r = l.world - 1; r > l.rank; --r) { FSum<double, D> sr; link_wait_element<D>(l, mybuf, par, e, r, sr); fsum_combine_info<double, D>(sr, f, f); }
+        for (int r = l.world - 1; r > l.rank; --r) { FSum<double, D> sr; link_wait_element<D>(l, l.my_buf, par, e, r, sr); fsum_combine_info<double, D>(sr, f, f); }
+      }
 #pragma unroll
       for (int i = 0; i < D; ++i) { info_in[i] = f.eta[i]; for (int j = 0; j < D; ++j) info_in[D + i * D + j] = f.J[i][j]; }
     }
@@ -554,9 +570,9 @@ __global__ void __launch_bounds__(KJX_BLOCK, KJX_R4_MINB) fused_smoother_kernel(
   {
     Info<T, D> info; load_info<T, D>(SHARDED ? info_in : fa.s_info_in, info);
     {   // everything after this chunk
-      int64_t idx[3] = {c, c / fa.seg, c / ((int64_t)fa.seg * fa.seg)};
+      int64_t idx[3] = {c, c / fa.seg0, c / ((int64_t)fa.seg0 * fa.seg1)};
 #pragma unroll 1
-      for (int l = 2; l >= 0; --l) { FS q; sum_load<FS>(fa.lvl[l].suffix, fa.lvl[l].stride, seg_slot(idx[l], fa.seg), q); fsum_combine_info<T, D>(q, info, info); }
+      for (int l = 2; l >= 0; --l) { FS q; sum_load<FS>(fa.lvl[l].suffix, fa.lvl[l].stride, seg_slot(idx[l], l ? fa.seg1 : fa.seg0), q); fsum_combine_info<T, D>(q, info, info); }
     }
     xf_load<T, D>(xf + (k - s0) * NP * 32, x.m, x.P);
     info_smooth<T, D>(info, x);
@@ -622,19 +638,10 @@ __global__ void __launch_bounds__(KJX_BLOCK, KJX_R4_MINB) fused_smoother_kernel(
       s_last = (t == (unsigned long long)gridDim.x - 1ull) ? 1 : 0;
     }
     __syncthreads();
-    if (s_last && threadIdx.x == 0) {
-      const unsigned long long e = l.ctrl[0] + 1ull;
-      const int par = (int)(e & 1ull);
-      double* mybuf = l.peer_bufs[l.rank];
-      double total = 0.0;
-      for (int r = 0; r < l.world; ++r) {
-        wait_flag_sys(link_nlml_flag(mybuf, l, par, r), e);
-        total += ld_relaxed_sys(link_nlml(mybuf, l, par, r));
-      }
-      l.nlml_out[0] = total;
+    if (s_last && threadIdx.x == 0) {                        // every block (the extra one included) is through
       l.ctrl[3] = 0ull;
       __threadfence();
-      l.ctrl[0] = e;                                         // epoch closed: every block of this iteration has read it
+      l.ctrl[0] = l.ctrl[0] + 1ull;                          // epoch closed
     }
   }
 }

@@ -41,6 +41,7 @@ class PeerExchange(object):
             self.buf = torch.zeros(n, dtype=torch.float64, device=device)
             ptrs = [self.buf.data_ptr()]
         self.ptrs = torch.tensor(ptrs, dtype=torch.int64, device=device)
+        self.my_ptr = int(ptrs[rank])                                     # this rank's own buffer as every kernel addresses it
         self.epoch = torch.zeros(1, dtype=torch.int64, device=device)     # kjx_exchange_fold (separate-kernel form)
         self.ctrl = torch.zeros(4, dtype=torch.int64, device=device)      # kjx_sharded_iteration: epoch + three tickets
         self.world, self.rank = world, rank
@@ -100,7 +101,7 @@ class ShardedIteration(object):
         if self.linked:
             flags = 0 if update_sites else _lib.FLAG_NO_SITE_UPDATE
             _lib.check(L.kjx_sharded_iteration_f64(m, N, p(self.dt), p(self.y), p(self.site_mean), p(self.site_var),
-                                                   p(self.peer.ptrs), C.c_int64(self.peer.STRIDE), self.world, self.rank,
+                                                   p(self.peer.ptrs), C.c_void_p(self.peer.my_ptr), C.c_int64(self.peer.STRIDE), self.world, self.rank,
                                                    p(self.peer.ctrl), p(self.post_mean), p(self.post_var),
                                                    p(self.new_site_mean), p(self.new_site_var), p(self.nlml_all), p(self.ws),
                                                    wsb, C.c_uint32(flags), st), "kjx_sharded_iteration")
@@ -145,10 +146,11 @@ class ShardedIteration(object):
 
 
 class GraphedIteration(object):
-    """Two CUDA graphs (sites ping -> pong, pong -> ping) replaying ShardedIteration.iteration() without any host
-    work per step: at 8 GPUs a shard's iteration is ~200 us of device time, the same order as the Python / ctypes /
-    NCCL launch path, so the launch sequence is captured once (the all-gather included) and replayed."""
-    def __init__(self, it, reduce_nlml=None):
+    """CUDA graphs replaying ShardedIteration.iteration() without any host work per step: at 8 GPUs a shard's iteration
+    is ~200 us of device time, the same order as the Python / ctypes launch path, so the launch sequence is captured
+    once and replayed.  The sites ping-pong between two buffers, so the natural unit is a PAIR of iterations; `pairs`
+    of them go into one graph (replay_many), plus two single-iteration graphs (ping -> pong, pong -> ping) for replay()."""
+    def __init__(self, it, reduce_nlml=None, pairs=0):
         self.it, self.graphs, self.parity = it, [], 0
         assert it.site_mean is not None
         stream = torch.cuda.Stream(device=it.device)
@@ -164,12 +166,24 @@ class GraphedIteration(object):
             with torch.cuda.graph(g, stream=stream):
                 self.nlml.append(it.iteration(reduce_nlml=reduce_nlml))
             self.graphs.append(g)
+        self.pairs, self.many = int(pairs), None
+        if self.pairs > 0:
+            self.many = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.many, stream=stream):
+                for _ in range(2 * self.pairs):
+                    self.many_nlml = it.iteration(reduce_nlml=reduce_nlml)
 
     def replay(self):
         self.graphs[self.parity].replay()
         out = self.nlml[self.parity]
         self.parity ^= 1
         return out
+
+    def replay_many(self):
+        """2 * pairs iterations in one graph launch (only from parity 0: an even number of iterations so far)."""
+        assert self.many is not None and self.parity == 0
+        self.many.replay()
+        return self.many_nlml
 
 
 def split_series(dt, y, world):
