@@ -47,6 +47,7 @@ int env_knob(const char* name) {
 int knob_chunk() { static const int v = env_knob("KJX_CHUNK"); return v; }
 int knob_threads() { static const int v = env_knob("KJX_THREADS"); return v; }
 int knob_seg() { static const int v = env_knob("KJX_SEG"); return v; }
+int knob_balance() { static const int v = env_knob("KJX_BALANCE"); return v; }
 int knob_seg1() { static const int v = env_knob("KJX_SEG1"); return v; }
 
 // steps per thread chunk: long chunks amortise the O(d^3) scan combines, short ones keep every SM
@@ -75,8 +76,48 @@ int pick_threads(int64_t nchunks) {
   return KJX_BLOCK;
 }
 
+// Chunking of the FUSED kernels (fold / filter / smoother: one thread per chunk, 128-thread blocks).  The smoother runs 3
+// blocks per SM (168 registers), the fold and the filter 4; a kernel ends with its fullest SM, so the chunk count is made
+// a whole number of waves: a multiple of SMs x 3 blocks (and of SMs x 12 when that leaves 32..96 steps per chunk, which
+// is whole waves for all three kernels).  An exact count needs two chunk lengths, L and L - 4 (both multiples of 4: every
+// chunk starts on a 32-byte boundary of the per-step arrays).  Measured on a 2^21-step shard: 12 warps on every SM instead
+// of 12 on some and 8 on others.  Short series fall back to equal chunks of pick_chunk().
+struct ChunkPlan { int L1, L2; int64_t nbig, nchunks; };
+ChunkPlan plan_chunks(int64_t N) {
+  ChunkPlan p;
+  const int64_t max_chunks = (int64_t)KJX_SEG_MAX * KJX_SEG_MAX * KJX_SEG_MAX;
+  const int64_t wave3 = (int64_t)sm_count() * 3, wave12 = (int64_t)sm_count() * 12;      // blocks
+  int64_t blocks = 0;
+  // (off by default: on B200 it measured no faster than equal chunks — 2^21 steps: 192 vs 192.5 us per iteration — and
+  // slower at 2^24, where it picks 76 / 72-step chunks: 1.185 vs 1.138 ms; KJX_BALANCE=1 turns it on for experiments)
+  if (knob_balance() == 1 && knob_chunk() == 0 && N >= wave3 * KJX_BLOCK * 8) {
+    // whole waves with about 64 steps per chunk; prefer the common multiple when the chunks stay reasonable
+    const double want = (double)N / (64.0 * KJX_BLOCK);
+    const int64_t k12 = std::max<int64_t>(1, (int64_t)(want / wave12 + 0.5));
+    const double l12 = (double)N / (double)(k12 * wave12 * KJX_BLOCK);
+    if (l12 >= 32.0 && l12 <= 96.0) blocks = k12 * wave12;
+    else blocks = std::max<int64_t>(1, (int64_t)(want / wave3 + 0.5)) * wave3;
+    if (blocks * KJX_BLOCK > max_chunks) blocks = 0;
+  }
+  if (blocks == 0) {                                          // equal chunks
+    p.L1 = p.L2 = pick_chunk(N);
+    p.nchunks = std::max<int64_t>(1, (N + p.L1 - 1) / p.L1);
+    p.nbig = p.nchunks;
+    return p;
+  }
+  p.nchunks = blocks * KJX_BLOCK;
+  const int64_t q = (N + 3) / 4;                              // groups of 4 steps to hand out
+  const int64_t base = q / p.nchunks, extra = q % p.nchunks; // `extra` chunks get one group more
+  p.L1 = (int)(4 * (base + (extra ? 1 : 0)));
+  p.L2 = (int)(4 * base);
+  p.nbig = extra ? extra : p.nchunks;
+  if (p.L2 < 4) { p.L1 = p.L2 = pick_chunk(N); p.nchunks = std::max<int64_t>(1, (N + p.L1 - 1) / p.L1); p.nbig = p.nchunks; }
+  return p;
+}
+
 template <typename T, int D> struct SmallLayout {
-  int L; int64_t nchunks, nblocks; size_t cstride, bstride;
+  int L; int64_t nchunks, nblocks; size_t cstride, bstride;   // equal chunks: the stand-alone smoother's kernels
+  ChunkPlan plan;                   // fused kernels
   int threads; int64_t fblocks;     // fused kernels: threads per block (32 / 64 / 128) and blocks
   size_t off_ftp, off_fbt, off_fbp, off_fst, off_sts, off_sbt, off_sbs, off_sst, off_nl, off_fin, off_sin;
   size_t off_info, off_xf, off_lvl[3][3], lvl_stride[3], total;
@@ -87,35 +128,37 @@ template <typename T, int D> struct SmallLayout {
     L = pick_chunk(N);
     nchunks = std::max<int64_t>(1, (N + L - 1) / L);
     nblocks = (nchunks + KJX_BLOCK - 1) / KJX_BLOCK;
-    threads = pick_threads(nchunks);
-    fblocks = (nchunks + threads - 1) / threads;
+    plan = plan_chunks(N);
+    threads = pick_threads(plan.nchunks);
+    fblocks = (plan.nchunks + threads - 1) / threads;
+    const int64_t fchunks = plan.nchunks;
     cstride = round_up((size_t)nchunks, 128);
     bstride = round_up((size_t)nblocks, 32);
     size_t o = 0;
     auto take = [&](size_t n) { size_t r = o; o += round_up(n * sizeof(T), 256); return r; };
     off_ftp = take(FNS * cstride); off_fbt = take(FNS * bstride); off_fbp = take(FNS * bstride); off_fst = take(FNS);
     off_sts = take(SNS * cstride); off_sbt = take(SNS * bstride); off_sbs = take(SNS * bstride); off_sst = take(SNS);
-    off_nl = take(round_up((size_t)((nchunks + 31) / 32), 32)); off_fin = take(D + D * D); off_sin = take(D + D * D);
+    off_nl = take(round_up((size_t)((std::max(nchunks, fchunks) + 31) / 32), 32)); off_fin = take(D + D * D); off_sin = take(D + D * D);
     off_info = take(D + D * D);
     // three scan levels of the fused path: elements, exclusive prefix, exclusive suffix (strides = whole segments)
     // segments of 64 while three levels of 64 hold every chunk (shorter dependent chains), else 128
     // level 0: long segments (3 + 5 + 3 combines per 128 elements instead of 1 + 5 + 1 per 64: less FP64 work per
     // element; measured 16.5 vs 20.5 us at 52 429 chunks) unless the series is short; levels 1 and 2 are one or a few
     // blocks each, i.e. pure latency: the shortest segments that still reach the top in three levels
-    seg0 = (nchunks >= 8192) ? 128 : 64;
+    seg0 = (fchunks >= 8192) ? 128 : 64;
     if (knob_seg() == 64 || knob_seg() == 128) seg0 = knob_seg();
     seg1 = 128;
-    for (int c : {64, 32}) if ((int64_t)seg0 * c * c >= nchunks) seg1 = c;
+    for (int c : {64, 32}) if ((int64_t)seg0 * c * c >= fchunks) seg1 = c;
     if (knob_seg1() == 32 || knob_seg1() == 64 || knob_seg1() == 128) seg1 = std::max(seg1, knob_seg1());
-    if ((int64_t)seg0 * seg1 * seg1 < nchunks) { seg0 = 128; seg1 = 128; }
-    int64_t n = nchunks;
+    if ((int64_t)seg0 * seg1 * seg1 < fchunks) { seg0 = 128; seg1 = 128; }
+    int64_t n = fchunks;
     for (int l = 0; l < 3; ++l) {
       lvl_n[l] = n; lvl_stride[l] = round_up((size_t)n, KJX_SEG_MAX);
       for (int q = 0; q < 3; ++q) off_lvl[l][q] = take(FNS * lvl_stride[l]);
       n = (n + (l ? seg1 : seg0) - 1) / (l ? seg1 : seg0);
     }
     // filtered moments between the fused filter and smoother passes: [warp][step][element][lane]
-    off_xf = take(cstride * (size_t)L * Packed<D>::NP);
+    off_xf = take(round_up((size_t)fchunks, 128) * (size_t)plan.L1 * Packed<D>::NP);
     total = o;
   }
 };
@@ -138,6 +181,7 @@ void bind_fused(FusedArgs<T, D>& fa, const SmallLayout<T, D>& lay, void* ws) {
   bind_workspace<T, D>(fa.a, lay, ws);
   fa.s_info_in = (T*)(w + lay.off_info); fa.xf = (T*)(w + lay.off_xf);
   fa.seg0 = lay.seg0; fa.seg1 = lay.seg1;
+  fa.a.L = lay.plan.L1; fa.L2 = lay.plan.L2; fa.nbig = lay.plan.nbig; fa.a.nchunks = lay.plan.nchunks;
   for (int l = 0; l < 3; ++l) {
     fa.lvl[l].items = (T*)(w + lay.off_lvl[l][0]); fa.lvl[l].prefix = (T*)(w + lay.off_lvl[l][1]);
     fa.lvl[l].suffix = (T*)(w + lay.off_lvl[l][2]); fa.lvl[l].stride = lay.lvl_stride[l]; fa.lvl[l].n = lay.lvl_n[l];
@@ -203,7 +247,7 @@ struct Fused {
     nthread_blocks = lay.fblocks;
     ngroups = 0;
     const size_t al = sizeof(T) * 4;
-    fa.vec_ok = (lay.L % 4 == 0) && aligned_to(dt, al) && aligned_to(y, al) && aligned_to(site_mean, al) && aligned_to(site_var, al);
+    fa.vec_ok = (lay.plan.L1 % 4 == 0) && (lay.plan.L2 % 4 == 0) && aligned_to(dt, al) && aligned_to(y, al) && aligned_to(site_mean, al) && aligned_to(site_var, al);
   }
   unsigned grid() const { return (unsigned)lay.fblocks; }
   unsigned threads() const { return (unsigned)lay.threads; }
@@ -288,11 +332,12 @@ struct Fused {
 
 // private packed filtered moments -> the reference's dense [N,d,1] / [N,d,d] layout (optional output of kjx_run)
 template <typename T, int D>
-__global__ void unpack_filtered_kernel(const T* __restrict__ xf, int64_t N, int L, T* __restrict__ fm, T* __restrict__ fP) {
+__global__ void unpack_filtered_kernel(const T* __restrict__ xf, int64_t N, int L, int L2, int64_t nbig, T* __restrict__ fm, T* __restrict__ fP) {
   constexpr int NP = Packed<D>::NP;
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= N) return;
-  const int64_t c = k / L, i = k % L;
+  const int64_t kb = nbig * L;                               // steps covered by the chunks of length L
+  const int64_t c = (k < kb) ? k / L : nbig + (k - kb) / L2, i = (k < kb) ? k % L : (k - kb) % L2;
   const T* base = xf + (((c >> 5) * (int64_t)L + i) * NP) * 32 + (c & 31);
   T m[D], P[D][D];
   int e = 0;
@@ -341,7 +386,7 @@ int small_filter(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const
     launch_set_prior_state<T, D>((T*)f.fa.a.f_state_in, m, st);
     f.filter(st, /*plain=*/false);
     nlml_reduce_kernel<T><<<1, 256, 0, st>>>(f.fa.a.block_nlml, f.nthread_blocks, nlml);
-    if (filt_mean) unpack_filtered_kernel<T, D><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(f.fa.xf, N, f.lay.L, filt_mean, filt_cov);
+    if (filt_mean) unpack_filtered_kernel<T, D><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(f.fa.xf, N, f.lay.plan.L1, f.lay.plan.L2, f.lay.plan.nbig, filt_mean, filt_cov);
   }
   KJX_CUDA_CHECK(cudaGetLastError());
   return KJX_OK;
@@ -423,7 +468,7 @@ int small_run(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const T*
     if (nlml) nlml_reduce_kernel<T><<<1, 256, 0, st>>>(f.fa.a.block_nlml, f.nthread_blocks, nlml);
     f.smoother(post_mean, post_var, new_site_mean, new_site_var, update, st);
     if (filt_mean && filt_cov)
-      unpack_filtered_kernel<T, D><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(f.fa.xf, N, f.lay.L, filt_mean, filt_cov);
+      unpack_filtered_kernel<T, D><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(f.fa.xf, N, f.lay.plan.L1, f.lay.plan.L2, f.lay.plan.nbig, filt_mean, filt_cov);
   }
   KJX_CUDA_CHECK(cudaGetLastError());
   return KJX_OK;

@@ -153,6 +153,8 @@ template <typename T, int D> struct FusedArgs {
   T* xf;                    // filtered moments, private layout
   const T* s_info_in;       // [D + D*D] information (eta, J) of all later shards about this shard's last state
   int vec_ok;               // every per-step array is 32-byte (fp64) / 16-byte (fp32) aligned
+  int L2; int64_t nbig;     // chunks [0, nbig) have a.L steps, chunks [nbig, nchunks) have L2 (= a.L - 4 or a.L) steps:
+                            // two lengths make the chunk count whatever fills the SMs evenly (see plan_chunks)
   int seg0, seg1;           // elements per scan segment: level 0 (64 / 128: throughput) and levels 1, 2 (32 / 64 / 128: latency)
   int store_xf;             // keep the filtered moments (0: energy-only filter)
 };
@@ -165,6 +167,17 @@ __device__ __forceinline__ void load_info(const T* p, Info<T, D>& f) {
   for (int i = 0; i < D; ++i)
 #pragma unroll
     for (int j = 0; j < D; ++j) f.J[i][j] = p[D + i * D + j];
+}
+
+// steps [s0, s1) of thread chunk c
+template <typename T, int D>
+__device__ __forceinline__ void chunk_range(const FusedArgs<T, D>& fa, int64_t c, int64_t& s0, int64_t& s1) {
+  const int64_t L1 = fa.a.L;
+  const bool big = c < fa.nbig;
+  s0 = big ? c * L1 : fa.nbig * L1 + (c - fa.nbig) * (int64_t)fa.L2;
+  s1 = s0 + (big ? L1 : (int64_t)fa.L2);
+  if (s1 > fa.a.N) s1 = fa.a.N;
+  if (s0 > fa.a.N) s0 = fa.a.N;
 }
 
 constexpr int KJX_SEG_MAX = 128;         // most elements per scan segment (= one block of the segment-scan kernel).  Level 0
@@ -190,8 +203,7 @@ __global__ void __launch_bounds__(KJX_BLOCK) fused_fold_kernel(const FusedArgs<T
   const SmallArgs<T, D>& a = fa.a;
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= a.nchunks) return;
-  const int64_t s0 = c * a.L;
-  const int64_t s1 = (s0 + a.L < a.N) ? s0 + a.L : a.N;
+  int64_t s0, s1; chunk_range<T, D>(fa, c, s0, s1);
   T Pinf[D][D]; load_pinf<T, D>(a.prior, Pinf);
   S mine; fsum_identity<T, D>(mine);
   const T* ysrc = a.gaussian_init ? a.y : a.site_mean;
@@ -382,8 +394,7 @@ __global__ void __launch_bounds__(KJX_BLOCK, KJX_R3_MINB) fused_filter_kernel(co
   __shared__ T red[KJX_BLOCK / 32];
   __shared__ T st_in[D + D * D];
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t s0 = c * a.L;
-  const int64_t s1 = (s0 + a.L < a.N) ? s0 + a.L : a.N;
+  int64_t s0, s1; chunk_range<T, D>(fa, c, s0, s1);
   T Pinf[D][D]; load_pinf<T, D>(a.prior, Pinf);
   T nl = T(0);
   if constexpr (SHARDED && std::is_same<T, double>::value) {
@@ -511,8 +522,7 @@ __global__ void __launch_bounds__(KJX_BLOCK, KJX_R4_MINB) fused_smoother_kernel(
   __shared__ T info_in[D + D * D];
   __shared__ int s_last;
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t s0 = c * a.L;
-  const int64_t s1 = (s0 + a.L < a.N) ? s0 + a.L : a.N;
+  int64_t s0, s1; chunk_range<T, D>(fa, c, s0, s1);
   if constexpr (SHARDED && std::is_same<T, double>::value) {
     const ShardLink& l = fa.link;
     if (blockIdx.x == gridDim.x - 1) {

@@ -58,6 +58,15 @@ template <typename T> struct GenArgs {
   T* in_eta; T* in_J;      // [nchunks][d], [nchunks][d^2]  information of everything after every chunk (equilibrated)
   T* gsum;                 // [ngroups][3 d^2 + 2 d]   group elements of the two-level boundary walk
   T* chunk_nlml;           // [nchunks]
+  // per-call precomputation (generic_rows_kernel): the non-zeros of every row of A(dt[n]) for all steps, so the chain
+  // kernels load 4 d scalars per step instead of evaluating exp / sincos in double on their critical path
+  const T* rows;           // [N + 1][d][4]; slot N is A(0) = I (the smoother's transition out of the last step, sde_gp.py:337)
+  const int* c0n_g;        // [d]  first column | nnz << 24 of every row (step-invariant)
+  // batched per-step work taken OUT of the chains (steady-state iterations, where it does not feed the recursion)
+  T* pred_mean; T* pred_var;   // [N] filter predictive H m_, H P_ H^T -> log-likelihood terms by generic_loglik_kernel
+  T* post_mean; T* post_var;   // [N] smoothed marginal H m, H P H^T -> site update by site_update_kernel
+  // RTS recursion in affine form (generic_gain_kernel): P_s[n] = Gt[n]^T P_s[n+1] Gt[n] + Lc[n],  m_s[n] = Gt[n]^T m_s[n+1] + gc[n]
+  T* Lc; T* gc;            // [N][d][ld] (padded tile layout, like the gains) and [N][d]
   unsigned char* gscratch; // d > KJX_GEN_DMAX: per-CTA working set in global memory instead of shared memory
   size_t gscratch_stride;
 };
@@ -102,6 +111,28 @@ __device__ __forceinline__ void build_rows(const DiscArgs& da, int d, T dt, T* v
     for (int q = 0; q < 4; ++q) vals[r * 4 + q] = v[q];
   }
 }
+// all rows of all steps, once per call
+template <typename T>
+__global__ void __launch_bounds__(256) generic_rows_kernel(const DiscArgs da, int d, int64_t N, const T* __restrict__ dt,
+                                                           T* __restrict__ rows, int* __restrict__ c0n_g) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (N + 1) * d) return;
+  const int64_t n = e / d; const int r = (int)(e - n * d);
+  int c0, nnz; T v[4] = {T(0), T(0), T(0), T(0)};
+  transition_row<T>(da, r, (n < N) ? dt[n] : T(0), c0, nnz, v);
+  if (n == 0) c0n_g[r] = c0 | (nnz << 24);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) rows[e * 4 + q] = v[q];
+}
+// the precomputed rows of step `idx` -> vals (all threads; caller synchronises)
+template <typename T>
+__device__ __forceinline__ void fetch_rows(const GenArgs<T>& g, int64_t idx, T* vals) {
+  const T* src = g.rows + idx * 4 * (int64_t)g.d;
+  KJX_GEN_VEC(e, 4 * g.d) vals[e] = src[e];
+}
+template <typename T>
+__device__ __forceinline__ void fetch_c0n(const GenArgs<T>& g, int* c0n) { KJX_GEN_VEC(r, g.d) c0n[r] = g.c0n_g[r]; }
+
 // Element-wise pass over a d x d tile with (row = warp, column = lane): every thread first issues the loads of up to 4
 // rows, then stores, so the loads are in flight together (a plain load/store loop serialises on possible aliasing).
 template <typename T, class LoadF, class StoreF>
@@ -563,8 +594,9 @@ template <typename T> __device__ void chol_blocked(const GenLayout& L, T* W, T* 
 
 // X <- solve(L L^T, X) for the ncol right-hand-side columns of X (utils.py:30) with the tile chol_blocked left behind:
 // block forward / backward substitution where the diagonal solves are products with the inverted diagonal blocks (in
-// place: a 16 x 16 block of the product only reads its own block of X), so everything is gemm_cta.
-template <typename T> __device__ void chol_solve_blocked(const GenLayout& L, const T* Lw, T* X, int ncol) {
+// place: a 16 x 16 block of the product only reads its own block of X), so everything is gemm_cta.  The two halves are
+// separate calls because the gain kernel needs the intermediate Z = L^-1 X (Z^T Z = X^T (L L^T)^-1 X).
+template <typename T> __device__ void chol_forward_blocked(const GenLayout& L, const T* Lw, T* X, int ncol) {
   const int d = L.d, ld = L.ld;
   for (int k0 = 0; k0 < d; k0 += 16) {                        // forward: L z = b
     const int kb = (d - k0 < 16) ? d - k0 : 16;
@@ -578,6 +610,9 @@ template <typename T> __device__ void chol_solve_blocked(const GenLayout& L, con
       __syncthreads();
     }
   }
+}
+template <typename T> __device__ void chol_backward_blocked(const GenLayout& L, const T* Lw, T* X, int ncol) {
+  const int d = L.d, ld = L.ld;
   for (int k0 = ((d - 1) >> 4) << 4; k0 >= 0; k0 -= 16) {     // backward: L^T x = z
     const int kb = (d - k0 < 16) ? d - k0 : 16;
     T* X1 = X + k0 * ld;
@@ -589,6 +624,10 @@ template <typename T> __device__ void chol_solve_blocked(const GenLayout& L, con
       __syncthreads();
     }
   }
+}
+template <typename T> __device__ void chol_solve_blocked(const GenLayout& L, const T* Lw, T* X, int ncol) {
+  chol_forward_blocked<T>(L, Lw, X, ncol);
+  chol_backward_blocked<T>(L, Lw, X, ncol);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -607,7 +646,7 @@ template <typename T> size_t generic_filter_smem(int d) {
 }
 template <typename T> size_t generic_gain_smem(int d) {
   const GenLayout L = gen_layout(d);
-  return (size_t)(2 * L.msz + 4 * d + 16) * sizeof(T) + (size_t)(2 * d + 8) * sizeof(int) + 256;
+  return (size_t)(2 * L.msz + 5 * d + 16) * sizeof(T) + (size_t)(2 * d + 8) * sizeof(int) + 256;
 }
 template <typename T> size_t generic_smoother_smem(int d) {
   const GenLayout L = gen_layout(d);
@@ -644,6 +683,7 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_fold_kernel(const Gen
   const int64_t n0 = (int64_t)blockIdx.x * g.chunk_len, n1 = (n0 + g.chunk_len < g.N) ? n0 + g.chunk_len : g.N;
   KJX_GEN_VEC(e, 6 * L.msz) A[e] = T(0);                   // the six tiles are contiguous
   scale_vectors<T>(d, g.Pinf, Dv, Dinv);
+  fetch_c0n<T>(g, c0n);
   __syncthreads();
   {
     const double* Pg = g.Pinf;
@@ -652,10 +692,12 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_fold_kernel(const Gen
   KJX_GEN_VEC(i, d) { A[i * ld + i] = T(1); b[i] = T(0); eta[i] = T(0); if (g.H) Hrow[i] = (T)g.H[i] * Dv[i]; }
   __syncthreads();
   for (int64_t n = n0; n < n1; ++n) {
-    build_rows<T>(g.disc, d, g.dt[n], vals, c0n);
-    KJX_GEN_VEC(r, d) {                                     // A~ = D^-1 A D  (each thread rescales the row it just built)
-      const int c0 = c0n[r] & 0xffffff, nn = c0n[r] >> 24;
-      for (int q = 0; q < nn; ++q) vals[r * 4 + q] *= Dv[c0 + q] * Dinv[r];
+    {                                                       // rows of A~ = D^-1 A D from the precomputed rows of A(dt[n])
+      const T* src = g.rows + n * 4 * (int64_t)d;
+      KJX_GEN_VEC(e, 4 * d) {
+        const int r = e >> 2, q = e & 3, c0 = c0n[r] & 0xffffff, nn = c0n[r] >> 24;
+        vals[e] = (q < nn) ? src[e] * Dv[c0 + q] * Dinv[r] : T(0);
+      }
     }
     if (g.H_steps) KJX_GEN_VEC(i, d) Hrow[i] = (T)g.H_steps[n * d + i] * Dv[i];
     __syncthreads();
@@ -894,6 +936,24 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_group_kernel(const Ge
 }
 
 // ------------------------------------------------------------------------------------------------
+// log Z of every step from the recorded predictive moments (sde_gp.py:287, 300-301), embarrassingly parallel; one partial
+// sum per block (fixed order), reduced by nlml_reduce_kernel
+template <typename T>
+__global__ void __launch_bounds__(128) generic_loglik_kernel(const SiteModel site, int64_t N, const T* __restrict__ y,
+                                                             const uint8_t* __restrict__ mask, const T* __restrict__ pm,
+                                                             const T* __restrict__ pv, T* __restrict__ partial) {
+  __shared__ T red[4];
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  T lml = T(0);
+  if (n < N && !(mask && mask[n] != 0)) lml = filter_loglik<T>(site, y[n], pm[n], pv[n]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lml += __shfl_down_sync(0xffffffffu, lml, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lml;
+  __syncthreads();
+  if (threadIdx.x == 0) partial[blockIdx.x] = (red[0] + red[1]) + (red[2] + red[3]);
+}
+
+// ------------------------------------------------------------------------------------------------
 // forward filter, sde_gp.py:271-306
 template <typename T>
 __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_filter_kernel(const GenArgs<T> g) {
@@ -909,6 +969,7 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_filter_kernel(const G
   // this CTA's chunk and the filtered state entering it (chunk 0: the prior, sde_gp.py:265)
   const int64_t n0 = (int64_t)blockIdx.x * g.chunk_len, n1 = (n0 + g.chunk_len < g.N) ? n0 + g.chunk_len : g.N;
   KJX_GEN_VEC(e, 3 * L.msz) P[e] = T(0);
+  fetch_c0n<T>(g, c0n);
   __syncthreads();
   load_dense<T>(L, g.Pinf, Pinf);
   load_dense<T>(L, g.st_P + (size_t)blockIdx.x * dd, P);
@@ -916,7 +977,7 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_filter_kernel(const G
   if (threadIdx.x == 0) sh[6] = T(0);
   __syncthreads();
   for (int64_t n = n0; n < n1; ++n) {
-    build_rows<T>(g.disc, d, g.dt[n], vals, c0n);                                   // :276
+    fetch_rows<T>(g, n, vals);                                                      // :276
     if (g.H_steps) KJX_GEN_VEC(i, d) Hrow[i] = (T)g.H_steps[n * d + i];             // :282
     __syncthreads();
     rows_matvec<T>(d, vals, c0n, m, mp);                                            // :277
@@ -939,7 +1000,10 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_filter_kernel(const G
       } else {
         if (g.site_mean) { smean = g.site_mean[n]; svar = g.site_var[n]; }           // :290
         else { smean = g.y[n]; svar = T(g.site.lik_hyp); }                           // Gaussian + EP initialisation
-        if (!masked) lml = filter_loglik<T, WarpRed>(g.site, g.y[n], pm, pv);        // log Z is always the true likelihood's
+        // log Z is always the true likelihood's (:287).  It does not feed the recursion, so steady-state iterations
+        // only record the predictive here and generic_loglik_kernel evaluates all steps at once afterwards.
+        if (g.pred_mean) { if (lane == 0) { g.pred_mean[n] = pm; g.pred_var[n] = pv; } }
+        else if (!masked) lml = filter_loglik<T, WarpRed>(g.site, g.y[n], pm, pv);
       }
       if (masked) lml = T(0);                                                        // :300
       if (lane == 0) {
@@ -984,7 +1048,7 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS, 1) generic_filter_blocks_kern
   T* sh = sc.take(16);                 // scalars: 0 pm, 2 site_mean, 4 Sinv, 5 masked, 6 nlml
   int* c0n = sc.take_int(d); int* bstart = sc.take_int(17); int* bsize = sc.take_int(17);
   const int64_t n0 = (int64_t)blockIdx.x * g.chunk_len, n1 = (n0 + g.chunk_len < g.N) ? n0 + g.chunk_len : g.N;
-  build_rows<T>(g.disc, d, T(0), vals, c0n);                 // block structure of A
+  fetch_c0n<T>(g, c0n);                                      // block structure of A
   __syncthreads();
   if (threadIdx.x == 0) {
     int nb = 0;
@@ -1010,7 +1074,7 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS, 1) generic_filter_blocks_kern
       }
   }
   for (int64_t n = n0; n < n1; ++n) {
-    build_rows<T>(g.disc, d, g.dt[n], vals, c0n);                                   // :276
+    fetch_rows<T>(g, n, vals);                                                      // :276
     if (g.H_steps) KJX_GEN_VEC(i, d) Hrow[i] = (T)g.H_steps[n * d + i];             // :282
     __syncthreads();
     rows_matvec<T>(d, vals, c0n, m, mp);                                            // :277
@@ -1062,7 +1126,10 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS, 1) generic_filter_blocks_kern
       } else {
         if (g.site_mean) { smean = g.site_mean[n]; svar = g.site_var[n]; }           // :290
         else { smean = g.y[n]; svar = T(g.site.lik_hyp); }                           // Gaussian + EP initialisation
-        if (!masked) lml = filter_loglik<T, WarpRed>(g.site, g.y[n], pm, pv);        // log Z is always the true likelihood's
+        // log Z is always the true likelihood's (:287).  It does not feed the recursion, so steady-state iterations
+        // only record the predictive here and generic_loglik_kernel evaluates all steps at once afterwards.
+        if (g.pred_mean) { if (lane == 0) { g.pred_mean[n] = pm; g.pred_var[n] = pv; } }
+        else if (!masked) lml = filter_loglik<T, WarpRed>(g.site, g.y[n], pm, pv);
       }
       if (masked) lml = T(0);                                                        // :300
       if (lane == 0) {
@@ -1099,30 +1166,38 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS, 1) generic_filter_blocks_kern
 
 // ------------------------------------------------------------------------------------------------
 // RTS gains, embarrassingly parallel over time: Gt[n] = solve(P_pred[n], A[n+1] Pf[n]) depends only on the FILTERED
-// moments (sde_gp.py:351-359), so a grid of CTAs computes them all before the (sequential) backward recursion.
-// Working set: two tiles in shared memory (61 KB at d = 59, three CTAs per SM); Pf and Pinf are read from global / L1.
+// moments (sde_gp.py:351-359), so a grid of CTAs computes them all before the (sequential) backward recursion — and with
+// them the constant terms of that recursion written in affine form,
+//     P_s[n] = Pf + G (P_s[n+1] - P_pred) G^T = G P_s[n+1] G^T + Lc,   Lc = Pf - G P_pred G^T = Pf - Z^T Z,
+//     m_s[n] = mf + G (m_s[n+1] - A mf)       = G m_s[n+1] + gc,       gc = mf - G A mf,
+// with G = Gt^T and Z = L^-1 A Pf the intermediate of the Cholesky solve (P_pred = L L^T): the chain kernel is left with
+// two products per step.  Gt and Lc go out in the padded tile layout ([d][ld]: 16-byte rows) so that the smoother can
+// fetch each with one bulk copy.  Working set: two tiles in shared memory (61 KB at d = 59, three CTAs per SM).
+template <typename T> __host__ __device__ inline int gen_vec_stride(int d) { return (d + 3) & ~3; }   // 16-byte multiple for both types
 template <typename T>
 __global__ void __launch_bounds__(KJX_GEN_GAIN_THREADS, 3) generic_gain_kernel(const GenArgs<T> g, T* __restrict__ Gt_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemCarver<T> sc(g.gscratch ? g.gscratch + (size_t)blockIdx.x * g.gscratch_stride : smem_raw);
   const GenLayout L = gen_layout(g.d);
-  const int d = L.d, dd = d * d, ld = L.ld;
+  const int d = L.d, dd = d * d, ld = L.ld, tsz = d * ld, gs = gen_vec_stride<T>(d), lane = threadIdx.x & 31;
   T* W = sc.take(L.msz); T* Gt = sc.take(L.msz);
-  T* vals = sc.take(4 * d); T* scr16 = sc.take(16);
+  T* vals = sc.take(4 * d); T* scr16 = sc.take(16); T* mpv = sc.take(d);
   int* c0n = sc.take_int(d); int* bstart = sc.take_int(d + 1);
   KJX_GEN_VEC(e, 2 * L.msz) W[e] = T(0);
-  build_rows<T>(g.disc, d, T(0), vals, c0n);                 // block structure of A: first rows of the diagonal blocks
+  fetch_c0n<T>(g, c0n);                                      // block structure of A: first rows of the diagonal blocks
   __syncthreads();
   if (threadIdx.x == 0) { int nb = 0; for (int i = 0; i < d; ++i) if ((c0n[i] & 0xffffff) == i) bstart[nb++] = i; bstart[d] = nb; }
   __syncthreads();
   const int nblk = bstart[d];
   const double* Pinf = g.Pinf;
   for (int64_t n = blockIdx.x; n < g.N; n += gridDim.x) {
-    build_rows<T>(g.disc, d, (n + 1 < g.N) ? g.dt[n + 1] : T(0), vals, c0n);        // :337, :351
+    fetch_rows<T>(g, n + 1, vals);                                                  // A(dt[n+1]), A = I after the last step: :337, :351
     const T* Pf = g.filt_cov_in + n * (int64_t)dd;
+    const T* mf = g.filt_mean_in + n * (int64_t)d;
     tile_map<T>(d, [&](int i, int j) { return Pf[i * d + j] - (T)Pinf[i * d + j]; }, [&](int i, int j, T v) { W[i * ld + j] = v; });
     __syncthreads();
     rows_left<T, T>(L, vals, c0n, W, ld, nullptr, 0, Gt);                           // Gt <- A (Pf - Pinf)
+    rows_matvec<T>(d, vals, c0n, mf, mpv);                                          // A mf                      (:352)
     __syncthreads();
     rows_right_add<T, double>(L, vals, c0n, Gt, Pinf, d, W);                        // W <- P_pred = . A^T + Pinf   (:354)
     __syncthreads();
@@ -1131,108 +1206,171 @@ __global__ void __launch_bounds__(KJX_GEN_GAIN_THREADS, 3) generic_gain_kernel(c
     rows_left_inplace<T>(L, vals, c0n, bstart, nblk, Gt);                           // Gt <- A Pf                  (:353)
     __syncthreads();
     chol_blocked<T>(L, W, scr16);                                                   // utils.py:29
-    chol_solve_blocked<T>(L, W, Gt, d);                                             // :359, utils.py:30
-    store_dense<T>(L, Gt, Gt_out + n * (int64_t)dd);
+    chol_forward_blocked<T>(L, W, Gt, d);                                           // Gt <- Z = L^-1 A Pf
+    if (g.Lc) {
+      T* Lo = g.Lc + n * (int64_t)tsz;
+      gemm_cta<T, true, false>(d, d, d, Gt, Gt, ld, [&](int i, int j, T v) { Lo[i * ld + j] = Pf[i * d + j] - v; });   // Lc = Pf - Z^T Z
+      KJX_GEN_ROWS(i, d) for (int j = d + lane; j < ld; j += 32) Lo[i * ld + j] = T(0);   // padding columns: the smoother's k loops read them
+      __syncthreads();
+    }
+    chol_backward_blocked<T>(L, W, Gt, d);                                          // Gt <- L^-T Z               (:359, utils.py:30)
+    T* Go = Gt_out + n * (int64_t)tsz;
+    KJX_GEN_ROWS(i, d) KJX_GEN_COLS(j, ld) Go[i * ld + j] = Gt[i * ld + j];             // whole padded rows (padding stays zero)
+    if (g.gc) KJX_GEN_VEC(i, d) { T v = mf[i]; for (int k = 0; k < d; ++k) v -= Gt[k * ld + i] * mpv[k]; g.gc[n * (int64_t)gs + i] = v; }
     __syncthreads();
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward smoother, sde_gp.py:337-379
+// bulk copies global -> shared through the TMA unit with mbarrier completion (cp.async.bulk; SASS UBLKCP)
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "KJX_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra KJX_MBAR_DONE;\n"
+      "bra KJX_MBAR_WAIT;\n"
+      "KJX_MBAR_DONE:\n"
+      "}\n" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src), "r"(bytes),
+                  "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+// backward smoother, sde_gp.py:337-379.  Last step of the chunk: filtered x information of everything after the chunk
+// (two-filter identity; the chunk that ends the series: smoothed = filtered, sde_gp.py:339).  Every other step: the
+// affine recursion with the terms generic_gain_kernel prepared — two d^3 products on the FP64 tensor pipe per step, the
+// next step's (Gt, Lc, gc) arriving by bulk copy (TMA, mbarrier) while the current one is being multiplied.  The marginal
+// H m, H P H^T of every step goes to post_mean / post_var; the site update is a batched kernel afterwards.
 template <typename T>
 __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_smoother_kernel(const GenArgs<T> g, const T* __restrict__ Gt_in) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long bars[2];
   SmemCarver<T> sc(g.gscratch ? g.gscratch + (size_t)blockIdx.x * g.gscratch_stride : smem_raw);
   const GenLayout L = gen_layout(g.d);
-  const int d = L.d, dd = d * d, ld = L.ld, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  T* Pf = sc.take(L.msz); T* Pp = sc.take(L.msz); T* Gt = sc.take(L.msz); T* Ps = sc.take(L.msz); T* W = sc.take(L.msz);
-  T* Pinf = sc.take(L.msz);
-  T* vals = sc.take(4 * d); T* mf = sc.take(d); T* mp = sc.take(d); T* ms = sc.take(d); T* dm = sc.take(d); T* Hrow = sc.take(d);
-  T* rv = sc.take(d); T* mnew = sc.take(d); T* part = sc.take(KJX_GEN_WARPS * d); T* Dv = sc.take(d); T* Dinv = sc.take(d); T* dscr = sc.take(16);
-  int* c0n = sc.take_int(d); int* piv = sc.take_int(d);
+  const int d = L.d, dd = d * d, ld = L.ld, tsz = d * ld, gs = gen_vec_stride<T>(d), lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  T* Ps = sc.take(L.msz); T* T1 = sc.take(L.msz);
+  T* GtS[2]; T* LcS[2]; T* gvS[2];
+  GtS[0] = sc.take(L.msz); GtS[1] = sc.take(L.msz); LcS[0] = sc.take(L.msz); LcS[1] = sc.take(L.msz);
+  gvS[0] = sc.take(gs); gvS[1] = sc.take(gs);
+  T* ms = sc.take(d); T* mnew = sc.take(d); T* mf = sc.take(d); T* Hrow = sc.take(d);
+  T* rv = sc.take(d); T* part = sc.take(KJX_GEN_WARPS * d); T* Dv = sc.take(d); T* Dinv = sc.take(d); T* dscr = sc.take(16);
+  int* piv = sc.take_int(d);
+  const bool tma = g.gscratch == nullptr;                  // tiles in shared memory: bulk copies; in global scratch: plain copies
   const int64_t n0 = (int64_t)blockIdx.x * g.chunk_len, n1 = (n0 + g.chunk_len < g.N) ? n0 + g.chunk_len : g.N;
-  KJX_GEN_VEC(e, 6 * L.msz) Pf[e] = T(0);
+  KJX_GEN_VEC(e, 6 * L.msz) Ps[e] = T(0);
   scale_vectors<T>(d, g.Pinf, Dv, Dinv);
-  __syncthreads();
-  load_dense<T>(L, g.Pinf, Pinf);
+  if (threadIdx.x == 0 && tma) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   KJX_GEN_VEC(i, d) if (g.H) Hrow[i] = (T)g.H[i];
   __syncthreads();
-  for (int64_t n = n1 - 1; n >= n0; --n) {
-    if (n == n1 - 1) {
-      // Last step of the chunk: smoothed = filtered x information of everything after the chunk (two-filter identity;
-      // for the chunk that ends the series the information is zero and this is sde_gp.py:339).  Pp/Gt/W are scratch here.
-      if (g.H_steps) KJX_GEN_VEC(i, d) Hrow[i] = (T)g.H_steps[n * d + i];
-      const T* Pg = g.filt_cov_in + n * (int64_t)dd;
-      if (n1 == g.N) {
-        // the chunk that ends the series: nothing comes after it, smoothed = filtered (sde_gp.py:339)
-        load_dense<T>(L, Pg, Ps);
-        KJX_GEN_VEC(i, d) ms[i] = g.filt_mean_in[n * d + i];
-        __syncthreads();
-      } else {
-        // (I + P~ J~) X~ = [P~ | m~ + P~ eta~] in the equilibrated coordinates of the scan (see scale_vectors)
-        tile_map<T>(d, [&](int i, int j) { return Pg[(size_t)i * d + j] * Dinv[i] * Dinv[j]; }, [&](int i, int j, T v) { Pf[i * ld + j] = v; });
-        load_dense<T>(L, g.in_J + (size_t)blockIdx.x * dd, W);
-        KJX_GEN_VEC(i, d) mf[i] = g.filt_mean_in[n * d + i] * Dinv[i];
-        __syncthreads();
-        const T* eta = g.in_eta + (size_t)blockIdx.x * d;
-        gemm_cta<T, false, false>(d, d, d, Pf, W, ld, [&](int i, int j, T v) { Pp[i * ld + j] = v + ((i == j) ? T(1) : T(0)); });
-        tile_map<T>(d, [&](int i, int j) { return Pf[i * ld + j]; }, [&](int i, int j, T v) { Gt[i * ld + j] = v; });
-        KJX_GEN_VEC(i, d) { T s = mf[i]; for (int k = 0; k < d; ++k) s += Pf[i * ld + k] * eta[k]; rv[i] = s; }
-        __syncthreads();
-        lu_solve_blocked<T>(L, Pp, Gt, (T*)nullptr, rv, piv, dscr);           // Gt <- (I + P J)^-1 P,  rv <- (I + P J)^-1 (m + P eta)
-        tile_map<T>(d, [&](int i, int j) { return ((i <= j) ? Gt[i * ld + j] : Gt[j * ld + i]) * Dv[i] * Dv[j]; },   // symmetric by construction; keep the upper part
-                    [&](int i, int j, T v) { Ps[i * ld + j] = v; });
-        KJX_GEN_VEC(i, d) ms[i] = rv[i] * Dv[i];
-        __syncthreads();
-      }
-      if (g.smooth_mean && g.return_full) {
-        store_dense<T>(L, Ps, g.smooth_cov + n * (int64_t)dd);
-        KJX_GEN_VEC(i, d) g.smooth_mean[n * d + i] = ms[i];
-      }
-    } else {
-      build_rows<T>(g.disc, d, (n + 1 < g.N) ? g.dt[n + 1] : T(0), vals, c0n);      // :337, :351
-      if (g.H_steps) KJX_GEN_VEC(i, d) Hrow[i] = (T)g.H_steps[n * d + i];
-      load_dense<T>(L, g.filt_cov_in + n * (int64_t)dd, Pf);
-      load_dense<T>(L, Gt_in + n * (int64_t)dd, Gt);                                // gain from generic_gain_kernel
-      KJX_GEN_VEC(i, d) mf[i] = g.filt_mean_in[n * d + i];
-      __syncthreads();
-      rows_matvec<T>(d, vals, c0n, mf, mp);                                         // :352
-      rows_left<T, T>(L, vals, c0n, Pf, ld, Pinf, ld, Pp);                          // Pp <- A (Pf - Pinf)
-      __syncthreads();
-      rows_right_add<T, T>(L, vals, c0n, Pp, Pinf, ld, W, Ps, T(-1));               // W <- Ps - P_pred          (:354)
-      KJX_GEN_VEC(i, d) dm[i] = ms[i] - mp[i];
-      __syncthreads();
-      // m = mf + G (m - m_pred);  P = Pf + G (P - P_pred) G^T  with G = Gt^T          (:360-361)
-      gemm_cta<T, true, false>(d, d, d, Gt, W, ld, [&](int i, int j, T v) { Pp[i * ld + j] = v; });   // Pp <- G (Ps - P_pred)
-      KJX_GEN_VEC(i, d) { T v = mf[i]; for (int k = 0; k < d; ++k) v += Gt[k * ld + i] * dm[k]; mnew[i] = v; }
-      __syncthreads();
-      T* sc_out = (g.smooth_mean && g.return_full) ? g.smooth_cov + n * (int64_t)dd : nullptr;
-      gemm_cta<T, false, false>(d, d, d, Pp, Gt, ld, [&](int i, int j, T v) {
-        const T r = Pf[i * ld + j] + v;
-        Ps[i * ld + j] = r;
-        if (sc_out) sc_out[i * d + j] = r;
-      });
-      KJX_GEN_VEC(i, d) { ms[i] = mnew[i]; if (sc_out) g.smooth_mean[n * d + i] = mnew[i]; }
-      __syncthreads();
-    }
-    // marginal of the function value: H m, H P H^T                                      (:368-369, :373)
+  // marginal of the function value of step n from (ms, Ps): H m, H P H^T                 (:368-369, :373)
+  auto project = [&](int64_t n) {
     rowvec_partial<T>(L, Hrow, Ps, part, 0, KJX_GEN_WARPS);
     __syncthreads();
-    if (warp == 0) {                   // warp 0, cubature points spread over its lanes
+    if (warp == 0) {
       T pm = T(0), pv = T(0);
       KJX_GEN_COLS(j, d) { pm += Hrow[j] * ms[j]; pv += partial_total<T>(d, part, j, KJX_GEN_WARPS) * Hrow[j]; }
       pm = warp_sum(pm); pv = warp_sum(pv);
-      if (lane == 0 && g.smooth_mean && !g.return_full) { g.smooth_mean[n] = pm; g.smooth_cov[n] = pv; }
-      if (g.update_sites) {
-        T pmean, pvar;
-        if (g.site_mean) { pmean = g.site_mean[n]; pvar = g.site_var[n]; } else { pmean = g.y[n]; pvar = T(g.site.lik_hyp); }
-        __syncwarp();                    // every lane has read the previous site before lane 0 may overwrite it in place
-        const SiteOut<T> o = site_update<T, WarpRed>(g.site, g.y[n], pm, pv, true, pmean, pvar);   // :375
-        if (lane == 0) { g.new_site_mean[n] = o.mean; g.new_site_var[n] = o.var; }
-      }
+      if (lane == 0) { g.post_mean[n] = pm; g.post_var[n] = pv; }
     }
+  };
+  {
+    const int64_t n = n1 - 1;
+    T* Mm = GtS[0]; T* Rr = GtS[1]; T* Pf = LcS[0]; T* Wj = LcS[1];           // scratch roles of this step (the LU's
+    // operands must not be the last tiles: its fragment loads may read up to 16 rows past a tile)
+    if (g.H_steps) KJX_GEN_VEC(i, d) Hrow[i] = (T)g.H_steps[n * d + i];
+    const T* Pg = g.filt_cov_in + n * (int64_t)dd;
+    if (n1 == g.N) {
+      load_dense<T>(L, Pg, Ps);
+      KJX_GEN_VEC(i, d) ms[i] = g.filt_mean_in[n * d + i];
+      __syncthreads();
+    } else {
+      // (I + P~ J~) X~ = [P~ | m~ + P~ eta~] in the equilibrated coordinates of the scan (see scale_vectors)
+      tile_map<T>(d, [&](int i, int j) { return Pg[(size_t)i * d + j] * Dinv[i] * Dinv[j]; }, [&](int i, int j, T v) { Pf[i * ld + j] = v; });
+      load_dense<T>(L, g.in_J + (size_t)blockIdx.x * dd, Wj);
+      KJX_GEN_VEC(i, d) mf[i] = g.filt_mean_in[n * d + i] * Dinv[i];
+      __syncthreads();
+      const T* eta = g.in_eta + (size_t)blockIdx.x * d;
+      gemm_cta<T, false, false>(d, d, d, Pf, Wj, ld, [&](int i, int j, T v) { Mm[i * ld + j] = v + ((i == j) ? T(1) : T(0)); });
+      tile_map<T>(d, [&](int i, int j) { return Pf[i * ld + j]; }, [&](int i, int j, T v) { Rr[i * ld + j] = v; });
+      KJX_GEN_VEC(i, d) { T s = mf[i]; for (int k = 0; k < d; ++k) s += Pf[i * ld + k] * eta[k]; rv[i] = s; }
+      __syncthreads();
+      lu_solve_blocked<T>(L, Mm, Rr, (T*)nullptr, rv, piv, dscr);         // Rr <- (I + P J)^-1 P,  rv <- (I + P J)^-1 (m + P eta)
+      tile_map<T>(d, [&](int i, int j) { return ((i <= j) ? Rr[i * ld + j] : Rr[j * ld + i]) * Dv[i] * Dv[j]; },   // symmetric by construction; keep the upper part
+                  [&](int i, int j, T v) { Ps[i * ld + j] = v; });
+      KJX_GEN_VEC(i, d) ms[i] = rv[i] * Dv[i];
+      __syncthreads();
+    }
+    if (g.smooth_mean && g.return_full) {
+      store_dense<T>(L, Ps, g.smooth_cov + n * (int64_t)dd);
+      KJX_GEN_VEC(i, d) g.smooth_mean[n * d + i] = ms[i];
+    }
+    project(n);
+    __syncthreads();
+    // the scratch tiles go back to zero padding (rows d.. and columns d.. must be finite zeros for the fragment loads)
+    KJX_GEN_VEC(e, 4 * L.msz) GtS[0][e] = T(0);
     __syncthreads();
   }
+  const unsigned tbytes = (unsigned)(tsz * sizeof(T)), gbytes = (unsigned)(gs * sizeof(T));
+  auto fetch = [&](int64_t n, int st) {                    // (Gt, Lc, gc) of step n -> stage st
+    if (tma) {
+      if (threadIdx.x == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the stage's last generic-proxy accesses are ordered before the copies
+        mbar_expect_tx(&bars[st], 2 * tbytes + gbytes);
+        bulk_load(GtS[st], Gt_in + n * (int64_t)tsz, tbytes, &bars[st]);
+        bulk_load(LcS[st], g.Lc + n * (int64_t)tsz, tbytes, &bars[st]);
+        bulk_load(gvS[st], g.gc + n * (int64_t)gs, gbytes, &bars[st]);
+      }
+    } else {
+      const T* G0 = Gt_in + n * (int64_t)tsz; const T* L0 = g.Lc + n * (int64_t)tsz;
+      KJX_GEN_VEC(e, tsz) { GtS[st][e] = G0[e]; LcS[st][e] = L0[e]; }
+      KJX_GEN_VEC(i, d) gvS[st][i] = g.gc[n * (int64_t)gs + i];
+    }
+  };
+  unsigned phase[2] = {0u, 0u};
+  if (n1 - 2 >= n0) fetch(n1 - 2, 0);
+  for (int64_t n = n1 - 2; n >= n0; --n) {
+    const int st = (int)((n1 - 2 - n) & 1);
+    if (n - 1 >= n0 && tma) fetch(n - 1, st ^ 1);          // stage st^1 was last read two barriers ago
+    if (tma) { mbar_wait(&bars[st], phase[st]); phase[st] ^= 1u; } else __syncthreads();
+    const T* Gt = GtS[st]; const T* Lc = LcS[st]; const T* gv = gvS[st];
+    if (g.H_steps) KJX_GEN_VEC(i, d) Hrow[i] = (T)g.H_steps[n * d + i];
+    gemm_cta<T, false, false>(d, d, d, Ps, Gt, ld, [&](int i, int j, T v) { T1[i * ld + j] = v; });             // T1 = P_s[n+1] Gt
+    KJX_GEN_VEC(i, d) { T v = gv[i]; for (int k = 0; k < d; ++k) v += Gt[k * ld + i] * ms[k]; mnew[i] = v; }   // :360
+    __syncthreads();
+    T* sc_out = (g.smooth_mean && g.return_full) ? g.smooth_cov + n * (int64_t)dd : nullptr;
+    gemm_cta<T, true, false>(d, d, d, Gt, T1, ld, [&](int i, int j, T v) {                                     // :361
+      const T r = Lc[i * ld + j] + v;
+      Ps[i * ld + j] = r;
+      if (sc_out) sc_out[i * d + j] = r;
+    });
+    KJX_GEN_VEC(i, d) { ms[i] = mnew[i]; if (sc_out) g.smooth_mean[n * d + i] = mnew[i]; }
+    __syncthreads();
+    if (!tma && n - 1 >= n0) fetch(n - 1, st ^ 1);
+    project(n);
+  }
+}
+
+// (log_lik, site) of every step from the smoothed marginals (sde_gp.py:373-379), embarrassingly parallel.  Without stored
+// sites (Gaussian likelihood + EP before the first update) the previous site is (y, sigma^2), utils.py:241-244.
+template <typename T>
+__global__ void __launch_bounds__(128) generic_site_update_kernel(const SiteModel sm, int64_t N, const T* __restrict__ y,
+                                                                  const T* __restrict__ pm, const T* __restrict__ pv,
+                                                                  const T* sprev_mean, const T* sprev_var, T* site_mean, T* site_var) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= N) return;
+  const T pmean = sprev_mean ? sprev_mean[k] : y[k], pvar = sprev_var ? sprev_var[k] : T(sm.lik_hyp);
+  const SiteOut<T> o = site_update<T>(sm, y[k], pm[k], pv[k], true, pmean, pvar);
+  site_mean[k] = o.mean; site_var[k] = o.var;
 }
 
 }  // namespace kjx

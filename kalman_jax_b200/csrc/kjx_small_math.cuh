@@ -365,6 +365,37 @@ template <typename T, int D> KJX_HD void inv_gj(T (&M)[D][D], T (&R)[D][D]) {
   }
 }
 
+// Inverse of M = I + C J (C, J symmetric positive semi-definite: real eigenvalues >= 1, det >= 1) in closed form —
+// adjugate over determinant, one reciprocal.  The scan's combines and boundary applications are pure latency (one warp
+// walks a dependent chain of them), and Gauss-Jordan's three dependent pivot searches + reciprocals were a third of each;
+// the forward error of the closed form is of the same order (condition number x epsilon) for these matrices, and the
+// scan only sets the state entering a chunk — the recursions inside the chunks are the reference's.
+template <typename T, int D> struct InvSmall {
+  static KJX_HD void run(T (&M)[D][D], T (&R)[D][D]) { inv_gj<T, D>(M, R); }
+};
+template <typename T> struct InvSmall<T, 2> {
+  static KJX_HD void run(T (&M)[2][2], T (&R)[2][2]) {
+    const T rdet = T(1) / (M[0][0] * M[1][1] - M[0][1] * M[1][0]);
+    R[0][0] = M[1][1] * rdet; R[0][1] = -M[0][1] * rdet;
+    R[1][0] = -M[1][0] * rdet; R[1][1] = M[0][0] * rdet;
+  }
+};
+template <typename T> struct InvSmall<T, 3> {
+  static KJX_HD void run(T (&M)[3][3], T (&R)[3][3]) {
+    const T c00 = M[1][1] * M[2][2] - M[1][2] * M[2][1];
+    const T c01 = M[1][2] * M[2][0] - M[1][0] * M[2][2];
+    const T c02 = M[1][0] * M[2][1] - M[1][1] * M[2][0];
+    const T rdet = T(1) / (M[0][0] * c00 + M[0][1] * c01 + M[0][2] * c02);
+    R[0][0] = c00 * rdet; R[1][0] = c01 * rdet; R[2][0] = c02 * rdet;
+    R[0][1] = (M[0][2] * M[2][1] - M[0][1] * M[2][2]) * rdet;
+    R[1][1] = (M[0][0] * M[2][2] - M[0][2] * M[2][0]) * rdet;
+    R[2][1] = (M[0][1] * M[2][0] - M[0][0] * M[2][1]) * rdet;
+    R[0][2] = (M[0][1] * M[1][2] - M[0][2] * M[1][1]) * rdet;
+    R[1][2] = (M[0][2] * M[1][0] - M[0][0] * M[1][2]) * rdet;
+    R[2][2] = (M[0][0] * M[1][1] - M[0][1] * M[1][0]) * rdet;
+  }
+};
+
 // out = i (earlier) ⊗ j (later)          (Sarkka & Garcia-Fernandez 2021, Lemma 8)
 template <typename T, int D>
 KJX_HDN void fsum_combine(const FSum<T, D>& si, const FSum<T, D>& sj, FSum<T, D>& out) {
@@ -378,7 +409,7 @@ KJX_HDN void fsum_combine(const FSum<T, D>& si, const FSum<T, D>& sj, FSum<T, D>
       for (int k = 0; k < D; ++k) v += si.C[i][k] * sj.J[k][j];
       M[i][j] = v;
     }
-  inv_gj<T, D>(M, Minv);
+  InvSmall<T, D>::run(M, Minv);
   T T1[D][D], T2[D][D], W[D][D], u[D], w[D];
   mat_mul<T, D>(sj.A, Minv, T1);                   // T1 = A_j M^-1
   // u = b_i + C_i eta_j ; b = T1 u + b_j
@@ -445,7 +476,7 @@ KJX_HDN void fsum_apply(const FSum<T, D>& s, FiltState<T, D>& x) {
       for (int k = 0; k < D; ++k) v += x.P[i][k] * s.J[k][j];
       M[i][j] = v;
     }
-  inv_gj<T, D>(M, Minv);
+  InvSmall<T, D>::run(M, Minv);
   mat_mul<T, D>(s.A, Minv, T1);
 #pragma unroll
   for (int i = 0; i < D; ++i) {
@@ -504,7 +535,7 @@ KJX_HDN void fsum_combine_info(const FSum<T, D>& si, const Info<T, D>& fj, Info<
       for (int k = 0; k < D; ++k) v += si.C[i][k] * fj.J[k][j];
       M[i][j] = v;
     }
-  inv_gj<T, D>(M, Minv);
+  InvSmall<T, D>::run(M, Minv);
 #pragma unroll
   for (int i = 0; i < D; ++i)
 #pragma unroll
@@ -551,7 +582,7 @@ KJX_HDN void info_smooth(const Info<T, D>& f, FiltState<T, D>& x) {
       for (int k = 0; k < D; ++k) v += x.P[i][k] * f.J[k][j];
       M[i][j] = v;
     }
-  inv_gj<T, D>(M, Minv);
+  InvSmall<T, D>::run(M, Minv);
 #pragma unroll
   for (int i = 0; i < D; ++i) {
     T v = x.m[i];
