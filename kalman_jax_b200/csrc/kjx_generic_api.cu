@@ -100,6 +100,17 @@ template <typename T> int generic_launch_rows(const GenArgs<T>& g, cudaStream_t 
   generic_rows_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g.disc, g.d, g.N, g.dt, const_cast<T*>(g.rows), const_cast<int*>(g.c0n_g));
   return KJX_OK;
 }
+// shared-memory build (tiles addressed as __shared__) or global-scratch build (d > 64) of a kernel template
+#define KJX_GEN_LAUNCH(kernel, grid, threads, smem_bytes, st, ...)                                                        \
+  do {                                                                                                                    \
+    if (g.gscratch) {                                                                                                     \
+      kernel<T, true><<<(grid), (threads), 0, (st)>>>(__VA_ARGS__);                                                       \
+    } else {                                                                                                              \
+      KJX_CUDA_CHECK(cudaFuncSetAttribute(kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_bytes))); \
+      kernel<T, false><<<(grid), (threads), (smem_bytes), (st)>>>(__VA_ARGS__);                                           \
+    }                                                                                                                     \
+  } while (0)
+
 template <typename T> void generic_set_chunks(GenArgs<T>& g, bool chunked) {
   g.nchunks = chunked ? generic_chunks(g.N) : 1;
   g.chunk_len = (g.N + g.nchunks - 1) / g.nchunks;
@@ -107,41 +118,34 @@ template <typename T> void generic_set_chunks(GenArgs<T>& g, bool chunked) {
 }
 // elements of all chunks (when there are several), then the state / information at every chunk boundary
 template <typename T> int generic_launch_scan(const GenArgs<T>& g, cudaStream_t st) {
-  if (g.nchunks > 1) {
-    const size_t smem = g.gscratch ? 0 : generic_fold_smem<T>(g.d);
-    KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_fold_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    generic_fold_kernel<T><<<g.nchunks, KJX_GEN_THREADS, smem, st>>>(g);
-  }
-  const size_t smem = g.gscratch ? 0 : generic_boundary_smem<T>(g.d);
-  KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_boundary_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (g.nchunks > 1) KJX_GEN_LAUNCH(generic_fold_kernel, g.nchunks, KJX_GEN_THREADS, generic_fold_smem<T>(g.d), st, g);
+  const size_t smem = generic_boundary_smem<T>(g.d);
   // a walk over the chunk elements is a dependent chain (~90 us per element at d = 59, ~105 us per combine): beyond a
   // few dozen chunks do it in two levels — group elements, a walk over the groups, walks inside all groups at once
+  static const int group_knob = [] { const char* e = getenv("KJX_GEN_GROUP"); return e ? atoi(e) : 0; }();   // tuning knob, read once
   int gsz = (int)(sqrt(0.46 * (double)g.nchunks) + 0.5);
-  if (const char* e = getenv("KJX_GEN_GROUP")) gsz = atoi(e);
+  if (group_knob > 0) gsz = group_knob;
   if (g.nchunks >= 24 && gsz >= 2 && (g.nchunks + gsz - 1) / gsz <= KJX_GEN_MAXGROUPS) {
     const int ngroups = (g.nchunks + gsz - 1) / gsz;
-    const size_t gs = g.gscratch ? 0 : generic_group_smem<T>(g.d);
-    KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_group_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gs));
-    generic_group_kernel<T><<<ngroups, KJX_GEN_THREADS, gs, st>>>(g, gsz);
-    generic_boundary_kernel<T><<<2, KJX_GEN_THREADS, smem, st>>>(g, KJX_WALK_TOP, gsz);
-    generic_boundary_kernel<T><<<2 * ngroups, KJX_GEN_THREADS, smem, st>>>(g, KJX_WALK_INNER, gsz);
+    KJX_GEN_LAUNCH(generic_group_kernel, ngroups, KJX_GEN_THREADS, generic_group_smem<T>(g.d), st, g, gsz);
+    KJX_GEN_LAUNCH(generic_boundary_kernel, 2, KJX_GEN_THREADS, smem, st, g, (int)KJX_WALK_TOP, gsz);
+    KJX_GEN_LAUNCH(generic_boundary_kernel, 2 * ngroups, KJX_GEN_THREADS, smem, st, g, (int)KJX_WALK_INNER, gsz);
   } else {
-    generic_boundary_kernel<T><<<2, KJX_GEN_THREADS, smem, st>>>(g, KJX_WALK_FLAT, 1);
+    KJX_GEN_LAUNCH(generic_boundary_kernel, 2, KJX_GEN_THREADS, smem, st, g, (int)KJX_WALK_FLAT, 1);
   }
   return KJX_OK;
 }
 template <typename T> int generic_launch_filter(const GenArgs<T>& g, T* llpart, cudaStream_t st) {
   int nblk = 0;
   for (int b = 0; b < g.disc.n_blocks; ++b) nblk += g.disc.blocks[b].count;
-  if (nblk <= 16 && !getenv("KJX_GEN_TILE_FILTER")) {
+  static const bool tile_knob = getenv("KJX_GEN_TILE_FILTER") != nullptr;                              // tuning knob, read once
+  if (nblk <= 16 && !tile_knob && !g.gscratch) {
     // at most 16 diagonal blocks: P in registers, one thread per pair of blocks
     const size_t smem = generic_filter_blocks_smem<T>(g.d);
     KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_filter_blocks_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     generic_filter_blocks_kernel<T><<<g.nchunks, KJX_GEN_THREADS, smem, st>>>(g);
   } else {
-    const size_t smem = g.gscratch ? 0 : generic_filter_smem<T>(g.d);
-    KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_filter_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    generic_filter_kernel<T><<<g.nchunks, KJX_GEN_THREADS, smem, st>>>(g);
+    KJX_GEN_LAUNCH(generic_filter_kernel, g.nchunks, KJX_GEN_THREADS, generic_filter_smem<T>(g.d), st, g);
   }
   if (g.pred_mean) {
     // steady state: the chains only recorded the predictive moments; all log Z terms at once, then their fixed-order sum
@@ -154,15 +158,11 @@ template <typename T> int generic_launch_filter(const GenArgs<T>& g, T* llpart, 
   return KJX_OK;
 }
 template <typename T> int generic_launch_smoother(const GenArgs<T>& g, T* gains, cudaStream_t st) {
-  const size_t smem = g.gscratch ? 0 : generic_smoother_smem<T>(g.d);
-  // 1. all RTS gains, parallel over time (they depend on the filtered moments only)
-  const size_t gsmem = g.gscratch ? 0 : generic_gain_smem<T>(g.d);
-  KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_gain_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+  // 1. all RTS gains and the affine terms of the recursion, parallel over time (they depend on the filtered moments only)
   const unsigned grid = (unsigned)std::min<int64_t>(g.N, KJX_GEN_GAIN_GRID);
-  generic_gain_kernel<T><<<grid, KJX_GEN_GAIN_THREADS, gsmem, st>>>(g, gains);
-  // 2. the backward recursion (two d^3 products per step), every chunk concurrently, reference order inside a chunk
-  KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_smoother_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  generic_smoother_kernel<T><<<g.nchunks, KJX_GEN_THREADS, smem, st>>>(g, gains);
+  KJX_GEN_LAUNCH(generic_gain_kernel, grid, KJX_GEN_GAIN_THREADS, generic_gain_smem<T>(g.d), st, g, gains);
+  // 2. the backward recursion (two d^3 products per step), every chunk concurrently
+  KJX_GEN_LAUNCH(generic_smoother_kernel, g.nchunks, KJX_GEN_THREADS, generic_smoother_smem<T>(g.d), st, g, (const T*)gains);
   // 3. the site update of every step from the smoothed marginals, embarrassingly parallel (sde_gp.py:373-379)
   if (g.update_sites)
     generic_site_update_kernel<T><<<(unsigned)((g.N + 127) / 128), 128, 0, st>>>(g.site, g.N, g.y, g.post_mean, g.post_var, g.site_mean,

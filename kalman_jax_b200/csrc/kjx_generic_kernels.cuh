@@ -358,7 +358,7 @@ __device__ __forceinline__ void gemm_cta(int m, int n, int kk, const T* A, const
 // M and R must not be the last tiles of the working set (fragment loads of the trailing update may run past the
 // tile by up to 16 rows; those products are discarded).
 template <typename T>
-__device__ void lu_solve_blocked(const GenLayout& L, T* M, T* R, T* Rb, T* rv, int* piv, T* dscr) {
+__device__ __forceinline__ void lu_solve_blocked(const GenLayout& L, T* M, T* R, T* Rb, T* rv, int* piv, T* dscr) {
   const int nrb = Rb ? L.d : 0;                             // optional second block of d right-hand sides
   constexpr int NB = 8;
   const int d = L.d, ld = L.ld, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -530,7 +530,7 @@ __device__ void lu_solve_blocked(const GenLayout& L, T* M, T* R, T* Rb, T* rv, i
 // (strict upper part zeroed); the panel below (L21 = A21 L11^-T) and the trailing update then go through gemm_cta.
 // 3 barriers per panel.  On return the tile holds L below the diagonal blocks and L11^-1 in them, which is what
 // chol_solve_blocked wants.  A non-positive pivot gives NaN, like a failed potrf propagated by jaxlib.  scr16: 16 scalars.
-template <typename T> __device__ void chol_blocked(const GenLayout& L, T* W, T* scr16) {
+template <typename T> __device__ __forceinline__ void chol_blocked(const GenLayout& L, T* W, T* scr16) {
   const int d = L.d, ld = L.ld, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int k0 = 0; k0 < d; k0 += 16) {
     const int kb = (d - k0 < 16) ? d - k0 : 16;
@@ -596,7 +596,7 @@ template <typename T> __device__ void chol_blocked(const GenLayout& L, T* W, T* 
 // block forward / backward substitution where the diagonal solves are products with the inverted diagonal blocks (in
 // place: a 16 x 16 block of the product only reads its own block of X), so everything is gemm_cta.  The two halves are
 // separate calls because the gain kernel needs the intermediate Z = L^-1 X (Z^T Z = X^T (L L^T)^-1 X).
-template <typename T> __device__ void chol_forward_blocked(const GenLayout& L, const T* Lw, T* X, int ncol) {
+template <typename T> __device__ __forceinline__ void chol_forward_blocked(const GenLayout& L, const T* Lw, T* X, int ncol) {
   const int d = L.d, ld = L.ld;
   for (int k0 = 0; k0 < d; k0 += 16) {                        // forward: L z = b
     const int kb = (d - k0 < 16) ? d - k0 : 16;
@@ -611,7 +611,7 @@ template <typename T> __device__ void chol_forward_blocked(const GenLayout& L, c
     }
   }
 }
-template <typename T> __device__ void chol_backward_blocked(const GenLayout& L, const T* Lw, T* X, int ncol) {
+template <typename T> __device__ __forceinline__ void chol_backward_blocked(const GenLayout& L, const T* Lw, T* X, int ncol) {
   const int d = L.d, ld = L.ld;
   for (int k0 = ((d - 1) >> 4) << 4; k0 >= 0; k0 -= 16) {     // backward: L^T x = z
     const int kb = (d - k0 < 16) ? d - k0 : 16;
@@ -625,9 +625,121 @@ template <typename T> __device__ void chol_backward_blocked(const GenLayout& L, 
     }
   }
 }
-template <typename T> __device__ void chol_solve_blocked(const GenLayout& L, const T* Lw, T* X, int ncol) {
+template <typename T> __device__ __forceinline__ void chol_solve_blocked(const GenLayout& L, const T* Lw, T* X, int ncol) {
   chol_forward_blocked<T>(L, Lw, X, ncol);
   chol_backward_blocked<T>(L, Lw, X, ncol);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cholesky for the gain kernel (d <= 64): panels of 8 columns, the WHOLE column panel (all rows below the diagonal
+// included) in the registers of warp 0 — lane l owns rows k0 + l and k0 + 32 + l, all indices static so nothing spills
+// (the 16-column version above keeps a[16] in local memory: its one-warp diagonal phases were 36 % of the gain kernel in
+// the ncu source view) —, then a rank-8 update of the trailing block on the FP64 tensor pipe by all warps.  8 panels and
+// 16 barriers for d = 59.  On return the strict lower triangle of W holds L and rinv[j] = 1 / L[j][j] (the diagonal of W
+// holds L[j][j]); a non-positive pivot gives NaN like a failed potrf propagated by jaxlib (utils.py:29).
+template <typename T> __device__ __forceinline__ void chol_panel8(const GenLayout& L, T* W, T* rinv) {
+  constexpr int NB = 8;
+  const int d = L.d, ld = L.ld, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k0 = 0; k0 < d; k0 += NB) {
+    const int kb = (d - k0 < NB) ? d - k0 : NB;
+    if (warp == 0) {
+      const int i0 = k0 + lane, i1 = k0 + 32 + lane;
+      const bool ok0 = i0 < d, ok1 = i1 < d;
+      T a0[NB], a1[NB];
+#pragma unroll
+      for (int c = 0; c < NB; ++c) {
+        a0[c] = (ok0 && c < kb) ? W[i0 * ld + k0 + c] : ((c == lane) ? T(1) : T(0));      // identity padding keeps the arithmetic finite
+        a1[c] = (ok1 && c < kb) ? W[i1 * ld + k0 + c] : T(0);
+      }
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const T pv = __shfl_sync(0xffffffffu, a0[j], j);
+        const T r = rsqrt_(pv);
+        a0[j] = (lane == j) ? pv * r : a0[j] * r;            // L[j][j] = sqrt(pivot); rows below: column j of L
+        a1[j] *= r;
+        if (lane == j && j < kb) rinv[k0 + j] = r;
+#pragma unroll
+        for (int c = j + 1; c < NB; ++c) {
+          const T lcj = __shfl_sync(0xffffffffu, a0[j], c);  // L[k0 + c][k0 + j]
+          if (lane >= c) a0[c] -= a0[j] * lcj;
+          a1[c] -= a1[j] * lcj;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < NB; ++c) {
+        if (ok0 && c < kb && lane >= c) W[i0 * ld + k0 + c] = a0[c];
+        if (ok1 && c < kb) W[i1 * ld + k0 + c] = a1[c];
+      }
+    }
+    __syncthreads();
+    const int rem = d - k0 - kb;
+    if (rem > 0) {               // kb == NB here
+      const T* L21 = W + (k0 + NB) * ld + k0;
+      T* C = W + (k0 + NB) * ld + (k0 + NB);
+      gemm_cta<T, false, true>(rem, rem, NB, L21, L21, ld, [&](int i, int jj, T v) { C[i * ld + jj] -= v; });
+      __syncthreads();
+    }
+  }
+}
+// X <- L^-1 X (forward) / X <- L^-T X (backward) for the ncol columns of X with the factor chol_panel8 left in W:
+// panels of 16 rows; inside a panel one thread per column substitutes with the panel's 16 entries in registers (L is
+// read by broadcast), the rest of the rows are updated by a rank-16 product on the FP64 tensor pipe.
+template <typename T> __device__ __forceinline__ void tri_forward(const GenLayout& L, const T* W, const T* rinv, T* X, int ncol) {
+  const int d = L.d, ld = L.ld;
+  for (int k0 = 0; k0 < d; k0 += 16) {
+    const int kb = (d - k0 < 16) ? d - k0 : 16;
+    for (int c = threadIdx.x; c < ncol; c += blockDim.x) {
+      T x[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] = (i < kb) ? X[(k0 + i) * ld + c] : T(0);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (i < kb) {
+          const T z = x[i] * rinv[k0 + i];
+          x[i] = z;
+#pragma unroll
+          for (int q = i + 1; q < 16; ++q) if (q < kb) x[q] -= W[(k0 + q) * ld + k0 + i] * z;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) if (i < kb) X[(k0 + i) * ld + c] = x[i];
+    }
+    __syncthreads();
+    const int rem = d - k0 - kb;
+    if (rem > 0) {               // kb == 16 here
+      T* C = X + (k0 + 16) * ld;
+      gemm_cta<T, false, false>(rem, ncol, 16, W + (k0 + 16) * ld + k0, X + k0 * ld, ld, [&](int i, int j, T v) { C[i * ld + j] -= v; });
+      __syncthreads();
+    }
+  }
+}
+template <typename T> __device__ __forceinline__ void tri_backward(const GenLayout& L, const T* W, const T* rinv, T* X, int ncol) {
+  const int d = L.d, ld = L.ld;
+  for (int k0 = ((d - 1) >> 4) << 4; k0 >= 0; k0 -= 16) {
+    const int kb = (d - k0 < 16) ? d - k0 : 16;
+    for (int c = threadIdx.x; c < ncol; c += blockDim.x) {
+      T x[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] = (i < kb) ? X[(k0 + i) * ld + c] : T(0);
+#pragma unroll
+      for (int i = 15; i >= 0; --i) {
+        if (i < kb) {
+          const T z = x[i] * rinv[k0 + i];
+          x[i] = z;
+#pragma unroll
+          for (int q = 0; q < i; ++q) x[q] -= W[(k0 + i) * ld + k0 + q] * z;      // L^T[q][i] = L[i][q]
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) if (i < kb) X[(k0 + i) * ld + c] = x[i];
+    }
+    __syncthreads();
+    if (k0 > 0) {
+      // rows [0, k0) -= L[k0.., 0..k0)^T X[k0..]; the k range is kb: rows d.. of both tiles are zero padding
+      gemm_cta<T, true, false>(k0, ncol, kb, W + k0 * ld, X + k0 * ld, ld, [&](int i, int j, T v) { X[i * ld + j] -= v; });
+      __syncthreads();
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -646,7 +758,7 @@ template <typename T> size_t generic_filter_smem(int d) {
 }
 template <typename T> size_t generic_gain_smem(int d) {
   const GenLayout L = gen_layout(d);
-  return (size_t)(2 * L.msz + 5 * d + 16) * sizeof(T) + (size_t)(2 * d + 8) * sizeof(int) + 256;
+  return (size_t)(2 * L.msz + 7 * d + 16) * sizeof(T) + (size_t)(2 * d + 8) * sizeof(int) + 256;
 }
 template <typename T> size_t generic_smoother_smem(int d) {
   const GenLayout L = gen_layout(d);
@@ -668,10 +780,12 @@ template <typename T> __device__ __forceinline__ void scale_vectors(int d, const
 
 // ------------------------------------------------------------------------------------------------
 // fold: one CTA per chunk reduces its steps to the scan element (A, b, C, eta, J) of SURVEY.md 7.3
-template <typename T>
+template <typename T, bool GS>
 __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_fold_kernel(const GenArgs<T> g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  SmemCarver<T> sc(g.gscratch ? g.gscratch + (size_t)blockIdx.x * g.gscratch_stride : smem_raw);
+  // GS: the working set lives in per-CTA global scratch (d > 64); otherwise in shared memory — a compile-time choice so
+  // that the shared-memory build addresses its tiles with LDS / STS and 32-bit offsets instead of generic 64-bit pointers
+  SmemCarver<T> sc(GS ? g.gscratch + (size_t)blockIdx.x * g.gscratch_stride : smem_raw);
   const GenLayout L = gen_layout(g.d);
   const int d = L.d, ld = L.ld, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   T* A = sc.take(L.msz); T* A2 = sc.take(L.msz); T* C = sc.take(L.msz); T* Y = sc.take(L.msz); T* J = sc.take(L.msz);
@@ -769,10 +883,12 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_fold_kernel(const Gen
 // solve reads them, and it solves in scaled coordinates too).
 enum { KJX_WALK_FLAT = 0, KJX_WALK_TOP = 1, KJX_WALK_INNER = 2 };
 
-template <typename T>
+template <typename T, bool GS>
 __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_boundary_kernel(const GenArgs<T> g, int mode, int gsz) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  SmemCarver<T> sc(g.gscratch ? g.gscratch + (size_t)blockIdx.x * g.gscratch_stride : smem_raw);
+  // GS: the working set lives in per-CTA global scratch (d > 64); otherwise in shared memory — a compile-time choice so
+  // that the shared-memory build addresses its tiles with LDS / STS and 32-bit offsets instead of generic 64-bit pointers
+  SmemCarver<T> sc(GS ? g.gscratch + (size_t)blockIdx.x * g.gscratch_stride : smem_raw);
   const GenLayout L = gen_layout(g.d);
   const int d = L.d, dd = d * d, ld = L.ld;
   T* P = sc.take(L.msz); T* M = sc.take(L.msz); T* R = sc.take(L.msz); T* Tm = sc.take(L.msz);
@@ -884,10 +1000,12 @@ template <typename T> size_t generic_group_smem(int d) {
   const GenLayout L = gen_layout(d);
   return (size_t)(5 * L.msz + 8 * d + 16 + 32) * sizeof(T) + (size_t)(d + 8) * sizeof(int) + 512;
 }
-template <typename T>
+template <typename T, bool GS>
 __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_group_kernel(const GenArgs<T> g, int gsz) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  SmemCarver<T> sc(g.gscratch ? g.gscratch + (size_t)blockIdx.x * g.gscratch_stride : smem_raw);
+  // GS: the working set lives in per-CTA global scratch (d > 64); otherwise in shared memory — a compile-time choice so
+  // that the shared-memory build addresses its tiles with LDS / STS and 32-bit offsets instead of generic 64-bit pointers
+  SmemCarver<T> sc(GS ? g.gscratch + (size_t)blockIdx.x * g.gscratch_stride : smem_raw);
   const GenLayout L = gen_layout(g.d);
   const int d = L.d, dd = d * d, ld = L.ld;
   T* T0 = sc.take(L.msz); T* T1 = sc.take(L.msz); T* T2 = sc.take(L.msz); T* T3 = sc.take(L.msz); T* T4 = sc.take(L.msz);
@@ -955,10 +1073,12 @@ __global__ void __launch_bounds__(128) generic_loglik_kernel(const SiteModel sit
 
 // ------------------------------------------------------------------------------------------------
 // forward filter, sde_gp.py:271-306
-template <typename T>
+template <typename T, bool GS>
 __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_filter_kernel(const GenArgs<T> g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  SmemCarver<T> sc(g.gscratch ? g.gscratch + (size_t)blockIdx.x * g.gscratch_stride : smem_raw);
+  // GS: the working set lives in per-CTA global scratch (d > 64); otherwise in shared memory — a compile-time choice so
+  // that the shared-memory build addresses its tiles with LDS / STS and 32-bit offsets instead of generic 64-bit pointers
+  SmemCarver<T> sc(GS ? g.gscratch + (size_t)blockIdx.x * g.gscratch_stride : smem_raw);
   const GenLayout L = gen_layout(g.d);
   const int d = L.d, dd = d * d, ld = L.ld, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   T* P = sc.take(L.msz); T* Y = sc.take(L.msz); T* Pinf = sc.take(L.msz);
@@ -1174,14 +1294,16 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS, 1) generic_filter_blocks_kern
 // two products per step.  Gt and Lc go out in the padded tile layout ([d][ld]: 16-byte rows) so that the smoother can
 // fetch each with one bulk copy.  Working set: two tiles in shared memory (61 KB at d = 59, three CTAs per SM).
 template <typename T> __host__ __device__ inline int gen_vec_stride(int d) { return (d + 3) & ~3; }   // 16-byte multiple for both types
-template <typename T>
+template <typename T, bool GS>
 __global__ void __launch_bounds__(KJX_GEN_GAIN_THREADS, 3) generic_gain_kernel(const GenArgs<T> g, T* __restrict__ Gt_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  SmemCarver<T> sc(g.gscratch ? g.gscratch + (size_t)blockIdx.x * g.gscratch_stride : smem_raw);
+  // GS: the working set lives in per-CTA global scratch (d > 64); otherwise in shared memory — a compile-time choice so
+  // that the shared-memory build addresses its tiles with LDS / STS and 32-bit offsets instead of generic 64-bit pointers
+  SmemCarver<T> sc(GS ? g.gscratch + (size_t)blockIdx.x * g.gscratch_stride : smem_raw);
   const GenLayout L = gen_layout(g.d);
   const int d = L.d, dd = d * d, ld = L.ld, tsz = d * ld, gs = gen_vec_stride<T>(d), lane = threadIdx.x & 31;
   T* W = sc.take(L.msz); T* Gt = sc.take(L.msz);
-  T* vals = sc.take(4 * d); T* scr16 = sc.take(16); T* mpv = sc.take(d);
+  T* vals = sc.take(4 * d); T* mpv = sc.take(d); T* rinv = sc.take(d); T* scr16 = sc.take(16);
   int* c0n = sc.take_int(d); int* bstart = sc.take_int(d + 1);
   KJX_GEN_VEC(e, 2 * L.msz) W[e] = T(0);
   fetch_c0n<T>(g, c0n);                                      // block structure of A: first rows of the diagonal blocks
@@ -1205,15 +1327,16 @@ __global__ void __launch_bounds__(KJX_GEN_GAIN_THREADS, 3) generic_gain_kernel(c
     __syncthreads();
     rows_left_inplace<T>(L, vals, c0n, bstart, nblk, Gt);                           // Gt <- A Pf                  (:353)
     __syncthreads();
-    chol_blocked<T>(L, W, scr16);                                                   // utils.py:29
-    chol_forward_blocked<T>(L, W, Gt, d);                                           // Gt <- Z = L^-1 A Pf
+    // utils.py:29; Gt <- Z = L^-1 A Pf.  Shared-memory build (d <= 64): the register-panel factorisation (64 rows)
+    if constexpr (!GS) { chol_panel8<T>(L, W, rinv); tri_forward<T>(L, W, rinv, Gt, d); }
+    else { chol_blocked<T>(L, W, scr16); chol_forward_blocked<T>(L, W, Gt, d); }
     if (g.Lc) {
       T* Lo = g.Lc + n * (int64_t)tsz;
       gemm_cta<T, true, false>(d, d, d, Gt, Gt, ld, [&](int i, int j, T v) { Lo[i * ld + j] = Pf[i * d + j] - v; });   // Lc = Pf - Z^T Z
       KJX_GEN_ROWS(i, d) for (int j = d + lane; j < ld; j += 32) Lo[i * ld + j] = T(0);   // padding columns: the smoother's k loops read them
       __syncthreads();
     }
-    chol_backward_blocked<T>(L, W, Gt, d);                                          // Gt <- L^-T Z               (:359, utils.py:30)
+    if constexpr (!GS) tri_backward<T>(L, W, rinv, Gt, d); else chol_backward_blocked<T>(L, W, Gt, d);   // Gt <- L^-T Z   (:359, utils.py:30)
     T* Go = Gt_out + n * (int64_t)tsz;
     KJX_GEN_ROWS(i, d) KJX_GEN_COLS(j, ld) Go[i * ld + j] = Gt[i * ld + j];             // whole padded rows (padding stays zero)
     if (g.gc) KJX_GEN_VEC(i, d) { T v = mf[i]; for (int k = 0; k < d; ++k) v -= Gt[k * ld + i] * mpv[k]; g.gc[n * (int64_t)gs + i] = v; }
@@ -1251,11 +1374,13 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, 
 // affine recursion with the terms generic_gain_kernel prepared — two d^3 products on the FP64 tensor pipe per step, the
 // next step's (Gt, Lc, gc) arriving by bulk copy (TMA, mbarrier) while the current one is being multiplied.  The marginal
 // H m, H P H^T of every step goes to post_mean / post_var; the site update is a batched kernel afterwards.
-template <typename T>
+template <typename T, bool GS>
 __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_smoother_kernel(const GenArgs<T> g, const T* __restrict__ Gt_in) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long bars[2];
-  SmemCarver<T> sc(g.gscratch ? g.gscratch + (size_t)blockIdx.x * g.gscratch_stride : smem_raw);
+  // GS: the working set lives in per-CTA global scratch (d > 64); otherwise in shared memory — a compile-time choice so
+  // that the shared-memory build addresses its tiles with LDS / STS and 32-bit offsets instead of generic 64-bit pointers
+  SmemCarver<T> sc(GS ? g.gscratch + (size_t)blockIdx.x * g.gscratch_stride : smem_raw);
   const GenLayout L = gen_layout(g.d);
   const int d = L.d, dd = d * d, ld = L.ld, tsz = d * ld, gs = gen_vec_stride<T>(d), lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   T* Ps = sc.take(L.msz); T* T1 = sc.take(L.msz);
@@ -1265,7 +1390,7 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_smoother_kernel(const
   T* ms = sc.take(d); T* mnew = sc.take(d); T* mf = sc.take(d); T* Hrow = sc.take(d);
   T* rv = sc.take(d); T* part = sc.take(KJX_GEN_WARPS * d); T* Dv = sc.take(d); T* Dinv = sc.take(d); T* dscr = sc.take(16);
   int* piv = sc.take_int(d);
-  const bool tma = g.gscratch == nullptr;                  // tiles in shared memory: bulk copies; in global scratch: plain copies
+  constexpr bool tma = !GS;                                // tiles in shared memory: bulk copies; in global scratch: plain copies
   const int64_t n0 = (int64_t)blockIdx.x * g.chunk_len, n1 = (n0 + g.chunk_len < g.N) ? n0 + g.chunk_len : g.N;
   KJX_GEN_VEC(e, 6 * L.msz) Ps[e] = T(0);
   scale_vectors<T>(d, g.Pinf, Dv, Dinv);
