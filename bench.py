@@ -388,6 +388,7 @@ def main():
     for k in range(3 + n_ev):
         it_ph.iteration(events=ev[max(k - 3, 0)], reduce_nlml=reduce_ph)
     barrier()
+    phases = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(3)] for e in ev]).mean(axis=0)   # ms
     if linked:
         del it_ph
         torch.cuda.empty_cache()
@@ -423,7 +424,6 @@ def main():
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms_total = start.elapsed_time(stop)
-    phases = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(3)] for e in ev]).mean(axis=0)   # ms
     nlml = float(nl_t)
 
     # ---- parity at the benchmark size (untimed): one more iteration, its outputs gathered on rank 0 and compared

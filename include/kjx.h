@@ -229,7 +229,7 @@ int kjx_exchange_fold_f64(const kjx_model_t* m, const double* my_summary, double
  * bits) while the other blocks work; the block that finishes last closes the epoch.  peer_bufs: DEVICE array [world] of receive-buffer pointers (symmetric memory;
  * kjx_shard_link_doubles(world, stride) doubles each, ZERO before first use): summaries [2][world][stride] | flags
  * [2][world] | nlml [2][world] | nlml flags [2][world]; my_buf: this rank's own buffer, by value.  ctrl: DEVICE uint64[4]
- * owned by this rank, zero before first use (epoch and tickets).  Graph-capturable; all ranks must make the call the same number of times.  world == 1
+ * owned by this rank, zero before first use (epoch and tickets).  world <= 32.  Graph-capturable; all ranks must make the call the same number of times.  world == 1
  * works with an ordinary device buffer.  Same outputs as kjx_filter_summary / exchange / filter_apply / smoother_apply. */
 size_t kjx_shard_link_doubles(int32_t world, int64_t stride);
 int kjx_sharded_iteration_f64(const kjx_model_t* m, int64_t N, const double* dt, const double* y,

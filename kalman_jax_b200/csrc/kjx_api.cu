@@ -138,7 +138,7 @@ template <typename T, int D> struct SmallLayout {
     auto take = [&](size_t n) { size_t r = o; o += round_up(n * sizeof(T), 256); return r; };
     off_ftp = take(FNS * cstride); off_fbt = take(FNS * bstride); off_fbp = take(FNS * bstride); off_fst = take(FNS);
     off_sts = take(SNS * cstride); off_sbt = take(SNS * bstride); off_sbs = take(SNS * bstride); off_sst = take(SNS);
-    off_nl = take(round_up((size_t)((std::max(nchunks, fchunks) + 31) / 32), 32)); off_fin = take(D + D * D); off_sin = take(D + D * D);
+    off_nl = take(round_up((size_t)((std::max(nchunks, fchunks) + 31) / 32) + 2, 32)); off_fin = take(D + D * D); off_sin = take(D + D * D);
     off_info = take(D + D * D);
     // three scan levels of the fused path: elements, exclusive prefix, exclusive suffix (strides = whole segments)
     // segments of 64 while three levels of 64 hold every chunk (shorter dependent chains), else 128
@@ -179,7 +179,7 @@ template <typename T, int D>
 void bind_fused(FusedArgs<T, D>& fa, const SmallLayout<T, D>& lay, void* ws) {
   char* w = (char*)ws;
   bind_workspace<T, D>(fa.a, lay, ws);
-  fa.s_info_in = (T*)(w + lay.off_info); fa.xf = (T*)(w + lay.off_xf);
+  fa.s_info_in = (T*)(w + lay.off_info); fa.info_out = (T*)(w + lay.off_info); fa.xf = (T*)(w + lay.off_xf);
   fa.seg0 = lay.seg0; fa.seg1 = lay.seg1;
   fa.a.L = lay.plan.L1; fa.L2 = lay.plan.L2; fa.nbig = lay.plan.nbig; fa.a.nchunks = lay.plan.nchunks;
   for (int l = 0; l < 3; ++l) {
@@ -284,10 +284,11 @@ struct Fused {
   void filter_linked(cudaStream_t st) {
     const bool fast = gauss_ep(m);
     fa.store_xf = 1;
-    if (fast && fa.vec_ok) fused_filter_kernel<T, KIND, true, true, true, true><<<grid(), threads(), 0, st>>>(fa);
-    else if (fast) fused_filter_kernel<T, KIND, true, false, true, true><<<grid(), threads(), 0, st>>>(fa);
-    else if (fa.vec_ok) fused_filter_kernel<T, KIND, false, true, true, true><<<grid(), threads(), 0, st>>>(fa);
-    else fused_filter_kernel<T, KIND, false, false, true, true><<<grid(), threads(), 0, st>>>(fa);
+    const unsigned g1 = grid() + 1;                         // one extra block: folds the later shards' elements for the smoother
+    if (fast && fa.vec_ok) fused_filter_kernel<T, KIND, true, true, true, true><<<g1, threads(), 0, st>>>(fa);
+    else if (fast) fused_filter_kernel<T, KIND, true, false, true, true><<<g1, threads(), 0, st>>>(fa);
+    else if (fa.vec_ok) fused_filter_kernel<T, KIND, false, true, true, true><<<g1, threads(), 0, st>>>(fa);
+    else fused_filter_kernel<T, KIND, false, false, true, true><<<g1, threads(), 0, st>>>(fa);
   }
   void smoother_linked(T* post_mean, T* post_var, T* new_site_mean, T* new_site_var, bool update, cudaStream_t st) {
     fa.a.smooth_mean = post_mean; fa.a.smooth_cov = post_var; fa.a.new_site_mean = new_site_mean; fa.a.new_site_var = new_site_var;
@@ -931,7 +932,7 @@ int kjx_sharded_iteration_f64(const kjx_model_t* m, int64_t N, const double* dt,
   if ((site_mean == nullptr) != (site_cov == nullptr)) return KJX_ERR_INVALID_ARG;
   if ((post_mean == nullptr) != (post_var == nullptr)) return KJX_ERR_INVALID_ARG;
   if ((new_site_mean == nullptr) != (new_site_cov == nullptr)) return KJX_ERR_INVALID_ARG;
-  if (world < 1 || world > 64 || rank < 0 || rank >= world) return KJX_ERR_INVALID_ARG;
+  if (world < 1 || world > 32 || rank < 0 || rank >= world) return KJX_ERR_INVALID_ARG;
   if (stride < (int64_t)kjx_filter_summary_doubles(m->state_dim)) return KJX_ERR_INVALID_ARG;
   ShardLink link;
   link.peer_bufs = peer_bufs; link.my_buf = my_buf; link.ctrl = (unsigned long long*)ctrl; link.nlml_out = nlml; link.stride = stride;

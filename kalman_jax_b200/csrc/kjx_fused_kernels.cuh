@@ -146,12 +146,33 @@ __device__ __forceinline__ void link_wait_element(const ShardLink& l, double* my
   fsum_unpack<double, D>(v, s);
 }
 
+// Elements of the shards [r0, r1) of this epoch -> stage[(r - r0) * NS ..], one LANE per element (warp 0 calls): every
+// lane waits for its flag and issues its 27 loads, so the NVLink / HBM latencies of all elements overlap (walking them
+// one after the other cost ~2 us per element on the critical path of an 8-GPU iteration).  At most 32 elements.
+template <int D>
+__device__ __forceinline__ void link_stage_elements(const ShardLink& l, int r0, int r1, double* stage) {
+  constexpr int NS = FSum<double, D>::NS;
+  const int lane = threadIdx.x & 31;
+  if (r1 > r0) {
+    const unsigned long long e = l.ctrl[0] + 1ull;
+    const int par = (int)(e & 1ull);
+    for (int r = r0 + lane; r < r1; r += 32) {
+      wait_flag_sys(link_flag(l.my_buf, l, par, r), e);
+      const double* src = link_summary(l.my_buf, l, par, r);
+#pragma unroll
+      for (int k = 0; k < NS; ++k) stage[(r - r0) * NS + k] = ld_relaxed_sys(src + k);
+    }
+  }
+  __syncwarp();
+}
+
 template <typename T, int D> struct FusedArgs {
   SmallArgs<T, D> a;        // prior, site model, data pointers, scan workspace (see kjx_small_kernels.cuh)
   ShardLink link;           // time-sharded iteration only (kernels instantiated with SHARDED)
   ScanLevel<T, D> lvl[3];   // chunk elements / segment totals / super-segment totals with their scans
   T* xf;                    // filtered moments, private layout
   const T* s_info_in;       // [D + D*D] information (eta, J) of all later shards about this shard's last state
+  T* info_out;              // sharded iteration: where the filter kernel's extra block leaves that information (same buffer)
   int vec_ok;               // every per-step array is 32-byte (fp64) / 16-byte (fp32) aligned
   int L2; int64_t nbig;     // chunks [0, nbig) have a.L steps, chunks [nbig, nchunks) have L2 (= a.L - 4 or a.L) steps:
                             // two lengths make the chunk count whatever fills the SMs evenly (see plan_chunks)
@@ -382,8 +403,9 @@ __global__ void __launch_bounds__(64) fused_segscan_top_kernel(const ScanLevel<T
 // PLAIN: the run() iteration (no mask, filtered moments parked in the private layout, sites not written back).
 // !PLAIN adds, with runtime checks: masked (predict-only) steps, energy-only runs (no filtered moments kept) and
 // writing the initialised sites — the stand-alone kjx_filter and the prediction path.
-// SHARDED (fp64): the filtered state entering the shard is not read from f_state_in but folded, by thread 0 of every
-// block, from the elements the earlier shards published into this rank's receive buffer (waiting for them if need be).
+// SHARDED (fp64): the filtered state entering the shard is not read from f_state_in but folded, by warp 0 of every
+// block, from the elements the earlier shards published into this rank's receive buffer (waiting for them if need be);
+// ONE EXTRA block folds the later shards' elements into the information the smoother kernel will need.
 // The per-block log-likelihood sums are picked up by the smoother kernel's extra block.
 template <typename T, int KIND, bool GAUSS_EP, bool VEC, bool PLAIN, bool SHARDED = false>
 __global__ void __launch_bounds__(KJX_BLOCK, KJX_R3_MINB) fused_filter_kernel(const FusedArgs<T, BlockDim<KIND>::D> fa) {
@@ -398,19 +420,38 @@ __global__ void __launch_bounds__(KJX_BLOCK, KJX_R3_MINB) fused_filter_kernel(co
   T Pinf[D][D]; load_pinf<T, D>(a.prior, Pinf);
   T nl = T(0);
   if constexpr (SHARDED && std::is_same<T, double>::value) {
-    if (threadIdx.x == 0) {
-      const ShardLink& l = fa.link;
-      FiltState<double, D> x0;
-#pragma unroll
-      for (int i = 0; i < D; ++i) { x0.m[i] = 0.0; for (int j = 0; j < D; ++j) x0.P[i][j] = Pinf[i][j]; }    // sde_gp.py:265
-      if (l.rank > 0) {                                      // shard 0 starts from the prior: nothing to wait for
-        const unsigned long long e = l.ctrl[0] + 1ull;
-        const int par = (int)(e & 1ull);
+    const ShardLink& l = fa.link;
+    __shared__ double stage[31 * FSum<double, D>::NS];       // world <= 32
+    if (threadIdx.x < 32) {
+      if (blockIdx.x == gridDim.x - 1) {
+        // The EXTRA block (no chunks): information of the LATER shards about this shard's last state, for the smoother
+        // kernel — folded here, off the critical path, while the other blocks filter.
+        link_stage_elements<D>(l, l.rank + 1, l.world, stage);
+        if (threadIdx.x == 0) {
+          Info<double, D> f; info_zero<double, D>(f);
 #pragma unroll 1
-        for (int r = 0; r < l.rank; ++r) { FSum<double, D> sr; link_wait_element<D>(l, l.my_buf, par, e, r, sr); fsum_apply<double, D>(sr, x0); }
-      }
+          for (int r = l.world - 1; r > l.rank; --r) {
+            FSum<double, D> sr; fsum_unpack<double, D>(stage + (r - l.rank - 1) * FSum<double, D>::NS, sr);
+            fsum_combine_info<double, D>(sr, f, f);
+          }
 #pragma unroll
-      for (int i = 0; i < D; ++i) { st_in[i] = x0.m[i]; for (int j = 0; j < D; ++j) st_in[D + i * D + j] = x0.P[i][j]; }
+          for (int i = 0; i < D; ++i) { fa.info_out[i] = f.eta[i]; for (int j = 0; j < D; ++j) fa.info_out[D + i * D + j] = f.J[i][j]; }
+        }
+      } else {
+        link_stage_elements<D>(l, 0, l.rank, stage);         // shard 0 starts from the prior: nothing to wait for
+        if (threadIdx.x == 0) {
+          FiltState<double, D> x0;
+#pragma unroll
+          for (int i = 0; i < D; ++i) { x0.m[i] = 0.0; for (int j = 0; j < D; ++j) x0.P[i][j] = Pinf[i][j]; }    // sde_gp.py:265
+#pragma unroll 1
+          for (int r = 0; r < l.rank; ++r) {
+            FSum<double, D> sr; fsum_unpack<double, D>(stage + r * FSum<double, D>::NS, sr);
+            fsum_apply<double, D>(sr, x0);
+          }
+#pragma unroll
+          for (int i = 0; i < D; ++i) { st_in[i] = x0.m[i]; for (int j = 0; j < D; ++j) st_in[D + i * D + j] = x0.P[i][j]; }
+        }
+      }
     }
     __syncthreads();
   }
@@ -510,16 +551,15 @@ __device__ __forceinline__ void smoothed_outputs(const SmallArgs<T, D>& a, const
   }
 }
 
-// SHARDED (fp64): the information of the later shards about this shard's last state is folded, by thread 0 of every
-// block, from the elements in the receive buffer.  The grid has ONE EXTRA block that exchanges the shards' partial nlml
-// values while the others work; the block that finishes last closes the epoch.
+// SHARDED (fp64): the information of the later shards about this shard's last state was left in s_info_in by the filter
+// kernel's extra block.  The grid has ONE EXTRA block that exchanges the shards' partial nlml values while the others
+// work; the block that finishes last closes the epoch.
 template <typename T, int KIND, bool GAUSS_EP, bool VEC, bool SHARDED = false>
 __global__ void __launch_bounds__(KJX_BLOCK, KJX_R4_MINB) fused_smoother_kernel(const FusedArgs<T, BlockDim<KIND>::D> fa) {
   constexpr int D = BlockDim<KIND>::D;
   constexpr int NP = Packed<D>::NP;
   using FS = FSum<T, D>;
   const SmallArgs<T, D>& a = fa.a;
-  __shared__ T info_in[D + D * D];
   __shared__ int s_last;
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t s0, s1; chunk_range<T, D>(fa, c, s0, s1);
@@ -555,16 +595,6 @@ __global__ void __launch_bounds__(KJX_BLOCK, KJX_R4_MINB) fused_smoother_kernel(
         }
         l.nlml_out[0] = total;
       }
-    } else if (threadIdx.x == 0) {
-      Info<double, D> f; info_zero<double, D>(f);
-      if (l.rank + 1 < l.world) {                            // the last shard ends the series: no later information
-        const unsigned long long e = l.ctrl[0] + 1ull;
-        const int par = (int)(e & 1ull);
-#pragma unroll 1
-        for (int r = l.world - 1; r > l.rank; --r) { FSum<double, D> sr; link_wait_element<D>(l, l.my_buf, par, e, r, sr); fsum_combine_info<double, D>(sr, f, f); }
-      }
-#pragma unroll
-      for (int i = 0; i < D; ++i) { info_in[i] = f.eta[i]; for (int j = 0; j < D; ++j) info_in[D + i * D + j] = f.J[i][j]; }
     }
     __syncthreads();
   }
@@ -578,7 +608,7 @@ __global__ void __launch_bounds__(KJX_BLOCK, KJX_R4_MINB) fused_smoother_kernel(
   FiltState<T, D> x;
   int64_t k = s1 - 1;
   {
-    Info<T, D> info; load_info<T, D>(SHARDED ? info_in : fa.s_info_in, info);
+    Info<T, D> info; load_info<T, D>(fa.s_info_in, info);     // sharded: left there by the filter kernel's extra block
     {   // everything after this chunk
       int64_t idx[3] = {c, c / fa.seg0, c / ((int64_t)fa.seg0 * fa.seg1)};
 #pragma unroll 1
