@@ -685,17 +685,17 @@ int discretise_T(const kjx_model_t* m, int64_t N, const T* dt, T* A, T* Q, void*
   DiscArgs da; memset(&da, 0, sizeof(da));
   da.d = m->state_dim; da.n_blocks = m->n_blocks;
   for (int b = 0; b < m->n_blocks; ++b) da.blocks[b] = m->blocks[b];
+  const int threads = 128, nw = threads / 32;
+  const size_t smem = (size_t)nw * m->state_dim * (4 * sizeof(T) + sizeof(int));
+  if (smem > 48 * 1024) return KJX_ERR_UNSUPPORTED;          // before anything is allocated
   // Pinf is a host pointer: stage it into a small device buffer owned by this call's stream order
   double* pinf_dev = nullptr;
   if (Q) {
     KJX_CUDA_CHECK(cudaMallocAsync((void**)&pinf_dev, sizeof(double) * m->state_dim * m->state_dim, (cudaStream_t)stream));
     KJX_CUDA_CHECK(cudaMemcpyAsync(pinf_dev, m->Pinf, sizeof(double) * m->state_dim * m->state_dim, cudaMemcpyHostToDevice, (cudaStream_t)stream));
   }
-  const int threads = 128, nw = threads / 32;
   const int64_t blocks = (N + nw - 1) / nw;
-  const size_t smem = (size_t)nw * m->state_dim * (4 * sizeof(T) + sizeof(int));
-  if (smem > 48 * 1024) return KJX_ERR_UNSUPPORTED;
-  discretise_kernel<T><<<(unsigned)std::min<int64_t>(blocks, 148 * 16), threads, smem, (cudaStream_t)stream>>>(da, N, dt, A, Q, pinf_dev);
+  discretise_kernel<T><<<(unsigned)std::min<int64_t>(blocks, (int64_t)sm_count() * 16), threads, smem, (cudaStream_t)stream>>>(da, N, dt, A, Q, pinf_dev);
   if (pinf_dev) KJX_CUDA_CHECK(cudaFreeAsync(pinf_dev, (cudaStream_t)stream));
   KJX_CUDA_CHECK(cudaGetLastError());
   return KJX_OK;

@@ -173,9 +173,14 @@ class SDEGP(object):
 
     # ------------------------------------------------------------------ plumbing
     def _dev(self, x):
+        """Device copy of a host array.  Only the TRAINING arrays (self.y, self.dt) stay resident between calls; anything
+        else (merged train/test grids of predict(), zeros of posterior_sample(), ...) is uploaded for the call only, so
+        repeated predictions do not accumulate device memory."""
         if x is None or isinstance(x, torch.Tensor):
             return _as_dev(x, self.dtype, self.device)
-        key = id(x)
+        if not (x is self.y or x is self.dt):
+            return _as_dev(x, self.dtype, self.device)
+        key = (id(x), self.dtype)
         hit = self._resident.get(key)
         if hit is None or hit[0] is not x:
             hit = (x, _as_dev(x, self.dtype, self.device))
@@ -196,6 +201,9 @@ class SDEGP(object):
             # spatio-temporal prior with scattered data: H depends on r_n (priors.py:1148-1161).  All steps at once:
             # one factorisation of Kzz and one solve with N right-hand sides instead of N of each
             r_all = np.asarray(r, dtype=np.float64).reshape(len(r), -1)
+            # rows without a spatial location (test steps of a different spatial layout, sde_gp.py:77: predict-only, their
+            # measurement row is never used) get a placeholder so the batched solve stays finite
+            r_all = np.where(np.isnan(r_all), 0.0, r_all)
             Kx = self.prior.spatial_weights(r_all[:, 0], theta_prior)                 # [N, M]
             bs = self.prior.state_dim // self.prior.M                                 # temporal states per inducing point
             Hs = np.zeros((Kx.shape[0], 1, self.prior.state_dim))
@@ -248,6 +256,8 @@ class SDEGP(object):
         y_d = self._dev(y)
         sm_in = sv_in = new_sm = new_sv = None
         if site_params is not None:
+            if y is None:
+                raise ValueError("the site update needs the observations: pass y together with site_params")
             sm_in, sv_in = self._dev(site_params[0]), self._dev(site_params[1])
             new_sm = torch.empty(N, f, 1, dtype=self.dtype, device=self.device)
             new_sv = torch.empty(N, f, f, dtype=self.dtype, device=self.device)
@@ -270,7 +280,14 @@ class SDEGP(object):
 
     # ------------------------------------------------------------------ gradients (finite differences)
     def _energy(self, params, site_params):
-        return float(self.kalman_filter(self.y, self.dt, params, False, None, site_params, self.r))
+        """Filter energy for the finite differences: ALWAYS through the fp64 entry points — in float the energy carries
+        ~1e-4 of rounding noise, which a difference over eps = 1e-5 would turn into a meaningless gradient."""
+        keep = self.dtype
+        self.dtype = torch.float64
+        try:
+            return float(self.kalman_filter(self.y, self.dt, params, False, None, site_params, self.r))
+        finally:
+            self.dtype = keep
 
     def _fd_grad(self, params, site_params, eps=1e-5):
         prior_p, lik_p = params
@@ -382,13 +399,24 @@ class SDEGP(object):
         if t is None:
             t, y, r = self.t, self.y, self.r
         (t, y, r, r_test, dt, train_id, test_id, mask) = test_input_admin(self.t, self.y, self.r, t, None, r)
-        return_full = r_test.shape[1] != r.shape[1]
-        if return_full:
-            raise NotImplementedError("test points with a different spatial dimensionality (sde_gp.py:77-82)")
+        return_full = r_test.shape[1] != r.shape[1]   # spatial test locations of a different size than the training ones
         y = np.where(np.isnan(y), 0.0, y)   # masked entries are never read for their value (sde_gp.py:286)
         pm, pc, site_params = self.predict_everywhere(y, r, dt, train_id, mask, site_params, sampling, return_full)
         idx = torch.as_tensor(test_id, device=self.device)
-        return torch.squeeze(pm[idx]), torch.squeeze(pc[idx])
+        pm, pc = pm[idx], pc[idx]
+        if return_full:
+            pm, pc = self.compute_measurement(r_test, pm, pc)                        # sde_gp.py:77-82
+        return torch.squeeze(pm), torch.squeeze(pc)
+
+    # ------------------------------------------------------------------ sde_gp.py:105-108 (vmapped over the test points)
+    def compute_measurement(self, r, mean, cov, hyp_prior=None):
+        """H(r_n) m_n and H(r_n) P_n H(r_n)^T for every test point: the full-state posterior [M,d,1], [M,d,d] measured at
+        that point's own spatial locations r[M, K] (K function values per test time) -> [M,K,1], [M,K,K]."""
+        theta = _theta_prior(self.prior, self.prior.hyp) if hyp_prior is None else hyp_prior
+        r = np.asarray(r, dtype=np.float64).reshape(len(r), -1)
+        H = np.stack([self.prior.measurement_model(r[n], theta) for n in range(r.shape[0])])     # [M, K, d]
+        H = torch.as_tensor(H, dtype=mean.dtype, device=mean.device)
+        return H @ mean, H @ cov @ H.transpose(1, 2)
 
     # ------------------------------------------------------------------ sde_gp.py:386-417
     def prior_sample(self, num_samps, t=None, seed=0):
@@ -443,12 +471,17 @@ class SDEGP(object):
         if t is None:
             t, y, r = self.t, self.y, self.r
         (t, y_all, r, r_test, dt, train_id, test_id, mask) = test_input_admin(self.t, self.y, self.r, t, y, r)
-        if r_test.shape[1] != r.shape[1]:
-            raise NotImplementedError("test points with a different spatial dimensionality (sde_gp.py:133-137)")
+        return_full = r_test.shape[1] != r.shape[1]
         y_filter = np.where(np.isnan(y_all), 0.0, y_all)
-        pm, pc, _ = self.predict_everywhere(y_filter, r, dt, train_id, mask, sampling=False, return_full=False)
+        pm, pc, _ = self.predict_everywhere(y_filter, r, dt, train_id, mask, sampling=False, return_full=return_full)
         idx = torch.as_tensor(test_id, device=self.device)
+        pm, pc = pm[idx], pc[idx]
+        if return_full:
+            pm, pc = self.compute_measurement(r_test, pm, pc)                        # sde_gp.py:133-137
+            if pm.shape[1] != 1:
+                raise NotImplementedError("NLPD of several function values per test time needs a multi-dimensional "
+                                          "moment match (func_dim > 1)")
         hyp_lik = softplus(self.likelihood.hyp) if np.size(self.likelihood.hyp) else None
         # vmapped moment match with power 1 and the default 20-point Gauss-Hermite rule (sde_gp.py:139-142)
-        lpd, _, _ = self.likelihood.moment_match(y_all[test_id], pm[idx], pc[idx], hyp_lik, 1, None)
+        lpd, _, _ = self.likelihood.moment_match(y_all[test_id], pm, pc, hyp_lik, 1, None)
         return float(-torch.mean(lpd))

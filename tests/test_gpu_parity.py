@@ -225,6 +225,32 @@ def test_masked_prediction_path_vs_oracle():
         assert abs(nlpd - want) <= TOL64 * abs(want)
 
 
+def test_predict_with_a_different_spatial_test_layout():
+    """predict() when every test time carries K spatial locations while the training points carry one
+    (sde_gp.py:77-82: full-state posterior, then compute_measurement per test point): column k must equal the prediction at
+    the single location r_test[:, k], which the oracle computes."""
+    kjx = _kjx()
+    rng = np.random.default_rng(4)
+    N, M, K = 80, 13, 4
+    t = np.sort(rng.uniform(0, 10, N)); r = rng.uniform(-2, 2, N)
+    y = np.sign(np.sin(t) + 0.5 * r + 0.3 * rng.standard_normal(N))
+    z = np.linspace(-2, 2, 7)
+    mk = lambda mod, inf: mod.SDEGP(mod.priors.SpatioTemporalMatern52(1.0, 1.5, 1.0, z=z), mod.likelihoods.Probit(), t, y, r=r,  # noqa: E731
+                                    approx_inf=inf.EP(power=0.5))
+    model, ref = mk(kjx, kjx.approximate_inference), mk(oracle, oracle.approx_inf)
+    for _ in range(2):
+        model.run(compute_grad=False)
+        ref.run()
+    t_test = np.sort(rng.uniform(0.5, 9.5, M)); r_test = rng.uniform(-2, 2, (M, K))
+    pm, pc = model.predict(t=t_test, r=r_test)
+    pm, pc = _np(pm), _np(pc)
+    assert pm.shape == (M, K) and pc.shape == (M, K, K)
+    for k in range(K):
+        wm, wv = ref.predict(t=t_test, r=r_test[:, k])
+        assert rel_err(pm[:, k], wm) < TOL64 and rel_err(pc[:, k, k], wv) < TOL64
+    assert np.max(np.abs(pc - pc.transpose(0, 2, 1))) < 1e-12
+
+
 def test_empty_series_is_a_no_op():
     kjx = _kjx()
     import ctypes as C
@@ -503,7 +529,7 @@ def _state_space_cov(prior, t):
     return K
 
 
-@pytest.mark.parametrize("prior_name", ["Matern32", "Sum"])
+@pytest.mark.parametrize("prior_name", ["Matern32", "Sum", "Sum_d59"])
 def test_prior_sample_matches_the_prior_covariance(prior_name):
     """SDEGP.prior_sample (sde_gp.py:386-417) on the GPU: the draws' sample covariance against the prior covariance
     computed from the oracle's state-space matrices (parity for sampling is in distribution); same seed -> same draws."""
@@ -513,6 +539,10 @@ def test_prior_sample_matches_the_prior_covariance(prior_name):
     y = np.zeros_like(t)
     if prior_name == "Matern32":
         mk = lambda mod: mod.priors.Matern32(1.5, 2.0)  # noqa: E731
+    elif prior_name == "Sum_d59":        # d > 32: the noise factorisation spans several warps (barrier after every column)
+        mk = lambda mod: mod.priors.Sum([mod.priors.Matern52(variance=2., lengthscale=3.),  # noqa: E731
+                                         mod.priors.QuasiPeriodicMatern32(variance=1., lengthscale_periodic=2., period=4., lengthscale_matern=20.),
+                                         mod.priors.QuasiPeriodicMatern32(variance=.5, lengthscale_periodic=1., period=1.5, lengthscale_matern=10.)])
     else:
         mk = lambda mod: mod.priors.Sum([mod.priors.Matern52(variance=2., lengthscale=3.),  # noqa: E731
                                          mod.priors.QuasiPeriodicMatern32(variance=1., lengthscale_periodic=2., period=4.,
