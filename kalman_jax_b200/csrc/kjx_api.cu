@@ -120,7 +120,7 @@ template <typename T, int D> struct SmallLayout {
   ChunkPlan plan;                   // fused kernels
   int threads; int64_t fblocks;     // fused kernels: threads per block (32 / 64 / 128) and blocks
   size_t off_ftp, off_fbt, off_fbp, off_fst, off_sts, off_sbt, off_sbs, off_sst, off_nl, off_fin, off_sin;
-  size_t off_info, off_xf, off_lvl[3][3], lvl_stride[3], total;
+  size_t off_info, off_xf, off_jac, off_jdiff, off_lvl[3][3], lvl_stride[3], total;
   int64_t lvl_n[3];
   int seg0, seg1;
   explicit SmallLayout(int64_t N) {
@@ -159,6 +159,8 @@ template <typename T, int D> struct SmallLayout {
     }
     // filtered moments between the fused filter and smoother passes: [warp][step][element][lane]
     off_xf = take(round_up((size_t)fchunks, 128) * (size_t)plan.L1 * Packed<D>::NP);
+    // site-initialisation sweeps (first iteration of a non-Gaussian model): two pairs of site arrays + per-block changes
+    off_jac = take(4 * (size_t)std::max<int64_t>(N, 1)); off_jdiff = take(round_up((size_t)fblocks + 2, 32) + 32);
     total = o;
   }
 };
@@ -355,6 +357,60 @@ int small_smoother_apply(const kjx_model_t* m, SmallArgs<T, BlockDim<KIND>::D>& 
   return KJX_OK;
 }
 
+template <typename T> __global__ void max_reduce_kernel(const T* __restrict__ v, int64_t n, T* __restrict__ out) {
+  __shared__ T red[8];
+  T m = T(0);
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { const T x = v[i]; m = (x > m) ? x : m; }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) { const T o = __shfl_down_sync(0xffffffffu, m, off); m = (o > m) ? o : m; }
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) { T t = T(0); for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t = (red[w] > t) ? red[w] : t; out[0] = t; }
+}
+template <typename T> __global__ void fill_kernel(T* a, T va, T* b, T vb, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { a[i] = va; b[i] = vb; }
+}
+
+// Sites initialised from the predictive (sde_gp.py:287 with site_params=None) for a non-Gaussian model, as the fixed
+// point of parallel-in-time sweeps (see fused_filter_kernel).  On success site_mean / site_var point at the converged
+// sites (in the workspace) and the return value is the number of sweeps; 0 = did not converge (caller falls back to the
+// one-chain kernel).  Synchronises the stream once per sweep (a scalar comes back to decide on the next one).
+template <typename T, int KIND>
+int jacobi_init_sites(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const uint8_t* mask, void* ws,
+                      const T** site_mean, const T** site_var, cudaStream_t st) {
+  constexpr int D = BlockDim<KIND>::D;
+  static const int max_sweeps = [] { const char* e = getenv("KJX_INIT_SWEEPS"); return e ? atoi(e) : 400; }();
+  if (max_sweeps <= 0) return 0;
+  SmallLayout<T, D> lay(N);
+  char* w = (char*)ws;
+  T* buf = (T*)(w + lay.off_jac);
+  T* sm[2] = {buf, buf + 2 * N}; T* sv[2] = {buf + N, buf + 3 * N};
+  T* diff = (T*)(w + lay.off_jdiff);                         // [0]: the maximum; [32..]: per block
+  // start: sites that say nothing (the first sweep then initialises every site from the prior's predictive)
+  fill_kernel<T><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(sm[0], T(0), sv[0], T(1e12), N);
+  const T tol = std::is_same<T, double>::value ? T(1e-13) : T(2e-6);
+  T prev = T(1e30);
+  for (int it = 0; it < max_sweeps; ++it) {
+    const int cur = it & 1, nxt = cur ^ 1;
+    Fused<T, KIND> f(m, N, dt, y, sm[cur], sv[cur], ws);
+    f.fa.a.mask = mask; f.fa.a.out_site_mean = sm[nxt]; f.fa.a.out_site_var = sv[nxt];
+    f.fa.store_xf = 0; f.fa.jacobi = 1; f.fa.block_diff = diff + 32;
+    f.reduce(st);
+    launch_set_prior_state<T, D>((T*)f.fa.a.f_state_in, m, st);
+    f.filter(st, /*plain=*/false);
+    max_reduce_kernel<T><<<1, 256, 0, st>>>(diff + 32, f.nthread_blocks, diff);
+    T h = T(0);
+    if (cudaMemcpyAsync(&h, diff, sizeof(T), cudaMemcpyDeviceToHost, st) != cudaSuccess) return 0;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return 0;
+    if (h <= tol) { *site_mean = sm[nxt]; *site_var = sv[nxt]; return it + 1; }
+    // the change cannot shrink below rounding noise: accept a plateau at that level, give up on a real stall
+    if (it > 8 && h >= prev && h <= T(64) * tol) { *site_mean = sm[nxt]; *site_var = sv[nxt]; return it + 1; }
+    prev = h;
+  }
+  return 0;
+}
+
 // the filter must run as one chain when sites have to be initialised from the predictive and that
 // initialisation depends on the state (anything but Gaussian + EP, utils.py:241-244)
 bool needs_sequential_filter(const kjx_model_t* m, bool have_sites) { return !have_sites && !gauss_ep(m); }
@@ -374,7 +430,13 @@ int small_filter(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const
   const bool have_sites = site_mean != nullptr;
   a.gaussian_init = (!have_sites && gauss_ep(m)) ? 1 : 0;
   if (N == 0) { cudaMemsetAsync(nlml, 0, sizeof(T), st); return KJX_OK; }
-  if ((flags & KJX_FLAG_SEQUENTIAL) || needs_sequential_filter(m, have_sites)) {
+  bool chain = (flags & KJX_FLAG_SEQUENTIAL) || needs_sequential_filter(m, have_sites);
+  if (chain && !(flags & KJX_FLAG_SEQUENTIAL)) {
+    // sites to be initialised from the predictive: parallel-in-time sweeps to their fixed point, then the ordinary pass
+    const T *jm = nullptr, *jv = nullptr;
+    if (jacobi_init_sites<T, KIND>(m, N, dt, y, mask, ws, &jm, &jv, st) > 0) { site_mean = jm; site_var = jv; chain = false; }
+  }
+  if (chain) {
     launch_set_prior_state<T, D>((T*)a.f_state_in, m, st);
     const int init = (!have_sites && !a.gaussian_init) ? 1 : 0;
     filter_sequential_kernel<T, KIND><<<1, 32, 0, st>>>(a, init);
@@ -433,7 +495,14 @@ int small_run(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const T*
   const bool have_sites = site_mean != nullptr;
   const bool seq = (flags & KJX_FLAG_SEQUENTIAL) != 0;
   const bool update = !(flags & KJX_FLAG_NO_SITE_UPDATE);
-  if (seq || needs_sequential_filter(m, have_sites)) {
+  bool chain = seq || needs_sequential_filter(m, have_sites);
+  if (chain && !seq) {
+    // first iteration of a non-Gaussian model: the sites initialised from the predictive, by parallel-in-time sweeps to
+    // their fixed point; they are then the sites of an ordinary fused iteration (sde_gp.py:183-187)
+    const T *jm = nullptr, *jv = nullptr;
+    if (jacobi_init_sites<T, KIND>(m, N, dt, y, mask, ws, &jm, &jv, st) > 0) { site_mean = jm; site_var = jv; chain = false; }
+  }
+  if (chain) {
     // One dependent chain (reference order).  Needs dense filter output: use the caller's or scratch in ws is
     // not provisioned for it, so the caller must pass filt_mean/filt_cov on this path.
     if (!filt_mean || !filt_cov) return KJX_ERR_INVALID_ARG;

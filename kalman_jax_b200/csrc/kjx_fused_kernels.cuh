@@ -178,6 +178,9 @@ template <typename T, int D> struct FusedArgs {
                             // two lengths make the chunk count whatever fills the SMs evenly (see plan_chunks)
   int seg0, seg1;           // elements per scan segment: level 0 (64 / 128: throughput) and levels 1, 2 (32 / 64 / 128: latency)
   int store_xf;             // keep the filtered moments (0: energy-only filter)
+  int jacobi;               // site-initialisation sweep (see fused_filter_kernel): out_site_* receive the sites initialised
+                            // from THIS pass's predictive moments while the update uses the given sites
+  T* block_diff;            // [blocks] largest relative change between the given and the newly initialised sites
 };
 
 template <typename T, int D>
@@ -398,11 +401,27 @@ __global__ void __launch_bounds__(64) fused_segscan_top_kernel(const ScanLevel<T
   }
 }
 
+// largest relative change of a site, for the convergence test of the initialisation sweeps (a NaN counts as infinite)
+template <typename T> __device__ __forceinline__ T site_change(T dmax, T new_mean, T new_var, T old_mean, T old_var) {
+  const T a = fabs(new_mean - old_mean) / (T(1) + fabs(old_mean)), b = fabs(new_var - old_var) / (T(1) + fabs(old_var));
+  T d = (a > b) ? a : b;
+  if (!(d <= T(1e30))) d = T(1e30);          // NaN or overflow: "not converged"
+  return (d > dmax) ? d : dmax;
+}
+
 // ------------------------------------------------------------------------------------------------
 // R3
 // PLAIN: the run() iteration (no mask, filtered moments parked in the private layout, sites not written back).
 // !PLAIN adds, with runtime checks: masked (predict-only) steps, energy-only runs (no filtered moments kept) and
 // writing the initialised sites — the stand-alone kjx_filter and the prediction path.
+// Site-initialisation sweep (fa.jacobi, !PLAIN, non-Gaussian): the first iteration of a non-Gaussian model initialises
+// every site from the predictive moments of its own step (sde_gp.py:287 with site_params=None), which makes the
+// reference's loop a NONLINEAR recursion — one dependent chain, 0.4 M steps/s as a single-warp kernel.  It is the fixed
+// point of  sites -> init(predictive(sites)):  the predictive of step k only depends on the sites of steps < k, so a sweep
+// that filters with the current sites (parallel in time, like every other iteration) and re-initialises all sites from
+// the predictive moments it sees is exact for one more step at least, and in practice converges in a few dozen sweeps
+// because the filter forgets.  The host iterates until no site changes by more than 1e-13 (kjx_api.cu), then runs the
+// ordinary pass; if it does not converge it falls back to the one-chain kernel.
 // SHARDED (fp64): the filtered state entering the shard is not read from f_state_in but folded, by warp 0 of every
 // block, from the elements the earlier shards published into this rank's receive buffer (waiting for them if need be);
 // ONE EXTRA block folds the later shards' elements into the information the smoother kernel will need.
@@ -418,7 +437,7 @@ __global__ void __launch_bounds__(KJX_BLOCK, KJX_R3_MINB) fused_filter_kernel(co
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t s0, s1; chunk_range<T, D>(fa, c, s0, s1);
   T Pinf[D][D]; load_pinf<T, D>(a.prior, Pinf);
-  T nl = T(0);
+  T nl = T(0), dmax = T(0);
   if constexpr (SHARDED && std::is_same<T, double>::value) {
     const ShardLink& l = fa.link;
     __shared__ double stage[31 * FSum<double, D>::NS];       // world <= 32
@@ -502,13 +521,23 @@ __global__ void __launch_bounds__(KJX_BLOCK, KJX_R3_MINB) fused_filter_kernel(co
             for (int i = 0; i < D; ++i)
 #pragma unroll
               for (int q = i; q < D; ++q) { const T v = x.P[i][q] - (HP[i] * Sinv) * HP[q]; x.P[i][q] = v; x.P[q][i] = v; }   // :296
+          } else if (!PLAIN && fa.jacobi) {
+            const SiteOut<T> o = site_update<T>(a.site, vy.x[j], pm, pv, false, T(0), T(0));   // :287, from the predictive
+            nl += o.lml;
+            filter_update<T, D>(x, smean, svar);                            // with the CURRENT sites
+            a.out_site_mean[k + j] = o.mean; a.out_site_var[k + j] = o.var;
+            dmax = site_change<T>(dmax, o.mean, o.var, smean, svar);
           } else {
             nl += filter_loglik<T>(a.site, vy.x[j], pm, pv);                // sde_gp.py:287 (log Z only)
             filter_update<T, D>(x, smean, svar);                            // sde_gp.py:292-296
           }
+        } else if (!PLAIN && !GAUSS_EP && fa.jacobi) {                      // masked: y := predictive mean (:286), predict-only
+          const SiteOut<T> o = site_update<T>(a.site, pm, pm, pv, false, T(0), T(0));
+          a.out_site_mean[k + j] = o.mean; a.out_site_var[k + j] = o.var;
+          dmax = site_change<T>(dmax, o.mean, o.var, smean, svar);
         }                                                                   // masked: predict-only, :297-300
         if (PLAIN || fa.store_xf) xf_store<T, D>(xf + (k - s0 + j) * NP * 32, x);
-        if (!PLAIN && a.out_site_mean) { a.out_site_mean[k + j] = smean; a.out_site_var[k + j] = svar; }
+        if (!PLAIN && a.out_site_mean && !fa.jacobi) { a.out_site_mean[k + j] = smean; a.out_site_var[k + j] = svar; }
       }
       if (GAUSS_EP) nl -= T(0.5) * log(logarg);
     }
@@ -518,9 +547,31 @@ __global__ void __launch_bounds__(KJX_BLOCK, KJX_R3_MINB) fused_filter_kernel(co
       Transition<T, KIND>::eval(a.dt[k], a.prior.lam, F);
       filter_predict<T, D>(F, Pinf, x);
       T smean, svar;
-      nl += filter_step_body<T, D, GAUSS_EP>(a, k, x, false, smean, svar);   // handles the mask itself
+      if (!PLAIN && !GAUSS_EP && fa.jacobi) {
+        const bool masked = a.mask ? (a.mask[k] != 0) : false;
+        const T pm = x.m[0], pv = x.P[0][0];
+        step_site<T, D>(a, k, smean, svar);
+        const SiteOut<T> o = site_update<T>(a.site, masked ? pm : a.y[k], pm, pv, false, T(0), T(0));
+        if (!masked) { nl += o.lml; filter_update<T, D>(x, smean, svar); }
+        a.out_site_mean[k] = o.mean; a.out_site_var[k] = o.var;
+        dmax = site_change<T>(dmax, o.mean, o.var, smean, svar);
+      } else {
+        nl += filter_step_body<T, D, GAUSS_EP>(a, k, x, false, smean, svar);   // handles the mask itself
+        if (!PLAIN && a.out_site_mean) { a.out_site_mean[k] = smean; a.out_site_var[k] = svar; }
+      }
       if (PLAIN || fa.store_xf) xf_store<T, D>(xf + (k - s0) * NP * 32, x);
-      if (!PLAIN && a.out_site_mean) { a.out_site_mean[k] = smean; a.out_site_var[k] = svar; }
+    }
+  }
+  if (!PLAIN && !GAUSS_EP && fa.jacobi) {                    // block maximum of the sites' change
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { const T o = __shfl_down_sync(0xffffffffu, dmax, off); dmax = (o > dmax) ? o : dmax; }
+    __shared__ T dred[KJX_BLOCK / 32];
+    if ((threadIdx.x & 31) == 0) dred[threadIdx.x >> 5] = dmax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      T t = T(0);
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t = (dred[w] > t) ? dred[w] : t;
+      fa.block_diff[blockIdx.x] = t;
     }
   }
   T s = nl;

@@ -204,6 +204,31 @@ def test_fp32_fused_iteration_vs_fp64_c_oracle_at_2pow22():
     assert rel_err(_np(model.posterior[1]).reshape(-1), want["pv"]) < TOL32
 
 
+@pytest.mark.parametrize("lik_name,inf_name,inf_kw", [("Poisson", "EP", dict(power=0.5)), ("Probit", "VI", dict()),
+                                                      ("Logit", "EEP", dict(power=1)), ("Poisson", "GHEP", dict(power=1)),
+                                                      ("Poisson", "EKS", dict()), ("Probit", "EP", dict(power=1, intmethod="UT"))])
+def test_site_initialisation_sweeps_equal_the_one_chain_filter(lik_name, inf_name, inf_kw):
+    """First iteration of a non-Gaussian model (sites initialised from the predictive, sde_gp.py:287): the parallel-in-time
+    fixed-point sweeps against the single-chain kernel that walks the series in reference order, 60 000 steps, with a
+    mask on some steps: nlml, filtered moments and the initialised sites at 1e-9."""
+    kjx = _kjx()
+    N = 60_000
+    t, y = synth(N)
+    rng = np.random.default_rng(2)
+    yy = rng.poisson(np.exp(0.5 * y)).astype(float) if lik_name == "Poisson" else np.sign(y + 0.3 * rng.standard_normal(N))
+    model = kjx.SDEGP(kjx.priors.Matern52(1.0, 5.0), getattr(kjx.likelihoods, lik_name)(), t, yy,
+                      approx_inf=getattr(kjx.approximate_inference, inf_name)(**inf_kw))
+    params = model._params(None)
+    mask = (rng.uniform(size=[N, 1]) < 0.02)
+    out = {}
+    for seq in (True, False):
+        nlml, (fm, fP, sites) = model.kalman_filter(model.y, model.dt, params, True, mask, None, model.r, sequential=seq)
+        out[seq] = (float(nlml), _np(fm), _np(fP), _np(sites[0]), _np(sites[1]))
+    assert abs(out[False][0] - out[True][0]) <= TOL64 * abs(out[True][0])
+    for a, b in zip(out[False][1:], out[True][1:]):
+        assert np.isfinite(b).all() and rel_err(a, b) < TOL64
+
+
 def test_masked_prediction_path_vs_oracle():
     """predict(): merged train/test grid, masked steps are predict-only (sde_gp.py:286, 297-300)."""
     kjx = _kjx()
