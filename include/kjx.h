@@ -31,7 +31,7 @@
  *     error: like the reference (utils.py:25-38 — a failed Cholesky yields NaN, no exception) NaNs
  *     propagate into the outputs.
  *   - Hyperparameters are the already-transformed positive values (after the reference's
- *     softplus, utils.py:41-69); func_dim f = 1 (scalar sites) in this version.
+ *     softplus, utils.py:41-69); func_dim f = 1 (scalar sites), or f = 2 for the heteroscedastic-noise model.
  *   - `_f64` entry points compute in IEEE double, `_f32` in float (same signatures with float data).
  */
 #ifndef KJX_H_
@@ -79,7 +79,9 @@ enum kjx_likelihood {
   KJX_LIK_BERNOULLI_PROBIT = 2,  /* likelihoods.py:407-518, link 'probit' (with its 1e-10 jitter) */
   KJX_LIK_BERNOULLI_LOGIT = 3,   /* likelihoods.py:407-518, link 'logit'                          */
   KJX_LIK_POISSON_EXP = 4,       /* likelihoods.py:551-644, link 'exp'                            */
-  KJX_LIK_POISSON_LOGISTIC = 5   /* likelihoods.py:551-644, link 'logistic' (softplus)            */
+  KJX_LIK_POISSON_LOGISTIC = 5,  /* likelihoods.py:551-644, link 'logistic' (softplus)            */
+  KJX_LIK_HETERO_SOFTPLUS = 6,   /* HeteroscedasticNoise, likelihoods.py:647-728, link 'softplus'; func_dim = 2 */
+  KJX_LIK_HETERO_EXP = 7         /* HeteroscedasticNoise, link 'exp'; func_dim = 2                 */
 };
 
 enum kjx_method {
@@ -97,7 +99,8 @@ enum kjx_method {
 typedef struct kjx_model {
   /* ---- prior (priors.py): block-diagonal A(dt), stationary covariance, measurement model ---- */
   int32_t state_dim;               /* d = sum over blocks of count * block size                   */
-  int32_t func_dim;                /* f, rows of H; must be 1                                     */
+  int32_t func_dim;                /* f, rows of H: 1, or 2 for an Independent prior (priors.py:1417-1487) with a
+                                      HeteroscedasticNoise likelihood and EP (state_dim <= 8; sites [N,2,1], [N,2,2]) */
   int32_t n_blocks;
   int32_t reserved0;
   kjx_block_t blocks[KJX_MAX_BLOCKS];

@@ -16,6 +16,7 @@ KJX_MAX_CUBATURE = 32
 # enums (include/kjx.h)
 BLOCK_MATERN32, BLOCK_MATERN52, BLOCK_QP_MATERN32, BLOCK_MATERN12, BLOCK_ROTATION, BLOCK_MATERN72 = 1, 2, 3, 4, 5, 6
 LIK_GAUSSIAN, LIK_BERNOULLI_PROBIT, LIK_BERNOULLI_LOGIT, LIK_POISSON_EXP, LIK_POISSON_LOGISTIC = 1, 2, 3, 4, 5
+LIK_HETERO_SOFTPLUS, LIK_HETERO_EXP = 6, 7
 INF_EP, INF_EEP, INF_SLEP, INF_VI, INF_MOMENT_MATCH = 1, 2, 3, 4, 5
 FLAG_SEQUENTIAL, FLAG_RETURN_FULL, FLAG_NO_SITE_UPDATE, FLAG_RESIDENT_SITES, FLAG_RESIDENT_INIT = 1, 2, 4, 8, 16
 OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_CUDA = 0, -1, -2, -3, -4

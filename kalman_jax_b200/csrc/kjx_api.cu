@@ -9,6 +9,7 @@
 #include "kjx_internal.cuh"
 #include "kjx_small_kernels.cuh"
 #include "kjx_fused_kernels.cuh"
+#include "kjx_multi_kernels.cuh"
 
 using namespace kjx;
 using namespace kjx_impl;
@@ -123,7 +124,8 @@ template <typename T, int D> struct SmallLayout {
   size_t off_info, off_xf, off_jac, off_jdiff, off_lvl[3][3], lvl_stride[3], total;
   int64_t lvl_n[3];
   int seg0, seg1;
-  explicit SmallLayout(int64_t N) {
+  // jac: reserve the buffers of the site-initialisation sweeps (only models that need them: anything but Gaussian + EP)
+  explicit SmallLayout(int64_t N, bool jac = true) {
     constexpr size_t FNS = FSum<T, D>::NS, SNS = SSum<T, D>::NS;
     L = pick_chunk(N);
     nchunks = std::max<int64_t>(1, (N + L - 1) / L);
@@ -160,7 +162,7 @@ template <typename T, int D> struct SmallLayout {
     // filtered moments between the fused filter and smoother passes: [warp][step][element][lane]
     off_xf = take(round_up((size_t)fchunks, 128) * (size_t)plan.L1 * Packed<D>::NP);
     // site-initialisation sweeps (first iteration of a non-Gaussian model): two pairs of site arrays + per-block changes
-    off_jac = take(4 * (size_t)std::max<int64_t>(N, 1)); off_jdiff = take(round_up((size_t)fblocks + 2, 32) + 32);
+    off_jac = take(jac ? 4 * (size_t)std::max<int64_t>(N, 1) : 0); off_jdiff = take(round_up((size_t)fblocks + 2, 32) + 32);
     total = o;
   }
 };
@@ -239,7 +241,7 @@ struct Fused {
   const kjx_model_t* m;
   int64_t ngroups, nthread_blocks;
   Fused(const kjx_model_t* m_, int64_t N, const T* dt, const T* y, const T* site_mean, const T* site_var, void* ws)
-      : lay(N), m(m_) {
+      : lay(N, !gauss_ep(m_)), m(m_) {
     memset(&fa, 0, sizeof(fa));
     fill_prior<T, D>(fa.a, m);
     bind_fused<T, D>(fa, lay, ws);
@@ -382,7 +384,7 @@ int jacobi_init_sites(const kjx_model_t* m, int64_t N, const T* dt, const T* y, 
   constexpr int D = BlockDim<KIND>::D;
   static const int max_sweeps = [] { const char* e = getenv("KJX_INIT_SWEEPS"); return e ? atoi(e) : 400; }();
   if (max_sweeps <= 0) return 0;
-  SmallLayout<T, D> lay(N);
+  SmallLayout<T, D> lay(N, !gauss_ep(m));
   char* w = (char*)ws;
   T* buf = (T*)(w + lay.off_jac);
   T* sm[2] = {buf, buf + 2 * N}; T* sv[2] = {buf + N, buf + 3 * N};
@@ -420,7 +422,7 @@ int small_filter(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const
                  const T* site_mean, const T* site_var, T* filt_mean, T* filt_cov, T* out_site_mean,
                  T* out_site_var, T* nlml, void* ws, size_t ws_bytes, uint32_t flags, cudaStream_t st) {
   constexpr int D = BlockDim<KIND>::D;
-  SmallLayout<T, D> lay(N);
+  SmallLayout<T, D> lay(N, !gauss_ep(m));
   if (ws_bytes < lay.total || !ws) return KJX_ERR_WORKSPACE;
   SmallArgs<T, D> a; memset(&a, 0, sizeof(a));
   fill_prior<T, D>(a, m); bind_workspace<T, D>(a, lay, ws);
@@ -460,7 +462,7 @@ int small_smoother(const kjx_model_t* m, int64_t N, const T* dt, const T* filt_m
                    const T* y, const T* site_mean, const T* site_var, T* smooth_mean, T* smooth_cov,
                    T* new_site_mean, T* new_site_var, void* ws, size_t ws_bytes, uint32_t flags, cudaStream_t st) {
   constexpr int D = BlockDim<KIND>::D;
-  SmallLayout<T, D> lay(N);
+  SmallLayout<T, D> lay(N, !gauss_ep(m));
   if (ws_bytes < lay.total || !ws) return KJX_ERR_WORKSPACE;
   SmallArgs<T, D> a; memset(&a, 0, sizeof(a));
   fill_prior<T, D>(a, m); bind_workspace<T, D>(a, lay, ws);
@@ -489,7 +491,7 @@ int small_run(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const T*
               T* filt_mean, T* filt_cov, T* new_site_mean, T* new_site_var, T* post_mean, T* post_var,
               T* nlml, void* ws, size_t ws_bytes, uint32_t flags, cudaStream_t st, const uint8_t* mask = nullptr) {
   constexpr int D = BlockDim<KIND>::D;
-  SmallLayout<T, D> lay(N);
+  SmallLayout<T, D> lay(N, !gauss_ep(m));
   if (ws_bytes < lay.total || !ws) return KJX_ERR_WORKSPACE;
   if (N == 0) { if (nlml) cudaMemsetAsync(nlml, 0, sizeof(T), st); return KJX_OK; }
   const bool have_sites = site_mean != nullptr;
@@ -549,7 +551,7 @@ template <typename T, int KIND>
 int shard_summary(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const T* site_mean, const T* site_var,
                   T* summary_out, void* ws, size_t ws_bytes, cudaStream_t st) {
   constexpr int D = BlockDim<KIND>::D;
-  if (ws_bytes < SmallLayout<T, D>(N).total || !ws) return KJX_ERR_WORKSPACE;
+  if (ws_bytes < SmallLayout<T, D>(N, !gauss_ep(m)).total || !ws) return KJX_ERR_WORKSPACE;
   if (needs_sequential_filter(m, site_mean != nullptr)) return KJX_ERR_UNSUPPORTED;
   Fused<T, KIND> f(m, N, dt, y, site_mean, site_var, ws);
   f.reduce(st, summary_out);              // the top-level scan writes the shard's element straight to the caller
@@ -560,7 +562,7 @@ template <typename T, int KIND>
 int shard_filter(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const T* site_mean, const T* site_var,
                  const T* state_in, T* nlml_partial, void* ws, size_t ws_bytes, cudaStream_t st) {
   constexpr int D = BlockDim<KIND>::D;
-  if (ws_bytes < SmallLayout<T, D>(N).total || !ws) return KJX_ERR_WORKSPACE;
+  if (ws_bytes < SmallLayout<T, D>(N, !gauss_ep(m)).total || !ws) return KJX_ERR_WORKSPACE;
   Fused<T, KIND> f(m, N, dt, y, site_mean, site_var, ws);
   f.fa.a.f_state_in = state_in;           // read in place
   f.filter(st);
@@ -573,7 +575,7 @@ int shard_smoother(const kjx_model_t* m, int64_t N, const T* dt, const T* y, con
                    const T* info_in, T* post_mean, T* post_var, T* new_site_mean, T* new_site_var, void* ws,
                    size_t ws_bytes, uint32_t flags, cudaStream_t st) {
   constexpr int D = BlockDim<KIND>::D;
-  if (ws_bytes < SmallLayout<T, D>(N).total || !ws) return KJX_ERR_WORKSPACE;
+  if (ws_bytes < SmallLayout<T, D>(N, !gauss_ep(m)).total || !ws) return KJX_ERR_WORKSPACE;
   Fused<T, KIND> f(m, N, dt, y, site_mean, site_var, ws);
   f.fa.s_info_in = info_in;               // read in place
   f.smoother(post_mean, post_var, new_site_mean, new_site_var, !(flags & KJX_FLAG_NO_SITE_UPDATE), st);
@@ -587,7 +589,7 @@ int shard_iteration(const kjx_model_t* m, int64_t N, const double* dt, const dou
                     const ShardLink& link, double* post_mean, double* post_var, double* new_site_mean, double* new_site_var,
                     void* ws, size_t ws_bytes, uint32_t flags, cudaStream_t st) {
   constexpr int D = BlockDim<KIND>::D;
-  if (ws_bytes < SmallLayout<double, D>(N).total || !ws) return KJX_ERR_WORKSPACE;
+  if (ws_bytes < SmallLayout<double, D>(N, !gauss_ep(m)).total || !ws) return KJX_ERR_WORKSPACE;
   if (needs_sequential_filter(m, site_mean != nullptr)) return KJX_ERR_UNSUPPORTED;
   Fused<double, KIND> f(m, N, dt, y, site_mean, site_var, ws);
   f.fa.link = link;
@@ -658,6 +660,58 @@ __global__ void fold_shards_kernel(PinfArg<D> pinf, const double* summaries, int
   if (threadIdx.x == 0) fold_shards<D>(pinf.v, summaries, stride, world, rank, state_out, info_out);
 }
 
+// ---- multi-latent path (func_dim = 2: Independent prior + HeteroscedasticNoise + EP), kjx_multi_kernels.cuh ---------
+bool is_hetero(const kjx_model_t* m) { return m->likelihood == KJX_LIK_HETERO_SOFTPLUS || m->likelihood == KJX_LIK_HETERO_EXP; }
+bool multi_ok(const kjx_model_t* m) {
+  return m->func_dim == 2 && m->state_dim <= KJX_MULTI_DMAX && m->H && !m->H_steps && is_hetero(m) && m->method == KJX_INF_EP;
+}
+template <typename T> void multi_fill(MultiArgs<T>& g, const kjx_model_t* m, int64_t N) {
+  memset(&g, 0, sizeof(g));
+  g.disc.d = m->state_dim; g.disc.n_blocks = m->n_blocks;
+  for (int b = 0; b < m->n_blocks; ++b) g.disc.blocks[b] = m->blocks[b];
+  g.site = make_site(m); g.d = m->state_dim; g.N = N;
+  for (int i = 0; i < m->state_dim * m->state_dim; ++i) g.Pinf[i] = m->Pinf[i];
+  for (int i = 0; i < 2 * m->state_dim; ++i) g.H[i] = m->H[i];
+}
+template <typename T>
+int multi_filter(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const uint8_t* mask, const T* site_mean, const T* site_cov,
+                 T* filt_mean, T* filt_cov, T* out_site_mean, T* out_site_cov, T* nlml, cudaStream_t st) {
+  if (N == 0) { cudaMemsetAsync(nlml, 0, sizeof(T), st); return KJX_OK; }
+  MultiArgs<T> g; multi_fill<T>(g, m, N);
+  g.dt = dt; g.y = y; g.mask = mask; g.site_mean = site_mean; g.site_cov = site_cov; g.init_sites = site_mean ? 0 : 1;
+  g.filt_mean = filt_mean; g.filt_cov = filt_cov; g.out_site_mean = out_site_mean; g.out_site_cov = out_site_cov; g.nlml = nlml;
+  multi_filter_kernel<T><<<1, 32, 0, st>>>(g);
+  KJX_CUDA_CHECK(cudaGetLastError());
+  return KJX_OK;
+}
+template <typename T>
+int multi_smoother(const kjx_model_t* m, int64_t N, const T* dt, const T* filt_mean, const T* filt_cov, const T* y, const T* site_mean,
+                   const T* site_cov, T* smooth_mean, T* smooth_cov, T* new_site_mean, T* new_site_cov, uint32_t flags, cudaStream_t st) {
+  if (N == 0) return KJX_OK;
+  MultiArgs<T> g; multi_fill<T>(g, m, N);
+  g.dt = dt; g.y = y; g.site_mean = site_mean; g.site_cov = site_cov; g.filt_mean_in = filt_mean; g.filt_cov_in = filt_cov;
+  g.smooth_mean = smooth_mean; g.smooth_cov = smooth_cov; g.new_site_mean = new_site_mean; g.new_site_cov = new_site_cov;
+  g.return_full = (flags & KJX_FLAG_RETURN_FULL) ? 1 : 0;
+  g.update_sites = (new_site_mean != nullptr && site_mean != nullptr && y != nullptr) ? 1 : 0;
+  multi_smoother_kernel<T><<<1, 32, 0, st>>>(g);
+  KJX_CUDA_CHECK(cudaGetLastError());
+  return KJX_OK;
+}
+// one run() iteration: filter (dense moments from the caller) then smoother + site update; the sites the filter
+// initialised (first iteration) land in new_site_* and are updated in place by the smoother (sde_gp.py:183-187)
+template <typename T>
+int multi_run(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const T* site_mean, const T* site_cov, T* filt_mean, T* filt_cov,
+              T* new_site_mean, T* new_site_cov, T* post_mean, T* post_var, T* nlml, uint32_t flags, cudaStream_t st) {
+  if (!filt_mean || !filt_cov) return KJX_ERR_INVALID_ARG;    // this path keeps the filtered moments dense
+  int rc = multi_filter<T>(m, N, dt, y, nullptr, site_mean, site_cov, filt_mean, filt_cov, site_mean ? nullptr : new_site_mean,
+                           site_mean ? nullptr : new_site_cov, nlml, st);
+  if (rc != KJX_OK) return rc;
+  const T* prev_m = site_mean ? site_mean : new_site_mean; const T* prev_c = site_mean ? site_cov : new_site_cov;
+  const bool update = !(flags & KJX_FLAG_NO_SITE_UPDATE);
+  return multi_smoother<T>(m, N, dt, filt_mean, filt_cov, y, prev_m, prev_c, post_mean, post_var, update ? new_site_mean : nullptr,
+                           update ? new_site_cov : nullptr, 0, st);
+}
+
 // ---- typed front ends shared by the _f64 / _f32 entry points ------------------------------------------
 template <typename T>
 int filter_T(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const uint8_t* mask, const T* site_mean,
@@ -668,6 +722,9 @@ int filter_T(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const uin
   if ((filt_mean == nullptr) != (filt_cov == nullptr)) return KJX_ERR_INVALID_ARG;
   if ((out_site_mean == nullptr) != (out_site_cov == nullptr)) return KJX_ERR_INVALID_ARG;
   cudaStream_t st = (cudaStream_t)stream;
+  if (m->func_dim != 1 || is_hetero(m))
+    return multi_ok(m) ? multi_filter<T>(m, N, dt, y, mask, site_mean, site_cov, filt_mean, filt_cov, out_site_mean, out_site_cov, nlml, st)
+                       : KJX_ERR_UNSUPPORTED;
   switch (small_kind(m)) {
     case KJX_BLOCK_MATERN32: return small_filter<T, KJX_BLOCK_MATERN32>(m, N, dt, y, mask, site_mean, site_cov, filt_mean, filt_cov, out_site_mean, out_site_cov, nlml, ws, ws_bytes, flags, st);
     case KJX_BLOCK_MATERN52: return small_filter<T, KJX_BLOCK_MATERN52>(m, N, dt, y, mask, site_mean, site_cov, filt_mean, filt_cov, out_site_mean, out_site_cov, nlml, ws, ws_bytes, flags, st);
@@ -686,6 +743,9 @@ int smoother_T(const kjx_model_t* m, int64_t N, const T* dt, const T* filt_mean,
   if ((smooth_mean == nullptr) != (smooth_cov == nullptr)) return KJX_ERR_INVALID_ARG;
   if ((new_site_mean == nullptr) != (new_site_cov == nullptr)) return KJX_ERR_INVALID_ARG;
   cudaStream_t st = (cudaStream_t)stream;
+  if (m->func_dim != 1 || is_hetero(m))
+    return multi_ok(m) ? multi_smoother<T>(m, N, dt, filt_mean, filt_cov, y, site_mean, site_cov, smooth_mean, smooth_cov, new_site_mean, new_site_cov, flags, st)
+                       : KJX_ERR_UNSUPPORTED;
   switch (small_kind(m)) {
     case KJX_BLOCK_MATERN32: return small_smoother<T, KJX_BLOCK_MATERN32>(m, N, dt, filt_mean, filt_cov, y, site_mean, site_cov, smooth_mean, smooth_cov, new_site_mean, new_site_cov, ws, ws_bytes, flags, st);
     case KJX_BLOCK_MATERN52: return small_smoother<T, KJX_BLOCK_MATERN52>(m, N, dt, filt_mean, filt_cov, y, site_mean, site_cov, smooth_mean, smooth_cov, new_site_mean, new_site_cov, ws, ws_bytes, flags, st);
@@ -705,6 +765,9 @@ int run_T(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const T* sit
   if ((site_mean == nullptr) != (site_cov == nullptr)) return KJX_ERR_INVALID_ARG;
   if ((post_mean == nullptr) != (post_var == nullptr)) return KJX_ERR_INVALID_ARG;
   cudaStream_t st = (cudaStream_t)stream;
+  if (m->func_dim != 1 || is_hetero(m))
+    return multi_ok(m) ? multi_run<T>(m, N, dt, y, site_mean, site_cov, filt_mean, filt_cov, new_site_mean, new_site_cov, post_mean, post_var, nlml, flags, st)
+                       : KJX_ERR_UNSUPPORTED;
   switch (small_kind(m)) {
     case KJX_BLOCK_MATERN32: return small_run<T, KJX_BLOCK_MATERN32>(m, N, dt, y, site_mean, site_cov, filt_mean, filt_cov, new_site_mean, new_site_cov, post_mean, post_var, nlml, ws, ws_bytes, flags, st);
     case KJX_BLOCK_MATERN52: return small_run<T, KJX_BLOCK_MATERN52>(m, N, dt, y, site_mean, site_cov, filt_mean, filt_cov, new_site_mean, new_site_cov, post_mean, post_var, nlml, ws, ws_bytes, flags, st);
@@ -720,6 +783,7 @@ int posterior_T(const kjx_model_t* m, int64_t N, const T* dt, const T* y, const 
   if (!model_run_ok(m) || N < 0 || !dt || !y || !post_mean || !post_var) return KJX_ERR_INVALID_ARG;
   if ((site_mean == nullptr) != (site_cov == nullptr)) return KJX_ERR_INVALID_ARG;
   if (needs_sequential_filter(m, site_mean != nullptr)) return KJX_ERR_UNSUPPORTED;   // use kjx_filter + kjx_smoother
+  if (m->func_dim != 1 || is_hetero(m)) return KJX_ERR_UNSUPPORTED;                   // likewise (multi-latent path)
   cudaStream_t st = (cudaStream_t)stream;
   const uint32_t flags = KJX_FLAG_NO_SITE_UPDATE;
   switch (small_kind(m)) {
@@ -735,8 +799,16 @@ template <typename T>
 int site_update_T(const kjx_model_t* m, int64_t N, const T* y, const T* post_mean, const T* post_var,
                   const T* sprev_mean, const T* sprev_var, T* log_lik, T* site_mean, T* site_var, kjx_stream_t stream) {
   if (!model_basic_ok(m) || N < 0 || !y || !post_mean || !post_var) return KJX_ERR_INVALID_ARG;
-  if (m->func_dim != 1) return KJX_ERR_UNSUPPORTED;
   if ((sprev_mean == nullptr) != (sprev_var == nullptr)) return KJX_ERR_INVALID_ARG;
+  if ((site_mean == nullptr) != (site_var == nullptr)) return KJX_ERR_INVALID_ARG;
+  if (m->func_dim != 1 || is_hetero(m)) {
+    if (m->func_dim != 2 || !is_hetero(m) || (m->method != KJX_INF_EP && m->method != KJX_INF_MOMENT_MATCH)) return KJX_ERR_UNSUPPORTED;
+    if (N == 0) return KJX_OK;
+    multi_site_update_kernel<T><<<(unsigned)((N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(make_site(m), N, y, post_mean, post_var, sprev_mean,
+                                                                                              sprev_var, log_lik, site_mean, site_var);
+    KJX_CUDA_CHECK(cudaGetLastError());
+    return KJX_OK;
+  }
   if ((site_mean == nullptr) != (site_var == nullptr)) return KJX_ERR_INVALID_ARG;
   if (N == 0) return KJX_OK;
   const int threads = 128;
@@ -795,10 +867,11 @@ const char* kjx_status_string(int status) {
 #if KJX_PART != 32
 int kjx_workspace_bytes(const kjx_model_t* m, int64_t N, int dtype_bytes, size_t* bytes) {
   if (!model_basic_ok(m) || N < 0 || !bytes || (dtype_bytes != 4 && dtype_bytes != 8)) return KJX_ERR_INVALID_ARG;
+  if (m->func_dim != 1 || is_hetero(m)) { if (!multi_ok(m) && !(m->func_dim == 2 && is_hetero(m))) return KJX_ERR_UNSUPPORTED; *bytes = 256; return KJX_OK; }
   const int kind = small_kind(m);
   size_t total = 0;
-  if (kind == KJX_BLOCK_MATERN32) total = dtype_bytes == 8 ? SmallLayout<double, 2>(N).total : SmallLayout<float, 2>(N).total;
-  else if (kind == KJX_BLOCK_MATERN52) total = dtype_bytes == 8 ? SmallLayout<double, 3>(N).total : SmallLayout<float, 3>(N).total;
+  if (kind == KJX_BLOCK_MATERN32) total = dtype_bytes == 8 ? SmallLayout<double, 2>(N, !gauss_ep(m)).total : SmallLayout<float, 2>(N, !gauss_ep(m)).total;
+  else if (kind == KJX_BLOCK_MATERN52) total = dtype_bytes == 8 ? SmallLayout<double, 3>(N, !gauss_ep(m)).total : SmallLayout<float, 3>(N, !gauss_ep(m)).total;
   else if (generic_ok(m)) total = dtype_bytes == 8 ? generic_ws_bytes<double>(m, N) : generic_ws_bytes<float>(m, N);
   else return KJX_ERR_UNSUPPORTED;
   *bytes = total;

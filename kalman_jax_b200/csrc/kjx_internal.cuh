@@ -28,7 +28,7 @@ inline bool model_basic_ok(const kjx_model_t* m) {
   if (!m) return false;
   if (m->state_dim <= 0 || m->func_dim <= 0 || m->n_blocks <= 0 || m->n_blocks > KJX_MAX_BLOCKS) return false;
   if (m->n_cub < 1 || m->n_cub > KJX_MAX_CUBATURE) return false;
-  if (m->likelihood < KJX_LIK_GAUSSIAN || m->likelihood > KJX_LIK_POISSON_LOGISTIC) return false;
+  if (m->likelihood < KJX_LIK_GAUSSIAN || m->likelihood > KJX_LIK_HETERO_EXP) return false;
   if (m->method < KJX_INF_EP || m->method > KJX_INF_MOMENT_MATCH) return false;
   if (!m->Pinf) return false;
   int d = 0;

@@ -98,3 +98,22 @@ class Poisson(Likelihood):
             raise NotImplementedError('link function not implemented')
         self.link = link
         self.name = 'Poisson'
+
+
+class HeteroscedasticNoise(Likelihood):
+    """likelihoods.py:647-728: p(y | f1, f2) = N(y | f1, link(f2)^2) — two latent functions (func_dim = 2), used with an
+    `Independent` prior and (power-)EP; the moment match integrates f1 analytically and f2 with the one-dimensional
+    cubature of the inference method."""
+    def __init__(self, link='softplus'):
+        super().__init__(hyp=None)
+        if link == 'softplus':
+            self.kjx_code = _lib.LIK_HETERO_SOFTPLUS
+            self.link_fn = lambda mu: np.log(1 + np.exp(-np.abs(np.asarray(mu) - 0.5))) + np.maximum(np.asarray(mu) - 0.5, 0) + 1e-10
+        elif link == 'exp':
+            self.kjx_code = _lib.LIK_HETERO_EXP
+            self.link_fn = lambda mu: np.exp(np.asarray(mu) - 0.5)
+        else:
+            raise NotImplementedError('link function not implemented')
+        self.link = link
+        self.func_dim = 2
+        self.name = 'Heteroscedastic Noise'

@@ -454,6 +454,28 @@ class Sum(object):
         return out
 
 
+class Independent(Sum):
+    """priors.py:1417-1487: a stack of independent GP priors, each component fed to the likelihood — `Sum` with a
+    block-diagonal measurement model (one function value per component: func_dim = number of components)."""
+    def __init__(self, components):
+        Sum.__init__(self, components)
+        self.name = 'Independent'
+
+    def kernel_to_state_space(self, hyperparams=None):
+        hyperparams = self._theta(hyperparams)
+        F, L, Qc, _, Pinf = Sum.kernel_to_state_space(self, hyperparams)
+        H = sl.block_diag(*[c.kernel_to_state_space(h)[3] for c, h in zip(self.components, hyperparams)])
+        return F, L, Qc, H, Pinf
+
+    def measurement_model(self, r=None, hyperparams=None):
+        hyperparams = self._theta(hyperparams)
+        return sl.block_diag(*[c.measurement_model(r, h) for c, h in zip(self.components, hyperparams)])
+
+
+class Separate(Independent):
+    pass
+
+
 def _matern52_spatial_kernel(X, X2, lengthscale):
     """kernels.py:29-36, 90-93 with utils.py:626-654 (Matern-5/2 covariance of the spatial factor)."""
     X, X2 = X / lengthscale, X2 / lengthscale

@@ -122,13 +122,16 @@ def _stream(device):
 
 def site_update(likelihood, sites, y, post_mean, post_cov, hyp=None, site_params=None, force_power=None,
                 dtype=torch.float64, device="cuda"):
-    """Batched ApproxInf.update on the GPU (kjx_site_update): one entry per time step, scalar sites."""
-    class _NoPrior(object):   # kjx_site_update ignores the prior; give the model a trivial one
+    """Batched ApproxInf.update on the GPU (kjx_site_update): one entry per time step; scalar sites, or 2 x 2 sites for a
+    two-latent likelihood (post_mean [N,2,1], post_cov [N,2,2])."""
+    f = int(getattr(likelihood, "func_dim", 1))
+
+    class _NoPrior(object):   # kjx_site_update ignores the prior; give the model a trivial one with f function values
         def kernel_to_state_space(self, h=None):
-            return None, None, None, np.array([[1.0, 0.0]]), np.eye(2)
+            return None, None, None, np.kron(np.eye(f), np.array([[1.0, 0.0]])), np.eye(2 * f)
 
         def blocks(self, h=None):
-            return [(_lib.BLOCK_MATERN32, 1, 1.0, 0.0)]
+            return [(_lib.BLOCK_MATERN32, f, 1.0, 0.0)]
     for a in (post_mean, post_cov, y):
         if isinstance(a, torch.Tensor):
             device = a.device if a.is_cuda else device
@@ -143,10 +146,14 @@ def site_update(likelihood, sites, y, post_mean, post_cov, hyp=None, site_params
     if site_params is not None:
         sm_prev = _as_dev(site_params[0], dtype, device).reshape(-1)
         sv_prev = _as_dev(site_params[1], dtype, device).reshape(-1)
-    lml, sm, sv = (torch.empty(N, dtype=dtype, device=device) for _ in range(3))
+    lml = torch.empty(N, dtype=dtype, device=device)
+    sm = torch.empty(N * f, dtype=dtype, device=device)
+    sv = torch.empty(N * f * f, dtype=dtype, device=device)
     _lib.check(_fn("kjx_site_update", dtype)(model.ref(), C.c_int64(N), _lib.ptr(y_d), _lib.ptr(m_d), _lib.ptr(v_d),
                                              _lib.ptr(sm_prev), _lib.ptr(sv_prev), _lib.ptr(lml), _lib.ptr(sm),
                                              _lib.ptr(sv), _stream(y_d.device)), "kjx_site_update")
+    if f > 1:
+        return lml, sm.reshape(N, f, 1), sv.reshape(N, f, f)
     return lml, sm, sv
 
 
@@ -321,7 +328,7 @@ class SDEGP(object):
         # in its workspace.  Dense buffers are needed only by the one-chain filter that initialises the sites of
         # a non-Gaussian model on the first iteration.
         fm = fP = None
-        if sites_in is None and not (self.likelihood.kjx_code == _lib.LIK_GAUSSIAN and self.sites.kjx_code == _lib.INF_EP):
+        if f > 1 or (sites_in is None and not (self.likelihood.kjx_code == _lib.LIK_GAUSSIAN and self.sites.kjx_code == _lib.INF_EP)):
             fm = torch.empty(N, d, 1, dtype=self.dtype, device=self.device)
             fP = torch.empty(N, d, d, dtype=self.dtype, device=self.device)
         new_sm = torch.empty(N, f, 1, dtype=self.dtype, device=self.device)

@@ -12,5 +12,17 @@ notebooks (797.76, 295.62, 469.46, 178.81).  What stays unpinned: the arithmetic
 jax==0.1.67 / jaxlib==0.1.47 kernels (LAPACK potrf/potrs, XLA's erf/erfc/lgamma), replaced here by
 SciPy's.
 """
-from . import cubature, likelihoods, approx_inf, priors, sde_gp  # noqa: F401
-from .sde_gp import SDEGP  # noqa: F401
+from . import cubature, likelihoods, approx_inf, priors, sde_gp, multi  # noqa: F401
+from .sde_gp import SDEGP as _SDEGPScalar
+from .multi import SDEGPMulti, Independent as _Independent, HeteroscedasticNoise as _HeteroscedasticNoise
+
+# the multi-latent classes under the reference's names, next to the scalar ones
+priors.Independent = _Independent
+likelihoods.HeteroscedasticNoise = _HeteroscedasticNoise
+
+
+def SDEGP(prior, likelihood, t, y, r=None, approx_inf=None):
+    """The scalar-site oracle (sde_gp.py) or, for an `Independent` prior (func_dim > 1), the matrix-site one (multi.py)."""
+    if isinstance(prior, _Independent):
+        return SDEGPMulti(prior, likelihood, t, y, r, approx_inf)
+    return _SDEGPScalar(prior, likelihood, t, y, r, approx_inf)

@@ -105,6 +105,20 @@ def data_banana():
     return X, Y, R
 
 
+def data_mcycle():
+    # notebooks/heteroscedastic_noise.py:16-46: motorcycle data, standardised, fold 0 of the 10-fold split
+    D = np.loadtxt(os.path.join(DATA, "mcycle.csv"), delimiter=",")
+    X, Y = D[:, 1:2], D[:, 2:]
+    Xall = (X - X.mean(0)) / X.std(0)                       # sklearn's StandardScaler: population standard deviation
+    Yall = (Y - Y.mean(0)) / Y.std(0)
+    cvind = np.loadtxt(os.path.join(REF, "kalmanjax", "experiments", "heteroscedastic", "cvind.csv")).astype(int)
+    nt = np.floor(cvind.shape[0] / 10).astype(int)
+    cvind = np.reshape(cvind[:10 * nt], (10, nt))
+    test = cvind[0, :]
+    train = np.setdiff1d(cvind, test)
+    return Xall[train, :], Yall[train, :], Xall[test, :], Yall[test, :]
+
+
 # ----------------------------------------------------------------------------- the replay
 def replay(model, iters, keep_every=1, t_test=None, y_test=None, r_test=None):
     """What SDEGP.run() does (sde_gp.py:163-188) minus the gradient, recorded step by step."""
@@ -194,6 +208,9 @@ def load_data(name):
     if name == "aircraft160":
         x, y = data_aircraft()
         return x, y, None, x[5::20] + 0.5, y[5::20]
+    if name == "mcycle":
+        x, y, xt, yt = data_mcycle()
+        return x, y, None, xt, yt
     if name == "banana400":
         X, Y, R = data_banana()
         return X, Y, R, None, None

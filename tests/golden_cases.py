@@ -27,6 +27,9 @@ SP52 = ("SpatialMatern52", dict(variance=0.4, lengthscale=0.6))
 SP32 = ("SpatialMatern32", dict(variance=0.4, lengthscale=0.8, z=[-3.0 + 0.5 * i for i in range(13)]))
 M52FV = ("Matern52FixedVar", dict(variance=1.2, lengthscale=4.0))
 SUBFV = ("SubbandExponentialFixedVar", dict(variance=0.6, lengthscale=3.0, radial_frequency=1.1))
+M32_31 = ("Matern32", dict(variance=3.0, lengthscale=1.0))
+M52_205 = ("Matern52", dict(variance=2.0, lengthscale=0.5))
+HETERO = ("HeteroscedasticNoise", dict())
 POISSON = ("Poisson", dict())
 PROBIT = ("Probit", dict())
 LOGIT = ("Bernoulli", dict(link="logit"))
@@ -78,6 +81,12 @@ CASES = {
     "zoo_coal333_subband32_poisson_eks": ("coal333", SUB32, POISSON, ("EKS", dict(damping=0.8)), 3, None),
     "zoo_banana200_spatial52_probit_ep08": ("banana200", SP52, PROBIT, ("EP", dict(power=0.8)), 2, None),
     "zoo_banana200_spatial32_probit_vi": ("banana200", SP32, PROBIT, ("VI", dict()), 2, None),
+    # multi-latent (func_dim = 2): Independent prior + HeteroscedasticNoise, the mcycle model of
+    # notebooks/heteroscedastic_noise.py:51-58 (fold 0 of its 10-fold split)
+    "het_mcycle_indep_m32_ep001_gh_damped": ("mcycle", ("Independent", [M32_31, M32_31]), HETERO,
+                                             ("ExpectationPropagation", dict(power=0.01, intmethod="GH", damping=0.5)), 3, None),
+    "het_mcycle_indep_m32_m52_ep09_ut_damped": ("mcycle", ("Independent", [M32_31, M52_205]), HETERO,
+                                                ("ExpectationPropagation", dict(power=0.9, intmethod="UT", damping=0.1)), 3, None),
     # (on its own the reference's Matern52FixedVar fails in softplus_list — its hyp is a scalar — so: inside a Sum)
     "zoo_coal333_sum_fixedvar_poisson_eks": ("coal333", ("Sum", [SUBFV, M52FV]),
                                              POISSON, ("EKS", dict()), 3, None),
@@ -89,8 +98,8 @@ KEEP_EVERY = {"aircraft160": 8, "banana400": 16, "banana200": 16, "banana120": 2
 def build(spec, module):
     """Instantiate `spec` from `module` (the reference's module, oracle.*, or the product's mirror)."""
     name, arg = spec
-    if name == "Sum":
-        return module.Sum([build(s, module) for s in arg])
+    if name in ("Sum", "Independent"):
+        return getattr(module, name)([build(s, module) for s in arg])
     arg = dict(arg)
     if "z" in arg:
         import numpy as np
