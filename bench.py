@@ -506,12 +506,47 @@ def main():
                 nl = it.iteration(reduce_nlml=reduce_nlml)
                 o_nl.copy_(nl.reshape(1), non_blocking=True)
                 torch.cuda.synchronize()
+        v_pipe = None
+        if world == 1:
+            # the same call without its final synchronisation (kjx_run_host_submit_f64): step k+1's upload, on a copy
+            # stream into the other input slot, overlaps step k's kernels; every step still uploads its dt, y and has its
+            # nlml read back, and step k's nlml is on the host before step k+2 is submitted
+            copy_stream = torch.cuda.Stream(device=dev)
+            o_nl2 = torch.empty(2, dtype=torch.float64).pin_memory()
+            cs = C.c_void_p(copy_stream.cuda_stream)
+
+            def submit(k):
+                _lib.check(_lib.lib().kjx_run_host_submit_f64(it.model.ref(), C.c_int64(N), _lib.ptr(h_dt), _lib.ptr(h_y),
+                                                              C.c_void_p(o_nl2.data_ptr() + 8 * (k & 1)), _lib.ptr(scratch),
+                                                              C.c_size_t(nbytes.value), C.c_int32(k & 1), cs, stream), "kjx_run_host_submit")
+                e = torch.cuda.Event()
+                e.record()
+                return e
+
+            def pipelined(nsteps):
+                evs = []
+                for k in range(nsteps):
+                    if k >= 2:
+                        evs[k - 2].synchronize()
+                    evs.append(submit(k))
+                torch.cuda.synchronize()
+            pipelined(4)
+            barrier()
+            t0 = time.perf_counter()
+            pipelined(ke)
+            v_pipe = N * ke / (time.perf_counter() - t0)
         v_all = time_e2e(all_host_step)
         e2e_all = {"value": v_all, "unit": "time-steps/s", "h2d_bytes_per_step": 4 * 8 * N, "d2h_bytes_per_step": 2 * 8 * N + 8,
                    "steps": ke, "nlml": float(o_nl[0]), "api": "as e2e, with the site parameters passed and returned as host arrays too"}
         v_res = time_e2e(resident_step)
+        e2e_blocking = v_res
+        if v_pipe is not None and v_pipe > v_res:
+            v_res = v_pipe
         e2e = {"value": v_res, "unit": "time-steps/s", "h2d_bytes_per_step": 2 * 8 * N, "d2h_bytes_per_step": 8, "steps": ke,
-               "api": ("kjx_run_host_f64" if world == 1 else "pinned copies + sharded C-ABI calls per rank") +
+               "blocking_call_value": e2e_blocking, "pipelined_value": v_pipe,
+               "api": ("kjx_run_host_submit_f64 (step k+1's upload overlaps step k's kernels; kjx_run_host_f64, which returns "
+                       "after the step has drained, is `blocking_call_value`)" if world == 1 and v_pipe is not None and v_pipe >= e2e_blocking
+                       else "kjx_run_host_f64" if world == 1 else "pinned copies + sharded C-ABI calls per rank") +
                       ": dt, y from pinned host memory every step, nlml read back; the site parameters (the state the "
                       "iteration updates, self.sites.site_params) stay on the device between iterations",
                "nlml": float(o_nl[0])}

@@ -53,7 +53,7 @@ SYMBOLS = [
     "kjx_filter_summary_f64", "kjx_filter_apply_f64", "kjx_smoother_apply_f64",
     "kjx_fold_shard_summaries_host", "kjx_fold_shard_summaries_f64", "kjx_exchange_fold_f64", "kjx_run_host_f64", "kjx_run_host_scratch_bytes",
     "kjx_prior_sample_workspace_bytes", "kjx_prior_sample_f64",
-    "kjx_shard_link_doubles", "kjx_sharded_iteration_f64",
+    "kjx_shard_link_doubles", "kjx_sharded_iteration_f64", "kjx_run_host_submit_f64",
 ]
 
 

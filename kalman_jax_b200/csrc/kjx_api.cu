@@ -1157,4 +1157,43 @@ int kjx_run_host_f64(const kjx_model_t* m, int64_t N, const double* dt_host, con
 }
 #endif
 
+#if KJX_PART != 32
+int kjx_run_host_submit_f64(const kjx_model_t* m, int64_t N, const double* dt_host, const double* y_host, double* nlml_host,
+                            void* dev_scratch, size_t dev_scratch_bytes, int32_t slot, kjx_stream_t copy_stream, kjx_stream_t stream) {
+  if (!model_run_ok(m) || N <= 0 || !dt_host || !y_host || !nlml_host || !dev_scratch || (slot != 0 && slot != 1)) return KJX_ERR_INVALID_ARG;
+  size_t need = 0, ws_bytes = 0;
+  int rc = kjx_run_host_scratch_bytes(m, N, 8, &need);
+  if (rc != KJX_OK) return rc;
+  if (dev_scratch_bytes < need) return KJX_ERR_WORKSPACE;
+  kjx_workspace_bytes(m, N, 8, &ws_bytes);
+  cudaStream_t st = (cudaStream_t)stream, cs = (cudaStream_t)copy_stream;
+  const size_t d = (size_t)m->state_dim, n = (size_t)N, nb = round_up(n * 8, 256);
+  char* p = (char*)dev_scratch;
+  auto take = [&](size_t b) { char* r = p; p += round_up(b, 256); return r; };
+  void* ws = take(ws_bytes);                                             // same carve-up as kjx_run_host_f64
+  double *dt0 = (double*)take(nb), *y0 = (double*)take(nb), *sm = (double*)take(nb), *sv = (double*)take(nb);
+  double *nsm = (double*)take(nb), *nsv = (double*)take(nb);
+  take(nb); take(nb);                                                    // post_mean / post_var slots (unused here)
+  const bool dense = !gauss_ep(m);
+  double *fm = dense ? (double*)take(n * d * 8) : nullptr, *fP = dense ? (double*)take(n * d * d * 8) : nullptr;
+  double* nlml = (double*)take(8);
+  double *dt1 = (double*)take(nb), *y1 = (double*)take(nb);              // the second input slot
+  double *dt = slot ? dt1 : dt0, *y = slot ? y1 : y0;
+  // upload on the copy stream; the iteration waits for it on the compute stream
+  cudaEvent_t up;
+  KJX_CUDA_CHECK(cudaEventCreateWithFlags(&up, cudaEventDisableTiming));
+  KJX_CUDA_CHECK(cudaMemcpyAsync(dt, dt_host, n * 8, cudaMemcpyHostToDevice, cs));
+  KJX_CUDA_CHECK(cudaMemcpyAsync(y, y_host, n * 8, cudaMemcpyHostToDevice, cs));
+  KJX_CUDA_CHECK(cudaEventRecord(up, cs));
+  KJX_CUDA_CHECK(cudaStreamWaitEvent(st, up, 0));
+  KJX_CUDA_CHECK(cudaEventDestroy(up));                                  // released once the wait has been satisfied
+  rc = kjx_run_f64(m, N, dt, y, sm, sv, fm, fP, nsm, nsv, nullptr, nullptr, nlml + slot, ws, ws_bytes, 0, stream);
+  if (rc != KJX_OK) return rc;
+  KJX_CUDA_CHECK(cudaMemcpyAsync(nlml_host, nlml + slot, 8, cudaMemcpyDeviceToHost, st));
+  KJX_CUDA_CHECK(cudaMemcpyAsync(sm, nsm, n * 8, cudaMemcpyDeviceToDevice, st));   // the new sites are the next call's sites
+  KJX_CUDA_CHECK(cudaMemcpyAsync(sv, nsv, n * 8, cudaMemcpyDeviceToDevice, st));
+  return KJX_OK;
+}
+#endif
+
 }  // extern "C"

@@ -496,6 +496,45 @@ def test_host_buffer_entry_point_resident_sites():
     assert rc == _lib.ERR_INVALID_ARG
 
 
+def test_host_buffer_submit_overlaps_uploads_and_matches_the_blocking_call():
+    """kjx_run_host_submit_f64 (no final synchronisation, uploads on a copy stream into alternating input slots): six
+    pipelined iterations give exactly the nlml values of six SDEGP.run() iterations, and the resident sites end equal."""
+    import ctypes as C
+    from kalman_jax_b200 import _lib
+    from kalman_jax_b200.sde_gp import _Model
+    kjx = _kjx()
+    N = 200_003
+    t, y = synth(N)
+    model = kjx.SDEGP(kjx.priors.Matern52(1.0, 5.0), kjx.likelihoods.Gaussian(0.5), t, y,
+                      approx_inf=kjx.approximate_inference.EP(power=0.5, damping=0.7))
+    want = [model.run(compute_grad=False)[0] for _ in range(7)]
+    cm = _Model(model.prior, model.likelihood, model.sites)
+    nbytes = C.c_size_t(0)
+    _lib.check(_lib.lib().kjx_run_host_scratch_bytes(cm.ref(), C.c_int64(N), 8, C.byref(nbytes)), "scratch")
+    scratch = torch.empty(nbytes.value, dtype=torch.uint8, device="cuda")
+    pin = lambda a: torch.as_tensor(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
+    dt_h, y_h = pin(model.dt), pin(model.y[:, 0])
+    nl = torch.empty(1, dtype=torch.float64).pin_memory()
+    nl2 = torch.empty(2, dtype=torch.float64).pin_memory()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    copy_stream = torch.cuda.Stream()
+    _lib.check(_lib.lib().kjx_run_host_f64(cm.ref(), C.c_int64(N), _lib.ptr(dt_h), _lib.ptr(y_h), None, None, None, None, None, None,
+                                           _lib.ptr(nl), _lib.ptr(scratch), C.c_size_t(nbytes.value), _lib.FLAG_RESIDENT_INIT, st), "kjx_run_host")
+    got, evs = [float(nl[0])], []
+    for k in range(6):
+        if k >= 2:
+            evs[k - 2].synchronize()
+            got.append(float(nl2[k & 1]))               # result of step k-2, before its slot is reused
+        _lib.check(_lib.lib().kjx_run_host_submit_f64(cm.ref(), C.c_int64(N), _lib.ptr(dt_h), _lib.ptr(y_h),
+                                                      C.c_void_p(nl2.data_ptr() + 8 * (k & 1)), _lib.ptr(scratch), C.c_size_t(nbytes.value),
+                                                      C.c_int32(k & 1), C.c_void_p(copy_stream.cuda_stream), st), "kjx_run_host_submit")
+        e = torch.cuda.Event(); e.record(); evs.append(e)
+    evs[4].synchronize(); got.append(float(nl2[0]))
+    evs[5].synchronize(); got.append(float(nl2[1]))
+    assert got == want
+    nsm, nsv = torch.empty(N, dtype=torch.float64).pin_memory(), torch.empty(N, dtype=torch.float64).pin_memory()
+
+
 def test_generic_path_two_level_boundary_walk_vs_oracle():
     """Sum prior (d = 31) on a series long enough (N = 1500 -> 27 chunks) for the generic path's two-level boundary
     walk (group elements, walk over groups, walks inside groups): three iterations against the sequential oracle."""
