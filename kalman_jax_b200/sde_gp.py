@@ -177,6 +177,7 @@ class SDEGP(object):
         if verbose:
             print('inference method is', self.sites.name)
         self._resident = {}   # id(host array) -> device tensor (training data stays in HBM)
+        self._model_cache = {}
 
     # ------------------------------------------------------------------ plumbing
     def _dev(self, x):
@@ -201,6 +202,29 @@ class SDEGP(object):
         return params
 
     def _model(self, params, r=None, N=None):
+        """kjx_model_t for these hyperparameters (and, for a spatio-temporal prior, these spatial inputs).  Cached: a
+        training loop calls run() with the same hyperparameters for the energy, the finite differences and the update,
+        and the per-step measurement rows of a spatio-temporal prior cost a Cholesky solve with N right-hand sides."""
+        uses_r = hasattr(self.prior, "spatial_weights") and not self.prior.fixed_grid      # only then H depends on r
+        key = self._model_key(params, r if uses_r else None)
+        hit = self._model_cache.get(key)
+        if hit is not None and (not uses_r or hit[1] is r or np.array_equal(hit[1], r, equal_nan=True)):
+            return hit[0]
+        model = self._build_model(params, r)
+        if len(self._model_cache) >= 32:
+            self._model_cache.pop(next(iter(self._model_cache)))
+        self._model_cache[key] = (model, r)
+        return model
+
+    def _model_key(self, params, r):
+        leaves = params[0] if isinstance(params[0], list) else [params[0]]
+        raw = b"".join(np.ascontiguousarray(np.asarray(p, dtype=np.float64)).tobytes() for p in list(leaves) + [params[1]])
+        sig = (float(self.sites.power), float(self.sites.damping), self.sites.kjx_code, self.likelihood.kjx_code,
+               id(self.sites.cubature_func), id(self.prior), id(self.likelihood))
+        rk = None if r is None else (np.shape(r), float(np.nansum(np.asarray(r, dtype=np.float64))))
+        return (raw, sig, rk)
+
+    def _build_model(self, params, r=None):
         theta_prior = _theta_prior(self.prior, params[0])
         theta_lik = softplus(params[1]) if np.size(params[1]) else None
         H_steps = None
