@@ -475,7 +475,7 @@ class SDEGP(object):
         return out
 
     # ------------------------------------------------------------------ sde_gp.py:419-450
-    def posterior_sample(self, num_samps, t=None, r=None, seed=0):
+    def posterior_sample(self, num_samps, t=None, r=None, seed=0, batched=True):
         """Posterior draws at the test inputs by smoothing prior draws through the Gaussian sites (Doucet's conditional
         simulation, as the reference does it): prior_samp - smooth(prior_samp + site noise) + post_mean."""
         if t is None:
@@ -488,14 +488,38 @@ class SDEGP(object):
         gen.manual_seed(int(seed) + 123)
         noise = torch.randn(prior_samp.shape, generator=gen, dtype=torch.float64, device=self.device)
         prior_samp_y = prior_samp + torch.sqrt(site_cov.reshape(-1, 1, 1)) * noise                               # utils.py:247-250
-        smoothed = torch.empty_like(prior_samp_y)
-        zeros = np.zeros_like(y_all)
-        for i in range(int(num_samps)):                                                                         # :443-449
-            sm_i, _, _ = self.predict_everywhere(zeros, r_all, dt_all, train_id, mask,
-                                                 (prior_samp_y[..., i].reshape(-1, 1, 1).contiguous(), site_cov), sampling=True)
-            smoothed[..., i] = sm_i[..., 0]
+        smoothed = self._smooth_draws(prior_samp_y, site_cov, y_all, r_all, dt_all, train_id, mask) if batched else None
+        if smoothed is None:
+            smoothed = torch.empty_like(prior_samp_y)
+            zeros = np.zeros_like(y_all)
+            for i in range(int(num_samps)):                                                                     # :443-449
+                sm_i, _, _ = self.predict_everywhere(zeros, r_all, dt_all, train_id, mask,
+                                                     (prior_samp_y[..., i].reshape(-1, 1, 1).contiguous(), site_cov), sampling=True)
+                smoothed[..., i] = sm_i[..., 0]
         idx = torch.as_tensor(test_id, device=self.device)
         return torch.squeeze(prior_samp - smoothed + post_mean)[idx]                                             # :450
+
+    def _smooth_draws(self, draws, site_cov, y_all, r_all, dt_all, train_id, mask):
+        """The reference's loop over samples (sde_gp.py:443-449) as ONE filter + smoother call: the S pseudo-observation
+        series are laid end to end with a gap before each that is long enough for exp(-gap * lam) to underflow to zero for
+        every block of the prior, so the transition into a series is exactly A = 0, Q = Pinf — the prior, i.e. what the
+        first step of a separate call sees — and the smoother gain out of the previous series is exactly zero.  S * N steps
+        go through the parallel-in-time scan at once instead of S launch sequences of N steps.
+        Returns None (caller loops) when a block does not decay (Cosine / Periodic) or the model is spatial / multi-latent."""
+        S, N = int(draws.shape[-1]), int(draws.shape[0])
+        if S < 2 or self.func_dim != 1 or self.dtype != torch.float64 or hasattr(self.prior, "spatial_weights"):
+            return None
+        lam = [b[2] for b in self.prior.blocks(_theta_prior(self.prior, self._params(None)[0]))]
+        if min(lam) <= 0.0 or not np.isfinite(np.max(dt_all)):
+            return None
+        gap = max(800.0 / min(lam), 1e3 * float(np.max(dt_all)))           # exp(-800) == 0 in fp64
+        dt_cat = np.tile(np.asarray(dt_all, dtype=np.float64).reshape(-1), S)
+        dt_cat[N::N] = gap
+        mask_cat = None if mask is None else np.tile(np.asarray(mask).reshape(N, -1), (S, 1))
+        sm_cat = draws.reshape(N, S).t().contiguous().reshape(S * N, 1, 1)
+        sv_cat = site_cov.reshape(1, N).expand(S, N).contiguous().reshape(S * N, 1, 1)
+        pm, _, _ = self.predict_everywhere(np.zeros((S * N, 1)), r_all, dt_cat, train_id, mask_cat, (sm_cat, sv_cat), sampling=True)
+        return pm.reshape(S, N).t().reshape(N, 1, S)
 
     # ------------------------------------------------------------------ sde_gp.py:110-143
     def negative_log_predictive_density(self, t=None, y=None, r=None):
