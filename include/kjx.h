@@ -100,7 +100,8 @@ typedef struct kjx_model {
   /* ---- prior (priors.py): block-diagonal A(dt), stationary covariance, measurement model ---- */
   int32_t state_dim;               /* d = sum over blocks of count * block size                   */
   int32_t func_dim;                /* f, rows of H: 1, or 2 for an Independent prior (priors.py:1417-1487) with a
-                                      HeteroscedasticNoise likelihood and EP (state_dim <= 8; sites [N,2,1], [N,2,2]) */
+                                      HeteroscedasticNoise likelihood and any of the four update rules (state_dim <= 8;
+                                      sites [N,2,1], [N,2,2]) */
   int32_t n_blocks;
   int32_t reserved0;
   kjx_block_t blocks[KJX_MAX_BLOCKS];
@@ -115,7 +116,10 @@ typedef struct kjx_model {
   double power;                    /* EP power / fraction                                         */
   double damping;                  /* site damping                                                */
   int32_t n_cub;                   /* number of cubature points, 1..KJX_MAX_CUBATURE              */
-  int32_t reserved;
+  int32_t cub_rule;                /* func_dim 2 with KJX_INF_SLEP only: which TWO-dimensional rule the table stands for
+                                      (ApproxInf.cubature_func(2), approximate_inference.py:25-34): 0 = Gauss-Hermite, the
+                                      product rule of the 1-D table (utils.py:418-463); 3 / 5 = the symmetric 3rd- /
+                                      5th-order rule with the reference's literals (utils.py:484-488, 512-516).  Else 0. */
   double cub_x[KJX_MAX_CUBATURE];  /* unit sigma points  (utils.py:455-463 / 466-511)             */
   double cub_w[KJX_MAX_CUBATURE];  /* weights                                                     */
 } kjx_model_t;

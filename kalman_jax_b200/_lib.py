@@ -33,7 +33,7 @@ class KjxModel(C.Structure):
         ("Pinf", C.c_void_p), ("H", C.c_void_p), ("H_steps", C.c_void_p),
         ("likelihood", C.c_int32), ("method", C.c_int32),
         ("lik_hyp", C.c_double), ("power", C.c_double), ("damping", C.c_double),
-        ("n_cub", C.c_int32), ("reserved", C.c_int32),
+        ("n_cub", C.c_int32), ("cub_rule", C.c_int32),
         ("cub_x", C.c_double * KJX_MAX_CUBATURE), ("cub_w", C.c_double * KJX_MAX_CUBATURE),
     ]
 

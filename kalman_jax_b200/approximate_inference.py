@@ -16,6 +16,7 @@ class ApproxInf(object):
 
     def __init__(self, site_params=None, intmethod='GH', num_cub_pts=20):
         self.site_params = site_params
+        self.intmethod = intmethod
         if intmethod == 'GH':
             self.cubature_func = lambda dim: gauss_hermite(dim, num_cub_pts)
         elif intmethod == 'UT3':

@@ -663,7 +663,8 @@ __global__ void fold_shards_kernel(PinfArg<D> pinf, const double* summaries, int
 // ---- multi-latent path (func_dim = 2: Independent prior + HeteroscedasticNoise + EP), kjx_multi_kernels.cuh ---------
 bool is_hetero(const kjx_model_t* m) { return m->likelihood == KJX_LIK_HETERO_SOFTPLUS || m->likelihood == KJX_LIK_HETERO_EXP; }
 bool multi_ok(const kjx_model_t* m) {
-  return m->func_dim == 2 && m->state_dim <= KJX_MULTI_DMAX && m->H && !m->H_steps && is_hetero(m) && m->method == KJX_INF_EP;
+  if (m->method == KJX_INF_SLEP && (m->cub_rule != 0 && m->cub_rule != 3 && m->cub_rule != 5)) return false;
+  return m->func_dim == 2 && m->state_dim <= KJX_MULTI_DMAX && m->H && !m->H_steps && is_hetero(m) && m->method >= KJX_INF_EP && m->method <= KJX_INF_VI;
 }
 template <typename T> void multi_fill(MultiArgs<T>& g, const kjx_model_t* m, int64_t N) {
   memset(&g, 0, sizeof(g));
@@ -802,7 +803,7 @@ int site_update_T(const kjx_model_t* m, int64_t N, const T* y, const T* post_mea
   if ((sprev_mean == nullptr) != (sprev_var == nullptr)) return KJX_ERR_INVALID_ARG;
   if ((site_mean == nullptr) != (site_var == nullptr)) return KJX_ERR_INVALID_ARG;
   if (m->func_dim != 1 || is_hetero(m)) {
-    if (m->func_dim != 2 || !is_hetero(m) || (m->method != KJX_INF_EP && m->method != KJX_INF_MOMENT_MATCH)) return KJX_ERR_UNSUPPORTED;
+    if (m->func_dim != 2 || !is_hetero(m) || (m->method == KJX_INF_SLEP && m->cub_rule != 0 && m->cub_rule != 3 && m->cub_rule != 5)) return KJX_ERR_UNSUPPORTED;
     if (N == 0) return KJX_OK;
     multi_site_update_kernel<T><<<(unsigned)((N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(make_site(m), N, y, post_mean, post_var, sprev_mean,
                                                                                               sprev_var, log_lik, site_mean, site_var);

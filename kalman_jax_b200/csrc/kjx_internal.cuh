@@ -48,7 +48,7 @@ inline bool model_run_ok(const kjx_model_t* m) { return model_basic_ok(m) && m->
 inline SiteModel make_site(const kjx_model_t* m) {
   SiteModel s;
   memset(&s, 0, sizeof(s));
-  s.lik = m->likelihood; s.method = m->method; s.n_cub = m->n_cub;
+  s.lik = m->likelihood; s.method = m->method; s.n_cub = m->n_cub; s.cub_rule = m->cub_rule;
   s.lik_hyp = m->lik_hyp; s.power = m->power; s.damping = m->damping;
   for (int i = 0; i < KJX_MAX_CUBATURE; ++i) { s.cub_x[i] = m->cub_x[i]; s.cub_w[i] = m->cub_w[i]; }
   return s;

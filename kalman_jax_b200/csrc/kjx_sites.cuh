@@ -24,7 +24,8 @@ struct SiteModel {
   int lik;       // kjx_likelihood
   int method;    // kjx_method
   int n_cub;
-  int pad_;
+  int cub_rule;  // multi-dimensional cubature (func_dim 2, SLR family): 0 = Gauss-Hermite product of the 1-D table,
+                 // 3 / 5 = the reference's 3rd- / 5th-order symmetric rule (utils.py:466-516)
   double lik_hyp, power, damping;
   double cub_x[KJX_MAX_CUBATURE];
   double cub_w[KJX_MAX_CUBATURE];

@@ -101,9 +101,10 @@ class Poisson(Likelihood):
 
 
 class HeteroscedasticNoise(Likelihood):
-    """likelihoods.py:647-728: p(y | f1, f2) = N(y | f1, link(f2)^2) — two latent functions (func_dim = 2), used with an
-    `Independent` prior and (power-)EP; the moment match integrates f1 analytically and f2 with the one-dimensional
-    cubature of the inference method."""
+    """likelihoods.py:647-850: p(y | f1, f2) = N(y | f1, link(f2)^2) — two latent functions (func_dim = 2), used with an
+    `Independent` prior and any of the update rules: (power-)EP and VI integrate f1 analytically and f2 with the
+    one-dimensional cubature of the inference method, the SLR family (SLEP / GHEP / UEP / GHKS / UKS / PL) uses its
+    two-dimensional rule, EEP / EKS the analytical linearisation.  All of it runs in csrc/kjx_multi_kernels.cuh."""
     def __init__(self, link='softplus'):
         super().__init__(hyp=None)
         if link == 'softplus':

@@ -87,6 +87,8 @@ class _Model(object):
         if x.size > _lib.KJX_MAX_CUBATURE:
             raise _lib.KjxError("more than %d cubature points" % _lib.KJX_MAX_CUBATURE)
         m.n_cub = x.size
+        # which two-dimensional rule stands behind the table (f = 2 with the SLR family; kjx.h: cub_rule)
+        m.cub_rule = 0 if cubature is not None else {'UT3': 3, 'UT5': 5, 'UT': 5}.get(getattr(sites, 'intmethod', 'GH'), 0)
         for i in range(x.size):
             m.cub_x[i], m.cub_w[i] = x[i], w[i]
         self.c = m

@@ -27,23 +27,40 @@ def softplus_list(x_):
 
 
 def gauss_hermite(dim=1, num_quad_pts=20):
-    if dim != 1:
-        raise NotImplementedError("only one-dimensional (f = 1) cubature is built")
+    """utils.py:418-463: Gauss-Hermite points scaled for a unit Gaussian; dim > 1 is the product rule, x [dim, Q^dim]
+    with the LAST coordinate varying fastest (the order of itertools.product), w [Q^dim]."""
     x, w = hermgauss(num_quad_pts)
-    return np.sqrt(2) * x, w * pi ** (-0.5)
+    if dim == 1:
+        return np.sqrt(2) * x, w * pi ** (-0.5)
+    grid = np.stack(np.meshgrid(*([x] * dim), indexing="ij"), axis=0).reshape(dim, -1)
+    wts = np.prod(np.stack(np.meshgrid(*([w] * dim), indexing="ij"), axis=0).reshape(dim, -1), axis=0)
+    return np.sqrt(2) * grid, wts * pi ** (-0.5 * dim)
 
 
 def symmetric_cubature_third_order(dim=1, kappa=None):
-    if dim != 1:
-        raise NotImplementedError("only one-dimensional (f = 1) cubature is built")
-    return np.array([0., 1., -1.]), np.array([0., 0.5, 0.5])
+    """utils.py:466-503 with kappa = 0: the origin (weight 0) and +- sqrt(dim) along every axis; dims 1-3 carry the
+    reference's 4-digit literals."""
+    if kappa not in (None, 0):
+        raise NotImplementedError("only kappa = 0 (the reference's default) is built")
+    if dim == 1:
+        return np.array([0., 1., -1.]), np.array([0., 0.5, 0.5])
+    u, wm = {2: (1.4142, 0.25), 3: (1.7321, 0.1667)}.get(dim, (np.sqrt(dim), 1.0 / (2 * dim)))
+    pts = np.concatenate([np.zeros([dim, 1]), u * np.eye(dim), -u * np.eye(dim)], axis=1)
+    wts = np.concatenate([[0.], np.full(2 * dim, wm)])
+    return pts, (wts if dim in (2, 3) else wts[None, :])      # the reference's general branch returns weights [1, 2 dim + 1]
 
 
 def symmetric_cubature_fifth_order(dim=1):
-    if dim != 1:
-        raise NotImplementedError("only one-dimensional (f = 1) cubature is built")
-    # the reference's 4-digit literals (utils.py:510-511); weights sum to 1.0001 on purpose
-    return np.array([0., 1.7321, -1.7321]), np.array([0.6667, 0.1667, 0.1667])
+    """utils.py:505-516: the reference's 4-digit literals (the weights do not sum to one exactly; kept on purpose).
+    Dimensions 1 and 2 (scalar sites and the two-latent HeteroscedasticNoise); the reference's tables for 3 and 6 latent
+    functions belong to likelihoods that are not built."""
+    u = 1.7321
+    if dim == 1:
+        return np.array([0., u, -u]), np.array([0.6667, 0.1667, 0.1667])
+    if dim == 2:
+        return (np.array([[0., u, -u, 0., 0., u, -u, u, -u], [0., 0., 0., u, -u, u, -u, -u, u]]),
+                np.array([0.4444, 0.1111, 0.1111, 0.1111, 0.1111, 0.0278, 0.0278, 0.0278, 0.0278]))
+    raise NotImplementedError("fifth-order symmetric rule: dimensions 1 and 2 are built")
 
 
 def _as_columns(x, like=None):

@@ -35,3 +35,36 @@ def make(intmethod="GH", num_cub_pts=20):
     if intmethod in ("UT5", "UT"):
         return symmetric_cubature_fifth_order()
     raise NotImplementedError("integration method not recognised")
+
+
+# ---- two-dimensional rules (func_dim = 2: HeteroscedasticNoise with the SLR family) --------------------------------
+def gauss_hermite_2d(num_pts=20):
+    """utils.py:418-463 with dim = 2: the product rule in itertools.product order, x [2, Q^2], w [Q^2]."""
+    gx, gw = hermgauss(num_pts)
+    x = np.array([[a, b] for a in gx for b in gx])
+    w = np.array([a * b for a in gw for b in gw])
+    return np.sqrt(2.0) * x.T, w * np.pi ** -1.0
+
+
+def symmetric_cubature_third_order_2d():
+    """utils.py:484-488 (dim == 2, kappa == 0): 4-digit literals as written."""
+    return (np.array([[0., 1.4142, 0., -1.4142, 0.], [0., 0., 1.4142, 0., -1.4142]]),
+            np.array([0., 0.25, 0.25, 0.25, 0.25]))
+
+
+def symmetric_cubature_fifth_order_2d():
+    """utils.py:512-516 (dim == 2): 4-digit literals as written."""
+    return (np.array([[0., 1.7321, -1.7321, 0., 0., 1.7321, -1.7321, 1.7321, -1.7321],
+                      [0., 0., 0., 1.7321, -1.7321, 1.7321, -1.7321, -1.7321, 1.7321]]),
+            np.array([0.4444, 0.1111, 0.1111, 0.1111, 0.1111, 0.0278, 0.0278, 0.0278, 0.0278]))
+
+
+def make_2d(intmethod="GH", num_cub_pts=20):
+    """approximate_inference.py:25-34 evaluated at dim = 2."""
+    if intmethod == "GH":
+        return gauss_hermite_2d(num_cub_pts)
+    if intmethod == "UT3":
+        return symmetric_cubature_third_order_2d()
+    if intmethod in ("UT5", "UT"):
+        return symmetric_cubature_fifth_order_2d()
+    raise NotImplementedError("integration method not recognised")

@@ -1,11 +1,14 @@
 """ORACLE (test infrastructure, not product): the multi-latent case, func_dim f > 1 — `Independent` priors with the
-`HeteroscedasticNoise` likelihood and (power-)EP with f x f sites.
+`HeteroscedasticNoise` likelihood and every update rule (EP, EEP / EKS, the SLR family, VI) with f x f sites.
 
 NumPy fp64 restatement of /root/reference/kalmanjax:
   priors.py:1417-1487            Independent (block-diagonal A, Pinf; block-diagonal H: one function value per component)
   likelihoods.py:647-728         HeteroscedasticNoise: p(y | f1, f2) = N(y | f1, link(f2)^2), moment match with a
                                  one-dimensional cubature over f2 (f1 is integrated analytically), diagonal Hessian
+  likelihoods.py:763-850         its variational expectation (1-D cubature), statistical linear regression (2-D cubature,
+                                 utils.py:418-516 through oracle/cubature.py) and analytical linearisation
   approximate_inference.py:8-15, 50-73   cavity and EP update in matrix form (Cholesky inverses, utils.py:33-38)
+  approximate_inference.py:99-133, 180-210, 302-323   EEP / EKS, SLEP family and VI updates in matrix form
   sde_gp.py:230-384, 85-143      filter / smoother / predict / NLPD with matrix-valued sites
 Pinned by the reference-generated fixtures `het_*` (tests/test_oracle_golden.py).
 """
@@ -103,6 +106,39 @@ class HeteroscedasticNoise(object):
         return lZ, site_mean, site_cov
 
 
+    def variational_expectation(self, y, m, v, cub):
+        """:763-805: one-dimensional cubature over f2; returns E[log p], dE/dm [2,1], dE/dv [2,2] (diagonal)."""
+        x, w = cub
+        y = float(np.reshape(y, -1)[0])
+        m0, m1, v0, v1 = m[0, 0], m[1, 0], v[0, 0], v[1, 1]
+        with np.errstate(all="ignore"):
+            sigma_points = np.sqrt(v1) * x + m1
+            var = self.link_fn(sigma_points) ** 2
+            log_lik = np.log(var) + var ** -1 * ((y - m0) ** 2 + v0)
+            wll = w * log_lik
+            exp_log_lik = -0.5 * np.log(2 * pi) - 0.5 * np.sum(wll)
+            dE_dm1 = np.sum((var ** -1 * (y - m0 + v0)) * w)                                # :784 (as written, "+ v0" included)
+            dE_dm2 = -0.5 * np.sum(wll * v1 ** -1 * (sigma_points - m1))
+            dE_dv1 = -0.5 * np.sum(var ** -1 * w)
+            dE_dv2 = -0.25 * np.sum((v1 ** -2 * (sigma_points - m1) ** 2 - v1 ** -1) * wll)
+        return exp_log_lik, np.array([[dE_dm1], [dE_dm2]]), np.array([[dE_dv1, 0.], [0., dE_dv2]])
+
+    def statistical_linear_regression(self, cav_mean, cav_cov, cub2):
+        """:808-842.  cub2: the TWO-dimensional rule (x [2,Q], w [Q])."""
+        x, w = cub2
+        m0, v0 = cav_mean[0, 0], cav_cov[0, 0]
+        with np.errstate(all="ignore"):
+            sigma_points = np.linalg.cholesky(cav_cov) @ x + cav_mean
+            var = self.link_fn(sigma_points[1]) ** 2
+            S = (v0 + np.sum(w * var)).reshape(1, 1)
+            C = np.sum(w * (sigma_points - cav_mean) * (sigma_points[0] - m0), axis=-1).reshape(2, 1)
+        return m0.reshape(1, 1), S, C, np.array([[1., 0.]])
+
+    def analytical_linearisation(self, m):
+        """:845-850 with sigma = 0 (the only way the update rules call it): Jf = [1, 0], Jsigma = link(m[1])."""
+        return np.array([[1.0, 0.0]]), np.reshape(self.link_fn(np.array([m[1, 0]])), (1, 1))
+
+
 def compute_cavity(post_mean, post_cov, site_mean, site_cov, power):
     """approximate_inference.py:8-15."""
     post_precision, site_precision = inv(post_cov), inv(site_cov)
@@ -126,6 +162,101 @@ def ep_update(rule, likelihood, y, post_mean, post_cov, site_params=None):
             site_cov = inv((1. - rule.damping) * site_nat2_prev + rule.damping * site_nat2)
             site_mean = site_cov @ ((1. - rule.damping) * site_nat1_prev + rule.damping * site_nat1)
     return lml, site_mean, site_cov
+
+
+def _damp(rule, site_mean, site_cov, site_nat2, site_params, jitter_new, jitter_prev, jitter_sum):
+    """The damping step shared by the rules (each with its own jitter placement): approximate_inference.py:69-72,
+    125-132, 203-209."""
+    site_mean_prev, site_cov_prev = site_params
+    eye = np.eye(site_cov.shape[0])
+    nat2 = inv(site_cov + jitter_new * eye) if site_nat2 is None else site_nat2
+    nat2_prev = inv(site_cov_prev + jitter_prev * eye)
+    nat1, nat1_prev = nat2 @ site_mean, nat2_prev @ site_mean_prev
+    site_cov = inv((1. - rule.damping) * nat2_prev + rule.damping * nat2 + jitter_sum * eye)
+    site_mean = site_cov @ ((1. - rule.damping) * nat1_prev + rule.damping * nat1)
+    return site_mean, site_cov
+
+
+def eep_update(rule, likelihood, y, post_mean, post_cov, site_params=None):
+    """ExtendedEP.update, approximate_inference.py:99-133, matrix form (EKS: power 0)."""
+    y = np.reshape(np.asarray(y, dtype=float), (1, 1))
+    power = 1. if site_params is None else rule.power
+    with np.errstate(all="ignore"):
+        if site_params is None or power == 0:
+            cav_mean, cav_cov = post_mean, post_cov
+        else:
+            cav_mean, cav_cov = compute_cavity(post_mean, post_cov, site_params[0], site_params[1], power)
+        Jf, Jsigma = likelihood.analytical_linearisation(cav_mean)
+        residual = y - cav_mean[0:1, 0:1]                                                   # conditional_moments: E[y|f] = f1
+        sigma = Jsigma @ Jsigma.T + power * Jf @ cav_cov @ Jf.T
+        site_nat2 = Jf.T @ inv(Jsigma @ Jsigma.T) @ Jf
+        site_cov = inv(site_nat2 + 1e-10 * np.eye(2))
+        site_mean = cav_mean + (site_cov + power * cav_cov) @ Jf.T @ inv(sigma) @ residual
+        sigma_marg = Jsigma @ Jsigma.T + Jf @ cav_cov @ Jf.T
+        chol = np.linalg.cholesky(sigma_marg)
+        lml = -1 * (.5 * site_cov.shape[0] * np.log(2 * pi) + np.sum(np.log(np.diag(chol)))
+                    + .5 * (residual.T @ solve(sigma_marg, residual)).item())                  # :119-123
+        if site_params is not None and rule.damping != 1.:
+            site_mean, site_cov = _damp(rule, site_mean, site_cov, site_nat2, site_params, 0., 1e-10, 1e-10)
+    return lml, site_mean, site_cov
+
+
+def slep_update(rule, likelihood, y, post_mean, post_cov, site_params=None):
+    """StatisticallyLinearisedEP.update, approximate_inference.py:180-210, matrix form."""
+    y = np.reshape(np.asarray(y, dtype=float), (1, 1))
+    cub, cub2 = cubature.make(rule.intmethod, rule.num_cub_pts), cubature.make_2d(rule.intmethod, rule.num_cub_pts)
+    power = 1. if site_params is None else rule.power
+    with np.errstate(all="ignore"):
+        lml, _, _ = likelihood.moment_match(y, post_mean, post_cov, 1.0, cub)
+        if site_params is None or power == 0:
+            cav_mean, cav_cov = post_mean, post_cov
+        else:
+            cav_mean, cav_cov = compute_cavity(post_mean, post_cov, site_params[0], site_params[1], power)
+        mu, S, C, omega = likelihood.statistical_linear_regression(cav_mean, cav_cov, cub2)
+        residual = y - mu
+        sigma = S + (power - 1) * C.T @ inv(cav_cov + 1e-10 * np.eye(2)) @ C
+        om_sig_om = omega.T @ inv(sigma) @ omega
+        om_sig_om = np.diag(np.diag(om_sig_om))
+        osigo = inv(om_sig_om + 1e-10 * np.eye(2))
+        site_mean = cav_mean + osigo @ omega.T @ inv(sigma) @ residual
+        site_cov = -power * cav_cov + osigo
+        if site_params is not None and rule.damping != 1.:
+            site_mean, site_cov = _damp(rule, site_mean, site_cov, None, site_params, 1e-10, 1e-10, 1e-10)
+    return lml, site_mean, site_cov
+
+
+def vi_update(rule, likelihood, y, post_mean, post_cov, site_params=None):
+    """VariationalInference.update, approximate_inference.py:302-323, matrix form."""
+    cub = cubature.make(rule.intmethod, rule.num_cub_pts)
+    eye = np.eye(2)
+    with np.errstate(all="ignore"):
+        _, dE_dm, dE_dv = likelihood.variational_expectation(y, post_mean, post_cov, cub)
+        if site_params is None:
+            site_cov = 0.5 * inv(ensure_positive_precision(-dE_dv) + 1e-10 * eye)
+            site_mean = post_mean + site_cov @ dE_dm
+        else:
+            site_mean, site_cov = site_params
+            dE_dv = -ensure_positive_precision(-dE_dv)
+            lambda_t_2 = inv(site_cov + 1e-10 * eye)
+            lambda_t_1 = lambda_t_2 @ site_mean
+            lambda_t_1 = (1 - rule.damping) * lambda_t_1 + rule.damping * (dE_dm - 2 * dE_dv @ post_mean)
+            lambda_t_2 = (1 - rule.damping) * lambda_t_2 + rule.damping * (-2 * dE_dv)
+            site_cov = inv(lambda_t_2 + 1e-10 * eye)
+            site_mean = site_cov @ lambda_t_1
+        lml, _, _ = likelihood.moment_match(y, post_mean, post_cov, 1.0, cub)
+    return lml, site_mean, site_cov
+
+
+def site_update(rule, likelihood, y, post_mean, post_cov, site_params=None):
+    """The rule's `update` in matrix form, chosen by the class of `rule` (oracle.approx_inf's class tree)."""
+    from . import approx_inf as ai
+    if isinstance(rule, ai.VariationalInference):
+        return vi_update(rule, likelihood, y, post_mean, post_cov, site_params)
+    if isinstance(rule, ai.StatisticallyLinearisedEP):
+        return slep_update(rule, likelihood, y, post_mean, post_cov, site_params)
+    if isinstance(rule, ai.ExtendedEP):
+        return eep_update(rule, likelihood, y, post_mean, post_cov, site_params)
+    return ep_update(rule, likelihood, y, post_mean, post_cov, site_params)
 
 
 class SDEGPMulti(object):
@@ -153,7 +284,7 @@ class SDEGPMulti(object):
             predict_mean, predict_cov = H @ m_, H @ P_ @ H.T
             if mask is not None:
                 y_n = np.where(mask[n][..., None], predict_mean[:y_n.shape[0]], y_n)      # :286
-            log_lik_n, site_mean, site_cov = ep_update(self.sites, self.likelihood, y_n, predict_mean, predict_cov, None)
+            log_lik_n, site_mean, site_cov = site_update(self.sites, self.likelihood, y_n, predict_mean, predict_cov, None)
             if site_params is not None:
                 site_mean, site_cov = site_params[0][n], site_params[1][n]                # :290
             S = predict_cov + site_cov
@@ -191,7 +322,7 @@ class SDEGPMulti(object):
             if store:
                 sm[n], sc[n] = (m, P) if return_full else (H @ m, H @ P @ H.T)
             if site_params is not None:
-                _, mu, cov = ep_update(self.sites, self.likelihood, y[n][..., None], H @ m, H @ P @ H.T,
+                _, mu, cov = site_update(self.sites, self.likelihood, y[n][..., None], H @ m, H @ P @ H.T,
                                        (site_params[0][n], site_params[1][n]))
                 new_mean[n], new_cov[n] = mu, cov
         if site_params is not None:

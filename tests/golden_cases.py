@@ -87,6 +87,18 @@ CASES = {
                                              ("ExpectationPropagation", dict(power=0.01, intmethod="GH", damping=0.5)), 3, None),
     "het_mcycle_indep_m32_m52_ep09_ut_damped": ("mcycle", ("Independent", [M32_31, M52_205]), HETERO,
                                                 ("ExpectationPropagation", dict(power=0.9, intmethod="UT", damping=0.1)), 3, None),
+    "het_mcycle_indep_m32_vi_gh_damped": ("mcycle", ("Independent", [M32_31, M32_31]), HETERO,
+                                          ("VI", dict(intmethod="GH", damping=0.5)), 3, None),
+    "het_mcycle_indep_m32_m52_vi_ut": ("mcycle", ("Independent", [M32_31, M52_205]), HETERO,
+                                       ("VI", dict(intmethod="UT")), 3, None),
+    "het_mcycle_indep_m32_eep05_damped": ("mcycle", ("Independent", [M32_31, M32_31]), HETERO,
+                                          ("EEP", dict(power=0.5, damping=0.5)), 3, None),
+    "het_mcycle_indep_m32_m52_eks": ("mcycle", ("Independent", [M32_31, M52_205]), HETERO,
+                                     ("EKS", dict()), 3, None),
+    "het_mcycle_indep_m32_slep05_gh_damped": ("mcycle", ("Independent", [M32_31, M32_31]), HETERO,
+                                              ("SLEP", dict(power=0.5, intmethod="GH", damping=0.5, num_cub_pts=10)), 3, None),
+    "het_mcycle_indep_m32_m52_uks": ("mcycle", ("Independent", [M32_31, M52_205]), HETERO,
+                                     ("UKS", dict()), 3, None),
     # (on its own the reference's Matern52FixedVar fails in softplus_list — its hyp is a scalar — so: inside a Sum)
     "zoo_coal333_sum_fixedvar_poisson_eks": ("coal333", ("Sum", [SUBFV, M52FV]),
                                              POISSON, ("EKS", dict()), 3, None),
