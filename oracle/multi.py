@@ -21,12 +21,22 @@ from .sde_gp import input_admin, test_input_admin
 pi = 3.141592653589793
 
 
-def solve(P, Q):      # utils.py:25-30
-    return cho_solve(cho_factor(P), Q)
+def solve(P, Q):      # utils.py:25-30; a failed factorisation yields NaN (as under JAX), not an exception
+    try:
+        return cho_solve(cho_factor(P, check_finite=False), Q, check_finite=False)
+    except (np.linalg.LinAlgError, ValueError):
+        return np.full(np.shape(Q), np.nan)
 
 
 def inv(P):           # utils.py:33-38
-    return cho_solve(cho_factor(P), np.eye(P.shape[0]))
+    return solve(P, np.eye(P.shape[0]))
+
+
+def chol_lower(P):    # jnp.linalg.cholesky: NaN instead of an exception
+    try:
+        return np.linalg.cholesky(P)
+    except np.linalg.LinAlgError:
+        return np.full(np.shape(P), np.nan)
 
 
 def ensure_positive_precision(K):   # utils.py:15-22
@@ -128,7 +138,7 @@ class HeteroscedasticNoise(object):
         x, w = cub2
         m0, v0 = cav_mean[0, 0], cav_cov[0, 0]
         with np.errstate(all="ignore"):
-            sigma_points = np.linalg.cholesky(cav_cov) @ x + cav_mean
+            sigma_points = chol_lower(cav_cov) @ x + cav_mean
             var = self.link_fn(sigma_points[1]) ** 2
             S = (v0 + np.sum(w * var)).reshape(1, 1)
             C = np.sum(w * (sigma_points - cav_mean) * (sigma_points[0] - m0), axis=-1).reshape(2, 1)
@@ -193,7 +203,7 @@ def eep_update(rule, likelihood, y, post_mean, post_cov, site_params=None):
         site_cov = inv(site_nat2 + 1e-10 * np.eye(2))
         site_mean = cav_mean + (site_cov + power * cav_cov) @ Jf.T @ inv(sigma) @ residual
         sigma_marg = Jsigma @ Jsigma.T + Jf @ cav_cov @ Jf.T
-        chol = np.linalg.cholesky(sigma_marg)
+        chol = chol_lower(sigma_marg)
         lml = -1 * (.5 * site_cov.shape[0] * np.log(2 * pi) + np.sum(np.log(np.diag(chol)))
                     + .5 * (residual.T @ solve(sigma_marg, residual)).item())                  # :119-123
         if site_params is not None and rule.damping != 1.:

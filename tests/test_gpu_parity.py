@@ -346,6 +346,56 @@ def test_site_update_kernel_vs_oracle(lik, meth, has_prev):
         assert err.max() < 1e-5, float(err.max())
 
 
+HETERO_METHODS = {
+    "pep_gh_damped": ("EP", dict(power=0.5, damping=0.6)),
+    "ep_ut": ("EP", dict(power=1.0, intmethod="UT")),
+    "eep_damped": ("EEP", dict(power=0.5, damping=0.7)),
+    "eks": ("EKS", dict()),
+    "slep_gh12_damped": ("SLEP", dict(power=0.7, damping=0.5, num_cub_pts=12)),
+    "ghks": ("GHKS", dict(num_cub_pts=8)),
+    "uks": ("UKS", dict()),
+    "slep_ut3": ("SLEP", dict(power=0.3, intmethod="UT3")),
+    "vi_damped": ("VI", dict(damping=0.5)),
+    "vi_ut": ("VI", dict(intmethod="UT")),
+}
+
+
+@pytest.mark.parametrize("link", ["softplus", "exp"])
+@pytest.mark.parametrize("meth", sorted(HETERO_METHODS))
+@pytest.mark.parametrize("has_prev", [False, True])
+def test_two_latent_site_update_kernel_vs_oracle(link, meth, has_prev):
+    """kjx_site_update with func_dim = 2 (HeteroscedasticNoise): every update rule in matrix form, 2 x 2 sites, batched
+    over 2000 entries, against the oracle's restatement entry by entry (oracle/multi.py, pinned by the het_* fixtures)."""
+    from oracle import multi
+    kjx = _kjx()
+    rng = np.random.default_rng(5)
+    N = 2000
+    pm = rng.normal(0.0, 1.0, (N, 2, 1))
+    A = rng.normal(0.0, 0.5, (N, 2, 2))
+    pv = A @ A.transpose(0, 2, 1) + 0.3 * np.eye(2)
+    y = rng.normal(0.0, 1.5, (N, 1))
+    prev = None
+    if has_prev:
+        B = rng.normal(0.0, 0.3, (N, 2, 2))
+        prev = (rng.normal(0.0, 1.0, (N, 2, 1)), B @ B.transpose(0, 2, 1) + 3.0 * np.eye(2))   # cavity stays positive definite
+    o_lik = oracle.likelihoods.HeteroscedasticNoise(link)
+    o_rule = getattr(oracle.approx_inf, HETERO_METHODS[meth][0])(**HETERO_METHODS[meth][1])
+    want = [multi.site_update(o_rule, o_lik, y[i], pm[i], pv[i], None if prev is None else (prev[0][i], prev[1][i])) for i in range(N)]
+    k_rule = getattr(kjx.approximate_inference, HETERO_METHODS[meth][0])(**HETERO_METHODS[meth][1])
+    got = k_rule.update(kjx.likelihoods.HeteroscedasticNoise(link), y, pm, pv, None, prev)
+    for j, name in enumerate(("lml", "site_mean", "site_cov")):
+        a = _np(got[j]).reshape(N, -1)
+        b = np.stack([np.asarray(w[j], dtype=float).reshape(-1) for w in want])
+        assert np.array_equal(np.isnan(a), np.isnan(b)), name
+        ok = ~np.isnan(b)
+        assert ok.mean() > 0.9, name
+        # per entry, relative to the largest element of that entry's matrix (sites hold 1e10-sized "no information" entries)
+        scale = np.maximum(np.max(np.abs(np.where(ok, b, 0.0)), axis=1, keepdims=True), 1e-3)
+        err = np.abs(np.where(ok, a - b, 0.0)) / scale
+        assert np.mean(err > 5e-9) < 2e-3, (name, float(np.mean(err > 5e-9)))
+        assert err.max() < 1e-5, (name, float(err.max()))
+
+
 @pytest.mark.parametrize("lik_name,power", [("Poisson", 0.5), ("Probit", 0.3), ("Logit", 1.0), ("Gaussian", 0.7)])
 def test_likelihood_moment_match_honours_power(lik_name, power):
     """Likelihood.moment_match(y, m, v, hyp, power) (likelihoods.py:122-185): the likelihood raised to `power`."""
