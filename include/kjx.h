@@ -64,7 +64,9 @@ enum kjx_block_kind {
   KJX_BLOCK_MATERN12 = 4,      /* 1x1, priors.py:94-104 (Exponential / Matern12): exp(-dt lam), lam = 1/ell */
   KJX_BLOCK_ROTATION = 5,      /* 2x2, exp(-dt lam) R(dt omega): Cosine (priors.py:397-408, lam = 0), a harmonic
                                   of Periodic (:791-820, lam = 0) or of QuasiPeriodicMatern12 (:910-939, lam = 1/ell) */
-  KJX_BLOCK_MATERN72 = 6       /* 4x4, priors.py:326-350   : lam = sqrt(7)/ell                    */
+  KJX_BLOCK_MATERN72 = 6,      /* 4x4, priors.py:326-350   : lam = sqrt(7)/ell                    */
+  KJX_BLOCK_SUBBAND_MATERN52 = 7 /* 6x6, SubbandMatern52 (priors.py:605-721): (3x3 Matern-5/2 polynomial block) (x)
+                                  R(dt omega), lam = sqrt(5)/ell; states ordered (f, f', f'') x (cos, sin) pairs */
 };
 
 typedef struct kjx_block {

@@ -15,6 +15,7 @@ KJX_MAX_CUBATURE = 32
 
 # enums (include/kjx.h)
 BLOCK_MATERN32, BLOCK_MATERN52, BLOCK_QP_MATERN32, BLOCK_MATERN12, BLOCK_ROTATION, BLOCK_MATERN72 = 1, 2, 3, 4, 5, 6
+BLOCK_SUBBAND_MATERN52 = 7
 LIK_GAUSSIAN, LIK_BERNOULLI_PROBIT, LIK_BERNOULLI_LOGIT, LIK_POISSON_EXP, LIK_POISSON_LOGISTIC = 1, 2, 3, 4, 5
 LIK_HETERO_SOFTPLUS, LIK_HETERO_EXP = 6, 7
 INF_EP, INF_EEP, INF_SLEP, INF_VI, INF_MOMENT_MATCH = 1, 2, 3, 4, 5

@@ -828,7 +828,7 @@ int discretise_T(const kjx_model_t* m, int64_t N, const T* dt, T* A, T* Q, void*
   da.d = m->state_dim; da.n_blocks = m->n_blocks;
   for (int b = 0; b < m->n_blocks; ++b) da.blocks[b] = m->blocks[b];
   const int threads = 128, nw = threads / 32;
-  const size_t smem = (size_t)nw * m->state_dim * (4 * sizeof(T) + sizeof(int));
+  const size_t smem = (size_t)nw * m->state_dim * (KJX_ROW_W * sizeof(T) + sizeof(int));
   if (smem > 48 * 1024) return KJX_ERR_UNSUPPORTED;          // before anything is allocated
   // Pinf is a host pointer: stage it into a small device buffer owned by this call's stream order
   double* pinf_dev = nullptr;

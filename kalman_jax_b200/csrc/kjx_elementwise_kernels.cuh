@@ -39,11 +39,13 @@ struct DiscArgs {
 // rows (= columns) of one diagonal block of each kind
 __host__ __device__ __forceinline__ int block_size(int kind) {
   return kind == KJX_BLOCK_MATERN12 ? 1 : (kind == KJX_BLOCK_MATERN32 || kind == KJX_BLOCK_ROTATION) ? 2 : kind == KJX_BLOCK_MATERN52 ? 3
-         : (kind == KJX_BLOCK_QP_MATERN32 || kind == KJX_BLOCK_MATERN72) ? 4 : -1;
+         : (kind == KJX_BLOCK_QP_MATERN32 || kind == KJX_BLOCK_MATERN72) ? 4 : kind == KJX_BLOCK_SUBBAND_MATERN52 ? 6 : -1;
 }
-// Row r of A(dt): at most 4 non-zeros starting at column c0.  Expressions follow the reference's order.
+// the row format of A(dt): every row stores KJX_ROW_W values (its non-zeros first), the widest block being 6 x 6
+constexpr int KJX_ROW_W = 6;
+// Row r of A(dt): at most KJX_ROW_W non-zeros starting at column c0.  Expressions follow the reference's order.
 template <typename T>
-__device__ __forceinline__ void transition_row(const DiscArgs& da, int r, T dt, int& c0, int& nnz, T (&v)[4]) {
+__device__ __forceinline__ void transition_row(const DiscArgs& da, int r, T dt, int& c0, int& nnz, T (&v)[KJX_ROW_W]) {
   int base = 0;
   for (int b = 0; b < da.n_blocks; ++b) {
     const kjx_block_t& blk = da.blocks[b];
@@ -84,6 +86,17 @@ __device__ __forceinline__ void transition_row(const DiscArgs& da, int r, T dt, 
           v[0] = e * (dt * (lam2 * lam2 * (dtlam - T(1) - dtlam2 / T(6)))); v[1] = e * (dt * (lam3 * (T(3.5) * dtlam - T(4) - T(0.5) * dtlam2)));
           v[2] = e * (dt * (lam2 * (T(4) * dtlam - T(6) - T(0.5) * dtlam2))); v[3] = e * (dt * (lam * (T(1.5) * dtlam - T(3) - dtlam2 / T(6))) + T(1));
         }
+      } else if (blk.kind == KJX_BLOCK_SUBBAND_MATERN52) {  // priors.py:704-721: (Matern-5/2 polynomial block) (x) R(dt omega)
+        const T e = exp(-dt * lam), dtlam = dt * lam, lam2 = lam * lam, lam3 = lam2 * lam;
+        T sn, cs;
+        sincos((T)blk.omega * dt, &sn, &cs);
+        const T r0 = (rr & 1) ? sn : cs, r1 = (rr & 1) ? cs : -sn;   // row (rr&1) of R
+        const int br = rr >> 1;
+        T f0, f1, f2;
+        if (br == 0) { f0 = T(0.5) * (T(2) + dtlam * (T(2) + dtlam)); f1 = dt * (T(1) + dtlam); f2 = T(0.5) * dt * dt; }
+        else if (br == 1) { f0 = T(-0.5) * dt * dt * lam3; f1 = T(1) + dtlam * (T(1) - dtlam); f2 = T(-0.5) * dt * (T(-2) + dtlam); }
+        else { f0 = T(0.5) * dt * lam3 * (T(-2) + dtlam); f1 = dt * lam2 * (T(-3) + dtlam); f2 = T(0.5) * (T(2) + dtlam * (T(-4) + dtlam)); }
+        v[0] = e * (f0 * r0); v[1] = e * (f0 * r1); v[2] = e * (f1 * r0); v[3] = e * (f1 * r1); v[4] = e * (f2 * r0); v[5] = e * (f2 * r1);
       } else {                                              // priors.py:1066-1084, utils.py:253-265
         const T e = exp(-dt * lam);
         T sn, cs;
@@ -101,23 +114,23 @@ __device__ __forceinline__ void transition_row(const DiscArgs& da, int r, T dt, 
   c0 = 0; nnz = 0;
 }
 
-// one warp per time step (grid-stride); dynamic smem: warps * d * (4 T + 1 int)
+// one warp per time step (grid-stride); dynamic smem: warps * d * (KJX_ROW_W T + 1 int)
 template <typename T>
 __global__ void __launch_bounds__(128) discretise_kernel(const DiscArgs da, int64_t N, const T* __restrict__ dt,
                                                          T* __restrict__ A, T* __restrict__ Q,
                                                          const double* __restrict__ Pinf) {
   extern __shared__ unsigned char smem_raw[];
   const int d = da.d, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  T* rows = reinterpret_cast<T*>(smem_raw) + (size_t)warp * d * 4;
-  int* col0 = reinterpret_cast<int*>(reinterpret_cast<T*>(smem_raw) + (size_t)nw * d * 4) + (size_t)warp * d;
+  T* rows = reinterpret_cast<T*>(smem_raw) + (size_t)warp * d * KJX_ROW_W;
+  int* col0 = reinterpret_cast<int*>(reinterpret_cast<T*>(smem_raw) + (size_t)nw * d * KJX_ROW_W) + (size_t)warp * d;
   for (int64_t n = (int64_t)blockIdx.x * nw + warp; n < N; n += (int64_t)gridDim.x * nw) {
     const T h = dt[n];
     for (int r = lane; r < d; r += 32) {
-      int c0, nnz; T v[4] = {T(0), T(0), T(0), T(0)};
+      int c0, nnz; T v[KJX_ROW_W] = {};
       transition_row<T>(da, r, h, c0, nnz, v);
       col0[r] = c0 | (nnz << 24);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) rows[r * 4 + q] = v[q];
+      for (int q = 0; q < KJX_ROW_W; ++q) rows[r * KJX_ROW_W + q] = v[q];
     }
     __syncwarp();
     T* An = A + n * (int64_t)d * d;
@@ -125,14 +138,14 @@ __global__ void __launch_bounds__(128) discretise_kernel(const DiscArgs da, int6
     for (int e = lane; e < d * d; e += 32) {
       const int i = e / d, j = e % d;
       const int ci = col0[i] & 0xffffff, ni = col0[i] >> 24;
-      An[e] = (j >= ci && j < ci + ni) ? rows[i * 4 + (j - ci)] : T(0);
+      An[e] = (j >= ci && j < ci + ni) ? rows[i * KJX_ROW_W + (j - ci)] : T(0);
       if (Qn) {
         const int cj = col0[j] & 0xffffff, nj = col0[j] >> 24;
         T s = T(0);   // (A Pinf A^T)[i][j] over the two rows' non-zeros
         for (int p = 0; p < ni; ++p) {
           T t = T(0);
-          for (int q = 0; q < nj; ++q) t += (T)Pinf[(ci + p) * d + (cj + q)] * rows[j * 4 + q];
-          s += rows[i * 4 + p] * t;
+          for (int q = 0; q < nj; ++q) t += (T)Pinf[(ci + p) * d + (cj + q)] * rows[j * KJX_ROW_W + q];
+          s += rows[i * KJX_ROW_W + p] * t;
         }
         Qn[e] = (T)Pinf[e] - s;
       }

@@ -39,7 +39,7 @@ template <typename T> struct GenericCarve {
     pinf = take(d * d * 8); h = take(d * 8);
     mean = take(n * d * sizeof(T)); cov = take(n * d * d * sizeof(T));           // dense filter output (kjx_run without caller buffers)
     gain = take(n * tsz * sizeof(T)); lc = take(n * tsz * sizeof(T)); gc = take(n * gs * sizeof(T));   // RTS gains and affine terms, padded tiles
-    rows = take((n + 1) * d * 4 * sizeof(T)); c0n = take(d * sizeof(int));       // rows of A(dt[n]) for every step
+    rows = take((n + 1) * d * KJX_ROW_W * sizeof(T)); c0n = take(d * sizeof(int));       // rows of A(dt[n]) for every step
     pred = take(2 * n * sizeof(T)); post = take(2 * n * sizeof(T));              // predictive / smoothed marginals of every step
     llpart = take(((n + 127) / 128) * sizeof(T));
     sum = take(P * (3 * d * d + 2 * d) * sizeof(T));                             // chunk elements, states, informations, nlml
@@ -70,6 +70,8 @@ int generic_setup(const kjx_model_t* m, int64_t N, void* ws, size_t ws_bytes, Ge
   b.mean = (T*)(w + c.mean); b.cov = (T*)(w + c.cov); b.gain = (T*)(w + c.gain);
   g.Lc = (T*)(w + c.lc); g.gc = (T*)(w + c.gc);
   g.rows = (T*)(w + c.rows); g.c0n_g = (int*)(w + c.c0n);
+  g.roww = 4;
+  for (int k = 0; k < m->n_blocks; ++k) if (block_size(m->blocks[k].kind) > 4) g.roww = KJX_ROW_W;
   g.pred_mean = nullptr; g.pred_var = nullptr;               // set by the caller when the log-likelihood is batched
   b.post_mean = (T*)(w + c.post); b.post_var = b.post_mean + n;
   b.llpart = (T*)(w + c.llpart);
@@ -97,7 +99,7 @@ template <typename T> void generic_use_batched_loglik(GenArgs<T>& g, const kjx_m
 // rows of A(dt[n]) for every step of the call (g.dt must be set)
 template <typename T> int generic_launch_rows(const GenArgs<T>& g, cudaStream_t st) {
   const int64_t total = (g.N + 1) * (int64_t)g.d;
-  generic_rows_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g.disc, g.d, g.N, g.dt, const_cast<T*>(g.rows), const_cast<int*>(g.c0n_g));
+  generic_rows_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g.disc, g.d, g.roww, g.N, g.dt, const_cast<T*>(g.rows), const_cast<int*>(g.c0n_g));
   return KJX_OK;
 }
 // shared-memory build (tiles addressed as __shared__) or global-scratch build (d > 64) of a kernel template
@@ -142,8 +144,13 @@ template <typename T> int generic_launch_filter(const GenArgs<T>& g, T* llpart, 
   if (nblk <= 16 && !tile_knob && !g.gscratch) {
     // at most 16 diagonal blocks: P in registers, one thread per pair of blocks
     const size_t smem = generic_filter_blocks_smem<T>(g.d);
-    KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_filter_blocks_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    generic_filter_blocks_kernel<T><<<g.nchunks, KJX_GEN_THREADS, smem, st>>>(g);
+    if (g.roww > 4) {               // a 6 x 6 block (Subband Matern-5/2): larger register tiles, 6-wide rows
+      KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_filter_blocks_kernel<T, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      generic_filter_blocks_kernel<T, 6><<<g.nchunks, KJX_GEN_THREADS, smem, st>>>(g);
+    } else {
+      KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_filter_blocks_kernel<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      generic_filter_blocks_kernel<T, 4><<<g.nchunks, KJX_GEN_THREADS, smem, st>>>(g);
+    }
   } else {
     KJX_GEN_LAUNCH(generic_filter_kernel, g.nchunks, KJX_GEN_THREADS, generic_filter_smem<T>(g.d), st, g);
   }
@@ -160,7 +167,18 @@ template <typename T> int generic_launch_filter(const GenArgs<T>& g, T* llpart, 
 template <typename T> int generic_launch_smoother(const GenArgs<T>& g, T* gains, cudaStream_t st) {
   // 1. all RTS gains and the affine terms of the recursion, parallel over time (they depend on the filtered moments only)
   const unsigned grid = (unsigned)std::min<int64_t>(g.N, KJX_GEN_GAIN_GRID);
-  KJX_GEN_LAUNCH(generic_gain_kernel, grid, KJX_GEN_GAIN_THREADS, generic_gain_smem<T>(g.d), st, g, gains);
+#define KJX_GAIN_LAUNCH(RW)                                                                                              \
+  do {                                                                                                                  \
+    if (g.gscratch) {                                                                                                   \
+      generic_gain_kernel<T, true, RW><<<grid, KJX_GEN_GAIN_THREADS, 0, st>>>(g, gains);                                \
+    } else {                                                                                                            \
+      const size_t smem = generic_gain_smem<T>(g.d);                                                                    \
+      KJX_CUDA_CHECK(cudaFuncSetAttribute(generic_gain_kernel<T, false, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      generic_gain_kernel<T, false, RW><<<grid, KJX_GEN_GAIN_THREADS, smem, st>>>(g, gains);                            \
+    }                                                                                                                   \
+  } while (0)
+  if (g.roww == 4) KJX_GAIN_LAUNCH(4); else KJX_GAIN_LAUNCH(KJX_ROW_W);
+#undef KJX_GAIN_LAUNCH
   // 2. the backward recursion (two d^3 products per step), every chunk concurrently
   KJX_GEN_LAUNCH(generic_smoother_kernel, g.nchunks, KJX_GEN_THREADS, generic_smoother_smem<T>(g.d), st, g, (const T*)gains);
   // 3. the site update of every step from the smoothed marginals, embarrassingly parallel (sde_gp.py:373-379)

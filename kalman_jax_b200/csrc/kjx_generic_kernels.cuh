@@ -11,8 +11,8 @@
 // initialised from the predictive) it is the plain sequential walk.
 //
 // How a CTA (8 warps) spends a step:
-//   * A(dt) is never formed densely: every row of the block-diagonal transition has at most 4 non-zeros
-//     (transition_row, kjx_elementwise_kernels.cuh), so A X A^T costs 8 d^2 flops instead of 4 d^3;
+//   * A(dt) is never formed densely: every row of the block-diagonal transition has at most 6 non-zeros
+//     (transition_row, kjx_elementwise_kernels.cuh), so A X A^T costs at most 12 d^2 flops instead of 4 d^3;
 //   * the update is rank one (f = 1): K = P H^T / S, P -= K (H P);
 //   * the dense d^3 work — the two products of the RTS update, the trailing updates of the blocked Cholesky /
 //     triangular solves of the gain (utils.py:25-30), the products of the boundary walk — goes through the FP64
@@ -59,9 +59,10 @@ template <typename T> struct GenArgs {
   T* gsum;                 // [ngroups][3 d^2 + 2 d]   group elements of the two-level boundary walk
   T* chunk_nlml;           // [nchunks]
   // per-call precomputation (generic_rows_kernel): the non-zeros of every row of A(dt[n]) for all steps, so the chain
-  // kernels load 4 d scalars per step instead of evaluating exp / sincos in double on their critical path
-  const T* rows;           // [N + 1][d][4]; slot N is A(0) = I (the smoother's transition out of the last step, sde_gp.py:337)
+  // kernels load KJX_ROW_W d scalars per step instead of evaluating exp / sincos in double on their critical path
+  const T* rows;           // [N + 1][d][roww]; slot N is A(0) = I (the smoother's transition out of the last step, sde_gp.py:337)
   const int* c0n_g;        // [d]  first column | nnz << 24 of every row (step-invariant)
+  int roww;                // values stored per row: 4, or 6 (= KJX_ROW_W) when the prior has a 6 x 6 block
   // batched per-step work taken OUT of the chains (steady-state iterations, where it does not feed the recursion)
   T* pred_mean; T* pred_var;   // [N] filter predictive H m_, H P_ H^T -> log-likelihood terms by generic_loglik_kernel
   T* post_mean; T* post_var;   // [N] smoothed marginal H m, H P H^T -> site update by site_update_kernel
@@ -77,10 +78,11 @@ struct GenLayout {
   int ld;    // leading dimension: >= round_up(d, 4) and = 4 (mod 8)
   int mp;    // rows that fragment loads may touch: round_up(d, 16)
   int msz;   // scalars per tile (mp * ld + a tail for column over-reads of the last row)
+  int w;     // values stored per row of A(dt) (GenArgs::roww): 4 or 6
 };
-__host__ __device__ inline GenLayout gen_layout(int d) {
+__host__ __device__ inline GenLayout gen_layout(int d, int w = KJX_ROW_W) {
   GenLayout L;
-  L.d = d;
+  L.d = d; L.w = w;
   const int kp = (d + 3) & ~3;
   L.ld = kp + ((kp & 7) ? 0 : 4);
   L.mp = (d + 15) & ~15;
@@ -100,35 +102,35 @@ template <typename T> struct SmemCarver {
   __device__ int* take_int(int n) { int* r = reinterpret_cast<int*>(p); p += ((size_t)n * sizeof(int) + 15) / 16 * 16; return r; }
 };
 
-// rows of A(dt) for all d rows: vals[d][4], c0n[d] = first column | nnz << 24
+// rows of A(dt) for all d rows: vals[d][KJX_ROW_W], c0n[d] = first column | nnz << 24
 template <typename T>
-__device__ __forceinline__ void build_rows(const DiscArgs& da, int d, T dt, T* vals, int* c0n) {
+__device__ __forceinline__ void build_rows(const DiscArgs& da, int d, int w, T dt, T* vals, int* c0n) {
   KJX_GEN_VEC(r, d) {
-    int c0, nnz; T v[4] = {T(0), T(0), T(0), T(0)};
+    int c0, nnz; T v[KJX_ROW_W] = {};
     transition_row<T>(da, r, dt, c0, nnz, v);
     c0n[r] = c0 | (nnz << 24);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) vals[r * 4 + q] = v[q];
+    for (int q = 0; q < KJX_ROW_W; ++q) if (q < w) vals[r * w + q] = v[q];
   }
 }
 // all rows of all steps, once per call
 template <typename T>
-__global__ void __launch_bounds__(256) generic_rows_kernel(const DiscArgs da, int d, int64_t N, const T* __restrict__ dt,
+__global__ void __launch_bounds__(256) generic_rows_kernel(const DiscArgs da, int d, int w, int64_t N, const T* __restrict__ dt,
                                                            T* __restrict__ rows, int* __restrict__ c0n_g) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (N + 1) * d) return;
   const int64_t n = e / d; const int r = (int)(e - n * d);
-  int c0, nnz; T v[4] = {T(0), T(0), T(0), T(0)};
+  int c0, nnz; T v[KJX_ROW_W] = {};
   transition_row<T>(da, r, (n < N) ? dt[n] : T(0), c0, nnz, v);
   if (n == 0) c0n_g[r] = c0 | (nnz << 24);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) rows[e * 4 + q] = v[q];
+  for (int q = 0; q < KJX_ROW_W; ++q) if (q < w) rows[e * w + q] = v[q];
 }
 // the precomputed rows of step `idx` -> vals (all threads; caller synchronises)
 template <typename T>
 __device__ __forceinline__ void fetch_rows(const GenArgs<T>& g, int64_t idx, T* vals) {
-  const T* src = g.rows + idx * 4 * (int64_t)g.d;
-  KJX_GEN_VEC(e, 4 * g.d) vals[e] = src[e];
+  const T* src = g.rows + idx * g.roww * (int64_t)g.d;
+  KJX_GEN_VEC(e, g.roww * g.d) vals[e] = src[e];
 }
 template <typename T>
 __device__ __forceinline__ void fetch_c0n(const GenArgs<T>& g, int* c0n) { KJX_GEN_VEC(r, g.d) c0n[r] = g.c0n_g[r]; }
@@ -150,22 +152,22 @@ __device__ __forceinline__ void tile_map(int d, LoadF load, StoreF store) {
 }
 // out = A x
 template <typename T>
-__device__ __forceinline__ void rows_matvec(int d, const T* vals, const int* c0n, const T* x, T* out) {
-  KJX_GEN_VEC(i, d) {
+__device__ __forceinline__ void rows_matvec(const GenLayout& L, const T* vals, const int* c0n, const T* x, T* out) {
+  KJX_GEN_VEC(i, L.d) {
     const int c0 = c0n[i] & 0xffffff, nn = c0n[i] >> 24;
     T s = T(0);
-    for (int q = 0; q < nn; ++q) s += vals[i * 4 + q] * x[c0 + q];
+    for (int q = 0; q < nn; ++q) s += vals[i * L.w + q] * x[c0 + q];
     out[i] = s;
   }
 }
 // Y = A (X - S)     (S may be null; ldx / lds: leading dimensions of X and S, Y uses L.ld)
-template <typename T, typename TS>
-__device__ __forceinline__ void rows_left(const GenLayout& L, const T* vals, const int* c0n, const T* X, int ldx,
-                                          const TS* S, int lds, T* Y) {
+template <typename T, typename TS, int W>
+__device__ __forceinline__ void rows_left_w(const GenLayout& L, const T* vals, const int* c0n, const T* X, int ldx,
+                                            const TS* S, int lds, T* Y) {
   constexpr int U = 4;
   const int d = L.d, ld = L.ld, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int i0 = warp; i0 < d; i0 += U * nw) {
-    int c0[U], nn[U]; T v[U][4];
+    int c0[U], nn[U]; T v[U][W];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int i = i0 + u * nw;
@@ -173,7 +175,7 @@ __device__ __forceinline__ void rows_left(const GenLayout& L, const T* vals, con
       if (i < d) {
         const int c = c0n[i]; c0[u] = c & 0xffffff; nn[u] = c >> 24;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) v[u][q] = vals[i * 4 + q];
+        for (int q = 0; q < W; ++q) v[u][q] = vals[i * W + q];
       }
     }
     for (int j = lane; j < d; j += 32) {
@@ -184,7 +186,7 @@ __device__ __forceinline__ void rows_left(const GenLayout& L, const T* vals, con
         if (nn[u] >= 0) {
           const T* x = X + c0[u] * ldx + j;
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
+          for (int q = 0; q < W; ++q)
             if (q < nn[u]) s[u] += v[u][q] * (S ? x[q * ldx] - (T)S[(c0[u] + q) * lds + j] : x[q * ldx]);
         }
       }
@@ -193,41 +195,53 @@ __device__ __forceinline__ void rows_left(const GenLayout& L, const T* vals, con
     }
   }
 }
+// (the row width is uniform over the launch: one well-predicted branch; the 4-wide build keeps its registers and loads)
+template <typename T, typename TS>
+__device__ __forceinline__ void rows_left(const GenLayout& L, const T* vals, const int* c0n, const T* X, int ldx,
+                                          const TS* S, int lds, T* Y) {
+  if (L.w == 4) rows_left_w<T, TS, 4>(L, vals, c0n, X, ldx, S, lds, Y);
+  else rows_left_w<T, TS, KJX_ROW_W>(L, vals, c0n, X, ldx, S, lds, Y);
+}
 // X <- A X in place: the rows of one diagonal block of A only depend on the same rows of X.  bstart: first rows of the
 // blocks, nblk of them.
-template <typename T>
-__device__ __forceinline__ void rows_left_inplace(const GenLayout& L, const T* vals, const int* c0n, const int* bstart, int nblk, T* X) {
+template <typename T, int W>
+__device__ __forceinline__ void rows_left_inplace_w(const GenLayout& L, const T* vals, const int* c0n, const int* bstart, int nblk, T* X) {
   const int d = L.d, ld = L.ld, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int b = warp; b < nblk; b += nw) {
     const int i = bstart[b], nn = c0n[i] >> 24;
     for (int j = lane; j < d; j += 32) {
-      T x[4], s[4];
+      T x[W], s[W];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) x[q] = (q < nn) ? X[(i + q) * ld + j] : T(0);
+      for (int q = 0; q < W; ++q) x[q] = (q < nn) ? X[(i + q) * ld + j] : T(0);
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
+      for (int r = 0; r < W; ++r) {
         s[r] = T(0);
         if (r < nn) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) if (q < nn) s[r] += vals[(i + r) * 4 + q] * x[q];
+          for (int q = 0; q < W; ++q) if (q < nn) s[r] += vals[(i + r) * W + q] * x[q];
         }
       }
 #pragma unroll
-      for (int r = 0; r < 4; ++r) if (r < nn) X[(i + r) * ld + j] = s[r];
+      for (int r = 0; r < W; ++r) if (r < nn) X[(i + r) * ld + j] = s[r];
     }
   }
 }
+template <typename T>
+__device__ __forceinline__ void rows_left_inplace(const GenLayout& L, const T* vals, const int* c0n, const int* bstart, int nblk, T* X) {
+  if (L.w == 4) rows_left_inplace_w<T, 4>(L, vals, c0n, bstart, nblk, X);
+  else rows_left_inplace_w<T, KJX_ROW_W>(L, vals, c0n, bstart, nblk, X);
+}
 // Z = sign * (Y A^T + Pinf) + (Base ? Base : 0)      (ldp: leading dimension of Pinf; Y, Z, Base use L.ld)
-template <typename T, typename TP>
-__device__ __forceinline__ void rows_right_add(const GenLayout& L, const T* vals, const int* c0n, const T* Y, const TP* Pinf, int ldp,
-                                               T* Z, const T* Base = nullptr, T sign = T(1)) {
+template <typename T, typename TP, int W>
+__device__ __forceinline__ void rows_right_add_w(const GenLayout& L, const T* vals, const int* c0n, const T* Y, const TP* Pinf, int ldp,
+                                                 T* Z, const T* Base, T sign) {
   constexpr int U = 4;
   const int d = L.d, ld = L.ld, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int j = lane; j < d; j += 32) {
     const int c0 = c0n[j] & 0xffffff, nn = c0n[j] >> 24;
-    T v[4];
+    T v[W];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) v[q] = vals[j * 4 + q];
+    for (int q = 0; q < W; ++q) v[q] = vals[j * W + q];
     for (int i0 = warp; i0 < d; i0 += U * nw) {
       T s[U];
 #pragma unroll
@@ -238,7 +252,7 @@ __device__ __forceinline__ void rows_right_add(const GenLayout& L, const T* vals
           const T* y = Y + i * ld + c0;
           T t = T(0);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) if (q < nn) t += y[q] * v[q];
+          for (int q = 0; q < W; ++q) if (q < nn) t += y[q] * v[q];
           t += (T)Pinf[i * ldp + j];
           s[u] = Base ? Base[i * ld + j] + sign * t : sign * t;
         }
@@ -247,6 +261,12 @@ __device__ __forceinline__ void rows_right_add(const GenLayout& L, const T* vals
       for (int u = 0; u < U; ++u) { const int i = i0 + u * nw; if (i < d) Z[i * ld + j] = s[u]; }
     }
   }
+}
+template <typename T, typename TP>
+__device__ __forceinline__ void rows_right_add(const GenLayout& L, const T* vals, const int* c0n, const T* Y, const TP* Pinf, int ldp,
+                                               T* Z, const T* Base = nullptr, T sign = T(1)) {
+  if (L.w == 4) rows_right_add_w<T, TP, 4>(L, vals, c0n, Y, Pinf, ldp, Z, Base, sign);
+  else rows_right_add_w<T, TP, KJX_ROW_W>(L, vals, c0n, Y, Pinf, ldp, Z, Base, sign);
 }
 // dense [d][d] global <-> padded tile
 template <typename T, typename S>
@@ -746,7 +766,7 @@ template <typename T> __device__ __forceinline__ void tri_backward(const GenLayo
 // working-set sizes (bytes); the same carve-up lives in global scratch when d > KJX_GEN_DMAX
 template <typename T> size_t generic_fold_smem(int d) {
   const GenLayout L = gen_layout(d);
-  return (size_t)(6 * L.msz + 4 * d + 9 * d + KJX_GEN_WARPS * d + 16 + 32) * sizeof(T) + (size_t)(d + 4) * sizeof(int) + 256;
+  return (size_t)(6 * L.msz + KJX_ROW_W * d + 9 * d + KJX_GEN_WARPS * d + 16 + 32) * sizeof(T) + (size_t)(d + 4) * sizeof(int) + 256;
 }
 template <typename T> size_t generic_boundary_smem(int d) {
   const GenLayout L = gen_layout(d);
@@ -754,15 +774,15 @@ template <typename T> size_t generic_boundary_smem(int d) {
 }
 template <typename T> size_t generic_filter_smem(int d) {
   const GenLayout L = gen_layout(d);
-  return (size_t)(3 * L.msz + 4 * d + 5 * d + KJX_GEN_WARPS * d + 16 + 32) * sizeof(T) + (size_t)(d + 4) * sizeof(int) + 256;
+  return (size_t)(3 * L.msz + KJX_ROW_W * d + 5 * d + KJX_GEN_WARPS * d + 16 + 32) * sizeof(T) + (size_t)(d + 4) * sizeof(int) + 256;
 }
 template <typename T> size_t generic_gain_smem(int d) {
   const GenLayout L = gen_layout(d);
-  return (size_t)(2 * L.msz + 7 * d + 16) * sizeof(T) + (size_t)(2 * d + 8) * sizeof(int) + 256;
+  return (size_t)(2 * L.msz + (KJX_ROW_W + 3) * d + 16) * sizeof(T) + (size_t)(2 * d + 8) * sizeof(int) + 256;
 }
 template <typename T> size_t generic_smoother_smem(int d) {
   const GenLayout L = gen_layout(d);
-  return (size_t)(6 * L.msz + 4 * d + 9 * d + KJX_GEN_WARPS * d + 16 + 32) * sizeof(T) + (size_t)(3 * d + 44) * sizeof(int) + 512;
+  return (size_t)(6 * L.msz + KJX_ROW_W * d + 9 * d + KJX_GEN_WARPS * d + 16 + 32) * sizeof(T) + (size_t)(3 * d + 44) * sizeof(int) + 512;
 }
 
 // Scan quantities are kept in EQUILIBRATED coordinates x~ = D^-1 x with D = sqrt(diag(Pinf)): the components of a Sum
@@ -786,11 +806,11 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_fold_kernel(const Gen
   // GS: the working set lives in per-CTA global scratch (d > 64); otherwise in shared memory — a compile-time choice so
   // that the shared-memory build addresses its tiles with LDS / STS and 32-bit offsets instead of generic 64-bit pointers
   SmemCarver<T> sc(GS ? g.gscratch + (size_t)blockIdx.x * g.gscratch_stride : smem_raw);
-  const GenLayout L = gen_layout(g.d);
+  const GenLayout L = gen_layout(g.d, g.roww);
   const int d = L.d, ld = L.ld, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   T* A = sc.take(L.msz); T* A2 = sc.take(L.msz); T* C = sc.take(L.msz); T* Y = sc.take(L.msz); T* J = sc.take(L.msz);
   T* Pinf = sc.take(L.msz);
-  T* vals = sc.take(4 * d); T* b = sc.take(d); T* eta = sc.take(d); T* t1 = sc.take(d); T* Hrow = sc.take(d);
+  T* vals = sc.take(KJX_ROW_W * d); T* b = sc.take(d); T* eta = sc.take(d); T* t1 = sc.take(d); T* Hrow = sc.take(d);
   T* av = sc.take(d); T* cv = sc.take(d); T* part = sc.take(KJX_GEN_WARPS * d); T* sh = sc.take(16);
   T* Dv = sc.take(d); T* Dinv = sc.take(d);
   int* c0n = sc.take_int(d);
@@ -807,9 +827,10 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_fold_kernel(const Gen
   __syncthreads();
   for (int64_t n = n0; n < n1; ++n) {
     {                                                       // rows of A~ = D^-1 A D from the precomputed rows of A(dt[n])
-      const T* src = g.rows + n * 4 * (int64_t)d;
-      KJX_GEN_VEC(e, 4 * d) {
-        const int r = e >> 2, q = e & 3, c0 = c0n[r] & 0xffffff, nn = c0n[r] >> 24;
+      const int w = L.w;
+      const T* src = g.rows + n * w * (int64_t)d;
+      KJX_GEN_VEC(e, w * d) {
+        const int r = e / w, q = e - r * w, c0 = c0n[r] & 0xffffff, nn = c0n[r] >> 24;
         vals[e] = (q < nn) ? src[e] * Dv[c0 + q] * Dinv[r] : T(0);
       }
     }
@@ -817,7 +838,7 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_fold_kernel(const Gen
     __syncthreads();
     rows_left<T, T>(L, vals, c0n, A, ld, nullptr, 0, A2);   // A2 <- F A
     rows_left<T, T>(L, vals, c0n, C, ld, Pinf, ld, Y);      // Y  <- F (C - Pinf)
-    rows_matvec<T>(d, vals, c0n, b, t1);                    // t1 <- F b
+    rows_matvec<T>(L, vals, c0n, b, t1);                    // t1 <- F b
     __syncthreads();
     { T* t = A; A = A2; A2 = t; }
     rows_right_add<T, T>(L, vals, c0n, Y, Pinf, ld, C);     // C <- F (C - Pinf) F^T + Pinf
@@ -889,7 +910,7 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_boundary_kernel(const
   // GS: the working set lives in per-CTA global scratch (d > 64); otherwise in shared memory — a compile-time choice so
   // that the shared-memory build addresses its tiles with LDS / STS and 32-bit offsets instead of generic 64-bit pointers
   SmemCarver<T> sc(GS ? g.gscratch + (size_t)blockIdx.x * g.gscratch_stride : smem_raw);
-  const GenLayout L = gen_layout(g.d);
+  const GenLayout L = gen_layout(g.d, g.roww);
   const int d = L.d, dd = d * d, ld = L.ld;
   T* P = sc.take(L.msz); T* M = sc.take(L.msz); T* R = sc.take(L.msz); T* Tm = sc.take(L.msz);
   T* m = sc.take(d); T* w = sc.take(d); T* rv = sc.take(d); T* Dv = sc.take(d); T* Dinv = sc.take(d); T* dscr = sc.take(16);
@@ -1006,7 +1027,7 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_group_kernel(const Ge
   // GS: the working set lives in per-CTA global scratch (d > 64); otherwise in shared memory — a compile-time choice so
   // that the shared-memory build addresses its tiles with LDS / STS and 32-bit offsets instead of generic 64-bit pointers
   SmemCarver<T> sc(GS ? g.gscratch + (size_t)blockIdx.x * g.gscratch_stride : smem_raw);
-  const GenLayout L = gen_layout(g.d);
+  const GenLayout L = gen_layout(g.d, g.roww);
   const int d = L.d, dd = d * d, ld = L.ld;
   T* T0 = sc.take(L.msz); T* T1 = sc.take(L.msz); T* T2 = sc.take(L.msz); T* T3 = sc.take(L.msz); T* T4 = sc.take(L.msz);
   T* rv = sc.take(d); T* v = sc.take(d); T* w1 = sc.take(d); T* w2 = sc.take(d); T* bn = sc.take(d); T* en = sc.take(d); T* dscr = sc.take(16);
@@ -1079,10 +1100,10 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_filter_kernel(const G
   // GS: the working set lives in per-CTA global scratch (d > 64); otherwise in shared memory — a compile-time choice so
   // that the shared-memory build addresses its tiles with LDS / STS and 32-bit offsets instead of generic 64-bit pointers
   SmemCarver<T> sc(GS ? g.gscratch + (size_t)blockIdx.x * g.gscratch_stride : smem_raw);
-  const GenLayout L = gen_layout(g.d);
+  const GenLayout L = gen_layout(g.d, g.roww);
   const int d = L.d, dd = d * d, ld = L.ld, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   T* P = sc.take(L.msz); T* Y = sc.take(L.msz); T* Pinf = sc.take(L.msz);
-  T* vals = sc.take(4 * d); T* m = sc.take(d); T* mp = sc.take(d); T* Hrow = sc.take(d); T* HP = sc.take(d);
+  T* vals = sc.take(KJX_ROW_W * d); T* m = sc.take(d); T* mp = sc.take(d); T* Hrow = sc.take(d); T* HP = sc.take(d);
   T* part = sc.take(KJX_GEN_WARPS * d);
   T* sh = sc.take(16);                 // scalars: 0 pm, 2 site_mean, 4 Sinv, 5 masked, 6 nlml
   int* c0n = sc.take_int(d);
@@ -1100,7 +1121,7 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_filter_kernel(const G
     fetch_rows<T>(g, n, vals);                                                      // :276
     if (g.H_steps) KJX_GEN_VEC(i, d) Hrow[i] = (T)g.H_steps[n * d + i];             // :282
     __syncthreads();
-    rows_matvec<T>(d, vals, c0n, m, mp);                                            // :277
+    rows_matvec<T>(L, vals, c0n, m, mp);                                            // :277
     rows_left<T, T>(L, vals, c0n, P, ld, Pinf, ld, Y);                              // Y <- A (P - Pinf)
     __syncthreads();
     rows_right_add<T, T>(L, vals, c0n, Y, Pinf, ld, P);                             // P <- P_ = . A^T + Pinf   (:278)
@@ -1156,14 +1177,16 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_filter_kernel(const G
 // barrier — and only the row vector H P needs a reduction over block rows.  Three barriers per step instead of six and
 // none of the tile traffic that bounds the kernel above; bit-compatible with it up to the order of that one reduction.
 template <typename T> size_t generic_filter_blocks_smem(int d) {
-  return (size_t)(4 * d + 4 * d + 16 * d + 16) * sizeof(T) + (size_t)(d + 40) * sizeof(int) + 256;
+  return (size_t)(KJX_ROW_W * d + 4 * d + 16 * d + 16) * sizeof(T) + (size_t)(d + 40) * sizeof(int) + 256;
 }
-template <typename T>
+// BS: the largest diagonal block of A (4, or 6 with a Subband Matern-5/2 component): size of the register tiles
+template <typename T, int BS>
 __global__ void __launch_bounds__(KJX_GEN_THREADS, 1) generic_filter_blocks_kernel(const GenArgs<T> g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemCarver<T> sc(smem_raw);
+  const GenLayout L = gen_layout(g.d, g.roww);
   const int d = g.d, dd = d * d, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  T* vals = sc.take(4 * d); T* m = sc.take(d); T* mp = sc.take(d); T* Hrow = sc.take(d); T* HP = sc.take(d);
+  T* vals = sc.take(KJX_ROW_W * d); T* m = sc.take(d); T* mp = sc.take(d); T* Hrow = sc.take(d); T* HP = sc.take(d);
   T* part = sc.take(16 * d);
   T* sh = sc.take(16);                 // scalars: 0 pm, 2 site_mean, 4 Sinv, 5 masked, 6 nlml
   int* c0n = sc.take_int(d); int* bstart = sc.take_int(17); int* bsize = sc.take_int(17);
@@ -1181,13 +1204,14 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS, 1) generic_filter_blocks_kern
   const bool owner = (int)threadIdx.x < nblk * nblk;
   const int bi = owner ? (int)threadIdx.x / nblk : 0, bj = owner ? (int)threadIdx.x % nblk : 0;
   const int r0 = bstart[bi], ni = owner ? bsize[bi] : 0, c0 = bstart[bj], nj = owner ? bsize[bj] : 0;
-  T Pb[4][4], Qb[4][4];
+  constexpr int RW = (BS > 4) ? KJX_ROW_W : 4;     // the host launches BS = 6 exactly when the rows are 6 wide
+  T Pb[BS][BS], Qb[BS][BS];
   {
     const T* sP = g.st_P + (size_t)blockIdx.x * dd;
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < BS; ++a)
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
+      for (int b = 0; b < BS; ++b) {
         const bool in = a < ni && b < nj;
         Pb[a][b] = in ? sP[(size_t)(r0 + a) * d + c0 + b] : T(0);
         Qb[a][b] = in ? (T)g.Pinf[(size_t)(r0 + a) * d + c0 + b] : T(0);
@@ -1197,37 +1221,37 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS, 1) generic_filter_blocks_kern
     fetch_rows<T>(g, n, vals);                                                      // :276
     if (g.H_steps) KJX_GEN_VEC(i, d) Hrow[i] = (T)g.H_steps[n * d + i];             // :282
     __syncthreads();
-    rows_matvec<T>(d, vals, c0n, m, mp);                                            // :277
+    rows_matvec<T>(L, vals, c0n, m, mp);                                            // :277
     if (owner) {
-      T Fi[4][4], Fj[4][4], Y[4][4];
+      T Fi[BS][BS], Fj[BS][BS], Y[BS][BS];
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int a = 0; a < BS; ++a)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { Fi[a][q] = (a < ni) ? vals[(r0 + a) * 4 + q] : T(0); Fj[a][q] = (a < nj) ? vals[(c0 + a) * 4 + q] : T(0); }
+        for (int q = 0; q < BS; ++q) { Fi[a][q] = (a < ni) ? vals[(r0 + a) * RW + q] : T(0); Fj[a][q] = (a < nj) ? vals[(c0 + a) * RW + q] : T(0); }
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int a = 0; a < BS; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {                                               // Y = A (P - Pinf)
+        for (int b = 0; b < BS; ++b) {                                               // Y = A (P - Pinf)
           T s = T(0);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) if (q < ni) s += Fi[a][q] * (Pb[q][b] - Qb[q][b]);
+          for (int q = 0; q < BS; ++q) if (q < ni) s += Fi[a][q] * (Pb[q][b] - Qb[q][b]);
           Y[a][b] = s;
         }
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int a = 0; a < BS; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {                                               // P_ = Y A^T + Pinf        (:278)
+        for (int b = 0; b < BS; ++b) {                                               // P_ = Y A^T + Pinf        (:278)
           T t = T(0);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) if (q < nj) t += Y[a][q] * Fj[b][q];
+          for (int q = 0; q < BS; ++q) if (q < nj) t += Y[a][q] * Fj[b][q];
           Pb[a][b] = (a < ni && b < nj) ? t + Qb[a][b] : T(0);
         }
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {                                                 // this block row's share of H P_
+      for (int b = 0; b < BS; ++b) {                                                 // this block row's share of H P_
         if (b < nj) {
           T s = T(0);
 #pragma unroll
-          for (int a = 0; a < 4; ++a) if (a < ni) s += Hrow[r0 + a] * Pb[a][b];
+          for (int a = 0; a < BS; ++a) if (a < ni) s += Hrow[r0 + a] * Pb[a][b];
           part[bi * d + c0 + b] = s;
         }
       }
@@ -1269,9 +1293,9 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS, 1) generic_filter_blocks_kern
     if (owner) {
       T* fc = g.filt_cov ? g.filt_cov + n * (int64_t)dd : nullptr;
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int a = 0; a < BS; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
+        for (int b = 0; b < BS; ++b) {
           if (a < ni && b < nj) {
             if (!masked) Pb[a][b] = Pb[a][b] - HP[r0 + a] * Sinv * HP[c0 + b];       // :296 / :299
             if (fc) fc[(size_t)(r0 + a) * d + c0 + b] = Pb[a][b];
@@ -1294,16 +1318,18 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS, 1) generic_filter_blocks_kern
 // two products per step.  Gt and Lc go out in the padded tile layout ([d][ld]: 16-byte rows) so that the smoother can
 // fetch each with one bulk copy.  Working set: two tiles in shared memory (61 KB at d = 59, three CTAs per SM).
 template <typename T> __host__ __device__ inline int gen_vec_stride(int d) { return (d + 3) & ~3; }   // 16-byte multiple for both types
-template <typename T, bool GS>
+// RW: row width of A(dt) as a compile-time constant (4 or KJX_ROW_W = g.roww): this kernel sits at its register limit,
+// and carrying both row-product variants behind a run-time branch cost 16 % (6.8 against 5.8 ms at C3).
+template <typename T, bool GS, int RW>
 __global__ void __launch_bounds__(KJX_GEN_GAIN_THREADS, 3) generic_gain_kernel(const GenArgs<T> g, T* __restrict__ Gt_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // GS: the working set lives in per-CTA global scratch (d > 64); otherwise in shared memory — a compile-time choice so
   // that the shared-memory build addresses its tiles with LDS / STS and 32-bit offsets instead of generic 64-bit pointers
   SmemCarver<T> sc(GS ? g.gscratch + (size_t)blockIdx.x * g.gscratch_stride : smem_raw);
-  const GenLayout L = gen_layout(g.d);
+  const GenLayout L = gen_layout(g.d, g.roww);
   const int d = L.d, dd = d * d, ld = L.ld, tsz = d * ld, gs = gen_vec_stride<T>(d), lane = threadIdx.x & 31;
   T* W = sc.take(L.msz); T* Gt = sc.take(L.msz);
-  T* vals = sc.take(4 * d); T* mpv = sc.take(d); T* rinv = sc.take(d); T* scr16 = sc.take(16);
+  T* vals = sc.take(KJX_ROW_W * d); T* mpv = sc.take(d); T* rinv = sc.take(d); T* scr16 = sc.take(16);
   int* c0n = sc.take_int(d); int* bstart = sc.take_int(d + 1);
   KJX_GEN_VEC(e, 2 * L.msz) W[e] = T(0);
   fetch_c0n<T>(g, c0n);                                      // block structure of A: first rows of the diagonal blocks
@@ -1318,14 +1344,14 @@ __global__ void __launch_bounds__(KJX_GEN_GAIN_THREADS, 3) generic_gain_kernel(c
     const T* mf = g.filt_mean_in + n * (int64_t)d;
     tile_map<T>(d, [&](int i, int j) { return Pf[i * d + j] - (T)Pinf[i * d + j]; }, [&](int i, int j, T v) { W[i * ld + j] = v; });
     __syncthreads();
-    rows_left<T, T>(L, vals, c0n, W, ld, nullptr, 0, Gt);                           // Gt <- A (Pf - Pinf)
-    rows_matvec<T>(d, vals, c0n, mf, mpv);                                          // A mf                      (:352)
+    rows_left_w<T, T, RW>(L, vals, c0n, W, ld, nullptr, 0, Gt);                     // Gt <- A (Pf - Pinf)
+    rows_matvec<T>(L, vals, c0n, mf, mpv);                                          // A mf                      (:352)
     __syncthreads();
-    rows_right_add<T, double>(L, vals, c0n, Gt, Pinf, d, W);                        // W <- P_pred = . A^T + Pinf   (:354)
+    rows_right_add_w<T, double, RW>(L, vals, c0n, Gt, Pinf, d, W, nullptr, T(1));   // W <- P_pred = . A^T + Pinf   (:354)
     __syncthreads();
     load_dense<T>(L, Pf, Gt);
     __syncthreads();
-    rows_left_inplace<T>(L, vals, c0n, bstart, nblk, Gt);                           // Gt <- A Pf                  (:353)
+    rows_left_inplace_w<T, RW>(L, vals, c0n, bstart, nblk, Gt);                     // Gt <- A Pf                  (:353)
     __syncthreads();
     // utils.py:29; Gt <- Z = L^-1 A Pf.  Shared-memory build (d <= 64): the register-panel factorisation (64 rows)
     if constexpr (!GS) { chol_panel8<T>(L, W, rinv); tri_forward<T>(L, W, rinv, Gt, d); }
@@ -1381,7 +1407,7 @@ __global__ void __launch_bounds__(KJX_GEN_THREADS) generic_smoother_kernel(const
   // GS: the working set lives in per-CTA global scratch (d > 64); otherwise in shared memory — a compile-time choice so
   // that the shared-memory build addresses its tiles with LDS / STS and 32-bit offsets instead of generic 64-bit pointers
   SmemCarver<T> sc(GS ? g.gscratch + (size_t)blockIdx.x * g.gscratch_stride : smem_raw);
-  const GenLayout L = gen_layout(g.d);
+  const GenLayout L = gen_layout(g.d, g.roww);
   const int d = L.d, dd = d * d, ld = L.ld, tsz = d * ld, gs = gen_vec_stride<T>(d), lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   T* Ps = sc.take(L.msz); T* T1 = sc.take(L.msz);
   T* GtS[2]; T* LcS[2]; T* gvS[2];

@@ -254,7 +254,7 @@ template <typename T>
 __device__ __forceinline__ void multi_transition(const DiscArgs& da, int d, T dt, T (&A)[KJX_MULTI_DMAX][KJX_MULTI_DMAX]) {
   for (int i = 0; i < d; ++i) {
     for (int j = 0; j < d; ++j) A[i][j] = T(0);
-    int c0, nnz; T v[4] = {T(0), T(0), T(0), T(0)};
+    int c0, nnz; T v[KJX_ROW_W] = {};
     transition_row<T>(da, i, dt, c0, nnz, v);
     for (int q = 0; q < nnz; ++q) A[i][c0 + q] = v[q];
   }

@@ -43,7 +43,7 @@ constexpr int KJX_SAMPLE_THREADS = 128;
 constexpr int KJX_SAMPLE_MAXS = 64;       // samples per launch (the step's normals live in shared memory)
 
 inline size_t sample_noise_smem(int d, int S) {
-  return (size_t)(2 * d * d + 4 * d + d + (size_t)d * S) * sizeof(double) + (size_t)d * sizeof(int) + 64;
+  return (size_t)(2 * d * d + KJX_ROW_W * d + d + (size_t)d * S) * sizeof(double) + (size_t)d * sizeof(int) + 64;
 }
 
 // W: [N + 1][d][S].  slot 0: chol(Pinf) eps; slot k + 1: chol(Pinf - A_k Pinf A_k^T + 1e-6 I) eps.
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(KJX_SAMPLE_THREADS) sample_noise_kernel(const 
   double* Q = reinterpret_cast<double*>(smem_raw);
   double* X = Q + d * d;
   double* vals = X + d * d;
-  double* rinv = vals + 4 * d;
+  double* rinv = vals + KJX_ROW_W * d;
   double* eps = rinv + d;
   int* c0n = reinterpret_cast<int*>(eps + (size_t)d * S);
   for (int64_t slot = blockIdx.x; slot <= N; slot += gridDim.x) {
@@ -64,18 +64,18 @@ __global__ void __launch_bounds__(KJX_SAMPLE_THREADS) sample_noise_kernel(const 
     } else {
       const double h = dt[slot - 1];
       for (int r = threadIdx.x; r < d; r += blockDim.x) {
-        int c0, nnz; double v[4] = {0.0, 0.0, 0.0, 0.0};
+        int c0, nnz; double v[KJX_ROW_W] = {};
         transition_row<double>(da, r, h, c0, nnz, v);
         c0n[r] = c0 | (nnz << 24);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) vals[r * 4 + q] = v[q];
+        for (int q = 0; q < KJX_ROW_W; ++q) vals[r * KJX_ROW_W + q] = v[q];
       }
       __syncthreads();
       for (int e = threadIdx.x; e < d * d; e += blockDim.x) {          // X = A Pinf
         const int i = e / d, j = e - i * d;
         const int c0 = c0n[i] & 0xffffff, nn = c0n[i] >> 24;
         double s = 0.0;
-        for (int q = 0; q < nn; ++q) s += vals[i * 4 + q] * Pinf[(c0 + q) * d + j];
+        for (int q = 0; q < nn; ++q) s += vals[i * KJX_ROW_W + q] * Pinf[(c0 + q) * d + j];
         X[e] = s;
       }
       __syncthreads();
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(KJX_SAMPLE_THREADS) sample_noise_kernel(const 
         const int i = e / d, j = e - i * d;
         const int c0 = c0n[j] & 0xffffff, nn = c0n[j] >> 24;
         double s = 0.0;
-        for (int q = 0; q < nn; ++q) s += X[i * d + c0 + q] * vals[j * 4 + q];
+        for (int q = 0; q < nn; ++q) s += X[i * d + c0 + q] * vals[j * KJX_ROW_W + q];
         Q[e] = Pinf[e] - s + ((i == j) ? 1e-6 : 0.0);
       }
     }
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(KJX_SAMPLE_THREADS) sample_path_kernel(const D
     const double* Wk = W + (size_t)(k + 1) * d * S;
     double acc = 0.0;
     for (int i = lane; i < d; i += 32) {
-      int c0, nnz; double v[4] = {0.0, 0.0, 0.0, 0.0};
+      int c0, nnz; double v[KJX_ROW_W] = {};
       transition_row<double>(da, i, h, c0, nnz, v);
       double x = Wk[(size_t)i * S + s];
       for (int q = 0; q < nnz; ++q) x += v[q] * m[c0 + q];

@@ -417,6 +417,44 @@ class SubbandMatern32(Prior):
         return [(_lib.BLOCK_QP_MATERN32, 1, float(np.sqrt(3.0) / theta[1]), float(theta[2]))]
 
 
+class SubbandMatern52(Prior):
+    """priors.py:605-721 (product of Cosine and Matern-5/2): its transition is the 6 x 6 block kind — the Matern-5/2
+    polynomial block times a rotation of every (cos, sin) pair."""
+    state_dim = 6
+
+    def __init__(self, variance=1.0, lengthscale=1.0, radial_frequency=1.0):
+        super().__init__(hyp=[variance, lengthscale, radial_frequency])
+        self.name = 'Subband Matern-5/2'
+
+    def kernel_to_state_space(self, hyperparams=None):
+        var, ell, omega = self._theta(hyperparams)
+        lam = 5.0 ** 0.5 / ell
+        F_mat = np.array([[0.0, 1.0, 0.0], [0.0, 0.0, 1.0], [-lam ** 3.0, -3.0 * lam ** 2.0, -3.0 * lam]])
+        F = np.kron(F_mat, np.eye(2)) + np.kron(np.eye(3), np.array([[0.0, -omega], [omega, 0.0]]))
+        L = np.kron(np.array([[0.0], [0.0], [1.0]]), np.eye(2))
+        Qc = np.kron(np.eye(2), np.array([[var * 400.0 * 5.0 ** 0.5 / 3.0 / ell ** 5.0]]))
+        kappa = 5.0 / 3.0 * var / ell ** 2.0
+        Pinf_mat = np.array([[var, 0.0, -kappa], [0.0, kappa, 0.0], [-kappa, 0.0, 25.0 * var / ell ** 4.0]])
+        return F, L, Qc, self.measurement_model(), np.kron(Pinf_mat, np.eye(2))
+
+    def measurement_model(self, r=None, hyperparams=None):
+        return np.kron(np.array([[1.0, 0.0, 0.0]]), np.array([[1.0, 0.0]]))
+
+    def state_transition(self, dt, hyperparams=None):
+        theta = self._theta(hyperparams)
+        lam = 5.0 ** 0.5 / theta[1]
+        R = _rotation(dt, theta[2])
+        dl = dt * lam
+        return np.exp(-dl) * np.block([
+            [0.5 * (2. + dl * (2. + dl)) * R, dt * (1. + dl) * R, 0.5 * dt ** 2 * R],
+            [-0.5 * dt ** 2 * lam ** 3 * R, (1. + dl * (1. - dl)) * R, -0.5 * dt * (-2. + dl) * R],
+            [0.5 * dt * lam ** 3 * (-2. + dl) * R, dt * lam ** 2 * (-3. + dl) * R, 0.5 * (2. + dl * (-4. + dl)) * R]])
+
+    def blocks(self, hyperparams=None):
+        theta = self._theta(hyperparams)
+        return [(_lib.BLOCK_SUBBAND_MATERN52, 1, float(np.sqrt(5.0) / theta[1]), float(theta[2]))]
+
+
 class Sum(object):
     """priors.py:1347-1414."""
     def __init__(self, components):

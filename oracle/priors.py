@@ -282,6 +282,31 @@ class SubbandMatern32(object):
                                              [-dt * lam ** 2 * R, (1. - dt * lam) * R]])  # :598-601
 
 
+class SubbandMatern52(object):
+    """priors.py:605-721: kron(Matern-5/2, Cosine)."""
+    state_dim = 6
+
+    def __init__(self, variance=1.0, lengthscale=1.0, radial_frequency=1.0):
+        self.hyp = np.array([variance, lengthscale, radial_frequency], dtype=float)
+
+    def kernel_to_state_space(self):
+        var, ell = self.hyp[0], self.hyp[1]
+        kappa = 5.0 / 3.0 * var / ell ** 2.0                                              # :667
+        Pinf_mat = np.array([[var, 0.0, -kappa], [0.0, kappa, 0.0], [-kappa, 0.0, 25.0 * var / ell ** 4.0]])
+        return self.measurement_model(), np.kron(Pinf_mat, np.eye(2))                     # :685
+
+    def measurement_model(self, r=None):
+        return np.kron(np.array([[1.0, 0.0, 0.0]]), np.array([[1.0, 0.0]]))               # :690-693
+
+    def state_transition(self, dt):
+        lam = 5.0 ** 0.5 / self.hyp[1]                                                    # :706
+        R = rotation_matrix(dt, self.hyp[2])
+        return np.exp(-dt * lam) * np.block([                                             # :708-712
+            [0.5 * (2. + dt * lam * (2. + dt * lam)) * R, dt * (1. + dt * lam) * R, 0.5 * dt ** 2 * R],
+            [-0.5 * dt ** 2 * lam ** 3 * R, (1. + dt * lam * (1. - dt * lam)) * R, -0.5 * dt * (-2. + dt * lam) * R],
+            [0.5 * dt * lam ** 3 * (-2. + dt * lam) * R, dt * lam ** 2 * (-3. + dt * lam) * R, 0.5 * (2. + dt * lam * (-4. + dt * lam)) * R]])
+
+
 class Sum(object):
     """priors.py:1347-1414: block-diagonal stacking, H concatenated."""
     def __init__(self, components):

@@ -23,6 +23,7 @@ PER_3 = ("Periodic", dict(variance=0.8, lengthscale=1.5, period=3.0))
 QPM12 = ("QuasiPeriodicMatern12", dict(variance=1.0, lengthscale_periodic=1.5, period=20., lengthscale_matern=40.))
 SUB12 = ("SubbandMatern12", dict(variance=0.7, lengthscale=3.0, radial_frequency=1.3))
 SUB32 = ("SubbandMatern32", dict(variance=1.1, lengthscale=4.0, radial_frequency=0.4))
+SUB52 = ("SubbandMatern52", dict(variance=0.9, lengthscale=3.0, radial_frequency=0.7))
 SP52 = ("SpatialMatern52", dict(variance=0.4, lengthscale=0.6))
 SP32 = ("SpatialMatern32", dict(variance=0.4, lengthscale=0.8, z=[-3.0 + 0.5 * i for i in range(13)]))
 M52FV = ("Matern52FixedVar", dict(variance=1.2, lengthscale=4.0))
@@ -79,6 +80,10 @@ CASES = {
     "zoo_regression_sum_subbands_m12_gauss_ep1": ("regression", ("Sum", [SUB12, SUB32, M12_12]), ("Gaussian", dict(variance=0.5)),
                                                   ("EP", dict(power=1.0)), 2, None),
     "zoo_coal333_subband32_poisson_eks": ("coal333", SUB32, POISSON, ("EKS", dict(damping=0.8)), 3, None),
+    # the 6 x 6 block kind (priors.py:605-721), on its own and next to narrower blocks
+    "zoo_coal333_subband52_poisson_pep05": ("coal333", SUB52, POISSON, ("EP", dict(power=0.5)), 3, None),
+    "zoo_regression_sum_subband52_m32_gauss_vi": ("regression", ("Sum", [SUB52, M32_154, SUB32]), ("Gaussian", dict(variance=0.5)),
+                                                  ("VI", dict()), 2, None),
     "zoo_banana200_spatial52_probit_ep08": ("banana200", SP52, PROBIT, ("EP", dict(power=0.8)), 2, None),
     "zoo_banana200_spatial32_probit_vi": ("banana200", SP32, PROBIT, ("VI", dict()), 2, None),
     # multi-latent (func_dim = 2): Independent prior + HeteroscedasticNoise, the mcycle model of

@@ -62,7 +62,8 @@ def test_every_prior_gives_a_valid_model_and_workspace():
     from kalman_jax_b200.sde_gp import _Model
     zoo = [P.Matern12(1.0, 2.0), P.Matern32(1.0, 2.0), P.Matern52(1.0, 2.0), P.Matern72(1.0, 2.0), P.Cosine([0.5]),
            P.Periodic(1.0, 1.0, 3.0), P.QuasiPeriodicMatern12(1.0, 1.0, 3.0, 9.0), P.QuasiPeriodicMatern32(1.0, 1.0, 3.0, 9.0),
-           P.SubbandMatern12(1.0, 2.0, 0.7), P.SubbandMatern32(1.0, 2.0, 0.7),
+           P.SubbandMatern12(1.0, 2.0, 0.7), P.SubbandMatern32(1.0, 2.0, 0.7), P.SubbandMatern52(1.0, 2.0, 0.7),
+           P.Sum([P.SubbandMatern52(1.0, 2.0, 0.7), P.Matern32(1.0, 2.0)]),
            P.Sum([P.Matern52(1.0, 2.0), P.QuasiPeriodicMatern32(1.0, 1.0, 3.0, 9.0), P.Matern12(0.5, 1.0)]),
            P.SpatioTemporalMatern52(1.0, 1.0, 0.5), P.SpatialMatern52(1.0, 0.7), P.SpatialMatern32(1.0, 0.7)]
     lib = _lib.lib()
@@ -92,7 +93,7 @@ def test_every_prior_gives_a_valid_model_and_workspace():
 
 
 def _lib_block_size(kind):
-    return {1: 2, 2: 3, 3: 4, 4: 1, 5: 2, 6: 4}[kind]
+    return {1: 2, 2: 3, 3: 4, 4: 1, 5: 2, 6: 4, 7: 6}[kind]
 
 
 def test_product_never_imports_the_oracle():

@@ -432,13 +432,18 @@ def _disc_case(name):
                               P.QuasiPeriodicMatern32(variance=1., lengthscale_periodic=2., period=365., lengthscale_matern=1.5e4),
                               P.QuasiPeriodicMatern32(variance=1., lengthscale_periodic=2., period=7., lengthscale_matern=30 * 365.)])
         return mk(kjx.priors), mk(oracle.priors)
+    if name == "sub52":
+        return kjx.priors.SubbandMatern52(0.9, 3.0, 0.7), oracle.priors.SubbandMatern52(0.9, 3.0, 0.7)
+    if name == "sum_sub52":
+        mk = lambda P: P.Sum([P.Matern32(1.5, 4.0), P.SubbandMatern52(0.9, 3.0, 0.7), P.Matern12(0.5, 1.0)])  # noqa: E731
+        return mk(kjx.priors), mk(oracle.priors)
     if name == "st":
         z = np.linspace(-3, 3, 12)
         return (kjx.priors.SpatioTemporalMatern52(0.3, 0.3, 0.3, z=z), oracle.priors.SpatioTemporalMatern52(0.3, 0.3, 0.3, z=z))
     raise KeyError(name)
 
 
-@pytest.mark.parametrize("name", ["m32", "m52", "qp", "sum59", "st"])
+@pytest.mark.parametrize("name", ["m32", "m52", "qp", "sum59", "st", "sub52", "sum_sub52"])
 def test_discretise_kernel_vs_oracle(name):
     """kjx_discretise: A(dt) = expm(F dt) closed forms and Q = Pinf - A Pinf A^T for varying dt."""
     import ctypes as C
@@ -679,7 +684,7 @@ def _state_space_cov(prior, t):
     return K
 
 
-@pytest.mark.parametrize("prior_name", ["Matern32", "Sum", "Sum_d59"])
+@pytest.mark.parametrize("prior_name", ["Matern32", "Sum", "Sum_d59", "Sum_sub52"])
 def test_prior_sample_matches_the_prior_covariance(prior_name):
     """SDEGP.prior_sample (sde_gp.py:386-417) on the GPU: the draws' sample covariance against the prior covariance
     computed from the oracle's state-space matrices (parity for sampling is in distribution); same seed -> same draws."""
@@ -689,6 +694,8 @@ def test_prior_sample_matches_the_prior_covariance(prior_name):
     y = np.zeros_like(t)
     if prior_name == "Matern32":
         mk = lambda mod: mod.priors.Matern32(1.5, 2.0)  # noqa: E731
+    elif prior_name == "Sum_sub52":      # six-wide rows of A(dt)
+        mk = lambda mod: mod.priors.Sum([mod.priors.SubbandMatern52(0.9, 3.0, 0.7), mod.priors.Matern32(1.5, 2.0)])  # noqa: E731
     elif prior_name == "Sum_d59":        # d > 32: the noise factorisation spans several warps (barrier after every column)
         mk = lambda mod: mod.priors.Sum([mod.priors.Matern52(variance=2., lengthscale=3.),  # noqa: E731
                                          mod.priors.QuasiPeriodicMatern32(variance=1., lengthscale_periodic=2., period=4., lengthscale_matern=20.),

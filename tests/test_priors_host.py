@@ -18,11 +18,12 @@ ZOO = [
     ("QuasiPeriodicMatern32", dict(variance=1.2, lengthscale_periodic=1.5, period=20.0, lengthscale_matern=40.0)),
     ("SubbandMatern12", dict(variance=0.7, lengthscale=3.0, radial_frequency=1.3)),
     ("SubbandMatern32", dict(variance=1.1, lengthscale=4.0, radial_frequency=0.4)),
+    ("SubbandMatern52", dict(variance=0.9, lengthscale=3.0, radial_frequency=0.7)),
     ("SpatioTemporalMatern52", dict(variance=0.5, lengthscale_time=0.8, lengthscale_space=0.5, z=Z)),
     ("SpatialMatern52", dict(variance=0.4, lengthscale=0.6, z=Z)),
     ("SpatialMatern32", dict(variance=0.4, lengthscale=0.8, z=Z)),
 ]
-BLOCK_SIZE = {1: 2, 2: 3, 3: 4, 4: 1, 5: 2, 6: 4}
+BLOCK_SIZE = {1: 2, 2: 3, 3: 4, 4: 1, 5: 2, 6: 4, 7: 6}
 
 
 def _same(a, b):
