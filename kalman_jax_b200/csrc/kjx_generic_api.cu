@@ -166,7 +166,10 @@ template <typename T> int generic_launch_filter(const GenArgs<T>& g, T* llpart, 
 }
 template <typename T> int generic_launch_smoother(const GenArgs<T>& g, T* gains, cudaStream_t st) {
   // 1. all RTS gains and the affine terms of the recursion, parallel over time (they depend on the filtered moments only)
-  const unsigned grid = (unsigned)std::min<int64_t>(g.N, KJX_GEN_GAIN_GRID);
+  static const int grid_knob = [] { const char* e = getenv("KJX_GEN_GAIN_CTAS"); return e ? atoi(e) : 0; }();   // tuning knob, read once
+  int64_t ctas = KJX_GEN_GAIN_GRID;
+  if (grid_knob >= 1) ctas = std::min<int64_t>(grid_knob, KJX_GEN_GAIN_GRID);
+  const unsigned grid = (unsigned)std::min<int64_t>(g.N, ctas);
 #define KJX_GAIN_LAUNCH(RW)                                                                                              \
   do {                                                                                                                  \
     if (g.gscratch) {                                                                                                   \

@@ -210,12 +210,13 @@ class SDEGP(object):
         uses_r = hasattr(self.prior, "spatial_weights") and not self.prior.fixed_grid      # only then H depends on r
         key = self._model_key(params, r if uses_r else None)
         hit = self._model_cache.get(key)
-        if hit is not None and (not uses_r or hit[1] is r or np.array_equal(hit[1], r, equal_nan=True)):
+        if hit is not None and (not uses_r or np.array_equal(hit[1], r, equal_nan=True)):
             return hit[0]
         model = self._build_model(params, r)
         if len(self._model_cache) >= 32:
             self._model_cache.pop(next(iter(self._model_cache)))
-        self._model_cache[key] = (model, r)
+        # (a private copy of r: the caller may overwrite its array in place between calls)
+        self._model_cache[key] = (model, np.array(r, dtype=np.float64, copy=True) if uses_r else None)
         return model
 
     def _model_key(self, params, r):
