@@ -568,7 +568,7 @@ def main():
     traffic = None                                          # dram bytes per launch from the committed ncu --set full capture
     try:
         if world == 1 and args.log2n == 24:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")))["dram_bytes_per_launch"]
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r02.json")))["dram_bytes_per_launch"]
             traffic = tr[("fused_filter_kernel", "fused_smoother_kernel")[dom - 1]]
     except Exception:
         pass
