@@ -49,7 +49,7 @@ typedef struct CUstream_st* kjx_stream_t; /* == cudaStream_t */
 enum kjx_status {
   KJX_OK = 0,
   KJX_ERR_INVALID_ARG = -1,   /* null pointer, N < 0, bad enum, misaligned pointer ...          */
-  KJX_ERR_UNSUPPORTED = -2,   /* valid request this build has no kernel for (e.g. f > 1)        */
+  KJX_ERR_UNSUPPORTED = -2,   /* valid request this build has no kernel for (e.g. f > 2)        */
   KJX_ERR_WORKSPACE = -3,     /* ws_bytes smaller than kjx_workspace_bytes()                    */
   KJX_ERR_CUDA = -4           /* a CUDA runtime call / kernel launch failed                     */
 };
@@ -82,7 +82,7 @@ enum kjx_likelihood {
   KJX_LIK_BERNOULLI_LOGIT = 3,   /* likelihoods.py:407-518, link 'logit'                          */
   KJX_LIK_POISSON_EXP = 4,       /* likelihoods.py:551-644, link 'exp'                            */
   KJX_LIK_POISSON_LOGISTIC = 5,  /* likelihoods.py:551-644, link 'logistic' (softplus)            */
-  KJX_LIK_HETERO_SOFTPLUS = 6,   /* HeteroscedasticNoise, likelihoods.py:647-728, link 'softplus'; func_dim = 2 */
+  KJX_LIK_HETERO_SOFTPLUS = 6,   /* HeteroscedasticNoise, likelihoods.py:647-850, link 'softplus'; func_dim = 2 */
   KJX_LIK_HETERO_EXP = 7         /* HeteroscedasticNoise, link 'exp'; func_dim = 2                 */
 };
 
